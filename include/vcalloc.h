@@ -1,0 +1,333 @@
+/*
+ * vcalloc.h — C ABI of libvcalloc.so: the B200-native replacement for Volcano's
+ * per-cycle `allocate` hot path.
+ *
+ * Every entry point below is what a cgo shim inside the reference would bind
+ * (INTEGRATION.md shows the shim).  Citations are into /root/reference/pkg/scheduler
+ * unless a full path is given.
+ *
+ *   reference interface replaced                         entry point here
+ *   ---------------------------------------------------  ---------------------------
+ *   framework.OpenSession  (framework/framework.go:34,   vc_snapshot_create +
+ *     framework/session.go:166-282: Snapshot -> Session)   vc_snapshot_upload
+ *   Action.Execute for "allocate"                        vc_allocate_run
+ *     (actions/allocate/allocate.go:122-140, :283-348,
+ *      :558-694, :709-824; framework/interface.go:41-51)
+ *   util.PredicateNodes + util.PrioritizeNodes for one    vc_score_matrix
+ *     task over []*NodeInfo, i.e. what a PredicateFn /
+ *     BatchNodeOrderFn / BestNodeFn plugin would serve
+ *     (util/predicate_helper.go:43-140,
+ *      util/scheduler_helper.go:76-138,191-206;
+ *      framework/session_plugins.go:70-108)
+ *   Statement operations the shim replays through          vc_result_* accessors
+ *     Statement.Allocate/Pipeline/Commit/Discard
+ *     (framework/statement.go:146-412)
+ *   CloseSession (framework/framework.go:61-69)           vc_result_free / vc_snapshot_destroy
+ *
+ * Conventions: plain C types only; every pointer in an input struct is HOST memory
+ * owned by the caller and is copied during the call (pinned staging inside); return 0 on
+ * success or a negative VC_E* code, with vc_last_error() giving the message for the
+ * calling thread; no callbacks; results are library-owned until vc_result_free.
+ * There is NO CPU fallback: without a CUDA device vc_init fails with VC_ENODEV.
+ *
+ * Layout conventions ("SoA"): resource vectors are dimension-major double arrays,
+ * X[d * count + i] for dimension d of entity i.  Dimension 0 = cpu (milli), 1 = memory
+ * (bytes), 2.. = scalar resources sorted by name (milli units, except "pods" = count) —
+ * the units of api.NewResource (api/resource_info.go:86-127).  All values are
+ * integer-valued doubles exactly as in the reference (Appendix A-2 of SURVEY.md).
+ */
+#ifndef VCALLOC_H
+#define VCALLOC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VC_ABI_VERSION 1
+#define VC_MAX_DIMS 16   /* R  */
+#define VC_MAX_KDIMS 4   /* dims seen by the upstream kube-scheduler scorers (cpu, memory, nvidia.com/gpu, ...) */
+#define VC_MAX_WORDS 4   /* 64-bit words per label / taint bitset */
+#define VC_MAX_TERMS 4   /* required-affinity terms and preferred-affinity terms per class */
+#define VC_MAX_PLUGINS 16
+#define VC_MAX_JOB_ROLES 64
+
+/* error codes */
+#define VC_OK 0
+#define VC_EINVAL (-1)       /* malformed input (message in vc_last_error) */
+#define VC_ENODEV (-2)       /* no CUDA device / extension unusable: the product has no CPU path */
+#define VC_ECUDA (-3)        /* CUDA runtime error */
+#define VC_EUNSUPPORTED (-4) /* snapshot uses a feature outside the hot-path scope */
+#define VC_ENOMEM (-5)
+
+/* ---- sizes ------------------------------------------------------------------------ */
+typedef struct vc_dims {
+  int32_t n_nodes;     /* N: len(ssn.NodeList), NodeList order (framework/session.go:237) */
+  int32_t n_tasks;     /* T: Pending, non-BestEffort, non-gated tasks (allocate.go:255-271) */
+  int32_t n_jobs;      /* J: len(ssn.Jobs) */
+  int32_t n_queues;    /* Q: len(ssn.Queues) */
+  int32_t n_classes;   /* C: distinct (nodeSelector, affinity, tolerations, revocable) tuples */
+  int32_t n_roles;     /* total rows of the per-job role tables (vc_jobs.role_off[J]) */
+  int32_t n_dims;      /* R */
+  int32_t n_kdims;     /* K <= VC_MAX_KDIMS; kdim 0 = cpu, 1 = memory */
+  int32_t label_words; /* Wl */
+  int32_t taint_words; /* Wt */
+  int32_t n_zones;     /* tdm revocable zones */
+  int32_t pods_dim;    /* index of the "pods" scalar in [2,R) or -1 (api/resource_info.go:219) */
+} vc_dims;
+
+/* ---- api.NodeInfo (api/node_info.go:51-100) ---------------------------------------- */
+#define VC_NODE_UNSCHEDULABLE 1u /* node.Spec.Unschedulable (upstream NodeUnschedulable filter) */
+typedef struct vc_nodes {
+  const double *allocatable;           /* [R][N] NodeInfo.Allocatable */
+  const double *idle;                  /* [R][N] NodeInfo.Idle */
+  const double *used;                  /* [R][N] NodeInfo.Used */
+  const double *releasing;             /* [R][N] NodeInfo.Releasing */
+  const double *pipelined;             /* [R][N] NodeInfo.Pipelined */
+  const double *k8s_allocatable;       /* [K][N] k8s NodeInfo.Allocatable in upstream units (cpu milli, memory
+                                          bytes, extended resources as plain counts) */
+  const double *k8s_requested;         /* [K][N] k8s NodeInfo.Requested of ssn.NodeMap (framework/util.go:226-234) */
+  const double *k8s_nonzero_requested; /* [K][N] k8s NodeInfo.NonZeroRequested (rows >= 2 unused) */
+  const int32_t *max_tasks;            /* [N] Allocatable.MaxTaskNum (api/resource_info.go:95-97) */
+  const int32_t *pod_count;            /* [N] len(k8s NodeInfo.Pods) (plugins/predicates/predicates.go:662) */
+  const uint64_t *label_bits;          /* [Wl][N] bit b: node satisfies label requirement b */
+  const uint64_t *taint_hard;          /* [Wt][N] NoSchedule / NoExecute taints */
+  const uint64_t *taint_soft;          /* [Wt][N] PreferNoSchedule taints */
+  const uint32_t *flags;               /* [N] VC_NODE_* */
+  const int32_t *revocable_zone;       /* [N] zone id or -1 (NodeInfo.RevocableZone) */
+  const uint8_t *zone_active;          /* [Z] tdm availableRevocableZone() evaluated by the host once per cycle
+                                          (plugins/tdm/tdm.go:118-137 uses time.Now()) */
+} vc_nodes;
+
+/* ---- api.TaskInfo (api/job_info.go:117-154) ---------------------------------------- */
+typedef struct vc_tasks {
+  const double *resreq;          /* [R][T] Resreq (== InitResreq, api/job_info.go:185-186) */
+  const uint32_t *req_has;       /* [T] bit d (d>=2): scalar d is a key of Resreq.ScalarResources */
+  const double *k8s_req;         /* [K][T] pod request as upstream computes it (Requested flavour) */
+  const double *k8s_nonzero_req; /* [K][T] NonZero flavour (cpu 100m / memory 200Mi defaults) */
+  const int32_t *job;            /* [T] job index */
+  const int32_t *klass;          /* [T] class index */
+  const int32_t *role;           /* [T] row in the job's role tables (TaskRole == "" has its own row,
+                                    flagged VC_ROLE_EMPTY_NAME) */
+  const int32_t *priority;       /* [T] TaskInfo.Priority */
+  const int64_t *pod_index;      /* [T] numeric suffix of the pod name or -1
+                                    (pkg/controllers/job/helpers/helpers.go:44-52) */
+  const int64_t *creation_ts;    /* [T] Pod.CreationTimestamp */
+  const uint32_t *uid_rank;      /* [T] rank of TaskInfo.UID in byte-string order */
+} vc_tasks;
+
+/* ---- scheduling constraints shared by tasks ("class") ------------------------------ */
+#define VC_CLASS_REVOCABLE 1u             /* len(task.RevocableZone) > 0 */
+#define VC_CLASS_TOLERATES_UNSCHEDULABLE 2u
+typedef struct vc_classes {
+  const uint64_t *selector;     /* [C][Wl] nodeSelector: all bits required */
+  const int32_t *n_affinity;    /* [C] number of required nodeAffinity terms (0 = none) */
+  const uint64_t *affinity;     /* [C][VC_MAX_TERMS][Wl] OR of AND-masks */
+  const uint64_t *tolerated_hard; /* [C][Wt] */
+  const uint64_t *tolerated_soft; /* [C][Wt] tolerations with effect PreferNoSchedule or empty */
+  const int32_t *n_preferred;   /* [C] preferred nodeAffinity terms */
+  const uint64_t *preferred;    /* [C][VC_MAX_TERMS][Wl] */
+  const int32_t *preferred_weight; /* [C][VC_MAX_TERMS] */
+  const uint32_t *flags;        /* [C] VC_CLASS_* */
+} vc_classes;
+
+/* ---- api.JobInfo (api/job_info.go:341-386) ----------------------------------------- */
+#define VC_JOB_PENDING_PHASE 1u /* JobInfo.IsPending() (api/job_info.go:1181-1185) */
+#define VC_JOB_PREEMPTABLE 2u   /* JobInfo.Preemptable (tdm jobOrderFn) */
+#define VC_ROLE_EMPTY_NAME 1u    /* TaskRole == "": no predicate-error cache (util/predicate_helper.go:47-52),
+                                   TaskHasFitErrors is always false (api/job_info.go:894-902) */
+#define VC_ROLE_IN_MIN_MAP 2u    /* role is a key of JobInfo.TaskMinAvailable */
+#define VC_JOB_UNSUPPORTED 4u   /* hard topology / subjob policy: run returns VC_EUNSUPPORTED */
+typedef struct vc_jobs {
+  const int32_t *queue;            /* [J] queue index or -1 when ssn.Queues lacks it (allocate.go:171) */
+  const int32_t *min_available;    /* [J] JobInfo.MinAvailable */
+  const int32_t *priority;         /* [J] JobInfo.Priority */
+  const int64_t *creation_ts;      /* [J] */
+  const uint32_t *uid_rank;        /* [J] rank of JobID string */
+  const uint32_t *flags;           /* [J] VC_JOB_* */
+  const int32_t *n_tasks_total;    /* [J] len(ji.Tasks), every status */
+  const int32_t *ready_num;        /* [J] ReadyTaskNum() at open (api/job_info.go:844-853) */
+  const int32_t *waiting_num;      /* [J] WaitingTaskNum() at open */
+  const int32_t *pending_besteffort; /* [J] PendingBestEffortTaskNum() */
+  const int32_t *valid_num;        /* [J] ValidTaskNum() (api/job_info.go:1100-1113) */
+  const int32_t *task_min_total;   /* [J] TaskMinAvailableTotal */
+  const int32_t *role_off;         /* [J+1] rows [role_off[j], role_off[j+1]) of the role tables */
+  const double *allocated;         /* [R][J] sum Resreq over AllocatedStatus tasks at open (drf.go:196-203) */
+  /* role tables, one row per (job, TaskRole) incl. roles that only appear in TaskMinAvailable */
+  const int32_t *role_min;         /* [NR] TaskMinAvailable[role] (0 if absent) */
+  const int32_t *role_occupied;    /* [NR] getJobAllocatedRoles() at open (api/job_info.go:969-990) */
+  const int32_t *role_pipelined;   /* [NR] tasks of the role in Pipelined status at open */
+  const int32_t *role_pending_other; /* [NR] Pending tasks of the role NOT in vc_tasks (best-effort, gated) */
+  const int32_t *role_valid;       /* [NR] CheckTaskValid's `actual` at open (api/job_info.go:993-1019) */
+  const uint32_t *role_flags;      /* [NR] VC_ROLE_* */
+} vc_jobs;
+
+/* ---- api.QueueInfo (api/queue_info.go:36-51) + proportion inputs ------------------- */
+#define VC_QUEUE_OPEN 1u
+#define VC_RES_HAS_ANY 0x80000000u /* in a *_has word: the ResourceList itself is non-empty */
+typedef struct vc_queues {
+  const int32_t *weight;        /* [Q] */
+  const int32_t *priority;      /* [Q] Queue.Spec.Priority */
+  const int64_t *creation_ts;   /* [Q] */
+  const uint32_t *uid_rank;     /* [Q] */
+  const uint32_t *flags;        /* [Q] VC_QUEUE_* */
+  const double *capability;     /* [R][Q] Queue.Spec.Capability */
+  const uint32_t *capability_has; /* [Q] bit d: dim d present; VC_RES_HAS_ANY: len(Capability) != 0 */
+  const double *guarantee;      /* [R][Q] Queue.Spec.Guarantee.Resource */
+  const uint32_t *guarantee_has;/* [Q] */
+  const double *allocated;      /* [R][Q] proportion attr.allocated at open (proportion.go:143-149) */
+  const double *request;        /* [R][Q] proportion attr.request at open (allocated + ALL Pending tasks) */
+  const uint32_t *request_has;  /* [Q] scalar keys present in attr.request */
+  const uint32_t *allocated_has;/* [Q] scalar keys present in attr.allocated */
+} vc_queues;
+
+/* ---- conf.SchedulerConfiguration (conf/scheduler_conf.go:28-107) ------------------- */
+enum vc_plugin {
+  VC_PLUGIN_PRIORITY = 1,
+  VC_PLUGIN_GANG = 2,
+  VC_PLUGIN_DRF = 3,
+  VC_PLUGIN_PROPORTION = 4,
+  VC_PLUGIN_PREDICATES = 5,
+  VC_PLUGIN_NODEORDER = 6,
+  VC_PLUGIN_BINPACK = 7,
+  VC_PLUGIN_TDM = 8,
+  VC_PLUGIN_OTHER = 99 /* conformance, overcommit, ...: no effect on this path */
+};
+/* PluginOption enable flags (conf/scheduler_conf.go:60-107); nil == false unless
+   ApplyPluginConfDefaults ran (plugins/defaults.go:29-55) — the caller resolves that. */
+#define VC_EN_JOB_ORDER 0x001u
+#define VC_EN_JOB_READY 0x002u
+#define VC_EN_JOB_PIPELINED 0x004u
+#define VC_EN_TASK_ORDER 0x008u
+#define VC_EN_QUEUE_ORDER 0x010u
+#define VC_EN_PREDICATE 0x020u
+#define VC_EN_NODE_ORDER 0x040u
+#define VC_EN_BEST_NODE 0x080u
+#define VC_EN_OVERUSED 0x100u
+#define VC_EN_ALLOCATABLE 0x200u
+#define VC_EN_ALL 0x3ffu
+typedef struct vc_plugin_option {
+  int32_t plugin;   /* enum vc_plugin */
+  int32_t tier;     /* 0-based tier index; options are listed in tier, then plugin order */
+  uint32_t enabled; /* VC_EN_* */
+} vc_plugin_option;
+
+/* predicates plugin switches (plugins/predicates/predicates.go:126-151) */
+#define VC_PRED_NODE_AFFINITY 1u
+#define VC_PRED_TAINT_TOLERATION 2u
+typedef struct vc_conf {
+  int32_t n_plugins;
+  vc_plugin_option plugins[VC_MAX_PLUGINS];
+  /* binpack arguments (plugins/binpack/binpack.go:94-158) */
+  int32_t binpack_weight;
+  int32_t binpack_dim_weight[VC_MAX_DIMS]; /* -1: resource not in BinPackingResources */
+  /* nodeorder arguments (plugins/nodeorder/nodeorder.go:131-171) */
+  int32_t w_least, w_most, w_balanced, w_node_affinity, w_taint_toleration;
+  int32_t kdim_dim[VC_MAX_KDIMS]; /* volcano dim index of each k8s-scored dim */
+  /* predicates arguments */
+  uint32_t predicates_enable; /* VC_PRED_* */
+  /* allocate action + server options */
+  int32_t enable_predicate_error_cache; /* allocate.go:107-120, default 1 */
+  int32_t enqueue_action_enabled;       /* conf.EnabledActionMap["enqueue"] (allocate.go:154-164) */
+  int32_t percentage_nodes_to_find;     /* options.go:48-54; 100 = parity mode */
+  int32_t min_nodes_to_find;            /* 100 */
+  int32_t min_percentage_nodes_to_find; /* 5 */
+} vc_conf;
+
+/* ---- results ----------------------------------------------------------------------- */
+#define VC_OP_ALLOCATE 0 /* Statement.Allocate (framework/statement.go:242-302) */
+#define VC_OP_PIPELINE 1 /* Statement.Pipeline (framework/statement.go:146-200) */
+typedef struct vc_decision {
+  int32_t task;
+  int32_t node;
+  int32_t kind;  /* VC_OP_* */
+  int32_t visit; /* index into the visit list */
+  double score;  /* score of the chosen node (0 when it was the only candidate, allocate.go:757) */
+} vc_decision;
+
+#define VC_VISIT_COMMIT 0  /* stmt != nil && JobReady: stmt.Commit() (allocate.go:330-331) */
+#define VC_VISIT_KEEP 1    /* stmt != nil, job only pipelined: operations stay in the session */
+#define VC_VISIT_DISCARD 2 /* stmt.Discard() (allocate.go:692) — its operations are not reported */
+typedef struct vc_visit {
+  int32_t job;
+  int32_t outcome; /* VC_VISIT_* */
+  int32_t first_op;
+  int32_t n_ops;
+} vc_visit;
+
+typedef struct vc_stats {
+  double upload_ms;   /* host->device copies + session-open kernels */
+  double commit_ms;   /* the persistent commit kernel (CUDA events) */
+  double download_ms; /* device->host result copy */
+  double total_ms;
+  int64_t h2d_bytes, d2h_bytes;
+  int32_t kernel_launches;
+  int32_t n_steps;    /* node sweeps executed */
+} vc_stats;
+
+typedef struct vc_snapshot vc_snapshot;
+typedef struct vc_result vc_result;
+
+/* ---- entry points ------------------------------------------------------------------ */
+int vc_abi_version(void);
+const char *vc_last_error(void);
+
+/* Bind the calling process to CUDA device `device` (one process per GPU). */
+int vc_init(int device);
+
+/* Device memory for one scheduling session of the given size. */
+int vc_snapshot_create(const vc_dims *dims, vc_snapshot **out);
+void vc_snapshot_destroy(vc_snapshot *s);
+
+/* Upload the session snapshot (host SoA -> HBM) and run the session-open reductions
+   (ssn.TotalResource, drf shares, proportion deserved, class x node predicate mask). */
+int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nodes, const vc_tasks *tasks,
+                       const vc_classes *classes, const vc_jobs *jobs, const vc_queues *queues,
+                       const vc_conf *conf);
+
+/* Restrict the node axis of this process to [node_begin, node_end) for node-sharded
+   multi-GPU runs; tasks/jobs/queues stay replicated. Default: all nodes. */
+int vc_snapshot_set_shard(vc_snapshot *s, int32_t node_begin, int32_t node_end);
+
+/* The allocate action on the uploaded snapshot: exact sequential greedy assignment. */
+int vc_allocate_run(vc_snapshot *s, vc_result **out);
+
+/* Dense task x node pass on the opening snapshot: feasibility bit (allocate.predicate,
+   allocate.go:816-824), total score (util.PrioritizeNodes) of every feasible pair and
+   per-task best (score, node) under the canonical tie-break (lowest NodeList index).
+   mask_out: device or host? -> HOST buffers, may be NULL to keep results on the device
+   (used by bench to time the kernel alone).
+     mask_out  [T][ceil(N/64)] uint64, bit n of row t
+     score_out [T][N] double (0.0 where infeasible)
+     best_score[T] double, best_node[T] int32 (-1 = no feasible node)          */
+int vc_score_matrix(vc_snapshot *s, uint64_t *mask_out, double *score_out, double *best_score,
+                    int32_t *best_node);
+/* Same pass, outputs stay in HBM; returns the CUDA-event time of the kernel alone. */
+int vc_score_matrix_device(vc_snapshot *s, int repeats, double *kernel_ms_out,
+                           int64_t *algorithmic_bytes_out);
+/* Per-task best (score,node) packed for a MAX all-reduce across node shards:
+   key = orderable(score) << 32 | (0xffffffff - node). Device pointer, T entries. */
+int vc_best_keys_device(vc_snapshot *s, uint64_t **keys_dev_out);
+int vc_best_keys_unpack(vc_snapshot *s, const uint64_t *keys_host, double *best_score,
+                        int32_t *best_node);
+
+/* proportion's per-queue deserved / share after session open (plugins/proportion/
+   proportion.go:197-264), for parity checks: [R][Q] and [Q]. */
+int vc_queue_deserved(vc_snapshot *s, double *deserved_out, double *share_out);
+
+size_t vc_result_num_decisions(const vc_result *r);
+const vc_decision *vc_result_decisions(const vc_result *r);
+size_t vc_result_num_visits(const vc_result *r);
+const vc_visit *vc_result_visits(const vc_result *r);
+/* tasks for which job.NodesFitErrors was recorded (allocate.go:600-607,651) */
+size_t vc_result_num_fit_errors(const vc_result *r);
+const int32_t *vc_result_fit_errors(const vc_result *r);
+const vc_stats *vc_result_stats(const vc_result *r);
+void vc_result_free(vc_result *r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCALLOC_H */

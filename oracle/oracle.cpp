@@ -1,0 +1,1409 @@
+// oracle.cpp — CPU restatement of Volcano's `allocate` hot path.
+//
+// THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  It exists so that the CUDA path can be
+// checked against an independent, straightforward restatement of the reference algorithm.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may load it.  libvcalloc.so never links or calls anything in this directory.
+//
+// Parity status: the reference is Go (go 1.25, k8s.io/kubernetes v1.35.0 un-vendored) and
+// cannot be compiled in this image, so the oracle is pinned against the reference's own
+// golden vectors transcribed under tests/golden/ (binpack scores, LessEqual tables,
+// feasible-node-count table, allocate placements, proportion/drf orderings) — see
+// tests/test_oracle_golden.py.  Upstream kube-scheduler score arithmetic (LeastAllocated,
+// MostAllocated, BalancedAllocation, TaintToleration, NodeAffinity) is restated from the
+// published v1.35 algorithm and is pinned by the reference only at placement level:
+// for those numeric values parity is UNPINNED.
+//
+// Citations are into /root/reference/pkg/scheduler unless a full path is given.
+//
+// Canonical determinism contract: tie-break = lowest NodeList index
+// among max-score nodes (the reference picks uniformly at random, util/scheduler_helper.go:
+// 201-205); map iterations are replaced by index order; scalar dimensions iterate in
+// dimension order.
+//
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared oracle.cpp -o liboracle.so -lpthread
+#include "../include/vcalloc.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+constexpr double kMinResource = 0.1;  // api/resource_info.go:45-47
+constexpr int64_t kMaxNodeScore = 100; // fwk.MaxNodeScore
+
+// lessEqualFunc, api/resource_info.go:430-435
+inline bool le_eps(double l, double r) { return l < r || std::fabs(l - r) < kMinResource; }
+
+// ---------------------------------------------------------------------------------------
+// api.Resource with the presence semantics of its ScalarResources map
+// (api/resource_info.go:60-70).  Used for the proportion plugin's session-open arithmetic.
+// ---------------------------------------------------------------------------------------
+struct Res {
+  double v[VC_MAX_DIMS];
+  uint32_t has = 0;    // bit d (d >= 2): key present in ScalarResources
+  bool nilmap = true;  // ScalarResources == nil
+  Res() { std::fill(v, v + VC_MAX_DIMS, 0.0); }
+};
+
+
+// Resource.Add, api/resource_info.go:277-290
+void res_add(Res &r, const Res &rr, int R) {
+  r.v[0] += rr.v[0];
+  r.v[1] += rr.v[1];
+  for (int d = 2; d < R; ++d)
+    if (rr.has & (1u << d)) {
+      r.nilmap = false;
+      r.has |= 1u << d;
+      r.v[d] += rr.v[d];
+    }
+}
+// Resource.Multi, api/resource_info.go:323-330
+void res_multi(Res &r, double ratio, int R) {
+  r.v[0] *= ratio;
+  r.v[1] *= ratio;
+  for (int d = 2; d < R; ++d)
+    if (r.has & (1u << d)) r.v[d] = r.v[d] * ratio;
+}
+// Resource.MinDimensionResource, api/resource_info.go:939-976
+void res_min_dimension(Res &r, const Res &rr, bool infinity, int R) {
+  if (rr.v[0] < r.v[0]) r.v[0] = rr.v[0];
+  if (rr.v[1] < r.v[1]) r.v[1] = rr.v[1];
+  if (r.nilmap) return;
+  if (rr.nilmap) {
+    if (infinity) return;
+    for (int d = 2; d < R; ++d)
+      if (r.has & (1u << d)) r.v[d] = 0;
+    return;
+  }
+  for (int d = 2; d < R; ++d) {
+    if (!(r.has & (1u << d))) continue;
+    if (rr.has & (1u << d)) {
+      r.v[d] = std::fmin(r.v[d], rr.v[d]);
+    } else if (!infinity) {
+      r.v[d] = 0;
+    }
+  }
+}
+// helpers.Max, api/helpers/helpers.go:51-77
+Res res_max(const Res &l, const Res &r, int R) {
+  Res o;
+  o.v[0] = std::fmax(l.v[0], r.v[0]);
+  o.v[1] = std::fmax(l.v[1], r.v[1]);
+  if (l.nilmap && r.nilmap) return o;
+  o.nilmap = false;
+  for (int d = 2; d < R; ++d)
+    if ((l.has & (1u << d)) && l.v[d] >= 0) {
+      o.has |= 1u << d;
+      o.v[d] = l.v[d];
+    }
+  for (int d = 2; d < R; ++d)
+    if ((r.has & (1u << d)) && r.v[d] >= 0) {
+      double cur = (o.has & (1u << d)) ? o.v[d] : 0.0;
+      o.has |= 1u << d;
+      o.v[d] = std::fmax(r.v[d], cur);
+    }
+  return o;
+}
+// Resource.Diff(rr, Zero), api/resource_info.go:879-918 (+ setDefaultValue :979-1000)
+void res_diff_zero(const Res &l, const Res &r, Res &inc, Res &dec, int R) {
+  inc = Res();
+  dec = Res();
+  uint32_t keys = l.has | r.has;
+  if (l.v[0] > r.v[0]) inc.v[0] = l.v[0] - r.v[0]; else dec.v[0] = r.v[0] - l.v[0];
+  if (l.v[1] > r.v[1]) inc.v[1] = l.v[1] - r.v[1]; else dec.v[1] = r.v[1] - l.v[1];
+  inc.nilmap = dec.nilmap = false;  // make(map) in Diff
+  for (int d = 2; d < R; ++d) {
+    if (!(keys & (1u << d))) continue;
+    double lq = (l.has & (1u << d)) ? l.v[d] : 0.0;
+    double rq = (r.has & (1u << d)) ? r.v[d] : 0.0;
+    if (lq == -1.0) { inc.has |= 1u << d; inc.v[d] = lq; continue; }
+    if (rq == -1.0) { dec.has |= 1u << d; dec.v[d] = rq; continue; }
+    if (lq > rq) { inc.has |= 1u << d; inc.v[d] = lq - rq; }
+    else { dec.has |= 1u << d; dec.v[d] = rq - lq; }
+  }
+}
+// ExceededPart, api/resource_info.go:1075-1086
+Res res_exceeded_part(const Res &l, const Res &r, int R) {
+  Res inc, dec;
+  res_diff_zero(l, r, inc, dec, R);
+  return inc;
+}
+// Resource.LessEqual(rr, Zero), api/resource_info.go:429-463
+bool res_less_equal_zero(const Res &l, const Res &r, int R) {
+  if (!le_eps(l.v[0], r.v[0])) return false;
+  if (!le_eps(l.v[1], r.v[1])) return false;
+  for (int d = 2; d < R; ++d) {
+    if (!(l.has & (1u << d))) continue;
+    double rv = (r.has & (1u << d)) ? r.v[d] : 0.0;
+    if (!le_eps(l.v[d], rv)) return false;
+  }
+  return true;
+}
+// Resource.IsEmpty, api/resource_info.go:240-255
+bool res_is_empty(const Res &r, int R, int pods_dim) {
+  if (!(r.v[0] < kMinResource && r.v[1] < kMinResource)) return false;
+  for (int d = 2; d < R; ++d) {
+    if (!(r.has & (1u << d)) || d == pods_dim) continue;
+    if (r.v[d] >= kMinResource) return false;
+  }
+  return true;
+}
+// equality.Semantic.DeepEqual on *Resource: same values, same key set (nil == empty map)
+bool res_deep_equal(const Res &a, const Res &b, int R) {
+  if (a.v[0] != b.v[0] || a.v[1] != b.v[1] || a.has != b.has) return false;
+  for (int d = 2; d < R; ++d)
+    if ((a.has & (1u << d)) && a.v[d] != b.v[d]) return false;
+  return true;
+}
+// helpers.Share, api/helpers/helpers.go:80-93
+inline double share_of(double l, double r) {
+  if (r == 0) return l == 0 ? 0.0 : 1.0;
+  return l / r;
+}
+
+// ---------------------------------------------------------------------------------------
+// container/heap as used by util.PriorityQueue (util/priority_queue.go:30-111):
+// heap.Push = append + up, heap.Pop = swap(0,n-1) + down + remove last.
+// ---------------------------------------------------------------------------------------
+struct GoHeap {
+  std::vector<int> items;
+  std::function<bool(int, int)> less;  // lessFn(items[i], items[j])
+  bool empty() const { return items.empty(); }
+  size_t size() const { return items.size(); }
+  void push(int x) {
+    items.push_back(x);
+    int j = (int)items.size() - 1;
+    for (;;) {
+      int i = (j - 1) / 2;
+      if (i == j || !less(items[j], items[i])) break;
+      std::swap(items[i], items[j]);
+      j = i;
+    }
+  }
+  int pop() {
+    int n = (int)items.size() - 1;
+    std::swap(items[0], items[n]);
+    int i = 0;
+    for (;;) {
+      int j1 = 2 * i + 1;
+      if (j1 >= n || j1 < 0) break;
+      int j = j1;
+      int j2 = j1 + 1;
+      if (j2 < n && less(items[j2], items[j1])) j = j2;
+      if (!less(items[j], items[i])) break;
+      std::swap(items[i], items[j]);
+      i = j;
+    }
+    int x = items.back();
+    items.pop_back();
+    return x;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// A tiny spinning thread pool: mirrors workqueue.ParallelizeUntil(ctx, 16, n, fn)
+// (util/predicate_helper.go:133, util/scheduler_helper.go:103) with static chunks.
+// ---------------------------------------------------------------------------------------
+struct Pool {
+  int nthreads = 1;
+  std::vector<std::thread> workers;
+  std::atomic<uint64_t> gen{0};
+  std::atomic<int> done{0};
+  std::atomic<bool> stop{false};
+  std::function<void(int, int)> job;  // (begin, end)
+  int total = 0;
+  explicit Pool(int n) : nthreads(std::max(1, n)) {
+    for (int w = 1; w < nthreads; ++w)
+      workers.emplace_back([this, w] {
+        uint64_t seen = 0;
+        for (;;) {
+          uint64_t g;
+          int spins = 0;
+          while ((g = gen.load(std::memory_order_acquire)) == seen) {
+            if (stop.load(std::memory_order_relaxed)) return;
+            if (++spins > 2000) { std::this_thread::yield(); spins = 0; }
+          }
+          seen = g;
+          run_chunk(w);
+          done.fetch_add(1, std::memory_order_release);
+        }
+      });
+  }
+  ~Pool() {
+    stop.store(true);
+    for (auto &t : workers) t.join();
+  }
+  void run_chunk(int w) {
+    int per = (total + nthreads - 1) / nthreads;
+    int b = std::min(total, w * per), e = std::min(total, b + per);
+    if (b < e) job(b, e);
+  }
+  void parallel_for(int n, std::function<void(int, int)> fn) {
+    if (nthreads == 1 || n < 256) { fn(0, n); return; }
+    job = std::move(fn);
+    total = n;
+    done.store(0, std::memory_order_relaxed);
+    gen.fetch_add(1, std::memory_order_release);
+    run_chunk(0);
+    while (done.load(std::memory_order_acquire) < nthreads - 1) {}
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Session: the snapshot plus everything the plugins keep (framework/session.go:66-164)
+// ---------------------------------------------------------------------------------------
+enum TaskStatus : int8_t { kPending = 0, kAllocated = 1, kPipelined = 2, kBinding = 3 };
+
+struct Op { int task; int node; int kind; double score; };  // Statement.operations (framework/statement.go:47-52)
+
+struct QueueAttr {  // proportion.queueAttr (plugins/proportion/proportion.go:57-74)
+  bool exists = false;
+  Res deserved, allocated, request, capability, realCapability, guarantee;
+  double share = 0;
+  int32_t weight = 0;
+};
+
+struct Session {
+  vc_dims d{};
+  vc_conf conf{};
+  int N = 0, T = 0, J = 0, Q = 0, C = 0, R = 0, K = 0, Wl = 0, Wt = 0, NR = 0;
+  // nodes
+  std::vector<double> alloc, idle, used, rel, pip, kalloc, kreq, knz;
+  std::vector<int32_t> max_tasks, pod_count, zone;
+  std::vector<uint64_t> labels, thard, tsoft;
+  std::vector<uint32_t> nflags;
+  std::vector<uint8_t> zone_active;
+  // tasks
+  std::vector<double> req, tkreq, tknz;
+  std::vector<uint32_t> req_has, t_uid;
+  std::vector<int32_t> t_job, t_class, t_role, t_prio;
+  std::vector<int64_t> t_podidx, t_ts;
+  std::vector<int8_t> t_status;
+  std::vector<int32_t> t_node;
+  // classes
+  std::vector<uint64_t> c_sel, c_aff, c_tolh, c_tols, c_pref;
+  std::vector<int32_t> c_naff, c_npref, c_prefw;
+  std::vector<uint32_t> c_flags;
+  // jobs
+  std::vector<int32_t> j_queue, j_min, j_prio, j_ntasks, j_ready, j_waiting, j_pbe, j_valid, j_taskmintotal,
+      j_roleoff;
+  std::vector<int64_t> j_ts;
+  std::vector<uint32_t> j_uid, j_flags;
+  std::vector<double> j_alloc;  // drf attr.allocated [R][J]
+  std::vector<double> j_share;  // drf attr.share
+  std::vector<int32_t> r_min, r_occ, r_pip, r_pending, r_valid;
+  std::vector<uint32_t> r_flags;
+  std::vector<uint8_t> r_failed;  // role has an entry in job.NodesFitErrors (FitFailedRoles, job_info.go:881-891)
+  // queues
+  std::vector<int32_t> q_weight, q_prio;
+  std::vector<int64_t> q_ts;
+  std::vector<uint32_t> q_uid, q_flags;
+  std::vector<Res> q_cap, q_guar, q_alloc0, q_req0;
+  std::vector<uint8_t> q_cap_any, q_guar_any;
+  std::vector<QueueAttr> qattr;
+  Res total;  // ssn.TotalResource (framework/session.go:272-274)
+  bool has_plugin[128] = {false};
+  // results
+  std::vector<vc_decision> decisions;
+  std::vector<vc_visit> visits;
+  std::vector<int32_t> fit_errors;
+  int64_t sweeps = 0;
+  int64_t last_processed_node_index = 0;  // util/scheduler_helper.go:50
+  Pool *pool = nullptr;
+  ~Session() { delete pool; }
+};
+
+inline double &at(std::vector<double> &v, int d, int n, int i) { return v[(size_t)d * n + i]; }
+inline double at(const std::vector<double> &v, int d, int n, int i) { return v[(size_t)d * n + i]; }
+
+template <typename Tv>
+void copy_in(std::vector<Tv> &dst, const Tv *src, size_t n, Tv fill = Tv()) {
+  dst.assign(n, fill);
+  if (src && n) std::memcpy(dst.data(), src, n * sizeof(Tv));
+}
+
+// ---------------------------------------------------------------------------------------
+// JobInfo readiness (api/job_info.go)
+// ---------------------------------------------------------------------------------------
+// CheckTaskReady, api/job_info.go:1024-1036
+bool check_task_ready(const Session &s, int j) {
+  if (s.j_min[j] < s.j_taskmintotal[j]) return true;
+  for (int r = s.j_roleoff[j]; r < s.j_roleoff[j + 1]; ++r)
+    if ((s.r_flags[r] & VC_ROLE_IN_MIN_MAP) && s.r_occ[r] < s.r_min[r]) return false;
+  return true;
+}
+// CheckTaskPipelined, api/job_info.go:1039-1070
+bool check_task_pipelined(const Session &s, int j) {
+  if (s.j_min[j] < s.j_taskmintotal[j]) return true;
+  for (int r = s.j_roleoff[j]; r < s.j_roleoff[j + 1]; ++r)
+    if ((s.r_flags[r] & VC_ROLE_IN_MIN_MAP) && s.r_occ[r] + s.r_pip[r] < s.r_min[r]) return false;
+  return true;
+}
+// IsReady / IsPipelined, api/job_info.go:1169-1175
+bool is_ready(const Session &s, int j) { return s.j_ready[j] + s.j_pbe[j] >= s.j_min[j]; }
+bool is_pipelined(const Session &s, int j) { return s.j_waiting[j] + s.j_ready[j] + s.j_pbe[j] >= s.j_min[j]; }
+
+// ssn.JobReady, framework/session_plugins.go:428-446; gang fn plugins/gang/gang.go:183-189
+bool job_ready(const Session &s, int j) {
+  for (int i = 0; i < s.conf.n_plugins; ++i) {
+    const vc_plugin_option &p = s.conf.plugins[i];
+    if (!(p.enabled & VC_EN_JOB_READY)) continue;
+    if (p.plugin == VC_PLUGIN_GANG && !(check_task_ready(s, j) && is_ready(s, j))) return false;
+  }
+  return true;
+}
+// ssn.JobPipelined, framework/session_plugins.go:450-478 (Permit=1, Abstain=0, Reject=-1)
+bool job_pipelined(const Session &s, int j) {
+  bool has_found = false;
+  int i = 0;
+  while (i < s.conf.n_plugins) {
+    int tier = s.conf.plugins[i].tier;
+    for (; i < s.conf.n_plugins && s.conf.plugins[i].tier == tier; ++i) {
+      const vc_plugin_option &p = s.conf.plugins[i];
+      if (!(p.enabled & VC_EN_JOB_PIPELINED)) continue;
+      int res;
+      if (p.plugin == VC_PLUGIN_GANG)  // gang.go:191-197
+        res = (check_task_pipelined(s, j) && is_pipelined(s, j)) ? 1 : -1;
+      else if (p.plugin == VC_PLUGIN_TDM)  // tdm.go:275-281
+        res = is_pipelined(s, j) ? 1 : -1;
+      else
+        continue;
+      if (res < 0) return false;
+      if (res > 0) has_found = true;
+    }
+    if (has_found) return true;
+  }
+  return true;
+}
+// ssn.JobValid -> gang validJobFn, plugins/gang/gang.go:58-93; CheckTaskValid job_info.go:993-1019
+bool job_valid(const Session &s, int j) {
+  if (!s.has_plugin[VC_PLUGIN_GANG]) return true;
+  if (!(s.j_min[j] < s.j_taskmintotal[j])) {
+    for (int r = s.j_roleoff[j]; r < s.j_roleoff[j + 1]; ++r) {
+      if (!(s.r_flags[r] & VC_ROLE_IN_MIN_MAP) || s.r_min[r] == 0) continue;
+      if (s.r_valid[r] < s.r_min[r]) return false;  // `!ok || act < minAvailable`
+    }
+  }
+  return s.j_valid[j] >= s.j_min[j];
+}
+
+// ---------------------------------------------------------------------------------------
+// Ordering functions (framework/session_plugins.go:660-783)
+// ---------------------------------------------------------------------------------------
+bool job_order_less(const Session &s, int l, int r) {  // ssn.JobOrderFn :660-683
+  for (int i = 0; i < s.conf.n_plugins; ++i) {
+    const vc_plugin_option &p = s.conf.plugins[i];
+    if (!(p.enabled & VC_EN_JOB_ORDER)) continue;
+    int c = 0;
+    switch (p.plugin) {
+      case VC_PLUGIN_PRIORITY:  // priority.go:73-89
+        if (s.j_prio[l] > s.j_prio[r]) c = -1;
+        else if (s.j_prio[l] < s.j_prio[r]) c = 1;
+        break;
+      case VC_PLUGIN_GANG: {  // gang.go:131-155
+        bool lr = is_ready(s, l), rr = is_ready(s, r);
+        if (lr && rr) c = 0;
+        else if (lr) c = 1;
+        else if (rr) c = -1;
+        break;
+      }
+      case VC_PLUGIN_DRF:  // drf.go:370-388
+        if (s.j_share[l] == s.j_share[r]) c = 0;
+        else c = s.j_share[l] < s.j_share[r] ? -1 : 1;
+        break;
+      case VC_PLUGIN_TDM: {  // tdm.go:261-273
+        bool lp = (s.j_flags[l] & VC_JOB_PREEMPTABLE) != 0, rp = (s.j_flags[r] & VC_JOB_PREEMPTABLE) != 0;
+        if (lp == rp) c = 0;
+        else c = !lp ? -1 : 1;
+        break;
+      }
+      default: break;
+    }
+    if (c != 0) return c < 0;
+  }
+  if (s.j_ts[l] == s.j_ts[r]) return s.j_uid[l] < s.j_uid[r];
+  return s.j_ts[l] < s.j_ts[r];
+}
+// ssn.QueueOrderFn :709-731; proportion fn plugins/proportion/proportion.go:266-284
+bool queue_order_less(const Session &s, int l, int r) {
+  for (int i = 0; i < s.conf.n_plugins; ++i) {
+    const vc_plugin_option &p = s.conf.plugins[i];
+    if (!(p.enabled & VC_EN_QUEUE_ORDER)) continue;
+    if (p.plugin == VC_PLUGIN_PROPORTION) {
+      if (s.q_prio[l] != s.q_prio[r]) return (s.q_prio[r] - s.q_prio[l]) < 0;
+      double ls = s.qattr[l].share, rs = s.qattr[r].share;
+      if (ls != rs) return ls < rs;
+    }
+  }
+  if (s.q_ts[l] == s.q_ts[r]) return s.q_uid[l] < s.q_uid[r];
+  return s.q_ts[l] < s.q_ts[r];
+}
+// ssn.TaskOrderFn :772-783: priority plugin (priority.go:50-69) then helpers.CompareTask
+// (pkg/controllers/job/helpers/helpers.go:54-69)
+bool task_order_less(const Session &s, int l, int r) {
+  for (int i = 0; i < s.conf.n_plugins; ++i) {
+    const vc_plugin_option &p = s.conf.plugins[i];
+    if (!(p.enabled & VC_EN_TASK_ORDER)) continue;
+    if (p.plugin == VC_PLUGIN_PRIORITY && s.t_prio[l] != s.t_prio[r]) return s.t_prio[l] > s.t_prio[r];
+  }
+  bool lerr = s.t_podidx[l] < 0, rerr = s.t_podidx[r] < 0;
+  if (lerr || rerr || s.t_podidx[l] == s.t_podidx[r]) {
+    if (s.t_ts[l] == s.t_ts[r]) return s.t_uid[l] < s.t_uid[r];
+    return s.t_ts[l] < s.t_ts[r];
+  }
+  return !(s.t_podidx[l] > s.t_podidx[r]);
+}
+
+// ---------------------------------------------------------------------------------------
+// Plugin state
+// ---------------------------------------------------------------------------------------
+// drf.calculateShare, plugins/drf/drf.go:566-578 (ResourceNames() = dims with total >= 0.1)
+void drf_update_share(Session &s, int j) {
+  double res = 0;
+  for (int d = 0; d < s.R; ++d) {
+    if (d >= 2 && !(s.total.has & (1u << d))) continue;
+    if (!(s.total.v[d] >= kMinResource)) continue;
+    double sh = share_of(at(s.j_alloc, d, s.J, j), s.total.v[d]);
+    if (sh > res) res = sh;
+  }
+  s.j_share[j] = res;
+}
+// updateQueueAttrShare, plugins/proportion/proportion.go:590-602
+void proportion_update_share(const Session &s, QueueAttr &a) {
+  double res = 0;
+  for (int d = 0; d < s.R; ++d) {
+    if (d >= 2 && !(a.deserved.has & (1u << d))) continue;
+    if (!(a.deserved.v[d] >= kMinResource)) continue;
+    double al = (d < 2 || (a.allocated.has & (1u << d))) ? a.allocated.v[d] : 0.0;
+    double sh = share_of(al, a.deserved.v[d]);
+    if (sh > res) res = sh;
+  }
+  a.share = res;
+}
+
+Res task_res(const Session &s, int t) {
+  Res r;
+  for (int d = 0; d < s.R; ++d) r.v[d] = at(s.req, d, s.T, t);
+  r.has = s.req_has[t] & ~3u;
+  for (int d = 2; d < s.R; ++d)
+    if (!(r.has & (1u << d))) r.v[d] = 0;
+  r.nilmap = r.has == 0;
+  return r;
+}
+
+// proportion OnSessionOpen, plugins/proportion/proportion.go:90-264
+void proportion_open(Session &s) {
+  const int R = s.R;
+  s.qattr.assign(s.Q, QueueAttr());
+  if (!s.has_plugin[VC_PLUGIN_PROPORTION]) return;
+  Res total_guarantee;  // :95-101, over every queue of the session
+  for (int q = 0; q < s.Q; ++q)
+    if (s.q_guar_any[q]) res_add(total_guarantee, s.q_guar[q], R);
+  // :103-142 — attributes exist only for queues that own at least one job
+  for (int j = 0; j < s.J; ++j) {
+    int q = s.j_queue[j];
+    if (q < 0 || s.qattr[q].exists) continue;
+    QueueAttr &a = s.qattr[q];
+    a.exists = true;
+    a.weight = s.q_weight[q];
+    bool has_cap = s.q_cap_any[q];
+    if (has_cap) {
+      a.capability = s.q_cap[q];
+      if (a.capability.v[0] <= 0) a.capability.v[0] = std::numeric_limits<double>::max();
+      if (a.capability.v[1] <= 0) a.capability.v[1] = std::numeric_limits<double>::max();
+    }
+    if (s.q_guar_any[q]) a.guarantee = s.q_guar[q];
+    Res real_cap = res_exceeded_part(s.total, total_guarantee, R);
+    res_add(real_cap, a.guarantee, R);
+    if (has_cap) res_min_dimension(real_cap, a.capability, /*infinity=*/true, R);
+    a.realCapability = real_cap;
+    a.allocated = s.q_alloc0[q];  // :143-156, summed by the snapshot encoder
+    a.request = s.q_req0[q];
+  }
+  // :197-264 water-filling
+  Res remaining = s.total;
+  std::vector<uint8_t> meet(s.Q, 0);
+  for (;;) {
+    int32_t total_weight = 0;
+    for (int q = 0; q < s.Q; ++q)
+      if (s.qattr[q].exists && !meet[q]) total_weight += s.qattr[q].weight;
+    if (total_weight == 0) break;
+    Res old_remaining = remaining;
+    Res increased, decreased;
+    for (int q = 0; q < s.Q; ++q) {
+      QueueAttr &a = s.qattr[q];
+      if (!a.exists || meet[q]) continue;
+      Res old_deserved = a.deserved;
+      Res part = remaining;
+      res_multi(part, (double)a.weight / (double)total_weight, R);
+      res_add(a.deserved, part, R);
+      res_min_dimension(a.deserved, a.realCapability, /*infinity=*/true, R);
+      res_min_dimension(a.deserved, a.request, /*infinity=*/false, R);
+      a.deserved = res_max(a.deserved, a.guarantee, R);
+      proportion_update_share(s, a);
+      if (res_less_equal_zero(a.request, a.deserved, R)) meet[q] = 1;
+      else if (res_deep_equal(a.deserved, old_deserved, R)) meet[q] = 1;
+      Res inc, dec;
+      res_diff_zero(a.deserved, old_deserved, inc, dec, R);
+      res_add(increased, inc, R);
+      res_add(decreased, dec, R);
+    }
+    Res tmp = remaining;
+    res_add(tmp, decreased, R);
+    remaining = res_exceeded_part(tmp, increased, R);
+    if (res_is_empty(remaining, R, s.d.pods_dim) || res_deep_equal(remaining, old_remaining, R)) break;
+  }
+}
+
+// proportion OverusedFn, plugins/proportion/proportion.go:319-331
+bool overused(const Session &s, int q) {
+  for (int i = 0; i < s.conf.n_plugins; ++i) {
+    const vc_plugin_option &p = s.conf.plugins[i];
+    if (!(p.enabled & VC_EN_OVERUSED)) continue;
+    if (p.plugin == VC_PLUGIN_PROPORTION) {
+      const QueueAttr &a = s.qattr[q];
+      if (res_less_equal_zero(a.deserved, a.allocated, s.R)) return true;
+    }
+  }
+  return false;
+}
+// ssn.Allocatable :350-366 -> proportion queueAllocatable, proportion.go:333-348, using
+// LessEqualWithDimensionAndResourcesName, api/resource_info.go:469-514
+bool allocatable(const Session &s, int q, int t) {
+  for (int i = 0; i < s.conf.n_plugins; ++i) {
+    const vc_plugin_option &p = s.conf.plugins[i];
+    if (!(p.enabled & VC_EN_ALLOCATABLE)) continue;
+    if (p.plugin != VC_PLUGIN_PROPORTION) continue;
+    if (!(s.q_flags[q] & VC_QUEUE_OPEN)) return false;
+    const QueueAttr &a = s.qattr[q];
+    Res fu = a.allocated;
+    Res rq = task_res(s, t);
+    res_add(fu, rq, s.R);
+    bool ok = true;
+    if (rq.v[0] > 0 && fu.v[0] > a.deserved.v[0]) ok = false;
+    if (rq.v[1] > 0 && fu.v[1] > a.deserved.v[1]) ok = false;
+    if (!fu.nilmap) {
+      for (int d = 2; d < s.R; ++d) {
+        if (!(rq.has & (1u << d)) || d == s.d.pods_dim) continue;
+        double rquant = (fu.has & (1u << d)) ? fu.v[d] : 0.0;
+        double rrquant = (a.deserved.has & (1u << d)) ? a.deserved.v[d] : 0.0;
+        if (rq.v[d] > 0 && rquant > rrquant) ok = false;
+      }
+    }
+    if (!ok) return false;
+  }
+  return true;
+}
+
+// Event handlers fired by Statement.Allocate / Pipeline (AllocateFunc) and by
+// unallocate / UnPipeline (DeallocateFunc): drf.go:391-454, proportion.go:475-518,
+// predicates.go:212-304 (k8s NodeInfo AddPodInfo / RemovePod).
+void on_allocate_event(Session &s, int t, int n) {
+  int j = s.t_job[t];
+  if (s.has_plugin[VC_PLUGIN_DRF]) {
+    for (int d = 0; d < s.R; ++d) at(s.j_alloc, d, s.J, j) += at(s.req, d, s.T, t);
+    drf_update_share(s, j);
+  }
+  if (s.has_plugin[VC_PLUGIN_PROPORTION] && s.j_queue[j] >= 0 && s.qattr[s.j_queue[j]].exists) {
+    QueueAttr &a = s.qattr[s.j_queue[j]];
+    res_add(a.allocated, task_res(s, t), s.R);
+    proportion_update_share(s, a);
+  }
+  if (s.has_plugin[VC_PLUGIN_PREDICATES]) {
+    s.pod_count[n] += 1;
+    for (int k = 0; k < s.K; ++k) {
+      at(s.kreq, k, s.N, n) += at(s.tkreq, k, s.T, t);
+      at(s.knz, k, s.N, n) += at(s.tknz, k, s.T, t);
+    }
+  }
+}
+void on_deallocate_event(Session &s, int t, int n) {
+  int j = s.t_job[t];
+  if (s.has_plugin[VC_PLUGIN_DRF]) {
+    for (int d = 0; d < s.R; ++d) at(s.j_alloc, d, s.J, j) -= at(s.req, d, s.T, t);
+    drf_update_share(s, j);
+  }
+  if (s.has_plugin[VC_PLUGIN_PROPORTION] && s.j_queue[j] >= 0 && s.qattr[s.j_queue[j]].exists) {
+    QueueAttr &a = s.qattr[s.j_queue[j]];
+    Res rq = task_res(s, t);  // Resource.Sub -> sub, api/resource_info.go:293-320
+    a.allocated.v[0] -= rq.v[0];
+    a.allocated.v[1] -= rq.v[1];
+    if (!a.allocated.nilmap)
+      for (int d = 2; d < s.R; ++d)
+        if (rq.has & (1u << d)) {
+          a.allocated.has |= 1u << d;
+          a.allocated.v[d] -= rq.v[d];
+        }
+    proportion_update_share(s, a);
+  }
+  if (s.has_plugin[VC_PLUGIN_PREDICATES]) {
+    s.pod_count[n] -= 1;
+    for (int k = 0; k < s.K; ++k) {
+      at(s.kreq, k, s.N, n) -= at(s.tkreq, k, s.T, t);
+      at(s.knz, k, s.N, n) -= at(s.tknz, k, s.T, t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Resource fit: task.InitResreq.LessEqual(x, Zero), api/resource_info.go:429-463
+// ---------------------------------------------------------------------------------------
+inline double future_idle(const Session &s, int d, int n) {  // NodeInfo.FutureIdle, api/node_info.go:114-116
+  return (at(s.idle, d, s.N, n) + at(s.rel, d, s.N, n)) - at(s.pip, d, s.N, n);
+}
+bool fits_idle(const Session &s, int t, int n) {
+  for (int d = 0; d < s.R; ++d) {
+    if (d >= 2 && !(s.req_has[t] & (1u << d))) continue;
+    if (!le_eps(at(s.req, d, s.T, t), at(s.idle, d, s.N, n))) return false;
+  }
+  return true;
+}
+bool fits_future_idle(const Session &s, int t, int n) {
+  for (int d = 0; d < s.R; ++d) {
+    if (d >= 2 && !(s.req_has[t] & (1u << d))) continue;
+    if (!le_eps(at(s.req, d, s.T, t), future_idle(s, d, n))) return false;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// Predicates (allocate.predicate allocate.go:816-824 -> ssn.PredicateForAllocateAction
+// session.go:657-674 -> ssn.PredicateFn session_plugins.go:784-801)
+// ---------------------------------------------------------------------------------------
+inline bool mask_subset(const uint64_t *need, const std::vector<uint64_t> &bits, int W, int N, int n) {
+  for (int w = 0; w < W; ++w)
+    if ((bits[(size_t)w * N + n] & need[w]) != need[w]) return false;
+  return true;
+}
+// predicates.Predicate for pods without ports/volumes/pod-affinity/DRA:
+// pod-count cap (predicates.go:662-671), then the stable filters NodeUnschedulable,
+// NodeAffinity (nodeSelector + required terms), TaintToleration (NoSchedule/NoExecute).
+bool predicates_plugin_ok(const Session &s, int t, int n) {
+  bool ok = true;
+  if (s.max_tasks[n] <= s.pod_count[n]) ok = false;
+  int c = s.t_class[t];
+  if ((s.nflags[n] & VC_NODE_UNSCHEDULABLE) && !(s.c_flags[c] & VC_CLASS_TOLERATES_UNSCHEDULABLE)) ok = false;
+  if (s.conf.predicates_enable & VC_PRED_NODE_AFFINITY) {
+    if (!mask_subset(&s.c_sel[(size_t)c * s.Wl], s.labels, s.Wl, s.N, n)) ok = false;
+    int na = s.c_naff[c];
+    if (na > 0) {
+      bool any = false;
+      for (int k = 0; k < na && !any; ++k)
+        any = mask_subset(&s.c_aff[((size_t)c * VC_MAX_TERMS + k) * s.Wl], s.labels, s.Wl, s.N, n);
+      if (!any) ok = false;
+    }
+  }
+  if (s.conf.predicates_enable & VC_PRED_TAINT_TOLERATION) {
+    for (int w = 0; w < s.Wt; ++w)
+      if (s.thard[(size_t)w * s.N + n] & ~s.c_tolh[(size_t)c * s.Wt + w]) ok = false;
+  }
+  return ok;
+}
+// tdm predicateFn, plugins/tdm/tdm.go:146-171
+bool tdm_predicate_ok(const Session &s, int t, int n) {
+  int z = s.zone[n];
+  if (z < 0) return true;
+  if (!s.zone_active[z]) return false;
+  if (!(s.c_flags[s.t_class[t]] & VC_CLASS_REVOCABLE)) return false;
+  return true;
+}
+bool predicate(const Session &s, int t, int n) {
+  if (!fits_future_idle(s, t, n)) return false;
+  for (int i = 0; i < s.conf.n_plugins; ++i) {
+    const vc_plugin_option &p = s.conf.plugins[i];
+    if (!(p.enabled & VC_EN_PREDICATE)) continue;
+    if (p.plugin == VC_PLUGIN_PREDICATES && !predicates_plugin_ok(s, t, n)) return false;
+    if (p.plugin == VC_PLUGIN_TDM && !tdm_predicate_ok(s, t, n)) return false;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// Scores
+// ---------------------------------------------------------------------------------------
+// BinPackingScore / ResourceBinPackingScore, plugins/binpack/binpack.go:206-261
+double binpack_score(const Session &s, int t, int n) {
+  double score = 0.0;
+  int weight_sum = 0;
+  for (int d = 0; d < s.R; ++d) {
+    double request = at(s.req, d, s.T, t);
+    if (d >= 2 && !(s.req_has[t] & (1u << d))) continue;  // ResourceNames(): keys of the map ...
+    if (!(request >= kMinResource)) continue;             // ... with amount >= minResource
+    if (request == 0) continue;
+    int w = s.conf.binpack_dim_weight[d];
+    if (w < 0) continue;  // not found in BinPackingResources
+    double allocate = at(s.alloc, d, s.N, n);
+    double node_used = at(s.used, d, s.N, n);
+    double resource_score = 0;
+    if (!(allocate == 0 || w == 0)) {
+      double used_finally = request + node_used;
+      if (used_finally > allocate) return 0;
+      resource_score = used_finally * (double)w / allocate;
+    }
+    score += resource_score;
+    weight_sum += w;
+  }
+  if (weight_sum > 0) score /= (double)weight_sum;
+  score *= (double)(kMaxNodeScore * (int64_t)s.conf.binpack_weight);
+  return score;
+}
+
+// Upstream kube-scheduler v1.35 noderesources scorers (pkg/scheduler/framework/plugins/
+// noderesources/{resource_allocation,least_allocated,most_allocated,balanced_allocation}.go),
+// restated from the published algorithm; constructed at plugins/nodeorder/nodeorder.go:204-244.
+int64_t least_requested_score(int64_t requested, int64_t capacity) {
+  if (capacity == 0) return 0;
+  if (requested > capacity) return 0;
+  return ((capacity - requested) * kMaxNodeScore) / capacity;
+}
+int64_t most_requested_score(int64_t requested, int64_t capacity) {
+  if (capacity == 0) return 0;
+  if (requested > capacity) requested = capacity;
+  return (requested * kMaxNodeScore) / capacity;
+}
+int64_t least_allocated(const Session &s, int t, int n) {  // resources cpu:50, memory:50 (nodeorder.go:206-211)
+  int64_t node_score = 0, weight_sum = 0;
+  for (int k = 0; k < 2 && k < s.K; ++k) {
+    int64_t alloc = (int64_t)at(s.kalloc, k, s.N, n);
+    int64_t reqv = (int64_t)at(s.knz, k, s.N, n) + (int64_t)at(s.tknz, k, s.T, t);
+    if (alloc == 0) continue;
+    node_score += least_requested_score(reqv, alloc) * 50;
+    weight_sum += 50;
+  }
+  return weight_sum == 0 ? 0 : node_score / weight_sum;
+}
+int64_t most_allocated(const Session &s, int t, int n) {  // cpu:1, memory:1 (nodeorder.go:222-227)
+  int64_t node_score = 0, weight_sum = 0;
+  for (int k = 0; k < 2 && k < s.K; ++k) {
+    int64_t alloc = (int64_t)at(s.kalloc, k, s.N, n);
+    int64_t reqv = (int64_t)at(s.knz, k, s.N, n) + (int64_t)at(s.tknz, k, s.T, t);
+    if (alloc == 0) continue;
+    node_score += most_requested_score(reqv, alloc) * 1;
+    weight_sum += 1;
+  }
+  return weight_sum == 0 ? 0 : node_score / weight_sum;
+}
+int64_t balanced_allocation(const Session &s, int t, int n) {  // cpu, memory, nvidia.com/gpu (nodeorder.go:238-244)
+  double fractions[VC_MAX_KDIMS];
+  int nf = 0;
+  double total_fraction = 0;
+  for (int k = 0; k < s.K; ++k) {
+    int64_t pod_req = (int64_t)at(s.tkreq, k, s.T, t);
+    if (k >= 2 && pod_req == 0) continue;  // extended resource the pod does not request
+    int64_t alloc = (int64_t)at(s.kalloc, k, s.N, n);
+    if (alloc == 0) continue;
+    int64_t reqv = (int64_t)at(s.kreq, k, s.N, n) + pod_req;
+    double fraction = (double)reqv / (double)alloc;
+    if (fraction > 1) fraction = 1;
+    total_fraction += fraction;
+    fractions[nf++] = fraction;
+  }
+  double stdv = 0.0;
+  if (nf == 2) {
+    stdv = std::fabs((fractions[0] - fractions[1]) / 2);
+  } else if (nf > 2) {
+    double mean = total_fraction / (double)nf;
+    double sum = 0;
+    for (int i = 0; i < nf; ++i) sum = sum + (fractions[i] - mean) * (fractions[i] - mean);
+    stdv = std::sqrt(sum / (double)nf);
+  }
+  return (int64_t)((1 - stdv) * (double)kMaxNodeScore);
+}
+// NodeAffinity.Score without PreScore/NormalizeScore (nodeorder.go:314-330 calls Score only)
+int64_t node_affinity_score(const Session &s, int t, int n) {
+  int c = s.t_class[t];
+  int64_t count = 0;
+  for (int k = 0; k < s.c_npref[c]; ++k)
+    if (mask_subset(&s.c_pref[((size_t)c * VC_MAX_TERMS + k) * s.Wl], s.labels, s.Wl, s.N, n))
+      count += s.c_prefw[(size_t)c * VC_MAX_TERMS + k];
+  return count;
+}
+// nodeorder NodeOrderFn, plugins/nodeorder/nodeorder.go:314-330
+double nodeorder_score(const Session &s, int t, int n) {
+  double node_score = 0.0;
+  if (s.conf.w_least != 0) node_score += (double)least_allocated(s, t, n) * (double)s.conf.w_least;
+  if (s.conf.w_most != 0) node_score += (double)most_allocated(s, t, n) * (double)s.conf.w_most;
+  if (s.conf.w_balanced != 0) node_score += (double)balanced_allocation(s, t, n) * (double)s.conf.w_balanced;
+  if (s.conf.w_node_affinity != 0) node_score += (double)node_affinity_score(s, t, n) * (double)s.conf.w_node_affinity;
+  return node_score;
+}
+// TaintToleration.Score: number of PreferNoSchedule taints the pod does not tolerate
+int64_t taint_soft_count(const Session &s, int t, int n) {
+  int c = s.t_class[t];
+  int64_t cnt = 0;
+  for (int w = 0; w < s.Wt; ++w)
+    cnt += __builtin_popcountll(s.tsoft[(size_t)w * s.N + n] & ~s.c_tols[(size_t)c * s.Wt + w]);
+  return cnt;
+}
+
+// ssn.NodeOrderMapFn, framework/session_plugins.go:974-999 (no plugin on this path registers
+// a NodeMapFn, so mapScores stays empty).  Returns false when a NodeOrderFn returned an error
+// (tdm.go:181-184): util.PrioritizeNodes then records no order score for the node.
+bool node_order(const Session &s, int t, int n, double *out) {
+  double priority_score = 0.0;
+  for (int i = 0; i < s.conf.n_plugins; ++i) {
+    const vc_plugin_option &p = s.conf.plugins[i];
+    if (!(p.enabled & VC_EN_NODE_ORDER)) continue;
+    switch (p.plugin) {
+      case VC_PLUGIN_BINPACK:
+        if (s.conf.binpack_weight != 0) priority_score += binpack_score(s, t, n);  // binpack.go:192-196
+        break;
+      case VC_PLUGIN_NODEORDER: priority_score += nodeorder_score(s, t, n); break;
+      case VC_PLUGIN_TDM: {  // tdm.go:174-195
+        int z = s.zone[n];
+        double sc = 0.0;
+        if (z >= 0) {
+          if (!s.zone_active[z]) return false;
+          if (s.c_flags[s.t_class[t]] & VC_CLASS_REVOCABLE) sc = (double)kMaxNodeScore;
+        }
+        priority_score += sc;
+        break;
+      }
+      default: break;
+    }
+  }
+  *out = priority_score;
+  return true;
+}
+bool batch_enabled(const Session &s) {  // does any BatchNodeOrderFn produce entries?
+  for (int i = 0; i < s.conf.n_plugins; ++i) {
+    const vc_plugin_option &p = s.conf.plugins[i];
+    if ((p.enabled & VC_EN_NODE_ORDER) && (p.plugin == VC_PLUGIN_NODEORDER || p.plugin == VC_PLUGIN_PREDICATES))
+      return true;
+  }
+  return false;
+}
+bool taint_batch_enabled(const Session &s) {
+  if (s.conf.w_taint_toleration == 0) return false;
+  for (int i = 0; i < s.conf.n_plugins; ++i)
+    if ((s.conf.plugins[i].enabled & VC_EN_NODE_ORDER) && s.conf.plugins[i].plugin == VC_PLUGIN_NODEORDER) return true;
+  return false;
+}
+
+// util.PrioritizeNodes (util/scheduler_helper.go:76-138) + util.SelectBestNodeAndScore (:191-206)
+// with the canonical tie-break.  `scores_out` (optional) receives the per-node totals.
+int prioritize_and_select(Session &s, int t, const std::vector<int> &nodes, double *best_score,
+                          std::vector<double> *scores_out) {
+  const int m = (int)nodes.size();
+  std::vector<double> order(m, 0.0);
+  std::vector<uint8_t> has_order(m, 0);
+  std::vector<int64_t> tcount(m, 0);
+  const bool taint = taint_batch_enabled(s);
+  s.pool->parallel_for(m, [&](int b, int e) {
+    for (int i = b; i < e; ++i) {
+      double o;
+      if (node_order(s, t, nodes[i], &o)) { order[i] = o; has_order[i] = 1; }
+      if (taint) tcount[i] = taint_soft_count(s, t, nodes[i]);
+    }
+  });
+  // nodeorder BatchNodeOrderFn (nodeorder.go:332-384): TaintToleration through
+  // nodescore.CalculatePluginScore (plugins/util/nodescore/score_helper.go:42-109) with
+  // DefaultNormalizeScore(MaxNodeScore, reverse=true).
+  int64_t max_count = 0;
+  if (taint)
+    for (int i = 0; i < m; ++i) max_count = std::max(max_count, tcount[i]);
+  const bool batch = batch_enabled(s);
+  int best = -1;
+  double best_sc = -std::numeric_limits<double>::infinity();
+  if (scores_out) scores_out->assign(m, 0.0);
+  for (int i = 0; i < m; ++i) {
+    double score = 0.0;
+    if (has_order[i]) score += order[i];
+    if (batch) {
+      double b = 0.0;  // priorityScore[nodeName] += score, session_plugins.go:946-967
+      if (taint) {
+        int64_t sc = max_count == 0 ? kMaxNodeScore : kMaxNodeScore - (kMaxNodeScore * tcount[i] / max_count);
+        sc *= (int64_t)s.conf.w_taint_toleration;
+        double node_sc = 0.0;
+        node_sc += (double)sc;  // nodeorder.go:369-381
+        b += node_sc;
+      }
+      score += b;
+    }
+    if (scores_out) (*scores_out)[i] = score;
+    if (score > best_sc || (score == best_sc && best >= 0 && nodes[i] < nodes[best])) {
+      best_sc = score;
+      best = i;
+    }
+  }
+  if (best < 0) return -1;
+  *best_score = best_sc;
+  return nodes[best];
+}
+
+// CalculateNumOfFeasibleNodesToFind, util/scheduler_helper.go:54-73
+int32_t num_feasible_nodes_to_find(int32_t num_all, int32_t pct, int32_t min_nodes, int32_t min_pct) {
+  if (num_all <= min_nodes || pct >= 100) return num_all;
+  int32_t adaptive = pct;
+  if (adaptive <= 0) {
+    adaptive = 50 - num_all / 125;
+    if (adaptive < min_pct) adaptive = min_pct;
+  }
+  int32_t num = num_all * adaptive / 100;
+  if (num < min_nodes) num = min_nodes;
+  return num;
+}
+
+// ---------------------------------------------------------------------------------------
+// Statement (framework/statement.go)
+// ---------------------------------------------------------------------------------------
+void stmt_allocate(Session &s, std::vector<Op> &ops, int t, int n, double score) {  // :242-302
+  int j = s.t_job[t], r = s.t_role[t];
+  s.t_status[t] = kAllocated;  // job.UpdateTaskStatus(task, Allocated)
+  s.r_pending[r] -= 1;
+  s.r_occ[r] += 1;
+  s.j_ready[j] += 1;
+  s.t_node[t] = n;
+  for (int d = 0; d < s.R; ++d) {  // node.AddTask default branch, api/node_info.go:467-471
+    at(s.idle, d, s.N, n) -= at(s.req, d, s.T, t);
+    at(s.used, d, s.N, n) += at(s.req, d, s.T, t);
+  }
+  on_allocate_event(s, t, n);
+  ops.push_back({t, n, VC_OP_ALLOCATE, score});
+}
+void stmt_pipeline(Session &s, std::vector<Op> &ops, int t, int n, double score) {  // :146-200
+  int j = s.t_job[t], r = s.t_role[t];
+  s.t_status[t] = kPipelined;
+  s.r_pending[r] -= 1;
+  s.r_pip[r] += 1;
+  s.j_waiting[j] += 1;
+  s.t_node[t] = n;
+  for (int d = 0; d < s.R; ++d) at(s.pip, d, s.N, n) += at(s.req, d, s.T, t);  // node_info.go:457-458
+  on_allocate_event(s, t, n);
+  ops.push_back({t, n, VC_OP_PIPELINE, score});
+}
+void stmt_discard(Session &s, std::vector<Op> &ops) {  // :357-381
+  for (int i = (int)ops.size() - 1; i >= 0; --i) {
+    int t = ops[i].task, n = ops[i].node;
+    int j = s.t_job[t], r = s.t_role[t];
+    if (ops[i].kind == VC_OP_ALLOCATE) {  // unallocate :328-354
+      s.t_status[t] = kPending;
+      s.r_pending[r] += 1;
+      s.r_occ[r] -= 1;
+      s.j_ready[j] -= 1;
+      for (int d = 0; d < s.R; ++d) {  // node.RemoveTask default branch, node_info.go:507-510
+        at(s.idle, d, s.N, n) += at(s.req, d, s.T, t);
+        at(s.used, d, s.N, n) -= at(s.req, d, s.T, t);
+      }
+    } else {  // UnPipeline :205-239
+      s.t_status[t] = kPending;
+      s.r_pending[r] += 1;
+      s.r_pip[r] -= 1;
+      s.j_waiting[j] -= 1;
+      for (int d = 0; d < s.R; ++d) at(s.pip, d, s.N, n) -= at(s.req, d, s.T, t);
+    }
+    on_deallocate_event(s, t, n);
+    s.t_node[t] = -1;
+  }
+  ops.clear();
+}
+void stmt_commit(Session &s, std::vector<Op> &ops) {  // :384-412 -> allocate :309-325
+  for (auto &op : ops)
+    if (op.kind == VC_OP_ALLOCATE) s.t_status[op.task] = kBinding;  // still counted by ReadyTaskNum
+}
+
+// ---------------------------------------------------------------------------------------
+// The action (actions/allocate/allocate.go)
+// ---------------------------------------------------------------------------------------
+// JobInfo.NeedContinueAllocating, api/job_info.go:918-966
+bool need_continue_allocating(const Session &s, int j) {
+  if (s.j_min[j] == s.j_ntasks[j]) return false;
+  if (s.j_min[j] >= s.j_ntasks[j]) return false;  // default SubJob: MinAvailable = job.MinAvailable (:1236-1250)
+  if (s.j_min[j] < s.j_taskmintotal[j]) {
+    int32_t left = 0;
+    for (int r = s.j_roleoff[j]; r < s.j_roleoff[j + 1]; ++r)
+      if (!s.r_failed[r]) left += s.r_pending[r];
+    return s.j_ready[j] + left >= s.j_min[j];
+  }
+  for (int r = s.j_roleoff[j]; r < s.j_roleoff[j + 1]; ++r) {
+    if (!s.r_failed[r]) continue;
+    int32_t mn = (s.r_flags[r] & VC_ROLE_IN_MIN_MAP) ? s.r_min[r] : 0;
+    if (mn == 0) continue;
+    if (s.r_occ[r] < mn) return false;
+  }
+  return true;
+}
+
+struct PredicateHelper {  // util/predicate_helper.go:38-41, one per allocateResourcesForTasks call
+  int role_base = 0;
+  std::vector<std::vector<uint8_t>> node_err;  // taskPredicateErrorCache[job/role][node]
+  std::vector<uint8_t> exists;
+};
+
+// ph.PredicateNodes, util/predicate_helper.go:43-140
+void predicate_nodes(Session &s, PredicateHelper &ph, int t, std::vector<int> &out) {
+  out.clear();
+  const int N = s.N;
+  if (N == 0) return;
+  int r = s.t_role[t];
+  bool enable_cache = s.conf.enable_predicate_error_cache != 0 && !(s.r_flags[r] & VC_ROLE_EMPTY_NAME);
+  int lr = r - ph.role_base;
+  bool failed_before = ph.exists[lr] != 0;
+  if (ph.node_err[lr].empty()) ph.node_err[lr].assign(N, 0);
+  std::vector<uint8_t> &cache = ph.node_err[lr];
+  int32_t to_find = num_feasible_nodes_to_find(N, s.conf.percentage_nodes_to_find, s.conf.min_nodes_to_find,
+                                               s.conf.min_percentage_nodes_to_find);
+  s.sweeps++;
+  if (to_find >= N) {
+    std::vector<uint8_t> ok(N, 0);
+    std::atomic<int> any_err{0};
+    s.pool->parallel_for(N, [&](int b, int e) {
+      bool err = false;
+      for (int n = b; n < e; ++n) {
+        if (enable_cache && failed_before && cache[n]) continue;
+        if (!predicate(s, t, n)) { cache[n] = 1; err = true; continue; }
+        ok[n] = 1;
+      }
+      if (err) any_err.store(1, std::memory_order_relaxed);
+    });
+    if (any_err.load()) ph.exists[lr] = 1;
+    for (int n = 0; n < N; ++n)
+      if (ok[n]) out.push_back(n);
+    // processedNodes == allNodes -> lastProcessedNodeIndex unchanged modulo N
+    return;
+  }
+  // Sampling mode: the deterministic (single-worker) reading of the early-stop loop.
+  int start = (int)s.last_processed_node_index;
+  int processed = 0;
+  for (int i = 0; i < N && (int)out.size() < to_find; ++i) {
+    int n = (start + i) % N;
+    processed++;
+    if (enable_cache && failed_before && cache[n]) continue;
+    if (!predicate(s, t, n)) { cache[n] = 1; ph.exists[lr] = 1; continue; }
+    out.push_back(n);
+  }
+  s.last_processed_node_index = (start + processed) % N;
+}
+
+// alloc.prioritizeNodes, allocate.go:709-778 (sharding mode none)
+int prioritize_nodes(Session &s, int t, const std::vector<int> &predicate_nodes_v, double *score_out) {
+  std::vector<int> idle_c, future_c;
+  for (int n : predicate_nodes_v) {
+    if (fits_idle(s, t, n)) idle_c.push_back(n);
+    else if (fits_future_idle(s, t, n)) future_c.push_back(n);
+  }
+  int best = -1;
+  double highest = 0;
+  const std::vector<int> *grads[2] = {&idle_c, &future_c};
+  for (int g = 0; g < 2; ++g) {
+    const std::vector<int> &nodes = *grads[g];
+    if (nodes.empty()) continue;
+    if (nodes.size() == 1) {
+      best = nodes[0];
+    } else {
+      double sc;
+      best = prioritize_and_select(s, t, nodes, &sc, nullptr);
+      if (best >= 0) highest = sc;
+    }
+    if (best >= 0) break;
+  }
+  *score_out = highest;
+  return best;
+}
+
+// alloc.allocateResourcesForTasks, allocate.go:558-694. Returns true when a statement is returned.
+bool allocate_resources_for_tasks(Session &s, int j, GoHeap &tasks, std::vector<Op> &ops) {
+  int q = s.j_queue[j];
+  ops.clear();
+  if (s.N == 0) return false;
+  PredicateHelper ph;
+  ph.role_base = s.j_roleoff[j];
+  int nroles = s.j_roleoff[j + 1] - s.j_roleoff[j];
+  ph.node_err.resize(nroles);
+  ph.exists.assign(nroles, 0);
+  std::vector<int> feasible;
+  while (!tasks.empty()) {
+    int t = tasks.pop();
+    if (!allocatable(s, q, t)) continue;
+    int r = s.t_role[t];
+    // job.TaskHasFitErrors, api/job_info.go:894-902
+    if (!(s.r_flags[r] & VC_ROLE_EMPTY_NAME) && s.r_failed[r]) {
+      s.fit_errors.push_back(t);
+      continue;
+    }
+    // ssn.PrePredicateFn: nil for pods in scope (predicates PreFilter skip/ok; proportion state clone)
+    predicate_nodes(s, ph, t, feasible);
+    if (feasible.empty()) {
+      s.fit_errors.push_back(t);
+      s.r_failed[r] = 1;
+      if (need_continue_allocating(s, j)) continue;
+      break;
+    }
+    double score = 0;
+    int best = prioritize_nodes(s, t, feasible, &score);
+    if (best < 0) continue;
+    // alloc.allocateResourcesForTask, allocate.go:780-814
+    if (fits_idle(s, t, best)) stmt_allocate(s, ops, t, best, score);
+    else if (fits_future_idle(s, t, best)) stmt_pipeline(s, ops, t, best, score);
+    if (job_ready(s, j)) break;  // ssn.SubJobReady == ssn.JobReady without a subjob policy (:369-372)
+  }
+  if (job_ready(s, j)) return true;
+  if (job_pipelined(s, j)) return true;
+  stmt_discard(s, ops);
+  return false;
+}
+
+// Action.Execute -> buildAllocateContext (:142-206) + allocateResources (:283-348)
+int allocate_execute(Session &s) {
+  for (int j = 0; j < s.J; ++j)
+    if (s.j_flags[j] & VC_JOB_UNSUPPORTED) return VC_EUNSUPPORTED;
+  std::vector<GoHeap> task_pq(s.J);
+  for (int j = 0; j < s.J; ++j) task_pq[j].less = [&s](int l, int r) { return task_order_less(s, l, r); };
+  for (int t = 0; t < s.T; ++t) task_pq[s.t_job[t]].push(t);  // organizeJobWorksheet :208-281
+  GoHeap queues;
+  queues.less = [&s](int l, int r) { return queue_order_less(s, l, r); };
+  std::vector<GoHeap> jobs_by_queue(s.Q);
+  std::vector<uint8_t> queue_seen(s.Q, 0);
+  for (int q = 0; q < s.Q; ++q) jobs_by_queue[q].less = [&s](int l, int r) { return job_order_less(s, l, r); };
+  for (int j = 0; j < s.J; ++j) {
+    if ((s.j_flags[j] & VC_JOB_PENDING_PHASE) && s.conf.enqueue_action_enabled) continue;
+    if (!job_valid(s, j)) continue;
+    int q = s.j_queue[j];
+    if (q < 0) continue;
+    if (task_pq[j].empty()) continue;  // worksheet.Empty()
+    if (!queue_seen[q]) {
+      queue_seen[q] = 1;
+      queues.push(q);
+    }
+    jobs_by_queue[q].push(j);
+  }
+  std::vector<Op> ops;
+  while (!queues.empty()) {
+    int q = queues.pop();
+    if (overused(s, q)) continue;
+    GoHeap &jobs = jobs_by_queue[q];
+    if (jobs.empty()) continue;
+    int j = jobs.pop();
+    bool stmt = allocate_resources_for_tasks(s, j, task_pq[j], ops);
+    vc_visit v;
+    v.job = j;
+    v.first_op = (int32_t)s.decisions.size();
+    v.n_ops = 0;
+    v.outcome = VC_VISIT_DISCARD;
+    if (stmt) {
+      bool ready = job_ready(s, j);
+      v.outcome = ready ? VC_VISIT_COMMIT : VC_VISIT_KEEP;
+      v.n_ops = (int32_t)ops.size();
+      for (auto &op : ops) {
+        vc_decision dcs;
+        dcs.task = op.task;
+        dcs.node = op.node;
+        dcs.kind = op.kind;
+        dcs.visit = (int32_t)s.visits.size();
+        dcs.score = op.score;
+        s.decisions.push_back(dcs);
+      }
+      if (ready) {
+        stmt_commit(s, ops);
+        if (task_pq[j].size() > 0) jobs.push(j);
+      }
+    }
+    s.visits.push_back(v);
+    queues.push(q);
+  }
+  return VC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Dense pass on the opening snapshot (the oracle for vc_score_matrix)
+// ---------------------------------------------------------------------------------------
+void score_matrix(Session &s, uint64_t *mask_out, double *score_out, double *best_score, int32_t *best_node) {
+  const int N = s.N, T = s.T;
+  const size_t mw = ((size_t)N + 63) / 64;
+  std::vector<int> idle_c, fut_c;
+  std::vector<double> sc;
+  for (int t = 0; t < T; ++t) {
+    idle_c.clear();
+    fut_c.clear();
+    if (mask_out) std::fill(mask_out + t * mw, mask_out + (t + 1) * mw, 0ull);
+    if (score_out) std::fill(score_out + (size_t)t * N, score_out + (size_t)(t + 1) * N, 0.0);
+    for (int n = 0; n < N; ++n) {
+      if (!predicate(s, t, n)) continue;
+      if (mask_out) mask_out[t * mw + n / 64] |= 1ull << (n % 64);
+      if (fits_idle(s, t, n)) idle_c.push_back(n);
+      else fut_c.push_back(n);  // predicate() already established the FutureIdle fit
+    }
+    const std::vector<int> &cand = !idle_c.empty() ? idle_c : fut_c;
+    double bs = 0;
+    int bn = -1;
+    if (!cand.empty()) {
+      bn = prioritize_and_select(s, t, cand, &bs, &sc);
+      if (score_out)
+        for (size_t i = 0; i < cand.size(); ++i) score_out[(size_t)t * N + cand[i]] = sc[i];
+    }
+    if (best_score) best_score[t] = bn >= 0 ? bs : 0.0;
+    if (best_node) best_node[t] = bn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Load
+// ---------------------------------------------------------------------------------------
+Res res_from_soa(const double *base, int count, int idx, int R, uint32_t has_bits) {
+  Res r;
+  if (!base) return r;
+  for (int d = 0; d < R; ++d) r.v[d] = base[(size_t)d * count + idx];
+  r.has = has_bits & ~(VC_RES_HAS_ANY | 3u) & ((R >= 32) ? ~0u : ((1u << R) - 1));
+  for (int d = 2; d < R; ++d)
+    if (!(r.has & (1u << d))) r.v[d] = 0.0;
+  r.nilmap = r.has == 0;
+  return r;
+}
+
+Session *load(const vc_dims *dims, const vc_nodes *nd, const vc_tasks *tk, const vc_classes *cl, const vc_jobs *jb,
+              const vc_queues *qu, const vc_conf *conf, int threads) {
+  Session *sp = new Session();
+  Session &s = *sp;
+  s.d = *dims;
+  s.conf = *conf;
+  s.N = dims->n_nodes; s.T = dims->n_tasks; s.J = dims->n_jobs; s.Q = dims->n_queues; s.C = dims->n_classes;
+  s.R = dims->n_dims; s.K = dims->n_kdims; s.Wl = dims->label_words; s.Wt = dims->taint_words; s.NR = dims->n_roles;
+  const size_t N = s.N, T = s.T, J = s.J, Q = s.Q, C = s.C, R = s.R, K = s.K;
+  copy_in(s.alloc, nd->allocatable, R * N); copy_in(s.idle, nd->idle, R * N); copy_in(s.used, nd->used, R * N);
+  copy_in(s.rel, nd->releasing, R * N); copy_in(s.pip, nd->pipelined, R * N);
+  copy_in(s.kalloc, nd->k8s_allocatable, K * N); copy_in(s.kreq, nd->k8s_requested, K * N);
+  copy_in(s.knz, nd->k8s_nonzero_requested, K * N);
+  copy_in(s.max_tasks, nd->max_tasks, N); copy_in(s.pod_count, nd->pod_count, N);
+  copy_in(s.zone, nd->revocable_zone, N, (int32_t)-1);
+  copy_in(s.labels, nd->label_bits, (size_t)s.Wl * N); copy_in(s.thard, nd->taint_hard, (size_t)s.Wt * N);
+  copy_in(s.tsoft, nd->taint_soft, (size_t)s.Wt * N); copy_in(s.nflags, nd->flags, N);
+  copy_in(s.zone_active, nd->zone_active, (size_t)dims->n_zones);
+  copy_in(s.req, tk->resreq, R * T); copy_in(s.req_has, tk->req_has, T);
+  copy_in(s.tkreq, tk->k8s_req, K * T); copy_in(s.tknz, tk->k8s_nonzero_req, K * T);
+  copy_in(s.t_job, tk->job, T); copy_in(s.t_class, tk->klass, T); copy_in(s.t_role, tk->role, T);
+  copy_in(s.t_prio, tk->priority, T); copy_in(s.t_podidx, tk->pod_index, T, (int64_t)-1);
+  copy_in(s.t_ts, tk->creation_ts, T); copy_in(s.t_uid, tk->uid_rank, T);
+  s.t_status.assign(T, kPending);
+  s.t_node.assign(T, -1);
+  copy_in(s.c_sel, cl->selector, C * s.Wl); copy_in(s.c_naff, cl->n_affinity, C);
+  copy_in(s.c_aff, cl->affinity, C * VC_MAX_TERMS * s.Wl); copy_in(s.c_tolh, cl->tolerated_hard, C * s.Wt);
+  copy_in(s.c_tols, cl->tolerated_soft, C * s.Wt); copy_in(s.c_npref, cl->n_preferred, C);
+  copy_in(s.c_pref, cl->preferred, C * VC_MAX_TERMS * s.Wl); copy_in(s.c_prefw, cl->preferred_weight, C * VC_MAX_TERMS);
+  copy_in(s.c_flags, cl->flags, C);
+  copy_in(s.j_queue, jb->queue, J); copy_in(s.j_min, jb->min_available, J); copy_in(s.j_prio, jb->priority, J);
+  copy_in(s.j_ts, jb->creation_ts, J); copy_in(s.j_uid, jb->uid_rank, J); copy_in(s.j_flags, jb->flags, J);
+  copy_in(s.j_ntasks, jb->n_tasks_total, J); copy_in(s.j_ready, jb->ready_num, J);
+  copy_in(s.j_waiting, jb->waiting_num, J); copy_in(s.j_pbe, jb->pending_besteffort, J);
+  copy_in(s.j_valid, jb->valid_num, J); copy_in(s.j_taskmintotal, jb->task_min_total, J);
+  copy_in(s.j_roleoff, jb->role_off, J + 1); copy_in(s.j_alloc, jb->allocated, R * J);
+  const size_t NR = s.NR;
+  copy_in(s.r_min, jb->role_min, NR); copy_in(s.r_occ, jb->role_occupied, NR); copy_in(s.r_pip, jb->role_pipelined, NR);
+  copy_in(s.r_pending, jb->role_pending_other, NR); copy_in(s.r_valid, jb->role_valid, NR);
+  copy_in(s.r_flags, jb->role_flags, NR);
+  s.r_failed.assign(NR, 0);
+  for (size_t t = 0; t < T; ++t) s.r_pending[s.t_role[t]] += 1;  // pending[role], job_info.go:936-939
+  copy_in(s.q_weight, qu->weight, Q); copy_in(s.q_prio, qu->priority, Q); copy_in(s.q_ts, qu->creation_ts, Q);
+  copy_in(s.q_uid, qu->uid_rank, Q); copy_in(s.q_flags, qu->flags, Q);
+  s.q_cap.resize(Q); s.q_guar.resize(Q); s.q_alloc0.resize(Q); s.q_req0.resize(Q);
+  s.q_cap_any.assign(Q, 0); s.q_guar_any.assign(Q, 0);
+  for (size_t q = 0; q < Q; ++q) {
+    uint32_t ch = qu->capability_has ? qu->capability_has[q] : 0, gh = qu->guarantee_has ? qu->guarantee_has[q] : 0;
+    s.q_cap_any[q] = (ch & VC_RES_HAS_ANY) != 0;
+    s.q_guar_any[q] = (gh & VC_RES_HAS_ANY) != 0;
+    s.q_cap[q] = res_from_soa(qu->capability, (int)Q, (int)q, (int)R, ch);
+    s.q_guar[q] = res_from_soa(qu->guarantee, (int)Q, (int)q, (int)R, gh);
+    s.q_alloc0[q] = res_from_soa(qu->allocated, (int)Q, (int)q, (int)R, qu->allocated_has ? qu->allocated_has[q] : 0);
+    s.q_req0[q] = res_from_soa(qu->request, (int)Q, (int)q, (int)R, qu->request_has ? qu->request_has[q] : 0);
+  }
+  for (int i = 0; i < conf->n_plugins; ++i)
+    if (conf->plugins[i].plugin > 0 && conf->plugins[i].plugin < 128) s.has_plugin[conf->plugins[i].plugin] = true;
+  // ssn.TotalResource = sum of Allocatable (framework/session.go:272-274); a scalar is a key of the
+  // sum when any node carries it (node vectors are dense: every dim is a key of every node)
+  for (int d = 0; d < s.R; ++d) {
+    double acc = 0;
+    for (int n = 0; n < s.N; ++n) acc += at(s.alloc, d, s.N, n);
+    s.total.v[d] = acc;
+    if (d >= 2 && s.N > 0) { s.total.has |= 1u << d; s.total.nilmap = false; }
+  }
+  s.j_share.assign(J, 0.0);
+  if (s.has_plugin[VC_PLUGIN_DRF])
+    for (int j = 0; j < s.J; ++j) drf_update_share(s, j);  // drf.go:186-214
+  proportion_open(s);
+  s.pool = new Pool(threads);
+  return sp;
+}
+
+}  // namespace
+
+// =======================================================================================
+// C interface (ctypes)
+// =======================================================================================
+extern "C" {
+
+void *vco_session_create(const vc_dims *dims, const vc_nodes *nd, const vc_tasks *tk, const vc_classes *cl,
+                         const vc_jobs *jb, const vc_queues *qu, const vc_conf *conf, int threads) {
+  return load(dims, nd, tk, cl, jb, qu, conf, threads);
+}
+void vco_session_destroy(void *h) { delete (Session *)h; }
+int vco_allocate_run(void *h) { return allocate_execute(*(Session *)h); }
+size_t vco_num_decisions(void *h) { return ((Session *)h)->decisions.size(); }
+const vc_decision *vco_decisions(void *h) { return ((Session *)h)->decisions.data(); }
+size_t vco_num_visits(void *h) { return ((Session *)h)->visits.size(); }
+const vc_visit *vco_visits(void *h) { return ((Session *)h)->visits.data(); }
+size_t vco_num_fit_errors(void *h) { return ((Session *)h)->fit_errors.size(); }
+const int32_t *vco_fit_errors(void *h) { return ((Session *)h)->fit_errors.data(); }
+int64_t vco_num_sweeps(void *h) { return ((Session *)h)->sweeps; }
+void vco_score_matrix(void *h, uint64_t *mask_out, double *score_out, double *best_score, int32_t *best_node) {
+  score_matrix(*(Session *)h, mask_out, score_out, best_score, best_node);
+}
+void vco_queue_deserved(void *h, double *deserved_out, double *share_out) {
+  Session &s = *(Session *)h;
+  for (int q = 0; q < s.Q; ++q) {
+    for (int d = 0; d < s.R; ++d)
+      deserved_out[(size_t)d * s.Q + q] = (d < 2 || (s.qattr[q].deserved.has & (1u << d))) ? s.qattr[q].deserved.v[d] : 0.0;
+    share_out[q] = s.qattr[q].share;
+  }
+}
+// node state after the run (for round-trip checks): idle/used/pipelined [R][N]
+void vco_node_state(void *h, double *idle, double *used, double *pipelined) {
+  Session &s = *(Session *)h;
+  size_t n = (size_t)s.R * s.N;
+  if (idle) std::memcpy(idle, s.idle.data(), n * sizeof(double));
+  if (used) std::memcpy(used, s.used.data(), n * sizeof(double));
+  if (pipelined) std::memcpy(pipelined, s.pip.data(), n * sizeof(double));
+}
+
+// ---- primitives for the reference's known-answer tests ---------------------------------
+// Resource.LessEqual (api/resource_info_test.go:609 TestLessEqual)
+int vco_less_equal(const double *l, uint32_t l_has, const double *r, uint32_t r_has, int R, int infinity) {
+  if (!le_eps(l[0], r[0])) return 0;
+  if (!le_eps(l[1], r[1])) return 0;
+  if (infinity) {  // :444-450
+    for (int d = 2; d < R; ++d)
+      if ((r_has & (1u << d)) && !(l_has & (1u << d))) return 0;
+  }
+  for (int d = 2; d < R; ++d) {
+    if (!(l_has & (1u << d))) continue;
+    bool ok = (r_has & (1u << d)) != 0;
+    if (!ok && infinity) continue;
+    double rv = ok ? r[d] : 0.0;
+    if (!le_eps(l[d], rv)) return 0;
+  }
+  return 1;
+}
+int32_t vco_num_feasible_nodes(int32_t n, int32_t pct, int32_t min_nodes, int32_t min_pct) {
+  return num_feasible_nodes_to_find(n, pct, min_nodes, min_pct);
+}
+int64_t vco_least_requested_score(int64_t requested, int64_t capacity) { return least_requested_score(requested, capacity); }
+int64_t vco_most_requested_score(int64_t requested, int64_t capacity) { return most_requested_score(requested, capacity); }
+// single (task,node) scores on the opening snapshot
+double vco_binpack_score(void *h, int t, int n) { return binpack_score(*(Session *)h, t, n); }
+double vco_nodeorder_score(void *h, int t, int n) { return nodeorder_score(*(Session *)h, t, n); }
+int64_t vco_least_allocated(void *h, int t, int n) { return least_allocated(*(Session *)h, t, n); }
+int64_t vco_most_allocated(void *h, int t, int n) { return most_allocated(*(Session *)h, t, n); }
+int64_t vco_balanced_allocation(void *h, int t, int n) { return balanced_allocation(*(Session *)h, t, n); }
+int vco_predicate(void *h, int t, int n) { return predicate(*(Session *)h, t, n) ? 1 : 0; }
+double vco_job_share(void *h, int j) { return ((Session *)h)->j_share[j]; }
+int vco_job_ready(void *h, int j) { return job_ready(*(Session *)h, j) ? 1 : 0; }
+
+}  // extern "C"

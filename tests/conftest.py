@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle_engine():
+    """Snapshot -> AllocateResult through the CPU oracle (test infrastructure)."""
+    from oracle.pyoracle import OracleSession
+    from volcano_b200.uthelper import AllocateResult
+
+    def run(snap, threads=1):
+        s = OracleSession(snap, threads=threads)
+        dec, vis, fe = s.allocate()
+        s.close()
+        return AllocateResult(dec, vis, fe)
+
+    return run

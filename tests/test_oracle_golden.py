@@ -1,0 +1,94 @@
+"""Pin the CPU oracle against the reference's own golden vectors (tests/golden/reference_cases.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from oracle.pyoracle import OracleSession
+from tests.golden import reference_cases as G
+from volcano_b200.snapshot import PluginOption, SchedulerConf, build_conf, encode_cluster
+from volcano_b200.uthelper import TestCommonStruct
+
+
+@pytest.mark.parametrize("case", G.allocate_cases(), ids=lambda c: c.Name[:40])
+def test_allocate_cases(case, oracle_engine):
+    case.RegisterSession(G.allocate_tiers())
+    case.Run(oracle_engine)
+    assert case.CheckAll() is None, case.CheckAll()
+
+
+@pytest.mark.parametrize("case", G.fareshare_cases(), ids=lambda c: c.Name[:40])
+def test_fareshare_cases(case, oracle_engine):
+    case.RegisterSession(G.fareshare_tiers())
+    case.Run(oracle_engine)
+    assert case.CheckAll() is None, case.CheckAll()
+
+
+@pytest.mark.parametrize("case,weights", G.nodeorder_cases(), ids=lambda c: getattr(c, "Name", "w")[:40])
+def test_nodeorder_cases(case, weights, oracle_engine):
+    case.RegisterSession(G.nodeorder_tiers(**weights))
+    case.Run(oracle_engine)
+    assert case.CheckAll() is None, case.CheckAll()
+
+
+@pytest.mark.parametrize("args,expected", G.BINPACK_CASES)
+def test_binpack_scores(args, expected):
+    tc = TestCommonStruct(Name="binpack", **G.binpack_cluster())
+    snap = tc.RegisterSession([[PluginOption.make("binpack", arguments=args, EnabledNodeOrder=True)]])
+    s = OracleSession(snap)
+    L = pyoracle.lib()
+    for t, key in enumerate(snap.task_keys):
+        for n, node in enumerate(snap.node_names):
+            got = L.vco_binpack_score(s.h, t, n)
+            assert abs(got - expected[key][node]) <= G.BINPACK_EPS, (key, node, got)
+    s.close()
+
+
+def test_binpack_arguments():
+    args, want = G.BINPACK_ARGUMENTS
+    dims = ["cpu", "memory", "example.com/foo", "nvidia.com/gpu", "pods"]
+    c = build_conf(SchedulerConf(tiers=[[PluginOption.make("binpack", arguments=args, EnabledNodeOrder=True)]]),
+                   dims, ("cpu", "memory", "nvidia.com/gpu"))
+    assert c.binpack_weight == want["weight"]
+    got = {d: c.binpack_dim_weight[i] for i, d in enumerate(dims)}
+    assert got == {"cpu": 5, "memory": 2, "example.com/foo": 1, "nvidia.com/gpu": 7, "pods": -1}
+
+
+@pytest.mark.parametrize("pct,n,want", G.NUM_FEASIBLE)
+def test_num_feasible_nodes(pct, n, want):
+    assert pyoracle.lib().vco_num_feasible_nodes(n, pct, 100, 5) == want
+
+
+def _res(r, names):
+    cpu, mem, sc = r
+    v = np.zeros(2 + len(names))
+    v[0], v[1] = cpu, mem
+    has = 0
+    for i, nm in enumerate(names):
+        if sc and nm in sc:
+            v[2 + i] = sc[nm]
+            has |= 1 << (2 + i)
+    return v, has
+
+
+@pytest.mark.parametrize("table,infinity", [(G.LESS_EQUAL_ZERO, 0), (G.LESS_EQUAL_INFINITY, 1)])
+def test_less_equal(table, infinity):
+    names = ["hugepages-test", "scalar.test/scalar1"]
+    dp = C.POINTER(C.c_double)
+    for l, r, want in table:
+        lv, lh = _res(l, names)
+        rv, rh = _res(r, names)
+        got = pyoracle.lib().vco_less_equal(lv.ctypes.data_as(dp), lh, rv.ctypes.data_as(dp), rh, 4, infinity)
+        assert bool(got) == want, (l, r, infinity)
+
+
+def test_upstream_score_sanity():
+    """recalled kube-scheduler formulas vs the reference's placement goldens."""
+    L = pyoracle.lib()
+    gi = 1 << 30
+    # leastAllocated n1(2c,4Gi) vs n2(4c,8Gi), pod 1c/1G: (50*50+76*50)/100=63 vs (75*50+88*50)/100=81
+    assert (L.vco_least_requested_score(1000, 2000) * 50 + L.vco_least_requested_score(10**9, 4 * gi) * 50) // 100 == 63
+    assert (L.vco_least_requested_score(1000, 4000) * 50 + L.vco_least_requested_score(10**9, 8 * gi) * 50) // 100 == 81
+    assert (L.vco_most_requested_score(1000, 2000) + L.vco_most_requested_score(10**9, 4 * gi)) // 2 == 36
+    assert (L.vco_most_requested_score(1000, 4000) + L.vco_most_requested_score(10**9, 8 * gi)) // 2 == 18

@@ -1,0 +1,85 @@
+"""Mirror of the reference's action-test harness, pkg/scheduler/uthelper/helper.go:60-296.
+
+`TestCommonStruct` keeps the reference's field names (Name, Plugins, Pods, Nodes, PodGroups,
+Queues, ExpectBindMap, ExpectBindsNum, ExpectPipeLined) so a reference test case can be
+transcribed literally.  RegisterSession(tiers) ~ framework.OpenSession with explicit tiers
+(helper.go:127-132); Run(engine) ~ action.Execute(ssn) where `engine` is any callable
+Snapshot -> AllocateResult (the CUDA engine in volcano_b200.engine, or the CPU oracle in
+tests); CheckAll ~ helper.go:239-296 with the FakeBinder (util/test_utils.go:544-588)
+replaced by replaying the returned Statement operations.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import abi
+from .api import Node, Pod, PodGroup, Queue
+from .snapshot import PluginOption, SchedulerConf, Snapshot, encode_cluster
+
+
+@dataclass
+class AllocateResult:
+    decisions: np.ndarray   # structured: task,node,kind,visit,score
+    visits: np.ndarray      # structured: job,outcome,first_op,n_ops
+    fit_errors: np.ndarray  # int32 task indices
+    stats: Optional[dict] = None
+
+
+@dataclass
+class TestCommonStruct:
+    __test__ = False  # not a pytest class
+    Name: str = ""
+    Plugins: Optional[dict] = None  # reference: name -> PluginBuilder; informational here
+    Pods: List[Pod] = field(default_factory=list)
+    Nodes: List[Node] = field(default_factory=list)
+    PodGroups: List[PodGroup] = field(default_factory=list)
+    Queues: List[Queue] = field(default_factory=list)
+    ExpectBindMap: Dict[str, str] = field(default_factory=dict)
+    ExpectBindsNum: Optional[int] = None
+    ExpectPipeLined: Optional[Dict[str, List[str]]] = None  # job -> node names
+    TdmZoneActive: Optional[Dict[str, bool]] = None
+
+    def RegisterSession(self, tiers: Sequence[Sequence[PluginOption]], actions=("allocate",), **conf_kw) -> Snapshot:
+        self.conf = SchedulerConf(tiers=[list(t) for t in tiers], actions=tuple(actions), **conf_kw)
+        self.snap = encode_cluster(self.Nodes, self.Pods, self.PodGroups, self.Queues, self.conf,
+                                   tdm_zone_active=self.TdmZoneActive)
+        return self.snap
+
+    def Run(self, engine: Callable[[Snapshot], AllocateResult]) -> AllocateResult:
+        self.result = engine(self.snap)
+        # FakeBinder: Statement.Commit -> cache.AddBindTask for every Allocate op (statement.go:309-325)
+        self.binds: Dict[str, str] = {}
+        self.pipelined: Dict[str, List[str]] = {}
+        dec, vis = self.result.decisions, self.result.visits
+        for v in vis:
+            ops = dec[v["first_op"]: v["first_op"] + v["n_ops"]]
+            for op in ops:
+                key = self.snap.task_keys[op["task"]]
+                node = self.snap.node_names[op["node"]]
+                if op["kind"] == abi.VC_OP_ALLOCATE and v["outcome"] == abi.VC_VISIT_COMMIT:
+                    self.binds[key] = node
+                elif op["kind"] == abi.VC_OP_PIPELINE:
+                    self.pipelined.setdefault(self.snap.job_names[v["job"]], []).append(node)
+        return self.result
+
+    def CheckBind(self) -> Optional[str]:
+        if self.ExpectBindsNum is not None and len(self.binds) != self.ExpectBindsNum:
+            return f"case {self.Name!r}: expected {self.ExpectBindsNum} binds, got {len(self.binds)}: {self.binds}"
+        if self.binds != dict(self.ExpectBindMap):
+            return f"case {self.Name!r}: expected bind map {self.ExpectBindMap}, got {self.binds}"
+        return None
+
+    def CheckPipelined(self) -> Optional[str]:
+        if self.ExpectPipeLined is None:
+            return None
+        got = {k: sorted(v) for k, v in self.pipelined.items()}
+        want = {k: sorted(v) for k, v in self.ExpectPipeLined.items()}
+        if got != want:
+            return f"case {self.Name!r}: expected pipelined {want}, got {got}"
+        return None
+
+    def CheckAll(self) -> Optional[str]:
+        return self.CheckBind() or self.CheckPipelined()
