@@ -297,21 +297,30 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out);
 /* Dense task x node pass on the opening snapshot: feasibility bit (allocate.predicate,
    allocate.go:816-824), total score (util.PrioritizeNodes) of every feasible pair and
    per-task best (score, node) under the canonical tie-break (lowest NodeList index).
-   mask_out: device or host? -> HOST buffers, may be NULL to keep results on the device
-   (used by bench to time the kernel alone).
+   All outputs are HOST buffers (any may be NULL):
      mask_out  [T][ceil(N/64)] uint64, bit n of row t
      score_out [T][N] double (0.0 where infeasible)
      best_score[T] double, best_node[T] int32 (-1 = no feasible node)          */
 int vc_score_matrix(vc_snapshot *s, uint64_t *mask_out, double *score_out, double *best_score,
                     int32_t *best_node);
-/* Same pass, outputs stay in HBM; returns the CUDA-event time of the kernel alone. */
-int vc_score_matrix_device(vc_snapshot *s, int repeats, double *kernel_ms_out,
-                           int64_t *algorithmic_bytes_out);
-/* Per-task best (score,node) packed for a MAX all-reduce across node shards:
-   key = orderable(score) << 32 | (0xffffffff - node). Device pointer, T entries. */
-int vc_best_keys_device(vc_snapshot *s, uint64_t **keys_dev_out);
-int vc_best_keys_unpack(vc_snapshot *s, const uint64_t *keys_host, double *best_score,
-                        int32_t *best_node);
+/* Same pass with the outputs kept in HBM, run `repeats` times; returns CUDA-event times measured on the
+   launching stream: kernel_ms_out[0] = mean of the whole dense pass (K1a + best + K1b),
+   kernel_ms_out[1] = mean of the materialising kernel K1b alone; *algorithmic_bytes_out = the bytes of
+   SURVEY.md §8(d): T*N*(8 + 1/8) + per-task and per-node operand bytes. */
+int vc_score_matrix_device(vc_snapshot *s, int repeats, double *kernel_ms_out, int64_t *algorithmic_bytes_out);
+
+/* Node-sharded dense pass, one process per GPU, tasks replicated:
+     vc_dense_begin   K1a on this shard (per group: any idle-fit / future-fit node, max soft-taint count)
+     vc_dense_stats   device pointer to those int32 counters so the caller can MAX-all-reduce them (NCCL)
+     vc_dense_finish  per-task best (score,node) of this shard [+ materialised shard of the matrix]
+     vc_dense_best    device pointers to best_score[T] (f64) / best_node[T] (i32; -1 none) for the
+                      cross-shard arg-max (all-gather + fold, or two all-reduces)            */
+int vc_dense_begin(vc_snapshot *s);
+int vc_dense_stats(vc_snapshot *s, int32_t **stats_dev_out, int32_t *count_out);
+int vc_dense_finish(vc_snapshot *s, int materialize);
+int vc_dense_best(vc_snapshot *s, double **best_score_dev_out, int32_t **best_node_dev_out);
+/* copy the materialised matrix of the last vc_dense_finish(.,1) to host buffers (any may be NULL) */
+int vc_dense_fetch(vc_snapshot *s, uint64_t *mask_out, double *score_out, double *best_score, int32_t *best_node);
 
 /* proportion's per-queue deserved / share after session open (plugins/proportion/
    proportion.go:197-264), for parity checks: [R][Q] and [Q]. */

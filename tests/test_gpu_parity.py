@@ -1,0 +1,143 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libvcalloc.so), against the CPU oracle
+and the reference's golden vectors.  Placements must be identical (same node per task, same order, same
+visit outcomes); fp64 scores must agree within 1e-6 (north_star) — in practice they are bit-equal because
+both sides execute the same IEEE operations in the same order."""
+import numpy as np
+import pytest
+
+from tests.golden import reference_cases as G
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from volcano_b200 import engine
+    engine.init(0)
+    return engine
+
+
+def _assert_same(a, b):
+    assert len(a.visits) == len(b.visits), (len(a.visits), len(b.visits))
+    assert np.array_equal(a.visits["job"], b.visits["job"])
+    assert np.array_equal(a.visits["outcome"], b.visits["outcome"])
+    assert np.array_equal(a.visits["n_ops"], b.visits["n_ops"])
+    assert np.array_equal(a.visits["first_op"], b.visits["first_op"])
+    assert len(a.decisions) == len(b.decisions)
+    for f in ("task", "node", "kind", "visit"):
+        assert np.array_equal(a.decisions[f], b.decisions[f]), f
+    assert np.allclose(a.decisions["score"], b.decisions["score"], rtol=0, atol=SCORE_TOL)
+    assert np.array_equal(a.fit_errors, b.fit_errors)
+
+
+@pytest.mark.parametrize("case", G.allocate_cases(), ids=lambda c: c.Name[:40])
+def test_allocate_goldens(case, gpu, oracle_engine):
+    snap = case.RegisterSession(G.allocate_tiers())
+    case.Run(gpu.gpu_engine)
+    assert case.CheckAll() is None, case.CheckAll()
+    _assert_same(case.result, oracle_engine(snap))
+
+
+@pytest.mark.parametrize("case", G.fareshare_cases(), ids=lambda c: c.Name[:40])
+def test_fareshare_goldens(case, gpu, oracle_engine):
+    snap = case.RegisterSession(G.fareshare_tiers())
+    case.Run(gpu.gpu_engine)
+    assert case.CheckAll() is None, case.CheckAll()
+    _assert_same(case.result, oracle_engine(snap))
+
+
+@pytest.mark.parametrize("case,weights", G.nodeorder_cases(), ids=lambda c: getattr(c, "Name", "w")[:40])
+def test_nodeorder_goldens(case, weights, gpu, oracle_engine):
+    snap = case.RegisterSession(G.nodeorder_tiers(**weights))
+    case.Run(gpu.gpu_engine)
+    assert case.CheckAll() is None, case.CheckAll()
+    _assert_same(case.result, oracle_engine(snap))
+
+
+@pytest.mark.parametrize("args,expected", G.BINPACK_CASES)
+def test_binpack_goldens(args, expected, gpu):
+    """binpack_test.go:100-238: exact scores through the dense pass (only binpack registered)."""
+    from volcano_b200.snapshot import PluginOption
+    from volcano_b200.uthelper import TestCommonStruct
+    tc = TestCommonStruct(Name="binpack", **G.binpack_cluster())
+    snap = tc.RegisterSession([[PluginOption.make("binpack", arguments=args, EnabledNodeOrder=True)]])
+    e = gpu.Engine(snap)
+    e.upload()
+    mask, score, bs, bn = e.score_matrix()
+    e.close()
+    for t, key in enumerate(snap.task_keys):
+        for n, node in enumerate(snap.node_names):
+            feasible = bool((mask[t, n // 64] >> np.uint64(n % 64)) & np.uint64(1))
+            want = expected[key][node]
+            if feasible:
+                assert abs(score[t, n] - want) <= G.BINPACK_EPS, (key, node, score[t, n])
+            else:
+                assert want == 0  # infeasible pairs are exactly the reference's zero-score pairs here
+
+
+@pytest.mark.parametrize("cfg,seed", [("tiny", 1), ("tiny", 2), ("tiny", 3), ("small", 1), ("cfg1", None), ("small", 7)])
+def test_allocate_vs_oracle(cfg, seed, gpu, oracle_engine):
+    from volcano_b200.synth import make_snapshot
+    snap = make_snapshot(cfg, seed)
+    res = gpu.gpu_engine(snap)
+    ref = oracle_engine(snap, threads=4)
+    _assert_same(res, ref)
+    assert len(res.decisions) > 0
+
+
+@pytest.mark.parametrize("cfg,seed", [("tiny", 1), ("small", 2), ("cfg1", None)])
+def test_score_matrix_vs_oracle(cfg, seed, gpu):
+    from oracle.pyoracle import OracleSession
+    from volcano_b200.synth import make_snapshot
+    snap = make_snapshot(cfg, seed)
+    e = gpu.Engine(snap)
+    e.upload()
+    mask, score, bs, bn = e.score_matrix()
+    e.close()
+    o = OracleSession(snap)
+    omask, oscore, obs, obn = o.score_matrix()
+    o.close()
+    assert np.array_equal(mask, omask)
+    assert np.array_equal(bn, obn)
+    assert np.allclose(score, oscore, rtol=0, atol=SCORE_TOL)
+    assert np.allclose(bs, obs, rtol=0, atol=SCORE_TOL)
+    assert np.array_equal(score, oscore), "scores are expected to be bit-identical"
+
+
+def test_deserved_vs_oracle(gpu):
+    from oracle.pyoracle import OracleSession
+    from volcano_b200.synth import make_snapshot
+    snap = make_snapshot("small", 3)
+    e = gpu.Engine(snap)
+    e.upload()
+    des, share = e.queue_deserved()
+    e.close()
+    o = OracleSession(snap)
+    odes, oshare = o.queue_deserved()
+    o.close()
+    assert np.array_equal(des, odes) and np.array_equal(share, oshare)
+
+
+def test_full_size_properties(gpu):
+    """BASELINE configs[1] (10k x 100k): size-independent properties — every decision respects capacity,
+    re-running is idempotent, gang minAvailable holds for every committed job."""
+    from volcano_b200.synth import make_snapshot
+    snap = make_snapshot("cfg2")
+    e = gpu.Engine(snap)
+    e.upload()
+    r1 = e.allocate()
+    r2 = e.allocate()
+    e.close()
+    assert np.array_equal(r1.decisions, r2.decisions) and np.array_equal(r1.visits, r2.visits)
+    dec = r1.decisions
+    assert len(np.unique(dec["task"])) == len(dec)  # a task is placed at most once
+    used = snap.n_used.copy()
+    np.add.at(used.T, dec["node"], snap.t_resreq.T[dec["task"]])
+    assert (used <= snap.n_allocatable + 0.1).all()  # no node over-committed on any dimension
+    # gang: committed allocations per job >= minAvailable
+    committed = r1.visits["outcome"][dec["visit"]] == 0
+    per_job = np.bincount(snap.t_job[dec["task"][committed]], minlength=snap.J)
+    jobs_committed = np.unique(r1.visits["job"][r1.visits["outcome"] == 0])
+    assert (per_job[jobs_committed] >= snap.j_min_available[jobs_committed]).all()

@@ -197,8 +197,11 @@ SYMBOLS = {
     "vc_allocate_run": (C.c_int, [_vp, C.POINTER(_vp)]),
     "vc_score_matrix": (C.c_int, [_vp, _u64p, _dp, _dp, _i32p]),
     "vc_score_matrix_device": (C.c_int, [_vp, C.c_int, _dp, _i64p]),
-    "vc_best_keys_device": (C.c_int, [_vp, C.POINTER(_vp)]),
-    "vc_best_keys_unpack": (C.c_int, [_vp, _u64p, _dp, _i32p]),
+    "vc_dense_begin": (C.c_int, [_vp]),
+    "vc_dense_stats": (C.c_int, [_vp, C.POINTER(_i32p), C.POINTER(C.c_int32)]),
+    "vc_dense_finish": (C.c_int, [_vp, C.c_int]),
+    "vc_dense_best": (C.c_int, [_vp, C.POINTER(_dp), C.POINTER(_i32p)]),
+    "vc_dense_fetch": (C.c_int, [_vp, _u64p, _dp, _dp, _i32p]),
     "vc_queue_deserved": (C.c_int, [_vp, _dp, _dp]),
     "vc_result_num_decisions": (C.c_size_t, [_vp]),
     "vc_result_decisions": (C.POINTER(vc_decision), [_vp]),

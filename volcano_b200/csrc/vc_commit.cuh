@@ -1,0 +1,867 @@
+// vc_commit.cuh — K2, the persistent cooperative commit kernel.
+//
+// One launch per scheduling cycle executes the reference's whole allocate action
+// (actions/allocate/allocate.go:283-348, :558-694) with its exact sequential semantics:
+//
+//   * the node axis is partitioned over the CTAs (one CTA per SM); every CTA keeps the mutable state
+//     of its nodes (Idle / Used / Pipelined / k8s requested / pod count) in SHARED MEMORY for the
+//     whole cycle, one node per thread, dimension-major so a warp reads consecutive banks;
+//   * the control state (queue order, job order, gang counters, drf / proportion shares, Statement
+//     undo log) is REPLICATED: every CTA runs the same deterministic control code on its own copy, so
+//     the only cross-CTA traffic per placement is one all-gather of 48-byte records through an
+//     L2-resident mailbox (no grid barrier, no broadcast hop);
+//   * per task: every thread evaluates predicate + score of its node, warp-shuffle arg-max, one
+//     mailbox exchange, all CTAs derive the same winner, the owner thread mutates its node row.
+//
+// Bound: latency (mailbox round trip + fp64 dependency chain per step), not HBM — see DESIGN.md.
+#pragma once
+#include "vc_device.cuh"
+
+struct HeapEnt {  // a re-pushed job with the key it had when pushed (keys are stable inside the PQ)
+  double share;
+  int32_t job;
+  int32_t prio;
+  uint32_t rank;
+  uint32_t bits;  // bit0 ready, bit1 preemptable
+};
+
+struct K2Params {
+  DevDims d;
+  DevConf c;
+  int npc;    // nodes per CTA
+  int n_cta;  // CTAs that take part in the exchange (== gridDim.x)
+  int max_job_tasks;
+  // nodes (master copies in HBM; dynamic ones are written back at the end)
+  const double *alloc, *rel, *kalloc;
+  double *idle, *used, *pip, *kreq, *knz;
+  const int32_t *max_tasks;
+  int32_t *pod_count;
+  const uint32_t *cstat;
+  // tasks
+  const double *req, *tkreq, *tknz;
+  const uint32_t *req_has;
+  const int32_t *t_class, *t_role;
+  const int32_t *task_order, *job_task_off;
+  // jobs
+  const int32_t *j_queue, *j_min, *j_ntasks, *j_pbe, *j_taskmintotal, *j_roleoff, *j_prio, *j_ready0, *j_waiting0;
+  const uint32_t *j_flags, *j_rank;
+  const double *j_alloc0, *j_share0;
+  const int32_t *r_min, *r_occ0, *r_pip0, *r_pending0;
+  const uint32_t *r_flags;
+  // queues
+  const int32_t *q_prio;
+  const uint32_t *q_rank, *q_flags, *q_alloc_has0, *q_des_has, *q_flags2;  // q_flags2: bit0 attr exists, bit1 alloc nil map
+  const double *q_alloc0, *q_des, *q_share0;
+  const int32_t *qjobs_off, *qjobs;
+  double total[VC_MAX_DIMS];
+  uint32_t total_has;
+  // per-CTA replicas of the mutable control state
+  int32_t *rep_i32;
+  size_t rep_i32_stride;
+  double *rep_f64;
+  size_t rep_f64_stride;
+  HeapEnt *rep_heap;
+  size_t rep_heap_stride;
+  // mailbox [2 parity][3 units][n_cta]
+  uint4 *mbox;
+  // outputs
+  vc_decision *decisions;
+  vc_visit *visits;
+  int32_t *fit_errors;
+  int32_t *counters;  // 0 n_decisions, 1 n_visits, 2 n_fit_errors, 3 n_steps, 4 error
+};
+
+// ---------------------------------------------------------------------------------------
+// shared-memory resident node slice of one CTA
+// ---------------------------------------------------------------------------------------
+struct SmemNodes {
+  double *alloc, *idle, *used, *rel, *pip, *kalloc, *kreq, *knz;  // [dims][cap]
+  int32_t *max_tasks, *pod_count;
+  unsigned long long *nerr;  // predicate-error cache bits per role of the current visit
+  int cap;
+};
+struct SmemNodeView {
+  const SmemNodes &s;
+  int i;
+  __device__ __forceinline__ double alloc(int d) const { return s.alloc[d * s.cap + i]; }
+  __device__ __forceinline__ double idle(int d) const { return s.idle[d * s.cap + i]; }
+  __device__ __forceinline__ double used(int d) const { return s.used[d * s.cap + i]; }
+  __device__ __forceinline__ double rel(int d) const { return s.rel[d * s.cap + i]; }
+  __device__ __forceinline__ double pip(int d) const { return s.pip[d * s.cap + i]; }
+  __device__ __forceinline__ double kalloc(int k) const { return s.kalloc[k * s.cap + i]; }
+  __device__ __forceinline__ double kreq(int k) const { return s.kreq[k * s.cap + i]; }
+  __device__ __forceinline__ double knz(int k) const { return s.knz[k * s.cap + i]; }
+};
+
+// ---------------------------------------------------------------------------------------
+// control state of the visit in flight (shared memory, identical in every CTA)
+// ---------------------------------------------------------------------------------------
+struct Ctl {
+  // job under allocation
+  int job, queue, cursor, task_end, ready, waiting, pbe, minav, ntasks_total, taskmintotal, role_base, nroles;
+  uint32_t jflags;
+  double jalloc[VC_MAX_DIMS];
+  double jshare;
+  int r_occ[VC_MAX_JOB_ROLES], r_pip[VC_MAX_JOB_ROLES], r_pending[VC_MAX_JOB_ROLES], r_min[VC_MAX_JOB_ROLES];
+  uint32_t r_flags[VC_MAX_JOB_ROLES];
+  uint8_t r_failed[VC_MAX_JOB_ROLES];
+  // queue attr (proportion.queueAttr)
+  double qalloc[VC_MAX_DIMS], qdes[VC_MAX_DIMS];
+  double qshare;
+  uint32_t qalloc_has, qdes_has, qflags2, qflags;
+  // task under evaluation
+  TaskRec trec;
+  int task, role_local;
+  // exchange result
+  int cnt[2], best_node[2], max_soft[2];
+  double best_score[2];
+  // bookkeeping
+  int n_ops;
+  unsigned seq;
+  int n_dec, n_vis, n_fit, n_steps;
+  // scratch for CTA-level reductions
+  double w_score[2][32];
+  int w_node[2][32];
+  int w_cnt[2][32];
+  int w_soft[2][32];
+  int pick;  // scratch for warp0 -> CTA broadcasts
+  int pick2;
+};
+
+// ---- mailbox --------------------------------------------------------------------------------
+__device__ __forceinline__ void mbox_store(uint4 *p, uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 mbox_load(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+struct Local {  // what one CTA (or one lane while folding) contributes per category
+  double score[2];
+  int node[2];
+  int cnt[2];
+  int soft[2];
+};
+__device__ __forceinline__ void local_init(Local &l) {
+  l.score[0] = l.score[1] = 0.0;
+  l.node[0] = l.node[1] = -1;
+  l.cnt[0] = l.cnt[1] = 0;
+  l.soft[0] = l.soft[1] = 0;
+}
+__device__ __forceinline__ void local_fold(Local &a, const Local &b) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (b.node[k] >= 0 && (a.node[k] < 0 || better(b.score[k], b.node[k], a.score[k], a.node[k]))) {
+      a.score[k] = b.score[k];
+      a.node[k] = b.node[k];
+    }
+    a.cnt[k] += b.cnt[k];
+    a.soft[k] = max(a.soft[k], b.soft[k]);
+  }
+}
+__device__ __forceinline__ void local_warp_reduce(Local &l) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    Local b;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      b.score[k] = __shfl_xor_sync(0xffffffffu, l.score[k], o);
+      b.node[k] = __shfl_xor_sync(0xffffffffu, l.node[k], o);
+      b.cnt[k] = __shfl_xor_sync(0xffffffffu, l.cnt[k], o);
+      b.soft[k] = __shfl_xor_sync(0xffffffffu, l.soft[k], o);
+    }
+    local_fold(l, b);
+  }
+}
+
+// All-gather of one Local per CTA. Called by warp 0 of every CTA with the CTA's folded contribution
+// (identical in all lanes); returns the global fold in all lanes of warp 0.
+__device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigned seq) {
+  const int lane = threadIdx.x & 31;
+  const int G = p.n_cta;
+  uint4 *base = p.mbox + (size_t)(seq & 1u) * 3 * G;
+  if (lane < 3) {
+    uint4 v;
+    if (lane < 2) {
+      unsigned long long sb = (unsigned long long)__double_as_longlong(mine.score[lane]);
+      v = make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)mine.node[lane], seq);
+    } else {
+      v = make_uint4((unsigned)mine.cnt[0], (unsigned)mine.cnt[1],
+                     (unsigned)mine.soft[0] | ((unsigned)mine.soft[1] << 16), seq);
+    }
+    mbox_store(base + (size_t)lane * G + blockIdx.x, v);
+  }
+  Local acc;
+  local_init(acc);
+  for (int s = lane; s < G; s += 32) {
+    uint4 a, b, c;
+    do { a = mbox_load(base + s); } while (a.w != seq);
+    do { b = mbox_load(base + (size_t)G + s); } while (b.w != seq);
+    do { c = mbox_load(base + (size_t)2 * G + s); } while (c.w != seq);
+    Local o;
+    o.score[0] = __longlong_as_double((long long)((unsigned long long)a.x | ((unsigned long long)a.y << 32)));
+    o.node[0] = (int)a.z;
+    o.score[1] = __longlong_as_double((long long)((unsigned long long)b.x | ((unsigned long long)b.y << 32)));
+    o.node[1] = (int)b.z;
+    o.cnt[0] = (int)c.x;
+    o.cnt[1] = (int)c.y;
+    o.soft[0] = (int)(c.z & 0xffffu);
+    o.soft[1] = (int)(c.z >> 16);
+    local_fold(acc, o);
+  }
+  local_warp_reduce(acc);
+  return acc;
+}
+
+// ---- replicated control helpers (executed by every thread on shared Ctl; mutations by thread 0) ----
+__device__ __forceinline__ bool ctl_is_ready(const Ctl &s) { return s.ready + s.pbe >= s.minav; }            // job_info.go:1169
+__device__ __forceinline__ bool ctl_is_pipelined(const Ctl &s) { return s.waiting + s.ready + s.pbe >= s.minav; }  // :1173
+__device__ __forceinline__ bool ctl_check_task_ready(const Ctl &s) {  // job_info.go:1024-1036
+  if (s.minav < s.taskmintotal) return true;
+  for (int r = 0; r < s.nroles; ++r)
+    if ((s.r_flags[r] & VC_ROLE_IN_MIN_MAP) && s.r_occ[r] < s.r_min[r]) return false;
+  return true;
+}
+__device__ __forceinline__ bool ctl_check_task_pipelined(const Ctl &s) {  // job_info.go:1039-1070
+  if (s.minav < s.taskmintotal) return true;
+  for (int r = 0; r < s.nroles; ++r)
+    if ((s.r_flags[r] & VC_ROLE_IN_MIN_MAP) && s.r_occ[r] + s.r_pip[r] < s.r_min[r]) return false;
+  return true;
+}
+__device__ __forceinline__ bool ctl_job_ready(const DevConf &c, const Ctl &s) {  // session_plugins.go:428-446
+  for (int i = 0; i < c.n_plugins; ++i)
+    if ((c.enabled[i] & VC_EN_JOB_READY) && c.plugin[i] == VC_PLUGIN_GANG)
+      if (!(ctl_check_task_ready(s) && ctl_is_ready(s))) return false;
+  return true;
+}
+__device__ __forceinline__ bool ctl_job_pipelined(const DevConf &c, const Ctl &s) {  // session_plugins.go:450-478
+  bool has_found = false;
+  int i = 0;
+  while (i < c.n_plugins) {
+    int tier = c.tier[i];
+    for (; i < c.n_plugins && c.tier[i] == tier; ++i) {
+      if (!(c.enabled[i] & VC_EN_JOB_PIPELINED)) continue;
+      int res;
+      if (c.plugin[i] == VC_PLUGIN_GANG) res = (ctl_check_task_pipelined(s) && ctl_is_pipelined(s)) ? 1 : -1;
+      else if (c.plugin[i] == VC_PLUGIN_TDM) res = ctl_is_pipelined(s) ? 1 : -1;
+      else continue;
+      if (res < 0) return false;
+      if (res > 0) has_found = true;
+    }
+    if (has_found) return true;
+  }
+  return true;
+}
+__device__ __forceinline__ bool ctl_need_continue(const Ctl &s) {  // job_info.go:918-966
+  if (s.minav >= s.ntasks_total) return false;
+  if (s.minav < s.taskmintotal) {
+    int left = 0;
+    for (int r = 0; r < s.nroles; ++r)
+      if (!s.r_failed[r]) left += s.r_pending[r];
+    return s.ready + left >= s.minav;
+  }
+  for (int r = 0; r < s.nroles; ++r) {
+    if (!s.r_failed[r]) continue;
+    int mn = (s.r_flags[r] & VC_ROLE_IN_MIN_MAP) ? s.r_min[r] : 0;
+    if (mn == 0) continue;
+    if (s.r_occ[r] < mn) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ double share_of(double l, double r) {  // api/helpers/helpers.go:80-93
+  if (r == 0.0) return l == 0.0 ? 0.0 : 1.0;
+  return l / r;
+}
+__device__ __forceinline__ double drf_share(const K2Params &p, const double *jalloc) {  // drf.go:566-578
+  double res = 0.0;
+  for (int d = 0; d < p.d.R; ++d) {
+    if (d >= 2 && !(p.total_has & (1u << d))) continue;
+    if (!(p.total[d] >= VC_MIN_RESOURCE)) continue;
+    double sh = share_of(jalloc[d], p.total[d]);
+    if (sh > res) res = sh;
+  }
+  return res;
+}
+__device__ __forceinline__ double queue_share(int R, const double *qalloc, uint32_t alloc_has, const double *qdes,
+                                              uint32_t des_has) {  // proportion.go:590-602
+  double res = 0.0;
+  for (int d = 0; d < R; ++d) {
+    if (d >= 2 && !(des_has & (1u << d))) continue;
+    if (!(qdes[d] >= VC_MIN_RESOURCE)) continue;
+    double al = (d < 2 || (alloc_has & (1u << d))) ? qalloc[d] : 0.0;
+    double sh = share_of(al, qdes[d]);
+    if (sh > res) res = sh;
+  }
+  return res;
+}
+// proportion queueAllocatable (proportion.go:333-348) through ssn.Allocatable (session_plugins.go:350-366)
+__device__ __forceinline__ bool ctl_allocatable(const K2Params &p, const Ctl &s) {
+  const DevConf &c = p.c;
+  for (int i = 0; i < c.n_plugins; ++i) {
+    if (!(c.enabled[i] & VC_EN_ALLOCATABLE) || c.plugin[i] != VC_PLUGIN_PROPORTION) continue;
+    if (!(s.qflags & VC_QUEUE_OPEN)) return false;
+    const TaskRec &t = s.trec;
+    bool ok = true;
+    if (t.req[0] > 0.0 && s.qalloc[0] + t.req[0] > s.qdes[0]) ok = false;
+    if (t.req[1] > 0.0 && s.qalloc[1] + t.req[1] > s.qdes[1]) ok = false;
+    const uint32_t rq_has = t.has & ~3u;
+    const bool fu_nil = (s.qflags2 & 2u) && rq_has == 0;
+    if (!fu_nil) {
+      for (int d = 2; d < p.d.R; ++d) {
+        if (!(rq_has & (1u << d)) || d == p.d.pods_dim) continue;
+        double al = (s.qalloc_has & (1u << d)) ? s.qalloc[d] : 0.0;
+        double fu = al + t.req[d];
+        double de = (s.qdes_has & (1u << d)) ? s.qdes[d] : 0.0;
+        if (t.req[d] > 0.0 && fu > de) ok = false;
+      }
+    }
+    if (!ok) return false;
+  }
+  return true;
+}
+
+// ssn.JobOrderFn (session_plugins.go:660-683) on (static keys, ready, share)
+struct JobKey {
+  double share;
+  int prio;
+  uint32_t rank;
+  bool ready, preempt;
+};
+__device__ __forceinline__ bool job_less(const DevConf &c, const JobKey &l, const JobKey &r) {
+  for (int i = 0; i < c.n_plugins; ++i) {
+    if (!(c.enabled[i] & VC_EN_JOB_ORDER)) continue;
+    int cmp = 0;
+    switch (c.plugin[i]) {
+      case VC_PLUGIN_PRIORITY: cmp = l.prio > r.prio ? -1 : (l.prio < r.prio ? 1 : 0); break;
+      case VC_PLUGIN_GANG: cmp = (l.ready && r.ready) ? 0 : (l.ready ? 1 : (r.ready ? -1 : 0)); break;
+      case VC_PLUGIN_DRF: cmp = l.share == r.share ? 0 : (l.share < r.share ? -1 : 1); break;
+      case VC_PLUGIN_TDM: cmp = l.preempt == r.preempt ? 0 : (!l.preempt ? -1 : 1); break;
+      default: break;
+    }
+    if (cmp != 0) return cmp < 0;
+  }
+  return l.rank < r.rank;  // (CreationTimestamp, UID) rank precomputed on the host
+}
+__device__ __forceinline__ JobKey key_of(const HeapEnt &e) {
+  JobKey k;
+  k.share = e.share; k.prio = e.prio; k.rank = e.rank; k.ready = e.bits & 1u; k.preempt = (e.bits & 2u) != 0;
+  return k;
+}
+
+// =======================================================================================
+// the kernel
+// =======================================================================================
+extern __shared__ __align__(16) unsigned char k2_smem[];
+
+__global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
+  const DevConf &c = p.c;
+  const int R = p.d.R, K = p.d.K, N = p.d.N, J = p.d.J, Q = p.d.Q, NR = p.d.NR, T = p.d.T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int cta = blockIdx.x;
+  const int nbase = p.d.node_begin + cta * p.npc;
+  const int nmine = max(0, min(p.npc, p.d.node_end - nbase));
+  const int cap = p.npc;
+
+  // ---- carve shared memory ----
+  unsigned char *sp = k2_smem;
+  Ctl &S = *reinterpret_cast<Ctl *>(sp);
+  sp += (sizeof(Ctl) + 15) & ~(size_t)15;
+  SmemNodes sn;
+  sn.cap = cap;
+  auto take = [&](int rows) { double *q = reinterpret_cast<double *>(sp); sp += (size_t)rows * cap * sizeof(double); return q; };
+  sn.alloc = take(R); sn.idle = take(R); sn.used = take(R);
+  sn.rel = c.has_future ? take(R) : nullptr;
+  sn.pip = c.has_future ? take(R) : nullptr;
+  sn.kalloc = take(K); sn.kreq = take(K); sn.knz = take(2);
+  sn.nerr = reinterpret_cast<unsigned long long *>(sp); sp += (size_t)cap * 8;
+  sn.max_tasks = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
+  sn.pod_count = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
+
+  for (int i = tid; i < nmine; i += blockDim.x) {
+    const int n = nbase + i;
+    for (int d = 0; d < R; ++d) {
+      sn.alloc[d * cap + i] = p.alloc[(size_t)d * N + n];
+      sn.idle[d * cap + i] = p.idle[(size_t)d * N + n];
+      sn.used[d * cap + i] = p.used[(size_t)d * N + n];
+      if (c.has_future) {
+        sn.rel[d * cap + i] = p.rel[(size_t)d * N + n];
+        sn.pip[d * cap + i] = p.pip[(size_t)d * N + n];
+      }
+    }
+    for (int k = 0; k < K; ++k) {
+      sn.kalloc[k * cap + i] = p.kalloc[(size_t)k * N + n];
+      sn.kreq[k * cap + i] = p.kreq[(size_t)k * N + n];
+    }
+    for (int k = 0; k < 2; ++k) sn.knz[k * cap + i] = p.knz[(size_t)k * N + n];
+    sn.max_tasks[i] = p.max_tasks[n];
+    sn.pod_count[i] = p.pod_count[n];
+    sn.nerr[i] = 0ull;
+  }
+
+  // ---- per-CTA replica of the control state ----
+  int32_t *ri = p.rep_i32 + (size_t)cta * p.rep_i32_stride;
+  double *rf = p.rep_f64 + (size_t)cta * p.rep_f64_stride;
+  HeapEnt *heap = p.rep_heap + (size_t)cta * p.rep_heap_stride;
+  int32_t *j_ready = ri; ri += J;
+  int32_t *j_waiting = ri; ri += J;
+  int32_t *j_cursor = ri; ri += J;
+  int32_t *r_occ = ri; ri += NR;
+  int32_t *r_pip = ri; ri += NR;
+  int32_t *r_pending = ri; ri += NR;
+  int32_t *r_failed = ri; ri += NR;
+  int32_t *q_active = ri; ri += Q;      // queue is in the queue PQ
+  int32_t *q_scursor = ri; ri += Q;     // cursor into the static, pre-sorted job list of the queue
+  int32_t *q_hsize = ri; ri += Q;       // size of the dynamic heap of re-pushed jobs
+  uint32_t *q_alloc_has = reinterpret_cast<uint32_t *>(ri); ri += Q;
+  uint32_t *q_flags2 = reinterpret_cast<uint32_t *>(ri); ri += Q;
+  int32_t *ops = ri; ri += (size_t)p.max_job_tasks * 3;  // task, node, kind
+  double *j_share = rf; rf += J;
+  double *j_alloc = rf; rf += (size_t)R * J;
+  double *q_alloc = rf; rf += (size_t)R * Q;
+  double *q_share = rf; rf += Q;
+  double *ops_score = rf; rf += p.max_job_tasks;
+
+  for (int j = tid; j < J; j += blockDim.x) {
+    j_ready[j] = p.j_ready0[j];
+    j_waiting[j] = p.j_waiting0[j];
+    j_cursor[j] = 0;
+    j_share[j] = p.j_share0[j];
+    for (int d = 0; d < R; ++d) j_alloc[(size_t)d * J + j] = p.j_alloc0[(size_t)d * J + j];
+  }
+  for (int r = tid; r < NR; r += blockDim.x) {
+    r_occ[r] = p.r_occ0[r];
+    r_pip[r] = p.r_pip0[r];
+    r_pending[r] = p.r_pending0[r];
+    r_failed[r] = 0;
+  }
+  for (int q = tid; q < Q; q += blockDim.x) {
+    q_active[q] = (p.qjobs_off[q + 1] > p.qjobs_off[q]) ? 1 : 0;  // buildAllocateContext: queues with a job
+    q_scursor[q] = 0;
+    q_hsize[q] = 0;
+    q_alloc_has[q] = p.q_alloc_has0[q];
+    q_flags2[q] = p.q_flags2[q];
+    q_share[q] = p.q_share0[q];
+    for (int d = 0; d < R; ++d) q_alloc[(size_t)d * Q + q] = p.q_alloc0[(size_t)d * Q + q];
+  }
+  if (tid == 0) {
+    S.seq = 0;
+    S.n_dec = S.n_vis = S.n_fit = S.n_steps = 0;
+  }
+  __syncthreads();
+
+  const bool out_cta = (cta == 0);  // CTA 0 writes the result lists
+  const bool qorder_prop = [&] {
+    for (int i = 0; i < c.n_plugins; ++i)
+      if ((c.enabled[i] & VC_EN_QUEUE_ORDER) && c.plugin[i] == VC_PLUGIN_PROPORTION) return true;
+    return false;
+  }();
+  const bool overused_prop = [&] {
+    for (int i = 0; i < c.n_plugins; ++i)
+      if ((c.enabled[i] & VC_EN_OVERUSED) && c.plugin[i] == VC_PLUGIN_PROPORTION) return true;
+    return false;
+  }();
+
+  // =====================================================================================
+  // allocateResources loop, allocate.go:283-348
+  // =====================================================================================
+  for (;;) {
+    // ---- queues.Pop(): arg-min over the active queues by ssn.QueueOrderFn (session_plugins.go:709-731;
+    //      proportion: priority desc, then share asc — proportion.go:266-284; then (ts, uid) rank)
+    if (warp == 0) {
+      int bq = -1, bprio = 0;
+      double bshare = 0.0;
+      uint32_t brank = 0;
+      for (int q = lane; q < Q; q += 32) {
+        if (!q_active[q]) continue;
+        int pr = qorder_prop ? p.q_prio[q] : 0;
+        double sh = qorder_prop ? q_share[q] : 0.0;
+        uint32_t rk = p.q_rank[q];
+        bool lt = bq < 0 || pr > bprio || (pr == bprio && (sh < bshare || (sh == bshare && rk < brank)));
+        if (lt) { bq = q; bprio = pr; bshare = sh; brank = rk; }
+      }
+      for (int o = 16; o; o >>= 1) {
+        int oq = __shfl_xor_sync(0xffffffffu, bq, o);
+        int opr = __shfl_xor_sync(0xffffffffu, bprio, o);
+        double osh = __shfl_xor_sync(0xffffffffu, bshare, o);
+        uint32_t ork = __shfl_xor_sync(0xffffffffu, brank, o);
+        bool lt = oq >= 0 && (bq < 0 || opr > bprio || (opr == bprio && (osh < bshare || (osh == bshare && ork < brank))));
+        if (lt) { bq = oq; bprio = opr; bshare = osh; brank = ork; }
+      }
+      if (lane == 0) S.pick = bq;
+    }
+    __syncthreads();
+    const int q = S.pick;
+    if (q < 0) break;
+    __syncthreads();
+
+    // ---- load the queue attr; ssn.Overused (proportion.go:319-331); jobs.Pop() ----
+    if (tid == 0) {
+      q_active[q] = 0;
+      S.queue = q;
+      S.qflags = p.q_flags[q];
+      S.qflags2 = q_flags2[q];
+      S.qalloc_has = q_alloc_has[q];
+      S.qdes_has = p.q_des_has[q];
+      S.qshare = q_share[q];
+      for (int d = 0; d < R; ++d) {
+        S.qalloc[d] = q_alloc[(size_t)d * Q + q];
+        S.qdes[d] = p.q_des[(size_t)d * Q + q];
+      }
+      bool over = false;
+      if (overused_prop && (S.qflags2 & 1u)) {
+        // attr.deserved.LessEqual(attr.allocated, Zero), resource_info.go:429-463
+        over = le_eps(S.qdes[0], S.qalloc[0]) && le_eps(S.qdes[1], S.qalloc[1]);
+        for (int d = 2; d < R && over; ++d) {
+          if (!(S.qdes_has & (1u << d))) continue;
+          double rv = (S.qalloc_has & (1u << d)) ? S.qalloc[d] : 0.0;
+          if (!le_eps(S.qdes[d], rv)) over = false;
+        }
+      }
+      int j = -1;
+      if (!over) {
+        // jobs.Pop(): the better of (front of the static sorted list, top of the dynamic heap)
+        const int sbeg = p.qjobs_off[q], send = p.qjobs_off[q + 1];
+        const int sc = sbeg + q_scursor[q];
+        HeapEnt *h = heap + sbeg;
+        int hs = q_hsize[q];
+        bool have_s = sc < send, have_h = hs > 0;
+        bool take_heap = false;
+        if (have_s && have_h) {
+          int js = p.qjobs[sc];
+          JobKey ks;
+          ks.share = j_share[js]; ks.prio = p.j_prio[js]; ks.rank = p.j_rank[js];
+          ks.ready = j_ready[js] + p.j_pbe[js] >= p.j_min[js];
+          ks.preempt = (p.j_flags[js] & VC_JOB_PREEMPTABLE) != 0;
+          take_heap = job_less(c, key_of(h[0]), ks);
+        } else if (have_h) {
+          take_heap = true;
+        }
+        if (take_heap) {
+          j = h[0].job;
+          HeapEnt last = h[--hs];
+          q_hsize[q] = hs;
+          int i = 0;  // sift-down
+          for (;;) {
+            int l = 2 * i + 1;
+            if (l >= hs) break;
+            int m = l;
+            if (l + 1 < hs && job_less(c, key_of(h[l + 1]), key_of(h[l]))) m = l + 1;
+            if (!job_less(c, key_of(h[m]), key_of(last))) break;
+            h[i] = h[m];
+            i = m;
+          }
+          if (hs > 0) h[i] = last;
+        } else if (have_s) {
+          j = p.qjobs[sc];
+          q_scursor[q] += 1;
+        }
+      }
+      S.job = j;  // -1: queue dropped (overused, or no jobs left)
+      if (j >= 0) {
+        S.cursor = p.job_task_off[j] + j_cursor[j];
+        S.task_end = p.job_task_off[j + 1];
+        S.ready = j_ready[j];
+        S.waiting = j_waiting[j];
+        S.pbe = p.j_pbe[j];
+        S.minav = p.j_min[j];
+        S.ntasks_total = p.j_ntasks[j];
+        S.taskmintotal = p.j_taskmintotal[j];
+        S.jflags = p.j_flags[j];
+        S.role_base = p.j_roleoff[j];
+        S.nroles = p.j_roleoff[j + 1] - p.j_roleoff[j];
+        S.jshare = j_share[j];
+        for (int d = 0; d < R; ++d) S.jalloc[d] = j_alloc[(size_t)d * J + j];
+        for (int r = 0; r < S.nroles; ++r) {
+          int gr = S.role_base + r;
+          S.r_occ[r] = r_occ[gr]; S.r_pip[r] = r_pip[gr]; S.r_pending[r] = r_pending[gr];
+          S.r_min[r] = p.r_min[gr]; S.r_flags[r] = p.r_flags[gr]; S.r_failed[r] = (uint8_t)r_failed[gr];
+        }
+        S.n_ops = 0;
+      }
+    }
+    for (int i = tid; i < nmine; i += blockDim.x) sn.nerr[i] = 0ull;  // util.NewPredicateHelper()
+    __syncthreads();
+    if (S.job < 0) continue;
+    const int j = S.job;
+
+    // =================================================================================
+    // allocateResourcesForTasks, allocate.go:558-694
+    // =================================================================================
+    for (;;) {
+      if (S.cursor >= S.task_end) break;  // tasks.Empty()
+      // ---- tasks.Pop() + task record ----
+      const int t = p.task_order[S.cursor];
+      __syncthreads();
+      if (tid < R) S.trec.req[tid] = p.req[(size_t)tid * T + t];
+      if (tid >= 32 && tid < 32 + K) S.trec.kreq[tid - 32] = p.tkreq[(size_t)(tid - 32) * T + t];
+      if (tid >= 64 && tid < 66) S.trec.knz[tid - 64] = p.tknz[(size_t)(tid - 64) * T + t];
+      if (tid == 96 % blockDim.x) {
+        S.trec.has = p.req_has[t];
+        S.trec.klass = p.t_class[t];
+        S.task = t;
+        S.role_local = p.t_role[t] - S.role_base;
+        S.cursor += 1;
+      }
+      __syncthreads();
+      const int rl = S.role_local;
+      if (!ctl_allocatable(p, S)) continue;  // allocate.go:575-578
+      const bool named_role = !(S.r_flags[rl] & VC_ROLE_EMPTY_NAME);
+      if (named_role && S.r_failed[rl]) {  // job.TaskHasFitErrors, allocate.go:600-607
+        if (out_cta && tid == 0) p.fit_errors[S.n_fit] = t;
+        __syncthreads();
+        if (tid == 0) S.n_fit += 1;
+        __syncthreads();
+        continue;
+      }
+      const bool use_cache = c.enable_ecache && named_role;
+
+      // ---- ph.PredicateNodes + alloc.prioritizeNodes over this CTA's nodes ----
+      const TaskRec &trec = S.trec;
+      const uint32_t *cs_row = p.cstat + (size_t)trec.klass * N + nbase;
+      Local mine;
+      local_init(mine);
+      // With a normalising batch scorer two passes are needed (max over the candidate set first);
+      // pass 0 = categories, counts and max soft-taint count; pass 1 = scores.
+      const int n_pass = c.soft_active ? 2 : 1;
+      int g_soft[2] = {0, 0};
+      for (int pass = 0; pass < n_pass; ++pass) {
+        local_init(mine);
+        for (int i = tid; i < nmine; i += blockDim.x) {
+          SmemNodeView nv{sn, i};
+          const uint32_t cs = cs_row[i];
+          int cat = 2;
+          if (!(use_cache && ((sn.nerr[i] >> rl) & 1ull))) {
+            bool ok = (cs & CS_STATIC_OK) != 0;
+            if (c.pred_predicates && sn.max_tasks[i] <= sn.pod_count[i]) ok = false;
+            int fc = fit_category(c, R, trec, nv);
+            if (ok && fc != 2) cat = fc;
+            else if (use_cache && pass == 0) sn.nerr[i] |= (1ull << rl);
+          }
+          if (cat == 2) continue;
+          const int soft = (cs >> CS_SOFT_SHIFT) & 0xff;
+          mine.cnt[cat] += 1;
+          mine.soft[cat] = max(mine.soft[cat], soft);
+          if (n_pass == 2 && pass == 0) continue;
+          double order = 0.0;
+          bool has_order = node_order(c, R, K, trec, nv, cs, &order);
+          double sc = total_score(c, has_order, order, soft, g_soft[cat]);
+          const int n = nbase + i;
+          if (mine.node[cat] < 0 || better(sc, n, mine.score[cat], mine.node[cat])) {
+            mine.score[cat] = sc;
+            mine.node[cat] = n;
+          }
+        }
+        // CTA-level fold
+        local_warp_reduce(mine);
+        if (lane == 0) {
+          for (int k = 0; k < 2; ++k) {
+            S.w_score[k][warp] = mine.score[k]; S.w_node[k][warp] = mine.node[k];
+            S.w_cnt[k][warp] = mine.cnt[k]; S.w_soft[k][warp] = mine.soft[k];
+          }
+        }
+        __syncthreads();
+        if (warp == 0) {
+          Local l;
+          local_init(l);
+          if (lane < nwarps) {
+            for (int k = 0; k < 2; ++k) {
+              l.score[k] = S.w_score[k][lane]; l.node[k] = S.w_node[k][lane];
+              l.cnt[k] = S.w_cnt[k][lane]; l.soft[k] = S.w_soft[k][lane];
+            }
+          }
+          local_warp_reduce(l);
+          const unsigned seq = S.seq + 1;
+          Local g = exchange(p, l, seq);
+          if (lane == 0) {
+            S.seq = seq;
+            for (int k = 0; k < 2; ++k) {
+              S.cnt[k] = g.cnt[k]; S.best_node[k] = g.node[k]; S.best_score[k] = g.score[k]; S.max_soft[k] = g.soft[k];
+            }
+          }
+        }
+        __syncthreads();
+        g_soft[0] = S.max_soft[0];
+        g_soft[1] = S.max_soft[1];
+        if (S.cnt[0] + S.cnt[1] == 0) break;
+      }
+      if (tid == 0) S.n_steps += 1;
+
+      if (S.cnt[0] + S.cnt[1] == 0) {  // no feasible node, allocate.go:639-659
+        if (out_cta && tid == 0) p.fit_errors[S.n_fit] = t;
+        __syncthreads();
+        if (tid == 0) { S.n_fit += 1; S.r_failed[rl] = 1; }
+        __syncthreads();
+        if (ctl_need_continue(S)) continue;
+        break;
+      }
+      // ---- gradient choice (allocate.go:750-776) and allocateResourcesForTask (:780-814) ----
+      const int cat = S.cnt[0] > 0 ? 0 : 1;
+      const int best = S.best_node[cat];
+      const double score = S.cnt[cat] == 1 ? 0.0 : S.best_score[cat];
+      const int kind = cat == 0 ? VC_OP_ALLOCATE : VC_OP_PIPELINE;
+      // owner thread: node.AddTask, api/node_info.go:435-484
+      if (best >= nbase && best < nbase + nmine) {
+        const int i = best - nbase;
+        if ((i % blockDim.x) == tid) {
+          if (kind == VC_OP_ALLOCATE) {
+            for (int d = 0; d < R; ++d) {
+              sn.idle[d * cap + i] -= trec.req[d];
+              sn.used[d * cap + i] += trec.req[d];
+            }
+          } else {
+            for (int d = 0; d < R; ++d) sn.pip[d * cap + i] += trec.req[d];
+          }
+          if (c.has_predicates) {  // predicates AllocateFunc: k8s NodeInfo.AddPodInfo, predicates.go:212-256
+            sn.pod_count[i] += 1;
+            for (int k = 0; k < K; ++k) sn.kreq[k * cap + i] += trec.kreq[k];
+            for (int k = 0; k < 2; ++k) sn.knz[k * cap + i] += trec.knz[k];
+          }
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        // job.UpdateTaskStatus (job_info.go:651-660) + event handlers (drf.go:391-418, proportion.go:475-497)
+        S.r_pending[rl] -= 1;
+        if (kind == VC_OP_ALLOCATE) { S.r_occ[rl] += 1; S.ready += 1; }
+        else { S.r_pip[rl] += 1; S.waiting += 1; }
+        if (c.has_drf) {
+          for (int d = 0; d < R; ++d) S.jalloc[d] += trec.req[d];
+          S.jshare = drf_share(p, S.jalloc);
+        }
+        if (c.has_proportion && (S.qflags2 & 1u)) {
+          S.qalloc[0] += trec.req[0];
+          S.qalloc[1] += trec.req[1];
+          for (int d = 2; d < R; ++d)
+            if (trec.has & (1u << d)) { S.qalloc[d] += trec.req[d]; S.qalloc_has |= 1u << d; S.qflags2 &= ~2u; }
+          S.qshare = queue_share(R, S.qalloc, S.qalloc_has, S.qdes, S.qdes_has);
+        }
+        const int k = S.n_ops;
+        ops[k * 3 + 0] = t; ops[k * 3 + 1] = best; ops[k * 3 + 2] = kind;
+        ops_score[k] = score;
+        S.n_ops = k + 1;
+      }
+      __syncthreads();
+      if (ctl_job_ready(c, S)) break;  // ssn.SubJobReady, allocate.go:676-678
+    }
+
+    // ---- statement outcome, allocate.go:681-693 and :330-337 ----
+    const bool ready = ctl_job_ready(c, S);
+    const bool stmt = ready || ctl_job_pipelined(c, S);
+    const int n_ops = S.n_ops;
+    __syncthreads();
+    if (!stmt && n_ops > 0) {
+      // stmt.Discard(): undo in reverse order (statement.go:357-381)
+      for (int k = n_ops - 1; k >= 0; --k) {
+        const int ot = ops[k * 3 + 0], on = ops[k * 3 + 1], okind = ops[k * 3 + 2];
+        if (on >= nbase && on < nbase + nmine && ((on - nbase) % blockDim.x) == tid) {
+          const int i = on - nbase;
+          for (int d = 0; d < R; ++d) {
+            double rq = p.req[(size_t)d * T + ot];
+            if (okind == VC_OP_ALLOCATE) { sn.idle[d * cap + i] += rq; sn.used[d * cap + i] -= rq; }
+            else sn.pip[d * cap + i] -= rq;
+          }
+          if (c.has_predicates) {
+            sn.pod_count[i] -= 1;
+            for (int kk = 0; kk < K; ++kk) sn.kreq[kk * cap + i] -= p.tkreq[(size_t)kk * T + ot];
+            for (int kk = 0; kk < 2; ++kk) sn.knz[kk * cap + i] -= p.tknz[(size_t)kk * T + ot];
+          }
+        }
+        if (tid == 0) {
+          const int orl = p.t_role[ot] - S.role_base;
+          S.r_pending[orl] += 1;
+          if (okind == VC_OP_ALLOCATE) { S.r_occ[orl] -= 1; S.ready -= 1; }
+          else { S.r_pip[orl] -= 1; S.waiting -= 1; }
+          if (c.has_drf)
+            for (int d = 0; d < R; ++d) S.jalloc[d] -= p.req[(size_t)d * T + ot];
+          if (c.has_proportion && (S.qflags2 & 1u)) {
+            const uint32_t oh = p.req_has[ot];
+            S.qalloc[0] -= p.req[(size_t)0 * T + ot];
+            S.qalloc[1] -= p.req[(size_t)1 * T + ot];
+            if (!(S.qflags2 & 2u))
+              for (int d = 2; d < R; ++d)
+                if (oh & (1u << d)) { S.qalloc[d] -= p.req[(size_t)d * T + ot]; S.qalloc_has |= 1u << d; }
+          }
+        }
+      }
+      if (tid == 0) {
+        if (c.has_drf) S.jshare = drf_share(p, S.jalloc);
+        if (c.has_proportion && (S.qflags2 & 1u)) S.qshare = queue_share(R, S.qalloc, S.qalloc_has, S.qdes, S.qdes_has);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // write the job / queue state back into the replica
+      j_ready[j] = S.ready;
+      j_waiting[j] = S.waiting;
+      j_cursor[j] = S.cursor - p.job_task_off[j];
+      j_share[j] = S.jshare;
+      for (int d = 0; d < R; ++d) j_alloc[(size_t)d * J + j] = S.jalloc[d];
+      for (int r = 0; r < S.nroles; ++r) {
+        int gr = S.role_base + r;
+        r_occ[gr] = S.r_occ[r]; r_pip[gr] = S.r_pip[r]; r_pending[gr] = S.r_pending[r]; r_failed[gr] = S.r_failed[r];
+      }
+      for (int d = 0; d < R; ++d) q_alloc[(size_t)d * Q + q] = S.qalloc[d];
+      q_alloc_has[q] = S.qalloc_has;
+      q_flags2[q] = S.qflags2;
+      q_share[q] = S.qshare;
+      // results (CTA 0)
+      if (out_cta) {
+        vc_visit v;
+        v.job = j;
+        v.outcome = stmt ? (ready ? VC_VISIT_COMMIT : VC_VISIT_KEEP) : VC_VISIT_DISCARD;
+        v.first_op = S.n_dec;
+        v.n_ops = stmt ? n_ops : 0;
+        p.visits[S.n_vis] = v;
+      }
+      if (stmt) {
+        if (out_cta)
+          for (int k = 0; k < n_ops; ++k) {
+            vc_decision dcs;
+            dcs.task = ops[k * 3 + 0]; dcs.node = ops[k * 3 + 1]; dcs.kind = ops[k * 3 + 2];
+            dcs.visit = S.n_vis; dcs.score = ops_score[k];
+            p.decisions[S.n_dec + k] = dcs;
+          }
+        S.n_dec += n_ops;
+      }
+      S.n_vis += 1;
+      // jobs.Push(job) when committed and tasks remain (allocate.go:334-336)
+      if (stmt && ready && S.cursor < S.task_end) {
+        HeapEnt e;
+        e.share = S.jshare; e.job = j; e.prio = p.j_prio[j]; e.rank = p.j_rank[j];
+        e.bits = (ctl_is_ready(S) ? 1u : 0u) | ((S.jflags & VC_JOB_PREEMPTABLE) ? 2u : 0u);
+        HeapEnt *h = heap + p.qjobs_off[q];
+        int i = q_hsize[q]++;
+        while (i > 0) {  // sift-up
+          int par = (i - 1) / 2;
+          if (!job_less(c, key_of(e), key_of(h[par]))) break;
+          h[i] = h[par];
+          i = par;
+        }
+        h[i] = e;
+      }
+      q_active[q] = 1;  // queues.Push(queue), allocate.go:346
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: node state back to HBM, counters ----
+  for (int i = tid; i < nmine; i += blockDim.x) {
+    const int n = nbase + i;
+    for (int d = 0; d < R; ++d) {
+      p.idle[(size_t)d * N + n] = sn.idle[d * cap + i];
+      p.used[(size_t)d * N + n] = sn.used[d * cap + i];
+      if (c.has_future) p.pip[(size_t)d * N + n] = sn.pip[d * cap + i];
+    }
+    for (int k = 0; k < K; ++k) p.kreq[(size_t)k * N + n] = sn.kreq[k * cap + i];
+    for (int k = 0; k < 2; ++k) p.knz[(size_t)k * N + n] = sn.knz[k * cap + i];
+    p.pod_count[n] = sn.pod_count[i];
+  }
+  if (out_cta && tid == 0) {
+    p.counters[0] = S.n_dec;
+    p.counters[1] = S.n_vis;
+    p.counters[2] = S.n_fit;
+    p.counters[3] = S.n_steps;
+  }
+}

@@ -1,0 +1,248 @@
+// vc_host.hpp — host-side session-open logic of libvcalloc.so (product code, C++17).
+//
+// What the reference does in plugin OnSessionOpen callbacks and in buildAllocateContext before the
+// first task is placed: ssn.TotalResource, drf job shares, proportion's deserved water-filling, gang
+// JobValid, the TaskOrderFn order inside each job and the initial JobOrderFn order inside each queue.
+// These are O(J + Q + T) scalar passes; the O(T x N) work is on the GPU.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../../include/vcalloc.h"
+
+namespace vch {
+
+constexpr double kMinRes = 0.1;
+inline bool le_eps(double l, double r) { return l < r || std::fabs(l - r) < kMinRes; }
+inline double share_of(double l, double r) { return r == 0 ? (l == 0 ? 0.0 : 1.0) : l / r; }
+
+// api.Resource as a dense vector + key-presence mask + nil-map flag (api/resource_info.go:60-70)
+struct HRes {
+  double v[VC_MAX_DIMS];
+  uint32_t has = 0;
+  bool nil = true;
+  HRes() { for (double &x : v) x = 0; }
+  static HRes load(const double *base, int count, int idx, int R, uint32_t has_bits) {
+    HRes r;
+    if (!base) return r;
+    uint32_t m = has_bits & ~(VC_RES_HAS_ANY | 3u);
+    if (R < 32) m &= (1u << R) - 1;
+    for (int d = 0; d < R; ++d)
+      if (d < 2 || (m & (1u << d))) r.v[d] = base[(size_t)d * count + idx];
+    r.has = m;
+    r.nil = m == 0;
+    return r;
+  }
+  bool k(int d) const { return (has >> d) & 1u; }
+  void add(const HRes &o, int R) {  // Resource.Add :277-290
+    v[0] += o.v[0]; v[1] += o.v[1];
+    for (int d = 2; d < R; ++d) if (o.k(d)) { v[d] += o.v[d]; has |= 1u << d; nil = false; }
+  }
+  void multi(double ratio, int R) {  // Resource.Multi :323-330
+    v[0] *= ratio; v[1] *= ratio;
+    for (int d = 2; d < R; ++d) if (k(d)) v[d] *= ratio;
+  }
+  void min_dim(const HRes &o, bool inf, int R) {  // MinDimensionResource :939-976
+    if (o.v[0] < v[0]) v[0] = o.v[0];
+    if (o.v[1] < v[1]) v[1] = o.v[1];
+    if (nil) return;
+    if (o.nil) { if (!inf) for (int d = 2; d < R; ++d) if (k(d)) v[d] = 0; return; }
+    for (int d = 2; d < R; ++d) {
+      if (!k(d)) continue;
+      if (o.k(d)) v[d] = std::fmin(v[d], o.v[d]);
+      else if (!inf) v[d] = 0;
+    }
+  }
+  bool equal(const HRes &o, int R) const {  // equality.Semantic.DeepEqual
+    if (v[0] != o.v[0] || v[1] != o.v[1] || has != o.has) return false;
+    for (int d = 2; d < R; ++d) if (k(d) && v[d] != o.v[d]) return false;
+    return true;
+  }
+  bool less_equal_zero(const HRes &o, int R) const {  // LessEqual(o, Zero) :429-463
+    if (!le_eps(v[0], o.v[0]) || !le_eps(v[1], o.v[1])) return false;
+    for (int d = 2; d < R; ++d) if (k(d) && !le_eps(v[d], o.k(d) ? o.v[d] : 0.0)) return false;
+    return true;
+  }
+  bool is_empty(int R, int pods_dim) const {  // IsEmpty :240-255
+    if (!(v[0] < kMinRes && v[1] < kMinRes)) return false;
+    for (int d = 2; d < R; ++d) if (k(d) && d != pods_dim && v[d] >= kMinRes) return false;
+    return true;
+  }
+};
+inline HRes hmax(const HRes &l, const HRes &r, int R) {  // helpers.Max, api/helpers/helpers.go:51-77
+  HRes o;
+  o.v[0] = std::fmax(l.v[0], r.v[0]); o.v[1] = std::fmax(l.v[1], r.v[1]);
+  if (l.nil && r.nil) return o;
+  o.nil = false;
+  for (int d = 2; d < R; ++d) if (l.k(d) && l.v[d] >= 0) { o.has |= 1u << d; o.v[d] = l.v[d]; }
+  for (int d = 2; d < R; ++d) if (r.k(d) && r.v[d] >= 0) { double cur = o.k(d) ? o.v[d] : 0.0; o.has |= 1u << d; o.v[d] = std::fmax(r.v[d], cur); }
+  return o;
+}
+inline void hdiff(const HRes &l, const HRes &r, HRes &inc, HRes &dec, int R) {  // Diff(., Zero) :879-918
+  inc = HRes(); dec = HRes();
+  inc.nil = dec.nil = false;
+  for (int d = 0; d < 2; ++d) { if (l.v[d] > r.v[d]) inc.v[d] = l.v[d] - r.v[d]; else dec.v[d] = r.v[d] - l.v[d]; }
+  uint32_t keys = l.has | r.has;
+  for (int d = 2; d < R; ++d) {
+    if (!((keys >> d) & 1u)) continue;
+    double lq = l.k(d) ? l.v[d] : 0.0, rq = r.k(d) ? r.v[d] : 0.0;
+    if (lq == -1.0) { inc.has |= 1u << d; inc.v[d] = lq; continue; }
+    if (rq == -1.0) { dec.has |= 1u << d; dec.v[d] = rq; continue; }
+    if (lq > rq) { inc.has |= 1u << d; inc.v[d] = lq - rq; } else { dec.has |= 1u << d; dec.v[d] = rq - lq; }
+  }
+}
+inline HRes exceeded(const HRes &l, const HRes &r, int R) { HRes a, b; hdiff(l, r, a, b, R); return a; }
+
+struct QAttr {  // proportion.queueAttr, plugins/proportion/proportion.go:57-74
+  bool exists = false;
+  HRes deserved, allocated, request, capability, real_cap, guarantee;
+  double share = 0;
+  int32_t weight = 0;
+};
+inline double queue_share(const QAttr &a, int R) {  // updateQueueAttrShare :590-602
+  double res = 0;
+  for (int d = 0; d < R; ++d) {
+    if (d >= 2 && !a.deserved.k(d)) continue;
+    if (!(a.deserved.v[d] >= kMinRes)) continue;
+    double al = (d < 2 || a.allocated.k(d)) ? a.allocated.v[d] : 0.0;
+    double sh = share_of(al, a.deserved.v[d]);
+    if (sh > res) res = sh;
+  }
+  return res;
+}
+
+// proportion OnSessionOpen (plugins/proportion/proportion.go:90-264)
+inline void proportion_open(const vc_dims &d, const vc_jobs &jb, const vc_queues &qu, const HRes &total,
+                            std::vector<QAttr> &out) {
+  const int R = d.n_dims, Q = d.n_queues, J = d.n_jobs;
+  out.assign(Q, QAttr());
+  HRes total_guar;
+  for (int q = 0; q < Q; ++q)
+    if (qu.guarantee_has && (qu.guarantee_has[q] & VC_RES_HAS_ANY)) total_guar.add(HRes::load(qu.guarantee, Q, q, R, qu.guarantee_has[q]), R);
+  for (int j = 0; j < J; ++j) {
+    int q = jb.queue[j];
+    if (q < 0 || out[q].exists) continue;
+    QAttr &a = out[q];
+    a.exists = true;
+    a.weight = qu.weight[q];
+    bool has_cap = qu.capability_has && (qu.capability_has[q] & VC_RES_HAS_ANY);
+    if (has_cap) {
+      a.capability = HRes::load(qu.capability, Q, q, R, qu.capability_has[q]);
+      if (a.capability.v[0] <= 0) a.capability.v[0] = std::numeric_limits<double>::max();
+      if (a.capability.v[1] <= 0) a.capability.v[1] = std::numeric_limits<double>::max();
+    }
+    if (qu.guarantee_has && (qu.guarantee_has[q] & VC_RES_HAS_ANY)) a.guarantee = HRes::load(qu.guarantee, Q, q, R, qu.guarantee_has[q]);
+    a.real_cap = exceeded(total, total_guar, R);
+    a.real_cap.add(a.guarantee, R);
+    if (has_cap) a.real_cap.min_dim(a.capability, true, R);
+    a.allocated = HRes::load(qu.allocated, Q, q, R, qu.allocated_has ? qu.allocated_has[q] : 0);
+    a.request = HRes::load(qu.request, Q, q, R, qu.request_has ? qu.request_has[q] : 0);
+  }
+  HRes remaining = total;
+  std::vector<uint8_t> meet(Q, 0);
+  for (;;) {
+    int64_t tw = 0;
+    for (int q = 0; q < Q; ++q) if (out[q].exists && !meet[q]) tw += out[q].weight;
+    if (tw == 0) break;
+    HRes old_remaining = remaining, increased, decreased;
+    for (int q = 0; q < Q; ++q) {
+      QAttr &a = out[q];
+      if (!a.exists || meet[q]) continue;
+      HRes old = a.deserved;
+      HRes part = remaining;
+      part.multi((double)a.weight / (double)(int32_t)tw, R);
+      a.deserved.add(part, R);
+      a.deserved.min_dim(a.real_cap, true, R);
+      a.deserved.min_dim(a.request, false, R);
+      a.deserved = hmax(a.deserved, a.guarantee, R);
+      a.share = queue_share(a, R);
+      if (a.request.less_equal_zero(a.deserved, R)) meet[q] = 1;
+      else if (a.deserved.equal(old, R)) meet[q] = 1;
+      HRes inc, dec;
+      hdiff(a.deserved, old, inc, dec, R);
+      increased.add(inc, R);
+      decreased.add(dec, R);
+    }
+    HRes tmp = remaining;
+    tmp.add(decreased, R);
+    remaining = exceeded(tmp, increased, R);
+    if (remaining.is_empty(R, d.pods_dim) || remaining.equal(old_remaining, R)) break;
+  }
+}
+
+inline bool has_plugin(const vc_conf &c, int id) {
+  for (int i = 0; i < c.n_plugins; ++i) if (c.plugins[i].plugin == id) return true;
+  return false;
+}
+inline bool plugin_enabled(const vc_conf &c, int id, uint32_t flag) {
+  for (int i = 0; i < c.n_plugins; ++i) if (c.plugins[i].plugin == id && (c.plugins[i].enabled & flag)) return true;
+  return false;
+}
+
+// gang validJobFn (plugins/gang/gang.go:58-93) through ssn.JobValid (session_plugins.go:509-524)
+inline bool job_valid(const vc_conf &c, const vc_jobs &jb, int j) {
+  if (!has_plugin(c, VC_PLUGIN_GANG)) return true;
+  if (!(jb.min_available[j] < jb.task_min_total[j])) {
+    for (int r = jb.role_off[j]; r < jb.role_off[j + 1]; ++r) {
+      if (!(jb.role_flags[r] & VC_ROLE_IN_MIN_MAP) || jb.role_min[r] == 0) continue;
+      if (jb.role_valid[r] < jb.role_min[r]) return false;
+    }
+  }
+  return jb.valid_num[j] >= jb.min_available[j];
+}
+
+// ssn.TaskOrderFn (session_plugins.go:772-783): priority plugin, then helpers.CompareTask
+struct TaskLess {
+  const vc_tasks *t;
+  bool by_priority;
+  bool operator()(int l, int r) const {
+    if (by_priority && t->priority[l] != t->priority[r]) return t->priority[l] > t->priority[r];
+    bool lerr = t->pod_index[l] < 0, rerr = t->pod_index[r] < 0;
+    if (lerr || rerr || t->pod_index[l] == t->pod_index[r]) {
+      if (t->creation_ts[l] == t->creation_ts[r]) return t->uid_rank[l] < t->uid_rank[r];
+      return t->creation_ts[l] < t->creation_ts[r];
+    }
+    return !(t->pod_index[l] > t->pod_index[r]);
+  }
+};
+
+// Pop order of a util.PriorityQueue (container/heap) filled in index order — the order in which
+// allocateResourcesForTasks sees the tasks of a job (util/priority_queue.go:30-111).
+template <class Less>
+inline void go_heap_order(std::vector<int> &items, Less less) {
+  std::vector<int> h;
+  h.reserve(items.size());
+  for (int x : items) {
+    h.push_back(x);
+    int j = (int)h.size() - 1;
+    for (;;) {
+      int i = (j - 1) / 2;
+      if (i == j || !less(h[j], h[i])) break;
+      std::swap(h[i], h[j]);
+      j = i;
+    }
+  }
+  size_t out = 0;
+  while (!h.empty()) {
+    int n = (int)h.size() - 1;
+    std::swap(h[0], h[n]);
+    int i = 0;
+    for (;;) {
+      int j1 = 2 * i + 1;
+      if (j1 >= n || j1 < 0) break;
+      int j = j1;
+      if (j1 + 1 < n && less(h[j1 + 1], h[j1])) j = j1 + 1;
+      if (!less(h[j], h[i])) break;
+      std::swap(h[i], h[j]);
+      i = j;
+    }
+    items[out++] = h.back();
+    h.pop_back();
+  }
+}
+
+}  // namespace vch

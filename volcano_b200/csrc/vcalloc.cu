@@ -1,0 +1,936 @@
+// vcalloc.cu — libvcalloc.so: C ABI (include/vcalloc.h) + host orchestration of the CUDA kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 \
+//             -Xcompiler -fPIC -shared vcalloc.cu -o libvcalloc.so
+// There is no CPU path in this library: every entry point that computes needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vcalloc.h"
+#include "vc_commit.cuh"
+#include "vc_device.cuh"
+#include "vc_host.hpp"
+#include "vc_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(x)                                                                     \
+  do {                                                                                  \
+    cudaError_t e_ = (x);                                                               \
+    if (e_ != cudaSuccess) return fail(VC_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
+  } while (0)
+
+bool g_inited = false;
+int g_device = -1;
+int g_sm_count = 0;
+int g_launches = 0;
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// One device arena + one pinned staging arena per snapshot: the whole session goes up in a single
+// cudaMemcpyAsync (SURVEY §8f-2 'upload once per cycle').
+struct Arena {
+  unsigned char *dev = nullptr, *pin = nullptr;
+  size_t cap = 0, used = 0;
+  size_t reserve(size_t bytes) {
+    size_t off = (used + 255) & ~(size_t)255;
+    used = off + bytes;
+    return off;
+  }
+};
+
+template <class T>
+struct Slot {  // a typed region inside the arena
+  size_t off = 0, count = 0;
+  T *d(const Arena &a) const { return reinterpret_cast<T *>(a.dev + off); }
+  T *h(const Arena &a) const { return reinterpret_cast<T *>(a.pin + off); }
+};
+
+}  // namespace
+
+struct vc_result {
+  std::vector<vc_decision> decisions;
+  std::vector<vc_visit> visits;
+  std::vector<int32_t> fit_errors;
+  vc_stats stats{};
+};
+
+struct vc_snapshot {
+  vc_dims dims{};
+  DevDims dd{};
+  DevConf dc{};
+  vc_conf conf{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  bool uploaded = false;
+  Arena in;  // uploaded inputs (H2D once per cycle)
+  // ---- input slots ----
+  Slot<double> n_alloc, n_idle, n_used, n_rel, n_pip, n_kalloc, n_kreq, n_knz;
+  Slot<int32_t> n_max_tasks, n_pod_count, n_zone;
+  Slot<uint64_t> n_labels, n_thard, n_tsoft;
+  Slot<uint32_t> n_flags;
+  Slot<uint8_t> zone_active;
+  Slot<double> t_req, t_kreq, t_knz;
+  Slot<uint32_t> t_has;
+  Slot<int32_t> t_class, t_role, t_job;
+  Slot<uint64_t> c_sel, c_aff, c_tolh, c_tols, c_pref;
+  Slot<int32_t> c_naff, c_npref, c_prefw;
+  Slot<uint32_t> c_flags;
+  Slot<int32_t> j_queue, j_min, j_ntasks, j_pbe, j_taskmintotal, j_roleoff, j_prio, j_ready0, j_waiting0;
+  Slot<uint32_t> j_flags, j_rank;
+  Slot<double> j_alloc0, j_share0;
+  Slot<int32_t> r_min, r_occ0, r_pip0, r_pending0;
+  Slot<uint32_t> r_flags;
+  Slot<int32_t> q_prio;
+  Slot<uint32_t> q_rank, q_flags, q_alloc_has0, q_des_has, q_flags2;
+  Slot<double> q_alloc0, q_des, q_share0;
+  Slot<int32_t> qjobs_off, qjobs, task_order, job_task_off;
+  // ---- device-only buffers ----
+  uint32_t *cstat = nullptr;
+  double *w_idle = nullptr, *w_used = nullptr, *w_pip = nullptr, *w_kreq = nullptr, *w_knz = nullptr;  // working copies
+  int32_t *w_pod_count = nullptr;
+  int32_t *rep_i32 = nullptr;
+  double *rep_f64 = nullptr;
+  HeapEnt *rep_heap = nullptr;
+  size_t rep_i32_stride = 0, rep_f64_stride = 0, rep_heap_stride = 0;
+  uint4 *mbox = nullptr;
+  vc_decision *d_decisions = nullptr;
+  vc_visit *d_visits = nullptr;
+  int32_t *d_fit = nullptr, *d_counters = nullptr;
+  vc_decision *h_decisions = nullptr;  // pinned
+  vc_visit *h_visits = nullptr;
+  int32_t *h_fit = nullptr, *h_counters = nullptr;
+  int max_job_tasks = 1;
+  int n_cta = 0, block = 0, npc = 0;
+  size_t smem_bytes = 0;
+  double total[VC_MAX_DIMS]{};
+  uint32_t total_has = 0;
+  std::vector<vch::QAttr> qattr;
+  double upload_ms = 0;
+  int64_t h2d_bytes = 0;
+  // ---- dense pass (K1) ----
+  bool dense_ready = false;
+  int n_groups = 0, n_work = 0;
+  double *g_req = nullptr, *g_kreq = nullptr, *g_knz = nullptr, *g_order = nullptr, *g_best_score = nullptr;
+  uint32_t *g_has = nullptr;
+  int32_t *g_class = nullptr, *g_stats = nullptr, *g_best_node = nullptr;
+  uint8_t *g_cat = nullptr;
+  int32_t *work_group = nullptr, *work_begin = nullptr, *work_end = nullptr, *group_tasks = nullptr, *task_group = nullptr;
+  double *part_score = nullptr;
+  int32_t *part_node = nullptr;
+  uint32_t *mask_out = nullptr;
+  double *score_out = nullptr, *best_score = nullptr;
+  int32_t *best_node = nullptr;
+  int mw32 = 0;
+  bool matrix_allocated = false;
+  double last_expand_ms = 0, last_dense_ms = 0;
+  // host copies kept for the dense-pass grouping
+  std::vector<double> h_req, h_kreq, h_knz;
+  std::vector<uint32_t> h_has;
+  std::vector<int32_t> h_class;
+};
+
+namespace {
+
+template <class T>
+void put(vc_snapshot *s, Slot<T> &slot, const T *src, size_t count, bool plan) {
+  if (plan) {
+    slot.count = count;
+    slot.off = s->in.reserve(count * sizeof(T));
+  } else if (count) {
+    if (src) std::memcpy(slot.h(s->in), src, count * sizeof(T));
+    else std::memset(slot.h(s->in), 0, count * sizeof(T));
+  }
+}
+
+int build_devconf(vc_snapshot *s, const vc_nodes *nd) {
+  const vc_conf &c = s->conf;
+  DevConf &d = s->dc;
+  std::memset(&d, 0, sizeof d);
+  if (c.n_plugins < 0 || c.n_plugins > VC_MAX_PLUGINS) return fail(VC_EINVAL, "n_plugins out of range");
+  d.n_plugins = c.n_plugins;
+  for (int i = 0; i < c.n_plugins; ++i) {
+    d.plugin[i] = c.plugins[i].plugin;
+    d.tier[i] = c.plugins[i].tier;
+    d.enabled[i] = c.plugins[i].enabled;
+  }
+  d.binpack_weight = c.binpack_weight;
+  for (int i = 0; i < VC_MAX_DIMS; ++i) d.binpack_dim_weight[i] = c.binpack_dim_weight[i];
+  d.w_least = c.w_least; d.w_most = c.w_most; d.w_balanced = c.w_balanced;
+  d.w_node_affinity = c.w_node_affinity; d.w_taint = c.w_taint_toleration;
+  d.predicates_enable = c.predicates_enable;
+  d.enable_ecache = c.enable_predicate_error_cache;
+  d.has_gang = vch::has_plugin(c, VC_PLUGIN_GANG);
+  d.has_drf = vch::has_plugin(c, VC_PLUGIN_DRF);
+  d.has_proportion = vch::has_plugin(c, VC_PLUGIN_PROPORTION);
+  d.has_predicates = vch::has_plugin(c, VC_PLUGIN_PREDICATES);
+  d.pred_predicates = vch::plugin_enabled(c, VC_PLUGIN_PREDICATES, VC_EN_PREDICATE);
+  bool no = vch::plugin_enabled(c, VC_PLUGIN_NODEORDER, VC_EN_NODE_ORDER);
+  d.taint_batch = no && c.w_taint_toleration != 0;
+  d.batch_any = no || vch::plugin_enabled(c, VC_PLUGIN_PREDICATES, VC_EN_NODE_ORDER);
+  const size_t RN = (size_t)s->dims.n_dims * s->dims.n_nodes;
+  int fut = 0;
+  for (size_t i = 0; i < RN && !fut; ++i)
+    if ((nd->releasing && nd->releasing[i] != 0.0) || (nd->pipelined && nd->pipelined[i] != 0.0)) fut = 1;
+  d.has_future = fut;
+  int soft = 0;
+  const size_t WN = (size_t)s->dims.taint_words * s->dims.n_nodes;
+  for (size_t i = 0; i < WN && !soft; ++i)
+    if (nd->taint_soft && nd->taint_soft[i]) soft = 1;
+  d.soft_active = d.taint_batch && soft;
+  return VC_OK;
+}
+
+// smallest launch geometry that keeps one node per thread when possible
+void choose_geometry(vc_snapshot *s) {
+  const int nloc = s->dd.node_end - s->dd.node_begin;
+  int ctas = g_sm_count > 0 ? g_sm_count : 148;
+  if (const char *e = getenv("VC_COMMIT_CTAS")) ctas = std::max(1, atoi(e));
+  int block = 128;
+  if (const char *e = getenv("VC_COMMIT_THREADS")) block = std::max(128, std::min(256, atoi(e) / 32 * 32));
+  ctas = std::max(1, std::min(ctas, (nloc + 31) / 32));  // at least a warp of nodes per CTA
+  int npc = (nloc + ctas - 1) / ctas;
+  npc = (npc + 31) / 32 * 32;
+  ctas = std::max(1, (nloc + npc - 1) / npc);
+  if (npc > block) block = std::min(256, (npc + 31) / 32 * 32);
+  s->n_cta = ctas;
+  s->npc = npc;
+  s->block = block;
+  const int R = s->dims.n_dims, K = s->dims.n_kdims;
+  size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2;
+  s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 + 4) + 64;
+}
+
+int free_dense(vc_snapshot *s) {
+  void *ptrs[] = {s->g_req, s->g_kreq, s->g_knz, s->g_order, s->g_best_score, s->g_has, s->g_class, s->g_stats,
+                  s->g_best_node, s->g_cat, s->work_group, s->work_begin, s->work_end, s->group_tasks, s->task_group,
+                  s->part_score, s->part_node, s->mask_out, s->score_out, s->best_score, s->best_node};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  s->g_req = s->g_kreq = s->g_knz = s->g_order = s->g_best_score = nullptr;
+  s->g_has = nullptr; s->g_class = s->g_stats = s->g_best_node = nullptr; s->g_cat = nullptr;
+  s->work_group = s->work_begin = s->work_end = s->group_tasks = s->task_group = nullptr;
+  s->part_score = nullptr; s->part_node = nullptr;
+  s->mask_out = nullptr; s->score_out = s->best_score = nullptr; s->best_node = nullptr;
+  s->dense_ready = false;
+  s->matrix_allocated = false;
+  return VC_OK;
+}
+
+}  // namespace
+
+// =======================================================================================
+extern "C" {
+
+int vc_abi_version(void) { return VC_ABI_VERSION; }
+const char *vc_last_error(void) { return g_err.c_str(); }
+
+int vc_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(VC_ENODEV, "no CUDA device (%s): libvcalloc has no CPU path", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(VC_EINVAL, "device %d out of range (%d devices)", device, n);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (!prop.cooperativeLaunch) return fail(VC_ENODEV, "device lacks cooperative launch");
+  g_sm_count = prop.multiProcessorCount;
+  g_device = device;
+  g_inited = true;
+  return VC_OK;
+}
+
+int vc_snapshot_create(const vc_dims *dims, vc_snapshot **out) {
+  if (!g_inited) return fail(VC_ENODEV, "vc_init was not called (or failed): no CUDA device bound");
+  if (!dims || !out) return fail(VC_EINVAL, "null argument");
+  if (dims->n_dims < 2 || dims->n_dims > VC_MAX_DIMS) return fail(VC_EINVAL, "n_dims must be in [2,%d]", VC_MAX_DIMS);
+  if (dims->n_kdims < 2 || dims->n_kdims > VC_MAX_KDIMS) return fail(VC_EINVAL, "n_kdims must be in [2,%d]", VC_MAX_KDIMS);
+  if (dims->label_words < 1 || dims->label_words > VC_MAX_WORDS || dims->taint_words < 1 || dims->taint_words > VC_MAX_WORDS)
+    return fail(VC_EINVAL, "label_words / taint_words must be in [1,%d]", VC_MAX_WORDS);
+  if (dims->n_nodes < 0 || dims->n_tasks < 0 || dims->n_jobs < 0 || dims->n_queues < 0 || dims->n_classes < 1)
+    return fail(VC_EINVAL, "negative size");
+  vc_snapshot *s = new vc_snapshot();
+  s->dims = *dims;
+  DevDims &d = s->dd;
+  d.N = dims->n_nodes; d.T = dims->n_tasks; d.J = dims->n_jobs; d.Q = dims->n_queues; d.C = dims->n_classes;
+  d.R = dims->n_dims; d.K = dims->n_kdims; d.Wl = dims->label_words; d.Wt = dims->taint_words; d.NR = dims->n_roles;
+  d.Z = dims->n_zones; d.pods_dim = dims->pods_dim;
+  d.node_begin = 0; d.node_end = d.N;
+  cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->ev2);
+  if (e != cudaSuccess) { delete s; return fail(VC_ECUDA, "stream/event create: %s", cudaGetErrorString(e)); }
+  *out = s;
+  return VC_OK;
+}
+
+void vc_snapshot_destroy(vc_snapshot *s) {
+  if (!s) return;
+  free_dense(s);
+  void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
+                   s->rep_i32, s->rep_f64, s->rep_heap, s->mbox, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
+  for (void *p : dptrs) if (p) cudaFree(p);
+  void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters};
+  for (void *p : hptrs) if (p) cudaFreeHost(p);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->ev2) cudaEventDestroy(s->ev2);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int vc_snapshot_set_shard(vc_snapshot *s, int32_t node_begin, int32_t node_end) {
+  if (!s) return fail(VC_EINVAL, "null snapshot");
+  if (node_begin < 0 || node_end > s->dims.n_nodes || node_begin > node_end || (node_begin % 64) != 0)
+    return fail(VC_EINVAL, "shard [%d,%d) invalid (begin must be a multiple of 64)", node_begin, node_end);
+  s->dd.node_begin = node_begin;
+  s->dd.node_end = node_end;
+  s->dense_ready = false;
+  return VC_OK;
+}
+
+int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, const vc_classes *cl,
+                       const vc_jobs *jb, const vc_queues *qu, const vc_conf *conf) {
+  if (!s || !nd || !tk || !cl || !jb || !qu || !conf) return fail(VC_EINVAL, "null argument");
+  const double t0 = now_ms();
+  const vc_dims &D = s->dims;
+  const size_t N = D.n_nodes, T = D.n_tasks, J = D.n_jobs, Q = D.n_queues, C = D.n_classes, R = D.n_dims,
+               K = D.n_kdims, Wl = D.label_words, Wt = D.taint_words, NR = D.n_roles, Z = D.n_zones;
+  s->conf = *conf;
+  if (conf->percentage_nodes_to_find < 100 && (int)N > conf->min_nodes_to_find)
+    return fail(VC_EUNSUPPORTED, "feasible-node sampling (percentage_nodes_to_find < 100) is not implemented on the "
+                                 "device path; the parity contract runs with 100 (SURVEY §8c)");
+  for (size_t j = 0; j < J; ++j) {
+    if (jb->flags[j] & VC_JOB_UNSUPPORTED) return fail(VC_EUNSUPPORTED, "job %zu uses hard topology / subjob policy", j);
+    if (jb->role_off[j + 1] - jb->role_off[j] > VC_MAX_JOB_ROLES) return fail(VC_EUNSUPPORTED, "job %zu has too many roles", j);
+  }
+  int rc = build_devconf(s, nd);
+  if (rc) return rc;
+
+  // ---- host session-open logic ---------------------------------------------------------
+  // ssn.TotalResource (framework/session.go:272-274)
+  vch::HRes total;
+  for (size_t d = 0; d < R; ++d) {
+    double acc = 0;
+    const double *col = nd->allocatable + d * N;
+    for (size_t n = 0; n < N; ++n) acc += col[n];
+    total.v[d] = acc;
+    if (d >= 2 && N > 0) { total.has |= 1u << d; total.nil = false; }
+  }
+  for (int d = 0; d < VC_MAX_DIMS; ++d) s->total[d] = total.v[d];
+  s->total_has = total.has;
+  // drf job shares at open (plugins/drf/drf.go:186-214, :566-578)
+  std::vector<double> j_share(J, 0.0);
+  if (s->dc.has_drf)
+    for (size_t j = 0; j < J; ++j) {
+      double res = 0;
+      for (size_t d = 0; d < R; ++d) {
+        if (d >= 2 && !((total.has >> d) & 1u)) continue;
+        if (!(total.v[d] >= vch::kMinRes)) continue;
+        double sh = vch::share_of(jb->allocated[d * J + j], total.v[d]);
+        if (sh > res) res = sh;
+      }
+      j_share[j] = res;
+    }
+  // proportion deserved / share (plugins/proportion/proportion.go:90-264)
+  if (s->dc.has_proportion) vch::proportion_open(D, *jb, *qu, total, s->qattr);
+  else s->qattr.assign(Q, vch::QAttr());
+  // TaskOrderFn order inside each job
+  std::vector<int32_t> job_task_off(J + 1, 0), task_order(T);
+  for (size_t t = 0; t < T; ++t) {
+    if (tk->job[t] < 0 || (size_t)tk->job[t] >= J) return fail(VC_EINVAL, "task %zu: bad job index", t);
+    job_task_off[tk->job[t] + 1]++;
+  }
+  int max_job_tasks = 1;
+  for (size_t j = 0; j < J; ++j) {
+    max_job_tasks = std::max(max_job_tasks, job_task_off[j + 1]);
+    job_task_off[j + 1] += job_task_off[j];
+  }
+  {
+    std::vector<int32_t> fill(job_task_off.begin(), job_task_off.end() - 1);
+    for (size_t t = 0; t < T; ++t) task_order[fill[tk->job[t]]++] = (int32_t)t;
+    vch::TaskLess less{tk, vch::plugin_enabled(*conf, VC_PLUGIN_PRIORITY, VC_EN_TASK_ORDER)};
+    std::vector<int> tmp;
+    for (size_t j = 0; j < J; ++j) {
+      int b = job_task_off[j], e = job_task_off[j + 1];
+      bool sorted = true;
+      for (int i = b + 1; i < e && sorted; ++i)
+        if (!less(task_order[i - 1], task_order[i])) sorted = false;
+      if (sorted) continue;  // a strictly increasing run is its own heap-pop order
+      tmp.assign(task_order.begin() + b, task_order.begin() + e);
+      vch::go_heap_order(tmp, less);
+      std::copy(tmp.begin(), tmp.end(), task_order.begin() + b);
+    }
+  }
+  s->max_job_tasks = max_job_tasks;
+  // buildAllocateContext (allocate.go:142-206): jobs that enter the per-queue PQs, in JobOrderFn order
+  std::vector<uint32_t> j_rank(J);
+  {
+    std::vector<int> idx(J);
+    for (size_t j = 0; j < J; ++j) idx[j] = (int)j;
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) {
+      if (jb->creation_ts[a] != jb->creation_ts[b]) return jb->creation_ts[a] < jb->creation_ts[b];
+      return jb->uid_rank[a] < jb->uid_rank[b];
+    });
+    for (size_t r = 0; r < J; ++r) j_rank[idx[r]] = (uint32_t)r;
+  }
+  std::vector<uint32_t> q_rank(Q);
+  {
+    std::vector<int> idx(Q);
+    for (size_t q = 0; q < Q; ++q) idx[q] = (int)q;
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) {
+      if (qu->creation_ts[a] != qu->creation_ts[b]) return qu->creation_ts[a] < qu->creation_ts[b];
+      return qu->uid_rank[a] < qu->uid_rank[b];
+    });
+    for (size_t r = 0; r < Q; ++r) q_rank[idx[r]] = (uint32_t)r;
+  }
+  std::vector<std::vector<int>> qlists(Q);
+  for (size_t j = 0; j < J; ++j) {
+    if ((jb->flags[j] & VC_JOB_PENDING_PHASE) && conf->enqueue_action_enabled) continue;
+    if (!vch::job_valid(*conf, *jb, (int)j)) continue;
+    int q = jb->queue[j];
+    if (q < 0) continue;
+    if ((size_t)q >= Q) return fail(VC_EINVAL, "job %zu: bad queue index", j);
+    if (job_task_off[j + 1] == job_task_off[j]) continue;
+    qlists[q].push_back((int)j);
+  }
+  auto job_less = [&](int l, int r) {  // ssn.JobOrderFn, session_plugins.go:660-683
+    for (int i = 0; i < conf->n_plugins; ++i) {
+      const vc_plugin_option &p = conf->plugins[i];
+      if (!(p.enabled & VC_EN_JOB_ORDER)) continue;
+      int c = 0;
+      switch (p.plugin) {
+        case VC_PLUGIN_PRIORITY: c = jb->priority[l] > jb->priority[r] ? -1 : (jb->priority[l] < jb->priority[r] ? 1 : 0); break;
+        case VC_PLUGIN_GANG: {
+          bool lr = jb->ready_num[l] + jb->pending_besteffort[l] >= jb->min_available[l];
+          bool rr = jb->ready_num[r] + jb->pending_besteffort[r] >= jb->min_available[r];
+          c = (lr && rr) ? 0 : (lr ? 1 : (rr ? -1 : 0));
+          break;
+        }
+        case VC_PLUGIN_DRF: c = j_share[l] == j_share[r] ? 0 : (j_share[l] < j_share[r] ? -1 : 1); break;
+        case VC_PLUGIN_TDM: {
+          bool lp = jb->flags[l] & VC_JOB_PREEMPTABLE, rp = jb->flags[r] & VC_JOB_PREEMPTABLE;
+          c = lp == rp ? 0 : (!lp ? -1 : 1);
+          break;
+        }
+        default: break;
+      }
+      if (c != 0) return c < 0;
+    }
+    return j_rank[l] < j_rank[r];
+  };
+  std::vector<int32_t> qjobs_off(Q + 1, 0), qjobs;
+  for (size_t q = 0; q < Q; ++q) {
+    std::sort(qlists[q].begin(), qlists[q].end(), job_less);
+    qjobs_off[q + 1] = qjobs_off[q] + (int32_t)qlists[q].size();
+    qjobs.insert(qjobs.end(), qlists[q].begin(), qlists[q].end());
+  }
+  // role pending counts incl. the tasks in scope (job_info.go:936-939)
+  std::vector<int32_t> r_pending(NR, 0);
+  for (size_t r = 0; r < NR; ++r) r_pending[r] = jb->role_pending_other ? jb->role_pending_other[r] : 0;
+  for (size_t t = 0; t < T; ++t) {
+    int r = tk->role[t], j = tk->job[t];
+    if (r < jb->role_off[j] || r >= jb->role_off[j + 1]) return fail(VC_EINVAL, "task %zu: role row outside its job", t);
+    r_pending[r] += 1;
+  }
+  // queue arrays for the device
+  std::vector<double> q_des(R * Q, 0.0), q_alloc(R * Q, 0.0), q_share(Q, 0.0);
+  std::vector<uint32_t> q_des_has(Q, 0), q_alloc_has(Q, 0), q_flags2(Q, 0);
+  for (size_t q = 0; q < Q; ++q) {
+    const vch::QAttr &a = s->qattr[q];
+    if (!a.exists) continue;
+    for (size_t d = 0; d < R; ++d) { q_des[d * Q + q] = a.deserved.v[d]; q_alloc[d * Q + q] = a.allocated.v[d]; }
+    q_des_has[q] = a.deserved.has;
+    q_alloc_has[q] = a.allocated.has;
+    q_flags2[q] = 1u | (a.allocated.nil ? 2u : 0u);
+    q_share[q] = a.share;
+  }
+
+  // ---- plan + stage + one H2D copy ------------------------------------------------------
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool plan = pass == 0;
+    if (plan) s->in.used = 0;
+    put(s, s->n_alloc, nd->allocatable, R * N, plan); put(s, s->n_idle, nd->idle, R * N, plan);
+    put(s, s->n_used, nd->used, R * N, plan); put(s, s->n_rel, nd->releasing, R * N, plan);
+    put(s, s->n_pip, nd->pipelined, R * N, plan); put(s, s->n_kalloc, nd->k8s_allocatable, K * N, plan);
+    put(s, s->n_kreq, nd->k8s_requested, K * N, plan); put(s, s->n_knz, nd->k8s_nonzero_requested, 2 * N, plan);
+    put(s, s->n_max_tasks, nd->max_tasks, N, plan); put(s, s->n_pod_count, nd->pod_count, N, plan);
+    put(s, s->n_zone, nd->revocable_zone, N, plan); put(s, s->n_labels, nd->label_bits, Wl * N, plan);
+    put(s, s->n_thard, nd->taint_hard, Wt * N, plan); put(s, s->n_tsoft, nd->taint_soft, Wt * N, plan);
+    put(s, s->n_flags, nd->flags, N, plan); put(s, s->zone_active, nd->zone_active, std::max<size_t>(Z, 1), plan);
+    put(s, s->t_req, tk->resreq, R * T, plan); put(s, s->t_kreq, tk->k8s_req, K * T, plan);
+    put(s, s->t_knz, tk->k8s_nonzero_req, 2 * T, plan); put(s, s->t_has, tk->req_has, T, plan);
+    put(s, s->t_class, tk->klass, T, plan); put(s, s->t_role, tk->role, T, plan); put(s, s->t_job, tk->job, T, plan);
+    put(s, s->c_sel, cl->selector, C * Wl, plan); put(s, s->c_aff, cl->affinity, C * VC_MAX_TERMS * Wl, plan);
+    put(s, s->c_tolh, cl->tolerated_hard, C * Wt, plan); put(s, s->c_tols, cl->tolerated_soft, C * Wt, plan);
+    put(s, s->c_pref, cl->preferred, C * VC_MAX_TERMS * Wl, plan); put(s, s->c_naff, cl->n_affinity, C, plan);
+    put(s, s->c_npref, cl->n_preferred, C, plan); put(s, s->c_prefw, cl->preferred_weight, C * VC_MAX_TERMS, plan);
+    put(s, s->c_flags, cl->flags, C, plan);
+    put(s, s->j_queue, jb->queue, J, plan); put(s, s->j_min, jb->min_available, J, plan);
+    put(s, s->j_ntasks, jb->n_tasks_total, J, plan); put(s, s->j_pbe, jb->pending_besteffort, J, plan);
+    put(s, s->j_taskmintotal, jb->task_min_total, J, plan); put(s, s->j_roleoff, jb->role_off, J + 1, plan);
+    put(s, s->j_prio, jb->priority, J, plan); put(s, s->j_ready0, jb->ready_num, J, plan);
+    put(s, s->j_waiting0, jb->waiting_num, J, plan); put(s, s->j_flags, jb->flags, J, plan);
+    put(s, s->j_rank, j_rank.data(), J, plan); put(s, s->j_alloc0, jb->allocated, R * J, plan);
+    put(s, s->j_share0, j_share.data(), J, plan);
+    put(s, s->r_min, jb->role_min, NR, plan); put(s, s->r_occ0, jb->role_occupied, NR, plan);
+    put(s, s->r_pip0, jb->role_pipelined, NR, plan); put(s, s->r_pending0, r_pending.data(), NR, plan);
+    put(s, s->r_flags, jb->role_flags, NR, plan);
+    put(s, s->q_prio, qu->priority, Q, plan); put(s, s->q_rank, q_rank.data(), Q, plan);
+    put(s, s->q_flags, qu->flags, Q, plan); put(s, s->q_alloc_has0, q_alloc_has.data(), Q, plan);
+    put(s, s->q_des_has, q_des_has.data(), Q, plan); put(s, s->q_flags2, q_flags2.data(), Q, plan);
+    put(s, s->q_alloc0, q_alloc.data(), R * Q, plan); put(s, s->q_des, q_des.data(), R * Q, plan);
+    put(s, s->q_share0, q_share.data(), Q, plan);
+    put(s, s->qjobs_off, qjobs_off.data(), Q + 1, plan); put(s, s->qjobs, qjobs.data(), qjobs.size(), plan);
+    put(s, s->task_order, task_order.data(), T, plan); put(s, s->job_task_off, job_task_off.data(), J + 1, plan);
+    if (plan) {
+      size_t need = (s->in.used + 255) & ~(size_t)255;
+      if (need > s->in.cap) {
+        if (s->in.dev) cudaFree(s->in.dev);
+        if (s->in.pin) cudaFreeHost(s->in.pin);
+        s->in.dev = s->in.pin = nullptr;
+        CUDA_TRY(cudaMalloc(&s->in.dev, need));
+        CUDA_TRY(cudaMallocHost(&s->in.pin, need));
+        s->in.cap = need;
+      }
+    }
+  }
+  CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->in.dev, s->in.pin, s->in.used, cudaMemcpyHostToDevice, s->stream));
+  s->h2d_bytes = (int64_t)s->in.used;
+
+  // ---- device-only buffers --------------------------------------------------------------
+  auto ensure = [&](auto *&ptr, size_t bytes) -> int {
+    if (ptr) return VC_OK;
+    void *q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, std::max<size_t>(bytes, 16)));
+    ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(q);
+    return VC_OK;
+  };
+  if ((rc = ensure(s->cstat, C * N * 4))) return rc;
+  if ((rc = ensure(s->w_idle, R * N * 8)) || (rc = ensure(s->w_used, R * N * 8)) || (rc = ensure(s->w_pip, R * N * 8)) ||
+      (rc = ensure(s->w_kreq, K * N * 8)) || (rc = ensure(s->w_knz, 2 * N * 8)) || (rc = ensure(s->w_pod_count, N * 4)))
+    return rc;
+  choose_geometry(s);
+  // K0
+  K0Params k0;
+  k0.d = s->dd; k0.c = s->dc;
+  k0.labels = s->n_labels.d(s->in); k0.thard = s->n_thard.d(s->in); k0.tsoft = s->n_tsoft.d(s->in);
+  k0.nflags = s->n_flags.d(s->in); k0.zone = s->n_zone.d(s->in); k0.zone_active = s->zone_active.d(s->in);
+  k0.c_sel = s->c_sel.d(s->in); k0.c_aff = s->c_aff.d(s->in); k0.c_tolh = s->c_tolh.d(s->in);
+  k0.c_tols = s->c_tols.d(s->in); k0.c_pref = s->c_pref.d(s->in); k0.c_naff = s->c_naff.d(s->in);
+  k0.c_npref = s->c_npref.d(s->in); k0.c_prefw = s->c_prefw.d(s->in); k0.c_flags = s->c_flags.d(s->in);
+  k0.cstat = s->cstat;
+  if (N > 0) {
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)C);
+    k_class_static<<<grid, 256, 0, s->stream>>>(k0);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  s->uploaded = true;
+  s->dense_ready = false;
+  // keep what the dense pass needs to group tasks
+  s->h_req.assign(tk->resreq, tk->resreq + R * T);
+  s->h_kreq.assign(tk->k8s_req, tk->k8s_req + K * T);
+  s->h_knz.assign(tk->k8s_nonzero_req, tk->k8s_nonzero_req + 2 * T);
+  s->h_has.assign(tk->req_has, tk->req_has + T);
+  s->h_class.assign(tk->klass, tk->klass + T);
+  s->upload_ms = now_ms() - t0;
+  return VC_OK;
+}
+
+int vc_queue_deserved(vc_snapshot *s, double *deserved_out, double *share_out) {
+  if (!s || !s->uploaded) return fail(VC_EINVAL, "snapshot not uploaded");
+  const int R = s->dims.n_dims, Q = s->dims.n_queues;
+  for (int q = 0; q < Q; ++q) {
+    const vch::QAttr &a = s->qattr[q];
+    for (int d = 0; d < R; ++d)
+      if (deserved_out) deserved_out[(size_t)d * Q + q] = (d < 2 || a.deserved.k(d)) ? a.deserved.v[d] : 0.0;
+    if (share_out) share_out[q] = a.share;
+  }
+  return VC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// allocate
+// ---------------------------------------------------------------------------------------
+int vc_allocate_run(vc_snapshot *s, vc_result **out) {
+  if (!s || !out) return fail(VC_EINVAL, "null argument");
+  if (!s->uploaded) return fail(VC_EINVAL, "vc_snapshot_upload must precede vc_allocate_run");
+  const double t0 = now_ms();
+  const vc_dims &D = s->dims;
+  const size_t N = D.n_nodes, T = D.n_tasks, J = D.n_jobs, Q = D.n_queues, R = D.n_dims, K = D.n_kdims, NR = D.n_roles;
+  if (s->dd.node_begin != 0 || s->dd.node_end != (int)N)
+    return fail(VC_EUNSUPPORTED, "the commit engine runs on the full node axis (replicas only across GPUs, DESIGN.md)");
+  const int G = s->n_cta;
+  // replicas, mailbox, outputs
+  const size_t i32_stride = ((3 * J + 4 * NR + 5 * Q + 3 * (size_t)s->max_job_tasks) + 63) & ~(size_t)63;
+  const size_t f64_stride = ((J + R * J + R * Q + Q + (size_t)s->max_job_tasks) + 31) & ~(size_t)31;
+  const size_t heap_stride = (s->qjobs.count + 7) & ~(size_t)7;
+  if (!s->rep_i32 || s->rep_i32_stride != i32_stride || s->rep_f64_stride != f64_stride || s->rep_heap_stride != heap_stride) {
+    if (s->rep_i32) cudaFree(s->rep_i32);
+    if (s->rep_f64) cudaFree(s->rep_f64);
+    if (s->rep_heap) cudaFree(s->rep_heap);
+    s->rep_i32 = nullptr; s->rep_f64 = nullptr; s->rep_heap = nullptr;
+    CUDA_TRY(cudaMalloc(&s->rep_i32, std::max<size_t>(16, i32_stride * G * 4)));
+    CUDA_TRY(cudaMalloc(&s->rep_f64, std::max<size_t>(16, f64_stride * G * 8)));
+    CUDA_TRY(cudaMalloc(&s->rep_heap, std::max<size_t>(16, std::max<size_t>(heap_stride, 1) * G * sizeof(HeapEnt))));
+    s->rep_i32_stride = i32_stride; s->rep_f64_stride = f64_stride; s->rep_heap_stride = heap_stride;
+  }
+  if (!s->mbox) CUDA_TRY(cudaMalloc(&s->mbox, sizeof(uint4) * 2 * 3 * 1024));
+  if (!s->d_decisions) {
+    CUDA_TRY(cudaMalloc(&s->d_decisions, std::max<size_t>(1, T) * sizeof(vc_decision)));
+    CUDA_TRY(cudaMalloc(&s->d_visits, (T + J + 1) * sizeof(vc_visit)));
+    CUDA_TRY(cudaMalloc(&s->d_fit, std::max<size_t>(1, T) * 4));
+    CUDA_TRY(cudaMalloc(&s->d_counters, 8 * 4));
+    CUDA_TRY(cudaMallocHost(&s->h_decisions, std::max<size_t>(1, T) * sizeof(vc_decision)));
+    CUDA_TRY(cudaMallocHost(&s->h_visits, (T + J + 1) * sizeof(vc_visit)));
+    CUDA_TRY(cudaMallocHost(&s->h_fit, std::max<size_t>(1, T) * 4));
+    CUDA_TRY(cudaMallocHost(&s->h_counters, 8 * 4));
+  }
+  CUDA_TRY(cudaMemsetAsync(s->mbox, 0, sizeof(uint4) * 2 * 3 * 1024, s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 8 * 4, s->stream));
+  // working copies of the mutable node state (the uploaded snapshot stays intact for re-runs / K1)
+  CUDA_TRY(cudaMemcpyAsync(s->w_idle, s->n_idle.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->w_used, s->n_used.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->w_pip, s->n_pip.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->w_kreq, s->n_kreq.d(s->in), K * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->w_knz, s->n_knz.d(s->in), 2 * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->w_pod_count, s->n_pod_count.d(s->in), N * 4, cudaMemcpyDeviceToDevice, s->stream));
+
+  K2Params p;
+  std::memset(&p, 0, sizeof p);
+  p.d = s->dd; p.c = s->dc; p.npc = s->npc; p.n_cta = G; p.max_job_tasks = s->max_job_tasks;
+  p.alloc = s->n_alloc.d(s->in); p.rel = s->n_rel.d(s->in); p.kalloc = s->n_kalloc.d(s->in);
+  p.idle = s->w_idle; p.used = s->w_used; p.pip = s->w_pip; p.kreq = s->w_kreq; p.knz = s->w_knz;
+  p.max_tasks = s->n_max_tasks.d(s->in); p.pod_count = s->w_pod_count; p.cstat = s->cstat;
+  p.req = s->t_req.d(s->in); p.tkreq = s->t_kreq.d(s->in); p.tknz = s->t_knz.d(s->in); p.req_has = s->t_has.d(s->in);
+  p.t_class = s->t_class.d(s->in); p.t_role = s->t_role.d(s->in);
+  p.task_order = s->task_order.d(s->in); p.job_task_off = s->job_task_off.d(s->in);
+  p.j_queue = s->j_queue.d(s->in); p.j_min = s->j_min.d(s->in); p.j_ntasks = s->j_ntasks.d(s->in);
+  p.j_pbe = s->j_pbe.d(s->in); p.j_taskmintotal = s->j_taskmintotal.d(s->in); p.j_roleoff = s->j_roleoff.d(s->in);
+  p.j_prio = s->j_prio.d(s->in); p.j_ready0 = s->j_ready0.d(s->in); p.j_waiting0 = s->j_waiting0.d(s->in);
+  p.j_flags = s->j_flags.d(s->in); p.j_rank = s->j_rank.d(s->in); p.j_alloc0 = s->j_alloc0.d(s->in);
+  p.j_share0 = s->j_share0.d(s->in);
+  p.r_min = s->r_min.d(s->in); p.r_occ0 = s->r_occ0.d(s->in); p.r_pip0 = s->r_pip0.d(s->in);
+  p.r_pending0 = s->r_pending0.d(s->in); p.r_flags = s->r_flags.d(s->in);
+  p.q_prio = s->q_prio.d(s->in); p.q_rank = s->q_rank.d(s->in); p.q_flags = s->q_flags.d(s->in);
+  p.q_alloc_has0 = s->q_alloc_has0.d(s->in); p.q_des_has = s->q_des_has.d(s->in); p.q_flags2 = s->q_flags2.d(s->in);
+  p.q_alloc0 = s->q_alloc0.d(s->in); p.q_des = s->q_des.d(s->in); p.q_share0 = s->q_share0.d(s->in);
+  p.qjobs_off = s->qjobs_off.d(s->in); p.qjobs = s->qjobs.d(s->in);
+  for (int d = 0; d < VC_MAX_DIMS; ++d) p.total[d] = s->total[d];
+  p.total_has = s->total_has;
+  p.rep_i32 = s->rep_i32; p.rep_i32_stride = i32_stride; p.rep_f64 = s->rep_f64; p.rep_f64_stride = f64_stride;
+  p.rep_heap = s->rep_heap; p.rep_heap_stride = std::max<size_t>(heap_stride, 1);
+  p.mbox = s->mbox;
+  p.decisions = s->d_decisions; p.visits = s->d_visits; p.fit_errors = s->d_fit; p.counters = s->d_counters;
+
+  if (G > 1024) return fail(VC_EUNSUPPORTED, "too many CTAs");
+  CUDA_TRY(cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+  int max_blocks = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, k_commit, s->block, s->smem_bytes));
+  if (max_blocks * g_sm_count < G)
+    return fail(VC_EUNSUPPORTED, "commit kernel cannot be co-resident: %d CTAs x %zu B smem (max %d/SM)", G, s->smem_bytes, max_blocks);
+  void *args[] = {&p};
+  CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+  CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_commit, dim3(G), dim3(s->block), args, s->smem_bytes, s->stream));
+  g_launches++;
+  CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * 4, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  const double t_k = now_ms();
+  const int n_dec = s->h_counters[0], n_vis = s->h_counters[1], n_fit = s->h_counters[2];
+  if (n_dec) CUDA_TRY(cudaMemcpyAsync(s->h_decisions, s->d_decisions, (size_t)n_dec * sizeof(vc_decision), cudaMemcpyDeviceToHost, s->stream));
+  if (n_vis) CUDA_TRY(cudaMemcpyAsync(s->h_visits, s->d_visits, (size_t)n_vis * sizeof(vc_visit), cudaMemcpyDeviceToHost, s->stream));
+  if (n_fit) CUDA_TRY(cudaMemcpyAsync(s->h_fit, s->d_fit, (size_t)n_fit * 4, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  vc_result *r = new vc_result();
+  r->decisions.assign(s->h_decisions, s->h_decisions + n_dec);
+  r->visits.assign(s->h_visits, s->h_visits + n_vis);
+  r->fit_errors.assign(s->h_fit, s->h_fit + n_fit);
+  float kms = 0;
+  cudaEventElapsedTime(&kms, s->ev0, s->ev1);
+  r->stats.upload_ms = s->upload_ms;
+  r->stats.commit_ms = kms;
+  r->stats.download_ms = now_ms() - t_k;
+  r->stats.total_ms = now_ms() - t0;
+  r->stats.h2d_bytes = s->h2d_bytes;
+  r->stats.d2h_bytes = 32 + (int64_t)n_dec * sizeof(vc_decision) + (int64_t)n_vis * sizeof(vc_visit) + (int64_t)n_fit * 4;
+  r->stats.kernel_launches = 2;  // k_class_static + k_commit
+  r->stats.n_steps = s->h_counters[3];
+  *out = r;
+  return VC_OK;
+}
+
+size_t vc_result_num_decisions(const vc_result *r) { return r ? r->decisions.size() : 0; }
+const vc_decision *vc_result_decisions(const vc_result *r) { return r ? r->decisions.data() : nullptr; }
+size_t vc_result_num_visits(const vc_result *r) { return r ? r->visits.size() : 0; }
+const vc_visit *vc_result_visits(const vc_result *r) { return r ? r->visits.data() : nullptr; }
+size_t vc_result_num_fit_errors(const vc_result *r) { return r ? r->fit_errors.size() : 0; }
+const int32_t *vc_result_fit_errors(const vc_result *r) { return r ? r->fit_errors.data() : nullptr; }
+const vc_stats *vc_result_stats(const vc_result *r) { return r ? &r->stats : nullptr; }
+void vc_result_free(vc_result *r) { delete r; }
+
+// ---------------------------------------------------------------------------------------
+// dense pass (K1)
+// ---------------------------------------------------------------------------------------
+__global__ void k_best_to_tasks(const int32_t *task_group, const double *g_best_score, const int32_t *g_best_node,
+                                double *best_score, int32_t *best_node, int T);
+
+static int dense_prepare(vc_snapshot *s) {
+  if (s->dense_ready) return VC_OK;
+  free_dense(s);
+  const vc_dims &D = s->dims;
+  const size_t T = D.n_tasks, R = D.n_dims, K = D.n_kdims, N = D.n_nodes;
+  const int nloc = s->dd.node_end - s->dd.node_begin;
+  // group tasks by (class, request record): tasks of one pod template share their whole row
+  struct KeyHash {
+    size_t operator()(const std::string &k) const { return std::hash<std::string>()(k); }
+  };
+  std::unordered_map<std::string, int, KeyHash> index;
+  std::vector<int32_t> group_of(T);
+  std::vector<int32_t> rep;  // representative task of each group
+  std::string key;
+  for (size_t t = 0; t < T; ++t) {
+    key.clear();
+    key.append(reinterpret_cast<const char *>(&s->h_class[t]), 4);
+    key.append(reinterpret_cast<const char *>(&s->h_has[t]), 4);
+    for (size_t d = 0; d < R; ++d) key.append(reinterpret_cast<const char *>(&s->h_req[d * T + t]), 8);
+    for (size_t k = 0; k < K; ++k) key.append(reinterpret_cast<const char *>(&s->h_kreq[k * T + t]), 8);
+    for (size_t k = 0; k < 2; ++k) key.append(reinterpret_cast<const char *>(&s->h_knz[k * T + t]), 8);
+    auto it = index.find(key);
+    if (it == index.end()) {
+      it = index.emplace(key, (int)rep.size()).first;
+      rep.push_back((int32_t)t);
+    }
+    group_of[t] = it->second;
+  }
+  const size_t G = rep.size();
+  s->n_groups = (int)G;
+  std::vector<double> g_req(R * G), g_kreq(K * G), g_knz(2 * G);
+  std::vector<uint32_t> g_has(G);
+  std::vector<int32_t> g_class(G), g_count(G + 1, 0);
+  for (size_t g = 0; g < G; ++g) {
+    int t = rep[g];
+    for (size_t d = 0; d < R; ++d) g_req[d * G + g] = s->h_req[d * T + t];
+    for (size_t k = 0; k < K; ++k) g_kreq[k * G + g] = s->h_kreq[k * T + t];
+    for (size_t k = 0; k < 2; ++k) g_knz[k * G + g] = s->h_knz[k * T + t];
+    g_has[g] = s->h_has[t];
+    g_class[g] = s->h_class[t];
+  }
+  for (size_t t = 0; t < T; ++t) g_count[group_of[t] + 1]++;
+  for (size_t g = 0; g < G; ++g) g_count[g + 1] += g_count[g];
+  std::vector<int32_t> group_tasks(T), fill(g_count.begin(), g_count.end() - 1);
+  for (size_t t = 0; t < T; ++t) group_tasks[fill[group_of[t]]++] = (int32_t)t;
+  // work items: <= 64 rows of one group each
+  const int chunk = 64;
+  std::vector<int32_t> wg, wb, we;
+  for (size_t g = 0; g < G; ++g)
+    for (int b = g_count[g]; b < g_count[g + 1]; b += chunk) {
+      wg.push_back((int32_t)g); wb.push_back(b); we.push_back(std::min(b + chunk, g_count[g + 1]));
+    }
+  s->n_work = (int)wg.size();
+  auto up = [&](auto *&dptr, const auto &vec) -> int {
+    using E = typename std::remove_reference_t<decltype(vec)>::value_type;
+    void *q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, std::max<size_t>(16, vec.size() * sizeof(E))));
+    if (!vec.empty()) CUDA_TRY(cudaMemcpyAsync(q, vec.data(), vec.size() * sizeof(E), cudaMemcpyHostToDevice, s->stream));
+    dptr = reinterpret_cast<std::remove_reference_t<decltype(dptr)>>(q);
+    return VC_OK;
+  };
+  int rc;
+  if ((rc = up(s->g_req, g_req)) || (rc = up(s->g_kreq, g_kreq)) || (rc = up(s->g_knz, g_knz)) || (rc = up(s->g_has, g_has)) ||
+      (rc = up(s->g_class, g_class)) || (rc = up(s->work_group, wg)) || (rc = up(s->work_begin, wb)) ||
+      (rc = up(s->work_end, we)) || (rc = up(s->group_tasks, group_tasks)) || (rc = up(s->task_group, group_of)))
+    return rc;
+  CUDA_TRY(cudaStreamSynchronize(s->stream));  // the staging vectors die with this scope
+  const int nparts = (nloc + 255) / 256;
+  CUDA_TRY(cudaMalloc(&s->g_order, std::max<size_t>(16, G * (size_t)nloc * 8)));
+  CUDA_TRY(cudaMalloc(&s->g_cat, std::max<size_t>(16, G * (size_t)nloc)));
+  CUDA_TRY(cudaMalloc(&s->g_stats, std::max<size_t>(16, G * 4 * 4)));
+  CUDA_TRY(cudaMalloc(&s->g_best_score, std::max<size_t>(16, G * 8)));
+  CUDA_TRY(cudaMalloc(&s->g_best_node, std::max<size_t>(16, G * 4)));
+  CUDA_TRY(cudaMalloc(&s->part_score, std::max<size_t>(16, G * (size_t)std::max(nparts, 1) * 8)));
+  CUDA_TRY(cudaMalloc(&s->part_node, std::max<size_t>(16, G * (size_t)std::max(nparts, 1) * 4)));
+  CUDA_TRY(cudaMalloc(&s->best_score, std::max<size_t>(16, T * 8)));
+  CUDA_TRY(cudaMalloc(&s->best_node, std::max<size_t>(16, T * 4)));
+  s->mw32 = (int)(2 * ((N + 63) / 64));
+  s->dense_ready = true;
+  return VC_OK;
+}
+
+static K1Params dense_params(vc_snapshot *s) {
+  K1Params p;
+  std::memset(&p, 0, sizeof p);
+  p.d = s->dd; p.c = s->dc;
+  p.alloc = s->n_alloc.d(s->in); p.idle = s->n_idle.d(s->in); p.used = s->n_used.d(s->in);
+  p.rel = s->n_rel.d(s->in); p.pip = s->n_pip.d(s->in); p.kalloc = s->n_kalloc.d(s->in);
+  p.kreq = s->n_kreq.d(s->in); p.knz = s->n_knz.d(s->in);
+  p.max_tasks = s->n_max_tasks.d(s->in); p.pod_count = s->n_pod_count.d(s->in); p.cstat = s->cstat;
+  p.n_groups = s->n_groups; p.g_req = s->g_req; p.g_kreq = s->g_kreq; p.g_knz = s->g_knz; p.g_has = s->g_has;
+  p.g_class = s->g_class; p.g_order = s->g_order; p.g_cat = s->g_cat; p.g_stats = s->g_stats;
+  p.g_best_score = s->g_best_score; p.g_best_node = s->g_best_node;
+  p.n_work = s->n_work; p.work_group = s->work_group; p.work_begin = s->work_begin; p.work_end = s->work_end;
+  p.group_tasks = s->group_tasks; p.mask_out = s->mask_out; p.score_out = s->score_out;
+  p.best_score = s->best_score; p.best_node = s->best_node; p.mw32 = s->mw32;
+  return p;
+}
+
+int vc_dense_begin(vc_snapshot *s) {
+  if (!s || !s->uploaded) return fail(VC_EINVAL, "snapshot not uploaded");
+  int rc = dense_prepare(s);
+  if (rc) return rc;
+  const int nloc = s->dd.node_end - s->dd.node_begin;
+  CUDA_TRY(cudaMemsetAsync(s->g_stats, 0, std::max<size_t>(16, (size_t)s->n_groups * 16), s->stream));
+  if (nloc > 0 && s->n_groups > 0) {
+    K1Params p = dense_params(s);
+    dim3 grid((unsigned)((nloc + 255) / 256), (unsigned)s->n_groups);
+    k_group_eval<<<grid, 256, 0, s->stream>>>(p);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return VC_OK;
+}
+
+int vc_dense_stats(vc_snapshot *s, int32_t **stats_dev_out, int32_t *count_out) {
+  if (!s || !s->dense_ready) return fail(VC_EINVAL, "vc_dense_begin first");
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  *stats_dev_out = s->g_stats;
+  *count_out = s->n_groups * 4;
+  return VC_OK;
+}
+
+int vc_dense_finish(vc_snapshot *s, int materialize) {
+  if (!s || !s->dense_ready) return fail(VC_EINVAL, "vc_dense_begin first");
+  const vc_dims &D = s->dims;
+  const size_t T = D.n_tasks, N = D.n_nodes;
+  const int nloc = s->dd.node_end - s->dd.node_begin;
+  if (materialize && !s->matrix_allocated) {
+    CUDA_TRY(cudaMalloc(&s->score_out, std::max<size_t>(16, T * N * 8)));
+    CUDA_TRY(cudaMalloc(&s->mask_out, std::max<size_t>(16, T * (size_t)s->mw32 * 4)));
+    CUDA_TRY(cudaMemsetAsync(s->score_out, 0, std::max<size_t>(16, T * N * 8), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->mask_out, 0, std::max<size_t>(16, T * (size_t)s->mw32 * 4), s->stream));
+    s->matrix_allocated = true;
+  }
+  K1Params p = dense_params(s);
+  const int nparts = std::max(1, (nloc + 255) / 256);
+  if (s->n_groups > 0) {
+    if (nloc > 0) {
+      dim3 grid((unsigned)nparts, (unsigned)s->n_groups);
+      k_group_best_partial<<<grid, 256, 0, s->stream>>>(p, s->part_score, s->part_node);
+      g_launches++;
+    } else {
+      CUDA_TRY(cudaMemsetAsync(s->part_node, 0xff, (size_t)s->n_groups * nparts * 4, s->stream));
+    }
+    k_group_best_final<<<(s->n_groups + 127) / 128, 128, 0, s->stream>>>(p, s->part_score, s->part_node, nparts);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (materialize && s->n_work > 0 && nloc > 0) {
+    dim3 grid((unsigned)((nloc + 511) / 512), (unsigned)s->n_work);
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    k_group_expand<<<grid, 256, 0, s->stream>>>(p);
+    g_launches++;
+    CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (T > 0) {
+    k_best_to_tasks<<<(unsigned)((T + 255) / 256), 256, 0, s->stream>>>(s->task_group, s->g_best_score, s->g_best_node,
+                                                                       s->best_score, s->best_node, (int)T);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return VC_OK;
+}
+
+// per-task best = best of the task's group
+__global__ void k_best_to_tasks(const int32_t *task_group, const double *g_best_score, const int32_t *g_best_node,
+                                double *best_score, int32_t *best_node, int T) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  int g = task_group[t];
+  best_score[t] = g_best_score[g];
+  best_node[t] = g_best_node[g];
+}
+
+int vc_dense_best(vc_snapshot *s, double **best_score_dev_out, int32_t **best_node_dev_out) {
+  if (!s || !s->dense_ready) return fail(VC_EINVAL, "vc_dense_begin first");
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  *best_score_dev_out = s->best_score;
+  *best_node_dev_out = s->best_node;
+  return VC_OK;
+}
+
+int vc_dense_fetch(vc_snapshot *s, uint64_t *mask_out, double *score_out, double *best_score, int32_t *best_node) {
+  if (!s || !s->dense_ready) return fail(VC_EINVAL, "vc_dense_begin first");
+  const size_t T = s->dims.n_tasks, N = s->dims.n_nodes;
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if ((mask_out || score_out) && !s->matrix_allocated) return fail(VC_EINVAL, "matrix was not materialised");
+  if (mask_out) CUDA_TRY(cudaMemcpy(mask_out, s->mask_out, T * (size_t)s->mw32 * 4, cudaMemcpyDeviceToHost));
+  if (score_out) CUDA_TRY(cudaMemcpy(score_out, s->score_out, T * N * 8, cudaMemcpyDeviceToHost));
+  if (best_score) CUDA_TRY(cudaMemcpy(best_score, s->best_score, T * 8, cudaMemcpyDeviceToHost));
+  if (best_node) CUDA_TRY(cudaMemcpy(best_node, s->best_node, T * 4, cudaMemcpyDeviceToHost));
+  return VC_OK;
+}
+
+int vc_score_matrix(vc_snapshot *s, uint64_t *mask_out, double *score_out, double *best_score, int32_t *best_node) {
+  int rc = vc_dense_begin(s);
+  if (rc) return rc;
+  if ((rc = vc_dense_finish(s, 1))) return rc;
+  return vc_dense_fetch(s, mask_out, score_out, best_score, best_node);
+}
+
+int vc_score_matrix_device(vc_snapshot *s, int repeats, double *kernel_ms_out, int64_t *algorithmic_bytes_out) {
+  if (repeats < 1) repeats = 1;
+  double tot = 0, exp_tot = 0;
+  for (int i = 0; i < repeats; ++i) {
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    int rc = vc_dense_begin(s);
+    if (rc) return rc;
+    if ((rc = vc_dense_finish(s, 1))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, s->ev0, s->ev2);
+    cudaEventElapsedTime(&b, s->ev1, s->ev2);
+    if (i == 0 && repeats > 1) continue;  // first pass allocates + zero-fills the matrix
+    tot += a;
+    exp_tot += b;
+  }
+  const int used = repeats > 1 ? repeats - 1 : 1;
+  if (kernel_ms_out) { kernel_ms_out[0] = tot / used; kernel_ms_out[1] = exp_tot / used; }
+  if (algorithmic_bytes_out) {
+    const vc_dims &D = s->dims;
+    const int64_t T = D.n_tasks, R = D.n_dims, Wl = D.label_words, Wt = D.taint_words;
+    const int64_t nloc = s->dd.node_end - s->dd.node_begin;
+    // T*N*(8 + 1/8) + T*(R*8 + 8*Wc) + N*(5*R*8 + 8*(Wl+Wt) + 16), Wc = 4 class words
+    *algorithmic_bytes_out = T * nloc * 8 + T * nloc / 8 + T * (R * 8 + 8 * 4) + nloc * (5 * R * 8 + 8 * (Wl + Wt) + 16);
+  }
+  return VC_OK;
+}
+
+}  // extern "C"

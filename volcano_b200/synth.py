@@ -1,0 +1,209 @@
+"""Seeded synthetic session snapshots of the BASELINE.json configs.
+
+Generates the structure-of-arrays directly (no per-pod Python objects) so that the
+10k x 100k and 50k x 1M shapes build in seconds.  All resource values are integer-valued
+(milli-cpu, bytes, milli-scalars, pod counts) exactly like api.NewResource produces.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from . import abi
+from .snapshot import PluginOption, SchedulerConf, Snapshot, build_conf
+
+DIMS = ["cpu", "memory", "ephemeral-storage", "example.com/foo", "hugepages-2Mi", "nvidia.com/gpu", "pods", "rdma/hca"]
+D_CPU, D_MEM, D_EPH, D_FOO, D_HUGE, D_GPU, D_PODS, D_RDMA = range(8)
+KDIMS = ("cpu", "memory", "nvidia.com/gpu")
+GI = 1 << 30
+MI = 1 << 20
+DEFAULT_SEED = 20260921
+
+
+@dataclass
+class SynthConfig:
+    name: str
+    n_nodes: int
+    n_tasks: int
+    n_queues: int = 1
+    plugins: str = "gang+predicates+nodeorder+binpack"  # '+'-separated
+    utilisation: float = 0.6   # initial Used ~ U(0, utilisation) * Allocatable
+    n_classes: int = 64
+    seed: int = DEFAULT_SEED
+
+
+CONFIGS = {
+    # BASELINE.json configs[0]: plumbing-size case the CPU oracle runs instantly
+    "cfg1": SynthConfig("cfg1", 128, 1024, 1, "gang+predicates+binpack"),
+    # configs[1]: the headline single-GPU workload
+    "cfg2": SynthConfig("cfg2", 10_000, 100_000, 1, "priority+gang+predicates+nodeorder+binpack"),
+    # configs[2]: + DRF + proportion over 16 queues
+    "cfg3": SynthConfig("cfg3", 10_000, 100_000, 16, "priority+gang+drf+predicates+proportion+nodeorder+binpack"),
+    # configs[3] shape (topology-aware scoring is a §8f 'next' row)
+    "cfg4": SynthConfig("cfg4", 50_000, 1_000_000, 16, "priority+gang+drf+predicates+proportion+nodeorder+binpack"),
+    # small shapes for tests
+    "tiny": SynthConfig("tiny", 64, 300, 3, "priority+gang+drf+predicates+proportion+nodeorder+binpack", n_classes=12),
+    "small": SynthConfig("small", 700, 4000, 4, "priority+gang+drf+predicates+proportion+nodeorder+binpack", n_classes=24),
+}
+
+
+def scheduler_conf(cfg: SynthConfig) -> SchedulerConf:
+    names = cfg.plugins.split("+")
+    args = {
+        "binpack": {"binpack.weight": 10, "binpack.cpu": 5, "binpack.memory": 1,
+                    "binpack.resources": "nvidia.com/gpu", "binpack.resources.nvidia.com/gpu": 2},
+        "nodeorder": {},  # default weights: least 1, balanced 1, nodeaffinity 2, tainttoleration 3
+    }
+    tier1 = [PluginOption.defaults(n, args.get(n)) for n in names if n in ("priority", "gang")]
+    tier2 = [PluginOption.defaults(n, args.get(n)) for n in names if n not in ("priority", "gang")]
+    return SchedulerConf(tiers=[t for t in (tier1, tier2) if t], actions=("allocate",))
+
+
+def make_snapshot(cfg: SynthConfig | str, seed: Optional[int] = None) -> Snapshot:
+    if isinstance(cfg, str):
+        cfg = CONFIGS[cfg]
+    rng = np.random.default_rng(cfg.seed if seed is None else seed)
+    N, T, Q, R = cfg.n_nodes, cfg.n_tasks, cfg.n_queues, len(DIMS)
+
+    # ---- jobs: Zipf gang sizes, minAvailable = size (70 %) or size/2 (30 %) ------------------
+    sizes = np.array([1, 2, 4, 8, 16, 64, 256])
+    pz = 1.0 / np.arange(1, len(sizes) + 1)
+    pz /= pz.sum()
+    job_sizes: List[int] = []
+    tot = 0
+    while tot < T:
+        sz = int(rng.choice(sizes, p=pz))
+        sz = min(sz, T - tot)
+        job_sizes.append(sz)
+        tot += sz
+    job_sizes_a = np.array(job_sizes, np.int64)
+    J = len(job_sizes_a)
+    C_ = cfg.n_classes
+    s = Snapshot(N, T, J, Q, C_, J, R, K=len(KDIMS), Wl=1, Wt=1, Z=0, pods_dim=D_PODS)
+    s.dim_names = list(DIMS)
+    s.node_names = [f"node-{i:06d}" for i in range(N)] if N <= 20000 else []
+    s.queue_names = [f"q{i:02d}" for i in range(Q)]
+
+    # ---- nodes: 4 SKUs 40/30/20/10 % ---------------------------------------------------------
+    sku = rng.choice(4, size=N, p=[0.4, 0.3, 0.2, 0.1])
+    cpu = np.array([32, 64, 96, 128])[sku] * 1000.0
+    mem = np.array([128, 256, 768, 1024])[sku] * float(GI)
+    maxpods = np.array([110, 110, 110, 250])[sku]
+    gpus = np.array([0, 0, 8, 8])[sku]
+    a = s.n_allocatable
+    a[D_CPU], a[D_MEM] = cpu, mem
+    a[D_EPH] = np.array([1, 2, 4, 8])[sku] * 1e12 * 1000.0       # ephemeral-storage in milli-bytes
+    a[D_FOO] = 16 * 1000.0
+    a[D_HUGE] = np.array([0, 4, 16, 64])[sku] * float(GI) * 1000.0
+    a[D_GPU] = gpus * 1000.0
+    a[D_PODS] = maxpods
+    a[D_RDMA] = np.where(gpus > 0, 4, 0) * 1000.0
+    u = rng.uniform(0, cfg.utilisation, size=(R, N))
+    used = np.zeros((R, N))
+    used[D_CPU] = np.floor(u[D_CPU] * cpu / 100.0) * 100.0
+    used[D_MEM] = np.floor(u[D_MEM] * mem / (64 * MI)) * (64 * MI)
+    used[D_EPH] = np.floor(u[D_EPH] * a[D_EPH] / 1e12) * 1e12
+    used[D_GPU] = np.floor(u[D_GPU] * gpus) * 1000.0
+    used[D_PODS] = np.floor(u[D_PODS] * maxpods)
+    used[D_RDMA] = np.floor(u[D_RDMA] * a[D_RDMA] / 1000.0) * 1000.0
+    s.n_used[:] = used
+    s.n_idle[:] = a - used
+    s.n_max_tasks[:] = maxpods
+    s.n_pod_count[:] = used[D_PODS].astype(np.int32)
+    kmap = [D_CPU, D_MEM, D_GPU]
+    for k, d in enumerate(kmap):
+        scale = 1000.0 if d == D_GPU else 1.0
+        s.n_k8s_allocatable[k] = a[d] / scale
+        s.n_k8s_requested[k] = used[d] / scale
+        s.n_k8s_nonzero_requested[k] = used[d] / scale
+    # 64 label bits: zone one-hot(16) | sku one-hot(4) | pool one-hot(8) | 36 booleans p=0.1
+    zone = rng.integers(0, 16, N)
+    pool = rng.integers(0, 8, N)
+    lb = (np.uint64(1) << zone.astype(np.uint64)) | (np.uint64(1) << (16 + sku).astype(np.uint64)) | \
+         (np.uint64(1) << (20 + pool).astype(np.uint64))
+    rb = rng.random((36, N)) < 0.1
+    for b in range(36):
+        lb |= rb[b].astype(np.uint64) << np.uint64(28 + b)
+    s.n_label_bits[0] = lb
+    tb = np.zeros(N, np.uint64)
+    rt = rng.random((32, N)) < 0.02
+    for b in range(32):
+        tb |= rt[b].astype(np.uint64) << np.uint64(b)
+    s.n_taint_hard[0] = tb
+
+    # ---- classes: 25 % with a nodeSelector on <= 2 label bits, 10 % with tolerations -----------
+    for c in range(C_):
+        r = rng.random()
+        if c > 0 and r < 0.25:
+            bits = [int(rng.integers(0, 16))] if rng.random() < 0.5 else [16 + int(rng.integers(0, 4))]
+            if rng.random() < 0.5:
+                bits.append(20 + int(rng.integers(0, 8)))
+            for b in bits:
+                s.c_selector[c, 0] |= np.uint64(1) << np.uint64(b)
+        if c > 0 and rng.random() < 0.10:
+            s.c_tolerated_hard[c, 0] = np.uint64(rng.integers(0, 2**32))
+        if c > 0 and rng.random() < 0.15:
+            s.c_n_preferred[c] = 1
+            s.c_preferred[c, 0, 0] = np.uint64(1) << np.uint64(int(rng.integers(0, 16)))
+            s.c_preferred_weight[c, 0] = int(rng.integers(1, 101))
+
+    # ---- tasks: one request type and one class per job (a gang is homogeneous) ----------------
+    types = np.array([
+        # cpu(milli), mem(bytes), gpu(count)
+        [500, 1 * GI, 0], [1000, 2 * GI, 0], [2000, 8 * GI, 0], [4000, 16 * GI, 0], [8000, 64 * GI, 1], [32000, 256 * GI, 8],
+    ], dtype=np.float64)
+    job_type = rng.choice(6, size=J, p=[0.30, 0.30, 0.20, 0.10, 0.08, 0.02])
+    job_class = rng.integers(0, C_, J)
+    job_of_task = np.repeat(np.arange(J), job_sizes_a)
+    tt = job_type[job_of_task]
+    s.t_resreq[D_CPU] = types[tt, 0]
+    s.t_resreq[D_MEM] = types[tt, 1]
+    s.t_resreq[D_GPU] = types[tt, 2] * 1000.0
+    s.t_resreq[D_PODS] = 1.0
+    has = np.full(T, 1 << D_PODS, np.uint32)
+    has[types[tt, 2] > 0] |= np.uint32(1 << D_GPU)
+    s.t_req_has[:] = has
+    for k, col in enumerate((0, 1, 2)):
+        s.t_k8s_req[k] = types[tt, col]
+        s.t_k8s_nonzero_req[k] = types[tt, col]
+    s.t_job[:] = job_of_task
+    s.t_klass[:] = job_class[job_of_task]
+    s.t_role[:] = job_of_task  # one role row per job
+    s.t_priority[:] = 1
+    starts = np.concatenate([[0], np.cumsum(job_sizes_a)[:-1]])
+    s.t_pod_index[:] = np.arange(T) - starts[job_of_task]
+    s.t_uid_rank[:] = np.arange(T, dtype=np.uint32)
+
+    # ---- jobs --------------------------------------------------------------------------------
+    full = rng.random(J) < 0.7
+    s.j_min_available[:] = np.where(full, job_sizes_a, np.maximum(1, job_sizes_a // 2))
+    s.j_queue[:] = rng.integers(0, Q, J)
+    s.j_priority[:] = rng.integers(0, 3, J)
+    s.j_creation_ts[:] = rng.integers(0, 1000, J)
+    s.j_uid_rank[:] = np.arange(J, dtype=np.uint32)
+    s.j_n_tasks_total[:] = job_sizes_a
+    s.j_valid_num[:] = job_sizes_a
+    s.j_role_off[:] = np.arange(J + 1)
+    s.r_valid[:] = job_sizes_a
+    s.r_flags[:] = 0  # named role "worker", not in TaskMinAvailable
+    s.job_names = []
+
+    # ---- queues ------------------------------------------------------------------------------
+    s.q_weight[:] = rng.integers(1, 5, Q)
+    s.q_uid_rank[:] = np.arange(Q, dtype=np.uint32)
+    if Q >= 4:  # two queues with capability caps
+        total = a.sum(axis=1)
+        for qi in (1, 3):
+            s.q_capability[:, qi] = np.floor(total * 0.03)
+            s.q_capability_has[qi] = np.uint32(abi.VC_RES_HAS_ANY | sum(1 << d for d in range(2, R)))
+    # proportion request = sum of pending Resreq per queue (nothing allocated at open)
+    jq = s.j_queue[job_of_task]
+    for d in range(R):
+        s.q_request[d] = np.bincount(jq, weights=s.t_resreq[d], minlength=Q)
+    for qi in range(Q):
+        m = jq == qi
+        s.q_request_has[qi] = np.bitwise_or.reduce(has[m]) if m.any() else 0
+    s.conf = build_conf(scheduler_conf(cfg), DIMS, KDIMS)
+    return s
