@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py — pods scheduled/sec of the allocate hot path (BASELINE.json metric).
+
+A "step" is ONE scheduling cycle of the workload (BASELINE configs[1]: 10k nodes x 100k pending tasks,
+8 resource dims, gang + predicates + nodeorder + binpack) through the reference-facing C ABI:
+
+  value  : placements / device time of vc_allocate_run's commit kernel, snapshot already resident in HBM
+  e2e    : placements / wall time of vc_snapshot_upload (host SoA -> HBM, session-open) + vc_allocate_run +
+           result fetch to host buffers — the call sequence the cgo shim makes every cycle
+  roofline : the dense task x node mask + score kernel (K1) timed in the same process with CUDA
+             events; algorithmic bytes / time against the measured HBM peak of MEASURED_PEAKS.json
+  cpu_baseline : the CPU restatement of the reference path (oracle/, "port") on this box's host cores
+
+--impl reference times that CPU restatement alone (the Go reference cannot be built: no go toolchain).
+N > 1 (torchrun): every rank schedules its own cluster shard of the same shape (Volcano's node-sharded
+scheduler replicas, --scheduler-sharding-mode); no data-path collective; value = sum over ranks / max time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = "cfg2"
+METRIC = "pods scheduled/sec"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [ln.strip().split(", ") for ln in open(self.f.name) if ln.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_oracle(snap, threads):
+    from oracle.pyoracle import OracleSession
+    o = OracleSession(snap, threads=threads)
+    t0 = time.perf_counter()
+    dec, vis, fe = o.allocate()
+    dt = time.perf_counter() - t0
+    o.close()
+    return len(dec), dt
+
+
+def reference_arm(args, rank, world):
+    """The reference's CPU implementation of the path = oracle port (kind "port"), all usable host threads
+    (the reference runs 16 workers per task: util/predicate_helper.go:133)."""
+    if rank != 0:
+        return
+    from volcano_b200.synth import make_snapshot
+    snap = make_snapshot(WORKLOAD)
+    threads = max(1, min(16, cpu_cores()))
+    for _ in range(args.warmup if args.warmup < 2 else 1):  # warm-up is a CPU cache matter only; one pass
+        run_oracle(snap, threads)
+    placed, times = 0, []
+    for _ in range(args.steps):
+        n, dt = run_oracle(snap, threads)
+        placed += n
+        times.append(dt)
+    total = sum(times)
+    val = placed / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "pods/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: 10k nodes x 100k tasks, R=8, gang+predicates+nodeorder+binpack, "
+                               "percentage-nodes-to-find=100 (parity mode)"},
+        "cpu_baseline": {"value": val, "unit": "pods/s", "cores": threads, "kind": "port",
+                         "sample": "full workload, one allocate cycle per step"},
+        "e2e": {"value": val, "unit": "pods/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    from volcano_b200 import engine
+    from volcano_b200.synth import CONFIGS, make_snapshot
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libvcalloc has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = CONFIGS[args.workload]
+    snap = make_snapshot(cfg, seed=cfg.seed + rank)  # every rank its own cluster shard of the same shape
+    eng = engine.Engine(snap, device=local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also allocates every device buffer) ----
+    for _ in range(max(3, args.warmup)):
+        eng.upload()
+        res = eng.allocate()
+    # ---- device-timed value: commit kernel on a resident snapshot -------------------------------
+    eng.upload()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    dev_ms, placed = [], 0
+    n_steps = 0
+    for _ in range(args.steps):
+        flush.fill_(1)  # L2 flush between timed iterations
+        torch.cuda.synchronize()
+        res = eng.allocate()
+        dev_ms.append(res.stats["commit_ms"])  # CUDA events on the launching stream around k_commit
+        placed += len(res.decisions)
+        n_steps += res.stats["n_steps"]
+    barrier()
+    t_dev = sum(dev_ms) / 1e3
+    # ---- e2e: host buffers -> upload -> allocate -> decisions on the host ------------------------
+    barrier()
+    t0 = time.perf_counter()
+    e2e_placed, h2d, d2h = 0, 0, 0
+    for _ in range(args.steps):
+        eng.upload()
+        res = eng.allocate()
+        e2e_placed += len(res.decisions)
+        h2d, d2h = res.stats["h2d_bytes"], res.stats["d2h_bytes"]
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+    # ---- roofline kernel: dense task x node mask + score matrix ---------------------------------
+    roof = None
+    if rank == 0:
+        try:
+            dense_ms, expand_ms, nbytes = eng.score_matrix_device(repeats=4)
+            peak, how = _peaks()
+            ach = nbytes / (expand_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "k_group_expand (task x node mask + f64 score matrix, K1b)",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": how, "algorithmic_bytes": nbytes, "kernel_ms": expand_ms,
+                    "dense_pass_ms": dense_ms, "achieved_whole_pass": nbytes / (dense_ms * 1e-3) / 1e9}
+        except Exception as ex:  # e.g. not enough memory for the matrix
+            roof = {"bound": "hbm", "error": str(ex)}
+    # ---- aggregate over ranks: max time, sum of units ---------------------------------------------
+    if dist is not None:
+        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        cc = torch.tensor([placed, e2e_placed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        t_dev, t_e2e = tt.tolist()
+        placed, e2e_placed = cc.tolist()
+    value = placed / t_dev
+    e2e_value = e2e_placed / t_e2e
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = max(1, min(16, cpu_cores()))
+        n, dt = run_oracle(snap, threads)
+        cpu = {"value": n / dt, "unit": "pods/s", "cores": threads, "kind": "port",
+               "sample": "full workload, one allocate cycle (%.1f s)" % dt}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "pods/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {cfg.n_nodes} nodes x {cfg.n_tasks} tasks, R=8, {cfg.plugins}, "
+                                   "percentage-nodes-to-find=100 (parity mode)",
+                       "parallelism": "1 scheduler shard per GPU" if world > 1 else "1 GPU",
+                       "l2": "256 MB buffer written between timed iterations",
+                       "timed_region": "k_commit (CUDA events on its stream); e2e = upload + run + fetch wall time",
+                       "sweeps_per_step": n_steps / args.steps},
+            "e2e": {"value": e2e_value, "unit": "pods/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": 2 * args.steps,  # k_class_static + k_commit per e2e step (1 per device-timed step)
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "commit_kernel": {"bound": "latency", "ms": 1e3 * t_dev / args.steps,
+                              "us_per_sweep": 1e6 * t_dev / max(1, n_steps), "ctas": None},
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
