@@ -265,6 +265,8 @@ typedef struct vc_stats {
   int64_t h2d_bytes, d2h_bytes;
   int32_t kernel_launches;
   int32_t n_steps;    /* node sweeps executed */
+  int64_t prof_cycles[8]; /* commit kernel phase timers (SM cycles of CTA 0): 0 queue/job control, 1 task fetch +
+                             gates, 2 node sweep, 3 mailbox exchange, 4 apply + bookkeeping */
 } vc_stats;
 
 typedef struct vc_snapshot vc_snapshot;

@@ -180,7 +180,7 @@ class vc_visit(C.Structure):
 class vc_stats(C.Structure):
     _fields_ = [("upload_ms", C.c_double), ("commit_ms", C.c_double), ("download_ms", C.c_double),
                 ("total_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("kernel_launches", C.c_int32), ("n_steps", C.c_int32)]
+                ("kernel_launches", C.c_int32), ("n_steps", C.c_int32), ("prof_cycles", C.c_int64 * 8)]
 
 
 # every symbol include/vcalloc.h declares: name -> (restype, argtypes)

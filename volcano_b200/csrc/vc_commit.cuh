@@ -69,6 +69,7 @@ struct K2Params {
   vc_visit *visits;
   int32_t *fit_errors;
   int32_t *counters;  // 0 n_decisions, 1 n_visits, 2 n_fit_errors, 3 n_steps, 4 error
+  long long *prof;    // [8] phase cycle counters of CTA 0
 };
 
 // ---------------------------------------------------------------------------------------
@@ -124,6 +125,8 @@ struct Ctl {
   int w_node[2][32];
   int w_cnt[2][32];
   int w_soft[2][32];
+  long long prof[8];
+  long long prof_last;
   int pick;  // scratch for warp0 -> CTA broadcasts
   int pick2;
 };
@@ -176,42 +179,78 @@ __device__ __forceinline__ void local_warp_reduce(Local &l) {
   }
 }
 
-// All-gather of one Local per CTA. Called by warp 0 of every CTA with the CTA's folded contribution
-// (identical in all lanes); returns the global fold in all lanes of warp 0.
+// All-gather of one Local per CTA through the L2-resident mailbox. Called by warp 0 of every CTA with the
+// CTA's folded contribution (identical in all lanes); returns the global fold in all lanes of warp 0.
+// Each CTA owns one 256-byte block per parity (blocks of different CTAs hash to different L2 slices, so
+// the G x G reads of one step spread over the whole L2 instead of hammering a few slices). A record
+// carries its own sequence number, so readers validate each 16-byte unit on its own: no fence needed.
+//   FULL = false: one unit  {score0, node0, seq<<2 | min(cnt0,2)}            (no FutureIdle gradient, no
+//                                                                              normalising batch scorer)
+//   FULL = true : three units {score0,node0,seq} {score1,node1,seq} {cnt0,cnt1,soft0|soft1<<16,seq}
+#define MBOX_STRIDE 16  // uint4 per slot = 256 bytes
+template <bool FULL>
 __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigned seq) {
   const int lane = threadIdx.x & 31;
   const int G = p.n_cta;
-  uint4 *base = p.mbox + (size_t)(seq & 1u) * 3 * G;
-  if (lane < 3) {
-    uint4 v;
-    if (lane < 2) {
-      unsigned long long sb = (unsigned long long)__double_as_longlong(mine.score[lane]);
-      v = make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)mine.node[lane], seq);
-    } else {
-      v = make_uint4((unsigned)mine.cnt[0], (unsigned)mine.cnt[1],
-                     (unsigned)mine.soft[0] | ((unsigned)mine.soft[1] << 16), seq);
+  uint4 *base = p.mbox + (size_t)(seq & 1u) * G * MBOX_STRIDE;
+  if (FULL) {
+    if (lane < 3) {
+      uint4 v;
+      if (lane < 2) {
+        unsigned long long sb = (unsigned long long)__double_as_longlong(mine.score[lane]);
+        v = make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)mine.node[lane], seq);
+      } else {
+        v = make_uint4((unsigned)mine.cnt[0], (unsigned)mine.cnt[1],
+                       (unsigned)mine.soft[0] | ((unsigned)mine.soft[1] << 16), seq);
+      }
+      mbox_store(base + (size_t)blockIdx.x * MBOX_STRIDE + lane, v);
     }
-    mbox_store(base + (size_t)lane * G + blockIdx.x, v);
+  } else if (lane == 0) {
+    unsigned long long sb = (unsigned long long)__double_as_longlong(mine.score[0]);
+    mbox_store(base + (size_t)blockIdx.x * MBOX_STRIDE,
+               make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)mine.node[0], (seq << 2) | (unsigned)min(mine.cnt[0], 2)));
   }
   Local acc;
   local_init(acc);
-  for (int s = lane; s < G; s += 32) {
-    uint4 a, b, c;
-    do { a = mbox_load(base + s); } while (a.w != seq);
-    do { b = mbox_load(base + (size_t)G + s); } while (b.w != seq);
-    do { c = mbox_load(base + (size_t)2 * G + s); } while (c.w != seq);
-    Local o;
-    o.score[0] = __longlong_as_double((long long)((unsigned long long)a.x | ((unsigned long long)a.y << 32)));
-    o.node[0] = (int)a.z;
-    o.score[1] = __longlong_as_double((long long)((unsigned long long)b.x | ((unsigned long long)b.y << 32)));
-    o.node[1] = (int)b.z;
-    o.cnt[0] = (int)c.x;
-    o.cnt[1] = (int)c.y;
-    o.soft[0] = (int)(c.z & 0xffffu);
-    o.soft[1] = (int)(c.z >> 16);
-    local_fold(acc, o);
+  for (int s0 = 0; s0 < G; s0 += 32 * 4) {  // up to 4 slots per lane in flight
+    uint4 a[4];
+    bool need[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) need[k] = (s0 + k * 32 + lane) < G;
+    bool pending;
+    do {
+      pending = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (need[k]) a[k] = mbox_load(base + (size_t)(s0 + k * 32 + lane) * MBOX_STRIDE);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!need[k]) continue;
+        const bool ok = FULL ? (a[k].w == seq) : ((a[k].w >> 2) == (seq & 0x3fffffffu));
+        if (!ok) { pending = true; continue; }
+        Local o;
+        local_init(o);
+        o.score[0] = __longlong_as_double((long long)((unsigned long long)a[k].x | ((unsigned long long)a[k].y << 32)));
+        o.node[0] = (int)a[k].z;
+        if (FULL) {
+          const uint4 *sl = base + (size_t)(s0 + k * 32 + lane) * MBOX_STRIDE;
+          uint4 b, c;
+          do { b = mbox_load(sl + 1); } while (b.w != seq);
+          do { c = mbox_load(sl + 2); } while (c.w != seq);
+          o.score[1] = __longlong_as_double((long long)((unsigned long long)b.x | ((unsigned long long)b.y << 32)));
+          o.node[1] = (int)b.z;
+          o.cnt[0] = (int)c.x; o.cnt[1] = (int)c.y;
+          o.soft[0] = (int)(c.z & 0xffffu); o.soft[1] = (int)(c.z >> 16);
+        } else {
+          o.cnt[0] = (int)(a[k].w & 3u);
+        }
+        local_fold(acc, o);
+        need[k] = false;
+      }
+    } while (pending);
   }
   local_warp_reduce(acc);
+  if (!FULL) acc.cnt[0] = min(acc.cnt[0], 2);
   return acc;
 }
 
@@ -355,6 +394,18 @@ __device__ __forceinline__ JobKey key_of(const HeapEnt &e) {
 // =======================================================================================
 extern __shared__ __align__(16) unsigned char k2_smem[];
 
+// phase timers (cycles, CTA 0 / thread 0): 0 queue+job control, 1 task fetch + gates, 2 node sweep,
+// 3 mailbox exchange, 4 apply + bookkeeping
+#define PROF_MARK(k)                                  \
+  do {                                                \
+    if (tid == 0 && cta == 0) {                       \
+      long long now_ = clock64();                     \
+      S.prof[k] += now_ - S.prof_last;                \
+      S.prof_last = now_;                             \
+    }                                                 \
+  } while (0)
+
+template <bool FUT, bool SOFT>
 __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   const DevConf &c = p.c;
   const int R = p.d.R, K = p.d.K, N = p.d.N, J = p.d.J, Q = p.d.Q, NR = p.d.NR, T = p.d.T;
@@ -448,6 +499,8 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   if (tid == 0) {
     S.seq = 0;
     S.n_dec = S.n_vis = S.n_fit = S.n_steps = 0;
+    for (int k = 0; k < 8; ++k) S.prof[k] = 0;
+    S.prof_last = clock64();
   }
   __syncthreads();
 
@@ -591,6 +644,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
     // =================================================================================
     for (;;) {
       if (S.cursor >= S.task_end) break;  // tasks.Empty()
+      PROF_MARK(4);
       // ---- tasks.Pop() + task record ----
       const int t = p.task_order[S.cursor];
       __syncthreads();
@@ -620,13 +674,13 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       // ---- ph.PredicateNodes + alloc.prioritizeNodes over this CTA's nodes ----
       const TaskRec &trec = S.trec;
       const uint32_t *cs_row = p.cstat + (size_t)trec.klass * N + nbase;
-      Local mine;
-      local_init(mine);
-      // With a normalising batch scorer two passes are needed (max over the candidate set first);
-      // pass 0 = categories, counts and max soft-taint count; pass 1 = scores.
-      const int n_pass = c.soft_active ? 2 : 1;
-      int g_soft[2] = {0, 0};
+      PROF_MARK(1);
+      // With a normalising batch scorer (SOFT) two passes are needed: pass 0 = categories, counts and the
+      // max soft-taint count of the candidate set; pass 1 = scores.
+      constexpr int n_pass = SOFT ? 2 : 1;
+      int g_soft0 = 0, g_soft1 = 0;
       for (int pass = 0; pass < n_pass; ++pass) {
+        Local mine;
         local_init(mine);
         for (int i = tid; i < nmine; i += blockDim.x) {
           SmemNodeView nv{sn, i};
@@ -635,37 +689,42 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
           if (!(use_cache && ((sn.nerr[i] >> rl) & 1ull))) {
             bool ok = (cs & CS_STATIC_OK) != 0;
             if (c.pred_predicates && sn.max_tasks[i] <= sn.pod_count[i]) ok = false;
-            int fc = fit_category(c, R, trec, nv);
+            int fc = fit_category_t<FUT>(R, trec, nv);
             if (ok && fc != 2) cat = fc;
             else if (use_cache && pass == 0) sn.nerr[i] |= (1ull << rl);
           }
           if (cat == 2) continue;
-          const int soft = (cs >> CS_SOFT_SHIFT) & 0xff;
-          mine.cnt[cat] += 1;
-          mine.soft[cat] = max(mine.soft[cat], soft);
-          if (n_pass == 2 && pass == 0) continue;
+          const int soft = SOFT ? (int)((cs >> CS_SOFT_SHIFT) & 0xff) : 0;
+          const bool c0 = !FUT || cat == 0;
+          if (c0) { mine.cnt[0] += 1; mine.soft[0] = max(mine.soft[0], soft); }
+          else { mine.cnt[1] += 1; mine.soft[1] = max(mine.soft[1], soft); }
+          if (SOFT && pass == 0) continue;
           double order = 0.0;
           bool has_order = node_order(c, R, K, trec, nv, cs, &order);
-          double sc = total_score(c, has_order, order, soft, g_soft[cat]);
+          double sc = total_score(c, has_order, order, soft, c0 ? g_soft0 : g_soft1);
           const int n = nbase + i;
-          if (mine.node[cat] < 0 || better(sc, n, mine.score[cat], mine.node[cat])) {
-            mine.score[cat] = sc;
-            mine.node[cat] = n;
+          if (c0) {
+            if (mine.node[0] < 0 || better(sc, n, mine.score[0], mine.node[0])) { mine.score[0] = sc; mine.node[0] = n; }
+          } else {
+            if (mine.node[1] < 0 || better(sc, n, mine.score[1], mine.node[1])) { mine.score[1] = sc; mine.node[1] = n; }
           }
         }
         // CTA-level fold
         local_warp_reduce(mine);
         if (lane == 0) {
+#pragma unroll
           for (int k = 0; k < 2; ++k) {
             S.w_score[k][warp] = mine.score[k]; S.w_node[k][warp] = mine.node[k];
             S.w_cnt[k][warp] = mine.cnt[k]; S.w_soft[k][warp] = mine.soft[k];
           }
         }
         __syncthreads();
+        PROF_MARK(2);
         if (warp == 0) {
           Local l;
           local_init(l);
           if (lane < nwarps) {
+#pragma unroll
             for (int k = 0; k < 2; ++k) {
               l.score[k] = S.w_score[k][lane]; l.node[k] = S.w_node[k][lane];
               l.cnt[k] = S.w_cnt[k][lane]; l.soft[k] = S.w_soft[k][lane];
@@ -673,17 +732,19 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
           }
           local_warp_reduce(l);
           const unsigned seq = S.seq + 1;
-          Local g = exchange(p, l, seq);
+          Local g = exchange<(FUT || SOFT)>(p, l, seq);
           if (lane == 0) {
             S.seq = seq;
+#pragma unroll
             for (int k = 0; k < 2; ++k) {
               S.cnt[k] = g.cnt[k]; S.best_node[k] = g.node[k]; S.best_score[k] = g.score[k]; S.max_soft[k] = g.soft[k];
             }
           }
+          PROF_MARK(3);
         }
         __syncthreads();
-        g_soft[0] = S.max_soft[0];
-        g_soft[1] = S.max_soft[1];
+        g_soft0 = S.max_soft[0];
+        g_soft1 = S.max_soft[1];
         if (S.cnt[0] + S.cnt[1] == 0) break;
       }
       if (tid == 0) S.n_steps += 1;
@@ -746,6 +807,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       if (ctl_job_ready(c, S)) break;  // ssn.SubJobReady, allocate.go:676-678
     }
 
+    PROF_MARK(4);
     // ---- statement outcome, allocate.go:681-693 and :330-337 ----
     const bool ready = ctl_job_ready(c, S);
     const bool stmt = ready || ctl_job_pipelined(c, S);
@@ -844,6 +906,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       q_active[q] = 1;  // queues.Push(queue), allocate.go:346
     }
     __syncthreads();
+    PROF_MARK(0);
   }
 
   // ---- epilogue: node state back to HBM, counters ----
@@ -863,5 +926,6 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
     p.counters[1] = S.n_vis;
     p.counters[2] = S.n_fit;
     p.counters[3] = S.n_steps;
+    for (int k = 0; k < 8; ++k) p.prof[k] = S.prof[k];
   }
 }

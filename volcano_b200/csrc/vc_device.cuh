@@ -219,6 +219,24 @@ __device__ __forceinline__ int fit_category(const DevConf &c, int R, const TaskR
   return fit_idle ? 0 : 1;
 }
 
+template <bool FUT, class NV>
+__device__ __forceinline__ int fit_category_t(int R, const TaskRec &t, const NV &nv) {
+  bool fit_idle = true, fit_future = true;
+  for (int d = 0; d < R; ++d) {
+    if (d >= 2 && !(t.has & (1u << d))) continue;
+    double idle = nv.idle(d);
+    double rq = t.req[d];
+    if (!le_eps(rq, idle)) fit_idle = false;
+    if (FUT) {
+      double fut = (idle + nv.rel(d)) - nv.pip(d);
+      if (!le_eps(rq, fut)) fit_future = false;
+    }
+  }
+  if (!FUT) return fit_idle ? 0 : 2;
+  if (!fit_future) return 2;
+  return fit_idle ? 0 : 1;
+}
+
 // (score, node) ordering of util.SelectBestNodeAndScore with the canonical tie-break.
 __host__ __device__ __forceinline__ bool better(double sa, int na, double sb, int nb) {
   return sa > sb || (sa == sb && na < nb);

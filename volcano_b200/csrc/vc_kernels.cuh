@@ -192,7 +192,7 @@ __device__ __forceinline__ bool k1_final(const K1Params &p, int g, int li, int n
   uint8_t cw = p.g_cat[(size_t)g * nloc + li];
   int cat = cw & 3;
   *feasible = cat != 2;
-  if (cat != chosen) { *score = 0.0; return false; }
+  if (cat == 2 || cat != chosen) { *score = 0.0; return false; }
   *score = total_score(p.c, !(cw & 0x80), p.g_order[(size_t)g * nloc + li], klassN_word_soft, max_soft);
   return true;
 }

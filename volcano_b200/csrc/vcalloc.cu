@@ -114,6 +114,8 @@ struct vc_snapshot {
   HeapEnt *rep_heap = nullptr;
   size_t rep_i32_stride = 0, rep_f64_stride = 0, rep_heap_stride = 0;
   uint4 *mbox = nullptr;
+  long long *d_prof = nullptr;
+  long long h_prof[8] = {0};
   vc_decision *d_decisions = nullptr;
   vc_visit *d_visits = nullptr;
   int32_t *d_fit = nullptr, *d_counters = nullptr;
@@ -290,7 +292,7 @@ void vc_snapshot_destroy(vc_snapshot *s) {
   if (!s) return;
   free_dense(s);
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
-                   s->rep_i32, s->rep_f64, s->rep_heap, s->mbox, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
+                   s->rep_i32, s->rep_f64, s->rep_heap, s->mbox, s->d_prof, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
   for (void *p : dptrs) if (p) cudaFree(p);
   void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters};
   for (void *p : hptrs) if (p) cudaFreeHost(p);
@@ -601,7 +603,9 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
     CUDA_TRY(cudaMalloc(&s->rep_heap, std::max<size_t>(16, std::max<size_t>(heap_stride, 1) * G * sizeof(HeapEnt))));
     s->rep_i32_stride = i32_stride; s->rep_f64_stride = f64_stride; s->rep_heap_stride = heap_stride;
   }
-  if (!s->mbox) CUDA_TRY(cudaMalloc(&s->mbox, sizeof(uint4) * 2 * 3 * 1024));
+  const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024;
+  if (!s->mbox) CUDA_TRY(cudaMalloc(&s->mbox, mbox_bytes));
+  if (!s->d_prof) CUDA_TRY(cudaMalloc(&s->d_prof, 8 * sizeof(long long)));
   if (!s->d_decisions) {
     CUDA_TRY(cudaMalloc(&s->d_decisions, std::max<size_t>(1, T) * sizeof(vc_decision)));
     CUDA_TRY(cudaMalloc(&s->d_visits, (T + J + 1) * sizeof(vc_visit)));
@@ -612,7 +616,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
     CUDA_TRY(cudaMallocHost(&s->h_fit, std::max<size_t>(1, T) * 4));
     CUDA_TRY(cudaMallocHost(&s->h_counters, 8 * 4));
   }
-  CUDA_TRY(cudaMemsetAsync(s->mbox, 0, sizeof(uint4) * 2 * 3 * 1024, s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->mbox, 0, mbox_bytes, s->stream));
   CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 8 * 4, s->stream));
   // working copies of the mutable node state (the uploaded snapshot stays intact for re-runs / K1)
   CUDA_TRY(cudaMemcpyAsync(s->w_idle, s->n_idle.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
@@ -648,19 +652,23 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   p.rep_heap = s->rep_heap; p.rep_heap_stride = std::max<size_t>(heap_stride, 1);
   p.mbox = s->mbox;
   p.decisions = s->d_decisions; p.visits = s->d_visits; p.fit_errors = s->d_fit; p.counters = s->d_counters;
+  p.prof = s->d_prof;
 
   if (G > 1024) return fail(VC_EUNSUPPORTED, "too many CTAs");
-  CUDA_TRY(cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+  const void *kfn = s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
+                                     : (s->dc.soft_active ? (const void *)k_commit<false, true> : (const void *)k_commit<false, false>);
+  CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
   int max_blocks = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, k_commit, s->block, s->smem_bytes));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, kfn, s->block, s->smem_bytes));
   if (max_blocks * g_sm_count < G)
     return fail(VC_EUNSUPPORTED, "commit kernel cannot be co-resident: %d CTAs x %zu B smem (max %d/SM)", G, s->smem_bytes, max_blocks);
   void *args[] = {&p};
   CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-  CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_commit, dim3(G), dim3(s->block), args, s->smem_bytes, s->stream));
+  CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(G), dim3(s->block), args, s->smem_bytes, s->stream));
   g_launches++;
   CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
   CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * 4, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->h_prof, s->d_prof, 8 * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   const double t_k = now_ms();
   const int n_dec = s->h_counters[0], n_vis = s->h_counters[1], n_fit = s->h_counters[2];
@@ -682,6 +690,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->stats.d2h_bytes = 32 + (int64_t)n_dec * sizeof(vc_decision) + (int64_t)n_vis * sizeof(vc_visit) + (int64_t)n_fit * 4;
   r->stats.kernel_launches = 2;  // k_class_static + k_commit
   r->stats.n_steps = s->h_counters[3];
+  for (int k = 0; k < 8; ++k) r->stats.prof_cycles[k] = s->h_prof[k];
   *out = r;
   return VC_OK;
 }

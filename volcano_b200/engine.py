@@ -98,7 +98,7 @@ class Engine:
             vis = _struct_array(self.L.vc_result_visits(r), nv, VISIT_DTYPE)
             fe = np.ctypeslib.as_array(self.L.vc_result_fit_errors(r), (nf,)).copy() if nf else np.zeros(0, np.int32)
             st = self.L.vc_result_stats(r).contents
-            stats = {k: getattr(st, k) for k, _ in abi.vc_stats._fields_}
+            stats = {k: (list(getattr(st, k)) if k == "prof_cycles" else getattr(st, k)) for k, _ in abi.vc_stats._fields_}
         finally:
             self.L.vc_result_free(r)
         return AllocateResult(dec, vis, fe, stats)
