@@ -1,0 +1,58 @@
+"""The C-ABI library builds for sm_100a, loads, exports every symbol of include/vcalloc.h, and — on a box
+without a GPU — refuses to compute instead of falling back to a CPU path."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from volcano_b200.build import build_lib
+    from volcano_b200 import engine
+    build_lib()
+    return engine.load_library()
+
+
+def test_exports_every_declared_symbol(lib):
+    from volcano_b200 import abi
+    hdr = open(os.path.join(ROOT, "include", "vcalloc.h")).read()
+    declared = set(re.findall(r"\b(vc_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"vc_plugin_option", "vc_tasks"}  # "vc_tasks (best-effort, gated)" is prose in a comment
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libvcalloc.so lacks {name}"
+    assert declared == set(abi.SYMBOLS), declared ^ set(abi.SYMBOLS)
+    assert lib.vc_abi_version() == abi.VC_ABI_VERSION
+
+
+def test_struct_sizes_match_header(lib):
+    from volcano_b200 import abi
+    assert C.sizeof(abi.vc_decision) == 24 and C.sizeof(abi.vc_visit) == 16
+    assert C.sizeof(abi.vc_dims) == 12 * 4
+    assert C.sizeof(abi.vc_conf) == 4 + 16 * 12 + 4 + 16 * 4 + 5 * 4 + 4 * 4 + 4 + 5 * 4
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from volcano_b200 import abi, engine
+    from volcano_b200.synth import make_snapshot
+    assert lib.vc_init(0) == abi.VC_ENODEV
+    assert b"no CPU path" in lib.vc_last_error()
+    with pytest.raises(engine.VcError) as ei:
+        engine.gpu_engine(make_snapshot("tiny"))
+    assert ei.value.code == abi.VC_ENODEV
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "volcano_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in src and "oracle/" not in src and "import oracle" not in src, f
