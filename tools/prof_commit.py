@@ -21,13 +21,13 @@ r = e.allocate()
 t2 = time.perf_counter()
 st = r.stats
 prof = st["prof_cycles"]
-tot = sum(prof) or 1
+tot = sum(prof[:5]) or 1
 names = ["queue/job control", "task fetch+gates", "node sweep", "exchange", "apply+bookkeeping"]
 out = {"cfg": cfg, "ctas": os.environ.get("VC_COMMIT_CTAS"), "threads": os.environ.get("VC_COMMIT_THREADS"),
        "commit_ms": st["commit_ms"], "upload_ms": 1e3 * (t1 - t0), "run_ms": 1e3 * (t2 - t1), "steps": st["n_steps"],
        "placed": len(r.decisions), "us_per_step": 1e3 * st["commit_ms"] / max(1, st["n_steps"]),
        "cycles_per_step": tot / max(1, st["n_steps"]),
        "phases": {n: round(p / tot, 3) for n, p in zip(names, prof)},
-       "pods_per_s": len(r.decisions) / (st["commit_ms"] * 1e-3)}
+       "pods_per_s": len(r.decisions) / (st["commit_ms"] * 1e-3), "full_sweeps": prof[6], "incremental": prof[7]}
 print(json.dumps(out))
 e.close()

@@ -70,6 +70,15 @@ struct K2Params {
   int32_t *fit_errors;
   int32_t *counters;  // 0 n_decisions, 1 n_visits, 2 n_fit_errors, 3 n_steps, 4 error
   long long *prof;    // [8] phase cycle counters of CTA 0
+  // ---- fast (incremental) kernel ----
+  const int4 *tmeta;      // per position of task_order: {task, group, role row, 0}
+  int n_groups;
+  const double *g_req;    // [R][G] request record of each (class, request) group
+  const double *g_kreq;   // [K][G]
+  const double *g_knz;    // [2][G]
+  const uint32_t *g_has;
+  const int32_t *g_class;
+  uint4 *ring;            // publication ring, RING_DEPTH entries of RING_STRIDE uint4
 };
 
 // ---------------------------------------------------------------------------------------
@@ -129,6 +138,15 @@ struct Ctl {
   long long prof_last;
   int pick;  // scratch for warp0 -> CTA broadcasts
   int pick2;
+  // ---- fast (incremental) kernel only ----
+  int cmd, sweep_rl, sweep_use_cache, visit_id;
+  int cur_group;     // group whose record is staged in trec
+  int cache_group;   // group the per-node (cat, score) cache and the slot table describe; -1 = invalid
+  int dirty_node;    // node changed by the last placement and not yet re-evaluated for cache_group; -1 none
+  unsigned ag;       // all-gathers so far (mailbox parity / tag)
+  unsigned pc;       // single-slot publications so far (ring index / tag)
+  int since_sync;    // publications since the last all-gather (ring overrun guard)
+  int n_full, n_incr;
 };
 
 // ---- mailbox --------------------------------------------------------------------------------

@@ -237,6 +237,122 @@ __device__ __forceinline__ int fit_category_t(int R, const TaskRec &t, const NV 
   return fit_idle ? 0 : 1;
 }
 
+// ---------------------------------------------------------------------------------------
+// Straight-line evaluator for the commit kernel's common case (no FutureIdle gradient, no normalising
+// batch scorer, R <= 8, K <= 4). Same IEEE operations in the same order as the generic functions above,
+// but fully unrolled and predicated so the ~12 independent fp64 divisions of one (task, node) pair issue
+// back to back instead of one dependency chain after the other (the sweep is latency-bound: one warp per
+// SM sub-partition). Adding the 0.0 of a skipped term is exact, so predication does not change results.
+// Returns the fit category (0 idle-fit / 2 infeasible) and the total score of util.PrioritizeNodes.
+// ---------------------------------------------------------------------------------------
+template <class NV>
+__device__ __forceinline__ int eval_pair_fast(const DevConf &c, int R, int K, const TaskRec &t, const NV &nv,
+                                              uint32_t cs, bool pod_cap_hit, double *score_out) {
+  constexpr int RT = 8, KT = VC_MAX_KDIMS;
+  // ---- resource fit against Idle (resource_info.go:429-463) ----
+  bool fit = (cs & CS_STATIC_OK) != 0 && !pod_cap_hit;
+  double usedv[RT], allocv[RT];
+#pragma unroll
+  for (int d = 0; d < RT; ++d) {
+    const bool on = d < R && (d < 2 || (t.has & (1u << d)));
+    const double idle = d < R ? nv.idle(d) : 0.0;
+    if (on && !le_eps(t.req[d], idle)) fit = false;
+    usedv[d] = d < R ? nv.used(d) : 0.0;
+    allocv[d] = d < R ? nv.alloc(d) : 0.0;
+  }
+  // ---- binpack (plugins/binpack/binpack.go:206-261) ----
+  double bp_term[RT];
+  bool bp_over = false;
+  int bp_wsum = 0;
+#pragma unroll
+  for (int d = 0; d < RT; ++d) {
+    const double request = d < R ? t.req[d] : 0.0;
+    const int w = c.binpack_dim_weight[d];
+    const bool on = d < R && (d < 2 || (t.has & (1u << d))) && request >= VC_MIN_RESOURCE && w >= 0;
+    const bool scored = on && !(allocv[d] == 0.0 || w == 0);
+    const double used_finally = request + usedv[d];
+    if (scored && used_finally > allocv[d]) bp_over = true;
+    const double q = used_finally * (double)w / (scored ? allocv[d] : 1.0);
+    bp_term[d] = scored ? q : 0.0;
+    bp_wsum += on ? w : 0;
+  }
+  double bp = 0.0;
+#pragma unroll
+  for (int d = 0; d < RT; ++d) bp += bp_term[d];
+  if (bp_wsum > 0) bp /= (double)bp_wsum;
+  bp *= (double)(VC_MAX_NODE_SCORE * c.binpack_weight);
+  if (bp_over) bp = 0.0;
+  // ---- nodeorder NodeOrderFn (plugins/nodeorder/nodeorder.go:314-330) ----
+  double ls = 0.0, ms = 0.0, wl = 0.0, wm = 0.0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double alloc = nv.kalloc(k);
+    const bool on = alloc != 0.0;
+    const double a1 = on ? alloc : 1.0;
+    const double reqv = nv.knz(k) + t.knz[k];
+    const double l = least_requested_score(reqv, a1), m = most_requested_score(reqv, a1);
+    ls += on ? l * 50.0 : 0.0; wl += on ? 50.0 : 0.0;
+    ms += on ? m * 1.0 : 0.0;  wm += on ? 1.0 : 0.0;
+  }
+  double fr[KT];
+  bool fon[KT];
+  int nf = 0;
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    const double pod_req = k < K ? t.kreq[k] : 0.0;
+    const double alloc = k < K ? nv.kalloc(k) : 0.0;
+    fon[k] = k < K && !(k >= 2 && pod_req == 0.0) && alloc != 0.0;
+    double f = ((k < K ? nv.kreq(k) : 0.0) + pod_req) / (fon[k] ? alloc : 1.0);
+    if (f > 1.0) f = 1.0;
+    fr[k] = f;
+    nf += fon[k] ? 1 : 0;
+  }
+  double total = 0.0;
+#pragma unroll
+  for (int k = 0; k < KT; ++k) total += fon[k] ? fr[k] : 0.0;
+  double stdv = 0.0;
+  if (nf == 2) {
+    // the two active fractions in dimension order
+    double f0 = 0.0, f1 = 0.0;
+    int seen = 0;
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (fon[k]) { if (seen == 0) f0 = fr[k]; else f1 = fr[k]; ++seen; }
+    stdv = fabs((f0 - f1) / 2.0);
+  } else if (nf > 2) {
+    const double mean = total / (double)nf;
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (fon[k]) sum = sum + (fr[k] - mean) * (fr[k] - mean);
+    stdv = sqrt(sum / (double)nf);
+  }
+  const double bal = (double)__double2ll_rz((1.0 - stdv) * (double)VC_MAX_NODE_SCORE);
+  double no = 0.0;
+  if (c.w_least != 0) no += (wl == 0.0 ? 0.0 : idiv_floor(ls, wl == 0.0 ? 1.0 : wl)) * (double)c.w_least;
+  if (c.w_most != 0) no += (wm == 0.0 ? 0.0 : idiv_floor(ms, wm == 0.0 ? 1.0 : wm)) * (double)c.w_most;
+  if (c.w_balanced != 0) no += bal * (double)c.w_balanced;
+  if (c.w_node_affinity != 0) no += (double)(cs >> CS_NAFF_SHIFT) * (double)c.w_node_affinity;
+  // ---- ssn.NodeOrderMapFn sum in plugin order, then util.PrioritizeNodes total ----
+  double order = 0.0;
+  bool has_order = true;
+  for (int i = 0; i < c.n_plugins; ++i) {
+    if (!(c.enabled[i] & VC_EN_NODE_ORDER)) continue;
+    const int pl = c.plugin[i];
+    if (pl == VC_PLUGIN_BINPACK) { if (c.binpack_weight != 0) order += bp; }
+    else if (pl == VC_PLUGIN_NODEORDER) order += no;
+    else if (pl == VC_PLUGIN_TDM) {
+      if (has_order) {
+        if (cs & CS_TDM_ORDER_ERR) has_order = false;
+        else order += (cs & CS_TDM_ORDER_MAX) ? (double)VC_MAX_NODE_SCORE : 0.0;
+      }
+    }
+  }
+  // a NodeOrderFn error aborts the whole NodeOrderMapFn sum for the node (session_plugins.go:984-987)
+  *score_out = total_score(c, has_order, has_order ? order : 0.0, 0, 0);
+  return fit ? 0 : 2;
+}
+
 // (score, node) ordering of util.SelectBestNodeAndScore with the canonical tie-break.
 __host__ __device__ __forceinline__ bool better(double sa, int na, double sb, int nb) {
   return sa > sb || (sa == sb && na < nb);

@@ -15,6 +15,7 @@
 
 #include "../../include/vcalloc.h"
 #include "vc_commit.cuh"
+#include "vc_commit_fast.cuh"
 #include "vc_device.cuh"
 #include "vc_host.hpp"
 #include "vc_kernels.cuh"
@@ -104,7 +105,14 @@ struct vc_snapshot {
   Slot<int32_t> q_prio;
   Slot<uint32_t> q_rank, q_flags, q_alloc_has0, q_des_has, q_flags2;
   Slot<double> q_alloc0, q_des, q_share0;
-  Slot<int32_t> qjobs_off, qjobs, task_order, job_task_off;
+  Slot<int32_t> qjobs_off, qjobs, task_order, job_task_off, tmeta;
+  Slot<double> sg_req, sg_kreq, sg_knz;
+  Slot<uint32_t> sg_has;
+  Slot<int32_t> sg_class;
+  std::vector<int32_t> group_rep, h_group_of;
+  bool fast = false;
+  uint4 *ring = nullptr;
+  int last_full = 0, last_incr = 0;
   // ---- device-only buffers ----
   uint32_t *cstat = nullptr;
   double *w_idle = nullptr, *w_used = nullptr, *w_pip = nullptr, *w_kreq = nullptr, *w_knz = nullptr;  // working copies
@@ -219,8 +227,14 @@ void choose_geometry(vc_snapshot *s) {
   s->npc = npc;
   s->block = block;
   const int R = s->dims.n_dims, K = s->dims.n_kdims;
-  size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2;
-  s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 + 4) + 64;
+  s->fast = !s->dc.has_future && !s->dc.soft_active && R <= 8 && K <= VC_MAX_KDIMS && !getenv("VC_COMMIT_GENERIC");
+  if (s->fast) {
+    size_t rows = 3 * (size_t)R + 2 * (size_t)K + 2 + 1;
+    s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 * 4) + (size_t)ctas * (8 + 4 + 4) + 64;
+  } else {
+    size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2;
+    s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 + 4) + 64;
+  }
 }
 
 int free_dense(vc_snapshot *s) {
@@ -292,7 +306,7 @@ void vc_snapshot_destroy(vc_snapshot *s) {
   if (!s) return;
   free_dense(s);
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
-                   s->rep_i32, s->rep_f64, s->rep_heap, s->mbox, s->d_prof, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
+                   s->rep_i32, s->rep_f64, s->rep_heap, s->mbox, s->ring, s->d_prof, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
   for (void *p : dptrs) if (p) cudaFree(p);
   void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters};
   for (void *p : hptrs) if (p) cudaFreeHost(p);
@@ -449,6 +463,63 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     qjobs_off[q + 1] = qjobs_off[q] + (int32_t)qlists[q].size();
     qjobs.insert(qjobs.end(), qlists[q].begin(), qlists[q].end());
   }
+  // (class, request) groups: tasks of one pod template share their whole verdict / score row
+  std::vector<int32_t> group_of(T);
+  {
+    std::unordered_map<std::string, int> index;
+    index.reserve(1024);
+    s->group_rep.clear();
+    std::string key;
+    for (size_t t = 0; t < T; ++t) {
+      key.clear();
+      key.append(reinterpret_cast<const char *>(&tk->klass[t]), 4);
+      key.append(reinterpret_cast<const char *>(&tk->req_has[t]), 4);
+      for (size_t d = 0; d < R; ++d) key.append(reinterpret_cast<const char *>(&tk->resreq[d * T + t]), 8);
+      for (size_t k = 0; k < K; ++k) key.append(reinterpret_cast<const char *>(&tk->k8s_req[k * T + t]), 8);
+      for (size_t k = 0; k < 2; ++k) key.append(reinterpret_cast<const char *>(&tk->k8s_nonzero_req[k * T + t]), 8);
+      auto it = index.find(key);
+      if (it == index.end()) {
+        it = index.emplace(key, (int)s->group_rep.size()).first;
+        s->group_rep.push_back((int32_t)t);
+      }
+      group_of[t] = it->second;
+    }
+  }
+  const size_t NG = s->group_rep.size();
+  s->n_groups = (int)NG;
+  s->h_group_of = group_of;
+  std::vector<double> g_req(R * NG), g_kreq(K * NG), g_knz(2 * NG);
+  std::vector<uint32_t> g_has(NG);
+  std::vector<int32_t> g_class(NG);
+  for (size_t g = 0; g < NG; ++g) {
+    const int t = s->group_rep[g];
+    for (size_t d = 0; d < R; ++d) g_req[d * NG + g] = tk->resreq[d * T + t];
+    for (size_t k = 0; k < K; ++k) g_kreq[k * NG + g] = tk->k8s_req[k * T + t];
+    for (size_t k = 0; k < 2; ++k) g_knz[k * NG + g] = tk->k8s_nonzero_req[k * T + t];
+    g_has[g] = tk->req_has[t];
+    g_class[g] = tk->klass[t];
+  }
+  // per position of task_order: {task, group, role row}; a job is 'pure' when each named role maps to
+  // one group (then the role-level predicate-error cache cannot change any verdict)
+  std::vector<int32_t> tmeta(4 * T);
+  std::vector<uint32_t> j_flags_x(jb->flags, jb->flags + J);
+  {
+    std::vector<int32_t> role_group(NR, -1);
+    std::vector<uint8_t> impure(J, 0);
+    for (size_t pos = 0; pos < T; ++pos) {
+      const int t = task_order[pos];
+      tmeta[4 * pos + 0] = t; tmeta[4 * pos + 1] = group_of[t]; tmeta[4 * pos + 2] = tk->role[t]; tmeta[4 * pos + 3] = 0;
+    }
+    for (size_t t = 0; t < T; ++t) {
+      const int r = tk->role[t];
+      if (r < 0 || (size_t)r >= NR) return fail(VC_EINVAL, "task %zu: bad role row", t);
+      if (jb->role_flags[r] & VC_ROLE_EMPTY_NAME) continue;
+      if (role_group[r] < 0) role_group[r] = group_of[t];
+      else if (role_group[r] != group_of[t]) impure[tk->job[t]] = 1;
+    }
+    for (size_t j = 0; j < J; ++j)
+      if (!impure[j]) j_flags_x[j] |= VC_JOBX_PURE;
+  }
   // role pending counts incl. the tasks in scope (job_info.go:936-939)
   std::vector<int32_t> r_pending(NR, 0);
   for (size_t r = 0; r < NR; ++r) r_pending[r] = jb->role_pending_other ? jb->role_pending_other[r] : 0;
@@ -494,7 +565,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     put(s, s->j_ntasks, jb->n_tasks_total, J, plan); put(s, s->j_pbe, jb->pending_besteffort, J, plan);
     put(s, s->j_taskmintotal, jb->task_min_total, J, plan); put(s, s->j_roleoff, jb->role_off, J + 1, plan);
     put(s, s->j_prio, jb->priority, J, plan); put(s, s->j_ready0, jb->ready_num, J, plan);
-    put(s, s->j_waiting0, jb->waiting_num, J, plan); put(s, s->j_flags, jb->flags, J, plan);
+    put(s, s->j_waiting0, jb->waiting_num, J, plan); put(s, s->j_flags, j_flags_x.data(), J, plan);
     put(s, s->j_rank, j_rank.data(), J, plan); put(s, s->j_alloc0, jb->allocated, R * J, plan);
     put(s, s->j_share0, j_share.data(), J, plan);
     put(s, s->r_min, jb->role_min, NR, plan); put(s, s->r_occ0, jb->role_occupied, NR, plan);
@@ -507,6 +578,10 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     put(s, s->q_share0, q_share.data(), Q, plan);
     put(s, s->qjobs_off, qjobs_off.data(), Q + 1, plan); put(s, s->qjobs, qjobs.data(), qjobs.size(), plan);
     put(s, s->task_order, task_order.data(), T, plan); put(s, s->job_task_off, job_task_off.data(), J + 1, plan);
+    put(s, s->tmeta, tmeta.data(), 4 * T, plan);
+    put(s, s->sg_req, g_req.data(), R * NG, plan); put(s, s->sg_kreq, g_kreq.data(), K * NG, plan);
+    put(s, s->sg_knz, g_knz.data(), 2 * NG, plan); put(s, s->sg_has, g_has.data(), NG, plan);
+    put(s, s->sg_class, g_class.data(), NG, plan);
     if (plan) {
       size_t need = (s->in.used + 255) & ~(size_t)255;
       if (need > s->in.cap) {
@@ -606,6 +681,9 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024;
   if (!s->mbox) CUDA_TRY(cudaMalloc(&s->mbox, mbox_bytes));
   if (!s->d_prof) CUDA_TRY(cudaMalloc(&s->d_prof, 8 * sizeof(long long)));
+  const size_t ring_bytes = sizeof(uint4) * RING_STRIDE * RING_DEPTH;
+  if (!s->ring) CUDA_TRY(cudaMalloc(&s->ring, ring_bytes));
+  CUDA_TRY(cudaMemsetAsync(s->ring, 0, ring_bytes, s->stream));
   if (!s->d_decisions) {
     CUDA_TRY(cudaMalloc(&s->d_decisions, std::max<size_t>(1, T) * sizeof(vc_decision)));
     CUDA_TRY(cudaMalloc(&s->d_visits, (T + J + 1) * sizeof(vc_visit)));
@@ -653,9 +731,12 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   p.mbox = s->mbox;
   p.decisions = s->d_decisions; p.visits = s->d_visits; p.fit_errors = s->d_fit; p.counters = s->d_counters;
   p.prof = s->d_prof;
+  p.tmeta = reinterpret_cast<const int4 *>(s->tmeta.d(s->in)); p.n_groups = s->n_groups;
+  p.g_req = s->sg_req.d(s->in); p.g_kreq = s->sg_kreq.d(s->in); p.g_knz = s->sg_knz.d(s->in);
+  p.g_has = s->sg_has.d(s->in); p.g_class = s->sg_class.d(s->in); p.ring = s->ring;
 
   if (G > 1024) return fail(VC_EUNSUPPORTED, "too many CTAs");
-  const void *kfn = s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
+  const void *kfn = s->fast ? (const void *)k_commit_fast : s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
                                      : (s->dc.soft_active ? (const void *)k_commit<false, true> : (const void *)k_commit<false, false>);
   CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
   int max_blocks = 0;
@@ -691,6 +772,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->stats.kernel_launches = 2;  // k_class_static + k_commit
   r->stats.n_steps = s->h_counters[3];
   for (int k = 0; k < 8; ++k) r->stats.prof_cycles[k] = s->h_prof[k];
+  r->stats.prof_cycles[6] = s->h_counters[5];  // full sweeps (fast kernel)
+  r->stats.prof_cycles[7] = s->h_counters[6];  // incremental steps (fast kernel)
   *out = r;
   return VC_OK;
 }
@@ -716,28 +799,8 @@ static int dense_prepare(vc_snapshot *s) {
   const vc_dims &D = s->dims;
   const size_t T = D.n_tasks, R = D.n_dims, K = D.n_kdims, N = D.n_nodes;
   const int nloc = s->dd.node_end - s->dd.node_begin;
-  // group tasks by (class, request record): tasks of one pod template share their whole row
-  struct KeyHash {
-    size_t operator()(const std::string &k) const { return std::hash<std::string>()(k); }
-  };
-  std::unordered_map<std::string, int, KeyHash> index;
-  std::vector<int32_t> group_of(T);
-  std::vector<int32_t> rep;  // representative task of each group
-  std::string key;
-  for (size_t t = 0; t < T; ++t) {
-    key.clear();
-    key.append(reinterpret_cast<const char *>(&s->h_class[t]), 4);
-    key.append(reinterpret_cast<const char *>(&s->h_has[t]), 4);
-    for (size_t d = 0; d < R; ++d) key.append(reinterpret_cast<const char *>(&s->h_req[d * T + t]), 8);
-    for (size_t k = 0; k < K; ++k) key.append(reinterpret_cast<const char *>(&s->h_kreq[k * T + t]), 8);
-    for (size_t k = 0; k < 2; ++k) key.append(reinterpret_cast<const char *>(&s->h_knz[k * T + t]), 8);
-    auto it = index.find(key);
-    if (it == index.end()) {
-      it = index.emplace(key, (int)rep.size()).first;
-      rep.push_back((int32_t)t);
-    }
-    group_of[t] = it->second;
-  }
+  const std::vector<int32_t> &group_of = s->h_group_of;
+  const std::vector<int32_t> &rep = s->group_rep;
   const size_t G = rep.size();
   s->n_groups = (int)G;
   std::vector<double> g_req(R * G), g_kreq(K * G), g_knz(2 * G);
