@@ -5,17 +5,20 @@
 // R <= 8. It exploits the one structural fact of the greedy loop: a placement changes ONE node, so between
 // two consecutive tasks with the same (class, request) record every other (task, node) verdict and score
 // is unchanged. Per CTA it keeps, for the group being placed,
-//     c_cat[i], c_score[i]      verdict + total score of each of its nodes          (shared memory)
-//     sl_score/node/cnt[cta]    every CTA's current best (score, node) + #candidates (shared memory)
+//     c_cat[i], c_score[i], c_cs[i]   verdict, total score, static word of each of its nodes (shared memory)
+//     sl_score/node/cnt[cta]          every CTA's current best (score, node) + #candidates   (shared memory)
+//     cta best / global best          maintained incrementally, rescanned only when the holder got worse
 // and then a step is:
 //     group changed  -> full sweep: every thread re-evaluates its node, all-gather of the CTA bests
 //     same group     -> the CTA that owns the node changed by the previous placement re-evaluates that one
-//                       node, rescans its cache and PUBLISHES one 16-byte record into a ring in L2; every
-//                       other CTA reads that single record. The owner never waits for anybody, so a run of
-//                       placements inside one CTA proceeds at shared-memory speed and the L2 round trip is
-//                       only paid when the winner moves to another CTA.
-// Control state is replicated exactly as in k_commit; only warp 0 of each CTA runs it, the other warps
-// sleep on the block barrier and serve full sweeps / rollbacks on command.
+//                       node and PUBLISHES one 16-byte record into a ring in L2; every other CTA reads that
+//                       single record. The owner never waits for anybody, so a run of placements inside one
+//                       CTA proceeds at shared-memory speed and the L2 round trip is only paid when the
+//                       winner moves to another CTA.
+// Control state is replicated exactly as in k_commit, packed in per-job / per-queue records so that one
+// visit costs a handful of L2 round trips (lanes of warp 0 load a record in one coalesced access). Only
+// warp 0 of each CTA runs the control program; the other warps sleep on the block barrier and serve full
+// sweeps / rollbacks on command.
 #pragma once
 #include "vc_commit.cuh"
 
@@ -25,10 +28,48 @@
 #define CMD_DISCARD 2
 #define CMD_EXIT 3
 #define VC_JOBX_PURE 0x100u  // host-computed: every named role of the job maps to a single group
+#define FAST_R 8
+
+struct JobStatic {  // 64 B, read-only
+  int32_t min_available, n_tasks_total, pending_besteffort, task_min_total;
+  int32_t role_off, n_roles, priority;
+  uint32_t flags;
+  uint32_t rank;
+  int32_t task_off, task_end, queue;
+  int32_t pad[4];
+};
+struct JobDyn {  // 96 B, per-CTA replica
+  int32_t ready, waiting, cursor, pad;
+  double share;
+  double alloc[FAST_R];
+  double pad2;
+};
+struct RoleStatic { int32_t min; uint32_t flags; };
+struct RoleDyn { int32_t occ, pip, pending, failed; };
+struct QueueStatic {  // 80 B
+  int32_t prio;
+  uint32_t rank, flags, des_has;
+  double des[FAST_R];
+};
+struct QueueDyn {  // 96 B
+  uint32_t alloc_has, flags2;
+  int32_t active, scursor, hsize, pad;
+  double share;
+  double alloc[FAST_R];
+};
+static_assert(sizeof(JobStatic) == 64 && sizeof(JobDyn) == 96 && sizeof(QueueStatic) == 80 && sizeof(QueueDyn) == 96, "record layout");
+
+struct FastParams {  // extra kernel arguments of the fast kernel
+  const JobStatic *jstat;
+  const RoleStatic *rstat;
+  const QueueStatic *qstat;
+  const double *q_share0;  // [Q]
+};
 
 struct FastSmem {
   double *alloc, *idle, *used, *kalloc, *kreq, *knz;
   int32_t *max_tasks, *pod_count, *nerr_stamp, *c_cat;
+  uint32_t *c_cs;
   unsigned long long *nerr;
   double *c_score;
   double *sl_score;
@@ -108,7 +149,7 @@ __device__ __forceinline__ void exchange_all_fast(const K2Params &p, const Best 
   __syncwarp();
 }
 
-// best of this CTA from its verdict/score cache (warp 0)
+// best of this CTA from its verdict/score cache (warp 0); cnt = exact number of candidates
 __device__ __forceinline__ Best scan_cache(const FastSmem &fs, int nmine, int nbase) {
   const int lane = threadIdx.x & 31;
   Best b{0.0, -1, 0};
@@ -117,8 +158,36 @@ __device__ __forceinline__ Best scan_cache(const FastSmem &fs, int nmine, int nb
   best_warp_reduce(b);
   return b;
 }
+// arg-max over the slot table (warp 0)
+__device__ __forceinline__ Best fold_slots(const FastSmem &fs, int G) {
+  const int lane = threadIdx.x & 31;
+  Best g{0.0, -1, 0};
+  for (int s = lane; s < G; s += 32) best_fold(g, fs.sl_score[s], fs.sl_node[s], fs.sl_cnt[s]);
+  best_warp_reduce(g);
+  return g;
+}
 
-__global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
+// lanes of warp 0 copy a record of `words` 32-bit words from global to shared memory in one access
+__device__ __forceinline__ void load_record(void *dst_smem, const void *src_global, int words, bool read_only) {
+  const int lane = threadIdx.x & 31;
+  for (int w = lane; w < words; w += 32) {
+    const int *src = reinterpret_cast<const int *>(src_global) + w;
+    reinterpret_cast<int *>(dst_smem)[w] = read_only ? __ldg(src) : *src;
+  }
+}
+
+struct CtlFast {  // shared-memory state of the fast kernel next to Ctl
+  JobStatic js;
+  JobDyn jd;
+  QueueStatic qs;
+  QueueDyn qd;
+  RoleStatic rs[VC_MAX_JOB_ROLES];
+  RoleDyn rd[VC_MAX_JOB_ROLES];
+  double cta_best_score, g_best_score;
+  int cta_best_node, cta_cnt, g_best_node, g_cnt;
+};
+
+__global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams fp) {
   const DevConf &c = p.c;
   const int R = p.d.R, K = p.d.K, N = p.d.N, J = p.d.J, Q = p.d.Q, NR = p.d.NR, T = p.d.T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -132,6 +201,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
   unsigned char *sp = k2_smem;
   Ctl &S = *reinterpret_cast<Ctl *>(sp);
   sp += (sizeof(Ctl) + 15) & ~(size_t)15;
+  CtlFast &F = *reinterpret_cast<CtlFast *>(sp);
+  sp += (sizeof(CtlFast) + 15) & ~(size_t)15;
   FastSmem fs;
   fs.cap = cap;
   auto take = [&](int rows) { double *q = reinterpret_cast<double *>(sp); sp += (size_t)rows * cap * sizeof(double); return q; };
@@ -144,6 +215,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
   fs.pod_count = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
   fs.nerr_stamp = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
   fs.c_cat = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
+  fs.c_cs = reinterpret_cast<uint32_t *>(sp); sp += (size_t)cap * 4;
   fs.sl_node = reinterpret_cast<int32_t *>(sp); sp += (size_t)G * 4;
   fs.sl_cnt = reinterpret_cast<int32_t *>(sp); sp += (size_t)G * 4;
 
@@ -165,50 +237,40 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
     fs.nerr_stamp[i] = -1;
     fs.c_cat[i] = 2;
     fs.c_score[i] = 0.0;
+    fs.c_cs[i] = 0u;
   }
   for (int s = tid; s < G; s += blockDim.x) { fs.sl_score[s] = 0.0; fs.sl_node[s] = -1; fs.sl_cnt[s] = 0; }
 
-  // ---- per-CTA replica of the control state (same layout as k_commit) ----
-  int32_t *ri = p.rep_i32 + (size_t)cta * p.rep_i32_stride;
-  double *rf = p.rep_f64 + (size_t)cta * p.rep_f64_stride;
+  // ---- per-CTA replica of the mutable control state, packed records ----
+  unsigned char *rb = reinterpret_cast<unsigned char *>(p.rep_f64 + (size_t)cta * p.rep_f64_stride);
+  JobDyn *jdyn = reinterpret_cast<JobDyn *>(rb); rb += (size_t)J * sizeof(JobDyn);
+  QueueDyn *qdyn = reinterpret_cast<QueueDyn *>(rb); rb += (size_t)Q * sizeof(QueueDyn);
+  RoleDyn *rdyn = reinterpret_cast<RoleDyn *>(rb); rb += (size_t)NR * sizeof(RoleDyn);
+  double *ops_score = reinterpret_cast<double *>(rb);
+  int32_t *ops = p.rep_i32 + (size_t)cta * p.rep_i32_stride;  // task, node, kind
   HeapEnt *heap = p.rep_heap + (size_t)cta * p.rep_heap_stride;
-  int32_t *j_ready = ri; ri += J;
-  int32_t *j_waiting = ri; ri += J;
-  int32_t *j_cursor = ri; ri += J;
-  int32_t *r_occ = ri; ri += NR;
-  int32_t *r_pip = ri; ri += NR;
-  int32_t *r_pending = ri; ri += NR;
-  int32_t *r_failed = ri; ri += NR;
-  int32_t *q_active = ri; ri += Q;
-  int32_t *q_scursor = ri; ri += Q;
-  int32_t *q_hsize = ri; ri += Q;
-  uint32_t *q_alloc_has = reinterpret_cast<uint32_t *>(ri); ri += Q;
-  uint32_t *q_flags2 = reinterpret_cast<uint32_t *>(ri); ri += Q;
-  int32_t *ops = ri; ri += (size_t)p.max_job_tasks * 3;
-  double *j_share = rf; rf += J;
-  double *j_alloc = rf; rf += (size_t)R * J;
-  double *q_alloc = rf; rf += (size_t)R * Q;
-  double *q_share = rf; rf += Q;
-  double *ops_score = rf; rf += p.max_job_tasks;
 
   for (int j = tid; j < J; j += blockDim.x) {
-    j_ready[j] = p.j_ready0[j];
-    j_waiting[j] = p.j_waiting0[j];
-    j_cursor[j] = 0;
-    j_share[j] = p.j_share0[j];
-    for (int d = 0; d < R; ++d) j_alloc[(size_t)d * J + j] = p.j_alloc0[(size_t)d * J + j];
+    JobDyn jd;
+    jd.ready = p.j_ready0[j]; jd.waiting = p.j_waiting0[j]; jd.cursor = 0; jd.pad = 0;
+    jd.share = p.j_share0[j];
+    for (int d = 0; d < FAST_R; ++d) jd.alloc[d] = d < R ? p.j_alloc0[(size_t)d * J + j] : 0.0;
+    jd.pad2 = 0.0;
+    jdyn[j] = jd;
   }
   for (int r = tid; r < NR; r += blockDim.x) {
-    r_occ[r] = p.r_occ0[r]; r_pip[r] = p.r_pip0[r]; r_pending[r] = p.r_pending0[r]; r_failed[r] = 0;
+    RoleDyn rd;
+    rd.occ = p.r_occ0[r]; rd.pip = p.r_pip0[r]; rd.pending = p.r_pending0[r]; rd.failed = 0;
+    rdyn[r] = rd;
   }
   for (int q = tid; q < Q; q += blockDim.x) {
-    q_active[q] = (p.qjobs_off[q + 1] > p.qjobs_off[q]) ? 1 : 0;
-    q_scursor[q] = 0;
-    q_hsize[q] = 0;
-    q_alloc_has[q] = p.q_alloc_has0[q];
-    q_flags2[q] = p.q_flags2[q];
-    q_share[q] = p.q_share0[q];
-    for (int d = 0; d < R; ++d) q_alloc[(size_t)d * Q + q] = p.q_alloc0[(size_t)d * Q + q];
+    QueueDyn qd;
+    qd.alloc_has = p.q_alloc_has0[q]; qd.flags2 = p.q_flags2[q];
+    qd.active = (p.qjobs_off[q + 1] > p.qjobs_off[q]) ? 1 : 0;  // buildAllocateContext: queues with a job
+    qd.scursor = 0; qd.hsize = 0; qd.pad = 0;
+    qd.share = fp.q_share0[q];
+    for (int d = 0; d < FAST_R; ++d) qd.alloc[d] = d < R ? p.q_alloc0[(size_t)d * Q + q] : 0.0;
+    qdyn[q] = qd;
   }
   if (tid == 0) {
     S.seq = 0;
@@ -217,6 +279,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
     S.prof_last = clock64();
     S.cmd = 0; S.visit_id = 0; S.cur_group = -1; S.cache_group = -1; S.dirty_node = -1;
     S.ag = 0; S.pc = 0; S.since_sync = 0; S.n_full = 0; S.n_incr = 0;
+    F.cta_best_node = -1; F.cta_cnt = 0; F.g_best_node = -1; F.g_cnt = 0; F.cta_best_score = F.g_best_score = 0.0;
   }
   __syncthreads();
 
@@ -230,7 +293,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
     Best b{0.0, -1, 0};
     for (int i = tid; i < nmine; i += blockDim.x) {
       FastNodeView nv{fs, i};
-      const uint32_t cs = cs_row[i];
+      const uint32_t cs = __ldg(cs_row + i);
       if (use_cache && fs.nerr_stamp[i] != vid) { fs.nerr[i] = 0ull; fs.nerr_stamp[i] = vid; }
       int cat = 2;
       double sc = 0.0;
@@ -240,6 +303,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
       }
       fs.c_cat[i] = cat;
       fs.c_score[i] = sc;
+      fs.c_cs[i] = cs;
       if (cat == 0) best_fold(b, sc, nbase + i, 1);
     }
     best_warp_reduce(b);
@@ -287,15 +351,15 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
       if ((c.enabled[i] & VC_EN_OVERUSED) && c.plugin[i] == VC_PLUGIN_PROPORTION) overused_prop = true;
     }
     for (;;) {
-      // ---- queues.Pop() ----
+      // ---- queues.Pop(): arg-min by ssn.QueueOrderFn over the active queues ----
       int bq = -1, bprio = 0;
       double bshare = 0.0;
       uint32_t brank = 0;
       for (int q = lane; q < Q; q += 32) {
-        if (!q_active[q]) continue;
-        int pr = qorder_prop ? p.q_prio[q] : 0;
-        double sh = qorder_prop ? q_share[q] : 0.0;
-        uint32_t rk = p.q_rank[q];
+        if (!qdyn[q].active) continue;
+        int pr = qorder_prop ? __ldg(&fp.qstat[q].prio) : 0;
+        double sh = qorder_prop ? qdyn[q].share : 0.0;
+        uint32_t rk = __ldg(&fp.qstat[q].rank);
         bool lt = bq < 0 || pr > bprio || (pr == bprio && (sh < bshare || (sh == bshare && rk < brank)));
         if (lt) { bq = q; bprio = pr; bshare = sh; brank = rk; }
       }
@@ -310,101 +374,127 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
       const int q = bq;
       if (q < 0) break;
       __syncwarp();
-      // ---- queue attr, ssn.Overused, jobs.Pop(), job state ----
-      if (lane == 0) {
-        q_active[q] = 0;
-        S.queue = q;
-        S.qflags = p.q_flags[q];
-        S.qflags2 = q_flags2[q];
-        S.qalloc_has = q_alloc_has[q];
-        S.qdes_has = p.q_des_has[q];
-        S.qshare = q_share[q];
-        for (int d = 0; d < R; ++d) { S.qalloc[d] = q_alloc[(size_t)d * Q + q]; S.qdes[d] = p.q_des[(size_t)d * Q + q]; }
-        bool over = false;
-        if (overused_prop && (S.qflags2 & 1u)) {
-          over = le_eps(S.qdes[0], S.qalloc[0]) && le_eps(S.qdes[1], S.qalloc[1]);
-          for (int d = 2; d < R && over; ++d) {
-            if (!(S.qdes_has & (1u << d))) continue;
-            double rv = (S.qalloc_has & (1u << d)) ? S.qalloc[d] : 0.0;
-            if (!le_eps(S.qdes[d], rv)) over = false;
+      // ---- queue records (one coalesced access each), head of the static job list, heap top ----
+      load_record(&F.qs, &fp.qstat[q], sizeof(QueueStatic) / 4, true);
+      load_record(&F.qd, &qdyn[q], sizeof(QueueDyn) / 4, false);
+      const int sbeg = __ldg(&p.qjobs_off[q]), send = __ldg(&p.qjobs_off[q + 1]);
+      __syncwarp();
+      // ssn.Overused: attr.deserved.LessEqual(attr.allocated, Zero), proportion.go:319-331
+      bool over = false;
+      if (overused_prop && (F.qd.flags2 & 1u)) {
+        bool ok = true;
+        if (lane < R) {
+          const int d = lane;
+          if (d < 2 || (F.qs.des_has & (1u << d))) {
+            double rv = (d < 2 || (F.qd.alloc_has & (1u << d))) ? F.qd.alloc[d] : 0.0;
+            ok = le_eps(F.qs.des[d], rv);
           }
         }
-        int j = -1;
-        if (!over) {
-          const int sbeg = p.qjobs_off[q], send = p.qjobs_off[q + 1];
-          const int sc = sbeg + q_scursor[q];
-          HeapEnt *h = heap + sbeg;
-          int hs = q_hsize[q];
-          bool have_s = sc < send, have_h = hs > 0, take_heap = false;
-          if (have_s && have_h) {
-            int js = p.qjobs[sc];
-            JobKey ks;
-            ks.share = j_share[js]; ks.prio = p.j_prio[js]; ks.rank = p.j_rank[js];
-            ks.ready = j_ready[js] + p.j_pbe[js] >= p.j_min[js];
-            ks.preempt = (p.j_flags[js] & VC_JOB_PREEMPTABLE) != 0;
-            take_heap = job_less(c, key_of(h[0]), ks);
-          } else if (have_h) {
-            take_heap = true;
-          }
-          if (take_heap) {
-            j = h[0].job;
-            HeapEnt last = h[--hs];
-            q_hsize[q] = hs;
+        over = __all_sync(0xffffffffu, ok);
+      }
+      int j = -1;
+      bool from_heap = false;
+      if (!over) {
+        HeapEnt *h = heap + sbeg;
+        const int sc = sbeg + F.qd.scursor;
+        const int hs = F.qd.hsize;
+        const bool have_s = sc < send, have_h = hs > 0;
+        int js = have_s ? __ldg(&p.qjobs[sc]) : -1;
+        if (have_s) {  // records of the static candidate: needed for the comparison and, if chosen, as the job state
+          load_record(&F.js, &fp.jstat[js], sizeof(JobStatic) / 4, true);
+          load_record(&F.jd, &jdyn[js], sizeof(JobDyn) / 4, false);
+        }
+        HeapEnt top;
+        if (have_h) top = h[0];
+        __syncwarp();
+        if (have_s && have_h) {
+          JobKey ks;
+          ks.share = F.jd.share; ks.prio = F.js.priority; ks.rank = F.js.rank;
+          ks.ready = F.jd.ready + F.js.pending_besteffort >= F.js.min_available;
+          ks.preempt = (F.js.flags & VC_JOB_PREEMPTABLE) != 0;
+          from_heap = job_less(c, key_of(top), ks);
+        } else if (have_h) {
+          from_heap = true;
+        }
+        if (from_heap) {
+          j = top.job;
+          if (lane == 0) {  // heap pop: sift-down (only jobs that were re-pushed live here)
+            int n = hs - 1;
+            HeapEnt last = h[n];
             int i = 0;
             for (;;) {
               int l = 2 * i + 1;
-              if (l >= hs) break;
+              if (l >= n) break;
               int m = l;
-              if (l + 1 < hs && job_less(c, key_of(h[l + 1]), key_of(h[l]))) m = l + 1;
+              if (l + 1 < n && job_less(c, key_of(h[l + 1]), key_of(h[l]))) m = l + 1;
               if (!job_less(c, key_of(h[m]), key_of(last))) break;
               h[i] = h[m];
               i = m;
             }
-            if (hs > 0) h[i] = last;
-          } else if (have_s) {
-            j = p.qjobs[sc];
-            q_scursor[q] += 1;
+            if (n > 0) h[i] = last;
+            F.qd.hsize = n;
           }
-        }
-        S.job = j;
-        if (j >= 0) {
-          S.cursor = p.job_task_off[j] + j_cursor[j];
-          S.task_end = p.job_task_off[j + 1];
-          S.ready = j_ready[j]; S.waiting = j_waiting[j]; S.pbe = p.j_pbe[j]; S.minav = p.j_min[j];
-          S.ntasks_total = p.j_ntasks[j]; S.taskmintotal = p.j_taskmintotal[j]; S.jflags = p.j_flags[j];
-          S.role_base = p.j_roleoff[j];
-          S.nroles = p.j_roleoff[j + 1] - p.j_roleoff[j];
-          S.jshare = j_share[j];
-          for (int d = 0; d < R; ++d) S.jalloc[d] = j_alloc[(size_t)d * J + j];
-          for (int r = 0; r < S.nroles; ++r) {
-            int gr = S.role_base + r;
-            S.r_occ[r] = r_occ[gr]; S.r_pip[r] = r_pip[gr]; S.r_pending[r] = r_pending[gr];
-            S.r_min[r] = p.r_min[gr]; S.r_flags[r] = p.r_flags[gr]; S.r_failed[r] = (uint8_t)r_failed[gr];
-          }
-          S.n_ops = 0;
-          S.visit_id += 1;  // util.NewPredicateHelper(): a fresh error cache per visit
+          __syncwarp();
+          load_record(&F.js, &fp.jstat[j], sizeof(JobStatic) / 4, true);
+          load_record(&F.jd, &jdyn[j], sizeof(JobDyn) / 4, false);
+        } else if (have_s) {
+          j = js;
+          if (lane == 0) F.qd.scursor += 1;
         }
       }
       __syncwarp();
-      if (S.job < 0) continue;
-      const int j = S.job;
+      if (lane == 0) F.qd.active = 0;
+      if (j < 0) {  // queue dropped: overused, or no jobs left (allocate.go:295-305)
+        __syncwarp();
+        if (lane == 0) { qdyn[q].active = 0; qdyn[q].scursor = F.qd.scursor; qdyn[q].hsize = F.qd.hsize; }
+        __syncwarp();
+        continue;
+      }
+      // roles of the job
+      {
+        const int rb0 = F.js.role_off, nr = F.js.n_roles;
+        for (int r = lane; r < nr; r += 32) { F.rs[r] = fp.rstat[rb0 + r]; F.rd[r] = rdyn[rb0 + r]; }
+      }
+      __syncwarp();
+      if (lane == 0) {  // unpack into the scalar control block the ctl_* helpers read
+        S.queue = q; S.job = j;
+        S.qflags = F.qs.flags; S.qflags2 = F.qd.flags2; S.qalloc_has = F.qd.alloc_has; S.qdes_has = F.qs.des_has;
+        S.qshare = F.qd.share;
+        for (int d = 0; d < R; ++d) { S.qalloc[d] = F.qd.alloc[d]; S.qdes[d] = F.qs.des[d]; }
+        S.cursor = F.js.task_off + F.jd.cursor;
+        S.task_end = F.js.task_end;
+        S.ready = F.jd.ready; S.waiting = F.jd.waiting; S.pbe = F.js.pending_besteffort; S.minav = F.js.min_available;
+        S.ntasks_total = F.js.n_tasks_total; S.taskmintotal = F.js.task_min_total; S.jflags = F.js.flags;
+        S.role_base = F.js.role_off; S.nroles = F.js.n_roles;
+        S.jshare = F.jd.share;
+        for (int d = 0; d < R; ++d) S.jalloc[d] = F.jd.alloc[d];
+        for (int r = 0; r < S.nroles; ++r) {
+          S.r_occ[r] = F.rd[r].occ; S.r_pip[r] = F.rd[r].pip; S.r_pending[r] = F.rd[r].pending;
+          S.r_failed[r] = (uint8_t)F.rd[r].failed; S.r_min[r] = F.rs[r].min; S.r_flags[r] = F.rs[r].flags;
+        }
+        S.n_ops = 0;
+        S.visit_id += 1;  // util.NewPredicateHelper(): a fresh error cache per visit
+      }
+      __syncwarp();
       const bool pure = (S.jflags & VC_JOBX_PURE) != 0;
+      int4 meta = __ldg(&p.tmeta[S.cursor]);
       PROF_MARK(0);
 
       // ---- allocateResourcesForTasks, allocate.go:558-694 ----
       for (;;) {
         if (S.cursor >= S.task_end) break;
         PROF_MARK(4);
-        const int4 meta = p.tmeta[S.cursor];
         const int t = meta.x, grp = meta.y, rl = meta.z - S.role_base;
+        const int next_pos = S.cursor + 1;
+        if (next_pos < S.task_end) meta = __ldg(&p.tmeta[next_pos]);  // prefetch the next task's record
         __syncwarp();
         if (grp != S.cur_group) {  // stage the group's request record
-          if (lane < R) S.trec.req[lane] = p.g_req[(size_t)lane * p.n_groups + grp];
-          if (lane >= 16 && lane < 16 + K) S.trec.kreq[lane - 16] = p.g_kreq[(size_t)(lane - 16) * p.n_groups + grp];
-          if (lane >= 24 && lane < 26) S.trec.knz[lane - 24] = p.g_knz[(size_t)(lane - 24) * p.n_groups + grp];
-          if (lane == 31) { S.trec.has = p.g_has[grp]; S.trec.klass = p.g_class[grp]; }
+          if (lane < R) S.trec.req[lane] = __ldg(&p.g_req[(size_t)lane * p.n_groups + grp]);
+          if (lane >= 16 && lane < 16 + K) S.trec.kreq[lane - 16] = __ldg(&p.g_kreq[(size_t)(lane - 16) * p.n_groups + grp]);
+          if (lane >= 24 && lane < 26) S.trec.knz[lane - 24] = __ldg(&p.g_knz[(size_t)(lane - 24) * p.n_groups + grp]);
+          if (lane == 31) { S.trec.has = __ldg(&p.g_has[grp]); S.trec.klass = __ldg(&p.g_class[grp]); }
         }
-        if (lane == 0) { S.task = t; S.role_local = rl; S.cursor += 1; S.cur_group = grp; }
+        if (lane == 0) { S.task = t; S.role_local = rl; S.cursor = next_pos; S.cur_group = grp; }
         __syncwarp();
         if (!ctl_allocatable(p, S)) continue;
         const bool named_role = !(S.r_flags[rl] & VC_ROLE_EMPTY_NAME);
@@ -429,26 +519,60 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
             if (o == cta) {
               const int i = dn - nbase;
               FastNodeView nv{fs, i};
-              const uint32_t cs = p.cstat[(size_t)S.trec.klass * N + dn];
               double sc = 0.0;
-              int cat = eval_pair_fast(c, R, K, S.trec, nv, cs, c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i], &sc);
-              if (lane == 0) { fs.c_cat[i] = cat; fs.c_score[i] = sc; }
+              const int old_cat = fs.c_cat[i];
+              int cat = eval_pair_fast(c, R, K, S.trec, nv, fs.c_cs[i], c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i], &sc);
               __syncwarp();
-              nb = scan_cache(fs, nmine, nbase);
-              if (lane == 0) mbox_store(ent, pack_best(nb, tag));
+              if (lane == 0) { fs.c_cat[i] = cat; fs.c_score[i] = sc; }
+              // CTA best, incrementally: rescan only when the holder got worse
+              int cnt = F.cta_cnt + (cat == 0 ? 1 : 0) - (old_cat == 0 ? 1 : 0);
+              bool rescan = false;
+              double bs = F.cta_best_score;
+              int bn = F.cta_best_node;
+              if (bn == dn) {
+                if (cat == 0 && sc >= bs) bs = sc;
+                else rescan = true;
+              } else if (cat == 0 && (bn < 0 || better(sc, dn, bs, bn))) {
+                bs = sc; bn = dn;
+              }
+              __syncwarp();
+              if (rescan) { Best r = scan_cache(fs, nmine, nbase); bs = r.score; bn = r.node; cnt = r.cnt; }
+              nb.score = bs; nb.node = bn; nb.cnt = cnt;
+              if (lane == 0) {
+                F.cta_best_score = bs; F.cta_best_node = bn; F.cta_cnt = cnt;
+                mbox_store(ent, pack_best(nb, tag));
+              }
+              nb.cnt = min(cnt, 2);
             } else {
               uint4 v;
               do { v = mbox_load(ent); } while ((v.w >> 2) != tag);
               nb = unpack_best(v);
             }
+            // global best, incrementally
+            const int old_cnt = fs.sl_cnt[o];
+            int gcnt = F.g_cnt + nb.cnt - old_cnt;
+            double gs = F.g_best_score;
+            int gn = F.g_best_node;
+            bool refold = false;
+            const int g_owner = gn >= 0 ? (gn - p.d.node_begin) / p.npc : -1;
+            if (g_owner == o) {
+              if (nb.node >= 0 && (better(nb.score, nb.node, gs, gn) || (nb.node == gn && nb.score == gs))) { gs = nb.score; gn = nb.node; }
+              else refold = true;
+            } else if (nb.node >= 0 && (gn < 0 || better(nb.score, nb.node, gs, gn))) {
+              gs = nb.score; gn = nb.node;
+            }
+            __syncwarp();
             if (lane == 0) {
-              fs.sl_score[o] = nb.score; fs.sl_node[o] = nb.node; fs.sl_cnt[o] = min(nb.cnt, 2);
+              fs.sl_score[o] = nb.score; fs.sl_node[o] = nb.node; fs.sl_cnt[o] = nb.cnt;
               S.pc += 1; S.since_sync += 1; S.dirty_node = -1;
             }
             __syncwarp();
+            if (refold) { Best g = fold_slots(fs, G); gs = g.score; gn = g.node; gcnt = g.cnt; }
+            if (lane == 0) { F.g_best_score = gs; F.g_best_node = gn; F.g_cnt = gcnt; }
+            __syncwarp();
           }
           if (S.since_sync >= RING_DEPTH / 2) {  // keep the publication ring from being overrun
-            Best mine = scan_cache(fs, nmine, nbase);
+            Best mine{F.cta_best_score, F.cta_best_node, F.cta_cnt};
             exchange_all_fast(p, mine, S.ag, fs);
             if (lane == 0) { S.ag += 1; S.since_sync = 0; }
             __syncwarp();
@@ -466,27 +590,28 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
           if (lane < nwarps) best_fold(mine, S.w_score[0][lane], S.w_node[0][lane], S.w_cnt[0][lane]);
           best_warp_reduce(mine);
           exchange_all_fast(p, mine, S.ag, fs);
+          Best g = fold_slots(fs, G);
           if (lane == 0) {
             S.ag += 1; S.since_sync = 0; S.dirty_node = -1; S.n_full += 1;
             S.cache_group = pure ? grp : -1;  // verdicts taken under an error cache are not reusable
+            F.cta_best_score = mine.score; F.cta_best_node = mine.node; F.cta_cnt = mine.cnt;
+            F.g_best_score = g.score; F.g_best_node = g.node; F.g_cnt = g.cnt;
           }
           __syncwarp();
         }
-        // ---- global arg-max over the slot table ----
-        Best g{0.0, -1, 0};
-        for (int s = lane; s < G; s += 32) best_fold(g, fs.sl_score[s], fs.sl_node[s], fs.sl_cnt[s]);
-        best_warp_reduce(g);
+        const double g_score = F.g_best_score;
+        const int g_node = F.g_best_node, g_cnt = F.g_cnt;
         if (lane == 0) S.n_steps += 1;
         PROF_MARK(3);
 
-        if (g.cnt == 0) {  // no feasible node, allocate.go:639-659
+        if (g_cnt == 0) {  // no feasible node, allocate.go:639-659
           if (lane == 0) { if (out_cta) p.fit_errors[S.n_fit] = t; S.n_fit += 1; S.r_failed[rl] = 1; }
           __syncwarp();
           if (ctl_need_continue(S)) continue;
           break;
         }
-        const int best = g.node;
-        const double score = g.cnt == 1 ? 0.0 : g.score;
+        const int best = g_node;
+        const double score = g_cnt == 1 ? 0.0 : g_score;
         // ---- Statement.Allocate: node.AddTask on the owner CTA (api/node_info.go:435-484) ----
         if (best >= nbase && best < nbase + nmine) {
           const int i = best - nbase;
@@ -500,6 +625,32 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
             if (lane >= 24 && lane < 26) fs.knz[(lane - 24) * cap + i] += S.trec.knz[lane - 24];
           }
         }
+        // event handlers: drf (drf.go:391-418) and proportion (proportion.go:475-497), one lane per dimension
+        double new_jshare = 0.0, new_qshare = 0.0;
+        if (c.has_drf) {
+          double sh = 0.0;
+          if (lane < R) {
+            const int d = lane;
+            const double al = S.jalloc[d] + S.trec.req[d];
+            if ((d < 2 || (p.total_has & (1u << d))) && p.total[d] >= VC_MIN_RESOURCE) sh = share_of(al, p.total[d]);
+          }
+          for (int o = 16; o; o >>= 1) sh = fmax(sh, __shfl_xor_sync(0xffffffffu, sh, o));
+          new_jshare = sh;
+        }
+        const bool prop = c.has_proportion && (S.qflags2 & 1u);
+        if (prop) {
+          double sh = 0.0;
+          if (lane < R) {
+            const int d = lane;
+            const bool touched = d < 2 || (S.trec.has & (1u << d));
+            const bool has = d < 2 || (S.qalloc_has & (1u << d)) || touched;
+            const double al = has ? S.qalloc[d] + (touched ? S.trec.req[d] : 0.0) : 0.0;
+            if ((d < 2 || (S.qdes_has & (1u << d))) && S.qdes[d] >= VC_MIN_RESOURCE) sh = share_of(al, S.qdes[d]);
+          }
+          for (int o = 16; o; o >>= 1) sh = fmax(sh, __shfl_xor_sync(0xffffffffu, sh, o));
+          new_qshare = sh;
+        }
+        __syncwarp();
         if (lane == 0) {
           const TaskRec &trec = S.trec;
           S.dirty_node = best;
@@ -508,14 +659,14 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
           S.ready += 1;
           if (c.has_drf) {
             for (int d = 0; d < R; ++d) S.jalloc[d] += trec.req[d];
-            S.jshare = drf_share(p, S.jalloc);
+            S.jshare = new_jshare;
           }
-          if (c.has_proportion && (S.qflags2 & 1u)) {
+          if (prop) {
             S.qalloc[0] += trec.req[0];
             S.qalloc[1] += trec.req[1];
             for (int d = 2; d < R; ++d)
               if (trec.has & (1u << d)) { S.qalloc[d] += trec.req[d]; S.qalloc_has |= 1u << d; S.qflags2 &= ~2u; }
-            S.qshare = queue_share(R, S.qalloc, S.qalloc_has, S.qdes, S.qdes_has);
+            S.qshare = new_qshare;
           }
           const int k = S.n_ops;
           ops[k * 3 + 0] = t; ops[k * 3 + 1] = best; ops[k * 3 + 2] = VC_OP_ALLOCATE;
@@ -569,20 +720,15 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
         }
       }
       __syncwarp();
+      // ---- write the job / queue / role records back into the replica (one coalesced access each) ----
       if (lane == 0) {
-        j_ready[j] = S.ready;
-        j_waiting[j] = S.waiting;
-        j_cursor[j] = S.cursor - p.job_task_off[j];
-        j_share[j] = S.jshare;
-        for (int d = 0; d < R; ++d) j_alloc[(size_t)d * J + j] = S.jalloc[d];
+        F.jd.ready = S.ready; F.jd.waiting = S.waiting; F.jd.cursor = S.cursor - F.js.task_off; F.jd.share = S.jshare;
+        for (int d = 0; d < R; ++d) { F.jd.alloc[d] = S.jalloc[d]; F.qd.alloc[d] = S.qalloc[d]; }
+        F.qd.alloc_has = S.qalloc_has; F.qd.flags2 = S.qflags2; F.qd.share = S.qshare;
+        F.qd.active = 1;  // queues.Push(queue), allocate.go:346
         for (int r = 0; r < S.nroles; ++r) {
-          int gr = S.role_base + r;
-          r_occ[gr] = S.r_occ[r]; r_pip[gr] = S.r_pip[r]; r_pending[gr] = S.r_pending[r]; r_failed[gr] = S.r_failed[r];
+          F.rd[r].occ = S.r_occ[r]; F.rd[r].pip = S.r_pip[r]; F.rd[r].pending = S.r_pending[r]; F.rd[r].failed = S.r_failed[r];
         }
-        for (int d = 0; d < R; ++d) q_alloc[(size_t)d * Q + q] = S.qalloc[d];
-        q_alloc_has[q] = S.qalloc_has;
-        q_flags2[q] = S.qflags2;
-        q_share[q] = S.qshare;
         if (out_cta) {
           vc_visit v;
           v.job = j;
@@ -595,10 +741,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
         S.n_vis += 1;
         if (stmt && ready && S.cursor < S.task_end) {  // jobs.Push(job), allocate.go:334-336
           HeapEnt e;
-          e.share = S.jshare; e.job = j; e.prio = p.j_prio[j]; e.rank = p.j_rank[j];
+          e.share = S.jshare; e.job = j; e.prio = F.js.priority; e.rank = F.js.rank;
           e.bits = (ctl_is_ready(S) ? 1u : 0u) | ((S.jflags & VC_JOB_PREEMPTABLE) ? 2u : 0u);
-          HeapEnt *h = heap + p.qjobs_off[q];
-          int i = q_hsize[q]++;
+          HeapEnt *h = heap + sbeg;
+          int i = F.qd.hsize++;
           while (i > 0) {
             int par = (i - 1) / 2;
             if (!job_less(c, key_of(e), key_of(h[par]))) break;
@@ -607,8 +753,11 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p) {
           }
           h[i] = e;
         }
-        q_active[q] = 1;  // queues.Push(queue), allocate.go:346
       }
+      __syncwarp();
+      for (int w = lane; w < (int)(sizeof(JobDyn) / 4); w += 32) reinterpret_cast<int *>(&jdyn[j])[w] = reinterpret_cast<int *>(&F.jd)[w];
+      for (int w = lane; w < (int)(sizeof(QueueDyn) / 4); w += 32) reinterpret_cast<int *>(&qdyn[q])[w] = reinterpret_cast<int *>(&F.qd)[w];
+      for (int r = lane; r < S.nroles; r += 32) rdyn[S.role_base + r] = F.rd[r];
       __syncwarp();
       PROF_MARK(0);
     }

@@ -110,6 +110,9 @@ struct vc_snapshot {
   Slot<uint32_t> sg_has;
   Slot<int32_t> sg_class;
   std::vector<int32_t> group_rep, h_group_of;
+  Slot<JobStatic> s_jstat;
+  Slot<RoleStatic> s_rstat;
+  Slot<QueueStatic> s_qstat;
   bool fast = false;
   uint4 *ring = nullptr;
   int last_full = 0, last_incr = 0;
@@ -230,7 +233,8 @@ void choose_geometry(vc_snapshot *s) {
   s->fast = !s->dc.has_future && !s->dc.soft_active && R <= 8 && K <= VC_MAX_KDIMS && !getenv("VC_COMMIT_GENERIC");
   if (s->fast) {
     size_t rows = 3 * (size_t)R + 2 * (size_t)K + 2 + 1;
-    s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 * 4) + (size_t)ctas * (8 + 4 + 4) + 64;
+    s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + ((sizeof(CtlFast) + 15) & ~(size_t)15) + rows * npc * 8 +
+                    (size_t)npc * (8 + 4 * 5) + (size_t)ctas * (8 + 4 + 4) + 64;
   } else {
     size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 + 4) + 64;
@@ -541,6 +545,27 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     q_share[q] = a.share;
   }
 
+  // packed read-only records for the fast commit kernel (one coalesced access per record)
+  std::vector<JobStatic> jstat(J);
+  for (size_t j = 0; j < J; ++j) {
+    JobStatic &r = jstat[j];
+    std::memset(&r, 0, sizeof r);
+    r.min_available = jb->min_available[j]; r.n_tasks_total = jb->n_tasks_total[j];
+    r.pending_besteffort = jb->pending_besteffort[j]; r.task_min_total = jb->task_min_total[j];
+    r.role_off = jb->role_off[j]; r.n_roles = jb->role_off[j + 1] - jb->role_off[j];
+    r.priority = jb->priority[j]; r.flags = j_flags_x[j]; r.rank = j_rank[j];
+    r.task_off = job_task_off[j]; r.task_end = job_task_off[j + 1]; r.queue = jb->queue[j];
+  }
+  std::vector<RoleStatic> rstat(NR);
+  for (size_t r = 0; r < NR; ++r) { rstat[r].min = jb->role_min[r]; rstat[r].flags = jb->role_flags[r]; }
+  std::vector<QueueStatic> qstat(Q);
+  for (size_t q = 0; q < Q; ++q) {
+    QueueStatic &r = qstat[q];
+    std::memset(&r, 0, sizeof r);
+    r.prio = qu->priority[q]; r.rank = q_rank[q]; r.flags = qu->flags[q]; r.des_has = q_des_has[q];
+    for (size_t d = 0; d < R && d < FAST_R; ++d) r.des[d] = q_des[d * Q + q];
+  }
+
   // ---- plan + stage + one H2D copy ------------------------------------------------------
   for (int pass = 0; pass < 2; ++pass) {
     const bool plan = pass == 0;
@@ -582,6 +607,8 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     put(s, s->sg_req, g_req.data(), R * NG, plan); put(s, s->sg_kreq, g_kreq.data(), K * NG, plan);
     put(s, s->sg_knz, g_knz.data(), 2 * NG, plan); put(s, s->sg_has, g_has.data(), NG, plan);
     put(s, s->sg_class, g_class.data(), NG, plan);
+    put(s, s->s_jstat, jstat.data(), J, plan); put(s, s->s_rstat, rstat.data(), NR, plan);
+    put(s, s->s_qstat, qstat.data(), Q, plan);
     if (plan) {
       size_t need = (s->in.used + 255) & ~(size_t)255;
       if (need > s->in.cap) {
@@ -666,7 +693,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   const int G = s->n_cta;
   // replicas, mailbox, outputs
   const size_t i32_stride = ((3 * J + 4 * NR + 5 * Q + 3 * (size_t)s->max_job_tasks) + 63) & ~(size_t)63;
-  const size_t f64_stride = ((J + R * J + R * Q + Q + (size_t)s->max_job_tasks) + 31) & ~(size_t)31;
+  const size_t f64_words_fast = (J * sizeof(JobDyn) + Q * sizeof(QueueDyn) + NR * sizeof(RoleDyn)) / 8 + (size_t)s->max_job_tasks;
+  const size_t f64_stride = (std::max<size_t>(J + R * J + R * Q + Q + (size_t)s->max_job_tasks, f64_words_fast) + 31) & ~(size_t)31;
   const size_t heap_stride = (s->qjobs.count + 7) & ~(size_t)7;
   if (!s->rep_i32 || s->rep_i32_stride != i32_stride || s->rep_f64_stride != f64_stride || s->rep_heap_stride != heap_stride) {
     if (s->rep_i32) cudaFree(s->rep_i32);
@@ -743,7 +771,10 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, kfn, s->block, s->smem_bytes));
   if (max_blocks * g_sm_count < G)
     return fail(VC_EUNSUPPORTED, "commit kernel cannot be co-resident: %d CTAs x %zu B smem (max %d/SM)", G, s->smem_bytes, max_blocks);
-  void *args[] = {&p};
+  FastParams fp;
+  fp.jstat = s->s_jstat.d(s->in); fp.rstat = s->s_rstat.d(s->in); fp.qstat = s->s_qstat.d(s->in);
+  fp.q_share0 = s->q_share0.d(s->in);
+  void *args[] = {&p, &fp};
   CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
   CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(G), dim3(s->block), args, s->smem_bytes, s->stream));
   g_launches++;
