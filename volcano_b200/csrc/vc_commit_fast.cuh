@@ -342,14 +342,162 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     }
   } else {
     // ===================================================================================
-    // warp 0: the replicated control program (allocate.go:283-348, :558-694)
+    // warp 0: the replicated control program (allocate.go:283-348, :558-694).
+    // All 32 lanes execute it in lock step on REGISTER copies of the control state (identical in every
+    // lane); shared memory is used only for records loaded/stored once per visit and for what the worker
+    // warps read. Per-dimension vectors (drf / proportion accumulators) live one dimension per lane.
     // ===================================================================================
     const bool out_cta = (cta == 0);
-    bool qorder_prop = false, overused_prop = false;
+    // ---- configuration hoisted out of the loops ----
+    bool f_qorder_prop = false, f_over_prop = false, f_alloc_prop = false, f_gang_ready = false;
+    int ord_n = 0, ord_kind[3] = {0, 0, 0};
     for (int i = 0; i < c.n_plugins; ++i) {
-      if ((c.enabled[i] & VC_EN_QUEUE_ORDER) && c.plugin[i] == VC_PLUGIN_PROPORTION) qorder_prop = true;
-      if ((c.enabled[i] & VC_EN_OVERUSED) && c.plugin[i] == VC_PLUGIN_PROPORTION) overused_prop = true;
+      const int pl = c.plugin[i];
+      const uint32_t en = c.enabled[i];
+      if ((en & VC_EN_QUEUE_ORDER) && pl == VC_PLUGIN_PROPORTION) f_qorder_prop = true;
+      if ((en & VC_EN_OVERUSED) && pl == VC_PLUGIN_PROPORTION) f_over_prop = true;
+      if ((en & VC_EN_ALLOCATABLE) && pl == VC_PLUGIN_PROPORTION) f_alloc_prop = true;
+      if ((en & VC_EN_JOB_READY) && pl == VC_PLUGIN_GANG) f_gang_ready = true;
+      if ((en & VC_EN_NODE_ORDER) && ord_n < 3 &&
+          ((pl == VC_PLUGIN_BINPACK && c.binpack_weight != 0) || pl == VC_PLUGIN_NODEORDER || pl == VC_PLUGIN_TDM))
+        ord_kind[ord_n++] = pl;
     }
+    // ---- lane roles of the warp-cooperative single-node evaluation (see eval_dirty below) ----
+    enum { ROLE_NONE = 0, ROLE_BP = 1, ROLE_LEAST = 2, ROLE_MOST = 3, ROLE_BAL = 4 };
+    const int role = lane < 8 ? ROLE_BP : lane < 10 ? ROLE_LEAST : lane < 12 ? ROLE_MOST : lane < 16 ? ROLE_BAL : ROLE_NONE;
+    const int dk = role == ROLE_BP ? lane : role == ROLE_LEAST ? lane - 8 : role == ROLE_MOST ? lane - 10 : role == ROLE_BAL ? lane - 12 : 0;
+    const bool lane_valid = (role == ROLE_BP && dk < R) || role == ROLE_LEAST || role == ROLE_MOST || (role == ROLE_BAL && dk < K);
+    const int dk_c = lane_valid ? dk : 0;
+    const double *a_base = role == ROLE_BP ? fs.used + dk_c * cap : role == ROLE_BAL ? fs.kreq + dk_c * cap : fs.knz + dk_c * cap;
+    const double *al_base = role == ROLE_BP ? fs.alloc + dk_c * cap : fs.kalloc + dk_c * cap;
+    const double *idle_base = fs.idle + ((lane < 8 && lane < R) ? lane : 0) * cap;
+    const int w_d = (role == ROLE_BP && lane_valid) ? c.binpack_dim_weight[dk_c] : 0;
+    const double mul_const = role == ROLE_BP ? (double)w_d : (role == ROLE_LEAST || role == ROLE_MOST) ? 100.0 : 1.0;
+    // per-group lane operands (refreshed when the staged group record changes)
+    double b_val = 0.0, req_fit = 0.0;
+    bool fit_on = false, on_task = false;
+    uint32_t t_has = 0;
+
+    // ---- register copies of the control state ----
+    int cur_group = -1, cache_group = -1, dirty_node = -1, since_sync = 0;
+    unsigned ag = 0, pc = 0;
+    int n_dec = 0, n_vis = 0, n_fit = 0, n_steps = 0, n_full = 0, n_incr = 0, visit_id = 0;
+    double cta_best_score = 0.0, g_best_score = 0.0;
+    int cta_best_node = -1, cta_cnt = 0, g_best_node = -1, g_cnt = 0;
+
+    // Warp-cooperative evaluation of ONE node i of this CTA for the staged group: the same IEEE operations
+    // as eval_pair_fast / the generic functions, one division per lane instead of ~17 in a row:
+    //   lanes 0-7   fit of dim d against Idle + binpack term of dim d          (binpack.go:213-237)
+    //   lanes 8-9   leastRequestedScore of cpu / memory, lanes 10-11 mostRequestedScore
+    //   lanes 12-15 BalancedAllocation fraction of upstream dim k
+    // then one second-level division (binpack /weightSum, least, most, mean) and the std / sqrt.
+    auto eval_dirty = [&](int i, double *score_out) -> int {
+      const uint32_t cs = fs.c_cs[i];
+      const bool pod_cap = c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i];
+      const double a = a_base[i], alloc = al_base[i], idle = idle_base[i];
+      const bool bad_fit = fit_on && !le_eps(req_fit, idle);
+      const double s = a + b_val;
+      const bool scored = role == ROLE_BP ? (on_task && !(alloc == 0.0 || w_d == 0))
+                        : role == ROLE_BAL ? (on_task && alloc != 0.0)
+                        : (role != ROLE_NONE && alloc != 0.0);
+      const bool over = role == ROLE_BP && scored && s > alloc;
+      const bool zero_least = role == ROLE_LEAST && s > alloc;
+      const double x = role == ROLE_LEAST ? alloc - s : role == ROLE_MOST ? fmin(s, alloc) : s;
+      const double num = x * mul_const;
+      const double den = scored ? alloc : 1.0;
+      double q = num / den;
+      if (role == ROLE_LEAST || role == ROLE_MOST) {
+        double qq = trunc(q);
+        const double r = fma(-qq, den, num);
+        if (r < 0.0) qq -= 1.0;
+        else if (r >= den) qq += 1.0;
+        q = zero_least ? 0.0 : qq;
+      }
+      if (role == ROLE_BAL && q > 1.0) q = 1.0;
+      const double val = scored ? q : 0.0;
+      const unsigned m_bad = __ballot_sync(0xffffffffu, bad_fit);
+      const unsigned m_over = __ballot_sync(0xffffffffu, over);
+      const unsigned m_on = __ballot_sync(0xffffffffu, role == ROLE_BP ? on_task : scored);
+      const bool fit = (cs & CS_STATIC_OK) != 0 && !pod_cap && m_bad == 0;
+      double bp_sum = 0.0;
+      int wsum = 0;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        bp_sum += __shfl_sync(0xffffffffu, val, d);
+        wsum += ((m_on >> d) & 1u) ? c.binpack_dim_weight[d] : 0;
+      }
+      double ls = 0.0, ms = 0.0, wl = 0.0, wm = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double lv = __shfl_sync(0xffffffffu, val, 8 + k), mv = __shfl_sync(0xffffffffu, val, 10 + k);
+        if ((m_on >> (8 + k)) & 1u) { ls += lv * 50.0; wl += 50.0; }
+        if ((m_on >> (10 + k)) & 1u) { ms += mv * 1.0; wm += 1.0; }
+      }
+      double fr[4];
+      double total = 0.0;
+      const unsigned fonm = (m_on >> 12) & 0xfu;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        fr[k] = __shfl_sync(0xffffffffu, val, 12 + k);
+        if ((fonm >> k) & 1u) total += fr[k];
+      }
+      const int nf = __popc(fonm);
+      // second-level divisions, one per lane
+      const double num2 = lane == 0 ? bp_sum : lane == 1 ? ls : lane == 2 ? ms : lane == 3 ? total : 0.0;
+      const double den2 = lane == 0 ? (wsum > 0 ? (double)wsum : 1.0) : lane == 1 ? (wl > 0.0 ? wl : 1.0)
+                        : lane == 2 ? (wm > 0.0 ? wm : 1.0) : lane == 3 ? (nf > 0 ? (double)nf : 1.0) : 1.0;
+      double q2 = num2 / den2;
+      if (lane == 1 || lane == 2) {
+        double qq = trunc(q2);
+        const double r = fma(-qq, den2, num2);
+        if (r < 0.0) qq -= 1.0;
+        else if (r >= den2) qq += 1.0;
+        q2 = qq;
+      }
+      double bp = __shfl_sync(0xffffffffu, q2, 0);
+      if (!(wsum > 0)) bp = bp_sum;
+      bp *= (double)(VC_MAX_NODE_SCORE * c.binpack_weight);
+      if (m_over & 0xffu) bp = 0.0;
+      const double least = wl > 0.0 ? __shfl_sync(0xffffffffu, q2, 1) : 0.0;
+      const double most = wm > 0.0 ? __shfl_sync(0xffffffffu, q2, 2) : 0.0;
+      const double mean = __shfl_sync(0xffffffffu, q2, 3);
+      double stdv = 0.0;
+      if (nf == 2) {
+        double f0 = 0.0, f1 = 0.0;
+        int seen = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if ((fonm >> k) & 1u) { if (seen == 0) f0 = fr[k]; else f1 = fr[k]; ++seen; }
+        stdv = fabs((f0 - f1) / 2.0);
+      } else if (nf > 2) {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if ((fonm >> k) & 1u) sum = sum + (fr[k] - mean) * (fr[k] - mean);
+        stdv = sqrt(sum / (double)nf);
+      }
+      const double bal = (double)__double2ll_rz((1.0 - stdv) * (double)VC_MAX_NODE_SCORE);
+      double no = 0.0;
+      if (c.w_least != 0) no += least * (double)c.w_least;
+      if (c.w_most != 0) no += most * (double)c.w_most;
+      if (c.w_balanced != 0) no += bal * (double)c.w_balanced;
+      if (c.w_node_affinity != 0) no += (double)(cs >> CS_NAFF_SHIFT) * (double)c.w_node_affinity;
+      double order = 0.0;
+      bool has_order = true;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (k >= ord_n) break;
+        if (ord_kind[k] == VC_PLUGIN_BINPACK) order += bp;
+        else if (ord_kind[k] == VC_PLUGIN_NODEORDER) order += no;
+        else if (has_order) {
+          if (cs & CS_TDM_ORDER_ERR) has_order = false;
+          else order += (cs & CS_TDM_ORDER_MAX) ? (double)VC_MAX_NODE_SCORE : 0.0;
+        }
+      }
+      *score_out = total_score(c, has_order, has_order ? order : 0.0, 0, 0);
+      return fit ? 0 : 2;
+    };
+
     for (;;) {
       // ---- queues.Pop(): arg-min by ssn.QueueOrderFn over the active queues ----
       int bq = -1, bprio = 0;
@@ -357,8 +505,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       uint32_t brank = 0;
       for (int q = lane; q < Q; q += 32) {
         if (!qdyn[q].active) continue;
-        int pr = qorder_prop ? __ldg(&fp.qstat[q].prio) : 0;
-        double sh = qorder_prop ? qdyn[q].share : 0.0;
+        int pr = f_qorder_prop ? __ldg(&fp.qstat[q].prio) : 0;
+        double sh = f_qorder_prop ? qdyn[q].share : 0.0;
         uint32_t rk = __ldg(&fp.qstat[q].rank);
         bool lt = bq < 0 || pr > bprio || (pr == bprio && (sh < bshare || (sh == bshare && rk < brank)));
         if (lt) { bq = q; bprio = pr; bshare = sh; brank = rk; }
@@ -379,27 +527,30 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       load_record(&F.qd, &qdyn[q], sizeof(QueueDyn) / 4, false);
       const int sbeg = __ldg(&p.qjobs_off[q]), send = __ldg(&p.qjobs_off[q + 1]);
       __syncwarp();
+      const uint32_t qflags = F.qs.flags, qdes_has = F.qs.des_has;
+      uint32_t qflags2 = F.qd.flags2, qalloc_has = F.qd.alloc_has;
+      int q_scursor = F.qd.scursor, q_hsize = F.qd.hsize;
+      double qshare = F.qd.share;
+      // one dimension per lane
+      double qalloc_l = lane < R ? F.qd.alloc[lane] : 0.0;
+      const double qdes_l = lane < R ? F.qs.des[lane] : 0.0;
       // ssn.Overused: attr.deserved.LessEqual(attr.allocated, Zero), proportion.go:319-331
       bool over = false;
-      if (overused_prop && (F.qd.flags2 & 1u)) {
+      if (f_over_prop && (qflags2 & 1u)) {
         bool ok = true;
-        if (lane < R) {
-          const int d = lane;
-          if (d < 2 || (F.qs.des_has & (1u << d))) {
-            double rv = (d < 2 || (F.qd.alloc_has & (1u << d))) ? F.qd.alloc[d] : 0.0;
-            ok = le_eps(F.qs.des[d], rv);
-          }
+        if (lane < R && (lane < 2 || (qdes_has & (1u << lane)))) {
+          double rv = (lane < 2 || (qalloc_has & (1u << lane))) ? qalloc_l : 0.0;
+          ok = le_eps(qdes_l, rv);
         }
         over = __all_sync(0xffffffffu, ok);
       }
       int j = -1;
-      bool from_heap = false;
       if (!over) {
         HeapEnt *h = heap + sbeg;
-        const int sc = sbeg + F.qd.scursor;
-        const int hs = F.qd.hsize;
+        const int sc = sbeg + q_scursor;
+        const int hs = q_hsize;
         const bool have_s = sc < send, have_h = hs > 0;
-        int js = have_s ? __ldg(&p.qjobs[sc]) : -1;
+        const int js = have_s ? __ldg(&p.qjobs[sc]) : -1;
         if (have_s) {  // records of the static candidate: needed for the comparison and, if chosen, as the job state
           load_record(&F.js, &fp.jstat[js], sizeof(JobStatic) / 4, true);
           load_record(&F.jd, &jdyn[js], sizeof(JobDyn) / 4, false);
@@ -407,6 +558,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         HeapEnt top;
         if (have_h) top = h[0];
         __syncwarp();
+        bool from_heap = false;
         if (have_s && have_h) {
           JobKey ks;
           ks.share = F.jd.share; ks.prio = F.js.priority; ks.rank = F.js.rank;
@@ -432,75 +584,109 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
               i = m;
             }
             if (n > 0) h[i] = last;
-            F.qd.hsize = n;
           }
+          q_hsize = hs - 1;
           __syncwarp();
           load_record(&F.js, &fp.jstat[j], sizeof(JobStatic) / 4, true);
           load_record(&F.jd, &jdyn[j], sizeof(JobDyn) / 4, false);
         } else if (have_s) {
           j = js;
-          if (lane == 0) F.qd.scursor += 1;
+          q_scursor += 1;
         }
       }
       __syncwarp();
-      if (lane == 0) F.qd.active = 0;
       if (j < 0) {  // queue dropped: overused, or no jobs left (allocate.go:295-305)
-        __syncwarp();
-        if (lane == 0) { qdyn[q].active = 0; qdyn[q].scursor = F.qd.scursor; qdyn[q].hsize = F.qd.hsize; }
+        if (lane == 0) { qdyn[q].active = 0; qdyn[q].scursor = q_scursor; qdyn[q].hsize = q_hsize; }
         __syncwarp();
         continue;
       }
-      // roles of the job
-      {
-        const int rb0 = F.js.role_off, nr = F.js.n_roles;
-        for (int r = lane; r < nr; r += 32) { F.rs[r] = fp.rstat[rb0 + r]; F.rd[r] = rdyn[rb0 + r]; }
+      // ---- job state into registers; roles into the shared role tables ----
+      const int task_off = F.js.task_off, task_end = F.js.task_end;
+      const int role_base = F.js.role_off, nroles = F.js.n_roles;
+      const int minav = F.js.min_available, pbe = F.js.pending_besteffort, taskmintotal = F.js.task_min_total;
+      const int ntasks_total = F.js.n_tasks_total, j_prio = F.js.priority;
+      const uint32_t jflags = F.js.flags, j_rank = F.js.rank;
+      int cursor = task_off + F.jd.cursor, ready = F.jd.ready, waiting = F.jd.waiting, n_ops = 0;
+      double jshare = F.jd.share;
+      double jalloc_l = lane < R ? F.jd.alloc[lane] : 0.0;
+      bool role_min_any = false;
+      for (int r = lane; r < nroles; r += 32) {
+        const RoleStatic rs = fp.rstat[role_base + r];
+        const RoleDyn rd = rdyn[role_base + r];
+        S.r_occ[r] = rd.occ; S.r_pip[r] = rd.pip; S.r_pending[r] = rd.pending; S.r_failed[r] = (uint8_t)rd.failed;
+        S.r_min[r] = rs.min; S.r_flags[r] = rs.flags;
+        if (rs.flags & VC_ROLE_IN_MIN_MAP) role_min_any = true;
       }
+      role_min_any = __any_sync(0xffffffffu, role_min_any);
+      // CheckTaskReady (job_info.go:1024-1036) can only fail when role minima are in force
+      const bool role_min_active = role_min_any && !(minav < taskmintotal);
+      if (lane == 0) {
+        S.minav = minav; S.taskmintotal = taskmintotal; S.nroles = nroles; S.pbe = pbe; S.ntasks_total = ntasks_total;
+        S.role_base = role_base;
+      }
+      visit_id += 1;  // util.NewPredicateHelper(): a fresh error cache per visit
       __syncwarp();
-      if (lane == 0) {  // unpack into the scalar control block the ctl_* helpers read
-        S.queue = q; S.job = j;
-        S.qflags = F.qs.flags; S.qflags2 = F.qd.flags2; S.qalloc_has = F.qd.alloc_has; S.qdes_has = F.qs.des_has;
-        S.qshare = F.qd.share;
-        for (int d = 0; d < R; ++d) { S.qalloc[d] = F.qd.alloc[d]; S.qdes[d] = F.qs.des[d]; }
-        S.cursor = F.js.task_off + F.jd.cursor;
-        S.task_end = F.js.task_end;
-        S.ready = F.jd.ready; S.waiting = F.jd.waiting; S.pbe = F.js.pending_besteffort; S.minav = F.js.min_available;
-        S.ntasks_total = F.js.n_tasks_total; S.taskmintotal = F.js.task_min_total; S.jflags = F.js.flags;
-        S.role_base = F.js.role_off; S.nroles = F.js.n_roles;
-        S.jshare = F.jd.share;
-        for (int d = 0; d < R; ++d) S.jalloc[d] = F.jd.alloc[d];
-        for (int r = 0; r < S.nroles; ++r) {
-          S.r_occ[r] = F.rd[r].occ; S.r_pip[r] = F.rd[r].pip; S.r_pending[r] = F.rd[r].pending;
-          S.r_failed[r] = (uint8_t)F.rd[r].failed; S.r_min[r] = F.rs[r].min; S.r_flags[r] = F.rs[r].flags;
+      const bool pure = (jflags & VC_JOBX_PURE) != 0;
+      int4 meta = __ldg(&p.tmeta[cursor]);
+      // ssn.JobReady (session_plugins.go:428-446) on the register state
+      auto job_ready_now = [&]() -> bool {
+        if (!f_gang_ready) return true;
+        if (role_min_active) {
+          bool ok = true;
+          for (int r = 0; r < nroles; ++r)
+            if ((S.r_flags[r] & VC_ROLE_IN_MIN_MAP) && S.r_occ[r] < S.r_min[r]) ok = false;
+          if (!ok) return false;
         }
-        S.n_ops = 0;
-        S.visit_id += 1;  // util.NewPredicateHelper(): a fresh error cache per visit
-      }
-      __syncwarp();
-      const bool pure = (S.jflags & VC_JOBX_PURE) != 0;
-      int4 meta = __ldg(&p.tmeta[S.cursor]);
+        return ready + pbe >= minav;
+      };
       PROF_MARK(0);
 
       // ---- allocateResourcesForTasks, allocate.go:558-694 ----
       for (;;) {
-        if (S.cursor >= S.task_end) break;
+        if (cursor >= task_end) break;
         PROF_MARK(4);
-        const int t = meta.x, grp = meta.y, rl = meta.z - S.role_base;
-        const int next_pos = S.cursor + 1;
-        if (next_pos < S.task_end) meta = __ldg(&p.tmeta[next_pos]);  // prefetch the next task's record
-        __syncwarp();
-        if (grp != S.cur_group) {  // stage the group's request record
+        const int t = meta.x, grp = meta.y, rl = meta.z - role_base;
+        cursor += 1;
+        if (cursor < task_end) meta = __ldg(&p.tmeta[cursor]);  // prefetch the next task's record
+        if (grp != cur_group) {  // stage the group's request record (shared: workers read it in sweeps)
+          __syncwarp();
           if (lane < R) S.trec.req[lane] = __ldg(&p.g_req[(size_t)lane * p.n_groups + grp]);
           if (lane >= 16 && lane < 16 + K) S.trec.kreq[lane - 16] = __ldg(&p.g_kreq[(size_t)(lane - 16) * p.n_groups + grp]);
           if (lane >= 24 && lane < 26) S.trec.knz[lane - 24] = __ldg(&p.g_knz[(size_t)(lane - 24) * p.n_groups + grp]);
           if (lane == 31) { S.trec.has = __ldg(&p.g_has[grp]); S.trec.klass = __ldg(&p.g_class[grp]); }
-        }
-        if (lane == 0) { S.task = t; S.role_local = rl; S.cursor = next_pos; S.cur_group = grp; }
-        __syncwarp();
-        if (!ctl_allocatable(p, S)) continue;
-        const bool named_role = !(S.r_flags[rl] & VC_ROLE_EMPTY_NAME);
-        if (named_role && S.r_failed[rl]) {
-          if (lane == 0) { if (out_cta) p.fit_errors[S.n_fit] = t; S.n_fit += 1; }
           __syncwarp();
+          cur_group = grp;
+          t_has = S.trec.has;
+          req_fit = lane < 8 && lane < R ? S.trec.req[lane] : 0.0;
+          fit_on = lane < R && lane < 8 && (lane < 2 || (t_has & (1u << lane)));
+          b_val = !lane_valid ? 0.0 : role == ROLE_BP ? S.trec.req[dk_c] : role == ROLE_BAL ? S.trec.kreq[dk_c] : S.trec.knz[dk_c];
+          on_task = role == ROLE_BP ? (lane_valid && (dk_c < 2 || (t_has & (1u << dk_c))) && b_val >= VC_MIN_RESOURCE && w_d >= 0)
+                  : role == ROLE_BAL ? (lane_valid && !(dk_c >= 2 && b_val == 0.0))
+                  : (role != ROLE_NONE);
+        }
+        const double req_l = lane < R ? S.trec.req[lane] : 0.0;  // request, one dimension per lane
+        // ---- ssn.Allocatable -> proportion queueAllocatable (proportion.go:333-348) ----
+        if (f_alloc_prop) {
+          bool ok = (qflags & VC_QUEUE_OPEN) != 0;
+          const uint32_t rq_has = t_has & ~3u;
+          const bool fu_nil = (qflags2 & 2u) && rq_has == 0;
+          if (lane < R) {
+            const int d = lane;
+            if (d < 2) {
+              if (req_l > 0.0 && qalloc_l + req_l > qdes_l) ok = false;
+            } else if (!fu_nil && (rq_has & (1u << d)) && d != p.d.pods_dim) {
+              const double al = (qalloc_has & (1u << d)) ? qalloc_l : 0.0;
+              const double de = (qdes_has & (1u << d)) ? qdes_l : 0.0;
+              if (req_l > 0.0 && al + req_l > de) ok = false;
+            }
+          }
+          if (!__all_sync(0xffffffffu, ok)) continue;
+        }
+        const uint32_t rflags = S.r_flags[rl];
+        const bool named_role = !(rflags & VC_ROLE_EMPTY_NAME);
+        if (named_role && S.r_failed[rl]) {  // job.TaskHasFitErrors, allocate.go:600-607
+          if (lane == 0 && out_cta) p.fit_errors[n_fit] = t;
+          n_fit += 1;
           continue;
         }
         // For a 'pure' job the role-level error cache can never change a verdict (same record, node
@@ -508,40 +694,37 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         const bool use_cache = c.enable_ecache && named_role && !pure;
         PROF_MARK(1);
 
-        if (pure && grp == S.cache_group) {
+        if (pure && grp == cache_group) {
           // -------- incremental step --------
-          if (S.dirty_node >= 0) {
-            const int dn = S.dirty_node;
+          if (dirty_node >= 0) {
+            const int dn = dirty_node;
             const int o = (dn - p.d.node_begin) / p.npc;
-            const unsigned tag = (S.pc + 1u) & 0x3fffffffu;
-            uint4 *ent = p.ring + (size_t)(S.pc % RING_DEPTH) * RING_STRIDE;
+            const unsigned tag = (pc + 1u) & 0x3fffffffu;
+            uint4 *ent = p.ring + (size_t)(pc % RING_DEPTH) * RING_STRIDE;
             Best nb;
             if (o == cta) {
               const int i = dn - nbase;
-              FastNodeView nv{fs, i};
-              double sc = 0.0;
               const int old_cat = fs.c_cat[i];
-              int cat = eval_pair_fast(c, R, K, S.trec, nv, fs.c_cs[i], c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i], &sc);
-              __syncwarp();
+              double sc = 0.0;
+              const int cat = eval_dirty(i, &sc);
               if (lane == 0) { fs.c_cat[i] = cat; fs.c_score[i] = sc; }
               // CTA best, incrementally: rescan only when the holder got worse
-              int cnt = F.cta_cnt + (cat == 0 ? 1 : 0) - (old_cat == 0 ? 1 : 0);
+              int cnt = cta_cnt + (cat == 0 ? 1 : 0) - (old_cat == 0 ? 1 : 0);
               bool rescan = false;
-              double bs = F.cta_best_score;
-              int bn = F.cta_best_node;
-              if (bn == dn) {
-                if (cat == 0 && sc >= bs) bs = sc;
+              if (cta_best_node == dn) {
+                if (cat == 0 && sc >= cta_best_score) cta_best_score = sc;
                 else rescan = true;
-              } else if (cat == 0 && (bn < 0 || better(sc, dn, bs, bn))) {
-                bs = sc; bn = dn;
+              } else if (cat == 0 && (cta_best_node < 0 || better(sc, dn, cta_best_score, cta_best_node))) {
+                cta_best_score = sc; cta_best_node = dn;
               }
-              __syncwarp();
-              if (rescan) { Best r = scan_cache(fs, nmine, nbase); bs = r.score; bn = r.node; cnt = r.cnt; }
-              nb.score = bs; nb.node = bn; nb.cnt = cnt;
-              if (lane == 0) {
-                F.cta_best_score = bs; F.cta_best_node = bn; F.cta_cnt = cnt;
-                mbox_store(ent, pack_best(nb, tag));
+              if (rescan) {
+                __syncwarp();
+                Best r = scan_cache(fs, nmine, nbase);
+                cta_best_score = r.score; cta_best_node = r.node; cnt = r.cnt;
               }
+              cta_cnt = cnt;
+              nb.score = cta_best_score; nb.node = cta_best_node; nb.cnt = cnt;
+              if (lane == 0) mbox_store(ent, pack_best(nb, tag));
               nb.cnt = min(cnt, 2);
             } else {
               uint4 v;
@@ -550,38 +733,39 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             }
             // global best, incrementally
             const int old_cnt = fs.sl_cnt[o];
-            int gcnt = F.g_cnt + nb.cnt - old_cnt;
-            double gs = F.g_best_score;
-            int gn = F.g_best_node;
+            g_cnt += nb.cnt - old_cnt;
             bool refold = false;
-            const int g_owner = gn >= 0 ? (gn - p.d.node_begin) / p.npc : -1;
+            const int g_owner = g_best_node >= 0 ? (g_best_node - p.d.node_begin) / p.npc : -1;
             if (g_owner == o) {
-              if (nb.node >= 0 && (better(nb.score, nb.node, gs, gn) || (nb.node == gn && nb.score == gs))) { gs = nb.score; gn = nb.node; }
-              else refold = true;
-            } else if (nb.node >= 0 && (gn < 0 || better(nb.score, nb.node, gs, gn))) {
-              gs = nb.score; gn = nb.node;
+              if (nb.node >= 0 && (better(nb.score, nb.node, g_best_score, g_best_node) ||
+                                   (nb.node == g_best_node && nb.score == g_best_score))) {
+                g_best_score = nb.score; g_best_node = nb.node;
+              } else {
+                refold = true;
+              }
+            } else if (nb.node >= 0 && (g_best_node < 0 || better(nb.score, nb.node, g_best_score, g_best_node))) {
+              g_best_score = nb.score; g_best_node = nb.node;
             }
             __syncwarp();
-            if (lane == 0) {
-              fs.sl_score[o] = nb.score; fs.sl_node[o] = nb.node; fs.sl_cnt[o] = nb.cnt;
-              S.pc += 1; S.since_sync += 1; S.dirty_node = -1;
+            if (lane == 0) { fs.sl_score[o] = nb.score; fs.sl_node[o] = nb.node; fs.sl_cnt[o] = nb.cnt; }
+            pc += 1; since_sync += 1; dirty_node = -1;
+            if (refold) {
+              __syncwarp();
+              Best g = fold_slots(fs, G);
+              g_best_score = g.score; g_best_node = g.node; g_cnt = g.cnt;
             }
-            __syncwarp();
-            if (refold) { Best g = fold_slots(fs, G); gs = g.score; gn = g.node; gcnt = g.cnt; }
-            if (lane == 0) { F.g_best_score = gs; F.g_best_node = gn; F.g_cnt = gcnt; }
-            __syncwarp();
           }
-          if (S.since_sync >= RING_DEPTH / 2) {  // keep the publication ring from being overrun
-            Best mine{F.cta_best_score, F.cta_best_node, F.cta_cnt};
-            exchange_all_fast(p, mine, S.ag, fs);
-            if (lane == 0) { S.ag += 1; S.since_sync = 0; }
+          if (since_sync >= RING_DEPTH / 2) {  // keep the publication ring from being overrun
+            Best mine{cta_best_score, cta_best_node, cta_cnt};
             __syncwarp();
+            exchange_all_fast(p, mine, ag, fs);
+            ag += 1; since_sync = 0;
           }
-          if (lane == 0) S.n_incr += 1;
+          n_incr += 1;
           PROF_MARK(2);
         } else {
           // -------- full sweep --------
-          if (lane == 0) { S.cmd = CMD_SWEEP; S.sweep_rl = rl; S.sweep_use_cache = use_cache ? 1 : 0; }
+          if (lane == 0) { S.cmd = CMD_SWEEP; S.sweep_rl = rl; S.sweep_use_cache = use_cache ? 1 : 0; S.visit_id = visit_id; }
           __syncthreads();  // B1
           sweep_part();
           __syncthreads();  // B2
@@ -589,35 +773,48 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           Best mine{0.0, -1, 0};
           if (lane < nwarps) best_fold(mine, S.w_score[0][lane], S.w_node[0][lane], S.w_cnt[0][lane]);
           best_warp_reduce(mine);
-          exchange_all_fast(p, mine, S.ag, fs);
+          exchange_all_fast(p, mine, ag, fs);
           Best g = fold_slots(fs, G);
-          if (lane == 0) {
-            S.ag += 1; S.since_sync = 0; S.dirty_node = -1; S.n_full += 1;
-            S.cache_group = pure ? grp : -1;  // verdicts taken under an error cache are not reusable
-            F.cta_best_score = mine.score; F.cta_best_node = mine.node; F.cta_cnt = mine.cnt;
-            F.g_best_score = g.score; F.g_best_node = g.node; F.g_cnt = g.cnt;
-          }
-          __syncwarp();
+          ag += 1; since_sync = 0; dirty_node = -1; n_full += 1;
+          cache_group = pure ? grp : -1;  // verdicts taken under an error cache are not reusable
+          cta_best_score = mine.score; cta_best_node = mine.node; cta_cnt = mine.cnt;
+          g_best_score = g.score; g_best_node = g.node; g_cnt = g.cnt;
         }
-        const double g_score = F.g_best_score;
-        const int g_node = F.g_best_node, g_cnt = F.g_cnt;
-        if (lane == 0) S.n_steps += 1;
+        n_steps += 1;
         PROF_MARK(3);
 
         if (g_cnt == 0) {  // no feasible node, allocate.go:639-659
-          if (lane == 0) { if (out_cta) p.fit_errors[S.n_fit] = t; S.n_fit += 1; S.r_failed[rl] = 1; }
+          if (lane == 0) { if (out_cta) p.fit_errors[n_fit] = t; S.r_failed[rl] = 1; }
+          n_fit += 1;
           __syncwarp();
-          if (ctl_need_continue(S)) continue;
+          // job.NeedContinueAllocating, api/job_info.go:918-966
+          bool cont;
+          if (minav >= ntasks_total) {
+            cont = false;
+          } else if (minav < taskmintotal) {
+            int left = 0;
+            for (int r = 0; r < nroles; ++r)
+              if (!S.r_failed[r]) left += S.r_pending[r];
+            cont = ready + left >= minav;
+          } else {
+            cont = true;
+            for (int r = 0; r < nroles; ++r) {
+              if (!S.r_failed[r]) continue;
+              const int mn = (S.r_flags[r] & VC_ROLE_IN_MIN_MAP) ? S.r_min[r] : 0;
+              if (mn != 0 && S.r_occ[r] < mn) cont = false;
+            }
+          }
+          if (cont) continue;
           break;
         }
-        const int best = g_node;
-        const double score = g_cnt == 1 ? 0.0 : g_score;
+        const int best = g_best_node;
+        const double score = g_cnt == 1 ? 0.0 : g_best_score;
         // ---- Statement.Allocate: node.AddTask on the owner CTA (api/node_info.go:435-484) ----
         if (best >= nbase && best < nbase + nmine) {
           const int i = best - nbase;
           if (lane < R) {
-            fs.idle[lane * cap + i] -= S.trec.req[lane];
-            fs.used[lane * cap + i] += S.trec.req[lane];
+            fs.idle[lane * cap + i] -= req_l;
+            fs.used[lane * cap + i] += req_l;
           }
           if (c.has_predicates) {  // predicates AllocateFunc, predicates.go:212-256
             if (lane == 16) fs.pod_count[i] += 1;
@@ -625,89 +822,85 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             if (lane >= 24 && lane < 26) fs.knz[(lane - 24) * cap + i] += S.trec.knz[lane - 24];
           }
         }
-        // event handlers: drf (drf.go:391-418) and proportion (proportion.go:475-497), one lane per dimension
-        double new_jshare = 0.0, new_qshare = 0.0;
-        if (c.has_drf) {
-          double sh = 0.0;
-          if (lane < R) {
-            const int d = lane;
-            const double al = S.jalloc[d] + S.trec.req[d];
-            if ((d < 2 || (p.total_has & (1u << d))) && p.total[d] >= VC_MIN_RESOURCE) sh = share_of(al, p.total[d]);
-          }
-          for (int o = 16; o; o >>= 1) sh = fmax(sh, __shfl_xor_sync(0xffffffffu, sh, o));
-          new_jshare = sh;
-        }
-        const bool prop = c.has_proportion && (S.qflags2 & 1u);
-        if (prop) {
-          double sh = 0.0;
-          if (lane < R) {
-            const int d = lane;
-            const bool touched = d < 2 || (S.trec.has & (1u << d));
-            const bool has = d < 2 || (S.qalloc_has & (1u << d)) || touched;
-            const double al = has ? S.qalloc[d] + (touched ? S.trec.req[d] : 0.0) : 0.0;
-            if ((d < 2 || (S.qdes_has & (1u << d))) && S.qdes[d] >= VC_MIN_RESOURCE) sh = share_of(al, S.qdes[d]);
-          }
-          for (int o = 16; o; o >>= 1) sh = fmax(sh, __shfl_xor_sync(0xffffffffu, sh, o));
-          new_qshare = sh;
-        }
-        __syncwarp();
+        dirty_node = best;
+        // job.UpdateTaskStatus + event handlers: drf (drf.go:391-418), proportion (proportion.go:475-497)
+        ready += 1;
         if (lane == 0) {
-          const TaskRec &trec = S.trec;
-          S.dirty_node = best;
           S.r_pending[rl] -= 1;
           S.r_occ[rl] += 1;
-          S.ready += 1;
-          if (c.has_drf) {
-            for (int d = 0; d < R; ++d) S.jalloc[d] += trec.req[d];
-            S.jshare = new_jshare;
-          }
-          if (prop) {
-            S.qalloc[0] += trec.req[0];
-            S.qalloc[1] += trec.req[1];
-            for (int d = 2; d < R; ++d)
-              if (trec.has & (1u << d)) { S.qalloc[d] += trec.req[d]; S.qalloc_has |= 1u << d; S.qflags2 &= ~2u; }
-            S.qshare = new_qshare;
-          }
-          const int k = S.n_ops;
-          ops[k * 3 + 0] = t; ops[k * 3 + 1] = best; ops[k * 3 + 2] = VC_OP_ALLOCATE;
-          ops_score[k] = score;
-          S.n_ops = k + 1;
+          ops[n_ops * 3 + 0] = t; ops[n_ops * 3 + 1] = best; ops[n_ops * 3 + 2] = VC_OP_ALLOCATE;
+          ops_score[n_ops] = score;
         }
-        __syncwarp();
-        if (ctl_job_ready(c, S)) break;
+        n_ops += 1;
+        if (c.has_drf) {
+          jalloc_l += req_l;
+          double sh = 0.0;
+          if (lane < R && (lane < 2 || (p.total_has & (1u << lane))) && p.total[lane] >= VC_MIN_RESOURCE) sh = share_of(jalloc_l, p.total[lane]);
+          for (int o = 16; o; o >>= 1) sh = fmax(sh, __shfl_xor_sync(0xffffffffu, sh, o));
+          jshare = sh;
+        }
+        if (c.has_proportion && (qflags2 & 1u)) {
+          if (lane < 2 || (lane < R && (t_has & (1u << lane)))) qalloc_l += req_l;
+          const uint32_t add = t_has & ~3u & ((1u << R) - 1u);
+          if (add) { qalloc_has |= add; qflags2 &= ~2u; }
+          double sh = 0.0;
+          if (lane < R && (lane < 2 || (qdes_has & (1u << lane))) && qdes_l >= VC_MIN_RESOURCE) {
+            const double al = (lane < 2 || (qalloc_has & (1u << lane))) ? qalloc_l : 0.0;
+            sh = share_of(al, qdes_l);
+          }
+          for (int o = 16; o; o >>= 1) sh = fmax(sh, __shfl_xor_sync(0xffffffffu, sh, o));
+          qshare = sh;
+        }
+        if (role_min_active) __syncwarp();
+        if (job_ready_now()) break;  // ssn.SubJobReady, allocate.go:676-678
       }
       PROF_MARK(4);
 
       // ---- statement outcome, allocate.go:681-693 and :330-337 ----
-      const bool ready = ctl_job_ready(c, S);
-      const bool stmt = ready || ctl_job_pipelined(c, S);
-      const int n_ops = S.n_ops;
+      __syncwarp();
+      const bool jready = job_ready_now();
+      bool stmt = jready;
+      if (!stmt) {  // ssn.JobPipelined needs the shared control block (rare path)
+        if (lane == 0) { S.ready = ready; S.waiting = waiting; }
+        __syncwarp();
+        stmt = ctl_job_pipelined(c, S);
+      }
       if (!stmt && n_ops > 0) {
-        if (lane == 0) S.cmd = CMD_DISCARD;
+        if (lane == 0) { S.cmd = CMD_DISCARD; S.n_ops = n_ops; }
         __syncthreads();  // B1
         discard_part();
         __syncthreads();  // B2
-        if (lane == 0) {
-          for (int k = n_ops - 1; k >= 0; --k) {
-            const int ot = ops[k * 3 + 0];
-            const int orl = p.t_role[ot] - S.role_base;
-            S.r_pending[orl] += 1; S.r_occ[orl] -= 1; S.ready -= 1;
-            if (c.has_drf)
-              for (int d = 0; d < R; ++d) S.jalloc[d] -= p.req[(size_t)d * T + ot];
-            if (c.has_proportion && (S.qflags2 & 1u)) {
-              const uint32_t oh = p.req_has[ot];
-              S.qalloc[0] -= p.req[(size_t)0 * T + ot];
-              S.qalloc[1] -= p.req[(size_t)1 * T + ot];
-              if (!(S.qflags2 & 2u))
-                for (int d = 2; d < R; ++d)
-                  if (oh & (1u << d)) { S.qalloc[d] -= p.req[(size_t)d * T + ot]; S.qalloc_has |= 1u << d; }
-            }
+        for (int k = n_ops - 1; k >= 0; --k) {  // unallocate + DeallocateFunc handlers, reverse order
+          const int ot = ops[k * 3 + 0];
+          const int orl = p.t_role[ot] - role_base;
+          if (lane == 0) { S.r_pending[orl] += 1; S.r_occ[orl] -= 1; }
+          ready -= 1;
+          const double orq = lane < R ? p.req[(size_t)lane * T + ot] : 0.0;
+          if (c.has_drf) jalloc_l -= orq;
+          if (c.has_proportion && (qflags2 & 1u)) {
+            const uint32_t oh = p.req_has[ot];
+            if (lane < 2) qalloc_l -= orq;
+            else if (!(qflags2 & 2u) && lane < R && (oh & (1u << lane))) qalloc_l -= orq;
+            if (!(qflags2 & 2u)) qalloc_has |= oh & ~3u & ((1u << R) - 1u);
           }
-          if (c.has_drf) S.jshare = drf_share(p, S.jalloc);
-          if (c.has_proportion && (S.qflags2 & 1u)) S.qshare = queue_share(R, S.qalloc, S.qalloc_has, S.qdes, S.qdes_has);
-          S.cache_group = -1;  // several nodes changed at once: drop the verdict cache
-          S.dirty_node = -1;
         }
+        if (c.has_drf) {
+          double sh = 0.0;
+          if (lane < R && (lane < 2 || (p.total_has & (1u << lane))) && p.total[lane] >= VC_MIN_RESOURCE) sh = share_of(jalloc_l, p.total[lane]);
+          for (int o = 16; o; o >>= 1) sh = fmax(sh, __shfl_xor_sync(0xffffffffu, sh, o));
+          jshare = sh;
+        }
+        if (c.has_proportion && (qflags2 & 1u)) {
+          double sh = 0.0;
+          if (lane < R && (lane < 2 || (qdes_has & (1u << lane))) && qdes_l >= VC_MIN_RESOURCE) {
+            const double al = (lane < 2 || (qalloc_has & (1u << lane))) ? qalloc_l : 0.0;
+            sh = share_of(al, qdes_l);
+          }
+          for (int o = 16; o; o >>= 1) sh = fmax(sh, __shfl_xor_sync(0xffffffffu, sh, o));
+          qshare = sh;
+        }
+        cache_group = -1;  // several nodes changed at once: drop the verdict cache
+        dirty_node = -1;
         __syncwarp();
       }
       // results (CTA 0): decisions copied lane-parallel
@@ -715,36 +908,28 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         for (int k = lane; k < n_ops; k += 32) {
           vc_decision dcs;
           dcs.task = ops[k * 3 + 0]; dcs.node = ops[k * 3 + 1]; dcs.kind = ops[k * 3 + 2];
-          dcs.visit = S.n_vis; dcs.score = ops_score[k];
-          p.decisions[S.n_dec + k] = dcs;
+          dcs.visit = n_vis; dcs.score = ops_score[k];
+          p.decisions[n_dec + k] = dcs;
         }
       }
-      __syncwarp();
-      // ---- write the job / queue / role records back into the replica (one coalesced access each) ----
-      if (lane == 0) {
-        F.jd.ready = S.ready; F.jd.waiting = S.waiting; F.jd.cursor = S.cursor - F.js.task_off; F.jd.share = S.jshare;
-        for (int d = 0; d < R; ++d) { F.jd.alloc[d] = S.jalloc[d]; F.qd.alloc[d] = S.qalloc[d]; }
-        F.qd.alloc_has = S.qalloc_has; F.qd.flags2 = S.qflags2; F.qd.share = S.qshare;
-        F.qd.active = 1;  // queues.Push(queue), allocate.go:346
-        for (int r = 0; r < S.nroles; ++r) {
-          F.rd[r].occ = S.r_occ[r]; F.rd[r].pip = S.r_pip[r]; F.rd[r].pending = S.r_pending[r]; F.rd[r].failed = S.r_failed[r];
-        }
-        if (out_cta) {
-          vc_visit v;
-          v.job = j;
-          v.outcome = stmt ? (ready ? VC_VISIT_COMMIT : VC_VISIT_KEEP) : VC_VISIT_DISCARD;
-          v.first_op = S.n_dec;
-          v.n_ops = stmt ? n_ops : 0;
-          p.visits[S.n_vis] = v;
-        }
-        if (stmt) S.n_dec += n_ops;
-        S.n_vis += 1;
-        if (stmt && ready && S.cursor < S.task_end) {  // jobs.Push(job), allocate.go:334-336
+      if (out_cta && lane == 0) {
+        vc_visit v;
+        v.job = j;
+        v.outcome = stmt ? (jready ? VC_VISIT_COMMIT : VC_VISIT_KEEP) : VC_VISIT_DISCARD;
+        v.first_op = n_dec;
+        v.n_ops = stmt ? n_ops : 0;
+        p.visits[n_vis] = v;
+      }
+      if (stmt) n_dec += n_ops;
+      n_vis += 1;
+      // jobs.Push(job) when committed and tasks remain (allocate.go:334-336)
+      if (stmt && jready && cursor < task_end) {
+        if (lane == 0) {
           HeapEnt e;
-          e.share = S.jshare; e.job = j; e.prio = F.js.priority; e.rank = F.js.rank;
-          e.bits = (ctl_is_ready(S) ? 1u : 0u) | ((S.jflags & VC_JOB_PREEMPTABLE) ? 2u : 0u);
+          e.share = jshare; e.job = j; e.prio = j_prio; e.rank = j_rank;
+          e.bits = ((ready + pbe >= minav) ? 1u : 0u) | ((jflags & VC_JOB_PREEMPTABLE) ? 2u : 0u);
           HeapEnt *h = heap + sbeg;
-          int i = F.qd.hsize++;
+          int i = q_hsize;
           while (i > 0) {
             int par = (i - 1) / 2;
             if (!job_less(c, key_of(e), key_of(h[par]))) break;
@@ -753,15 +938,30 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           }
           h[i] = e;
         }
+        q_hsize += 1;
       }
+      // ---- write the job / queue / role records back into the replica ----
       __syncwarp();
-      for (int w = lane; w < (int)(sizeof(JobDyn) / 4); w += 32) reinterpret_cast<int *>(&jdyn[j])[w] = reinterpret_cast<int *>(&F.jd)[w];
-      for (int w = lane; w < (int)(sizeof(QueueDyn) / 4); w += 32) reinterpret_cast<int *>(&qdyn[q])[w] = reinterpret_cast<int *>(&F.qd)[w];
-      for (int r = lane; r < S.nroles; r += 32) rdyn[S.role_base + r] = F.rd[r];
+      if (lane == 0) {
+        JobDyn *jd = &jdyn[j];
+        jd->ready = ready; jd->waiting = waiting; jd->cursor = cursor - task_off; jd->share = jshare;
+        QueueDyn *qd = &qdyn[q];
+        qd->alloc_has = qalloc_has; qd->flags2 = qflags2; qd->active = 1;  // queues.Push(queue), allocate.go:346
+        qd->scursor = q_scursor; qd->hsize = q_hsize; qd->share = qshare;
+      }
+      if (lane < R) { jdyn[j].alloc[lane] = jalloc_l; qdyn[q].alloc[lane] = qalloc_l; }
+      for (int r = lane; r < nroles; r += 32) {
+        RoleDyn rd;
+        rd.occ = S.r_occ[r]; rd.pip = S.r_pip[r]; rd.pending = S.r_pending[r]; rd.failed = S.r_failed[r];
+        rdyn[role_base + r] = rd;
+      }
       __syncwarp();
       PROF_MARK(0);
     }
-    if (lane == 0) S.cmd = CMD_EXIT;
+    if (lane == 0) {
+      S.cmd = CMD_EXIT;
+      S.n_dec = n_dec; S.n_vis = n_vis; S.n_fit = n_fit; S.n_steps = n_steps; S.n_full = n_full; S.n_incr = n_incr;
+    }
     __syncthreads();  // B1 of the exit command
   }
 
