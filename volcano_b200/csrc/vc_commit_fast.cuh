@@ -36,7 +36,7 @@ struct JobStatic {  // 64 B, read-only
   uint32_t flags;
   uint32_t rank;
   int32_t task_off, task_end, queue;
-  int32_t pad[4];
+  unsigned long long key_pre, key_post;  // packed static part of the ssn.JobOrderFn key (see HeapKey)
 };
 struct JobDyn {  // 96 B, per-CTA replica
   int32_t ready, waiting, cursor, pad;
@@ -59,7 +59,28 @@ struct QueueDyn {  // 96 B
 };
 static_assert(sizeof(JobStatic) == 64 && sizeof(JobDyn) == 96 && sizeof(QueueStatic) == 80 && sizeof(QueueDyn) == 96, "record layout");
 
+// ssn.JobOrderFn (session_plugins.go:660-683) as one lexicographic integer key: the comparators enabled in
+// the conf, in plugin order, packed MSB-first — priority (dense rank of the value, higher first), gang
+// readiness bit, drf share (raw bits of a non-negative double), tdm preemptable bit — then the
+// (CreationTimestamp, UID) rank. Built on the host for the static parts; the ready bit and the share are
+// the only dynamic components and only change while the job is outside the queue.
+struct HeapKey {  // 32 B
+  unsigned long long pre, share, post;
+  int job, pad;
+};
+__device__ __forceinline__ bool hk_less(const HeapKey &a, const HeapKey &b) {
+  if (a.pre != b.pre) return a.pre < b.pre;
+  if (a.share != b.share) return a.share < b.share;
+  return a.post < b.post;
+}
+
 struct FastParams {  // extra kernel arguments of the fast kernel
+  const int32_t *heap_off;  // [Q+1] capacity prefix of the per-queue heaps of re-pushed jobs
+  int ready_word;           // 0: readiness not compared, 1: bit lives in key.pre, 2: in key.post
+  int ready_shift;
+  int share_on;             // drf JobOrderFn enabled
+  int heap_in_smem;         // the heaps fit in shared memory
+  int heap_total;
   const JobStatic *jstat;
   const RoleStatic *rstat;
   const QueueStatic *qstat;
@@ -218,6 +239,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   fs.c_cs = reinterpret_cast<uint32_t *>(sp); sp += (size_t)cap * 4;
   fs.sl_node = reinterpret_cast<int32_t *>(sp); sp += (size_t)G * 4;
   fs.sl_cnt = reinterpret_cast<int32_t *>(sp); sp += (size_t)G * 4;
+  sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 15) & ~(uintptr_t)15);
+  HeapKey *heap = fp.heap_in_smem ? reinterpret_cast<HeapKey *>(sp)
+                                  : reinterpret_cast<HeapKey *>(p.rep_heap) + (size_t)cta * p.rep_heap_stride;
 
   for (int i = tid; i < nmine; i += blockDim.x) {
     const int n = nbase + i;
@@ -248,7 +272,6 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   RoleDyn *rdyn = reinterpret_cast<RoleDyn *>(rb); rb += (size_t)NR * sizeof(RoleDyn);
   double *ops_score = reinterpret_cast<double *>(rb);
   int32_t *ops = p.rep_i32 + (size_t)cta * p.rep_i32_stride;  // task, node, kind
-  HeapEnt *heap = p.rep_heap + (size_t)cta * p.rep_heap_stride;
 
   for (int j = tid; j < J; j += blockDim.x) {
     JobDyn jd;
@@ -381,7 +404,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     // ---- register copies of the control state ----
     int cur_group = -1, cache_group = -1, dirty_node = -1, since_sync = 0;
     unsigned ag = 0, pc = 0;
-    int n_dec = 0, n_vis = 0, n_fit = 0, n_steps = 0, n_full = 0, n_incr = 0, visit_id = 0;
+    int n_dec = 0, n_vis = 0, n_fit = 0, n_steps = 0, n_full = 0, n_incr = 0, visit_id = 0, n_owner_change = 0, last_owner = -1;
     double cta_best_score = 0.0, g_best_score = 0.0;
     int cta_best_node = -1, cta_cnt = 0, g_best_node = -1, g_cnt = 0;
 
@@ -546,7 +569,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       }
       int j = -1;
       if (!over) {
-        HeapEnt *h = heap + sbeg;
+        HeapKey *h = heap + __ldg(&fp.heap_off[q]);
         const int sc = sbeg + q_scursor;
         const int hs = q_hsize;
         const bool have_s = sc < send, have_h = hs > 0;
@@ -555,16 +578,18 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           load_record(&F.js, &fp.jstat[js], sizeof(JobStatic) / 4, true);
           load_record(&F.jd, &jdyn[js], sizeof(JobDyn) / 4, false);
         }
-        HeapEnt top;
+        HeapKey top;
         if (have_h) top = h[0];
         __syncwarp();
         bool from_heap = false;
         if (have_s && have_h) {
-          JobKey ks;
-          ks.share = F.jd.share; ks.prio = F.js.priority; ks.rank = F.js.rank;
-          ks.ready = F.jd.ready + F.js.pending_besteffort >= F.js.min_available;
-          ks.preempt = (F.js.flags & VC_JOB_PREEMPTABLE) != 0;
-          from_heap = job_less(c, key_of(top), ks);
+          HeapKey ks;
+          ks.pre = F.js.key_pre; ks.post = F.js.key_post;
+          const bool rdy = F.jd.ready + F.js.pending_besteffort >= F.js.min_available;
+          if (rdy && fp.ready_word == 1) ks.pre |= 1ull << fp.ready_shift;
+          if (rdy && fp.ready_word == 2) ks.post |= 1ull << fp.ready_shift;
+          ks.share = fp.share_on ? (unsigned long long)__double_as_longlong(F.jd.share) : 0ull;
+          from_heap = hk_less(top, ks);
         } else if (have_h) {
           from_heap = true;
         }
@@ -572,16 +597,19 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           j = top.job;
           if (lane == 0) {  // heap pop: sift-down (only jobs that were re-pushed live here)
             int n = hs - 1;
-            HeapEnt last = h[n];
+            const HeapKey last = h[n];
             int i = 0;
             for (;;) {
               int l = 2 * i + 1;
               if (l >= n) break;
-              int m = l;
-              if (l + 1 < n && job_less(c, key_of(h[l + 1]), key_of(h[l]))) m = l + 1;
-              if (!job_less(c, key_of(h[m]), key_of(last))) break;
-              h[i] = h[m];
-              i = m;
+              HeapKey cl = h[l];
+              if (l + 1 < n) {
+                const HeapKey cr = h[l + 1];
+                if (hk_less(cr, cl)) { cl = cr; l = l + 1; }
+              }
+              if (!hk_less(cl, last)) break;
+              h[i] = cl;
+              i = l;
             }
             if (n > 0) h[i] = last;
           }
@@ -604,8 +632,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       const int task_off = F.js.task_off, task_end = F.js.task_end;
       const int role_base = F.js.role_off, nroles = F.js.n_roles;
       const int minav = F.js.min_available, pbe = F.js.pending_besteffort, taskmintotal = F.js.task_min_total;
-      const int ntasks_total = F.js.n_tasks_total, j_prio = F.js.priority;
-      const uint32_t jflags = F.js.flags, j_rank = F.js.rank;
+      const int ntasks_total = F.js.n_tasks_total;
+      const uint32_t jflags = F.js.flags;
+      const unsigned long long jkey_pre = F.js.key_pre, jkey_post = F.js.key_post;
       int cursor = task_off + F.jd.cursor, ready = F.jd.ready, waiting = F.jd.waiting, n_ops = 0;
       double jshare = F.jd.share;
       double jalloc_l = lane < R ? F.jd.alloc[lane] : 0.0;
@@ -699,6 +728,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           if (dirty_node >= 0) {
             const int dn = dirty_node;
             const int o = (dn - p.d.node_begin) / p.npc;
+            if (o != last_owner) { n_owner_change += 1; last_owner = o; }
             const unsigned tag = (pc + 1u) & 0x3fffffffu;
             uint4 *ent = p.ring + (size_t)(pc % RING_DEPTH) * RING_STRIDE;
             Best nb;
@@ -925,15 +955,19 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       // jobs.Push(job) when committed and tasks remain (allocate.go:334-336)
       if (stmt && jready && cursor < task_end) {
         if (lane == 0) {
-          HeapEnt e;
-          e.share = jshare; e.job = j; e.prio = j_prio; e.rank = j_rank;
-          e.bits = ((ready + pbe >= minav) ? 1u : 0u) | ((jflags & VC_JOB_PREEMPTABLE) ? 2u : 0u);
-          HeapEnt *h = heap + sbeg;
+          HeapKey e;
+          e.pre = jkey_pre; e.post = jkey_post; e.job = j; e.pad = 0;
+          const bool rdy = ready + pbe >= minav;
+          if (rdy && fp.ready_word == 1) e.pre |= 1ull << fp.ready_shift;
+          if (rdy && fp.ready_word == 2) e.post |= 1ull << fp.ready_shift;
+          e.share = fp.share_on ? (unsigned long long)__double_as_longlong(jshare) : 0ull;
+          HeapKey *h = heap + __ldg(&fp.heap_off[q]);
           int i = q_hsize;
           while (i > 0) {
             int par = (i - 1) / 2;
-            if (!job_less(c, key_of(e), key_of(h[par]))) break;
-            h[i] = h[par];
+            const HeapKey hp = h[par];
+            if (!hk_less(e, hp)) break;
+            h[i] = hp;
             i = par;
           }
           h[i] = e;
@@ -961,6 +995,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     if (lane == 0) {
       S.cmd = CMD_EXIT;
       S.n_dec = n_dec; S.n_vis = n_vis; S.n_fit = n_fit; S.n_steps = n_steps; S.n_full = n_full; S.n_incr = n_incr;
+      S.pick2 = n_owner_change;
     }
     __syncthreads();  // B1 of the exit command
   }
@@ -984,6 +1019,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     p.counters[3] = S.n_steps;
     p.counters[5] = S.n_full;
     p.counters[6] = S.n_incr;
+    p.counters[7] = S.pick2;
     for (int k = 0; k < 8; ++k) p.prof[k] = S.prof[k];
   }
 }

@@ -113,6 +113,8 @@ struct vc_snapshot {
   Slot<JobStatic> s_jstat;
   Slot<RoleStatic> s_rstat;
   Slot<QueueStatic> s_qstat;
+  Slot<int32_t> s_heap_off;
+  int fast_ready_word = 0, fast_ready_shift = 0, fast_share_on = 0, heap_total = 0, heap_in_smem = 0;
   bool fast = false;
   uint4 *ring = nullptr;
   int last_full = 0, last_incr = 0;
@@ -235,6 +237,9 @@ void choose_geometry(vc_snapshot *s) {
     size_t rows = 3 * (size_t)R + 2 * (size_t)K + 2 + 1;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + ((sizeof(CtlFast) + 15) & ~(size_t)15) + rows * npc * 8 +
                     (size_t)npc * (8 + 4 * 5) + (size_t)ctas * (8 + 4 + 4) + 64;
+    const size_t heap_bytes = (size_t)s->heap_total * sizeof(HeapKey);
+    s->heap_in_smem = (heap_bytes <= 96 * 1024 && s->smem_bytes + heap_bytes <= 200 * 1024) ? 1 : 0;
+    if (s->heap_in_smem) s->smem_bytes += heap_bytes + 16;
   } else {
     size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 + 4) + 64;
@@ -556,6 +561,58 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     r.priority = jb->priority[j]; r.flags = j_flags_x[j]; r.rank = j_rank[j];
     r.task_off = job_task_off[j]; r.task_end = job_task_off[j + 1]; r.queue = jb->queue[j];
   }
+  // packed JobOrderFn keys (see HeapKey): comparators in plugin order, MSB first
+  {
+    std::vector<int> pre_c, post_c;  // 0 priority, 1 gang readiness, 2 tdm preemptable
+    bool share_on = false;
+    for (int i = 0; i < conf->n_plugins; ++i) {
+      const vc_plugin_option &po = conf->plugins[i];
+      if (!(po.enabled & VC_EN_JOB_ORDER)) continue;
+      std::vector<int> &dst = share_on ? post_c : pre_c;
+      if (po.plugin == VC_PLUGIN_PRIORITY) dst.push_back(0);
+      else if (po.plugin == VC_PLUGIN_GANG) dst.push_back(1);
+      else if (po.plugin == VC_PLUGIN_TDM) dst.push_back(2);
+      else if (po.plugin == VC_PLUGIN_DRF) share_on = true;
+    }
+    std::vector<int32_t> prios(jb->priority, jb->priority + J);
+    std::sort(prios.begin(), prios.end(), std::greater<int32_t>());
+    prios.erase(std::unique(prios.begin(), prios.end()), prios.end());
+    if (prios.size() >= (1u << 24)) return fail(VC_EUNSUPPORTED, "too many distinct job priorities");
+    s->fast_ready_word = 0; s->fast_ready_shift = 0; s->fast_share_on = share_on ? 1 : 0;
+    for (size_t j = 0; j < J; ++j) {
+      const uint64_t prio_rank = (uint64_t)(std::lower_bound(prios.begin(), prios.end(), jb->priority[j], std::greater<int32_t>()) - prios.begin());
+      auto pack = [&](const std::vector<int> &comps, uint64_t low, int low_bits, int word) {
+        uint64_t v = low;
+        int shift = low_bits;
+        for (int k = (int)comps.size() - 1; k >= 0; --k) {
+          const int kind = comps[k];
+          if (kind == 0) { v |= prio_rank << shift; shift += 24; }
+          else if (kind == 1) { s->fast_ready_word = word; s->fast_ready_shift = shift; shift += 1; }
+          else { v |= (uint64_t)((jb->flags[j] & VC_JOB_PREEMPTABLE) ? 1 : 0) << shift; shift += 1; }
+        }
+        return v;
+      };
+      if (share_on) {
+        jstat[j].key_pre = pack(pre_c, 0, 0, 1);
+        jstat[j].key_post = pack(post_c, j_rank[j], 32, 2);
+      } else {
+        jstat[j].key_pre = pack(pre_c, j_rank[j], 32, 1);
+        jstat[j].key_post = 0;
+      }
+    }
+  }
+  // per-queue heap capacity: only jobs that can be Ready with tasks left are ever re-pushed (allocate.go:334-336)
+  std::vector<int32_t> heap_off(Q + 1, 0);
+  for (size_t q = 0; q < Q; ++q) {
+    int cnt = 0;
+    for (int k = qjobs_off[q]; k < qjobs_off[q + 1]; ++k) {
+      const int j = qjobs[k];
+      const int scope = job_task_off[j + 1] - job_task_off[j];
+      if (jb->ready_num[j] + jb->pending_besteffort[j] + scope > jb->min_available[j]) ++cnt;
+    }
+    heap_off[q + 1] = heap_off[q] + cnt;
+  }
+  s->heap_total = heap_off[Q];
   std::vector<RoleStatic> rstat(NR);
   for (size_t r = 0; r < NR; ++r) { rstat[r].min = jb->role_min[r]; rstat[r].flags = jb->role_flags[r]; }
   std::vector<QueueStatic> qstat(Q);
@@ -609,6 +666,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     put(s, s->sg_class, g_class.data(), NG, plan);
     put(s, s->s_jstat, jstat.data(), J, plan); put(s, s->s_rstat, rstat.data(), NR, plan);
     put(s, s->s_qstat, qstat.data(), Q, plan);
+    put(s, s->s_heap_off, heap_off.data(), Q + 1, plan);
     if (plan) {
       size_t need = (s->in.used + 255) & ~(size_t)255;
       if (need > s->in.cap) {
@@ -695,6 +753,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   const size_t i32_stride = ((3 * J + 4 * NR + 5 * Q + 3 * (size_t)s->max_job_tasks) + 63) & ~(size_t)63;
   const size_t f64_words_fast = (J * sizeof(JobDyn) + Q * sizeof(QueueDyn) + NR * sizeof(RoleDyn)) / 8 + (size_t)s->max_job_tasks;
   const size_t f64_stride = (std::max<size_t>(J + R * J + R * Q + Q + (size_t)s->max_job_tasks, f64_words_fast) + 31) & ~(size_t)31;
+  // per-CTA heap replica: HeapEnt entries for k_commit, HeapKey (32 B) entries for k_commit_fast; stride in entries of
+  // the kernel's own type, sized for the larger one
   const size_t heap_stride = (s->qjobs.count + 7) & ~(size_t)7;
   if (!s->rep_i32 || s->rep_i32_stride != i32_stride || s->rep_f64_stride != f64_stride || s->rep_heap_stride != heap_stride) {
     if (s->rep_i32) cudaFree(s->rep_i32);
@@ -703,7 +763,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
     s->rep_i32 = nullptr; s->rep_f64 = nullptr; s->rep_heap = nullptr;
     CUDA_TRY(cudaMalloc(&s->rep_i32, std::max<size_t>(16, i32_stride * G * 4)));
     CUDA_TRY(cudaMalloc(&s->rep_f64, std::max<size_t>(16, f64_stride * G * 8)));
-    CUDA_TRY(cudaMalloc(&s->rep_heap, std::max<size_t>(16, std::max<size_t>(heap_stride, 1) * G * sizeof(HeapEnt))));
+    CUDA_TRY(cudaMalloc(&s->rep_heap, std::max<size_t>(16, std::max<size_t>(heap_stride, 1) * G * sizeof(HeapKey))));
     s->rep_i32_stride = i32_stride; s->rep_f64_stride = f64_stride; s->rep_heap_stride = heap_stride;
   }
   const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024;
@@ -774,6 +834,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   FastParams fp;
   fp.jstat = s->s_jstat.d(s->in); fp.rstat = s->s_rstat.d(s->in); fp.qstat = s->s_qstat.d(s->in);
   fp.q_share0 = s->q_share0.d(s->in);
+  fp.heap_off = s->s_heap_off.d(s->in); fp.ready_word = s->fast_ready_word; fp.ready_shift = s->fast_ready_shift;
+  fp.share_on = s->fast_share_on; fp.heap_in_smem = s->heap_in_smem; fp.heap_total = s->heap_total;
   void *args[] = {&p, &fp};
   CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
   CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(G), dim3(s->block), args, s->smem_bytes, s->stream));
@@ -805,6 +867,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   for (int k = 0; k < 8; ++k) r->stats.prof_cycles[k] = s->h_prof[k];
   r->stats.prof_cycles[6] = s->h_counters[5];  // full sweeps (fast kernel)
   r->stats.prof_cycles[7] = s->h_counters[6];  // incremental steps (fast kernel)
+  r->stats.prof_cycles[5] = s->h_counters[7];  // owner changes between consecutive publications
   *out = r;
   return VC_OK;
 }
