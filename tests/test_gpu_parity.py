@@ -78,7 +78,15 @@ def test_binpack_goldens(args, expected, gpu):
     assert checked >= 4
 
 
-@pytest.mark.parametrize("cfg,seed", [("tiny", 1), ("tiny", 2), ("tiny", 3), ("small", 1), ("cfg1", None), ("small", 7)])
+ALLOC_CASES = [("tiny", 1), ("tiny", 2), ("tiny", 3), ("small", 1), ("cfg1", None), ("small", 7),
+               # general kernel: FutureIdle gradient (Pipeline ops, KEEP visits), normalising TaintToleration scorer
+               ("tiny_fut", 2), ("tiny_fut", None), ("small_fut_soft", None), ("small_fut_soft", 1), ("small_fut_soft", 2),
+               ("small_soft", None), ("small_soft", 3),
+               # two roles per job with different requests + TaskMinAvailable: role minima, predicate-error cache
+               ("small_roles", None), ("small_roles", 5)]
+
+
+@pytest.mark.parametrize("cfg,seed", ALLOC_CASES)
 def test_allocate_vs_oracle(cfg, seed, gpu, oracle_engine):
     from volcano_b200.synth import make_snapshot
     snap = make_snapshot(cfg, seed)
@@ -88,7 +96,16 @@ def test_allocate_vs_oracle(cfg, seed, gpu, oracle_engine):
     assert len(res.decisions) > 0
 
 
-@pytest.mark.parametrize("cfg,seed", [("tiny", 1), ("small", 2), ("cfg1", None)])
+@pytest.mark.parametrize("cfg,seed", [("tiny", 1), ("small", 7), ("small_roles", None)])
+def test_allocate_generic_kernel(cfg, seed, gpu, oracle_engine, monkeypatch):
+    """The same sessions through k_commit (per-step full sweeps) instead of the incremental k_commit_fast."""
+    from volcano_b200.synth import make_snapshot
+    monkeypatch.setenv("VC_COMMIT_GENERIC", "1")
+    snap = make_snapshot(cfg, seed)
+    _assert_same(gpu.gpu_engine(snap), oracle_engine(snap, threads=2))
+
+
+@pytest.mark.parametrize("cfg,seed", [("tiny", 1), ("small", 2), ("cfg1", None), ("small_fut_soft", None), ("small_soft", 1)])
 def test_score_matrix_vs_oracle(cfg, seed, gpu):
     from oracle.pyoracle import OracleSession
     from volcano_b200.synth import make_snapshot

@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     // ---- register copies of the control state ----
     int cur_group = -1, cache_group = -1, dirty_node = -1, since_sync = 0;
     unsigned ag = 0, pc = 0;
+    long long own_eval = 0, own_gap = 0, own_last = 0; int own_n = 0, own_gap_n = 0;
     int n_dec = 0, n_vis = 0, n_fit = 0, n_steps = 0, n_full = 0, n_incr = 0, visit_id = 0, n_owner_change = 0, last_owner = -1;
     double cta_best_score = 0.0, g_best_score = 0.0;
     int cta_best_node = -1, cta_cnt = 0, g_best_node = -1, g_cnt = 0;
@@ -736,7 +737,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
               const int i = dn - nbase;
               const int old_cat = fs.c_cat[i];
               double sc = 0.0;
+              const long long t_e0 = clock64();
+              if (own_last != 0) { own_gap += t_e0 - own_last; own_gap_n += 1; }
               const int cat = eval_dirty(i, &sc);
+              own_eval += clock64() - t_e0; own_n += 1;
               if (lane == 0) { fs.c_cat[i] = cat; fs.c_score[i] = sc; }
               // CTA best, incrementally: rescan only when the holder got worse
               int cnt = cta_cnt + (cat == 0 ? 1 : 0) - (old_cat == 0 ? 1 : 0);
@@ -756,7 +760,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
               nb.score = cta_best_score; nb.node = cta_best_node; nb.cnt = cnt;
               if (lane == 0) mbox_store(ent, pack_best(nb, tag));
               nb.cnt = min(cnt, 2);
+              own_last = clock64();
             } else {
+              own_last = 0;
               uint4 v;
               do { v = mbox_load(ent); } while ((v.w >> 2) != tag);
               nb = unpack_best(v);
@@ -996,6 +1002,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       S.cmd = CMD_EXIT;
       S.n_dec = n_dec; S.n_vis = n_vis; S.n_fit = n_fit; S.n_steps = n_steps; S.n_full = n_full; S.n_incr = n_incr;
       S.pick2 = n_owner_change;
+      atomicAdd((unsigned long long *)&p.prof[8], (unsigned long long)own_eval);
+      atomicAdd((unsigned long long *)&p.prof[9], (unsigned long long)own_n);
+      atomicAdd((unsigned long long *)&p.prof[10], (unsigned long long)own_gap);
+      atomicAdd((unsigned long long *)&p.prof[11], (unsigned long long)own_gap_n);
     }
     __syncthreads();  // B1 of the exit command
   }

@@ -128,7 +128,7 @@ struct vc_snapshot {
   size_t rep_i32_stride = 0, rep_f64_stride = 0, rep_heap_stride = 0;
   uint4 *mbox = nullptr;
   long long *d_prof = nullptr;
-  long long h_prof[8] = {0};
+  long long h_prof[16] = {0};
   vc_decision *d_decisions = nullptr;
   vc_visit *d_visits = nullptr;
   int32_t *d_fit = nullptr, *d_counters = nullptr;
@@ -768,7 +768,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   }
   const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024;
   if (!s->mbox) CUDA_TRY(cudaMalloc(&s->mbox, mbox_bytes));
-  if (!s->d_prof) CUDA_TRY(cudaMalloc(&s->d_prof, 8 * sizeof(long long)));
+  if (!s->d_prof) CUDA_TRY(cudaMalloc(&s->d_prof, 16 * sizeof(long long)));
+  CUDA_TRY(cudaMemsetAsync(s->d_prof, 0, 16 * sizeof(long long), s->stream));
   const size_t ring_bytes = sizeof(uint4) * RING_STRIDE * RING_DEPTH;
   if (!s->ring) CUDA_TRY(cudaMalloc(&s->ring, ring_bytes));
   CUDA_TRY(cudaMemsetAsync(s->ring, 0, ring_bytes, s->stream));
@@ -842,7 +843,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   g_launches++;
   CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
   CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * 4, cudaMemcpyDeviceToHost, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->h_prof, s->d_prof, 8 * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->h_prof, s->d_prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   const double t_k = now_ms();
   const int n_dec = s->h_counters[0], n_vis = s->h_counters[1], n_fit = s->h_counters[2];
@@ -868,6 +869,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->stats.prof_cycles[6] = s->h_counters[5];  // full sweeps (fast kernel)
   r->stats.prof_cycles[7] = s->h_counters[6];  // incremental steps (fast kernel)
   r->stats.prof_cycles[5] = s->h_counters[7];  // owner changes between consecutive publications
+  if (getenv("VC_PROF_OWNER")) fprintf(stderr, "owner eval cycles/n = %.1f (n=%lld), same-owner publish->next-eval gap = %.1f (n=%lld)\n",
+      s->h_prof[9] ? (double)s->h_prof[8] / s->h_prof[9] : 0.0, s->h_prof[9], s->h_prof[11] ? (double)s->h_prof[10] / s->h_prof[11] : 0.0, s->h_prof[11]);
   *out = r;
   return VC_OK;
 }

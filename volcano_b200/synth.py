@@ -29,9 +29,13 @@ class SynthConfig:
     n_tasks: int
     n_queues: int = 1
     plugins: str = "gang+predicates+nodeorder+binpack"  # '+'-separated
-    utilisation: float = 0.6   # initial Used ~ U(0, utilisation) * Allocatable
+    utilisation: float = 0.6   # initial Used ~ U(min_util, utilisation) * Allocatable
+    min_util: float = 0.0
     n_classes: int = 64
     seed: int = DEFAULT_SEED
+    releasing_frac: float = 0.0  # fraction of nodes with Releasing resources (exercises the FutureIdle gradient)
+    soft_taint_p: float = 0.0    # per-bit probability of PreferNoSchedule taints (normalising TaintToleration scorer)
+    mixed_roles: bool = False    # two roles with different requests per job + TaskMinAvailable (role minima, error cache)
 
 
 CONFIGS = {
@@ -46,6 +50,15 @@ CONFIGS = {
     # small shapes for tests
     "tiny": SynthConfig("tiny", 64, 300, 3, "priority+gang+drf+predicates+proportion+nodeorder+binpack", n_classes=12),
     "small": SynthConfig("small", 700, 4000, 4, "priority+gang+drf+predicates+proportion+nodeorder+binpack", n_classes=24),
+    # general-kernel shapes: Releasing resources (pipelining) and PreferNoSchedule taints
+    "tiny_fut": SynthConfig("tiny_fut", 64, 300, 3, "priority+gang+drf+predicates+proportion+nodeorder+binpack", n_classes=12,
+                            utilisation=0.99, min_util=0.9, releasing_frac=0.6),
+    "small_soft": SynthConfig("small_soft", 300, 1500, 2, "priority+gang+predicates+nodeorder+binpack", n_classes=16,
+                              soft_taint_p=0.08),
+    "small_fut_soft": SynthConfig("small_fut_soft", 300, 1500, 4, "priority+gang+drf+predicates+proportion+nodeorder+binpack",
+                                  n_classes=16, utilisation=0.99, min_util=0.88, releasing_frac=0.5, soft_taint_p=0.08),
+    "small_roles": SynthConfig("small_roles", 200, 1200, 2, "priority+gang+predicates+nodeorder+binpack", n_classes=8,
+                               utilisation=0.85, mixed_roles=True),
 }
 
 
@@ -100,7 +113,7 @@ def make_snapshot(cfg: SynthConfig | str, seed: Optional[int] = None) -> Snapsho
     a[D_GPU] = gpus * 1000.0
     a[D_PODS] = maxpods
     a[D_RDMA] = np.where(gpus > 0, 4, 0) * 1000.0
-    u = rng.uniform(0, cfg.utilisation, size=(R, N))
+    u = rng.uniform(cfg.min_util, cfg.utilisation, size=(R, N))
     used = np.zeros((R, N))
     used[D_CPU] = np.floor(u[D_CPU] * cpu / 100.0) * 100.0
     used[D_MEM] = np.floor(u[D_MEM] * mem / (64 * MI)) * (64 * MI)
@@ -132,6 +145,22 @@ def make_snapshot(cfg: SynthConfig | str, seed: Optional[int] = None) -> Snapsho
     for b in range(32):
         tb |= rt[b].astype(np.uint64) << np.uint64(b)
     s.n_taint_hard[0] = tb
+    if cfg.soft_taint_p > 0:
+        sb = np.zeros(N, np.uint64)
+        rs_ = rng.random((8, N)) < cfg.soft_taint_p
+        for b in range(8):
+            sb |= rs_[b].astype(np.uint64) << np.uint64(b)
+        s.n_taint_soft[0] = sb
+    if cfg.releasing_frac > 0:
+        # some of the used resources are being released (terminating pods): Releasing <= Used
+        relmask = rng.random(N) < cfg.releasing_frac
+        frac = rng.uniform(0.2, 0.8, size=N) * relmask
+        rel = np.zeros((R, N))
+        rel[D_CPU] = np.floor(frac * used[D_CPU] / 100.0) * 100.0
+        rel[D_MEM] = np.floor(frac * used[D_MEM] / (64 * MI)) * (64 * MI)
+        rel[D_PODS] = np.floor(frac * used[D_PODS])
+        rel[D_GPU] = np.floor(frac * used[D_GPU] / 1000.0) * 1000.0
+        s.n_releasing[:] = rel
 
     # ---- classes: 25 % with a nodeSelector on <= 2 label bits, 10 % with tolerations -----------
     for c in range(C_):
@@ -144,6 +173,8 @@ def make_snapshot(cfg: SynthConfig | str, seed: Optional[int] = None) -> Snapsho
                 s.c_selector[c, 0] |= np.uint64(1) << np.uint64(b)
         if c > 0 and rng.random() < 0.10:
             s.c_tolerated_hard[c, 0] = np.uint64(rng.integers(0, 2**32))
+        if cfg.soft_taint_p > 0 and c > 0 and rng.random() < 0.3:
+            s.c_tolerated_soft[c, 0] = np.uint64(rng.integers(0, 256))
         if c > 0 and rng.random() < 0.15:
             s.c_n_preferred[c] = 1
             s.c_preferred[c, 0, 0] = np.uint64(1) << np.uint64(int(rng.integers(0, 16)))
@@ -188,6 +219,32 @@ def make_snapshot(cfg: SynthConfig | str, seed: Optional[int] = None) -> Snapsho
     s.j_role_off[:] = np.arange(J + 1)
     s.r_valid[:] = job_sizes_a
     s.r_flags[:] = 0  # named role "worker", not in TaskMinAvailable
+    if cfg.mixed_roles:
+        # two roles per job: role 0 = even pod index, role 1 = odd pod index with a different request type;
+        # jobs with >= 4 tasks declare TaskMinAvailable {role0: 1, role1: 1}
+        s2 = Snapshot(N, T, J, Q, C_, 2 * J, R, K=len(KDIMS), Wl=1, Wt=1, Z=0, pods_dim=D_PODS)
+        for k, v in s.__dict__.items():
+            if isinstance(v, np.ndarray) and not k.startswith("r_") and k != "j_role_off":
+                getattr(s2, k)[...] = v
+        s2.dim_names, s2.node_names, s2.queue_names = s.dim_names, s.node_names, s.queue_names
+        s = s2
+        odd = (s.t_pod_index % 2 == 1)
+        s.t_role[:] = 2 * job_of_task + odd.astype(np.int32)
+        alt = (tt + 1) % 4
+        for col, d in ((0, D_CPU), (1, D_MEM)):
+            s.t_resreq[d, odd] = types[alt[odd], col]
+        for k, col in enumerate((0, 1)):
+            s.t_k8s_req[k, odd] = types[alt[odd], col]
+            s.t_k8s_nonzero_req[k, odd] = types[alt[odd], col]
+        s.j_role_off[:] = 2 * np.arange(J + 1)
+        s.r_valid[0::2] = (job_sizes_a + 1) // 2
+        s.r_valid[1::2] = job_sizes_a // 2
+        big = job_sizes_a >= 4
+        s.r_min[0::2] = np.where(big, 1, 0)
+        s.r_min[1::2] = np.where(big, 1, 0)
+        s.r_flags[0::2] = np.where(big, abi.VC_ROLE_IN_MIN_MAP, 0)
+        s.r_flags[1::2] = np.where(big, abi.VC_ROLE_IN_MIN_MAP, 0)
+        s.j_task_min_total[:] = np.where(big, 2, 0)
     s.job_names = []
 
     # ---- queues ------------------------------------------------------------------------------
