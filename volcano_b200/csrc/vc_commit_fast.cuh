@@ -27,6 +27,7 @@
 #define CMD_SWEEP 1
 #define CMD_DISCARD 2
 #define CMD_EXIT 3
+#define CMD_EVAL 4
 #define VC_JOBX_PURE 0x100u  // host-computed: every named role of the job maps to a single group
 #define FAST_R 8
 
@@ -180,11 +181,26 @@ __device__ __forceinline__ Best scan_cache(const FastSmem &fs, int nmine, int nb
   return b;
 }
 // arg-max over the slot table (warp 0)
-__device__ __forceinline__ Best fold_slots(const FastSmem &fs, int G) {
+__device__ __forceinline__ Best fold_slots(const FastSmem &fs, int G, int *owner_out) {
   const int lane = threadIdx.x & 31;
   Best g{0.0, -1, 0};
-  for (int s = lane; s < G; s += 32) best_fold(g, fs.sl_score[s], fs.sl_node[s], fs.sl_cnt[s]);
-  best_warp_reduce(g);
+  int owner = -1;
+  for (int s = lane; s < G; s += 32) {
+    const int before = g.node;
+    best_fold(g, fs.sl_score[s], fs.sl_node[s], fs.sl_cnt[s]);
+    if (g.node != before) owner = s;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    double os = __shfl_xor_sync(0xffffffffu, g.score, o);
+    int on = __shfl_xor_sync(0xffffffffu, g.node, o);
+    int oc = __shfl_xor_sync(0xffffffffu, g.cnt, o);
+    int oo = __shfl_xor_sync(0xffffffffu, owner, o);
+    const int before = g.node;
+    best_fold(g, os, on, oc);
+    if (g.node != before) owner = oo;
+  }
+  *owner_out = owner;
   return g;
 }
 
@@ -206,6 +222,10 @@ struct CtlFast {  // shared-memory state of the fast kernel next to Ctl
   RoleDyn rd[VC_MAX_JOB_ROLES];
   double cta_best_score, g_best_score;
   int cta_best_node, cta_cnt, g_best_node, g_cnt;
+  // CMD_EVAL mailbox between warp 0 (control) and warp 1 (evaluator)
+  double ev_score;
+  int ev_i, ev_ring, ev_node, ev_cnt, cur_group;
+  unsigned ev_tag;
 };
 
 __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams fp) {
@@ -353,15 +373,203 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     }
   };
 
+  // ---- configuration hoisted out of the loops ----
+  bool f_qorder_prop = false, f_over_prop = false, f_alloc_prop = false, f_gang_ready = false;
+  int ord_n = 0, ord_kind[3] = {0, 0, 0};
+  for (int i = 0; i < c.n_plugins; ++i) {
+    const int pl = c.plugin[i];
+    const uint32_t en = c.enabled[i];
+    if ((en & VC_EN_QUEUE_ORDER) && pl == VC_PLUGIN_PROPORTION) f_qorder_prop = true;
+    if ((en & VC_EN_OVERUSED) && pl == VC_PLUGIN_PROPORTION) f_over_prop = true;
+    if ((en & VC_EN_ALLOCATABLE) && pl == VC_PLUGIN_PROPORTION) f_alloc_prop = true;
+    if ((en & VC_EN_JOB_READY) && pl == VC_PLUGIN_GANG) f_gang_ready = true;
+    if ((en & VC_EN_NODE_ORDER) && ord_n < 3 &&
+        ((pl == VC_PLUGIN_BINPACK && c.binpack_weight != 0) || pl == VC_PLUGIN_NODEORDER || pl == VC_PLUGIN_TDM))
+      ord_kind[ord_n++] = pl;
+  }
+  // ---- lane roles of the warp-cooperative single-node evaluation (see eval_dirty below) ----
+  enum { ROLE_NONE = 0, ROLE_BP = 1, ROLE_LEAST = 2, ROLE_MOST = 3, ROLE_BAL = 4 };
+  const int role = lane < 8 ? ROLE_BP : lane < 10 ? ROLE_LEAST : lane < 12 ? ROLE_MOST : lane < 16 ? ROLE_BAL : ROLE_NONE;
+  const int dk = role == ROLE_BP ? lane : role == ROLE_LEAST ? lane - 8 : role == ROLE_MOST ? lane - 10 : role == ROLE_BAL ? lane - 12 : 0;
+  const bool lane_valid = (role == ROLE_BP && dk < R) || role == ROLE_LEAST || role == ROLE_MOST || (role == ROLE_BAL && dk < K);
+  const int dk_c = lane_valid ? dk : 0;
+  const double *a_base = role == ROLE_BP ? fs.used + dk_c * cap : role == ROLE_BAL ? fs.kreq + dk_c * cap : fs.knz + dk_c * cap;
+  const double *al_base = role == ROLE_BP ? fs.alloc + dk_c * cap : fs.kalloc + dk_c * cap;
+  const double *idle_base = fs.idle + ((lane < 8 && lane < R) ? lane : 0) * cap;
+  const int w_d = (role == ROLE_BP && lane_valid) ? c.binpack_dim_weight[dk_c] : 0;
+  const double mul_const = role == ROLE_BP ? (double)w_d : (role == ROLE_LEAST || role == ROLE_MOST) ? 100.0 : 1.0;
+  // per-group lane operands (refreshed when the staged group record changes)
+  double b_val = 0.0, req_fit = 0.0;
+  bool fit_on = false, on_task = false;
+  uint32_t t_has = 0;
+
+  // Warp-cooperative evaluation of ONE node i of this CTA for the staged group: the same IEEE operations
+  // as eval_pair_fast / the generic functions, one division per lane instead of ~17 in a row:
+  //   lanes 0-7   fit of dim d against Idle + binpack term of dim d          (binpack.go:213-237)
+  //   lanes 8-9   leastRequestedScore of cpu / memory, lanes 10-11 mostRequestedScore
+  //   lanes 12-15 BalancedAllocation fraction of upstream dim k
+  // then one second-level division (binpack /weightSum, least, most, mean) and the std / sqrt.
+  auto eval_dirty = [&](int i, double *score_out) -> int {
+    const uint32_t cs = fs.c_cs[i];
+    const bool pod_cap = c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i];
+    const double a = a_base[i], alloc = al_base[i], idle = idle_base[i];
+    const bool bad_fit = fit_on && !le_eps(req_fit, idle);
+    const double s = a + b_val;
+    const bool scored = role == ROLE_BP ? (on_task && !(alloc == 0.0 || w_d == 0))
+                      : role == ROLE_BAL ? (on_task && alloc != 0.0)
+                      : (role != ROLE_NONE && alloc != 0.0);
+    const bool over = role == ROLE_BP && scored && s > alloc;
+    const bool zero_least = role == ROLE_LEAST && s > alloc;
+    const double x = role == ROLE_LEAST ? alloc - s : role == ROLE_MOST ? fmin(s, alloc) : s;
+    const double num = x * mul_const;
+    const double den = scored ? alloc : 1.0;
+    double q = num / den;
+    if (role == ROLE_LEAST || role == ROLE_MOST) {
+      double qq = trunc(q);
+      const double r = fma(-qq, den, num);
+      if (r < 0.0) qq -= 1.0;
+      else if (r >= den) qq += 1.0;
+      q = zero_least ? 0.0 : qq;
+    }
+    if (role == ROLE_BAL && q > 1.0) q = 1.0;
+    const double val = scored ? q : 0.0;
+    const unsigned m_bad = __ballot_sync(0xffffffffu, bad_fit);
+    const unsigned m_over = __ballot_sync(0xffffffffu, over);
+    const unsigned m_on = __ballot_sync(0xffffffffu, role == ROLE_BP ? on_task : scored);
+    const bool fit = (cs & CS_STATIC_OK) != 0 && !pod_cap && m_bad == 0;
+    double bp_sum = 0.0;
+    int wsum = 0;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      bp_sum += __shfl_sync(0xffffffffu, val, d);
+      wsum += ((m_on >> d) & 1u) ? c.binpack_dim_weight[d] : 0;
+    }
+    double ls = 0.0, ms = 0.0, wl = 0.0, wm = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double lv = __shfl_sync(0xffffffffu, val, 8 + k), mv = __shfl_sync(0xffffffffu, val, 10 + k);
+      if ((m_on >> (8 + k)) & 1u) { ls += lv * 50.0; wl += 50.0; }
+      if ((m_on >> (10 + k)) & 1u) { ms += mv * 1.0; wm += 1.0; }
+    }
+    double fr[4];
+    double total = 0.0;
+    const unsigned fonm = (m_on >> 12) & 0xfu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      fr[k] = __shfl_sync(0xffffffffu, val, 12 + k);
+      if ((fonm >> k) & 1u) total += fr[k];
+    }
+    const int nf = __popc(fonm);
+    // second-level divisions, one per lane
+    const double num2 = lane == 0 ? bp_sum : lane == 1 ? ls : lane == 2 ? ms : lane == 3 ? total : 0.0;
+    const double den2 = lane == 0 ? (wsum > 0 ? (double)wsum : 1.0) : lane == 1 ? (wl > 0.0 ? wl : 1.0)
+                      : lane == 2 ? (wm > 0.0 ? wm : 1.0) : lane == 3 ? (nf > 0 ? (double)nf : 1.0) : 1.0;
+    double q2 = num2 / den2;
+    if (lane == 1 || lane == 2) {
+      double qq = trunc(q2);
+      const double r = fma(-qq, den2, num2);
+      if (r < 0.0) qq -= 1.0;
+      else if (r >= den2) qq += 1.0;
+      q2 = qq;
+    }
+    double bp = __shfl_sync(0xffffffffu, q2, 0);
+    if (!(wsum > 0)) bp = bp_sum;
+    bp *= (double)(VC_MAX_NODE_SCORE * c.binpack_weight);
+    if (m_over & 0xffu) bp = 0.0;
+    const double least = wl > 0.0 ? __shfl_sync(0xffffffffu, q2, 1) : 0.0;
+    const double most = wm > 0.0 ? __shfl_sync(0xffffffffu, q2, 2) : 0.0;
+    const double mean = __shfl_sync(0xffffffffu, q2, 3);
+    double stdv = 0.0;
+    if (nf == 2) {
+      double f0 = 0.0, f1 = 0.0;
+      int seen = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if ((fonm >> k) & 1u) { if (seen == 0) f0 = fr[k]; else f1 = fr[k]; ++seen; }
+      stdv = fabs((f0 - f1) / 2.0);
+    } else if (nf > 2) {
+      double sum = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if ((fonm >> k) & 1u) sum = sum + (fr[k] - mean) * (fr[k] - mean);
+      stdv = sqrt(sum / (double)nf);
+    }
+    const double bal = (double)__double2ll_rz((1.0 - stdv) * (double)VC_MAX_NODE_SCORE);
+    double no = 0.0;
+    if (c.w_least != 0) no += least * (double)c.w_least;
+    if (c.w_most != 0) no += most * (double)c.w_most;
+    if (c.w_balanced != 0) no += bal * (double)c.w_balanced;
+    if (c.w_node_affinity != 0) no += (double)(cs >> CS_NAFF_SHIFT) * (double)c.w_node_affinity;
+    double order = 0.0;
+    bool has_order = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k >= ord_n) break;
+      if (ord_kind[k] == VC_PLUGIN_BINPACK) order += bp;
+      else if (ord_kind[k] == VC_PLUGIN_NODEORDER) order += no;
+      else if (has_order) {
+        if (cs & CS_TDM_ORDER_ERR) has_order = false;
+        else order += (cs & CS_TDM_ORDER_MAX) ? (double)VC_MAX_NODE_SCORE : 0.0;
+      }
+    }
+    *score_out = total_score(c, has_order, has_order ? order : 0.0, 0, 0);
+    return fit ? 0 : 2;
+  };
+
+  // per-lane operands of eval_dirty for the group record staged in S.trec
+  auto stage_ops = [&]() {
+    t_has = S.trec.has;
+    req_fit = lane < 8 && lane < R ? S.trec.req[lane] : 0.0;
+    fit_on = lane < R && lane < 8 && (lane < 2 || (t_has & (1u << lane)));
+    b_val = !lane_valid ? 0.0 : role == ROLE_BP ? S.trec.req[dk_c] : role == ROLE_BAL ? S.trec.kreq[dk_c] : S.trec.knz[dk_c];
+    on_task = role == ROLE_BP ? (lane_valid && (dk_c < 2 || (t_has & (1u << dk_c))) && b_val >= VC_MIN_RESOURCE && w_d >= 0)
+            : role == ROLE_BAL ? (lane_valid && !(dk_c >= 2 && b_val == 0.0))
+            : (role != ROLE_NONE);
+  };
+  // CMD_EVAL (warp 1): re-evaluate node F.ev_i for the cached group, maintain this CTA's best incrementally
+  // (rescan only when the holder got worse) and publish the CTA's new best in the ring.
+  auto eval_and_publish = [&]() {
+    const int i = F.ev_i;
+    const int dn = nbase + i;
+    const int old_cat = fs.c_cat[i];
+    double sc = 0.0;
+    const int cat = eval_dirty(i, &sc);
+    __syncwarp();
+    if (lane == 0) { fs.c_cat[i] = cat; fs.c_score[i] = sc; }
+    double bs = F.cta_best_score;
+    int bn = F.cta_best_node;
+    int cnt = F.cta_cnt + (cat == 0 ? 1 : 0) - (old_cat == 0 ? 1 : 0);
+    bool rescan = false;
+    if (bn == dn) {
+      if (cat == 0 && sc >= bs) bs = sc;
+      else rescan = true;
+    } else if (cat == 0 && (bn < 0 || better(sc, dn, bs, bn))) {
+      bs = sc; bn = dn;
+    }
+    __syncwarp();
+    if (rescan) { Best r = scan_cache(fs, nmine, nbase); bs = r.score; bn = r.node; cnt = r.cnt; }
+    if (lane == 0) {
+      F.cta_best_score = bs; F.cta_best_node = bn; F.cta_cnt = cnt;
+      Best nb{bs, bn, cnt};
+      mbox_store(p.ring + (size_t)F.ev_ring * RING_STRIDE, pack_best(nb, F.ev_tag));
+      F.ev_score = bs; F.ev_node = bn; F.ev_cnt = min(cnt, 2);
+    }
+  };
+
   if (warp != 0) {
     // ---- worker warps: serve block-wide commands ----
+    int my_group = -1;
     for (;;) {
       __syncthreads();  // B1: command posted
       const int cmd = S.cmd;
       if (cmd == CMD_EXIT) break;
       if (cmd == CMD_SWEEP) sweep_part();
       else if (cmd == CMD_DISCARD) discard_part();
-      __syncthreads();  // B2: command done
+      else if (cmd == CMD_EVAL && warp == 1) {
+        if (F.cur_group != my_group) { stage_ops(); my_group = F.cur_group; }
+        eval_and_publish();
+      }
+      __syncthreads();  // B2: command done (for CMD_EVAL warp 0 arrives late: that is the join)
     }
   } else {
     // ===================================================================================
@@ -371,156 +579,15 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     // warps read. Per-dimension vectors (drf / proportion accumulators) live one dimension per lane.
     // ===================================================================================
     const bool out_cta = (cta == 0);
-    // ---- configuration hoisted out of the loops ----
-    bool f_qorder_prop = false, f_over_prop = false, f_alloc_prop = false, f_gang_ready = false;
-    int ord_n = 0, ord_kind[3] = {0, 0, 0};
-    for (int i = 0; i < c.n_plugins; ++i) {
-      const int pl = c.plugin[i];
-      const uint32_t en = c.enabled[i];
-      if ((en & VC_EN_QUEUE_ORDER) && pl == VC_PLUGIN_PROPORTION) f_qorder_prop = true;
-      if ((en & VC_EN_OVERUSED) && pl == VC_PLUGIN_PROPORTION) f_over_prop = true;
-      if ((en & VC_EN_ALLOCATABLE) && pl == VC_PLUGIN_PROPORTION) f_alloc_prop = true;
-      if ((en & VC_EN_JOB_READY) && pl == VC_PLUGIN_GANG) f_gang_ready = true;
-      if ((en & VC_EN_NODE_ORDER) && ord_n < 3 &&
-          ((pl == VC_PLUGIN_BINPACK && c.binpack_weight != 0) || pl == VC_PLUGIN_NODEORDER || pl == VC_PLUGIN_TDM))
-        ord_kind[ord_n++] = pl;
-    }
-    // ---- lane roles of the warp-cooperative single-node evaluation (see eval_dirty below) ----
-    enum { ROLE_NONE = 0, ROLE_BP = 1, ROLE_LEAST = 2, ROLE_MOST = 3, ROLE_BAL = 4 };
-    const int role = lane < 8 ? ROLE_BP : lane < 10 ? ROLE_LEAST : lane < 12 ? ROLE_MOST : lane < 16 ? ROLE_BAL : ROLE_NONE;
-    const int dk = role == ROLE_BP ? lane : role == ROLE_LEAST ? lane - 8 : role == ROLE_MOST ? lane - 10 : role == ROLE_BAL ? lane - 12 : 0;
-    const bool lane_valid = (role == ROLE_BP && dk < R) || role == ROLE_LEAST || role == ROLE_MOST || (role == ROLE_BAL && dk < K);
-    const int dk_c = lane_valid ? dk : 0;
-    const double *a_base = role == ROLE_BP ? fs.used + dk_c * cap : role == ROLE_BAL ? fs.kreq + dk_c * cap : fs.knz + dk_c * cap;
-    const double *al_base = role == ROLE_BP ? fs.alloc + dk_c * cap : fs.kalloc + dk_c * cap;
-    const double *idle_base = fs.idle + ((lane < 8 && lane < R) ? lane : 0) * cap;
-    const int w_d = (role == ROLE_BP && lane_valid) ? c.binpack_dim_weight[dk_c] : 0;
-    const double mul_const = role == ROLE_BP ? (double)w_d : (role == ROLE_LEAST || role == ROLE_MOST) ? 100.0 : 1.0;
-    // per-group lane operands (refreshed when the staged group record changes)
-    double b_val = 0.0, req_fit = 0.0;
-    bool fit_on = false, on_task = false;
-    uint32_t t_has = 0;
-
     // ---- register copies of the control state ----
-    int cur_group = -1, cache_group = -1, dirty_node = -1, since_sync = 0;
+    int cur_group = -1, cache_group = -1, since_sync = 0;
     unsigned ag = 0, pc = 0;
-    long long own_eval = 0, own_gap = 0, own_last = 0; int own_n = 0, own_gap_n = 0;
     int n_dec = 0, n_vis = 0, n_fit = 0, n_steps = 0, n_full = 0, n_incr = 0, visit_id = 0, n_owner_change = 0, last_owner = -1;
-    double cta_best_score = 0.0, g_best_score = 0.0;
-    int cta_best_node = -1, cta_cnt = 0, g_best_node = -1, g_cnt = 0;
-
-    // Warp-cooperative evaluation of ONE node i of this CTA for the staged group: the same IEEE operations
-    // as eval_pair_fast / the generic functions, one division per lane instead of ~17 in a row:
-    //   lanes 0-7   fit of dim d against Idle + binpack term of dim d          (binpack.go:213-237)
-    //   lanes 8-9   leastRequestedScore of cpu / memory, lanes 10-11 mostRequestedScore
-    //   lanes 12-15 BalancedAllocation fraction of upstream dim k
-    // then one second-level division (binpack /weightSum, least, most, mean) and the std / sqrt.
-    auto eval_dirty = [&](int i, double *score_out) -> int {
-      const uint32_t cs = fs.c_cs[i];
-      const bool pod_cap = c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i];
-      const double a = a_base[i], alloc = al_base[i], idle = idle_base[i];
-      const bool bad_fit = fit_on && !le_eps(req_fit, idle);
-      const double s = a + b_val;
-      const bool scored = role == ROLE_BP ? (on_task && !(alloc == 0.0 || w_d == 0))
-                        : role == ROLE_BAL ? (on_task && alloc != 0.0)
-                        : (role != ROLE_NONE && alloc != 0.0);
-      const bool over = role == ROLE_BP && scored && s > alloc;
-      const bool zero_least = role == ROLE_LEAST && s > alloc;
-      const double x = role == ROLE_LEAST ? alloc - s : role == ROLE_MOST ? fmin(s, alloc) : s;
-      const double num = x * mul_const;
-      const double den = scored ? alloc : 1.0;
-      double q = num / den;
-      if (role == ROLE_LEAST || role == ROLE_MOST) {
-        double qq = trunc(q);
-        const double r = fma(-qq, den, num);
-        if (r < 0.0) qq -= 1.0;
-        else if (r >= den) qq += 1.0;
-        q = zero_least ? 0.0 : qq;
-      }
-      if (role == ROLE_BAL && q > 1.0) q = 1.0;
-      const double val = scored ? q : 0.0;
-      const unsigned m_bad = __ballot_sync(0xffffffffu, bad_fit);
-      const unsigned m_over = __ballot_sync(0xffffffffu, over);
-      const unsigned m_on = __ballot_sync(0xffffffffu, role == ROLE_BP ? on_task : scored);
-      const bool fit = (cs & CS_STATIC_OK) != 0 && !pod_cap && m_bad == 0;
-      double bp_sum = 0.0;
-      int wsum = 0;
-#pragma unroll
-      for (int d = 0; d < 8; ++d) {
-        bp_sum += __shfl_sync(0xffffffffu, val, d);
-        wsum += ((m_on >> d) & 1u) ? c.binpack_dim_weight[d] : 0;
-      }
-      double ls = 0.0, ms = 0.0, wl = 0.0, wm = 0.0;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const double lv = __shfl_sync(0xffffffffu, val, 8 + k), mv = __shfl_sync(0xffffffffu, val, 10 + k);
-        if ((m_on >> (8 + k)) & 1u) { ls += lv * 50.0; wl += 50.0; }
-        if ((m_on >> (10 + k)) & 1u) { ms += mv * 1.0; wm += 1.0; }
-      }
-      double fr[4];
-      double total = 0.0;
-      const unsigned fonm = (m_on >> 12) & 0xfu;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        fr[k] = __shfl_sync(0xffffffffu, val, 12 + k);
-        if ((fonm >> k) & 1u) total += fr[k];
-      }
-      const int nf = __popc(fonm);
-      // second-level divisions, one per lane
-      const double num2 = lane == 0 ? bp_sum : lane == 1 ? ls : lane == 2 ? ms : lane == 3 ? total : 0.0;
-      const double den2 = lane == 0 ? (wsum > 0 ? (double)wsum : 1.0) : lane == 1 ? (wl > 0.0 ? wl : 1.0)
-                        : lane == 2 ? (wm > 0.0 ? wm : 1.0) : lane == 3 ? (nf > 0 ? (double)nf : 1.0) : 1.0;
-      double q2 = num2 / den2;
-      if (lane == 1 || lane == 2) {
-        double qq = trunc(q2);
-        const double r = fma(-qq, den2, num2);
-        if (r < 0.0) qq -= 1.0;
-        else if (r >= den2) qq += 1.0;
-        q2 = qq;
-      }
-      double bp = __shfl_sync(0xffffffffu, q2, 0);
-      if (!(wsum > 0)) bp = bp_sum;
-      bp *= (double)(VC_MAX_NODE_SCORE * c.binpack_weight);
-      if (m_over & 0xffu) bp = 0.0;
-      const double least = wl > 0.0 ? __shfl_sync(0xffffffffu, q2, 1) : 0.0;
-      const double most = wm > 0.0 ? __shfl_sync(0xffffffffu, q2, 2) : 0.0;
-      const double mean = __shfl_sync(0xffffffffu, q2, 3);
-      double stdv = 0.0;
-      if (nf == 2) {
-        double f0 = 0.0, f1 = 0.0;
-        int seen = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if ((fonm >> k) & 1u) { if (seen == 0) f0 = fr[k]; else f1 = fr[k]; ++seen; }
-        stdv = fabs((f0 - f1) / 2.0);
-      } else if (nf > 2) {
-        double sum = 0.0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if ((fonm >> k) & 1u) sum = sum + (fr[k] - mean) * (fr[k] - mean);
-        stdv = sqrt(sum / (double)nf);
-      }
-      const double bal = (double)__double2ll_rz((1.0 - stdv) * (double)VC_MAX_NODE_SCORE);
-      double no = 0.0;
-      if (c.w_least != 0) no += least * (double)c.w_least;
-      if (c.w_most != 0) no += most * (double)c.w_most;
-      if (c.w_balanced != 0) no += bal * (double)c.w_balanced;
-      if (c.w_node_affinity != 0) no += (double)(cs >> CS_NAFF_SHIFT) * (double)c.w_node_affinity;
-      double order = 0.0;
-      bool has_order = true;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (k >= ord_n) break;
-        if (ord_kind[k] == VC_PLUGIN_BINPACK) order += bp;
-        else if (ord_kind[k] == VC_PLUGIN_NODEORDER) order += no;
-        else if (has_order) {
-          if (cs & CS_TDM_ORDER_ERR) has_order = false;
-          else order += (cs & CS_TDM_ORDER_MAX) ? (double)VC_MAX_NODE_SCORE : 0.0;
-        }
-      }
-      *score_out = total_score(c, has_order, has_order ? order : 0.0, 0, 0);
-      return fit ? 0 : 2;
-    };
+    double g_best_score = 0.0;
+    int g_best_node = -1, g_cnt = 0, g_best_owner = -1;
+    bool pub_pending = false;
+    int pub_owner = -1, pub_node = -1;
+    unsigned pub_pc = 0;
 
     for (;;) {
       // ---- queues.Pop(): arg-min by ssn.QueueOrderFn over the active queues ----
@@ -670,6 +737,47 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         return ready + pbe >= minav;
       };
       PROF_MARK(0);
+      // Consume the publication of the last placement (made while the verdict cache was valid): the owner CTA
+      // joins its evaluator warp (B2 of CMD_EVAL), every other CTA reads the one ring record; then the global
+      // best is maintained incrementally (refolded only when its holder got worse).
+      auto resolve = [&]() {
+        if (!pub_pending) return;
+        pub_pending = false;
+        const int o = pub_owner;
+        if (o != last_owner) { n_owner_change += 1; last_owner = o; }
+        Best nb;
+        if (o == cta) {
+          __syncthreads();  // B2 of CMD_EVAL
+          nb.score = F.ev_score; nb.node = F.ev_node; nb.cnt = F.ev_cnt;
+        } else {
+          const unsigned tag = (pub_pc + 1u) & 0x3fffffffu;
+          const uint4 *ent = p.ring + (size_t)(pub_pc % RING_DEPTH) * RING_STRIDE;
+          uint4 v;
+          do { v = mbox_load(ent); } while ((v.w >> 2) != tag);
+          nb = unpack_best(v);
+        }
+        const int old_cnt = fs.sl_cnt[o];
+        g_cnt += nb.cnt - old_cnt;
+        bool refold = false;
+        if (g_best_owner == o) {
+          if (nb.node >= 0 && (better(nb.score, nb.node, g_best_score, g_best_node) ||
+                               (nb.node == g_best_node && nb.score == g_best_score))) {
+            g_best_score = nb.score; g_best_node = nb.node;
+          } else {
+            refold = true;
+          }
+        } else if (nb.node >= 0 && (g_best_node < 0 || better(nb.score, nb.node, g_best_score, g_best_node))) {
+          g_best_score = nb.score; g_best_node = nb.node; g_best_owner = o;
+        }
+        __syncwarp();
+        if (lane == 0) { fs.sl_score[o] = nb.score; fs.sl_node[o] = nb.node; fs.sl_cnt[o] = nb.cnt; }
+        since_sync += 1;
+        if (refold) {
+          __syncwarp();
+          Best g = fold_slots(fs, G, &g_best_owner);
+          g_best_score = g.score; g_best_node = g.node; g_cnt = g.cnt;
+        }
+      };
 
       // ---- allocateResourcesForTasks, allocate.go:558-694 ----
       for (;;) {
@@ -678,6 +786,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         const int t = meta.x, grp = meta.y, rl = meta.z - role_base;
         cursor += 1;
         if (cursor < task_end) meta = __ldg(&p.tmeta[cursor]);  // prefetch the next task's record
+        resolve();
         if (grp != cur_group) {  // stage the group's request record (shared: workers read it in sweeps)
           __syncwarp();
           if (lane < R) S.trec.req[lane] = __ldg(&p.g_req[(size_t)lane * p.n_groups + grp]);
@@ -686,13 +795,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           if (lane == 31) { S.trec.has = __ldg(&p.g_has[grp]); S.trec.klass = __ldg(&p.g_class[grp]); }
           __syncwarp();
           cur_group = grp;
-          t_has = S.trec.has;
-          req_fit = lane < 8 && lane < R ? S.trec.req[lane] : 0.0;
-          fit_on = lane < R && lane < 8 && (lane < 2 || (t_has & (1u << lane)));
-          b_val = !lane_valid ? 0.0 : role == ROLE_BP ? S.trec.req[dk_c] : role == ROLE_BAL ? S.trec.kreq[dk_c] : S.trec.knz[dk_c];
-          on_task = role == ROLE_BP ? (lane_valid && (dk_c < 2 || (t_has & (1u << dk_c))) && b_val >= VC_MIN_RESOURCE && w_d >= 0)
-                  : role == ROLE_BAL ? (lane_valid && !(dk_c >= 2 && b_val == 0.0))
-                  : (role != ROLE_NONE);
+          if (lane == 0) F.cur_group = grp;
+          stage_ops();
         }
         const double req_l = lane < R ? S.trec.req[lane] : 0.0;  // request, one dimension per lane
         // ---- ssn.Allocatable -> proportion queueAllocatable (proportion.go:333-348) ----
@@ -725,74 +829,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         PROF_MARK(1);
 
         if (pure && grp == cache_group) {
-          // -------- incremental step --------
-          if (dirty_node >= 0) {
-            const int dn = dirty_node;
-            const int o = (dn - p.d.node_begin) / p.npc;
-            if (o != last_owner) { n_owner_change += 1; last_owner = o; }
-            const unsigned tag = (pc + 1u) & 0x3fffffffu;
-            uint4 *ent = p.ring + (size_t)(pc % RING_DEPTH) * RING_STRIDE;
-            Best nb;
-            if (o == cta) {
-              const int i = dn - nbase;
-              const int old_cat = fs.c_cat[i];
-              double sc = 0.0;
-              const long long t_e0 = clock64();
-              if (own_last != 0) { own_gap += t_e0 - own_last; own_gap_n += 1; }
-              const int cat = eval_dirty(i, &sc);
-              own_eval += clock64() - t_e0; own_n += 1;
-              if (lane == 0) { fs.c_cat[i] = cat; fs.c_score[i] = sc; }
-              // CTA best, incrementally: rescan only when the holder got worse
-              int cnt = cta_cnt + (cat == 0 ? 1 : 0) - (old_cat == 0 ? 1 : 0);
-              bool rescan = false;
-              if (cta_best_node == dn) {
-                if (cat == 0 && sc >= cta_best_score) cta_best_score = sc;
-                else rescan = true;
-              } else if (cat == 0 && (cta_best_node < 0 || better(sc, dn, cta_best_score, cta_best_node))) {
-                cta_best_score = sc; cta_best_node = dn;
-              }
-              if (rescan) {
-                __syncwarp();
-                Best r = scan_cache(fs, nmine, nbase);
-                cta_best_score = r.score; cta_best_node = r.node; cnt = r.cnt;
-              }
-              cta_cnt = cnt;
-              nb.score = cta_best_score; nb.node = cta_best_node; nb.cnt = cnt;
-              if (lane == 0) mbox_store(ent, pack_best(nb, tag));
-              nb.cnt = min(cnt, 2);
-              own_last = clock64();
-            } else {
-              own_last = 0;
-              uint4 v;
-              do { v = mbox_load(ent); } while ((v.w >> 2) != tag);
-              nb = unpack_best(v);
-            }
-            // global best, incrementally
-            const int old_cnt = fs.sl_cnt[o];
-            g_cnt += nb.cnt - old_cnt;
-            bool refold = false;
-            const int g_owner = g_best_node >= 0 ? (g_best_node - p.d.node_begin) / p.npc : -1;
-            if (g_owner == o) {
-              if (nb.node >= 0 && (better(nb.score, nb.node, g_best_score, g_best_node) ||
-                                   (nb.node == g_best_node && nb.score == g_best_score))) {
-                g_best_score = nb.score; g_best_node = nb.node;
-              } else {
-                refold = true;
-              }
-            } else if (nb.node >= 0 && (g_best_node < 0 || better(nb.score, nb.node, g_best_score, g_best_node))) {
-              g_best_score = nb.score; g_best_node = nb.node;
-            }
-            __syncwarp();
-            if (lane == 0) { fs.sl_score[o] = nb.score; fs.sl_node[o] = nb.node; fs.sl_cnt[o] = nb.cnt; }
-            pc += 1; since_sync += 1; dirty_node = -1;
-            if (refold) {
-              __syncwarp();
-              Best g = fold_slots(fs, G);
-              g_best_score = g.score; g_best_node = g.node; g_cnt = g.cnt;
-            }
-          }
+          // -------- incremental step: verdict cache, slot table and global best are already current --------
           if (since_sync >= RING_DEPTH / 2) {  // keep the publication ring from being overrun
-            Best mine{cta_best_score, cta_best_node, cta_cnt};
+            Best mine{F.cta_best_score, F.cta_best_node, F.cta_cnt};
             __syncwarp();
             exchange_all_fast(p, mine, ag, fs);
             ag += 1; since_sync = 0;
@@ -810,10 +849,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           if (lane < nwarps) best_fold(mine, S.w_score[0][lane], S.w_node[0][lane], S.w_cnt[0][lane]);
           best_warp_reduce(mine);
           exchange_all_fast(p, mine, ag, fs);
-          Best g = fold_slots(fs, G);
-          ag += 1; since_sync = 0; dirty_node = -1; n_full += 1;
+          Best g = fold_slots(fs, G, &g_best_owner);
+          ag += 1; since_sync = 0; n_full += 1;
           cache_group = pure ? grp : -1;  // verdicts taken under an error cache are not reusable
-          cta_best_score = mine.score; cta_best_node = mine.node; cta_cnt = mine.cnt;
+          if (lane == 0) { F.cta_best_score = mine.score; F.cta_best_node = mine.node; F.cta_cnt = mine.cnt; }
           g_best_score = g.score; g_best_node = g.node; g_cnt = g.cnt;
         }
         n_steps += 1;
@@ -858,7 +897,20 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             if (lane >= 24 && lane < 26) fs.knz[(lane - 24) * cap + i] += S.trec.knz[lane - 24];
           }
         }
-        dirty_node = best;
+        // every placement made while the verdict cache is valid is followed by exactly one publication of the
+        // owner CTA's new best; the owner's evaluator warp starts on it now, overlapping the bookkeeping below
+        pub_pending = pure && cache_group == grp;
+        if (pub_pending) {
+          pub_owner = g_best_owner; pub_node = best; pub_pc = pc; pc += 1;
+          if (pub_owner == cta) {
+            __syncwarp();
+            if (lane == 0) {
+              F.ev_i = best - nbase; F.ev_ring = (int)(pub_pc % RING_DEPTH); F.ev_tag = (pub_pc + 1u) & 0x3fffffffu;
+              S.cmd = CMD_EVAL;
+            }
+            __syncthreads();  // B1 of CMD_EVAL
+          }
+        }
         // job.UpdateTaskStatus + event handlers: drf (drf.go:391-418), proportion (proportion.go:475-497)
         ready += 1;
         if (lane == 0) {
@@ -891,6 +943,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         if (job_ready_now()) break;  // ssn.SubJobReady, allocate.go:676-678
       }
       PROF_MARK(4);
+      resolve();
 
       // ---- statement outcome, allocate.go:681-693 and :330-337 ----
       __syncwarp();
@@ -936,7 +989,6 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           qshare = sh;
         }
         cache_group = -1;  // several nodes changed at once: drop the verdict cache
-        dirty_node = -1;
         __syncwarp();
       }
       // results (CTA 0): decisions copied lane-parallel
@@ -1002,10 +1054,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       S.cmd = CMD_EXIT;
       S.n_dec = n_dec; S.n_vis = n_vis; S.n_fit = n_fit; S.n_steps = n_steps; S.n_full = n_full; S.n_incr = n_incr;
       S.pick2 = n_owner_change;
-      atomicAdd((unsigned long long *)&p.prof[8], (unsigned long long)own_eval);
-      atomicAdd((unsigned long long *)&p.prof[9], (unsigned long long)own_n);
-      atomicAdd((unsigned long long *)&p.prof[10], (unsigned long long)own_gap);
-      atomicAdd((unsigned long long *)&p.prof[11], (unsigned long long)own_gap_n);
+
     }
     __syncthreads();  // B1 of the exit command
   }
