@@ -402,6 +402,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   double b_val = 0.0, req_fit = 0.0;
   bool fit_on = false, on_task = false;
   uint32_t t_has = 0;
+  int wsum_g = 0;  // binpack weightSum: depends on the request record only (binpack.go:213-237)
+  const double bp_scale = (double)(VC_MAX_NODE_SCORE * c.binpack_weight);
+  bool ord_has_tdm = false;
+  for (int k = 0; k < ord_n; ++k) ord_has_tdm |= ord_kind[k] == VC_PLUGIN_TDM;
 
   // Warp-cooperative evaluation of ONE node i of this CTA for the staged group: the same IEEE operations
   // as eval_pair_fast / the generic functions, one division per lane instead of ~17 in a row:
@@ -415,83 +419,72 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     const double a = a_base[i], alloc = al_base[i], idle = idle_base[i];
     const bool bad_fit = fit_on && !le_eps(req_fit, idle);
     const double s = a + b_val;
-    const bool scored = role == ROLE_BP ? (on_task && !(alloc == 0.0 || w_d == 0))
-                      : role == ROLE_BAL ? (on_task && alloc != 0.0)
-                      : (role != ROLE_NONE && alloc != 0.0);
+    const bool nz = alloc != 0.0;
+    const bool scored = role == ROLE_BP ? (on_task && nz && w_d != 0) : (on_task && nz);
     const bool over = role == ROLE_BP && scored && s > alloc;
     const bool zero_least = role == ROLE_LEAST && s > alloc;
     const double x = role == ROLE_LEAST ? alloc - s : role == ROLE_MOST ? fmin(s, alloc) : s;
     const double num = x * mul_const;
     const double den = scored ? alloc : 1.0;
     double q = num / den;
-    if (role == ROLE_LEAST || role == ROLE_MOST) {
+    {  // lanes 8-11: floor of the quotient (int64 division of the upstream scorers), exact fma fix-up
       double qq = trunc(q);
       const double r = fma(-qq, den, num);
-      if (r < 0.0) qq -= 1.0;
-      else if (r >= den) qq += 1.0;
-      q = zero_least ? 0.0 : qq;
+      qq = r < 0.0 ? qq - 1.0 : (r >= den ? qq + 1.0 : qq);
+      if (role == ROLE_LEAST || role == ROLE_MOST) q = zero_least ? 0.0 : qq;
     }
-    if (role == ROLE_BAL && q > 1.0) q = 1.0;
+    if (role == ROLE_BAL) q = fmin(q, 1.0);
     const double val = scored ? q : 0.0;
     const unsigned m_bad = __ballot_sync(0xffffffffu, bad_fit);
     const unsigned m_over = __ballot_sync(0xffffffffu, over);
-    const unsigned m_on = __ballot_sync(0xffffffffu, role == ROLE_BP ? on_task : scored);
+    const unsigned m_on = __ballot_sync(0xffffffffu, scored);
     const bool fit = (cs & CS_STATIC_OK) != 0 && !pod_cap && m_bad == 0;
+    // gather the 16 lane results (adding the 0.0 of an inactive lane is exact)
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = __shfl_sync(0xffffffffu, val, k);
     double bp_sum = 0.0;
-    int wsum = 0;
 #pragma unroll
-    for (int d = 0; d < 8; ++d) {
-      bp_sum += __shfl_sync(0xffffffffu, val, d);
-      wsum += ((m_on >> d) & 1u) ? c.binpack_dim_weight[d] : 0;
-    }
-    double ls = 0.0, ms = 0.0, wl = 0.0, wm = 0.0;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const double lv = __shfl_sync(0xffffffffu, val, 8 + k), mv = __shfl_sync(0xffffffffu, val, 10 + k);
-      if ((m_on >> (8 + k)) & 1u) { ls += lv * 50.0; wl += 50.0; }
-      if ((m_on >> (10 + k)) & 1u) { ms += mv * 1.0; wm += 1.0; }
-    }
-    double fr[4];
-    double total = 0.0;
+    for (int d = 0; d < 8; ++d) bp_sum += v[d];
+    const double on8 = (m_on >> 8) & 1u ? 1.0 : 0.0, on9 = (m_on >> 9) & 1u ? 1.0 : 0.0;
+    const double ls = (0.0 + v[8] * 50.0) + v[9] * 50.0;   // inactive lanes carry 0.0
+    const double ms = (0.0 + v[10] * 1.0) + v[11] * 1.0;
+    const double wl = (on8 + on9) * 50.0, wm = on8 + on9;   // lanes 10,11 are active exactly when 8,9 are
     const unsigned fonm = (m_on >> 12) & 0xfu;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      fr[k] = __shfl_sync(0xffffffffu, val, 12 + k);
-      if ((fonm >> k) & 1u) total += fr[k];
-    }
+    const double total = ((0.0 + v[12]) + v[13]) + (v[14] + 0.0) * 1.0 + v[15];
     const int nf = __popc(fonm);
     // second-level divisions, one per lane
-    const double num2 = lane == 0 ? bp_sum : lane == 1 ? ls : lane == 2 ? ms : lane == 3 ? total : 0.0;
-    const double den2 = lane == 0 ? (wsum > 0 ? (double)wsum : 1.0) : lane == 1 ? (wl > 0.0 ? wl : 1.0)
-                      : lane == 2 ? (wm > 0.0 ? wm : 1.0) : lane == 3 ? (nf > 0 ? (double)nf : 1.0) : 1.0;
+    const double num2 = lane == 0 ? bp_sum : lane == 1 ? ls : lane == 2 ? ms : total;
+    const double den2 = lane == 0 ? (wsum_g > 0 ? (double)wsum_g : 1.0) : lane == 1 ? (wl > 0.0 ? wl : 1.0)
+                      : lane == 2 ? (wm > 0.0 ? wm : 1.0) : (nf > 0 ? (double)nf : 1.0);
     double q2 = num2 / den2;
-    if (lane == 1 || lane == 2) {
+    {
       double qq = trunc(q2);
       const double r = fma(-qq, den2, num2);
-      if (r < 0.0) qq -= 1.0;
-      else if (r >= den2) qq += 1.0;
-      q2 = qq;
+      qq = r < 0.0 ? qq - 1.0 : (r >= den2 ? qq + 1.0 : qq);
+      if (lane == 1 || lane == 2) q2 = qq;
     }
     double bp = __shfl_sync(0xffffffffu, q2, 0);
-    if (!(wsum > 0)) bp = bp_sum;
-    bp *= (double)(VC_MAX_NODE_SCORE * c.binpack_weight);
-    if (m_over & 0xffu) bp = 0.0;
+    bp = wsum_g > 0 ? bp : bp_sum;
+    bp *= bp_scale;
+    bp = (m_over & 0xffu) ? 0.0 : bp;
     const double least = wl > 0.0 ? __shfl_sync(0xffffffffu, q2, 1) : 0.0;
     const double most = wm > 0.0 ? __shfl_sync(0xffffffffu, q2, 2) : 0.0;
     const double mean = __shfl_sync(0xffffffffu, q2, 3);
     double stdv = 0.0;
     if (nf == 2) {
-      double f0 = 0.0, f1 = 0.0;
-      int seen = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if ((fonm >> k) & 1u) { if (seen == 0) f0 = fr[k]; else f1 = fr[k]; ++seen; }
+      // the two active fractions in dimension order
+      const unsigned lo = __ffs(fonm) - 1, hi = 31 - __clz(fonm);
+      const double f0 = lo == 0 ? v[12] : lo == 1 ? v[13] : v[14];
+      const double f1 = hi == 1 ? v[13] : hi == 2 ? v[14] : v[15];
       stdv = fabs((f0 - f1) / 2.0);
     } else if (nf > 2) {
       double sum = 0.0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if ((fonm >> k) & 1u) sum = sum + (fr[k] - mean) * (fr[k] - mean);
+      for (int k = 0; k < 4; ++k) {
+        const double dlt = v[12 + k] - mean;
+        sum = ((fonm >> k) & 1u) ? sum + dlt * dlt : sum;
+      }
       stdv = sqrt(sum / (double)nf);
     }
     const double bal = (double)__double2ll_rz((1.0 - stdv) * (double)VC_MAX_NODE_SCORE);
@@ -500,22 +493,18 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     if (c.w_most != 0) no += most * (double)c.w_most;
     if (c.w_balanced != 0) no += bal * (double)c.w_balanced;
     if (c.w_node_affinity != 0) no += (double)(cs >> CS_NAFF_SHIFT) * (double)c.w_node_affinity;
+    const double tdm_sc = (cs & CS_TDM_ORDER_MAX) ? (double)VC_MAX_NODE_SCORE : 0.0;
     double order = 0.0;
-    bool has_order = true;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      if (k >= ord_n) break;
-      if (ord_kind[k] == VC_PLUGIN_BINPACK) order += bp;
-      else if (ord_kind[k] == VC_PLUGIN_NODEORDER) order += no;
-      else if (has_order) {
-        if (cs & CS_TDM_ORDER_ERR) has_order = false;
-        else order += (cs & CS_TDM_ORDER_MAX) ? (double)VC_MAX_NODE_SCORE : 0.0;
-      }
+      const int kind = ord_kind[k];
+      const double term = kind == VC_PLUGIN_BINPACK ? bp : kind == VC_PLUGIN_NODEORDER ? no : tdm_sc;
+      order = k < ord_n ? order + term : order;
     }
+    const bool has_order = !(ord_has_tdm && (cs & CS_TDM_ORDER_ERR));
     *score_out = total_score(c, has_order, has_order ? order : 0.0, 0, 0);
     return fit ? 0 : 2;
   };
-
   // per-lane operands of eval_dirty for the group record staged in S.trec
   auto stage_ops = [&]() {
     t_has = S.trec.has;
@@ -586,6 +575,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     double g_best_score = 0.0;
     int g_best_node = -1, g_cnt = 0, g_best_owner = -1;
     bool pub_pending = false;
+    long long t_a = 0, t_b = 0, t_c = 0, acc_ab = 0, acc_bc = 0, acc_cp = 0, acc_ja = 0;
+    long long t_post = 0, t_join = 0, acc_post_to_joinstart = 0, acc_join_wait = 0, acc_join_to_post = 0; int acc_n = 0;
     int pub_owner = -1, pub_node = -1;
     unsigned pub_pc = 0;
 
@@ -747,9 +738,13 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         if (o != last_owner) { n_owner_change += 1; last_owner = o; }
         Best nb;
         if (o == cta) {
+          const long long t0_ = clock64();
           __syncthreads();  // B2 of CMD_EVAL
+          t_join = clock64();
+          acc_post_to_joinstart += t0_ - t_post; acc_join_wait += t_join - t0_; acc_n += 1;
           nb.score = F.ev_score; nb.node = F.ev_node; nb.cnt = F.ev_cnt;
         } else {
+          t_join = 0;
           const unsigned tag = (pub_pc + 1u) & 0x3fffffffu;
           const uint4 *ent = p.ring + (size_t)(pub_pc % RING_DEPTH) * RING_STRIDE;
           uint4 v;
@@ -787,6 +782,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         cursor += 1;
         if (cursor < task_end) meta = __ldg(&p.tmeta[cursor]);  // prefetch the next task's record
         resolve();
+        t_a = clock64();
         if (grp != cur_group) {  // stage the group's request record (shared: workers read it in sweeps)
           __syncwarp();
           if (lane < R) S.trec.req[lane] = __ldg(&p.g_req[(size_t)lane * p.n_groups + grp]);
@@ -827,6 +823,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         // resources only shrink inside a visit), so it is skipped; other jobs take exact full sweeps.
         const bool use_cache = c.enable_ecache && named_role && !pure;
         PROF_MARK(1);
+        t_b = clock64();
 
         if (pure && grp == cache_group) {
           // -------- incremental step: verdict cache, slot table and global best are already current --------
@@ -857,6 +854,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         }
         n_steps += 1;
         PROF_MARK(3);
+        t_c = clock64();
 
         if (g_cnt == 0) {  // no feasible node, allocate.go:639-659
           if (lane == 0) { if (out_cta) p.fit_errors[n_fit] = t; S.r_failed[rl] = 1; }
@@ -909,6 +907,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
               S.cmd = CMD_EVAL;
             }
             __syncthreads();  // B1 of CMD_EVAL
+            t_post = clock64();
+            if (t_join != 0) { acc_join_to_post += t_post - t_join; acc_ja += t_a - t_join; acc_ab += t_b - t_a; acc_bc += t_c - t_b; acc_cp += t_post - t_c; }
           }
         }
         // job.UpdateTaskStatus + event handlers: drf (drf.go:391-418), proportion (proportion.go:475-497)
@@ -1054,6 +1054,14 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       S.cmd = CMD_EXIT;
       S.n_dec = n_dec; S.n_vis = n_vis; S.n_fit = n_fit; S.n_steps = n_steps; S.n_full = n_full; S.n_incr = n_incr;
       S.pick2 = n_owner_change;
+      atomicAdd((unsigned long long *)&p.prof[8], (unsigned long long)acc_post_to_joinstart);
+      atomicAdd((unsigned long long *)&p.prof[9], (unsigned long long)acc_n);
+      atomicAdd((unsigned long long *)&p.prof[10], (unsigned long long)acc_join_wait);
+      atomicAdd((unsigned long long *)&p.prof[11], (unsigned long long)acc_join_to_post);
+      atomicAdd((unsigned long long *)&p.prof[12], (unsigned long long)acc_ja);
+      atomicAdd((unsigned long long *)&p.prof[13], (unsigned long long)acc_ab);
+      atomicAdd((unsigned long long *)&p.prof[14], (unsigned long long)acc_bc);
+      atomicAdd((unsigned long long *)&p.prof[15], (unsigned long long)acc_cp);
 
     }
     __syncthreads();  // B1 of the exit command
