@@ -514,6 +514,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     on_task = role == ROLE_BP ? (lane_valid && (dk_c < 2 || (t_has & (1u << dk_c))) && b_val >= VC_MIN_RESOURCE && w_d >= 0)
             : role == ROLE_BAL ? (lane_valid && !(dk_c >= 2 && b_val == 0.0))
             : (role != ROLE_NONE);
+    int wv = (role == ROLE_BP && on_task) ? w_d : 0;
+    for (int o = 4; o; o >>= 1) wv += __shfl_xor_sync(0xffffffffu, wv, o);  // lane 0: sum over lanes 0-7
+    wsum_g = __shfl_sync(0xffffffffu, wv, 0);
   };
   // CMD_EVAL (warp 1): re-evaluate node F.ev_i for the cached group, maintain this CTA's best incrementally
   // (rescan only when the holder got worse) and publish the CTA's new best in the ring.
