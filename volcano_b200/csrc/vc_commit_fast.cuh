@@ -413,10 +413,17 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   //   lanes 8-9   leastRequestedScore of cpu / memory, lanes 10-11 mostRequestedScore
   //   lanes 12-15 BalancedAllocation fraction of upstream dim k
   // then one second-level division (binpack /weightSum, least, most, mean) and the std / sqrt.
-  auto eval_dirty = [&](int i, double *score_out) -> int {
+  // `extra` = 1 evaluates the node as it will be after ONE more placement of this same group (speculation: under
+  // best-fit scoring the node that just won usually wins again); the adds are the same IEEE operations the real
+  // placement performs (node_info.go:467-471, predicates.go:254-255), so the speculative score is bit-identical.
+  auto eval_dirty = [&](int i, int extra, double *score_out) -> int {
     const uint32_t cs = fs.c_cs[i];
-    const bool pod_cap = c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i];
-    const double a = a_base[i], alloc = al_base[i], idle = idle_base[i];
+    const int kx = (extra && c.has_predicates) ? 1 : 0;
+    const bool pod_cap = c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i] + kx;
+    const bool bump = extra && (role == ROLE_BP || kx);
+    const double a0 = a_base[i], alloc = al_base[i], idle0 = idle_base[i];
+    const double a = bump ? a0 + b_val : a0;
+    const double idle = extra ? idle0 - req_fit : idle0;
     const bool bad_fit = fit_on && !le_eps(req_fit, idle);
     const double s = a + b_val;
     const bool nz = alloc != 0.0;
@@ -520,12 +527,16 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   };
   // CMD_EVAL (warp 1): re-evaluate node F.ev_i for the cached group, maintain this CTA's best incrementally
   // (rescan only when the holder got worse) and publish the CTA's new best in the ring.
-  auto eval_and_publish = [&]() {
+  int spec_i = -1, spec_group = -2, spec_cat = 2, n_spec_hit = 0;
+  double spec_sc = 0.0;
+  auto eval_and_publish = [&](int my_group) {
     const int i = F.ev_i;
     const int dn = nbase + i;
     const int old_cat = fs.c_cat[i];
     double sc = 0.0;
-    const int cat = eval_dirty(i, &sc);
+    int cat;
+    if (spec_i == i && spec_group == my_group) { cat = spec_cat; sc = spec_sc; n_spec_hit += 1; }
+    else cat = eval_dirty(i, 0, &sc);
     __syncwarp();
     if (lane == 0) { fs.c_cat[i] = cat; fs.c_score[i] = sc; }
     double bs = F.cta_best_score;
@@ -546,6 +557,11 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       mbox_store(p.ring + (size_t)F.ev_ring * RING_STRIDE, pack_best(nb, F.ev_tag));
       F.ev_score = bs; F.ev_node = bn; F.ev_cnt = min(cnt, 2);
     }
+    __syncwarp();
+    asm volatile("bar.arrive 1, 64;" ::: "memory");  // results ready: warp 0 joins with bar.sync 1, 64
+    // run ahead: the same node after one more placement of this group
+    spec_i = -1;
+    if (cat == 0) { spec_cat = eval_dirty(i, 1, &spec_sc); spec_i = i; spec_group = my_group; }
   };
 
   if (warp != 0) {
@@ -557,11 +573,15 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       if (cmd == CMD_EXIT) break;
       if (cmd == CMD_SWEEP) sweep_part();
       else if (cmd == CMD_DISCARD) discard_part();
-      else if (cmd == CMD_EVAL && warp == 1) {
-        if (F.cur_group != my_group) { stage_ops(); my_group = F.cur_group; }
-        eval_and_publish();
+      else if (cmd == CMD_EVAL) {  // no block-wide B2: warp 1 signals warp 0 on named barrier 1
+        if (warp == 1) {
+          if (F.cur_group != my_group) { stage_ops(); my_group = F.cur_group; spec_i = -1; }
+          eval_and_publish(my_group);
+        }
+        continue;
       }
-      __syncthreads();  // B2: command done (for CMD_EVAL warp 0 arrives late: that is the join)
+      if (cmd == CMD_DISCARD) spec_i = -1;  // rolled-back nodes invalidate the speculation
+      __syncthreads();  // B2: command done
     }
   } else {
     // ===================================================================================
@@ -742,7 +762,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         Best nb;
         if (o == cta) {
           const long long t0_ = clock64();
-          __syncthreads();  // B2 of CMD_EVAL
+          asm volatile("bar.sync 1, 64;" ::: "memory");  // join the evaluator warp
           t_join = clock64();
           acc_post_to_joinstart += t0_ - t_post; acc_join_wait += t_join - t0_; acc_n += 1;
           nb.score = F.ev_score; nb.node = F.ev_node; nb.cnt = F.ev_cnt;
