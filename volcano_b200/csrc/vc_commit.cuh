@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
     // allocateResourcesForTasks, allocate.go:558-694
     // =================================================================================
     for (;;) {
-      if (S.cursor >= S.task_end) break;  // tasks.Empty()
+      if (S.cursor >= S.task_end || N == 0) break;  // tasks.Empty(); no nodes: return nil (allocate.go:563-567)
       PROF_MARK(4);
       // ---- tasks.Pop() + task record ----
       const int t = p.task_order[S.cursor];
@@ -827,8 +827,8 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
 
     PROF_MARK(4);
     // ---- statement outcome, allocate.go:681-693 and :330-337 ----
-    const bool ready = ctl_job_ready(c, S);
-    const bool stmt = ready || ctl_job_pipelined(c, S);
+    const bool ready = N != 0 && ctl_job_ready(c, S);
+    const bool stmt = N != 0 && (ready || ctl_job_pipelined(c, S));
     const int n_ops = S.n_ops;
     __syncthreads();
     if (!stmt && n_ops > 0) {

@@ -789,6 +789,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         }
         __syncwarp();
         if (lane == 0) { fs.sl_score[o] = nb.score; fs.sl_node[o] = nb.node; fs.sl_cnt[o] = nb.cnt; }
+        __syncwarp();
         since_sync += 1;
         if (refold) {
           __syncwarp();
@@ -799,7 +800,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
 
       // ---- allocateResourcesForTasks, allocate.go:558-694 ----
       for (;;) {
-        if (cursor >= task_end) break;
+        if (cursor >= task_end || N == 0) break;  // no nodes: return nil before touching the tasks (allocate.go:563-567)
         PROF_MARK(4);
         const int t = meta.x, grp = meta.y, rl = meta.z - role_base;
         cursor += 1;
@@ -880,6 +881,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         t_c = clock64();
 
         if (g_cnt == 0) {  // no feasible node, allocate.go:639-659
+          __syncwarp();
           if (lane == 0) { if (out_cta) p.fit_errors[n_fit] = t; S.r_failed[rl] = 1; }
           n_fit += 1;
           __syncwarp();
@@ -970,9 +972,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
 
       // ---- statement outcome, allocate.go:681-693 and :330-337 ----
       __syncwarp();
-      const bool jready = job_ready_now();
+      const bool jready = job_ready_now() && N != 0;
       bool stmt = jready;
-      if (!stmt) {  // ssn.JobPipelined needs the shared control block (rare path)
+      if (!stmt && N != 0) {  // ssn.JobPipelined needs the shared control block (rare path)
         if (lane == 0) { S.ready = ready; S.waiting = waiting; }
         __syncwarp();
         stmt = ctl_job_pipelined(c, S);

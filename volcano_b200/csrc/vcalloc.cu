@@ -225,7 +225,7 @@ void choose_geometry(vc_snapshot *s) {
   if (const char *e = getenv("VC_COMMIT_THREADS")) block = std::max(128, std::min(256, atoi(e) / 32 * 32));
   ctas = std::max(1, std::min(ctas, (nloc + 31) / 32));  // at least a warp of nodes per CTA
   int npc = (nloc + ctas - 1) / ctas;
-  npc = (npc + 31) / 32 * 32;
+  npc = std::max(32, (npc + 31) / 32 * 32);
   ctas = std::max(1, (nloc + npc - 1) / npc);
   if (npc > block) block = std::min(256, (npc + 31) / 32 * 32);
   s->n_cta = ctas;
