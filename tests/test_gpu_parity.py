@@ -56,6 +56,26 @@ def test_nodeorder_goldens(case, weights, gpu, oracle_engine):
     _assert_same(case.result, oracle_engine(snap))
 
 
+@pytest.mark.parametrize("case", G.proportion_cases(), ids=lambda c: c.Name[:40])
+def test_proportion_goldens(case, gpu, oracle_engine):
+    snap = case.RegisterSession(G.proportion_tiers())
+    case.Run(gpu.gpu_engine)
+    assert case.CheckAll() is None, case.CheckAll()
+    _assert_same(case.result, oracle_engine(snap))
+
+
+@pytest.mark.parametrize("case,nodes,scores", G.tdm_cases(), ids=lambda c: getattr(c, "Name", "x")[:40])
+def test_tdm_goldens(case, nodes, scores, gpu):
+    """tdm_test.go:107-270: predicate verdicts and scores of the tdm plugin through the dense pass."""
+    from tests.test_oracle_golden import _check_tdm
+    snap = case.RegisterSession(G.tdm_tiers())
+    e = gpu.Engine(snap)
+    e.upload()
+    mask, score, _, _ = e.score_matrix()
+    e.close()
+    _check_tdm(snap, mask, score, nodes, scores)
+
+
 @pytest.mark.parametrize("args,expected", G.BINPACK_CASES)
 def test_binpack_goldens(args, expected, gpu):
     """binpack_test.go:100-238: exact scores through the dense pass (only binpack registered)."""

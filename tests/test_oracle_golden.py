@@ -92,3 +92,47 @@ def test_upstream_score_sanity():
     assert (L.vco_least_requested_score(1000, 4000) * 50 + L.vco_least_requested_score(10**9, 8 * gi) * 50) // 100 == 81
     assert (L.vco_most_requested_score(1000, 2000) + L.vco_most_requested_score(10**9, 4 * gi)) // 2 == 36
     assert (L.vco_most_requested_score(1000, 4000) + L.vco_most_requested_score(10**9, 8 * gi)) // 2 == 18
+
+
+@pytest.mark.parametrize("case", G.proportion_cases(), ids=lambda c: c.Name[:40])
+def test_proportion_queue_priority(case, oracle_engine):
+    case.RegisterSession(G.proportion_tiers())
+    case.Run(oracle_engine)
+    assert case.CheckAll() is None, case.CheckAll()
+
+
+def _check_tdm(snap, mask, score, want_nodes, want_scores):
+    got = {snap.node_names[n] for n in range(snap.N) if (mask[0, n // 64] >> np.uint64(n % 64)) & np.uint64(1)}
+    assert got == want_nodes
+    key = snap.task_keys[0]
+    for n in range(snap.N):
+        if snap.node_names[n] in got:
+            assert abs(score[0, n] - want_scores[key][snap.node_names[n]]) <= G.TDM_EPS
+
+
+@pytest.mark.parametrize("case,nodes,scores", G.tdm_cases(), ids=lambda c: getattr(c, "Name", "x")[:40])
+def test_tdm_predicate_and_score(case, nodes, scores):
+    snap = case.RegisterSession(G.tdm_tiers())
+    o = OracleSession(snap)
+    mask, score, _, _ = o.score_matrix()
+    o.close()
+    _check_tdm(snap, mask, score, nodes, scores)
+
+
+@pytest.mark.parametrize("raw,delta,err", G.PARSE_REVOCABLE_ZONE)
+def test_parse_revocable_zone(raw, delta, err):
+    from volcano_b200.snapshot import parse_revocable_zone
+    if err:
+        with pytest.raises(ValueError):
+            parse_revocable_zone(raw)
+    else:
+        start, end = parse_revocable_zone(raw)
+        assert int((end - start).total_seconds()) == delta
+
+
+def test_tdm_windows_from_arguments():
+    """rz1 "0:00-0:00" covers the whole day, rz2 "0:00-0:01" only its first minute (tdm_test.go:218-221)."""
+    import datetime as dt
+    from volcano_b200.snapshot import tdm_zones_active
+    assert tdm_zones_active(G.TDM_ARGUMENTS, dt.datetime(2024, 5, 1, 12, 0)) == {"rz1": True, "rz2": False}
+    assert tdm_zones_active(G.TDM_ARGUMENTS, dt.datetime(2024, 5, 1, 0, 0, 30)) == {"rz1": True, "rz2": True}

@@ -144,6 +144,9 @@ class NodeSelectorRequirement:
         return (self.key, self.operator, tuple(self.values))
 
 
+REVOCABLE_ZONE = "volcano.sh/revocable-zone"  # v1beta1.RevocableZone
+
+
 @dataclass
 class Node:
     name: str
@@ -153,6 +156,10 @@ class Node:
     unschedulable: bool = False
     annotations: Dict[str, str] = field(default_factory=dict)
     revocable_zone: str = ""  # label volcano.sh/revocable-zone
+
+    def __post_init__(self):
+        if not self.revocable_zone:  # setRevocableZone, api/node_info.go:252-265
+            self.revocable_zone = self.labels.get(REVOCABLE_ZONE, "")
 
 
 @dataclass
@@ -181,6 +188,11 @@ class Pod:
     def __post_init__(self):
         if not self.uid:
             self.uid = f"{self.namespace}-{self.name}"  # util/test_utils.go:74
+        if not self.revocable_zone:  # GetPodRevocableZone, api/pod_info.go:153-165
+            if REVOCABLE_ZONE in self.annotations:  # only the wildcard zone is honoured
+                self.revocable_zone = "*" if self.annotations[REVOCABLE_ZONE] == "*" else ""
+            elif self.annotations.get("volcano.sh/preemptable", "").lower() in ("1", "t", "true"):
+                self.revocable_zone = "*"
 
     @property
     def key(self) -> str:

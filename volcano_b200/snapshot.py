@@ -12,6 +12,8 @@ import ctypes as C
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
+import re
+
 import numpy as np
 
 from . import abi
@@ -345,6 +347,47 @@ def _k8s_vector(rl: Optional[Dict[str, str]], nonzero: bool):
     return out
 
 
+_RZ_RE = re.compile(r"(\d{1,2}):(\d{2})")
+
+
+def parse_revocable_zone(rz_raw: str, now=None):
+    """parseRevocableZone (plugins/tdm/tdm.go:88-116): "H:MM-H:MM" -> (start, end) datetimes of today's window;
+    an end at or before the start rolls to tomorrow.  Raises ValueError on the inputs the reference rejects."""
+    import datetime as _dt
+    now = now or _dt.datetime.now()
+    parts = rz_raw.strip().split("-")
+    if len(parts) != 2:
+        raise ValueError(f"revocable zone {rz_raw} format error")
+    hm = []
+    for v in parts:  # Go layout "15:04": one or two hour digits, exactly two minute digits
+        m = _RZ_RE.fullmatch(v)
+        if not m or int(m.group(1)) > 23 or int(m.group(2)) > 59:
+            raise ValueError(f"parsing time {v!r}")
+        hm.append((int(m.group(1)), int(m.group(2))))
+    start = now.replace(hour=hm[0][0], minute=hm[0][1], second=0, microsecond=0)
+    end = now.replace(hour=hm[1][0], minute=hm[1][1], second=0, microsecond=0)
+    if hm[0] >= hm[1]:
+        end += _dt.timedelta(days=1)
+    return start, end
+
+
+def tdm_zones_active(arguments: Dict[str, object], now=None) -> Dict[str, bool]:
+    """availableRevocableZone (tdm.go:118-137) for every "tdm.revocable-zone.<name>" argument (tdm.go:65-77)."""
+    import datetime as _dt
+    now = now or _dt.datetime.now()
+    out = {}
+    for k, v in arguments.items():
+        if not k.startswith("tdm.revocable-zone."):
+            continue
+        name = k[len("tdm.revocable-zone."):]
+        try:
+            start, end = parse_revocable_zone(str(v), now)
+            out[name] = int(start.timestamp()) <= int(now.timestamp()) <= int(end.timestamp())
+        except ValueError:
+            out[name] = False
+    return out
+
+
 def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequence[PodGroup],
                    queues: Sequence[Queue], conf: SchedulerConf, tdm_zone_active: Optional[Dict[str, bool]] = None
                    ) -> Snapshot:
@@ -536,8 +579,14 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
             s.n_flags[i] |= abi.VC_NODE_UNSCHEDULABLE
         if n.revocable_zone:
             s.n_revocable_zone[i] = zones[n.revocable_zone]
+    if tdm_zone_active is None:  # derive from the tdm plugin's arguments at "now", as OnSessionOpen does
+        tdm_zone_active = {}
+        for tier in conf.tiers:
+            for po in tier:
+                if po.name == "tdm":
+                    tdm_zone_active.update(tdm_zones_active(po.arguments))
     for z, zi in zones.items():
-        s.zone_active[zi] = 1 if (tdm_zone_active or {}).get(z, False) else 0
+        s.zone_active[zi] = 1 if tdm_zone_active.get(z, False) else 0
     for p in pods:
         if not p.node_name or p.node_name not in nidx:
             continue
