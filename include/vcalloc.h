@@ -46,13 +46,14 @@
 extern "C" {
 #endif
 
-#define VC_ABI_VERSION 1
+#define VC_ABI_VERSION 2
 #define VC_MAX_DIMS 16   /* R  */
 #define VC_MAX_KDIMS 4   /* dims seen by the upstream kube-scheduler scorers (cpu, memory, nvidia.com/gpu, ...) */
 #define VC_MAX_WORDS 4   /* 64-bit words per label / taint bitset */
 #define VC_MAX_TERMS 4   /* required-affinity terms and preferred-affinity terms per class */
 #define VC_MAX_PLUGINS 16
 #define VC_MAX_JOB_ROLES 64
+#define VC_MAX_TIERS 8   /* HyperNode tiers incl. the cluster top tier */
 
 /* error codes */
 #define VC_OK 0
@@ -193,6 +194,7 @@ enum vc_plugin {
   VC_PLUGIN_NODEORDER = 6,
   VC_PLUGIN_BINPACK = 7,
   VC_PLUGIN_TDM = 8,
+  VC_PLUGIN_NETWORK_TOPOLOGY_AWARE = 9,
   VC_PLUGIN_OTHER = 99 /* conformance, overcommit, ...: no effect on this path */
 };
 /* PluginOption enable flags (conf/scheduler_conf.go:60-107); nil == false unless
@@ -234,7 +236,24 @@ typedef struct vc_conf {
   int32_t percentage_nodes_to_find;     /* options.go:48-54; 100 = parity mode */
   int32_t min_nodes_to_find;            /* 100 */
   int32_t min_percentage_nodes_to_find; /* 5 */
+  /* network-topology-aware arguments (plugins/network-topology-aware/network_topology_aware.go:155-229) */
+  int32_t nta_weight;                   /* "weight", default 1 */
+  int32_t nta_dim_weight[VC_MAX_DIMS];  /* hypernode.binpack.{cpu,memory,resources.*}; -1: not in the weight map */
+  int32_t nta_normal_pod_enable;        /* hypernode.binpack.normal-pod.enable, default 1 */
+  double nta_fading;                    /* hypernode.binpack.normal-pod.fading, default 0.8 */
 } vc_conf;
+
+/* ---- HyperNode tree (ssn.HyperNodesSetByTier / ssn.RealNodesSet, framework/session.go:239-245) -----
+   Consumed by network-topology-aware's hypernode-level binpacking of pods without a network topology
+   (batchNodeOrderFnForNormalPods, network_topology_aware.go:462-496). The cluster top hypernode that
+   Session open adds above the highest real tier (session.go:285-313) is part of the table. */
+typedef struct vc_hypernodes {
+  int32_t n_hypernodes;  /* H */
+  int32_t min_tier;      /* hyperNodesTier.init, network_topology_aware.go:97-104 */
+  int32_t max_tier;      /* max_tier - min_tier + 1 <= VC_MAX_TIERS */
+  const int32_t *member; /* [max_tier-min_tier+1][N]: index in [0,H) of the hypernode of tier min_tier+l whose
+                            RealNodesSet holds node n, -1 when no hypernode of that tier does */
+} vc_hypernodes;
 
 /* ---- results ----------------------------------------------------------------------- */
 #define VC_OP_ALLOCATE 0 /* Statement.Allocate (framework/statement.go:242-302) */
@@ -288,6 +307,10 @@ void vc_snapshot_destroy(vc_snapshot *s);
 int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nodes, const vc_tasks *tasks,
                        const vc_classes *classes, const vc_jobs *jobs, const vc_queues *queues,
                        const vc_conf *conf);
+
+/* Optional, before vc_snapshot_upload: the HyperNode tree of the session. Without it a configured
+   network-topology-aware plugin scores against the cluster top hypernode only (no HyperNode CRs). */
+int vc_snapshot_set_topology(vc_snapshot *s, const vc_hypernodes *topo);
 
 /* Restrict the node axis of this process to [node_begin, node_end) for node-sharded
    multi-GPU runs; tasks/jobs/queues stay replicated. Default: all nodes. */

@@ -313,6 +313,13 @@ struct Session {
   std::vector<QueueAttr> qattr;
   Res total;  // ssn.TotalResource (framework/session.go:272-274)
   bool has_plugin[128] = {false};
+  // network-topology-aware: hypernode membership per tier level and the plugin's hyperNodeResourceCache
+  int hn_H = 0, hn_L = 0, hn_min_tier = 1;
+  std::vector<int32_t> hn_member;         // [L][N]
+  std::vector<double> hn_alloc, hn_used;  // [R][H]
+  double tier_w[VC_MAX_TIERS] = {0};
+  double tier_w_total = 0.0;
+  bool nta_on = false;  // plugin registered with EnabledNodeOrder and normal-pod binpacking enabled
   // results
   std::vector<vc_decision> decisions;
   std::vector<vc_visit> visits;
@@ -608,6 +615,103 @@ bool allocatable(const Session &s, int q, int t) {
 // Event handlers fired by Statement.Allocate / Pipeline (AllocateFunc) and by
 // unallocate / UnPipeline (DeallocateFunc): drf.go:391-454, proportion.go:475-518,
 // predicates.go:212-304 (k8s NodeInfo AddPodInfo / RemovePod).
+// ---------------------------------------------------------------------------------------
+// network-topology-aware, hypernode-level binpacking of pods without a network topology
+// (plugins/network-topology-aware/network_topology_aware.go)
+// ---------------------------------------------------------------------------------------
+// Go's math.Pow for a non-negative integer exponent (restated from the published Go runtime
+// algorithm, src/math/pow.go: special cases, then binary exponentiation on the Frexp mantissa, which is
+// the same sequence of fp64 products as on the values themselves). Used for the tier weights :470-476.
+double go_pow_uint(double x, unsigned n) {
+  if (n == 0 || x == 1.0) return 1.0;
+  if (n == 1) return x;
+  if (x == 0.0) return 0.0;
+  int xe = 0, ae = 0;
+  double x1 = std::frexp(x, &xe), a1 = 1.0;
+  for (unsigned i = n; i != 0; i >>= 1) {
+    if (i & 1u) { a1 *= x1; ae += xe; }
+    x1 *= x1;
+    xe <<= 1;
+    if (x1 < 0.5) { x1 += x1; xe--; }
+  }
+  return std::ldexp(a1, ae);
+}
+// hyperNodesTier.init :97-104, initHyperNodeResourceCache :106-125, tier weights :469-476
+void nta_init(Session &s, const vc_hypernodes *topo) {
+  s.nta_on = false;
+  for (int i = 0; i < s.conf.n_plugins; ++i)
+    if (s.conf.plugins[i].plugin == VC_PLUGIN_NETWORK_TOPOLOGY_AWARE && (s.conf.plugins[i].enabled & VC_EN_NODE_ORDER) &&
+        s.conf.nta_normal_pod_enable)
+      s.nta_on = true;
+  if (topo && topo->member) {
+    s.hn_H = topo->n_hypernodes;
+    s.hn_min_tier = topo->min_tier;
+    s.hn_L = topo->max_tier - topo->min_tier + 1;
+    s.hn_member.assign(topo->member, topo->member + (size_t)s.hn_L * s.N);
+  } else {  // no HyperNode objects: only the cluster top hypernode, tier 1 (framework/session.go:285-313)
+    s.hn_H = 1; s.hn_min_tier = 1; s.hn_L = 1;
+    s.hn_member.assign((size_t)s.N, 0);
+  }
+  s.hn_alloc.assign((size_t)s.R * s.hn_H, 0.0);
+  s.hn_used.assign((size_t)s.R * s.hn_H, 0.0);
+  for (int l = 0; l < s.hn_L; ++l)
+    for (int n = 0; n < s.N; ++n) {
+      int h = s.hn_member[(size_t)l * s.N + n];
+      if (h < 0) continue;
+      for (int d = 0; d < s.R; ++d) {
+        at(s.hn_alloc, d, s.hn_H, h) += at(s.alloc, d, s.N, n);
+        at(s.hn_used, d, s.hn_H, h) += at(s.used, d, s.N, n);
+      }
+    }
+  s.tier_w_total = 0.0;
+  for (int l = 0; l < s.hn_L && l < VC_MAX_TIERS; ++l) {
+    int tier = s.hn_min_tier + l;
+    s.tier_w[l] = go_pow_uint(s.conf.nta_fading, (unsigned)(tier - 1));
+    s.tier_w_total += s.tier_w[l];
+  }
+}
+// getPodHyperNodeBinPackingScore :498-539
+double hn_binpack_score(const Session &s, int t, int h) {
+  double total_score = 0.0;
+  int total_weight = 0;
+  for (int d = 0; d < s.R; ++d) {
+    double request = at(s.req, d, s.T, t);
+    if (d >= 2 && !(s.req_has[t] & (1u << d))) continue;  // task.Resreq.ResourceNames()
+    if (!(request >= kMinResource)) continue;
+    int w = s.conf.nta_dim_weight[d];
+    if (w < 0) continue;  // getBinPackWeight: not found
+    double allocatable = at(s.hn_alloc, d, s.hn_H, h);
+    double used = at(s.hn_used, d, s.hn_H, h);
+    if (used + request > allocatable) return 0.0;
+    double score = (used + request) / allocatable;
+    total_score += (double)w * score;
+    total_weight += w;
+  }
+  if (total_weight > 0) return total_score / (double)total_weight;
+  return 0.0;
+}
+// batchNodeOrderFnForNormalPods :462-496 + scaleFinalScore :758-764 for one node
+double nta_node_score(const Session &s, int t, int n) {
+  double total = 0.0;
+  for (int l = 0; l < s.hn_L; ++l) {
+    int h = s.hn_member[(size_t)l * s.N + n];
+    double tier_score = h < 0 ? 1.0 : hn_binpack_score(s, t, h);  // FullScore when no hypernode of the tier holds the node
+    total += s.tier_w[l] * tier_score;
+  }
+  double sc = total / s.tier_w_total;
+  return (double)kMaxNodeScore * (double)s.conf.nta_weight * sc;
+}
+void nta_account(Session &s, int t, int n, double sign) {  // event handlers :374-399
+  for (int l = 0; l < s.hn_L; ++l) {
+    int h = s.hn_member[(size_t)l * s.N + n];
+    if (h < 0) continue;
+    for (int d = 0; d < s.R; ++d) {
+      if (d >= 2 && !(s.req_has[t] & (1u << d))) continue;
+      at(s.hn_used, d, s.hn_H, h) += sign * at(s.req, d, s.T, t);
+    }
+  }
+}
+
 void on_allocate_event(Session &s, int t, int n) {
   int j = s.t_job[t];
   if (s.has_plugin[VC_PLUGIN_DRF]) {
@@ -619,6 +723,7 @@ void on_allocate_event(Session &s, int t, int n) {
     res_add(a.allocated, task_res(s, t), s.R);
     proportion_update_share(s, a);
   }
+  if (s.has_plugin[VC_PLUGIN_NETWORK_TOPOLOGY_AWARE]) nta_account(s, t, n, 1.0);
   if (s.has_plugin[VC_PLUGIN_PREDICATES]) {
     s.pod_count[n] += 1;
     for (int k = 0; k < s.K; ++k) {
@@ -646,6 +751,7 @@ void on_deallocate_event(Session &s, int t, int n) {
         }
     proportion_update_share(s, a);
   }
+  if (s.has_plugin[VC_PLUGIN_NETWORK_TOPOLOGY_AWARE]) nta_account(s, t, n, -1.0);
   if (s.has_plugin[VC_PLUGIN_PREDICATES]) {
     s.pod_count[n] -= 1;
     for (int k = 0; k < s.K; ++k) {
@@ -881,7 +987,7 @@ bool batch_enabled(const Session &s) {  // does any BatchNodeOrderFn produce ent
     if ((p.enabled & VC_EN_NODE_ORDER) && (p.plugin == VC_PLUGIN_NODEORDER || p.plugin == VC_PLUGIN_PREDICATES))
       return true;
   }
-  return false;
+  return s.nta_on;
 }
 bool taint_batch_enabled(const Session &s) {
   if (s.conf.w_taint_toleration == 0) return false;
@@ -928,6 +1034,7 @@ int prioritize_and_select(Session &s, int t, const std::vector<int> &nodes, doub
         node_sc += (double)sc;  // nodeorder.go:369-381
         b += node_sc;
       }
+      if (s.nta_on) b += nta_node_score(s, t, nodes[i]);  // two addends: plugin order is immaterial
       score += b;
     }
     if (scores_out) (*scores_out)[i] = score;
@@ -1325,6 +1432,7 @@ Session *load(const vc_dims *dims, const vc_nodes *nd, const vc_tasks *tk, const
     s.total.v[d] = acc;
     if (d >= 2 && s.N > 0) { s.total.has |= 1u << d; s.total.nilmap = false; }
   }
+  nta_init(s, nullptr);
   s.j_share.assign(J, 0.0);
   if (s.has_plugin[VC_PLUGIN_DRF])
     for (int j = 0; j < s.J; ++j) drf_update_share(s, j);  // drf.go:186-214
@@ -1353,6 +1461,22 @@ const vc_visit *vco_visits(void *h) { return ((Session *)h)->visits.data(); }
 size_t vco_num_fit_errors(void *h) { return ((Session *)h)->fit_errors.size(); }
 const int32_t *vco_fit_errors(void *h) { return ((Session *)h)->fit_errors.data(); }
 int64_t vco_num_sweeps(void *h) { return ((Session *)h)->sweeps; }
+// HyperNode tree of the session (before any run); mirrors vc_snapshot_set_topology
+void vco_session_set_topology(void *h, const vc_hypernodes *topo) { nta_init(*(Session *)h, topo); }
+// hyperNodeResourceCache entry (allocatable, used) of hypernode `hn`, for Test_initHyperNodeResourceCache
+void vco_hypernode_status(void *h, int hn, double *alloc_out, double *used_out) {
+  Session &s = *(Session *)h;
+  for (int d = 0; d < s.R; ++d) {
+    alloc_out[d] = at(s.hn_alloc, d, s.hn_H, hn);
+    used_out[d] = at(s.hn_used, d, s.hn_H, hn);
+  }
+}
+// network-topology-aware BatchNodeOrderFn entry of (task, node); 0 when the map has no entry
+double vco_nta_node_score(void *h, int t, int n) {
+  Session &s = *(Session *)h;
+  return s.nta_on ? nta_node_score(s, t, n) : 0.0;
+}
+double vco_go_pow_uint(double x, unsigned n) { return go_pow_uint(x, n); }
 void vco_score_matrix(void *h, uint64_t *mask_out, double *score_out, double *best_score, int32_t *best_node) {
   score_matrix(*(Session *)h, mask_out, score_out, best_score, best_node);
 }

@@ -43,6 +43,12 @@ def lib() -> C.CDLL:
                                          C.POINTER(abi.vc_classes), C.POINTER(abi.vc_jobs), C.POINTER(abi.vc_queues),
                                          C.POINTER(abi.vc_conf), C.c_int]
         L.vco_session_destroy.argtypes = [_vp]
+        L.vco_session_set_topology.argtypes = [_vp, C.POINTER(abi.vc_hypernodes)]
+        L.vco_hypernode_status.argtypes = [_vp, C.c_int, _dp, _dp]
+        L.vco_nta_node_score.restype = C.c_double
+        L.vco_nta_node_score.argtypes = [_vp, C.c_int, C.c_int]
+        L.vco_go_pow_uint.restype = C.c_double
+        L.vco_go_pow_uint.argtypes = [C.c_double, C.c_uint]
         L.vco_allocate_run.argtypes = [_vp]
         for n in ("vco_num_decisions", "vco_num_visits", "vco_num_fit_errors"):
             getattr(L, n).restype = C.c_size_t
@@ -94,6 +100,9 @@ class OracleSession:
                                       C.byref(snap.conf), threads)
         if not self.h:
             raise RuntimeError("oracle session_create failed")
+        topo = snap.topology()
+        if topo is not None:
+            L.vco_session_set_topology(self.h, C.byref(topo))
 
     def close(self):
         if self.h:

@@ -76,6 +76,24 @@ def test_tdm_goldens(case, nodes, scores, gpu):
     _check_tdm(snap, mask, score, nodes, scores)
 
 
+@pytest.mark.parametrize("case,args,expected", G.nta_cases(), ids=lambda c: getattr(c, "Name", "x")[:40])
+def test_nta_goldens(case, args, expected, gpu):
+    """network_topology_aware_test.go:2011-2766, pods without a network topology: scores of the feasible nodes
+    through the dense pass (only network-topology-aware registered, so the total IS the plugin's score)."""
+    snap = case.RegisterSession(G.nta_tiers(args))
+    e = gpu.Engine(snap)
+    e.upload()
+    mask, score, _, _ = e.score_matrix()
+    e.close()
+    t = snap.task_keys.index("ns1/p1")
+    checked = 0
+    for n, name in enumerate(snap.node_names):
+        if (mask[t, n // 64] >> np.uint64(n % 64)) & np.uint64(1):
+            assert abs(score[t, n] - expected.get(name, 0.0)) <= G.NTA_EPS, (name, score[t, n])
+            checked += 1
+    assert checked >= 6
+
+
 @pytest.mark.parametrize("args,expected", G.BINPACK_CASES)
 def test_binpack_goldens(args, expected, gpu):
     """binpack_test.go:100-238: exact scores through the dense pass (only binpack registered)."""
@@ -103,7 +121,10 @@ ALLOC_CASES = [("tiny", 1), ("tiny", 2), ("tiny", 3), ("small", 1), ("cfg1", Non
                ("tiny_fut", 2), ("tiny_fut", None), ("small_fut_soft", None), ("small_fut_soft", 1), ("small_fut_soft", 2),
                ("small_soft", None), ("small_soft", 3),
                # two roles per job with different requests + TaskMinAvailable: role minima, predicate-error cache
-               ("small_roles", None), ("small_roles", 5)]
+               ("small_roles", None), ("small_roles", 5),
+               # network-topology-aware: hypernode-level binpacking term, hyperNodeResourceCache updated per placement
+               ("tiny_topo", None), ("tiny_topo", 3), ("small_topo", None), ("small_topo", 2),
+               ("small_topo_fut_soft", None), ("small_topo_fut_soft", 4)]
 
 
 @pytest.mark.parametrize("cfg,seed", ALLOC_CASES)
@@ -125,7 +146,8 @@ def test_allocate_generic_kernel(cfg, seed, gpu, oracle_engine, monkeypatch):
     _assert_same(gpu.gpu_engine(snap), oracle_engine(snap, threads=2))
 
 
-@pytest.mark.parametrize("cfg,seed", [("tiny", 1), ("small", 2), ("cfg1", None), ("small_fut_soft", None), ("small_soft", 1)])
+@pytest.mark.parametrize("cfg,seed", [("tiny", 1), ("small", 2), ("cfg1", None), ("small_fut_soft", None), ("small_soft", 1),
+                                      ("tiny_topo", None), ("small_topo", 1), ("small_topo_fut_soft", None)])
 def test_score_matrix_vs_oracle(cfg, seed, gpu):
     from oracle.pyoracle import OracleSession
     from volcano_b200.synth import make_snapshot

@@ -136,3 +136,60 @@ def test_tdm_windows_from_arguments():
     from volcano_b200.snapshot import tdm_zones_active
     assert tdm_zones_active(G.TDM_ARGUMENTS, dt.datetime(2024, 5, 1, 12, 0)) == {"rz1": True, "rz2": False}
     assert tdm_zones_active(G.TDM_ARGUMENTS, dt.datetime(2024, 5, 1, 0, 0, 30)) == {"rz1": True, "rz2": True}
+
+
+@pytest.mark.parametrize("case,args,expected", G.nta_cases(), ids=lambda c: getattr(c, "Name", "x")[:40])
+def test_nta_batch_node_order_normal_pods(case, args, expected):
+    """network_topology_aware_test.go:2011-2766 (pods without a network topology)."""
+    snap = case.RegisterSession(G.nta_tiers(args))
+    o = OracleSession(snap)
+    L = pyoracle.lib()
+    t = snap.task_keys.index("ns1/p1")
+    for n, name in enumerate(snap.node_names):
+        got = L.vco_nta_node_score(o.h, t, n)
+        assert abs(got - expected.get(name, 0.0)) <= G.NTA_EPS, (name, got)
+    # the same numbers through util.PrioritizeNodes for the feasible nodes
+    mask, score, _, _ = o.score_matrix()
+    for n, name in enumerate(snap.node_names):
+        if (mask[t, n // 64] >> np.uint64(n % 64)) & np.uint64(1):
+            assert abs(score[t, n] - expected.get(name, 0.0)) <= G.NTA_EPS
+    o.close()
+
+
+def test_nta_hypernode_resource_cache():
+    """network_topology_aware_test.go:3124-3247 Test_initHyperNodeResourceCache."""
+    from volcano_b200.api import BuildHyperNode, BuildNode, BuildPod, BuildPodGroup, BuildQueue, BuildResourceList
+    N, numbers = G.NTA_CACHE_NODES, G.NTA_CACHE_NUMBERS
+    nodes = [BuildNode(f"node-{i}", BuildResourceList("100", "8000", ("example.com/foo", "10"))) for i in range(N)]
+    hns = [BuildHyperNode(f"hypernode-tier-{t}-index-{k}", t, [(f"node-{i}", "Node") for i in range(k, N, cnt)])
+           for t, cnt in enumerate(numbers, 1) for k in range(cnt)]
+    tc = TestCommonStruct(Name="cache", Nodes=nodes, HyperNodes=hns, Queues=[BuildQueue("q1", 1, None)],
+                          PodGroups=[BuildPodGroup("pg1", "ns1", "q1", 1, None, "Inqueue")],
+                          Pods=[BuildPod("ns1", "p1", "", "Pending", BuildResourceList("1", "1"), "pg1")])
+    snap = tc.RegisterSession(G.nta_tiers({}))
+    # the reference test fills api.Resource directly (raw 10 for the scalar, not a parsed quantity)
+    snap.n_allocatable[snap.dim_names.index("example.com/foo")] = G.NTA_CACHE_PER_NODE["alloc"][2]
+    snap.n_used[:] = snap.n_allocatable / 2
+    snap.n_used[snap.dim_names.index("pods")] = 0
+    o = OracleSession(snap)
+    L = pyoracle.lib()
+    dims = [snap.dim_names.index(d) for d in ("cpu", "memory", "example.com/foo")]
+    a, u = np.zeros(snap.R), np.zeros(snap.R)
+    for t, cnt in enumerate(numbers, 1):
+        for k in (0, cnt - 1):
+            h = snap.hn_names.index(f"hypernode-tier-{t}-index-{k}")
+            L.vco_hypernode_status(o.h, h, a.ctypes.data_as(pyoracle._dp), u.ctypes.data_as(pyoracle._dp))
+            assert tuple(a[dims]) == tuple(N // cnt * v for v in G.NTA_CACHE_PER_NODE["alloc"])
+            assert tuple(u[dims]) == tuple(N // cnt * v for v in G.NTA_CACHE_PER_NODE["used"])
+    o.close()
+
+
+def test_go_pow_small_integer_exponents():
+    """Tier weights use Go's math.Pow (network_topology_aware.go:470-476): y == 0 -> 1 (also 0**0), y == 1 -> x,
+    otherwise binary exponentiation; fading 0.8 over four tiers gives the 2.952 total behind the 25.8 golden."""
+    L = pyoracle.lib()
+    assert L.vco_go_pow_uint(0.0, 0) == 1.0 and L.vco_go_pow_uint(0.0, 3) == 0.0
+    assert L.vco_go_pow_uint(0.8, 1) == 0.8
+    assert L.vco_go_pow_uint(0.8, 2) == 0.8 * 0.8
+    assert L.vco_go_pow_uint(0.8, 3) == 0.8 * (0.8 * 0.8)
+    assert abs(sum(L.vco_go_pow_uint(0.8, k) for k in range(4)) - 2.952) < 1e-12

@@ -7,13 +7,14 @@ from __future__ import annotations
 
 import ctypes as C
 
-VC_ABI_VERSION = 1
+VC_ABI_VERSION = 2
 VC_MAX_DIMS = 16
 VC_MAX_KDIMS = 4
 VC_MAX_WORDS = 4
 VC_MAX_TERMS = 4
 VC_MAX_PLUGINS = 16
 VC_MAX_JOB_ROLES = 64
+VC_MAX_TIERS = 8
 
 VC_OK = 0
 VC_EINVAL = -1
@@ -41,6 +42,7 @@ VC_PLUGIN_PREDICATES = 5
 VC_PLUGIN_NODEORDER = 6
 VC_PLUGIN_BINPACK = 7
 VC_PLUGIN_TDM = 8
+VC_PLUGIN_NETWORK_TOPOLOGY_AWARE = 9
 VC_PLUGIN_OTHER = 99
 PLUGIN_IDS = {
     "priority": VC_PLUGIN_PRIORITY,
@@ -51,6 +53,7 @@ PLUGIN_IDS = {
     "nodeorder": VC_PLUGIN_NODEORDER,
     "binpack": VC_PLUGIN_BINPACK,
     "tdm": VC_PLUGIN_TDM,
+    "network-topology-aware": VC_PLUGIN_NETWORK_TOPOLOGY_AWARE,
 }
 
 VC_EN_JOB_ORDER = 0x001
@@ -165,7 +168,16 @@ class vc_conf(C.Structure):
         ("percentage_nodes_to_find", C.c_int32),
         ("min_nodes_to_find", C.c_int32),
         ("min_percentage_nodes_to_find", C.c_int32),
+        ("nta_weight", C.c_int32),
+        ("nta_dim_weight", C.c_int32 * VC_MAX_DIMS),
+        ("nta_normal_pod_enable", C.c_int32),
+        ("nta_fading", C.c_double),
     ]
+
+
+class vc_hypernodes(C.Structure):
+    _fields_ = [("n_hypernodes", C.c_int32), ("min_tier", C.c_int32), ("max_tier", C.c_int32),
+                ("member", C.POINTER(C.c_int32))]
 
 
 class vc_decision(C.Structure):
@@ -193,6 +205,7 @@ SYMBOLS = {
     "vc_snapshot_destroy": (None, [_vp]),
     "vc_snapshot_upload": (C.c_int, [_vp, C.POINTER(vc_nodes), C.POINTER(vc_tasks), C.POINTER(vc_classes),
                                      C.POINTER(vc_jobs), C.POINTER(vc_queues), C.POINTER(vc_conf)]),
+    "vc_snapshot_set_topology": (C.c_int, [_vp, C.POINTER(vc_hypernodes)]),
     "vc_snapshot_set_shard": (C.c_int, [_vp, C.c_int32, C.c_int32]),
     "vc_allocate_run": (C.c_int, [_vp, C.POINTER(_vp)]),
     "vc_score_matrix": (C.c_int, [_vp, _u64p, _dp, _dp, _i32p]),

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import re
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Tuple
+from typing import Sequence, Dict, List, Optional, Tuple
 
 # ---------------------------------------------------------------------------------------
 # resource.Quantity (k8s.io/apimachinery/pkg/api/resource): only Value()/MilliValue()
@@ -222,6 +222,19 @@ class Queue:
     priority: int = 0
     state: str = "Open"
     creation_ts: int = 0
+
+
+@dataclass
+class HyperNode:
+    """topology.volcano.sh HyperNode (api.BuildHyperNode, api/test_utils.go): members are (name, type) with
+    type "Node" or "HyperNode"; only the exact-match selector is modelled."""
+    name: str
+    tier: int
+    members: List[Tuple[str, str]] = field(default_factory=list)
+
+
+def BuildHyperNode(name: str, tier: int, members: Sequence[Tuple[str, str]]) -> HyperNode:
+    return HyperNode(name=name, tier=tier, members=[(m[0], m[1]) for m in members])
 
 
 TASK_SPEC_KEY = "volcano.sh/task-spec"  # batch.TaskSpecKey

@@ -79,6 +79,15 @@ struct K2Params {
   const uint32_t *g_has;
   const int32_t *g_class;
   uint4 *ring;            // publication ring, RING_DEPTH entries of RING_STRIDE uint4
+  // ---- network-topology-aware (general kernel only) ----
+  int hn_H, hn_cap;           // hypernodes; capacity of a CTA's local hypernode list
+  const int32_t *hn_member;   // [L][N] global hypernode index per tier level, -1 none
+  const int32_t *hn_slot;     // [L][N] position of that hypernode in the owning CTA's local list, -1 none
+  const int32_t *cta_hn_off;  // [n_cta+1] local lists: the hypernodes that hold at least one node of the CTA
+  const int32_t *cta_hn;
+  const double *hn_alloc;     // [R][H] hyperNodeResourceCache allocatable
+  const double *hn_used0;     // [R][H] ... used at session open
+  double *rep_hn_used;        // [n_cta][R][hn_cap] per-CTA live copy of `used` for the CTA's local hypernodes
 };
 
 // ---------------------------------------------------------------------------------------
@@ -447,6 +456,31 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   sn.nerr = reinterpret_cast<unsigned long long *>(sp); sp += (size_t)cap * 8;
   sn.max_tasks = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
   sn.pod_count = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
+  // network-topology-aware: per-step binpack score of each local hypernode for the task under evaluation
+  sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 7) & ~(uintptr_t)7);
+  double *hn_score = reinterpret_cast<double *>(sp);
+  const int hn_cap = p.hn_cap;
+  const int hn_base = c.nta_on ? p.cta_hn_off[cta] : 0;
+  const int hn_n = c.nta_on ? p.cta_hn_off[cta + 1] - hn_base : 0;
+  double *hn_used = c.nta_on ? p.rep_hn_used + (size_t)cta * R * hn_cap : nullptr;
+  for (int k = tid; k < hn_n; k += blockDim.x) {
+    const int h = p.cta_hn[hn_base + k];
+    for (int d = 0; d < R; ++d) hn_used[d * hn_cap + k] = p.hn_used0[(size_t)d * p.hn_H + h];
+  }
+  // event handlers of the plugin (network_topology_aware.go:374-399): used += / -= Resreq for every hypernode
+  // whose RealNodesSet holds the node; each CTA maintains the entries of its own local list
+  auto hn_account = [&](int node, const double *req, size_t req_stride, uint32_t has, double sign) {
+    for (int k = tid; k < hn_n; k += blockDim.x) {
+      const int h = p.cta_hn[hn_base + k];
+      bool hit = false;
+      for (int l = 0; l < c.nta_L; ++l) hit = hit || p.hn_member[(size_t)l * N + node] == h;
+      if (!hit) continue;
+      for (int d = 0; d < R; ++d) {
+        if (d >= 2 && !(has & (1u << d))) continue;
+        hn_used[d * hn_cap + k] += sign * req[d * req_stride];
+      }
+    }
+  };
 
   for (int i = tid; i < nmine; i += blockDim.x) {
     const int n = nbase + i;
@@ -697,6 +731,15 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       // max soft-taint count of the candidate set; pass 1 = scores.
       constexpr int n_pass = SOFT ? 2 : 1;
       int g_soft0 = 0, g_soft1 = 0;
+      if (c.nta_on) {  // getPodHyperNodeBinPackingScore(task, hypernode) for the CTA's hypernodes
+        for (int k = tid; k < hn_n; k += blockDim.x) {
+          const int h = p.cta_hn[hn_base + k];
+          hn_score[k] = hn_binpack_score(
+              c, R, trec, [&](int d) { return hn_used[d * hn_cap + k]; },
+              [&](int d) { return p.hn_alloc[(size_t)d * p.hn_H + h]; });
+        }
+        __syncthreads();
+      }
       for (int pass = 0; pass < n_pass; ++pass) {
         Local mine;
         local_init(mine);
@@ -719,8 +762,14 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
           if (SOFT && pass == 0) continue;
           double order = 0.0;
           bool has_order = node_order(c, R, K, trec, nv, cs, &order);
-          double sc = total_score(c, has_order, order, soft, c0 ? g_soft0 : g_soft1);
           const int n = nbase + i;
+          double nta = 0.0;
+          if (c.nta_on)
+            nta = nta_node_score(c, [&](int l) {
+              const int k = p.hn_slot[(size_t)l * N + n];
+              return k < 0 ? 1.0 : hn_score[k];
+            });
+          double sc = total_score(c, has_order, order, soft, c0 ? g_soft0 : g_soft1, nta);
           if (c0) {
             if (mine.node[0] < 0 || better(sc, n, mine.score[0], mine.node[0])) { mine.score[0] = sc; mine.node[0] = n; }
           } else {
@@ -799,6 +848,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
           }
         }
       }
+      if (c.nta_on) hn_account(best, trec.req, 1, trec.has, 1.0);
       __syncthreads();
       if (tid == 0) {
         // job.UpdateTaskStatus (job_info.go:651-660) + event handlers (drf.go:391-418, proportion.go:475-497)
@@ -835,6 +885,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       // stmt.Discard(): undo in reverse order (statement.go:357-381)
       for (int k = n_ops - 1; k >= 0; --k) {
         const int ot = ops[k * 3 + 0], on = ops[k * 3 + 1], okind = ops[k * 3 + 2];
+        if (c.nta_on) hn_account(on, p.req + ot, (size_t)T, p.req_has[ot], -1.0);
         if (on >= nbase && on < nbase + nmine && ((on - nbase) % blockDim.x) == tid) {
           const int i = on - nbase;
           for (int d = 0; d < R; ++d) {

@@ -38,6 +38,13 @@ struct DevConf {
   int batch_any;        // some BatchNodeOrderFn yields entries
   int has_future;       // any Releasing/Pipelined resource at open -> FutureIdle != Idle possible
   int soft_active;      // taint_batch && some node carries a PreferNoSchedule taint
+  // network-topology-aware, hypernode-level binpacking of pods without a network topology
+  int nta_on;           // plugin has EnabledNodeOrder and hypernode.binpack.normal-pod.enable
+  int nta_weight;
+  int nta_dim_weight[VC_MAX_DIMS];
+  int nta_L;            // tier levels min_tier..max_tier (cluster top hypernode included)
+  double tier_w[VC_MAX_TIERS];  // math.Pow(fading, tier-1), computed on the host
+  double tier_w_total;
 };
 
 struct DevDims {
@@ -179,9 +186,42 @@ __device__ __forceinline__ bool node_order(const DevConf &c, int R, int K, const
   return true;
 }
 
+// getPodHyperNodeBinPackingScore, plugins/network-topology-aware/network_topology_aware.go:498-539.
+// used(d) / alloc(d): the plugin's hyperNodeResourceCache entry of one hypernode.
+template <class FU, class FA>
+__device__ __forceinline__ double hn_binpack_score(const DevConf &c, int R, const TaskRec &t, FU used, FA alloc) {
+  double total_score = 0.0;
+  int total_weight = 0;
+  for (int d = 0; d < R; ++d) {
+    const double request = t.req[d];
+    if (d >= 2 && !(t.has & (1u << d))) continue;  // task.Resreq.ResourceNames()
+    if (!(request >= VC_MIN_RESOURCE)) continue;
+    const int w = c.nta_dim_weight[d];
+    if (w < 0) continue;
+    const double allocatable = alloc(d), u = used(d);
+    if (u + request > allocatable) return 0.0;
+    const double score = (u + request) / allocatable;
+    total_score += (double)w * score;
+    total_weight += w;
+  }
+  if (total_weight > 0) return total_score / (double)total_weight;
+  return 0.0;
+}
+// batchNodeOrderFnForNormalPods :462-496 + scaleFinalScore :758-764. tier_score(l): binpack score of the
+// hypernode holding the node at tier level l, FullScore (1.0) when none does.
+template <class FT>
+__device__ __forceinline__ double nta_node_score(const DevConf &c, FT tier_score) {
+  double total = 0.0;
+  for (int l = 0; l < c.nta_L; ++l) total += c.tier_w[l] * tier_score(l);
+  const double sc = total / c.tier_w_total;
+  return (double)VC_MAX_NODE_SCORE * (double)c.nta_weight * sc;
+}
+
 // Total of util.PrioritizeNodes for one node (scheduler_helper.go:117-129): 0.0 + order + batch,
-// batch = TaintToleration with DefaultNormalizeScore(reverse) over the scored node set.
-__device__ __forceinline__ double total_score(const DevConf &c, bool has_order, double order, int soft, int max_soft) {
+// batch = TaintToleration with DefaultNormalizeScore(reverse) over the scored node set, plus the
+// network-topology-aware entry `nta` (two addends: their plugin order does not matter).
+__device__ __forceinline__ double total_score(const DevConf &c, bool has_order, double order, int soft, int max_soft,
+                                              double nta = 0.0) {
   double score = 0.0;
   if (has_order) score += order;
   if (c.batch_any) {
@@ -194,6 +234,7 @@ __device__ __forceinline__ double total_score(const DevConf &c, bool has_order, 
       node_sc += (double)sc;
       b += node_sc;
     }
+    if (c.nta_on) b += nta;
     score += b;
   }
   return score;

@@ -174,6 +174,24 @@ inline void proportion_open(const vc_dims &d, const vc_jobs &jb, const vc_queues
   }
 }
 
+// math.Pow(x, n) of the Go runtime for a small non-negative integer n (src/math/pow.go: y == 0 -> 1,
+// y == 1 -> x, x == 0 -> 0, else binary exponentiation on the Frexp mantissa with the exponent carried
+// separately). network-topology-aware derives its tier weights with it (network_topology_aware.go:470-476).
+inline double go_pow_uint(double x, unsigned n) {
+  if (n == 0 || x == 1.0) return 1.0;
+  if (n == 1) return x;
+  if (x == 0.0) return 0.0;
+  int xe = 0, ae = 0;
+  double x1 = std::frexp(x, &xe), a1 = 1.0;
+  for (unsigned i = n; i != 0; i >>= 1) {
+    if (i & 1u) { a1 *= x1; ae += xe; }
+    x1 *= x1;
+    xe <<= 1;
+    if (x1 < 0.5) { x1 += x1; --xe; }
+  }
+  return std::ldexp(a1, ae);
+}
+
 inline bool has_plugin(const vc_conf &c, int id) {
   for (int i = 0; i < c.n_plugins; ++i) if (c.plugins[i].plugin == id) return true;
   return false;

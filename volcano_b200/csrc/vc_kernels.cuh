@@ -140,7 +140,26 @@ struct K1Params {
   double *best_score;   // [T]
   int32_t *best_node;   // [T]
   int mw32;             // 32-bit words per mask row
+  // network-topology-aware (hypernode binpacking of normal pods) on the opening snapshot
+  int hn_H;
+  const int32_t *hn_member;  // [L][N]
+  const double *hn_alloc;    // [R][H]
+  const double *hn_used;     // [R][H]
+  double *hn_score;          // [G][H] getPodHyperNodeBinPackingScore(group, hypernode)
 };
+
+// K1h: grid (ceil(H/128), G). One thread per (group, hypernode).
+__global__ void __launch_bounds__(128) k_hn_scores(K1Params p) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
+  if (h >= p.hn_H) return;
+  TaskRec t;
+  for (int d = 0; d < p.d.R; ++d) t.req[d] = p.g_req[(size_t)d * p.n_groups + g];
+  t.has = p.g_has[g];
+  const int H = p.hn_H;
+  p.hn_score[(size_t)g * H + h] = hn_binpack_score(
+      p.c, p.d.R, t, [&](int d) { return p.hn_used[(size_t)d * H + h]; }, [&](int d) { return p.hn_alloc[(size_t)d * H + h]; });
+}
 
 // K1a: grid (ceil(Nloc/256), G). One thread per (group, node): predicate, fit category, order score.
 __global__ void __launch_bounds__(256) k_group_eval(K1Params p) {
@@ -193,7 +212,15 @@ __device__ __forceinline__ bool k1_final(const K1Params &p, int g, int li, int n
   int cat = cw & 3;
   *feasible = cat != 2;
   if (cat == 2 || cat != chosen) { *score = 0.0; return false; }
-  *score = total_score(p.c, !(cw & 0x80), p.g_order[(size_t)g * nloc + li], klassN_word_soft, max_soft);
+  double nta = 0.0;
+  if (p.c.nta_on) {
+    const int n = p.d.node_begin + li;
+    nta = nta_node_score(p.c, [&](int l) {
+      const int h = p.hn_member[(size_t)l * p.d.N + n];
+      return h < 0 ? 1.0 : p.hn_score[(size_t)g * p.hn_H + h];
+    });
+  }
+  *score = total_score(p.c, !(cw & 0x80), p.g_order[(size_t)g * nloc + li], klassN_word_soft, max_soft, nta);
   return true;
 }
 

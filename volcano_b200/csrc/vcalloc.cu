@@ -118,6 +118,15 @@ struct vc_snapshot {
   bool fast = false;
   uint4 *ring = nullptr;
   int last_full = 0, last_incr = 0;
+  // ---- HyperNode tree (vc_snapshot_set_topology) ----
+  bool has_topo = false;
+  int hn_H = 1, hn_L = 1, hn_min_tier = 1, hn_cap = 1;
+  std::vector<int32_t> h_member;  // [L][N]
+  Slot<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn;
+  Slot<double> hn_alloc, hn_used0;
+  double *rep_hn_used = nullptr;
+  size_t rep_hn_used_count = 0;
+  double *hn_score = nullptr;  // dense pass [G][H]
   // ---- device-only buffers ----
   uint32_t *cstat = nullptr;
   double *w_idle = nullptr, *w_used = nullptr, *w_pip = nullptr, *w_kreq = nullptr, *w_knz = nullptr;  // working copies
@@ -202,7 +211,16 @@ int build_devconf(vc_snapshot *s, const vc_nodes *nd) {
   d.pred_predicates = vch::plugin_enabled(c, VC_PLUGIN_PREDICATES, VC_EN_PREDICATE);
   bool no = vch::plugin_enabled(c, VC_PLUGIN_NODEORDER, VC_EN_NODE_ORDER);
   d.taint_batch = no && c.w_taint_toleration != 0;
-  d.batch_any = no || vch::plugin_enabled(c, VC_PLUGIN_PREDICATES, VC_EN_NODE_ORDER);
+  d.nta_on = vch::plugin_enabled(c, VC_PLUGIN_NETWORK_TOPOLOGY_AWARE, VC_EN_NODE_ORDER) && c.nta_normal_pod_enable;
+  d.nta_weight = c.nta_weight;
+  for (int i = 0; i < VC_MAX_DIMS; ++i) d.nta_dim_weight[i] = c.nta_dim_weight[i];
+  d.nta_L = s->hn_L;
+  d.tier_w_total = 0.0;
+  for (int l = 0; l < s->hn_L; ++l) {  // tierWeights, network_topology_aware.go:469-476
+    d.tier_w[l] = vch::go_pow_uint(c.nta_fading, (unsigned)(s->hn_min_tier + l - 1));
+    d.tier_w_total += d.tier_w[l];
+  }
+  d.batch_any = no || vch::plugin_enabled(c, VC_PLUGIN_PREDICATES, VC_EN_NODE_ORDER) || d.nta_on;
   const size_t RN = (size_t)s->dims.n_dims * s->dims.n_nodes;
   int fut = 0;
   for (size_t i = 0; i < RN && !fut; ++i)
@@ -232,7 +250,8 @@ void choose_geometry(vc_snapshot *s) {
   s->npc = npc;
   s->block = block;
   const int R = s->dims.n_dims, K = s->dims.n_kdims;
-  s->fast = !s->dc.has_future && !s->dc.soft_active && R <= 8 && K <= VC_MAX_KDIMS && !getenv("VC_COMMIT_GENERIC");
+  // hypernode-level scores change for every node after every placement: per-step full sweeps (k_commit)
+  s->fast = !s->dc.has_future && !s->dc.soft_active && !s->dc.nta_on && R <= 8 && K <= VC_MAX_KDIMS && !getenv("VC_COMMIT_GENERIC");
   if (s->fast) {
     size_t rows = 3 * (size_t)R + 2 * (size_t)K + 2 + 1;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + ((sizeof(CtlFast) + 15) & ~(size_t)15) + rows * npc * 8 +
@@ -243,6 +262,7 @@ void choose_geometry(vc_snapshot *s) {
   } else {
     size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 + 4) + 64;
+    if (s->dc.nta_on) s->smem_bytes += (size_t)npc * s->hn_L * 8 + 16;  // hn_score: at most npc * L local hypernodes
   }
 }
 
@@ -315,7 +335,7 @@ void vc_snapshot_destroy(vc_snapshot *s) {
   if (!s) return;
   free_dense(s);
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
-                   s->rep_i32, s->rep_f64, s->rep_heap, s->mbox, s->ring, s->d_prof, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
+                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->hn_score, s->mbox, s->ring, s->d_prof, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
   for (void *p : dptrs) if (p) cudaFree(p);
   void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters};
   for (void *p : hptrs) if (p) cudaFreeHost(p);
@@ -324,6 +344,28 @@ void vc_snapshot_destroy(vc_snapshot *s) {
   if (s->ev2) cudaEventDestroy(s->ev2);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
+}
+
+int vc_snapshot_set_topology(vc_snapshot *s, const vc_hypernodes *topo) {
+  if (!s) return fail(VC_EINVAL, "null snapshot");
+  s->uploaded = false;
+  if (!topo || !topo->member) {  // no HyperNode objects: the cluster top hypernode alone (tier 1)
+    s->has_topo = false;
+    s->hn_H = s->hn_L = s->hn_min_tier = 1;
+    s->h_member.clear();
+    return VC_OK;
+  }
+  const int L = topo->max_tier - topo->min_tier + 1;
+  if (topo->n_hypernodes < 1 || L < 1 || L > VC_MAX_TIERS || topo->min_tier < 1)
+    return fail(VC_EINVAL, "hypernode table: %d hypernodes, tiers [%d,%d] (at most %d tiers, tier >= 1)", topo->n_hypernodes,
+                topo->min_tier, topo->max_tier, VC_MAX_TIERS);
+  const size_t N = s->dims.n_nodes;
+  for (size_t i = 0; i < (size_t)L * N; ++i)
+    if (topo->member[i] < -1 || topo->member[i] >= topo->n_hypernodes) return fail(VC_EINVAL, "hypernode index out of range");
+  s->has_topo = true;
+  s->hn_H = topo->n_hypernodes; s->hn_L = L; s->hn_min_tier = topo->min_tier;
+  s->h_member.assign(topo->member, topo->member + (size_t)L * N);
+  return VC_OK;
 }
 
 int vc_snapshot_set_shard(vc_snapshot *s, int32_t node_begin, int32_t node_end) {
@@ -623,6 +665,49 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     for (size_t d = 0; d < R && d < FAST_R; ++d) r.des[d] = q_des[d * Q + q];
   }
 
+  // network-topology-aware: hyperNodeResourceCache at open (network_topology_aware.go:106-125) and, for the
+  // commit kernel, the hypernodes each CTA's node slice belongs to
+  choose_geometry(s);
+  std::vector<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn;
+  std::vector<double> hn_alloc, hn_used0;
+  s->hn_cap = 1;
+  if (s->dc.nta_on) {
+    const size_t L = s->hn_L, H = s->hn_H;
+    if (s->has_topo) hn_member = s->h_member;
+    else hn_member.assign(L * N, 0);
+    hn_alloc.assign(R * H, 0.0);
+    hn_used0.assign(R * H, 0.0);
+    for (size_t l = 0; l < L; ++l)
+      for (size_t n = 0; n < N; ++n) {
+        const int h = hn_member[l * N + n];
+        if (h < 0) continue;
+        for (size_t d = 0; d < R; ++d) {
+          hn_alloc[d * H + h] += nd->allocatable[d * N + n];
+          hn_used0[d * H + h] += nd->used[d * N + n];
+        }
+      }
+    hn_slot.assign(L * N, -1);
+    cta_hn_off.assign(s->n_cta + 1, 0);
+    std::unordered_map<int, int> local;
+    for (int cta = 0; cta < s->n_cta; ++cta) {
+      local.clear();
+      const size_t nb = (size_t)cta * s->npc, ne = std::min(N, nb + (size_t)s->npc);
+      for (size_t n = nb; n < ne; ++n)
+        for (size_t l = 0; l < L; ++l) {
+          const int h = hn_member[l * N + n];
+          if (h < 0) continue;
+          auto it = local.find(h);
+          if (it == local.end()) {
+            it = local.emplace(h, (int)local.size()).first;
+            cta_hn.push_back(h);
+          }
+          hn_slot[l * N + n] = it->second;
+        }
+      cta_hn_off[cta + 1] = (int32_t)cta_hn.size();
+      s->hn_cap = std::max<int>(s->hn_cap, (int)local.size());
+    }
+  }
+
   // ---- plan + stage + one H2D copy ------------------------------------------------------
   for (int pass = 0; pass < 2; ++pass) {
     const bool plan = pass == 0;
@@ -667,6 +752,9 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     put(s, s->s_jstat, jstat.data(), J, plan); put(s, s->s_rstat, rstat.data(), NR, plan);
     put(s, s->s_qstat, qstat.data(), Q, plan);
     put(s, s->s_heap_off, heap_off.data(), Q + 1, plan);
+    put(s, s->hn_member, hn_member.data(), hn_member.size(), plan); put(s, s->hn_slot, hn_slot.data(), hn_slot.size(), plan);
+    put(s, s->cta_hn_off, cta_hn_off.data(), cta_hn_off.size(), plan); put(s, s->cta_hn, cta_hn.data(), cta_hn.size(), plan);
+    put(s, s->hn_alloc, hn_alloc.data(), hn_alloc.size(), plan); put(s, s->hn_used0, hn_used0.data(), hn_used0.size(), plan);
     if (plan) {
       size_t need = (s->in.used + 255) & ~(size_t)255;
       if (need > s->in.cap) {
@@ -695,7 +783,6 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   if ((rc = ensure(s->w_idle, R * N * 8)) || (rc = ensure(s->w_used, R * N * 8)) || (rc = ensure(s->w_pip, R * N * 8)) ||
       (rc = ensure(s->w_kreq, K * N * 8)) || (rc = ensure(s->w_knz, 2 * N * 8)) || (rc = ensure(s->w_pod_count, N * 4)))
     return rc;
-  choose_geometry(s);
   // K0
   K0Params k0;
   k0.d = s->dd; k0.c = s->dc;
@@ -766,6 +853,15 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
     CUDA_TRY(cudaMalloc(&s->rep_heap, std::max<size_t>(16, std::max<size_t>(heap_stride, 1) * G * sizeof(HeapKey))));
     s->rep_i32_stride = i32_stride; s->rep_f64_stride = f64_stride; s->rep_heap_stride = heap_stride;
   }
+  if (s->dc.nta_on) {
+    const size_t cnt = (size_t)G * R * s->hn_cap;
+    if (!s->rep_hn_used || s->rep_hn_used_count < cnt) {
+      if (s->rep_hn_used) cudaFree(s->rep_hn_used);
+      s->rep_hn_used = nullptr;
+      CUDA_TRY(cudaMalloc(&s->rep_hn_used, std::max<size_t>(16, cnt * 8)));
+      s->rep_hn_used_count = cnt;
+    }
+  }
   const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024;
   if (!s->mbox) CUDA_TRY(cudaMalloc(&s->mbox, mbox_bytes));
   if (!s->d_prof) CUDA_TRY(cudaMalloc(&s->d_prof, 16 * sizeof(long long)));
@@ -823,6 +919,11 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   p.tmeta = reinterpret_cast<const int4 *>(s->tmeta.d(s->in)); p.n_groups = s->n_groups;
   p.g_req = s->sg_req.d(s->in); p.g_kreq = s->sg_kreq.d(s->in); p.g_knz = s->sg_knz.d(s->in);
   p.g_has = s->sg_has.d(s->in); p.g_class = s->sg_class.d(s->in); p.ring = s->ring;
+
+  p.hn_H = s->hn_H; p.hn_cap = s->hn_cap;
+  p.hn_member = s->hn_member.d(s->in); p.hn_slot = s->hn_slot.d(s->in); p.cta_hn_off = s->cta_hn_off.d(s->in);
+  p.cta_hn = s->cta_hn.d(s->in); p.hn_alloc = s->hn_alloc.d(s->in); p.hn_used0 = s->hn_used0.d(s->in);
+  p.rep_hn_used = s->rep_hn_used;
 
   if (G > 1024) return fail(VC_EUNSUPPORTED, "too many CTAs");
   const void *kfn = s->fast ? (const void *)k_commit_fast : s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
@@ -947,6 +1048,11 @@ static int dense_prepare(vc_snapshot *s) {
   CUDA_TRY(cudaMalloc(&s->part_node, std::max<size_t>(16, G * (size_t)std::max(nparts, 1) * 4)));
   CUDA_TRY(cudaMalloc(&s->best_score, std::max<size_t>(16, T * 8)));
   CUDA_TRY(cudaMalloc(&s->best_node, std::max<size_t>(16, T * 4)));
+  if (s->dc.nta_on) {
+    if (s->hn_score) cudaFree(s->hn_score);
+    s->hn_score = nullptr;
+    CUDA_TRY(cudaMalloc(&s->hn_score, std::max<size_t>(16, G * (size_t)s->hn_H * 8)));
+  }
   s->mw32 = (int)(2 * ((N + 63) / 64));
   s->dense_ready = true;
   return VC_OK;
@@ -966,6 +1072,8 @@ static K1Params dense_params(vc_snapshot *s) {
   p.n_work = s->n_work; p.work_group = s->work_group; p.work_begin = s->work_begin; p.work_end = s->work_end;
   p.group_tasks = s->group_tasks; p.mask_out = s->mask_out; p.score_out = s->score_out;
   p.best_score = s->best_score; p.best_node = s->best_node; p.mw32 = s->mw32;
+  p.hn_H = s->hn_H; p.hn_member = s->hn_member.d(s->in); p.hn_alloc = s->hn_alloc.d(s->in);
+  p.hn_used = s->hn_used0.d(s->in); p.hn_score = s->hn_score;
   return p;
 }
 
@@ -980,6 +1088,11 @@ int vc_dense_begin(vc_snapshot *s) {
     dim3 grid((unsigned)((nloc + 255) / 256), (unsigned)s->n_groups);
     k_group_eval<<<grid, 256, 0, s->stream>>>(p);
     g_launches++;
+    if (s->dc.nta_on) {
+      dim3 hgrid((unsigned)((s->hn_H + 127) / 128), (unsigned)s->n_groups);
+      k_hn_scores<<<hgrid, 128, 0, s->stream>>>(p);
+      g_launches++;
+    }
     CUDA_TRY(cudaGetLastError());
   }
   return VC_OK;

@@ -81,6 +81,9 @@ class Engine:
             self.snap = snap
         s = self.snap
         n, t, c, j, q = s.nodes(), s.tasks(), s.classes(), s.jobs(), s.queues()
+        topo = s.topology()
+        if topo is not None:
+            _check(self.L.vc_snapshot_set_topology(self.h, C.byref(topo)))
         _check(self.L.vc_snapshot_upload(self.h, C.byref(n), C.byref(t), C.byref(c), C.byref(j), C.byref(q),
                                          C.byref(s.conf)))
         self._uploaded = True

@@ -17,7 +17,7 @@ import re
 import numpy as np
 
 from . import abi
-from .api import (Node, Pod, PodGroup, Queue, TASK_PRIORITY_ANNOTATION, allocated_status, get_task_role,
+from .api import (HyperNode, Node, Pod, PodGroup, Queue, TASK_PRIORITY_ANNOTATION, allocated_status, get_task_role,
                   get_task_status, pod_index_under_task, quantity_milli, quantity_value, Taint, Toleration,
                   NodeSelectorRequirement)
 
@@ -109,6 +109,13 @@ def build_conf(conf: SchedulerConf, dim_names: Sequence[str], kdim_names: Sequen
     # nodeorder defaults (plugins/nodeorder/nodeorder.go:131-171)
     c.w_least, c.w_most, c.w_balanced, c.w_node_affinity, c.w_taint_toleration = 1, 0, 1, 2, 3
     c.predicates_enable = abi.VC_PRED_NODE_AFFINITY | abi.VC_PRED_TAINT_TOLERATION
+    # network-topology-aware defaults (network_topology_aware.go:56-63)
+    c.nta_weight, c.nta_normal_pod_enable, c.nta_fading = 1, 1, 0.8
+    for d in range(abi.VC_MAX_DIMS):
+        c.nta_dim_weight[d] = -1
+    for d, name in enumerate(dim_names):
+        if name in ("cpu", "memory"):
+            c.nta_dim_weight[d] = 1
     for _, p in opts:
         a = p.arguments
         if p.name == "binpack":
@@ -135,6 +142,23 @@ def build_conf(conf: SchedulerConf, dim_names: Sequence[str], kdim_names: Sequen
             c.w_most = _get_int(a, "mostrequested.weight", 0)
             c.w_balanced = _get_int(a, "balancedresource.weight", 1)
             c.w_taint_toleration = _get_int(a, "tainttoleration.weight", 3)
+        elif p.name == "network-topology-aware":  # getPriorityWeight / getNormalPodConfig :155-219
+            def nonneg(v):
+                return 1 if v < 0 else v
+            c.nta_weight = nonneg(_get_int(a, "weight", 1))
+            weights = {}
+            for r in str(a.get("hypernode.binpack.resources", "") or "").split(","):
+                r = r.strip()
+                if r:
+                    weights[r] = nonneg(_get_int(a, "hypernode.binpack.resources." + r, 1))
+            weights["cpu"] = nonneg(_get_int(a, "hypernode.binpack.cpu", 1))      # getBinPackWeight: cpu / memory
+            weights["memory"] = nonneg(_get_int(a, "hypernode.binpack.memory", 1))  # never come from the map
+            for d, name in enumerate(dim_names):
+                c.nta_dim_weight[d] = weights.get(name, -1)
+            c.nta_normal_pod_enable = 1 if _get_bool(a, "hypernode.binpack.normal-pod.enable", True) else 0
+            fading = a.get("hypernode.binpack.normal-pod.fading", 0.8)
+            fading = float(fading) if isinstance(fading, (int, float)) and not isinstance(fading, bool) else 0.8
+            c.nta_fading = 0.8 if fading < 0 else fading
         elif p.name == "predicates":
             en = 0
             if _get_bool(a, "predicate.NodeAffinityEnable", True):
@@ -247,12 +271,22 @@ class Snapshot:
         self.q_request_has = np.zeros(Q, u4)
         self.q_allocated_has = np.zeros(Q, u4)
         self.conf: Optional[abi.vc_conf] = None
+        # HyperNode tree (None: no HyperNode objects in the session)
+        self.hn_names: List[str] = []
+        self.hn_min_tier = 1
+        self.hn_max_tier = 1
+        self.hn_member: Optional[np.ndarray] = None  # int32 [L][N]
         # names for humans / tests
         self.dim_names: List[str] = []
         self.node_names: List[str] = []
         self.task_keys: List[str] = []
         self.job_names: List[str] = []
         self.queue_names: List[str] = []
+
+    def topology(self) -> Optional[abi.vc_hypernodes]:
+        if self.hn_member is None:
+            return None
+        return abi.vc_hypernodes(len(self.hn_names), self.hn_min_tier, self.hn_max_tier, _ptr(self.hn_member, _I32))
 
     # ---- ctypes views ----------------------------------------------------------------
     def dims(self) -> abi.vc_dims:
@@ -388,9 +422,54 @@ def tdm_zones_active(arguments: Dict[str, object], now=None) -> Dict[str, bool]:
     return out
 
 
+CLUSTER_TOP_HYPERNODE = "<cluster-top-hypernode>"  # framework.ClusterTopHyperNode
+
+
+def encode_hypernodes(s: "Snapshot", hypernodes: Sequence[HyperNode]) -> None:
+    """ssn.HyperNodesSetByTier + ssn.RealNodesSet (framework/session.go:239-245) as a [tier level][node] table of
+    hypernode indices, with the cluster top hypernode of addClusterTopHyperNode (:285-313) appended: its tier
+    is one above the highest real tier and its RealNodesSet is the whole NodeList."""
+    by_name = {h.name: h for h in hypernodes}
+    nidx = {n: i for i, n in enumerate(s.node_names)}
+    real: Dict[str, set] = {}
+
+    def real_nodes(name, seen=()):
+        if name in real:
+            return real[name]
+        out = set()
+        for mname, mtype in by_name[name].members:
+            if mtype == "Node":
+                if mname in nidx:  # GetRealNodesByHyperNode keeps nodes of the snapshot only
+                    out.add(nidx[mname])
+            elif mname in by_name and mname not in seen:
+                out |= real_nodes(mname, seen + (name,))
+        real[name] = out
+        return out
+
+    top_tier = 1
+    for h in hypernodes:
+        real_nodes(h.name)
+        top_tier = max(top_tier, h.tier + 1)
+    names = sorted(by_name) + [CLUSTER_TOP_HYPERNODE]
+    tiers = {h.name: h.tier for h in hypernodes}
+    tiers[CLUSTER_TOP_HYPERNODE] = top_tier
+    real[CLUSTER_TOP_HYPERNODE] = set(range(len(s.node_names)))
+    s.hn_names = names
+    s.hn_min_tier = min(tiers.values())
+    s.hn_max_tier = top_tier
+    L = s.hn_max_tier - s.hn_min_tier + 1
+    if L > abi.VC_MAX_TIERS:
+        raise ValueError("too many hypernode tiers")
+    s.hn_member = np.full((L, len(s.node_names)), -1, np.int32)
+    for hi, name in reversed(list(enumerate(names))):  # lowest name wins where sets of one tier overlap
+        l = tiers[name] - s.hn_min_tier
+        for n in real[name]:
+            s.hn_member[l, n] = hi
+
+
 def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequence[PodGroup],
-                   queues: Sequence[Queue], conf: SchedulerConf, tdm_zone_active: Optional[Dict[str, bool]] = None
-                   ) -> Snapshot:
+                   queues: Sequence[Queue], conf: SchedulerConf, tdm_zone_active: Optional[Dict[str, bool]] = None,
+                   hypernodes: Optional[Sequence[HyperNode]] = None) -> Snapshot:
     # ---- dimensions: cpu, memory, then scalars sorted by name -------------------------------
     scalars = set()
     for n in nodes:
@@ -532,6 +611,8 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
                  pods_dim=pods_dim)
     s.dim_names = dim_names
     s.node_names = [n.name for n in nodes]
+    if hypernodes is not None:
+        encode_hypernodes(s, hypernodes)
     s.task_keys = [p.key for p in task_pods]
     s.job_names = job_ids
     s.queue_names = [q.name for q in queues]

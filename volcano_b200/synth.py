@@ -36,6 +36,8 @@ class SynthConfig:
     releasing_frac: float = 0.0  # fraction of nodes with Releasing resources (exercises the FutureIdle gradient)
     soft_taint_p: float = 0.0    # per-bit probability of PreferNoSchedule taints (normalising TaintToleration scorer)
     mixed_roles: bool = False    # two roles with different requests per job + TaskMinAvailable (role minima, error cache)
+    topology: Optional[tuple] = None  # HyperNode tree fan-outs below the single root, e.g. (32, 40): 32 tier-2 x 40 tier-1 each
+    topology_scatter: float = 0.0     # fraction of nodes assigned to a random leaf / left outside the tree (tests)
 
 
 CONFIGS = {
@@ -45,8 +47,12 @@ CONFIGS = {
     "cfg2": SynthConfig("cfg2", 10_000, 100_000, 1, "priority+gang+predicates+nodeorder+binpack"),
     # configs[2]: + DRF + proportion over 16 queues
     "cfg3": SynthConfig("cfg3", 10_000, 100_000, 16, "priority+gang+drf+predicates+proportion+nodeorder+binpack"),
-    # configs[3] shape (topology-aware scoring is a §8f 'next' row)
-    "cfg4": SynthConfig("cfg4", 50_000, 1_000_000, 16, "priority+gang+drf+predicates+proportion+nodeorder+binpack"),
+    # configs[3]: 3-tier HyperNode tree (root -> 32 -> 40 each -> ~39 nodes), network-topology-aware weight 10
+    # (hypernode-level binpacking of pods without a network topology; topology-constrained jobs are not generated)
+    "cfg4": SynthConfig("cfg4", 50_000, 1_000_000, 16,
+                        "priority+gang+drf+predicates+proportion+nodeorder+binpack+network-topology-aware", topology=(32, 40)),
+    # the same shape without the topology plugin (incremental commit kernel)
+    "cfg4_flat": SynthConfig("cfg4_flat", 50_000, 1_000_000, 16, "priority+gang+drf+predicates+proportion+nodeorder+binpack"),
     # small shapes for tests
     "tiny": SynthConfig("tiny", 64, 300, 3, "priority+gang+drf+predicates+proportion+nodeorder+binpack", n_classes=12),
     "small": SynthConfig("small", 700, 4000, 4, "priority+gang+drf+predicates+proportion+nodeorder+binpack", n_classes=24),
@@ -57,6 +63,14 @@ CONFIGS = {
                               soft_taint_p=0.08),
     "small_fut_soft": SynthConfig("small_fut_soft", 300, 1500, 4, "priority+gang+drf+predicates+proportion+nodeorder+binpack",
                                   n_classes=16, utilisation=0.99, min_util=0.88, releasing_frac=0.5, soft_taint_p=0.08),
+    "tiny_topo": SynthConfig("tiny_topo", 96, 400, 2, "priority+gang+drf+predicates+proportion+nodeorder+binpack+network-topology-aware",
+                             n_classes=8, topology=(2, 3), topology_scatter=0.1),
+    "small_topo": SynthConfig("small_topo", 600, 3000, 3, "priority+gang+predicates+nodeorder+binpack+network-topology-aware",
+                              n_classes=16, topology=(4, 6), topology_scatter=0.15),
+    "small_topo_fut_soft": SynthConfig("small_topo_fut_soft", 300, 1500, 3,
+                                       "priority+gang+drf+predicates+proportion+nodeorder+binpack+network-topology-aware",
+                                       n_classes=12, utilisation=0.99, min_util=0.88, releasing_frac=0.5, soft_taint_p=0.08,
+                                       topology=(3, 4), topology_scatter=0.1),
     "small_roles": SynthConfig("small_roles", 200, 1200, 2, "priority+gang+predicates+nodeorder+binpack", n_classes=8,
                                utilisation=0.85, mixed_roles=True),
 }
@@ -68,6 +82,9 @@ def scheduler_conf(cfg: SynthConfig) -> SchedulerConf:
         "binpack": {"binpack.weight": 10, "binpack.cpu": 5, "binpack.memory": 1,
                     "binpack.resources": "nvidia.com/gpu", "binpack.resources.nvidia.com/gpu": 2},
         "nodeorder": {},  # default weights: least 1, balanced 1, nodeaffinity 2, tainttoleration 3
+        "network-topology-aware": {"weight": 10, "hypernode.binpack.cpu": 5, "hypernode.binpack.memory": 1,
+                                   "hypernode.binpack.resources": "nvidia.com/gpu",
+                                   "hypernode.binpack.resources.nvidia.com/gpu": 2},
     }
     tier1 = [PluginOption.defaults(n, args.get(n)) for n in names if n in ("priority", "gang")]
     tier2 = [PluginOption.defaults(n, args.get(n)) for n in names if n not in ("priority", "gang")]
@@ -263,4 +280,32 @@ def make_snapshot(cfg: SynthConfig | str, seed: Optional[int] = None) -> Snapsho
         m = jq == qi
         s.q_request_has[qi] = np.bitwise_or.reduce(has[m]) if m.any() else 0
     s.conf = build_conf(scheduler_conf(cfg), DIMS, KDIMS)
+    if cfg.topology is not None:
+        _make_topology(s, cfg, rng)
     return s
+
+
+def _make_topology(s: Snapshot, cfg: SynthConfig, rng) -> None:
+    """HyperNode tree as the [tier level][node] membership table Session open derives (snapshot.encode_hypernodes):
+    tier 1 = leaf hypernodes over contiguous node blocks, tier 2 = their parents, tier 3 = one root, tier 4 = the
+    cluster top hypernode.  `topology_scatter` moves some nodes to a random leaf and leaves some outside the tree."""
+    N = s.N
+    n_mid, per_mid = cfg.topology
+    n_leaf = n_mid * per_mid
+    block = -(-N // n_leaf)
+    leaf = np.minimum(np.arange(N) // block, n_leaf - 1)
+    outside = np.zeros(N, bool)
+    if cfg.topology_scatter > 0:
+        r = rng.random(N)
+        moved = r < cfg.topology_scatter
+        leaf[moved] = rng.integers(0, n_leaf, int(moved.sum()))
+        outside = r > 1.0 - cfg.topology_scatter / 2
+    mid = leaf // per_mid
+    member = np.full((4, N), -1, np.int32)
+    member[0] = np.where(outside, -1, leaf)
+    member[1] = np.where(outside, -1, n_leaf + mid)
+    member[2] = np.where(outside, -1, n_leaf + n_mid)
+    member[3] = n_leaf + n_mid + 1
+    s.hn_names = [f"leaf-{i}" for i in range(n_leaf)] + [f"mid-{i}" for i in range(n_mid)] + ["root", "<cluster-top-hypernode>"]
+    s.hn_min_tier, s.hn_max_tier = 1, 4
+    s.hn_member = np.ascontiguousarray(member)

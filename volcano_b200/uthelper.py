@@ -16,7 +16,7 @@ from typing import Callable, Dict, List, Optional, Sequence
 import numpy as np
 
 from . import abi
-from .api import Node, Pod, PodGroup, Queue
+from .api import HyperNode, Node, Pod, PodGroup, Queue
 from .snapshot import PluginOption, SchedulerConf, Snapshot, encode_cluster
 
 
@@ -41,11 +41,12 @@ class TestCommonStruct:
     ExpectBindsNum: Optional[int] = None
     ExpectPipeLined: Optional[Dict[str, List[str]]] = None  # job -> node names
     TdmZoneActive: Optional[Dict[str, bool]] = None
+    HyperNodes: Optional[List[HyperNode]] = None  # HyperNodesMap of the reference harness
 
     def RegisterSession(self, tiers: Sequence[Sequence[PluginOption]], actions=("allocate",), **conf_kw) -> Snapshot:
         self.conf = SchedulerConf(tiers=[list(t) for t in tiers], actions=tuple(actions), **conf_kw)
         self.snap = encode_cluster(self.Nodes, self.Pods, self.PodGroups, self.Queues, self.conf,
-                                   tdm_zone_active=self.TdmZoneActive)
+                                   tdm_zone_active=self.TdmZoneActive, hypernodes=self.HyperNodes)
         return self.snap
 
     def Run(self, engine: Callable[[Snapshot], AllocateResult]) -> AllocateResult:
