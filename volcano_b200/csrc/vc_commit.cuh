@@ -799,6 +799,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
           }
           local_warp_reduce(l);
           const unsigned seq = S.seq + 1;
+          __syncwarp();  // every lane has read S.seq before lane 0 advances it below
           Local g = exchange<(FUT || SOFT)>(p, l, seq);
           if (lane == 0) {
             S.seq = seq;
