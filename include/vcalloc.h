@@ -253,6 +253,16 @@ typedef struct vc_hypernodes {
   int32_t max_tier;      /* max_tier - min_tier + 1 <= VC_MAX_TIERS */
   const int32_t *member; /* [max_tier-min_tier+1][N]: index in [0,H) of the hypernode of tier min_tier+l whose
                             RealNodesSet holds node n, -1 when no hypernode of that tier does */
+  const int32_t *tier;   /* [H] HyperNodeInfo.Tier() */
+  const int32_t *parent; /* [H] HyperNodeInfo.Parent as an index, -1 for the cluster top hypernode */
+  /* Jobs whose default subJob carries a soft-mode network topology (SubJobInfo.IsSoftTopologyMode,
+     api/sub_job_info.go:94-99): their tasks are scored by batchNodeOrderFnForNetworkAwarePods
+     (network_topology_aware.go:541-571). All four may be NULL when the session has none. */
+  const uint8_t *job_soft;          /* [J] 1 = soft-mode topology job */
+  const int32_t *job_allocated;     /* [J] subJob.AllocatedHyperNode at open as an index, -1 = "" */
+  const int32_t *job_placed_off;    /* [J+1] CSR over job_placed_node */
+  const int32_t *job_placed_node;   /* node index of every task of the job that carries a NodeName at open
+                                       (FindJobTaskNumOfHyperNode counts subJob.Tasks by NodeName) */
 } vc_hypernodes;
 
 /* ---- results ----------------------------------------------------------------------- */

@@ -319,7 +319,13 @@ struct Session {
   std::vector<double> hn_alloc, hn_used;  // [R][H]
   double tier_w[VC_MAX_TIERS] = {0};
   double tier_w_total = 0.0;
-  bool nta_on = false;  // plugin registered with EnabledNodeOrder and normal-pod binpacking enabled
+  bool nta_on = false;      // plugin registered with EnabledNodeOrder and normal-pod binpacking enabled
+  bool nta_plugin = false;  // plugin registered with EnabledNodeOrder
+  std::vector<int32_t> hn_tier, hn_parent;     // [H]
+  std::vector<uint8_t> job_soft;               // [J] default subJob in soft topology mode
+  std::vector<int32_t> job_alloc_hn;           // [J] subJob.AllocatedHyperNode (-1 = "")
+  std::vector<std::vector<int32_t>> job_placed;  // [J] node of every task of the job that carries a NodeName
+  int task_alloc_hn = -1;                      // task.JobAllocatedHyperNode of the task being scored
   // results
   std::vector<vc_decision> decisions;
   std::vector<vc_visit> visits;
@@ -638,16 +644,27 @@ double go_pow_uint(double x, unsigned n) {
 }
 // hyperNodesTier.init :97-104, initHyperNodeResourceCache :106-125, tier weights :469-476
 void nta_init(Session &s, const vc_hypernodes *topo) {
-  s.nta_on = false;
+  s.nta_on = s.nta_plugin = false;
   for (int i = 0; i < s.conf.n_plugins; ++i)
-    if (s.conf.plugins[i].plugin == VC_PLUGIN_NETWORK_TOPOLOGY_AWARE && (s.conf.plugins[i].enabled & VC_EN_NODE_ORDER) &&
-        s.conf.nta_normal_pod_enable)
-      s.nta_on = true;
+    if (s.conf.plugins[i].plugin == VC_PLUGIN_NETWORK_TOPOLOGY_AWARE && (s.conf.plugins[i].enabled & VC_EN_NODE_ORDER)) {
+      s.nta_plugin = true;
+      if (s.conf.nta_normal_pod_enable) s.nta_on = true;
+    }
+  s.job_soft.assign(s.J, 0);
+  s.job_alloc_hn.assign(s.J, -1);
+  s.job_placed.assign(s.J, {});
   if (topo && topo->member) {
     s.hn_H = topo->n_hypernodes;
     s.hn_min_tier = topo->min_tier;
     s.hn_L = topo->max_tier - topo->min_tier + 1;
     s.hn_member.assign(topo->member, topo->member + (size_t)s.hn_L * s.N);
+    if (topo->tier) s.hn_tier.assign(topo->tier, topo->tier + s.hn_H);
+    if (topo->parent) s.hn_parent.assign(topo->parent, topo->parent + s.hn_H);
+    if (topo->job_soft) s.job_soft.assign(topo->job_soft, topo->job_soft + s.J);
+    if (topo->job_allocated) s.job_alloc_hn.assign(topo->job_allocated, topo->job_allocated + s.J);
+    if (topo->job_placed_off && topo->job_placed_node)
+      for (int j = 0; j < s.J; ++j)
+        s.job_placed[j].assign(topo->job_placed_node + topo->job_placed_off[j], topo->job_placed_node + topo->job_placed_off[j + 1]);
   } else {  // no HyperNode objects: only the cluster top hypernode, tier 1 (framework/session.go:285-313)
     s.hn_H = 1; s.hn_min_tier = 1; s.hn_L = 1;
     s.hn_member.assign((size_t)s.N, 0);
@@ -711,6 +728,74 @@ void nta_account(Session &s, int t, int n, double sign) {  // event handlers :37
     }
   }
 }
+
+// ---- pods WITH a (soft-mode) network topology: batchNodeOrderFnForNetworkAwarePods :541-571 ----
+// HyperNodeInfoMap.GetAncestors (api/hyper_node_info.go:737-758): the hypernode, then its parents upwards
+std::vector<int> hn_ancestors(const Session &s, int h) {
+  std::vector<int> out;
+  while (h >= 0 && std::find(out.begin(), out.end(), h) == out.end()) {
+    out.push_back(h);
+    h = h < (int)s.hn_parent.size() ? s.hn_parent[h] : -1;
+  }
+  return out;
+}
+// GetLCAHyperNode(hypernode, jobHyperNode), api/hyper_node_info.go:787-809
+int hn_lca(const Session &s, int hypernode, int job_hypernode) {
+  if (hypernode < 0) return job_hypernode;
+  if (job_hypernode < 0) return hypernode;
+  std::vector<int> a = hn_ancestors(s, hypernode);
+  for (int x : hn_ancestors(s, job_hypernode))
+    if (std::find(a.begin(), a.end(), x) != a.end()) return x;
+  return -1;
+}
+// util.FindHyperNodeForNode (util/scheduler_helper.go:361-376): only hypernodes of the LOWEST tier are searched
+int find_hypernode_for_node(const Session &s, int n) { return s.hn_member[n]; }
+// networkTopologyAwareScore :716-733 + scoreHyperNodeWithTier :747-756
+double topo_score(const Session &s, int hn, int allocated) {
+  if (hn < 0 || allocated < 0) return 0.0;
+  if (hn == allocated) return 1.0;
+  int lca = hn_lca(s, hn, allocated);
+  if (lca < 0) return 0.0;
+  const int min_tier = s.hn_min_tier, max_tier = s.hn_min_tier + s.hn_L - 1, tier = s.hn_tier[lca];
+  if (min_tier == max_tier) return 1.0;
+  if (min_tier <= tier && tier <= max_tier) return (double)(max_tier - tier) / (double)(max_tier - min_tier);
+  return 0.0;
+}
+// scoreWithTaskNum :737-745 -> util.FindJobTaskNumOfHyperNode (scheduler_helper.go:379-393)
+double task_num_score(const Session &s, int j, int hn) {
+  int cnt = 0;
+  if (hn >= 0)
+    for (int m : s.job_placed[j])
+      if (s.hn_member[m] == hn) ++cnt;
+  const int all = s.j_ntasks[j];
+  return all > 0 ? (double)cnt / (double)all : 0.0;
+}
+// the map batchNodeOrderFnForNetworkAwarePods returns for `nodes` (before scaleFinalScore); has[i] = entry present
+void topo_node_scores(const Session &s, int t, const std::vector<int> &nodes, std::vector<double> &out,
+                      std::vector<uint8_t> &has) {
+  out.assign(nodes.size(), 0.0);
+  has.assign(nodes.size(), 0);
+  const int allocated = s.task_alloc_hn;
+  if (allocated < 0) return;  // :544-547: no scores at all
+  double max_score = -1.0;
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    out[i] = topo_score(s, find_hypernode_for_node(s, nodes[i]), allocated);
+    has[i] = 1;
+    if (out[i] >= max_score) max_score = out[i];
+  }
+  size_t at_max = 0;
+  for (size_t i = 0; i < nodes.size(); ++i) at_max += out[i] == max_score;
+  if (at_max > 1)
+    for (size_t i = 0; i < nodes.size(); ++i)
+      if (out[i] == max_score) out[i] += task_num_score(s, s.t_job[t], find_hypernode_for_node(s, nodes[i]));
+}
+// allocate.getNewAllocatedHyperNode, actions/allocate/allocate.go:697-707
+int new_allocated_hypernode(const Session &s, int best_node, int allocated) {
+  int hn = find_hypernode_for_node(s, best_node);
+  if (hn >= 0) return allocated < 0 ? hn : hn_lca(s, hn, allocated);
+  return allocated;
+}
+bool topo_task(const Session &s, int t) { return s.nta_plugin && s.job_soft[s.t_job[t]]; }
 
 void on_allocate_event(Session &s, int t, int n) {
   int j = s.t_job[t];
@@ -987,7 +1072,7 @@ bool batch_enabled(const Session &s) {  // does any BatchNodeOrderFn produce ent
     if ((p.enabled & VC_EN_NODE_ORDER) && (p.plugin == VC_PLUGIN_NODEORDER || p.plugin == VC_PLUGIN_PREDICATES))
       return true;
   }
-  return s.nta_on;
+  return s.nta_plugin;
 }
 bool taint_batch_enabled(const Session &s) {
   if (s.conf.w_taint_toleration == 0) return false;
@@ -1019,6 +1104,10 @@ int prioritize_and_select(Session &s, int t, const std::vector<int> &nodes, doub
   if (taint)
     for (int i = 0; i < m; ++i) max_count = std::max(max_count, tcount[i]);
   const bool batch = batch_enabled(s);
+  const bool topo = topo_task(s, t);
+  std::vector<double> topo_sc;
+  std::vector<uint8_t> topo_has;
+  if (topo) topo_node_scores(s, t, nodes, topo_sc, topo_has);
   int best = -1;
   double best_sc = -std::numeric_limits<double>::infinity();
   if (scores_out) scores_out->assign(m, 0.0);
@@ -1034,7 +1123,12 @@ int prioritize_and_select(Session &s, int t, const std::vector<int> &nodes, doub
         node_sc += (double)sc;  // nodeorder.go:369-381
         b += node_sc;
       }
-      if (s.nta_on) b += nta_node_score(s, t, nodes[i]);  // two addends: plugin order is immaterial
+      // network-topology-aware BatchNodeOrderFn :422-460 (two addends: plugin order is immaterial)
+      if (topo) {
+        if (topo_has[i]) b += (double)kMaxNodeScore * (double)s.conf.nta_weight * topo_sc[i];
+      } else if (s.nta_on) {
+        b += nta_node_score(s, t, nodes[i]);
+      }
       score += b;
     }
     if (scores_out) (*scores_out)[i] = score;
@@ -1076,6 +1170,7 @@ void stmt_allocate(Session &s, std::vector<Op> &ops, int t, int n, double score)
     at(s.used, d, s.N, n) += at(s.req, d, s.T, t);
   }
   on_allocate_event(s, t, n);
+  s.job_placed[j].push_back(n);  // task.NodeName = hostname
   ops.push_back({t, n, VC_OP_ALLOCATE, score});
 }
 void stmt_pipeline(Session &s, std::vector<Op> &ops, int t, int n, double score) {  // :146-200
@@ -1087,6 +1182,7 @@ void stmt_pipeline(Session &s, std::vector<Op> &ops, int t, int n, double score)
   s.t_node[t] = n;
   for (int d = 0; d < s.R; ++d) at(s.pip, d, s.N, n) += at(s.req, d, s.T, t);  // node_info.go:457-458
   on_allocate_event(s, t, n);
+  s.job_placed[j].push_back(n);
   ops.push_back({t, n, VC_OP_PIPELINE, score});
 }
 void stmt_discard(Session &s, std::vector<Op> &ops) {  // :357-381
@@ -1110,6 +1206,7 @@ void stmt_discard(Session &s, std::vector<Op> &ops) {  // :357-381
       for (int d = 0; d < s.R; ++d) at(s.pip, d, s.N, n) -= at(s.req, d, s.T, t);
     }
     on_deallocate_event(s, t, n);
+    s.job_placed[j].pop_back();  // task.NodeName = "" (ops are undone in reverse order)
     s.t_node[t] = -1;
   }
   ops.clear();
@@ -1229,6 +1326,7 @@ bool allocate_resources_for_tasks(Session &s, int j, GoHeap &tasks, std::vector<
   ph.node_err.resize(nroles);
   ph.exists.assign(nroles, 0);
   std::vector<int> feasible;
+  int allocated_hn = s.job_alloc_hn[j];  // allocatedHyperNode := subJob.AllocatedHyperNode, allocate.go:572
   while (!tasks.empty()) {
     int t = tasks.pop();
     if (!allocatable(s, q, t)) continue;
@@ -1247,14 +1345,19 @@ bool allocate_resources_for_tasks(Session &s, int j, GoHeap &tasks, std::vector<
       break;
     }
     double score = 0;
+    s.task_alloc_hn = s.job_soft[j] ? allocated_hn : -1;  // task.JobAllocatedHyperNode, allocate.go:658-660
     int best = prioritize_nodes(s, t, feasible, &score);
     if (best < 0) continue;
     // alloc.allocateResourcesForTask, allocate.go:780-814
     if (fits_idle(s, t, best)) stmt_allocate(s, ops, t, best, score);
     else if (fits_future_idle(s, t, best)) stmt_pipeline(s, ops, t, best, score);
+    if (s.job_soft[j]) allocated_hn = new_allocated_hypernode(s, best, allocated_hn);  // :672-674
     if (job_ready(s, j)) break;  // ssn.SubJobReady == ssn.JobReady without a subjob policy (:369-372)
   }
-  if (job_ready(s, j)) return true;
+  if (job_ready(s, j)) {
+    if (s.job_soft[j]) s.job_alloc_hn[j] = allocated_hn;  // :681-686
+    return true;
+  }
   if (job_pipelined(s, j)) return true;
   stmt_discard(s, ops);
   return false;
@@ -1344,6 +1447,7 @@ void score_matrix(Session &s, uint64_t *mask_out, double *score_out, double *bes
     double bs = 0;
     int bn = -1;
     if (!cand.empty()) {
+      s.task_alloc_hn = s.job_soft[s.t_job[t]] ? s.job_alloc_hn[s.t_job[t]] : -1;
       bn = prioritize_and_select(s, t, cand, &bs, &sc);
       if (score_out)
         for (size_t i = 0; i < cand.size(); ++i) score_out[(size_t)t * N + cand[i]] = sc[i];
@@ -1476,6 +1580,18 @@ double vco_nta_node_score(void *h, int t, int n) {
   Session &s = *(Session *)h;
   return s.nta_on ? nta_node_score(s, t, n) : 0.0;
 }
+// BatchNodeOrderFn of the plugin for a pod WITH a network topology over `nodes` (scaled); out[i] = 0 when
+// the returned map has no entry for the node
+void vco_nta_topo_scores(void *h, int t, int allocated_hn, const int32_t *nodes, int n_nodes, double *out) {
+  Session &s = *(Session *)h;
+  std::vector<int> nv(nodes, nodes + n_nodes);
+  std::vector<double> sc;
+  std::vector<uint8_t> has;
+  s.task_alloc_hn = allocated_hn;
+  topo_node_scores(s, t, nv, sc, has);
+  for (int i = 0; i < n_nodes; ++i) out[i] = has[i] ? (double)kMaxNodeScore * (double)s.conf.nta_weight * sc[i] : 0.0;
+}
+int vco_job_allocated_hypernode(void *h, int j) { return ((Session *)h)->job_alloc_hn[j]; }
 double vco_go_pow_uint(double x, unsigned n) { return go_pow_uint(x, n); }
 void vco_score_matrix(void *h, uint64_t *mask_out, double *score_out, double *best_score, int32_t *best_node) {
   score_matrix(*(Session *)h, mask_out, score_out, best_score, best_node);

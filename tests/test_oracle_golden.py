@@ -193,3 +193,23 @@ def test_go_pow_small_integer_exponents():
     assert L.vco_go_pow_uint(0.8, 2) == 0.8 * 0.8
     assert L.vco_go_pow_uint(0.8, 3) == 0.8 * (0.8 * 0.8)
     assert abs(sum(L.vco_go_pow_uint(0.8, k) for k in range(4)) - 2.952) < 1e-12
+
+
+@pytest.mark.parametrize("name,kind,allocated,weight,running,score_nodes,expected", G.NTA_SOFT_CASES,
+                         ids=[c[0][:40] for c in G.NTA_SOFT_CASES])
+def test_nta_soft_topology_node_scores(name, kind, allocated, weight, running, score_nodes, expected):
+    """network_topology_aware_test.go:1072-1992 TestNetworkTopologyAwareNodeScore_Soft."""
+    tc = G.nta_soft_case(kind, allocated, running)
+    snap = tc.RegisterSession(G.nta_tiers({"weight": weight}))
+    assert snap.hn_job_soft[0] == 1
+    o = OracleSession(snap)
+    t = snap.task_keys.index("c1/pending")
+    nodes = np.array([snap.node_names.index(n) for n in score_nodes], np.int32)
+    out = np.zeros(len(nodes))
+    a = snap.hn_names.index(allocated) if allocated else -1
+    assert snap.hn_job_allocated[0] == a
+    pyoracle.lib().vco_nta_topo_scores(o.h, t, a, nodes.ctypes.data_as(pyoracle._i32p), len(nodes),
+                                       out.ctypes.data_as(pyoracle._dp))
+    o.close()
+    for n, got in zip(score_nodes, out):
+        assert abs(got - expected[n]) <= G.NTA_EPS, (n, got)

@@ -177,7 +177,9 @@ class vc_conf(C.Structure):
 
 class vc_hypernodes(C.Structure):
     _fields_ = [("n_hypernodes", C.c_int32), ("min_tier", C.c_int32), ("max_tier", C.c_int32),
-                ("member", C.POINTER(C.c_int32))]
+                ("member", C.POINTER(C.c_int32)), ("tier", C.POINTER(C.c_int32)), ("parent", C.POINTER(C.c_int32)),
+                ("job_soft", C.POINTER(C.c_uint8)), ("job_allocated", C.POINTER(C.c_int32)),
+                ("job_placed_off", C.POINTER(C.c_int32)), ("job_placed_node", C.POINTER(C.c_int32))]
 
 
 class vc_decision(C.Structure):

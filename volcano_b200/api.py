@@ -211,6 +211,12 @@ class PodGroup:
     creation_ts: int = 0
     preemptable: bool = False
     unsupported: bool = False  # hard network topology / subGroupPolicy
+    network_topology_mode: str = ""  # "" | "soft" | "hard" (Spec.NetworkTopology.Mode)
+    allocated_hypernode: str = ""    # volcano.sh/job-allocated-hypernode: AllocatedHyperNode carried into the session
+
+    def __post_init__(self):
+        if self.network_topology_mode == "hard":
+            self.unsupported = True
 
 
 @dataclass
@@ -253,6 +259,16 @@ def BuildPod(namespace, name, node_name, phase, req, group_name, labels=None, se
 def BuildPodGroup(name, ns, queue, min_member, task_min_member=None, phase="Inqueue") -> PodGroup:
     return PodGroup(name=name, namespace=ns, queue=queue, min_member=min_member,
                     min_task_member=dict(task_min_member) if task_min_member else None, phase=phase)
+
+
+def BuildPodGroupWithNetWorkTopologies(name, ns, hypernode_name, queue, min_member, task_min_member, phase, mode,
+                                       highest_tier_allowed) -> PodGroup:
+    """util/test_utils.go:393-402."""
+    pg = BuildPodGroup(name, ns, queue, min_member, task_min_member, phase)
+    pg.network_topology_mode = mode
+    pg.allocated_hypernode = hypernode_name
+    pg.__post_init__()
+    return pg
 
 
 def BuildQueue(name, weight, cap=None) -> Queue:

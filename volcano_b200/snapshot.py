@@ -276,6 +276,12 @@ class Snapshot:
         self.hn_min_tier = 1
         self.hn_max_tier = 1
         self.hn_member: Optional[np.ndarray] = None  # int32 [L][N]
+        self.hn_tier: Optional[np.ndarray] = None
+        self.hn_parent: Optional[np.ndarray] = None
+        self.hn_job_soft: Optional[np.ndarray] = None
+        self.hn_job_allocated: Optional[np.ndarray] = None
+        self.hn_job_placed_off: Optional[np.ndarray] = None
+        self.hn_job_placed_node: Optional[np.ndarray] = None
         # names for humans / tests
         self.dim_names: List[str] = []
         self.node_names: List[str] = []
@@ -286,7 +292,10 @@ class Snapshot:
     def topology(self) -> Optional[abi.vc_hypernodes]:
         if self.hn_member is None:
             return None
-        return abi.vc_hypernodes(len(self.hn_names), self.hn_min_tier, self.hn_max_tier, _ptr(self.hn_member, _I32))
+        return abi.vc_hypernodes(len(self.hn_names), self.hn_min_tier, self.hn_max_tier, _ptr(self.hn_member, _I32),
+                                 _ptr(self.hn_tier, _I32), _ptr(self.hn_parent, _I32), _ptr(self.hn_job_soft, _U8),
+                                 _ptr(self.hn_job_allocated, _I32), _ptr(self.hn_job_placed_off, _I32),
+                                 _ptr(self.hn_job_placed_node, _I32))
 
     # ---- ctypes views ----------------------------------------------------------------
     def dims(self) -> abi.vc_dims:
@@ -425,7 +434,8 @@ def tdm_zones_active(arguments: Dict[str, object], now=None) -> Dict[str, bool]:
 CLUSTER_TOP_HYPERNODE = "<cluster-top-hypernode>"  # framework.ClusterTopHyperNode
 
 
-def encode_hypernodes(s: "Snapshot", hypernodes: Sequence[HyperNode]) -> None:
+def encode_hypernodes(s: "Snapshot", hypernodes: Sequence[HyperNode], podgroups: Sequence[PodGroup] = (),
+                      job_pods: Sequence[Sequence[Pod]] = ()) -> None:
     """ssn.HyperNodesSetByTier + ssn.RealNodesSet (framework/session.go:239-245) as a [tier level][node] table of
     hypernode indices, with the cluster top hypernode of addClusterTopHyperNode (:285-313) appended: its tier
     is one above the highest real tier and its RealNodesSet is the whole NodeList."""
@@ -465,6 +475,40 @@ def encode_hypernodes(s: "Snapshot", hypernodes: Sequence[HyperNode]) -> None:
         l = tiers[name] - s.hn_min_tier
         for n in real[name]:
             s.hn_member[l, n] = hi
+    # HyperNodeInfo.Parent (api/hyper_node_info.go BuildHyperNodeCache; parentless ones hang under the cluster top)
+    hidx = {name: i for i, name in enumerate(names)}
+    s.hn_tier = np.array([tiers[n] for n in names], np.int32)
+    s.hn_parent = np.full(len(names), -1, np.int32)
+    for h in hypernodes:
+        for mname, mtype in h.members:
+            if mtype == "HyperNode" and mname in hidx:
+                s.hn_parent[hidx[mname]] = hidx[h.name]
+    for name in by_name:
+        if s.hn_parent[hidx[name]] < 0:
+            s.hn_parent[hidx[name]] = hidx[CLUSTER_TOP_HYPERNODE]
+    # soft-mode topology jobs: subJob.AllocatedHyperNode at open (carried annotation, else recovered from the
+    # nodes of the allocated tasks: lowest-tier hypernode holding all of them, framework/session.go:360-445)
+    J = len(podgroups)
+    s.hn_job_soft = np.zeros(J, np.uint8)
+    s.hn_job_allocated = np.full(J, -1, np.int32)
+    off, placed = [0], []
+    for j, pg in enumerate(podgroups):
+        nodes_j = [nidx[p.node_name] for p in job_pods[j] if p.node_name in nidx]
+        placed.extend(nodes_j)
+        off.append(len(placed))
+        if pg.network_topology_mode != "soft":
+            continue
+        s.hn_job_soft[j] = 1
+        alloc_nodes = [nidx[p.node_name] for p in job_pods[j]
+                       if p.node_name in nidx and allocated_status(get_task_status(p))]
+        if pg.allocated_hypernode in hidx and alloc_nodes:  # removeInvalidAllocatedHyperNode :317-356
+            s.hn_job_allocated[j] = hidx[pg.allocated_hypernode]
+        elif alloc_nodes:
+            cands = [hi for hi, name in enumerate(names) if all(n in real[name] for n in alloc_nodes)]
+            if cands:
+                s.hn_job_allocated[j] = min(cands, key=lambda hi: (s.hn_tier[hi], names[hi]))
+    s.hn_job_placed_off = np.array(off, np.int32)
+    s.hn_job_placed_node = np.array(placed if placed else [0], np.int32)
 
 
 def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequence[PodGroup],
@@ -611,8 +655,6 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
                  pods_dim=pods_dim)
     s.dim_names = dim_names
     s.node_names = [n.name for n in nodes]
-    if hypernodes is not None:
-        encode_hypernodes(s, hypernodes)
     s.task_keys = [p.key for p in task_pods]
     s.job_names = job_ids
     s.queue_names = [q.name for q in queues]
@@ -781,4 +823,6 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
                 s.q_request[:, qi] += v
                 s.q_request_has[qi] |= has
     s.conf = build_conf(conf, dim_names, KDIM_NAMES)
+    if hypernodes is not None:
+        encode_hypernodes(s, hypernodes, podgroups, job_pods)
     return s
