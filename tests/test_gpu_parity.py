@@ -94,6 +94,17 @@ def test_nta_goldens(case, args, expected, gpu):
     assert checked >= 6
 
 
+def test_nta_soft_topology_allocate(gpu, oracle_engine):
+    """Soft-mode topology job with an allocated hypernode and a running pod at open: LCA-tier scores, task-count
+    tie term and allocated-hypernode tracking inside the commit kernel, against the oracle."""
+    tc = G.nta_soft_allocate_case()
+    snap = tc.RegisterSession(G.nta_soft_allocate_tiers())
+    tc.Run(gpu.gpu_engine)
+    _assert_same(tc.result, oracle_engine(snap))
+    leaf = [tc.binds[f"c1/p{i}"].split("-")[0] for i in range(1, 7)]
+    assert leaf.count("s3") == 3 and leaf.count("s4") == 3, leaf
+
+
 @pytest.mark.parametrize("args,expected", G.BINPACK_CASES)
 def test_binpack_goldens(args, expected, gpu):
     """binpack_test.go:100-238: exact scores through the dense pass (only binpack registered)."""
@@ -124,7 +135,7 @@ ALLOC_CASES = [("tiny", 1), ("tiny", 2), ("tiny", 3), ("small", 1), ("cfg1", Non
                ("small_roles", None), ("small_roles", 5),
                # network-topology-aware: hypernode-level binpacking term, hyperNodeResourceCache updated per placement
                ("tiny_topo", None), ("tiny_topo", 3), ("small_topo", None), ("small_topo", 2),
-               ("small_topo_fut_soft", None), ("small_topo_fut_soft", 4)]
+               ("small_topo_fut_soft", None), ("small_topo_fut_soft", 4), ("small_topo_normal", None)]
 
 
 @pytest.mark.parametrize("cfg,seed", ALLOC_CASES)

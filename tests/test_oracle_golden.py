@@ -213,3 +213,12 @@ def test_nta_soft_topology_node_scores(name, kind, allocated, weight, running, s
     o.close()
     for n, got in zip(score_nodes, out):
         assert abs(got - expected[n]) <= G.NTA_EPS, (n, got)
+
+
+def test_nta_soft_topology_allocate(oracle_engine):
+    tc = G.nta_soft_allocate_case()
+    tc.RegisterSession(G.nta_soft_allocate_tiers())
+    tc.Run(oracle_engine)
+    leaf = {k: v.split("-")[0] for k, v in tc.binds.items()}
+    mine = [leaf[f"c1/p{i}"] for i in range(1, 7)]
+    assert mine.count("s3") == 3 and mine.count("s4") == 3, mine  # s3 has room for 3 more, then the sibling leaf

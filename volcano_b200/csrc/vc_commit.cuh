@@ -88,6 +88,20 @@ struct K2Params {
   const double *hn_alloc;     // [R][H] hyperNodeResourceCache allocatable
   const double *hn_used0;     // [R][H] ... used at session open
   double *rep_hn_used;        // [n_cta][R][hn_cap] per-CTA live copy of `used` for the CTA's local hypernodes
+  // pods with a soft-mode network topology (k_commit<.,.,true>)
+  int hn_min_tier;
+  const int32_t *hn_up;       // [L][H] ancestor of hypernode h (Parent chain, h included) at tier level l, -1 none
+  const int32_t *hn_tier;     // [H]
+  const int32_t *hn_parent;   // [H]
+  const int32_t *job_soft;    // [J] default subJob is in soft topology mode
+  const int32_t *job_alloc0;  // [J] subJob.AllocatedHyperNode at open, -1 = ""
+  const int32_t *placed_off;  // [J+1] capacity ranges of the per-job lists of nodes that hold a task of the job
+  const int32_t *placed0;     // lists at open
+  const int32_t *placed_n0;   // [J] their lengths
+  int32_t *rep_placed;        // [n_cta][placed_total] per-CTA live copies
+  size_t placed_total;
+  int topo_nval;              // distinct values networkTopologyAwareScore can take, ascending
+  double topo_val[VC_MAX_TIERS + 2];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -131,6 +145,10 @@ struct Ctl {
   // task under evaluation
   TaskRec trec;
   int task, role_local;
+  // soft-mode topology job: allocatedHyperNode of the visit (allocate.go:572), its Parent chain, list length
+  int job_soft, topo_A, n_anc, nplaced;
+  int anc[VC_MAX_TIERS + 2], anc_lvl[VC_MAX_TIERS + 2];
+  int tk[2];
   // exchange result
   int cnt[2], best_node[2], max_soft[2];
   double best_score[2];
@@ -173,12 +191,20 @@ struct Local {  // what one CTA (or one lane while folding) contributes per cate
   int node[2];
   int cnt[2];
   int soft[2];
+  int tk[2];  // topology pods: (1 + code of the best networkTopologyAwareScore) << 2 | min(nodes at that score, 2); 0 = none
 };
+__device__ __forceinline__ int tk_fold(int a, int b) {
+  const int ca = a >> 2, cb = b >> 2;
+  if (cb > ca) return b;
+  if (cb < ca) return a;
+  return (ca << 2) | min(2, (a & 3) + (b & 3));
+}
 __device__ __forceinline__ void local_init(Local &l) {
   l.score[0] = l.score[1] = 0.0;
   l.node[0] = l.node[1] = -1;
   l.cnt[0] = l.cnt[1] = 0;
   l.soft[0] = l.soft[1] = 0;
+  l.tk[0] = l.tk[1] = 0;
 }
 __device__ __forceinline__ void local_fold(Local &a, const Local &b) {
 #pragma unroll
@@ -189,6 +215,7 @@ __device__ __forceinline__ void local_fold(Local &a, const Local &b) {
     }
     a.cnt[k] += b.cnt[k];
     a.soft[k] = max(a.soft[k], b.soft[k]);
+    a.tk[k] = tk_fold(a.tk[k], b.tk[k]);
   }
 }
 __device__ __forceinline__ void local_warp_reduce(Local &l) {
@@ -201,6 +228,7 @@ __device__ __forceinline__ void local_warp_reduce(Local &l) {
       b.node[k] = __shfl_xor_sync(0xffffffffu, l.node[k], o);
       b.cnt[k] = __shfl_xor_sync(0xffffffffu, l.cnt[k], o);
       b.soft[k] = __shfl_xor_sync(0xffffffffu, l.soft[k], o);
+      b.tk[k] = __shfl_xor_sync(0xffffffffu, l.tk[k], o);
     }
     local_fold(l, b);
   }
@@ -213,7 +241,7 @@ __device__ __forceinline__ void local_warp_reduce(Local &l) {
 // carries its own sequence number, so readers validate each 16-byte unit on its own: no fence needed.
 //   FULL = false: one unit  {score0, node0, seq<<2 | min(cnt0,2)}            (no FutureIdle gradient, no
 //                                                                              normalising batch scorer)
-//   FULL = true : three units {score0,node0,seq} {score1,node1,seq} {cnt0,cnt1,soft0|soft1<<16,seq}
+//   FULL = true : three units {score0,node0,seq} {score1,node1,seq} {cnt0,cnt1,soft0|soft1<<8|tk0<<16|tk1<<24,seq}
 #define MBOX_STRIDE 16  // uint4 per slot = 256 bytes
 template <bool FULL>
 __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigned seq) {
@@ -228,7 +256,8 @@ __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigne
         v = make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)mine.node[lane], seq);
       } else {
         v = make_uint4((unsigned)mine.cnt[0], (unsigned)mine.cnt[1],
-                       (unsigned)mine.soft[0] | ((unsigned)mine.soft[1] << 16), seq);
+                       (unsigned)mine.soft[0] | ((unsigned)mine.soft[1] << 8) | ((unsigned)mine.tk[0] << 16) |
+                           ((unsigned)mine.tk[1] << 24), seq);
       }
       mbox_store(base + (size_t)blockIdx.x * MBOX_STRIDE + lane, v);
     }
@@ -267,7 +296,8 @@ __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigne
           o.score[1] = __longlong_as_double((long long)((unsigned long long)b.x | ((unsigned long long)b.y << 32)));
           o.node[1] = (int)b.z;
           o.cnt[0] = (int)c.x; o.cnt[1] = (int)c.y;
-          o.soft[0] = (int)(c.z & 0xffffu); o.soft[1] = (int)(c.z >> 16);
+          o.soft[0] = (int)(c.z & 0xffu); o.soft[1] = (int)((c.z >> 8) & 0xffu);
+          o.tk[0] = (int)((c.z >> 16) & 0xffu); o.tk[1] = (int)(c.z >> 24);
         } else {
           o.cnt[0] = (int)(a[k].w & 3u);
         }
@@ -432,8 +462,9 @@ extern __shared__ __align__(16) unsigned char k2_smem[];
     }                                                 \
   } while (0)
 
-template <bool FUT, bool SOFT>
+template <bool FUT, bool SOFT, bool TOPO = false>
 __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
+  static_assert(!TOPO || (FUT && SOFT), "the topology variant rides on the two-pass, three-unit exchange");
   const DevConf &c = p.c;
   const int R = p.d.R, K = p.d.K, N = p.d.N, J = p.d.J, Q = p.d.Q, NR = p.d.NR, T = p.d.T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -460,9 +491,9 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 7) & ~(uintptr_t)7);
   double *hn_score = reinterpret_cast<double *>(sp);
   const int hn_cap = p.hn_cap;
-  const int hn_base = c.nta_on ? p.cta_hn_off[cta] : 0;
-  const int hn_n = c.nta_on ? p.cta_hn_off[cta + 1] - hn_base : 0;
-  double *hn_used = c.nta_on ? p.rep_hn_used + (size_t)cta * R * hn_cap : nullptr;
+  const int hn_base = c.nta_tables ? p.cta_hn_off[cta] : 0;
+  const int hn_n = c.nta_tables ? p.cta_hn_off[cta + 1] - hn_base : 0;
+  double *hn_used = c.nta_tables ? p.rep_hn_used + (size_t)cta * R * hn_cap : nullptr;
   for (int k = tid; k < hn_n; k += blockDim.x) {
     const int h = p.cta_hn[hn_base + k];
     for (int d = 0; d < R; ++d) hn_used[d * hn_cap + k] = p.hn_used0[(size_t)d * p.hn_H + h];
@@ -519,6 +550,8 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   int32_t *q_hsize = ri; ri += Q;       // size of the dynamic heap of re-pushed jobs
   uint32_t *q_alloc_has = reinterpret_cast<uint32_t *>(ri); ri += Q;
   uint32_t *q_flags2 = reinterpret_cast<uint32_t *>(ri); ri += Q;
+  int32_t *j_alloc_hn = ri; ri += J;    // subJob.AllocatedHyperNode of soft-mode topology jobs
+  int32_t *j_nplaced = ri; ri += J;     // length of the job's placed-node list
   int32_t *ops = ri; ri += (size_t)p.max_job_tasks * 3;  // task, node, kind
   double *j_share = rf; rf += J;
   double *j_alloc = rf; rf += (size_t)R * J;
@@ -532,7 +565,12 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
     j_cursor[j] = 0;
     j_share[j] = p.j_share0[j];
     for (int d = 0; d < R; ++d) j_alloc[(size_t)d * J + j] = p.j_alloc0[(size_t)d * J + j];
+    j_alloc_hn[j] = TOPO ? p.job_alloc0[j] : -1;
+    j_nplaced[j] = TOPO ? p.placed_n0[j] : 0;
   }
+  int32_t *placed = TOPO ? p.rep_placed + (size_t)cta * p.placed_total : nullptr;
+  if (TOPO)
+    for (size_t i = tid; i < p.placed_total; i += blockDim.x) placed[i] = p.placed0[i];
   for (int r = tid; r < NR; r += blockDim.x) {
     r_occ[r] = p.r_occ0[r];
     r_pip[r] = p.r_pip0[r];
@@ -684,6 +722,9 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
           S.r_min[r] = p.r_min[gr]; S.r_flags[r] = p.r_flags[gr]; S.r_failed[r] = (uint8_t)r_failed[gr];
         }
         S.n_ops = 0;
+        S.job_soft = TOPO ? p.job_soft[j] : 0;
+        S.topo_A = TOPO ? j_alloc_hn[j] : -1;  // allocatedHyperNode := subJob.AllocatedHyperNode, allocate.go:572
+        S.nplaced = TOPO ? j_nplaced[j] : 0;
       }
     }
     for (int i = tid; i < nmine; i += blockDim.x) sn.nerr[i] = 0ull;  // util.NewPredicateHelper()
@@ -731,7 +772,55 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       // max soft-taint count of the candidate set; pass 1 = scores.
       constexpr int n_pass = SOFT ? 2 : 1;
       int g_soft0 = 0, g_soft1 = 0;
-      if (c.nta_on) {  // getPodHyperNodeBinPackingScore(task, hypernode) for the CTA's hypernodes
+      // pods of a soft-mode topology job are scored by batchNodeOrderFnForNetworkAwarePods (:541-571) with
+      // task.JobAllocatedHyperNode = the visit's allocatedHyperNode; no entries at all while that is ""
+      const bool topo_task = TOPO && S.job_soft != 0 && c.nta_plugin;
+      const bool topo_scored = topo_task && S.topo_A >= 0;
+      const int H = p.hn_H;
+      if (TOPO && topo_scored) {
+        if (tid == 0) {  // GetAncestors(jobAllocatedHyperNode), api/hyper_node_info.go:737-758
+          int na = 0;
+          for (int h = S.topo_A; h >= 0 && na < VC_MAX_TIERS + 2; h = p.hn_parent[h]) {
+            S.anc[na] = h;
+            S.anc_lvl[na] = p.hn_tier[h] - p.hn_min_tier;
+            ++na;
+          }
+          S.n_anc = na;
+        }
+        // FindJobTaskNumOfHyperNode for the CTA's lowest-tier hypernodes: tasks of the job by NodeName
+        for (int k = tid; k < hn_n; k += blockDim.x) hn_score[k] = 0.0;
+        __syncthreads();
+        const int32_t *lst = placed + p.placed_off[j];
+        for (int m = tid; m < S.nplaced; m += blockDim.x) {
+          const int h = p.hn_member[lst[m]];
+          if (h < 0) continue;
+          for (int k = 0; k < hn_n; ++k)
+            if (p.cta_hn[hn_base + k] == h) atomicAdd(&hn_score[k], 1.0);
+        }
+        __syncthreads();
+      }
+      // 1 + index into topo_val of networkTopologyAwareScore(FindHyperNodeForNode(node), allocated) :716-756
+      auto topo_code = [&](int n) -> int {
+        const int hn = p.hn_member[n];  // util.FindHyperNodeForNode: lowest tier only
+        double sc = 0.0;
+        if (hn >= 0) {
+          if (hn == S.topo_A) {
+            sc = 1.0;
+          } else {  // GetLCAHyperNode: first ancestor of the allocated hypernode that is an ancestor of hn
+            for (int i = 0; i < S.n_anc; ++i) {
+              if (p.hn_up[(size_t)S.anc_lvl[i] * H + hn] != S.anc[i]) continue;
+              const int min_t = p.hn_min_tier, max_t = p.hn_min_tier + c.nta_L - 1, tier = S.anc_lvl[i] + p.hn_min_tier;
+              sc = min_t == max_t ? 1.0 : (double)(max_t - tier) / (double)(max_t - min_t);
+              break;
+            }
+          }
+        }
+        int code = 1;
+        for (int v = 0; v < p.topo_nval; ++v)
+          if (p.topo_val[v] == sc) code = v + 1;
+        return code;
+      };
+      if (c.nta_on && !topo_task) {  // getPodHyperNodeBinPackingScore(task, hypernode) for the CTA's hypernodes
         for (int k = tid; k < hn_n; k += blockDim.x) {
           const int h = p.cta_hn[hn_base + k];
           hn_score[k] = hn_binpack_score(
@@ -759,16 +848,33 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
           const bool c0 = !FUT || cat == 0;
           if (c0) { mine.cnt[0] += 1; mine.soft[0] = max(mine.soft[0], soft); }
           else { mine.cnt[1] += 1; mine.soft[1] = max(mine.soft[1], soft); }
+          int tcode = 0;
+          if (TOPO && topo_scored) {
+            tcode = topo_code(nbase + i);
+            if (pass == 0) mine.tk[c0 ? 0 : 1] = tk_fold(mine.tk[c0 ? 0 : 1], (tcode << 2) | 1);
+          }
           if (SOFT && pass == 0) continue;
           double order = 0.0;
           bool has_order = node_order(c, R, K, trec, nv, cs, &order);
           const int n = nbase + i;
           double nta = 0.0;
-          if (c.nta_on)
+          if (TOPO && topo_task) {
+            if (topo_scored) {
+              const int gk = S.tk[c0 ? 0 : 1];
+              double tsc = p.topo_val[tcode - 1];
+              if (tcode == (gk >> 2) && (gk & 3) > 1) {  // several nodes share the best score: + taskNum / allTaskNum
+                const int k = p.hn_slot[n];
+                const double cntv = k < 0 ? 0.0 : hn_score[k];
+                if (S.ntasks_total > 0) tsc += cntv / (double)S.ntasks_total;
+              }
+              nta = (double)VC_MAX_NODE_SCORE * (double)c.nta_weight * tsc;  // scaleFinalScore :758-764
+            }
+          } else if (c.nta_on) {
             nta = nta_node_score(c, [&](int l) {
               const int k = p.hn_slot[(size_t)l * N + n];
               return k < 0 ? 1.0 : hn_score[k];
             });
+          }
           double sc = total_score(c, has_order, order, soft, c0 ? g_soft0 : g_soft1, nta);
           if (c0) {
             if (mine.node[0] < 0 || better(sc, n, mine.score[0], mine.node[0])) { mine.score[0] = sc; mine.node[0] = n; }
@@ -782,7 +888,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             S.w_score[k][warp] = mine.score[k]; S.w_node[k][warp] = mine.node[k];
-            S.w_cnt[k][warp] = mine.cnt[k]; S.w_soft[k][warp] = mine.soft[k];
+            S.w_cnt[k][warp] = mine.cnt[k]; S.w_soft[k][warp] = mine.soft[k] | (mine.tk[k] << 8);
           }
         }
         __syncthreads();
@@ -794,7 +900,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               l.score[k] = S.w_score[k][lane]; l.node[k] = S.w_node[k][lane];
-              l.cnt[k] = S.w_cnt[k][lane]; l.soft[k] = S.w_soft[k][lane];
+              l.cnt[k] = S.w_cnt[k][lane]; l.soft[k] = S.w_soft[k][lane] & 0xff; l.tk[k] = S.w_soft[k][lane] >> 8;
             }
           }
           local_warp_reduce(l);
@@ -806,6 +912,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               S.cnt[k] = g.cnt[k]; S.best_node[k] = g.node[k]; S.best_score[k] = g.score[k]; S.max_soft[k] = g.soft[k];
+              if (SOFT && pass == 0) S.tk[k] = g.tk[k];
             }
           }
           PROF_MARK(3);
@@ -867,6 +974,22 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
             if (trec.has & (1u << d)) { S.qalloc[d] += trec.req[d]; S.qalloc_has |= 1u << d; S.qflags2 &= ~2u; }
           S.qshare = queue_share(R, S.qalloc, S.qalloc_has, S.qdes, S.qdes_has);
         }
+        if (TOPO && S.job_soft) {
+          placed[p.placed_off[j] + S.nplaced] = best;  // task.NodeName = hostname
+          S.nplaced += 1;
+          // getNewAllocatedHyperNode, allocate.go:697-707
+          const int hn = p.hn_member[best];
+          if (hn >= 0) {
+            if (S.topo_A < 0) {
+              S.topo_A = hn;
+            } else {
+              int lca = -1;
+              for (int a = S.topo_A, guard = 0; a >= 0 && guard < VC_MAX_TIERS + 2; a = p.hn_parent[a], ++guard)
+                if (p.hn_up[(size_t)(p.hn_tier[a] - p.hn_min_tier) * p.hn_H + hn] == a) { lca = a; break; }
+              S.topo_A = lca;
+            }
+          }
+        }
         const int k = S.n_ops;
         ops[k * 3 + 0] = t; ops[k * 3 + 1] = best; ops[k * 3 + 2] = kind;
         ops_score[k] = score;
@@ -920,6 +1043,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       if (tid == 0) {
         if (c.has_drf) S.jshare = drf_share(p, S.jalloc);
         if (c.has_proportion && (S.qflags2 & 1u)) S.qshare = queue_share(R, S.qalloc, S.qalloc_has, S.qdes, S.qdes_has);
+        if (TOPO && S.job_soft) S.nplaced -= n_ops;  // unallocate / UnPipeline: task.NodeName = ""
       }
     }
     __syncthreads();
@@ -929,6 +1053,10 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       j_waiting[j] = S.waiting;
       j_cursor[j] = S.cursor - p.job_task_off[j];
       j_share[j] = S.jshare;
+      if (TOPO) {
+        j_nplaced[j] = S.nplaced;
+        if (ready && S.job_soft) j_alloc_hn[j] = S.topo_A;  // subJob.AllocatedHyperNode = allocatedHyperNode, :681-686
+      }
       for (int d = 0; d < R; ++d) j_alloc[(size_t)d * J + j] = S.jalloc[d];
       for (int r = 0; r < S.nroles; ++r) {
         int gr = S.role_base + r;

@@ -21,6 +21,10 @@
 #define CS_SOFT_SHIFT 8        // bits 8..15: intolerable PreferNoSchedule taints
 #define CS_NAFF_SHIFT 16       // bits 16..31: sum of matching preferred nodeAffinity weights
 
+// internal flag in a group's presence word (bits >= VC_MAX_DIMS are free): the tasks of the group belong to a
+// soft-mode topology job, so network-topology-aware scores them as network-aware pods, not by hypernode binpacking
+#define VC_HAS_TOPO_TASK 0x40000000u
+
 struct DevConf {
   int n_plugins;
   int plugin[VC_MAX_PLUGINS];
@@ -39,7 +43,9 @@ struct DevConf {
   int has_future;       // any Releasing/Pipelined resource at open -> FutureIdle != Idle possible
   int soft_active;      // taint_batch && some node carries a PreferNoSchedule taint
   // network-topology-aware, hypernode-level binpacking of pods without a network topology
-  int nta_on;           // plugin has EnabledNodeOrder and hypernode.binpack.normal-pod.enable
+  int nta_plugin;       // plugin has EnabledNodeOrder (its BatchNodeOrderFn is registered)
+  int nta_tables;       // per-CTA hypernode lists are built (nta_on, or soft-mode topology jobs exist)
+  int nta_on;           // ... and hypernode.binpack.normal-pod.enable
   int nta_weight;
   int nta_dim_weight[VC_MAX_DIMS];
   int nta_L;            // tier levels min_tier..max_tier (cluster top hypernode included)
@@ -234,7 +240,7 @@ __device__ __forceinline__ double total_score(const DevConf &c, bool has_order, 
       node_sc += (double)sc;
       b += node_sc;
     }
-    if (c.nta_on) b += nta;
+    if (c.nta_plugin) b += nta;  // callers pass 0.0 when the plugin's map has no entry for the node
     score += b;
   }
   return score;

@@ -213,7 +213,7 @@ __device__ __forceinline__ bool k1_final(const K1Params &p, int g, int li, int n
   *feasible = cat != 2;
   if (cat == 2 || cat != chosen) { *score = 0.0; return false; }
   double nta = 0.0;
-  if (p.c.nta_on) {
+  if (p.c.nta_on && !(p.g_has[g] & VC_HAS_TOPO_TASK)) {
     const int n = p.d.node_begin + li;
     nta = nta_node_score(p.c, [&](int l) {
       const int h = p.hn_member[(size_t)l * p.d.N + n];

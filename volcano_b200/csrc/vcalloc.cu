@@ -122,6 +122,14 @@ struct vc_snapshot {
   bool has_topo = false;
   int hn_H = 1, hn_L = 1, hn_min_tier = 1, hn_cap = 1;
   std::vector<int32_t> h_member;  // [L][N]
+  std::vector<int32_t> h_tier, h_parent, h_job_alloc, h_placed_off, h_placed_node;
+  std::vector<uint8_t> h_job_soft;
+  bool topo_any = false;  // the plugin scores pods of soft-mode topology jobs in this session
+  Slot<int32_t> hn_up, hn_tier_s, hn_parent_s, job_soft_s, job_alloc0_s, placed_off_s, placed0_s, placed_n0_s;
+  int32_t *rep_placed = nullptr;
+  size_t rep_placed_count = 0, placed_total = 0;
+  int topo_nval = 0;
+  double topo_val[VC_MAX_TIERS + 2]{};
   Slot<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn;
   Slot<double> hn_alloc, hn_used0;
   double *rep_hn_used = nullptr;
@@ -171,7 +179,7 @@ struct vc_snapshot {
   // host copies kept for the dense-pass grouping
   std::vector<double> h_req, h_kreq, h_knz;
   std::vector<uint32_t> h_has;
-  std::vector<int32_t> h_class;
+  std::vector<int32_t> h_class, h_task_job;
 };
 
 namespace {
@@ -211,7 +219,12 @@ int build_devconf(vc_snapshot *s, const vc_nodes *nd) {
   d.pred_predicates = vch::plugin_enabled(c, VC_PLUGIN_PREDICATES, VC_EN_PREDICATE);
   bool no = vch::plugin_enabled(c, VC_PLUGIN_NODEORDER, VC_EN_NODE_ORDER);
   d.taint_batch = no && c.w_taint_toleration != 0;
-  d.nta_on = vch::plugin_enabled(c, VC_PLUGIN_NETWORK_TOPOLOGY_AWARE, VC_EN_NODE_ORDER) && c.nta_normal_pod_enable;
+  d.nta_plugin = vch::plugin_enabled(c, VC_PLUGIN_NETWORK_TOPOLOGY_AWARE, VC_EN_NODE_ORDER);
+  d.nta_on = d.nta_plugin && c.nta_normal_pod_enable;
+  s->topo_any = false;
+  if (d.nta_plugin)
+    for (uint8_t f : s->h_job_soft) s->topo_any = s->topo_any || f;
+  d.nta_tables = d.nta_on || s->topo_any;
   d.nta_weight = c.nta_weight;
   for (int i = 0; i < VC_MAX_DIMS; ++i) d.nta_dim_weight[i] = c.nta_dim_weight[i];
   d.nta_L = s->hn_L;
@@ -220,12 +233,12 @@ int build_devconf(vc_snapshot *s, const vc_nodes *nd) {
     d.tier_w[l] = vch::go_pow_uint(c.nta_fading, (unsigned)(s->hn_min_tier + l - 1));
     d.tier_w_total += d.tier_w[l];
   }
-  d.batch_any = no || vch::plugin_enabled(c, VC_PLUGIN_PREDICATES, VC_EN_NODE_ORDER) || d.nta_on;
+  d.batch_any = no || vch::plugin_enabled(c, VC_PLUGIN_PREDICATES, VC_EN_NODE_ORDER) || d.nta_plugin;
   const size_t RN = (size_t)s->dims.n_dims * s->dims.n_nodes;
   int fut = 0;
   for (size_t i = 0; i < RN && !fut; ++i)
     if ((nd->releasing && nd->releasing[i] != 0.0) || (nd->pipelined && nd->pipelined[i] != 0.0)) fut = 1;
-  d.has_future = fut;
+  d.has_future = fut || s->topo_any;  // the topology variant of the commit kernel is the <FUT, SOFT> one
   int soft = 0;
   const size_t WN = (size_t)s->dims.taint_words * s->dims.n_nodes;
   for (size_t i = 0; i < WN && !soft; ++i)
@@ -262,7 +275,7 @@ void choose_geometry(vc_snapshot *s) {
   } else {
     size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 + 4) + 64;
-    if (s->dc.nta_on) s->smem_bytes += (size_t)npc * s->hn_L * 8 + 16;  // hn_score: at most npc * L local hypernodes
+    if (s->dc.nta_tables) s->smem_bytes += (size_t)npc * s->hn_L * 8 + 16;  // hn_score: at most npc * L local hypernodes
   }
 }
 
@@ -335,7 +348,7 @@ void vc_snapshot_destroy(vc_snapshot *s) {
   if (!s) return;
   free_dense(s);
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
-                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->hn_score, s->mbox, s->ring, s->d_prof, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
+                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->hn_score, s->mbox, s->ring, s->d_prof, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
   for (void *p : dptrs) if (p) cudaFree(p);
   void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters};
   for (void *p : hptrs) if (p) cudaFreeHost(p);
@@ -352,7 +365,7 @@ int vc_snapshot_set_topology(vc_snapshot *s, const vc_hypernodes *topo) {
   if (!topo || !topo->member) {  // no HyperNode objects: the cluster top hypernode alone (tier 1)
     s->has_topo = false;
     s->hn_H = s->hn_L = s->hn_min_tier = 1;
-    s->h_member.clear();
+    s->h_member.clear(); s->h_tier.clear(); s->h_parent.clear(); s->h_job_soft.clear();
     return VC_OK;
   }
   const int L = topo->max_tier - topo->min_tier + 1;
@@ -365,6 +378,29 @@ int vc_snapshot_set_topology(vc_snapshot *s, const vc_hypernodes *topo) {
   s->has_topo = true;
   s->hn_H = topo->n_hypernodes; s->hn_L = L; s->hn_min_tier = topo->min_tier;
   s->h_member.assign(topo->member, topo->member + (size_t)L * N);
+  const size_t H = topo->n_hypernodes, J = s->dims.n_jobs;
+  s->h_tier.clear(); s->h_parent.clear(); s->h_job_soft.clear(); s->h_job_alloc.clear();
+  s->h_placed_off.clear(); s->h_placed_node.clear();
+  if (topo->tier && topo->parent) {
+    s->h_tier.assign(topo->tier, topo->tier + H);
+    s->h_parent.assign(topo->parent, topo->parent + H);
+    for (size_t h = 0; h < H; ++h) {
+      if (s->h_tier[h] < topo->min_tier || s->h_tier[h] > topo->max_tier) return fail(VC_EINVAL, "hypernode %zu: tier outside [min_tier,max_tier]", h);
+      if (s->h_parent[h] < -1 || s->h_parent[h] >= (int)H) return fail(VC_EINVAL, "hypernode %zu: bad parent", h);
+    }
+  }
+  if (topo->job_soft) {
+    if (!topo->tier || !topo->parent || !topo->job_allocated || !topo->job_placed_off || !topo->job_placed_node)
+      return fail(VC_EINVAL, "soft-mode topology jobs need tier, parent, job_allocated and the placed-node lists");
+    s->h_job_soft.assign(topo->job_soft, topo->job_soft + J);
+    s->h_job_alloc.assign(topo->job_allocated, topo->job_allocated + J);
+    s->h_placed_off.assign(topo->job_placed_off, topo->job_placed_off + J + 1);
+    s->h_placed_node.assign(topo->job_placed_node, topo->job_placed_node + s->h_placed_off[J]);
+    for (size_t j = 0; j < J; ++j)
+      if (s->h_job_alloc[j] < -1 || s->h_job_alloc[j] >= (int)H) return fail(VC_EINVAL, "job %zu: bad allocated hypernode", j);
+    for (int32_t n : s->h_placed_node)
+      if (n < 0 || (size_t)n >= N) return fail(VC_EINVAL, "placed-node list: node index out of range");
+  }
   return VC_OK;
 }
 
@@ -524,7 +560,8 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     for (size_t t = 0; t < T; ++t) {
       key.clear();
       key.append(reinterpret_cast<const char *>(&tk->klass[t]), 4);
-      key.append(reinterpret_cast<const char *>(&tk->req_has[t]), 4);
+      const uint32_t has_x = tk->req_has[t] | ((s->topo_any && s->h_job_soft[tk->job[t]]) ? VC_HAS_TOPO_TASK : 0u);
+      key.append(reinterpret_cast<const char *>(&has_x), 4);
       for (size_t d = 0; d < R; ++d) key.append(reinterpret_cast<const char *>(&tk->resreq[d * T + t]), 8);
       for (size_t k = 0; k < K; ++k) key.append(reinterpret_cast<const char *>(&tk->k8s_req[k * T + t]), 8);
       for (size_t k = 0; k < 2; ++k) key.append(reinterpret_cast<const char *>(&tk->k8s_nonzero_req[k * T + t]), 8);
@@ -547,7 +584,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     for (size_t d = 0; d < R; ++d) g_req[d * NG + g] = tk->resreq[d * T + t];
     for (size_t k = 0; k < K; ++k) g_kreq[k * NG + g] = tk->k8s_req[k * T + t];
     for (size_t k = 0; k < 2; ++k) g_knz[k * NG + g] = tk->k8s_nonzero_req[k * T + t];
-    g_has[g] = tk->req_has[t];
+    g_has[g] = tk->req_has[t] | ((s->topo_any && s->h_job_soft[tk->job[t]]) ? VC_HAS_TOPO_TASK : 0u);
     g_class[g] = tk->klass[t];
   }
   // per position of task_order: {task, group, role row}; a job is 'pure' when each named role maps to
@@ -671,7 +708,45 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   std::vector<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn;
   std::vector<double> hn_alloc, hn_used0;
   s->hn_cap = 1;
-  if (s->dc.nta_on) {
+  std::vector<int32_t> hn_up, job_soft32, placed_off, placed0, placed_n0;
+  s->placed_total = 0;
+  if (s->topo_any) {
+    // ancestor (Parent chain, the hypernode itself included) of every hypernode at every tier level
+    const size_t L = s->hn_L, H = s->hn_H;
+    hn_up.assign(L * H, -1);
+    for (size_t h = 0; h < H; ++h) {
+      int a = (int)h;
+      for (int guard = 0; a >= 0 && guard < VC_MAX_TIERS + 2; ++guard) {
+        const size_t l = (size_t)(s->h_tier[a] - s->hn_min_tier);
+        if (hn_up[l * H + h] < 0) hn_up[l * H + h] = a;
+        a = s->h_parent[a];
+      }
+    }
+    // values networkTopologyAwareScore can return (network_topology_aware.go:716-756), ascending
+    std::vector<double> vals{0.0, 1.0};
+    const int min_t = s->hn_min_tier, max_t = s->hn_min_tier + s->hn_L - 1;
+    for (int tier = min_t; tier <= max_t; ++tier)
+      vals.push_back(min_t == max_t ? 1.0 : (double)(max_t - tier) / (double)(max_t - min_t));
+    std::sort(vals.begin(), vals.end());
+    vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+    s->topo_nval = (int)vals.size();
+    for (size_t i = 0; i < vals.size(); ++i) s->topo_val[i] = vals[i];
+    // per-job lists of nodes that hold a task of the job: room for the tasks in scope on top of those at open
+    job_soft32.assign(J, 0);
+    placed_off.assign(J + 1, 0);
+    placed_n0.assign(J, 0);
+    for (size_t j = 0; j < J; ++j) {
+      job_soft32[j] = s->h_job_soft[j];
+      const int n0 = s->h_job_soft[j] ? s->h_placed_off[j + 1] - s->h_placed_off[j] : 0;
+      placed_n0[j] = n0;
+      placed_off[j + 1] = placed_off[j] + (s->h_job_soft[j] ? n0 + (job_task_off[j + 1] - job_task_off[j]) : 0);
+    }
+    s->placed_total = (size_t)placed_off[J];
+    placed0.assign(std::max<size_t>(s->placed_total, 1), 0);
+    for (size_t j = 0; j < J; ++j)
+      for (int k = 0; k < placed_n0[j]; ++k) placed0[placed_off[j] + k] = s->h_placed_node[s->h_placed_off[j] + k];
+  }
+  if (s->dc.nta_tables) {
     const size_t L = s->hn_L, H = s->hn_H;
     if (s->has_topo) hn_member = s->h_member;
     else hn_member.assign(L * N, 0);
@@ -755,6 +830,12 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     put(s, s->hn_member, hn_member.data(), hn_member.size(), plan); put(s, s->hn_slot, hn_slot.data(), hn_slot.size(), plan);
     put(s, s->cta_hn_off, cta_hn_off.data(), cta_hn_off.size(), plan); put(s, s->cta_hn, cta_hn.data(), cta_hn.size(), plan);
     put(s, s->hn_alloc, hn_alloc.data(), hn_alloc.size(), plan); put(s, s->hn_used0, hn_used0.data(), hn_used0.size(), plan);
+    put(s, s->hn_up, hn_up.data(), hn_up.size(), plan); put(s, s->hn_tier_s, s->h_tier.data(), s->topo_any ? s->h_tier.size() : 0, plan);
+    put(s, s->hn_parent_s, s->h_parent.data(), s->topo_any ? s->h_parent.size() : 0, plan);
+    put(s, s->job_soft_s, job_soft32.data(), job_soft32.size(), plan);
+    put(s, s->job_alloc0_s, s->h_job_alloc.data(), s->topo_any ? s->h_job_alloc.size() : 0, plan);
+    put(s, s->placed_off_s, placed_off.data(), placed_off.size(), plan); put(s, s->placed0_s, placed0.data(), placed0.size(), plan);
+    put(s, s->placed_n0_s, placed_n0.data(), placed_n0.size(), plan);
     if (plan) {
       size_t need = (s->in.used + 255) & ~(size_t)255;
       if (need > s->in.cap) {
@@ -808,6 +889,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   s->h_knz.assign(tk->k8s_nonzero_req, tk->k8s_nonzero_req + 2 * T);
   s->h_has.assign(tk->req_has, tk->req_has + T);
   s->h_class.assign(tk->klass, tk->klass + T);
+  s->h_task_job.assign(tk->job, tk->job + T);
   s->upload_ms = now_ms() - t0;
   return VC_OK;
 }
@@ -837,7 +919,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
     return fail(VC_EUNSUPPORTED, "the commit engine runs on the full node axis (replicas only across GPUs, DESIGN.md)");
   const int G = s->n_cta;
   // replicas, mailbox, outputs
-  const size_t i32_stride = ((3 * J + 4 * NR + 5 * Q + 3 * (size_t)s->max_job_tasks) + 63) & ~(size_t)63;
+  const size_t i32_stride = ((5 * J + 4 * NR + 5 * Q + 3 * (size_t)s->max_job_tasks) + 63) & ~(size_t)63;
   const size_t f64_words_fast = (J * sizeof(JobDyn) + Q * sizeof(QueueDyn) + NR * sizeof(RoleDyn)) / 8 + (size_t)s->max_job_tasks;
   const size_t f64_stride = (std::max<size_t>(J + R * J + R * Q + Q + (size_t)s->max_job_tasks, f64_words_fast) + 31) & ~(size_t)31;
   // per-CTA heap replica: HeapEnt entries for k_commit, HeapKey (32 B) entries for k_commit_fast; stride in entries of
@@ -853,7 +935,16 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
     CUDA_TRY(cudaMalloc(&s->rep_heap, std::max<size_t>(16, std::max<size_t>(heap_stride, 1) * G * sizeof(HeapKey))));
     s->rep_i32_stride = i32_stride; s->rep_f64_stride = f64_stride; s->rep_heap_stride = heap_stride;
   }
-  if (s->dc.nta_on) {
+  if (s->topo_any) {
+    const size_t cnt = (size_t)G * std::max<size_t>(s->placed_total, 1);
+    if (!s->rep_placed || s->rep_placed_count < cnt) {
+      if (s->rep_placed) cudaFree(s->rep_placed);
+      s->rep_placed = nullptr;
+      CUDA_TRY(cudaMalloc(&s->rep_placed, cnt * 4));
+      s->rep_placed_count = cnt;
+    }
+  }
+  if (s->dc.nta_tables) {
     const size_t cnt = (size_t)G * R * s->hn_cap;
     if (!s->rep_hn_used || s->rep_hn_used_count < cnt) {
       if (s->rep_hn_used) cudaFree(s->rep_hn_used);
@@ -924,9 +1015,15 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   p.hn_member = s->hn_member.d(s->in); p.hn_slot = s->hn_slot.d(s->in); p.cta_hn_off = s->cta_hn_off.d(s->in);
   p.cta_hn = s->cta_hn.d(s->in); p.hn_alloc = s->hn_alloc.d(s->in); p.hn_used0 = s->hn_used0.d(s->in);
   p.rep_hn_used = s->rep_hn_used;
+  p.hn_min_tier = s->hn_min_tier; p.hn_up = s->hn_up.d(s->in); p.hn_tier = s->hn_tier_s.d(s->in);
+  p.hn_parent = s->hn_parent_s.d(s->in); p.job_soft = s->job_soft_s.d(s->in); p.job_alloc0 = s->job_alloc0_s.d(s->in);
+  p.placed_off = s->placed_off_s.d(s->in); p.placed0 = s->placed0_s.d(s->in); p.placed_n0 = s->placed_n0_s.d(s->in);
+  p.rep_placed = s->rep_placed; p.placed_total = s->placed_total;
+  p.topo_nval = s->topo_nval;
+  for (int i = 0; i < VC_MAX_TIERS + 2; ++i) p.topo_val[i] = s->topo_val[i];
 
   if (G > 1024) return fail(VC_EUNSUPPORTED, "too many CTAs");
-  const void *kfn = s->fast ? (const void *)k_commit_fast : s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
+  const void *kfn = s->fast ? (const void *)k_commit_fast : s->topo_any ? (const void *)k_commit<true, true, true> : s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
                                      : (s->dc.soft_active ? (const void *)k_commit<false, true> : (const void *)k_commit<false, false>);
   CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
   int max_blocks = 0;
@@ -1009,7 +1106,7 @@ static int dense_prepare(vc_snapshot *s) {
     for (size_t d = 0; d < R; ++d) g_req[d * G + g] = s->h_req[d * T + t];
     for (size_t k = 0; k < K; ++k) g_kreq[k * G + g] = s->h_kreq[k * T + t];
     for (size_t k = 0; k < 2; ++k) g_knz[k * G + g] = s->h_knz[k * T + t];
-    g_has[g] = s->h_has[t];
+    g_has[g] = s->h_has[t] | ((s->topo_any && s->h_job_soft[s->h_task_job[t]]) ? VC_HAS_TOPO_TASK : 0u);
     g_class[g] = s->h_class[t];
   }
   for (size_t t = 0; t < T; ++t) g_count[group_of[t] + 1]++;
@@ -1079,6 +1176,11 @@ static K1Params dense_params(vc_snapshot *s) {
 
 int vc_dense_begin(vc_snapshot *s) {
   if (!s || !s->uploaded) return fail(VC_EINVAL, "snapshot not uploaded");
+  if (s->topo_any)
+    for (size_t j = 0; j < s->h_job_soft.size(); ++j)
+      if (s->h_job_soft[j] && s->h_job_alloc[j] >= 0)
+        return fail(VC_EUNSUPPORTED, "dense pass: job %zu is a soft-mode topology job with an allocated hypernode; its pods are "
+                                     "scored per job inside the commit kernel only", j);
   int rc = dense_prepare(s);
   if (rc) return rc;
   const int nloc = s->dd.node_end - s->dd.node_begin;

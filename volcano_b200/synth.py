@@ -38,6 +38,7 @@ class SynthConfig:
     mixed_roles: bool = False    # two roles with different requests per job + TaskMinAvailable (role minima, error cache)
     topology: Optional[tuple] = None  # HyperNode tree fan-outs below the single root, e.g. (32, 40): 32 tier-2 x 40 tier-1 each
     topology_scatter: float = 0.0     # fraction of nodes assigned to a random leaf / left outside the tree (tests)
+    soft_topology_frac: float = 0.0   # fraction of jobs whose PodGroup carries a soft-mode network topology
 
 
 CONFIGS = {
@@ -50,7 +51,8 @@ CONFIGS = {
     # configs[3]: 3-tier HyperNode tree (root -> 32 -> 40 each -> ~39 nodes), network-topology-aware weight 10
     # (hypernode-level binpacking of pods without a network topology; topology-constrained jobs are not generated)
     "cfg4": SynthConfig("cfg4", 50_000, 1_000_000, 16,
-                        "priority+gang+drf+predicates+proportion+nodeorder+binpack+network-topology-aware", topology=(32, 40)),
+                        "priority+gang+drf+predicates+proportion+nodeorder+binpack+network-topology-aware", topology=(32, 40),
+                        soft_topology_frac=0.1),
     # the same shape without the topology plugin (incremental commit kernel)
     "cfg4_flat": SynthConfig("cfg4_flat", 50_000, 1_000_000, 16, "priority+gang+drf+predicates+proportion+nodeorder+binpack"),
     # small shapes for tests
@@ -64,13 +66,16 @@ CONFIGS = {
     "small_fut_soft": SynthConfig("small_fut_soft", 300, 1500, 4, "priority+gang+drf+predicates+proportion+nodeorder+binpack",
                                   n_classes=16, utilisation=0.99, min_util=0.88, releasing_frac=0.5, soft_taint_p=0.08),
     "tiny_topo": SynthConfig("tiny_topo", 96, 400, 2, "priority+gang+drf+predicates+proportion+nodeorder+binpack+network-topology-aware",
-                             n_classes=8, topology=(2, 3), topology_scatter=0.1),
+                             n_classes=8, topology=(2, 3), topology_scatter=0.1, soft_topology_frac=0.3),
     "small_topo": SynthConfig("small_topo", 600, 3000, 3, "priority+gang+predicates+nodeorder+binpack+network-topology-aware",
-                              n_classes=16, topology=(4, 6), topology_scatter=0.15),
+                              n_classes=16, topology=(4, 6), topology_scatter=0.15, soft_topology_frac=0.2),
     "small_topo_fut_soft": SynthConfig("small_topo_fut_soft", 300, 1500, 3,
                                        "priority+gang+drf+predicates+proportion+nodeorder+binpack+network-topology-aware",
                                        n_classes=12, utilisation=0.99, min_util=0.88, releasing_frac=0.5, soft_taint_p=0.08,
-                                       topology=(3, 4), topology_scatter=0.1),
+                                       topology=(3, 4), topology_scatter=0.1, soft_topology_frac=0.3),
+    # hypernode binpacking only (no topology-constrained jobs)
+    "small_topo_normal": SynthConfig("small_topo_normal", 600, 3000, 3, "priority+gang+predicates+nodeorder+binpack+network-topology-aware",
+                                     n_classes=16, topology=(4, 6), topology_scatter=0.15),
     "small_roles": SynthConfig("small_roles", 200, 1200, 2, "priority+gang+predicates+nodeorder+binpack", n_classes=8,
                                utilisation=0.85, mixed_roles=True),
 }
@@ -309,3 +314,11 @@ def _make_topology(s: Snapshot, cfg: SynthConfig, rng) -> None:
     s.hn_names = [f"leaf-{i}" for i in range(n_leaf)] + [f"mid-{i}" for i in range(n_mid)] + ["root", "<cluster-top-hypernode>"]
     s.hn_min_tier, s.hn_max_tier = 1, 4
     s.hn_member = np.ascontiguousarray(member)
+    H = n_leaf + n_mid + 2
+    s.hn_tier = np.concatenate([np.full(n_leaf, 1), np.full(n_mid, 2), [3, 4]]).astype(np.int32)
+    s.hn_parent = np.concatenate([n_leaf + np.arange(n_leaf) // per_mid, np.full(n_mid, n_leaf + n_mid), [H - 1, -1]]).astype(np.int32)
+    # soft-mode topology jobs: nothing is allocated at open, so AllocatedHyperNode = "" and the node lists are empty
+    s.hn_job_soft = (rng.random(s.J) < cfg.soft_topology_frac).astype(np.uint8)
+    s.hn_job_allocated = np.full(s.J, -1, np.int32)
+    s.hn_job_placed_off = np.zeros(s.J + 1, np.int32)
+    s.hn_job_placed_node = np.zeros(1, np.int32)
