@@ -369,6 +369,9 @@ const vc_visit *vc_result_visits(const vc_result *r);
 size_t vc_result_num_fit_errors(const vc_result *r);
 const int32_t *vc_result_fit_errors(const vc_result *r);
 const vc_stats *vc_result_stats(const vc_result *r);
+/* subJob.AllocatedHyperNode of every job after the run (index into the hypernode table, -1 = ""): what
+   allocate.go:681-686 stores for soft-mode topology jobs. NULL / 0 when the session has no such job. */
+const int32_t *vc_result_job_allocated_hypernodes(const vc_result *r, size_t *n_jobs);
 void vc_result_free(vc_result *r);
 
 #ifdef __cplusplus

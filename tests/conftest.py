@@ -21,7 +21,13 @@ def oracle_engine():
     def run(snap, threads=1):
         s = OracleSession(snap, threads=threads)
         dec, vis, fe = s.allocate()
+        res = AllocateResult(dec, vis, fe)
+        if snap.hn_job_soft is not None and snap.hn_job_soft.any():
+            import numpy as np
+            from oracle import pyoracle
+            res.job_allocated_hypernodes = np.array([pyoracle.lib().vco_job_allocated_hypernode(s.h, j) for j in range(snap.J)],
+                                                    np.int32)
         s.close()
-        return AllocateResult(dec, vis, fe)
+        return res
 
     return run

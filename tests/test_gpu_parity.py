@@ -30,6 +30,9 @@ def _assert_same(a, b):
         assert np.array_equal(a.decisions[f], b.decisions[f]), f
     assert np.allclose(a.decisions["score"], b.decisions["score"], rtol=0, atol=SCORE_TOL)
     assert np.array_equal(a.fit_errors, b.fit_errors)
+    if b.job_allocated_hypernodes is not None:  # topology sessions: subJob.AllocatedHyperNode after the run
+        assert a.job_allocated_hypernodes is not None
+        assert np.array_equal(a.job_allocated_hypernodes, b.job_allocated_hypernodes)
 
 
 @pytest.mark.parametrize("case", G.allocate_cases(), ids=lambda c: c.Name[:40])

@@ -225,6 +225,7 @@ SYMBOLS = {
     "vc_result_num_fit_errors": (C.c_size_t, [_vp]),
     "vc_result_fit_errors": (_i32p, [_vp]),
     "vc_result_stats": (C.POINTER(vc_stats), [_vp]),
+    "vc_result_job_allocated_hypernodes": (_i32p, [_vp, C.POINTER(C.c_size_t)]),
     "vc_result_free": (None, [_vp]),
 }
 

@@ -85,6 +85,10 @@ struct K2Params {
   const int32_t *hn_slot;     // [L][N] position of that hypernode in the owning CTA's local list, -1 none
   const int32_t *cta_hn_off;  // [n_cta+1] local lists: the hypernodes that hold at least one node of the CTA
   const int32_t *cta_hn;
+  const int32_t *node_chain;  // [N] position, in the owning CTA's chain list, of the node's tuple of per-tier hypernodes
+  const int32_t *cta_chain_off;  // [n_cta+1]
+  const int32_t *cta_chain;   // [chains][L] local hypernode slot per tier level (-1 none)
+  int chain_cap;              // max chains of one CTA
   const double *hn_alloc;     // [R][H] hyperNodeResourceCache allocatable
   const double *hn_used0;     // [R][H] ... used at session open
   double *rep_hn_used;        // [n_cta][R][hn_cap] per-CTA live copy of `used` for the CTA's local hypernodes
@@ -100,6 +104,7 @@ struct K2Params {
   const int32_t *placed_n0;   // [J] their lengths
   int32_t *rep_placed;        // [n_cta][placed_total] per-CTA live copies
   size_t placed_total;
+  int32_t *job_alloc_out;     // [J] subJob.AllocatedHyperNode after the run
   int topo_nval;              // distinct values networkTopologyAwareScore can take, ascending
   double topo_val[VC_MAX_TIERS + 2];
 };
@@ -487,9 +492,20 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   sn.nerr = reinterpret_cast<unsigned long long *>(sp); sp += (size_t)cap * 8;
   sn.max_tasks = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
   sn.pod_count = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
-  // network-topology-aware: per-step binpack score of each local hypernode for the task under evaluation
+  // verdict cache: (fit category, NodeOrderFn sum) of node i for the (class, request) group c_group[i]; an entry dies
+  // when the node's state changes (placement / rollback), so a sweep re-evaluates only what a placement touched
   sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 7) & ~(uintptr_t)7);
-  double *hn_score = reinterpret_cast<double *>(sp);
+  double *c_order = reinterpret_cast<double *>(sp); sp += (size_t)cap * 8;
+  int32_t *c_group = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
+  uint8_t *c_cat = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;
+  for (int i = tid; i < cap; i += blockDim.x) c_group[i] = -1;
+  // network-topology-aware: per-step binpack score of each local hypernode for the task under evaluation, and
+  // the plugin's score of each distinct per-tier hypernode tuple ("chain") among the CTA's nodes
+  sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 7) & ~(uintptr_t)7);
+  double *hn_score = reinterpret_cast<double *>(sp); sp += (size_t)p.hn_cap * 8;
+  double *chain_val = reinterpret_cast<double *>(sp);
+  const int chain_base = c.nta_on ? p.cta_chain_off[cta] : 0;
+  const int chain_n = c.nta_on ? p.cta_chain_off[cta + 1] - chain_base : 0;
   const int hn_cap = p.hn_cap;
   const int hn_base = c.nta_tables ? p.cta_hn_off[cta] : 0;
   const int hn_n = c.nta_tables ? p.cta_hn_off[cta + 1] - hn_base : 0;
@@ -749,6 +765,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
         S.trec.klass = p.t_class[t];
         S.task = t;
         S.role_local = p.t_role[t] - S.role_base;
+        S.cur_group = p.tmeta[S.cursor].y;
         S.cursor += 1;
       }
       __syncthreads();
@@ -763,6 +780,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
         continue;
       }
       const bool use_cache = c.enable_ecache && named_role;
+      const int cur_group = S.cur_group;
 
       // ---- ph.PredicateNodes + alloc.prioritizeNodes over this CTA's nodes ----
       const TaskRec &trec = S.trec;
@@ -828,6 +846,11 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
               [&](int d) { return p.hn_alloc[(size_t)d * p.hn_H + h]; });
         }
         __syncthreads();
+        for (int k = tid; k < chain_n; k += blockDim.x) {  // batchNodeOrderFnForNormalPods per distinct chain
+          const int32_t *sl = p.cta_chain + (size_t)(chain_base + k) * c.nta_L;
+          chain_val[k] = nta_node_score(c, [&](int l) { return sl[l] < 0 ? 1.0 : hn_score[sl[l]]; });
+        }
+        __syncthreads();
       }
       for (int pass = 0; pass < n_pass; ++pass) {
         Local mine;
@@ -836,12 +859,23 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
           SmemNodeView nv{sn, i};
           const uint32_t cs = cs_row[i];
           int cat = 2;
+          bool has_order = false;
+          double order = 0.0;
           if (!(use_cache && ((sn.nerr[i] >> rl) & 1ull))) {
-            bool ok = (cs & CS_STATIC_OK) != 0;
-            if (c.pred_predicates && sn.max_tasks[i] <= sn.pod_count[i]) ok = false;
-            int fc = fit_category_t<FUT>(R, trec, nv);
-            if (ok && fc != 2) cat = fc;
-            else if (use_cache && pass == 0) sn.nerr[i] |= (1ull << rl);
+            if (c_group[i] == cur_group) {
+              const uint8_t cw = c_cat[i];
+              cat = cw & 3; has_order = (cw & 0x80) != 0; order = c_order[i];
+            } else {
+              bool ok = (cs & CS_STATIC_OK) != 0;
+              if (c.pred_predicates && sn.max_tasks[i] <= sn.pod_count[i]) ok = false;
+              int fc = fit_category_t<FUT>(R, trec, nv);
+              if (ok && fc != 2) {
+                cat = fc;
+                has_order = node_order(c, R, K, trec, nv, cs, &order);
+              }
+              c_group[i] = cur_group; c_cat[i] = (uint8_t)(cat | (has_order ? 0x80 : 0)); c_order[i] = order;
+            }
+            if (cat == 2 && use_cache && pass == 0) sn.nerr[i] |= (1ull << rl);
           }
           if (cat == 2) continue;
           const int soft = SOFT ? (int)((cs >> CS_SOFT_SHIFT) & 0xff) : 0;
@@ -854,8 +888,6 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
             if (pass == 0) mine.tk[c0 ? 0 : 1] = tk_fold(mine.tk[c0 ? 0 : 1], (tcode << 2) | 1);
           }
           if (SOFT && pass == 0) continue;
-          double order = 0.0;
-          bool has_order = node_order(c, R, K, trec, nv, cs, &order);
           const int n = nbase + i;
           double nta = 0.0;
           if (TOPO && topo_task) {
@@ -870,10 +902,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
               nta = (double)VC_MAX_NODE_SCORE * (double)c.nta_weight * tsc;  // scaleFinalScore :758-764
             }
           } else if (c.nta_on) {
-            nta = nta_node_score(c, [&](int l) {
-              const int k = p.hn_slot[(size_t)l * N + n];
-              return k < 0 ? 1.0 : hn_score[k];
-            });
+            nta = chain_val[p.node_chain[n]];
           }
           double sc = total_score(c, has_order, order, soft, c0 ? g_soft0 : g_soft1, nta);
           if (c0) {
@@ -941,6 +970,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       if (best >= nbase && best < nbase + nmine) {
         const int i = best - nbase;
         if ((i % blockDim.x) == tid) {
+          c_group[i] = -1;
           if (kind == VC_OP_ALLOCATE) {
             for (int d = 0; d < R; ++d) {
               sn.idle[d * cap + i] -= trec.req[d];
@@ -1012,6 +1042,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
         if (c.nta_on) hn_account(on, p.req + ot, (size_t)T, p.req_has[ot], -1.0);
         if (on >= nbase && on < nbase + nmine && ((on - nbase) % blockDim.x) == tid) {
           const int i = on - nbase;
+          c_group[i] = -1;
           for (int d = 0; d < R; ++d) {
             double rq = p.req[(size_t)d * T + ot];
             if (okind == VC_OP_ALLOCATE) { sn.idle[d * cap + i] += rq; sn.used[d * cap + i] -= rq; }
@@ -1119,6 +1150,8 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
     for (int k = 0; k < 2; ++k) p.knz[(size_t)k * N + n] = sn.knz[k * cap + i];
     p.pod_count[n] = sn.pod_count[i];
   }
+  if (TOPO && out_cta)
+    for (int j = tid; j < J; j += blockDim.x) p.job_alloc_out[j] = j_alloc_hn[j];
   if (out_cta && tid == 0) {
     p.counters[0] = S.n_dec;
     p.counters[1] = S.n_vis;

@@ -73,6 +73,7 @@ struct vc_result {
   std::vector<vc_decision> decisions;
   std::vector<vc_visit> visits;
   std::vector<int32_t> fit_errors;
+  std::vector<int32_t> job_alloc;
   vc_stats stats{};
 };
 
@@ -126,11 +127,12 @@ struct vc_snapshot {
   std::vector<uint8_t> h_job_soft;
   bool topo_any = false;  // the plugin scores pods of soft-mode topology jobs in this session
   Slot<int32_t> hn_up, hn_tier_s, hn_parent_s, job_soft_s, job_alloc0_s, placed_off_s, placed0_s, placed_n0_s;
-  int32_t *rep_placed = nullptr;
+  int32_t *rep_placed = nullptr, *d_job_alloc = nullptr;
   size_t rep_placed_count = 0, placed_total = 0;
   int topo_nval = 0;
   double topo_val[VC_MAX_TIERS + 2]{};
-  Slot<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn;
+  Slot<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn, node_chain, cta_chain_off, cta_chain;
+  int chain_cap = 1;
   Slot<double> hn_alloc, hn_used0;
   double *rep_hn_used = nullptr;
   size_t rep_hn_used_count = 0;
@@ -275,7 +277,9 @@ void choose_geometry(vc_snapshot *s) {
   } else {
     size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 + 4) + 64;
-    if (s->dc.nta_tables) s->smem_bytes += (size_t)npc * s->hn_L * 8 + 16;  // hn_score: at most npc * L local hypernodes
+    s->smem_bytes += (size_t)npc * (8 + 4 + 1) + 32;  // verdict cache
+    // hn_score (at most npc * L local hypernodes) + chain_val (at most npc chains); hn_cap is set after this call
+    if (s->dc.nta_tables) s->smem_bytes += (size_t)npc * (s->hn_L + 1) * 8 + 32;
   }
 }
 
@@ -348,7 +352,7 @@ void vc_snapshot_destroy(vc_snapshot *s) {
   if (!s) return;
   free_dense(s);
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
-                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->hn_score, s->mbox, s->ring, s->d_prof, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
+                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_prof, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
   for (void *p : dptrs) if (p) cudaFree(p);
   void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters};
   for (void *p : hptrs) if (p) cudaFreeHost(p);
@@ -705,9 +709,10 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   // network-topology-aware: hyperNodeResourceCache at open (network_topology_aware.go:106-125) and, for the
   // commit kernel, the hypernodes each CTA's node slice belongs to
   choose_geometry(s);
-  std::vector<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn;
+  std::vector<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn, node_chain, cta_chain_off, cta_chain;
   std::vector<double> hn_alloc, hn_used0;
   s->hn_cap = 1;
+  s->chain_cap = 1;
   std::vector<int32_t> hn_up, job_soft32, placed_off, placed0, placed_n0;
   s->placed_total = 0;
   if (s->topo_any) {
@@ -781,6 +786,28 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
       cta_hn_off[cta + 1] = (int32_t)cta_hn.size();
       s->hn_cap = std::max<int>(s->hn_cap, (int)local.size());
     }
+    // distinct per-tier slot tuples ("chains") among each CTA's nodes: the plugin's normal-pod score is one value
+    // per chain and step
+    node_chain.assign(N, 0);
+    cta_chain_off.assign(s->n_cta + 1, 0);
+    std::unordered_map<std::string, int> chains;
+    std::string key;
+    for (int cta = 0; cta < s->n_cta; ++cta) {
+      chains.clear();
+      const size_t nb = (size_t)cta * s->npc, ne = std::min(N, nb + (size_t)s->npc);
+      for (size_t n = nb; n < ne; ++n) {
+        key.clear();
+        for (size_t l = 0; l < L; ++l) key.append(reinterpret_cast<const char *>(&hn_slot[l * N + n]), 4);
+        auto it = chains.find(key);
+        if (it == chains.end()) {
+          it = chains.emplace(key, (int)chains.size()).first;
+          for (size_t l = 0; l < L; ++l) cta_chain.push_back(hn_slot[l * N + n]);
+        }
+        node_chain[n] = it->second;
+      }
+      cta_chain_off[cta + 1] = cta_chain_off[cta] + (int32_t)chains.size();
+      s->chain_cap = std::max<int>(s->chain_cap, (int)chains.size());
+    }
   }
 
   // ---- plan + stage + one H2D copy ------------------------------------------------------
@@ -830,6 +857,8 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     put(s, s->hn_member, hn_member.data(), hn_member.size(), plan); put(s, s->hn_slot, hn_slot.data(), hn_slot.size(), plan);
     put(s, s->cta_hn_off, cta_hn_off.data(), cta_hn_off.size(), plan); put(s, s->cta_hn, cta_hn.data(), cta_hn.size(), plan);
     put(s, s->hn_alloc, hn_alloc.data(), hn_alloc.size(), plan); put(s, s->hn_used0, hn_used0.data(), hn_used0.size(), plan);
+    put(s, s->node_chain, node_chain.data(), node_chain.size(), plan); put(s, s->cta_chain_off, cta_chain_off.data(), cta_chain_off.size(), plan);
+    put(s, s->cta_chain, cta_chain.data(), cta_chain.size(), plan);
     put(s, s->hn_up, hn_up.data(), hn_up.size(), plan); put(s, s->hn_tier_s, s->h_tier.data(), s->topo_any ? s->h_tier.size() : 0, plan);
     put(s, s->hn_parent_s, s->h_parent.data(), s->topo_any ? s->h_parent.size() : 0, plan);
     put(s, s->job_soft_s, job_soft32.data(), job_soft32.size(), plan);
@@ -935,6 +964,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
     CUDA_TRY(cudaMalloc(&s->rep_heap, std::max<size_t>(16, std::max<size_t>(heap_stride, 1) * G * sizeof(HeapKey))));
     s->rep_i32_stride = i32_stride; s->rep_f64_stride = f64_stride; s->rep_heap_stride = heap_stride;
   }
+  if (s->topo_any && !s->d_job_alloc) CUDA_TRY(cudaMalloc(&s->d_job_alloc, std::max<size_t>(16, J * 4)));
   if (s->topo_any) {
     const size_t cnt = (size_t)G * std::max<size_t>(s->placed_total, 1);
     if (!s->rep_placed || s->rep_placed_count < cnt) {
@@ -1015,10 +1045,12 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   p.hn_member = s->hn_member.d(s->in); p.hn_slot = s->hn_slot.d(s->in); p.cta_hn_off = s->cta_hn_off.d(s->in);
   p.cta_hn = s->cta_hn.d(s->in); p.hn_alloc = s->hn_alloc.d(s->in); p.hn_used0 = s->hn_used0.d(s->in);
   p.rep_hn_used = s->rep_hn_used;
+  p.node_chain = s->node_chain.d(s->in); p.cta_chain_off = s->cta_chain_off.d(s->in); p.cta_chain = s->cta_chain.d(s->in);
+  p.chain_cap = s->chain_cap;
   p.hn_min_tier = s->hn_min_tier; p.hn_up = s->hn_up.d(s->in); p.hn_tier = s->hn_tier_s.d(s->in);
   p.hn_parent = s->hn_parent_s.d(s->in); p.job_soft = s->job_soft_s.d(s->in); p.job_alloc0 = s->job_alloc0_s.d(s->in);
   p.placed_off = s->placed_off_s.d(s->in); p.placed0 = s->placed0_s.d(s->in); p.placed_n0 = s->placed_n0_s.d(s->in);
-  p.rep_placed = s->rep_placed; p.placed_total = s->placed_total;
+  p.rep_placed = s->rep_placed; p.placed_total = s->placed_total; p.job_alloc_out = s->d_job_alloc;
   p.topo_nval = s->topo_nval;
   for (int i = 0; i < VC_MAX_TIERS + 2; ++i) p.topo_val[i] = s->topo_val[i];
 
@@ -1053,6 +1085,10 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->decisions.assign(s->h_decisions, s->h_decisions + n_dec);
   r->visits.assign(s->h_visits, s->h_visits + n_vis);
   r->fit_errors.assign(s->h_fit, s->h_fit + n_fit);
+  if (s->topo_any) {
+    r->job_alloc.resize(J);
+    CUDA_TRY(cudaMemcpy(r->job_alloc.data(), s->d_job_alloc, J * 4, cudaMemcpyDeviceToHost));
+  }
   float kms = 0;
   cudaEventElapsedTime(&kms, s->ev0, s->ev1);
   r->stats.upload_ms = s->upload_ms;
@@ -1080,6 +1116,10 @@ const vc_visit *vc_result_visits(const vc_result *r) { return r ? r->visits.data
 size_t vc_result_num_fit_errors(const vc_result *r) { return r ? r->fit_errors.size() : 0; }
 const int32_t *vc_result_fit_errors(const vc_result *r) { return r ? r->fit_errors.data() : nullptr; }
 const vc_stats *vc_result_stats(const vc_result *r) { return r ? &r->stats : nullptr; }
+const int32_t *vc_result_job_allocated_hypernodes(const vc_result *r, size_t *n_jobs) {
+  if (n_jobs) *n_jobs = r ? r->job_alloc.size() : 0;
+  return (r && !r->job_alloc.empty()) ? r->job_alloc.data() : nullptr;
+}
 void vc_result_free(vc_result *r) { delete r; }
 
 // ---------------------------------------------------------------------------------------

@@ -100,11 +100,16 @@ class Engine:
             dec = _struct_array(self.L.vc_result_decisions(r), nd, DECISION_DTYPE)
             vis = _struct_array(self.L.vc_result_visits(r), nv, VISIT_DTYPE)
             fe = np.ctypeslib.as_array(self.L.vc_result_fit_errors(r), (nf,)).copy() if nf else np.zeros(0, np.int32)
+            nj = C.c_size_t(0)
+            ja = self.L.vc_result_job_allocated_hypernodes(r, C.byref(nj))
+            job_alloc = np.ctypeslib.as_array(ja, (nj.value,)).copy() if nj.value else None
             st = self.L.vc_result_stats(r).contents
             stats = {k: (list(getattr(st, k)) if k == "prof_cycles" else getattr(st, k)) for k, _ in abi.vc_stats._fields_}
         finally:
             self.L.vc_result_free(r)
-        return AllocateResult(dec, vis, fe, stats)
+        res = AllocateResult(dec, vis, fe, stats)
+        res.job_allocated_hypernodes = job_alloc
+        return res
 
     def set_shard(self, begin: int, end: int):
         _check(self.L.vc_snapshot_set_shard(self.h, begin, end))

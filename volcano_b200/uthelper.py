@@ -26,6 +26,7 @@ class AllocateResult:
     visits: np.ndarray      # structured: job,outcome,first_op,n_ops
     fit_errors: np.ndarray  # int32 task indices
     stats: Optional[dict] = None
+    job_allocated_hypernodes: Optional[np.ndarray] = None  # subJob.AllocatedHyperNode after the run (topology sessions)
 
 
 @dataclass
