@@ -70,6 +70,7 @@ struct K2Params {
   int32_t *fit_errors;
   int32_t *counters;  // 0 n_decisions, 1 n_visits, 2 n_fit_errors, 3 n_steps, 4 error
   long long *prof;    // [8] phase cycle counters of CTA 0
+  long long *cta_wait;  // optional [n_cta]: cycles each CTA spent inside the all-gather (the straggler waits least)
   // ---- fast (incremental) kernel ----
   const int4 *tmeta;      // per position of task_order: {task, group, role row, 0}
   int n_groups;
@@ -92,6 +93,7 @@ struct K2Params {
   const double *hn_alloc;     // [R][H] hyperNodeResourceCache allocatable
   const double *hn_used0;     // [R][H] ... used at session open
   double *rep_hn_used;        // [n_cta][R][hn_cap] per-CTA live copy of `used` for the CTA's local hypernodes
+  int hn_smem;                // the CTA's hypernode tables (used, allocatable, ids) fit in shared memory
   // pods with a soft-mode network topology (k_commit<.,.,true>)
   int hn_min_tier;
   const int32_t *hn_up;       // [L][H] ancestor of hypernode h (Parent chain, h included) at tier level l, -1 none
@@ -223,19 +225,41 @@ __device__ __forceinline__ void local_fold(Local &a, const Local &b) {
     a.tk[k] = tk_fold(a.tk[k], b.tk[k]);
   }
 }
+// Warp-wide fold with the hardware reductions (redux.sync) instead of 5 shuffle rounds over 12 words: the
+// (score, node) arg-max goes through an order-preserving 64-bit key reduced as two 32-bit maxima, then the
+// lowest node among the lanes that hold the maximum (util.SelectBestNodeAndScore with the canonical tie-break).
+// TWO = false skips category 1 (no FutureIdle gradient in this kernel instance).
+__device__ __forceinline__ unsigned long long score_key(double x) {
+  x += 0.0;  // -0.0 -> +0.0, so equal scores have equal keys
+  return order_bits(x);
+}
+__device__ __forceinline__ double score_of_key(unsigned long long k) {
+  const unsigned long long u = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+template <bool TWO = true>
 __device__ __forceinline__ void local_warp_reduce(Local &l) {
+  constexpr unsigned FULLM = 0xffffffffu;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    Local b;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      b.score[k] = __shfl_xor_sync(0xffffffffu, l.score[k], o);
-      b.node[k] = __shfl_xor_sync(0xffffffffu, l.node[k], o);
-      b.cnt[k] = __shfl_xor_sync(0xffffffffu, l.cnt[k], o);
-      b.soft[k] = __shfl_xor_sync(0xffffffffu, l.soft[k], o);
-      b.tk[k] = __shfl_xor_sync(0xffffffffu, l.tk[k], o);
-    }
-    local_fold(l, b);
+  for (int k = 0; k < (TWO ? 2 : 1); ++k) {
+    const bool valid = l.node[k] >= 0;
+    const unsigned long long key = valid ? score_key(l.score[k]) : 0ull;
+    const unsigned hi = (unsigned)(key >> 32);
+    const unsigned mhi = __reduce_max_sync(FULLM, hi);
+    const unsigned lo = hi == mhi ? (unsigned)key : 0u;
+    const unsigned mlo = __reduce_max_sync(FULLM, lo);
+    const unsigned long long mkey = ((unsigned long long)mhi << 32) | mlo;
+    const bool is_max = valid && key == mkey;
+    const unsigned mnode = __reduce_min_sync(FULLM, is_max ? (unsigned)l.node[k] : 0xffffffffu);
+    if (mnode == 0xffffffffu) { l.node[k] = -1; l.score[k] = 0.0; }
+    else { l.node[k] = (int)mnode; l.score[k] = score_of_key(mkey); }
+    l.cnt[k] = (int)__reduce_add_sync(FULLM, (unsigned)l.cnt[k]);
+    // soft-taint maximum and the topology (code, count) pair share one word: soft in bits 0..7, tk above
+    const unsigned tcode = (unsigned)l.tk[k] >> 2;
+    const unsigned mcode = __reduce_max_sync(FULLM, tcode);
+    const unsigned tcnt = __reduce_add_sync(FULLM, tcode == mcode ? ((unsigned)l.tk[k] & 3u) : 0u);
+    l.tk[k] = (int)((mcode << 2) | min(2u, tcnt));
+    l.soft[k] = (int)__reduce_max_sync(FULLM, (unsigned)l.soft[k]);
   }
 }
 
@@ -274,7 +298,7 @@ __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigne
   Local acc;
   local_init(acc);
   for (int s0 = 0; s0 < G; s0 += 32 * 4) {  // up to 4 slots per lane in flight
-    uint4 a[4];
+    uint4 a[4], b[4], c[4];
     bool need[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) need[k] = (s0 + k * 32 + lane) < G;
@@ -283,26 +307,26 @@ __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigne
       pending = false;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (need[k]) a[k] = mbox_load(base + (size_t)(s0 + k * 32 + lane) * MBOX_STRIDE);
+        if (need[k]) {  // the three units of a slot share one 128-byte line: issue them together
+          const uint4 *sl = base + (size_t)(s0 + k * 32 + lane) * MBOX_STRIDE;
+          a[k] = mbox_load(sl);
+          if (FULL) { b[k] = mbox_load(sl + 1); c[k] = mbox_load(sl + 2); }
+        }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (!need[k]) continue;
-        const bool ok = FULL ? (a[k].w == seq) : ((a[k].w >> 2) == (seq & 0x3fffffffu));
+        const bool ok = FULL ? (a[k].w == seq && b[k].w == seq && c[k].w == seq) : ((a[k].w >> 2) == (seq & 0x3fffffffu));
         if (!ok) { pending = true; continue; }
         Local o;
         local_init(o);
         o.score[0] = __longlong_as_double((long long)((unsigned long long)a[k].x | ((unsigned long long)a[k].y << 32)));
         o.node[0] = (int)a[k].z;
         if (FULL) {
-          const uint4 *sl = base + (size_t)(s0 + k * 32 + lane) * MBOX_STRIDE;
-          uint4 b, c;
-          do { b = mbox_load(sl + 1); } while (b.w != seq);
-          do { c = mbox_load(sl + 2); } while (c.w != seq);
-          o.score[1] = __longlong_as_double((long long)((unsigned long long)b.x | ((unsigned long long)b.y << 32)));
-          o.node[1] = (int)b.z;
-          o.cnt[0] = (int)c.x; o.cnt[1] = (int)c.y;
-          o.soft[0] = (int)(c.z & 0xffu); o.soft[1] = (int)((c.z >> 8) & 0xffu);
-          o.tk[0] = (int)((c.z >> 16) & 0xffu); o.tk[1] = (int)(c.z >> 24);
+          o.score[1] = __longlong_as_double((long long)((unsigned long long)b[k].x | ((unsigned long long)b[k].y << 32)));
+          o.node[1] = (int)b[k].z;
+          o.cnt[0] = (int)c[k].x; o.cnt[1] = (int)c[k].y;
+          o.soft[0] = (int)(c[k].z & 0xffu); o.soft[1] = (int)((c[k].z >> 8) & 0xffu);
+          o.tk[0] = (int)((c[k].z >> 16) & 0xffu); o.tk[1] = (int)(c[k].z >> 24);
         } else {
           o.cnt[0] = (int)(a[k].w & 3u);
         }
@@ -311,7 +335,7 @@ __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigne
       }
     } while (pending);
   }
-  local_warp_reduce(acc);
+  local_warp_reduce<FULL>(acc);
   if (!FULL) acc.cnt[0] = min(acc.cnt[0], 2);
   return acc;
 }
@@ -503,13 +527,33 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   // the plugin's score of each distinct per-tier hypernode tuple ("chain") among the CTA's nodes
   sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 7) & ~(uintptr_t)7);
   double *hn_score = reinterpret_cast<double *>(sp); sp += (size_t)p.hn_cap * 8;
-  double *chain_val = reinterpret_cast<double *>(sp);
+  double *chain_val = reinterpret_cast<double *>(sp); sp += (size_t)p.chain_cap * 8;
+  int32_t *s_chain = reinterpret_cast<int32_t *>(sp);  // node -> chain of the CTA
   const int chain_base = c.nta_on ? p.cta_chain_off[cta] : 0;
   const int chain_n = c.nta_on ? p.cta_chain_off[cta + 1] - chain_base : 0;
+  if (c.nta_on)
+    for (int i = tid; i < nmine; i += blockDim.x) s_chain[i] = p.node_chain[nbase + i];
   const int hn_cap = p.hn_cap;
   const int hn_base = c.nta_tables ? p.cta_hn_off[cta] : 0;
   const int hn_n = c.nta_tables ? p.cta_hn_off[cta + 1] - hn_base : 0;
+  // live `used` of the CTA's hypernodes: shared memory when the local list is short (the usual tree), else an
+  // L2-resident per-CTA replica
   double *hn_used = c.nta_tables ? p.rep_hn_used + (size_t)cta * R * hn_cap : nullptr;
+  const double *hn_alloc_l = nullptr;  // [R][hn_cap] allocatable of the local hypernodes (shared-memory copy)
+  const int32_t *hn_ids = p.cta_hn + hn_base;
+  if (c.nta_tables && p.hn_smem) {
+    sp = reinterpret_cast<unsigned char *>(((uintptr_t)(s_chain + cap) + 7) & ~(uintptr_t)7);
+    hn_used = reinterpret_cast<double *>(sp); sp += (size_t)R * hn_cap * 8;
+    double *al = reinterpret_cast<double *>(sp); sp += (size_t)R * hn_cap * 8;
+    int32_t *ids = reinterpret_cast<int32_t *>(sp);
+    for (int k = tid; k < hn_n; k += blockDim.x) {
+      const int h = p.cta_hn[hn_base + k];
+      ids[k] = h;
+      for (int d = 0; d < R; ++d) al[d * hn_cap + k] = p.hn_alloc[(size_t)d * p.hn_H + h];
+    }
+    hn_alloc_l = al;
+    hn_ids = ids;
+  }
   for (int k = tid; k < hn_n; k += blockDim.x) {
     const int h = p.cta_hn[hn_base + k];
     for (int d = 0; d < R; ++d) hn_used[d * hn_cap + k] = p.hn_used0[(size_t)d * p.hn_H + h];
@@ -518,7 +562,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   // whose RealNodesSet holds the node; each CTA maintains the entries of its own local list
   auto hn_account = [&](int node, const double *req, size_t req_stride, uint32_t has, double sign) {
     for (int k = tid; k < hn_n; k += blockDim.x) {
-      const int h = p.cta_hn[hn_base + k];
+      const int h = hn_ids[k];
       bool hit = false;
       for (int l = 0; l < c.nta_L; ++l) hit = hit || p.hn_member[(size_t)l * N + node] == h;
       if (!hit) continue;
@@ -788,7 +832,6 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       PROF_MARK(1);
       // With a normalising batch scorer (SOFT) two passes are needed: pass 0 = categories, counts and the
       // max soft-taint count of the candidate set; pass 1 = scores.
-      constexpr int n_pass = SOFT ? 2 : 1;
       int g_soft0 = 0, g_soft1 = 0;
       // pods of a soft-mode topology job are scored by batchNodeOrderFnForNetworkAwarePods (:541-571) with
       // task.JobAllocatedHyperNode = the visit's allocatedHyperNode; no entries at all while that is ""
@@ -813,7 +856,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
           const int h = p.hn_member[lst[m]];
           if (h < 0) continue;
           for (int k = 0; k < hn_n; ++k)
-            if (p.cta_hn[hn_base + k] == h) atomicAdd(&hn_score[k], 1.0);
+            if (hn_ids[k] == h) atomicAdd(&hn_score[k], 1.0);
         }
         __syncthreads();
       }
@@ -840,10 +883,10 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       };
       if (c.nta_on && !topo_task) {  // getPodHyperNodeBinPackingScore(task, hypernode) for the CTA's hypernodes
         for (int k = tid; k < hn_n; k += blockDim.x) {
-          const int h = p.cta_hn[hn_base + k];
+          const int h = hn_ids[k];
           hn_score[k] = hn_binpack_score(
               c, R, trec, [&](int d) { return hn_used[d * hn_cap + k]; },
-              [&](int d) { return p.hn_alloc[(size_t)d * p.hn_H + h]; });
+              [&](int d) { return hn_alloc_l ? hn_alloc_l[d * hn_cap + k] : p.hn_alloc[(size_t)d * p.hn_H + h]; });
         }
         __syncthreads();
         for (int k = tid; k < chain_n; k += blockDim.x) {  // batchNodeOrderFnForNormalPods per distinct chain
@@ -852,12 +895,16 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
         }
         __syncthreads();
       }
+      // the first pass is only needed when something is normalised over the candidate set
+      const bool two_pass = SOFT && (c.soft_active || (TOPO && topo_scored));
+      const int n_pass = two_pass ? 2 : 1;
       for (int pass = 0; pass < n_pass; ++pass) {
         Local mine;
         local_init(mine);
         for (int i = tid; i < nmine; i += blockDim.x) {
           SmemNodeView nv{sn, i};
-          const uint32_t cs = cs_row[i];
+          // the class x node word is only needed to (re)evaluate the node or for the soft-taint count
+          const uint32_t cs = ((SOFT && c.soft_active) || c_group[i] != cur_group) ? cs_row[i] : 0u;
           int cat = 2;
           bool has_order = false;
           double order = 0.0;
@@ -887,7 +934,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
             tcode = topo_code(nbase + i);
             if (pass == 0) mine.tk[c0 ? 0 : 1] = tk_fold(mine.tk[c0 ? 0 : 1], (tcode << 2) | 1);
           }
-          if (SOFT && pass == 0) continue;
+          if (two_pass && pass == 0) continue;
           const int n = nbase + i;
           double nta = 0.0;
           if (TOPO && topo_task) {
@@ -902,7 +949,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
               nta = (double)VC_MAX_NODE_SCORE * (double)c.nta_weight * tsc;  // scaleFinalScore :758-764
             }
           } else if (c.nta_on) {
-            nta = chain_val[p.node_chain[n]];
+            nta = chain_val[s_chain[i]];
           }
           double sc = total_score(c, has_order, order, soft, c0 ? g_soft0 : g_soft1, nta);
           if (c0) {
@@ -912,7 +959,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
           }
         }
         // CTA-level fold
-        local_warp_reduce(mine);
+        local_warp_reduce<FUT>(mine);
         if (lane == 0) {
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
@@ -932,16 +979,18 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
               l.cnt[k] = S.w_cnt[k][lane]; l.soft[k] = S.w_soft[k][lane] & 0xff; l.tk[k] = S.w_soft[k][lane] >> 8;
             }
           }
-          local_warp_reduce(l);
+          local_warp_reduce<FUT>(l);
           const unsigned seq = S.seq + 1;
           __syncwarp();  // every lane has read S.seq before lane 0 advances it below
+          const long long tw0 = p.cta_wait ? clock64() : 0;
           Local g = exchange<(FUT || SOFT)>(p, l, seq);
+          if (p.cta_wait && lane == 0) p.cta_wait[cta] += clock64() - tw0;
           if (lane == 0) {
             S.seq = seq;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               S.cnt[k] = g.cnt[k]; S.best_node[k] = g.node[k]; S.best_score[k] = g.score[k]; S.max_soft[k] = g.soft[k];
-              if (SOFT && pass == 0) S.tk[k] = g.tk[k];
+              if (two_pass && pass == 0) S.tk[k] = g.tk[k];
             }
           }
           PROF_MARK(3);

@@ -132,7 +132,7 @@ struct vc_snapshot {
   int topo_nval = 0;
   double topo_val[VC_MAX_TIERS + 2]{};
   Slot<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn, node_chain, cta_chain_off, cta_chain;
-  int chain_cap = 1;
+  int chain_cap = 1, hn_smem = 0;
   Slot<double> hn_alloc, hn_used0;
   double *rep_hn_used = nullptr;
   size_t rep_hn_used_count = 0;
@@ -279,7 +279,7 @@ void choose_geometry(vc_snapshot *s) {
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 + 4) + 64;
     s->smem_bytes += (size_t)npc * (8 + 4 + 1) + 32;  // verdict cache
     // hn_score (at most npc * L local hypernodes) + chain_val (at most npc chains); hn_cap is set after this call
-    if (s->dc.nta_tables) s->smem_bytes += (size_t)npc * (s->hn_L + 1) * 8 + 32;
+    if (s->dc.nta_tables) s->smem_bytes += (size_t)npc * (s->hn_L + 1) * 8 + (size_t)npc * 4 + 32;
   }
 }
 
@@ -808,6 +808,8 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
       cta_chain_off[cta + 1] = cta_chain_off[cta] + (int32_t)chains.size();
       s->chain_cap = std::max<int>(s->chain_cap, (int)chains.size());
     }
+    s->hn_smem = (!s->fast && s->hn_cap <= 96) ? 1 : 0;
+    if (s->hn_smem) s->smem_bytes += 2 * R * (size_t)s->hn_cap * 8 + (size_t)s->hn_cap * 4 + 32;
   }
 
   // ---- plan + stage + one H2D copy ------------------------------------------------------
@@ -1047,6 +1049,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   p.rep_hn_used = s->rep_hn_used;
   p.node_chain = s->node_chain.d(s->in); p.cta_chain_off = s->cta_chain_off.d(s->in); p.cta_chain = s->cta_chain.d(s->in);
   p.chain_cap = s->chain_cap;
+  p.hn_smem = s->hn_smem;
   p.hn_min_tier = s->hn_min_tier; p.hn_up = s->hn_up.d(s->in); p.hn_tier = s->hn_tier_s.d(s->in);
   p.hn_parent = s->hn_parent_s.d(s->in); p.job_soft = s->job_soft_s.d(s->in); p.job_alloc0 = s->job_alloc0_s.d(s->in);
   p.placed_off = s->placed_off_s.d(s->in); p.placed0 = s->placed0_s.d(s->in); p.placed_n0 = s->placed_n0_s.d(s->in);
@@ -1054,6 +1057,12 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   p.topo_nval = s->topo_nval;
   for (int i = 0; i < VC_MAX_TIERS + 2; ++i) p.topo_val[i] = s->topo_val[i];
 
+  long long *d_wait = nullptr;
+  if (getenv("VC_PROF_WAIT")) {
+    CUDA_TRY(cudaMalloc(&d_wait, 1024 * 8));
+    CUDA_TRY(cudaMemsetAsync(d_wait, 0, 1024 * 8, s->stream));
+  }
+  p.cta_wait = d_wait;
   if (G > 1024) return fail(VC_EUNSUPPORTED, "too many CTAs");
   const void *kfn = s->fast ? (const void *)k_commit_fast : s->topo_any ? (const void *)k_commit<true, true, true> : s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
                                      : (s->dc.soft_active ? (const void *)k_commit<false, true> : (const void *)k_commit<false, false>);
@@ -1075,6 +1084,14 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * 4, cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaMemcpyAsync(s->h_prof, s->d_prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (d_wait) {
+    std::vector<long long> w(G);
+    cudaMemcpy(w.data(), d_wait, G * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_wait);
+    fprintf(stderr, "all-gather wait per CTA (Mcycles):");
+    for (int i = 0; i < G; ++i) fprintf(stderr, " %.0f", w[i] / 1e6);
+    fprintf(stderr, "\n");
+  }
   const double t_k = now_ms();
   const int n_dec = s->h_counters[0], n_vis = s->h_counters[1], n_fit = s->h_counters[2];
   if (n_dec) CUDA_TRY(cudaMemcpyAsync(s->h_decisions, s->d_decisions, (size_t)n_dec * sizeof(vc_decision), cudaMemcpyDeviceToHost, s->stream));
