@@ -213,9 +213,14 @@ __device__ __forceinline__ void load_record(void *dst_smem, const void *src_glob
   }
 }
 
+#define FAST_MAXQ 64  // queues mirrored in shared memory for the queue scan
 struct CtlFast {  // shared-memory state of the fast kernel next to Ctl
   JobStatic js;
   JobDyn jd;
+  JobStatic js2;  // head of the queue's static job list (the candidate the heap top is compared with)
+  JobDyn jd2;
+  double q_share[FAST_MAXQ];
+  int q_active[FAST_MAXQ];
   QueueStatic qs;
   QueueDyn qd;
   RoleStatic rs[VC_MAX_JOB_ROLES];
@@ -314,6 +319,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     qd.share = fp.q_share0[q];
     for (int d = 0; d < FAST_R; ++d) qd.alloc[d] = d < R ? p.q_alloc0[(size_t)d * Q + q] : 0.0;
     qdyn[q] = qd;
+    if (q < FAST_MAXQ) { F.q_active[q] = qd.active; F.q_share[q] = qd.share; }
   }
   if (tid == 0) {
     S.seq = 0;
@@ -603,15 +609,33 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     int pub_owner = -1, pub_node = -1;
     unsigned pub_pc = 0;
 
+    // Visit state that survives from one visit to the next: a re-pushed job is usually popped again right away
+    // (one task per visit once it is Ready, allocate.go:676), and a session often has few queues — so the queue
+    // and job records of the previous visit are kept in registers / shared memory and only reloaded from the
+    // L2-resident replica when the queue or the job actually changes.
+    const bool q_mirror = Q <= FAST_MAXQ;
+    int last_q = -1, last_j = -1, cand_tag = -1, cand_sc = -1, cand_js = -1;
+    int sbeg = 0, send = 0, q_scursor = 0, q_hsize = 0;
+    uint32_t qflags = 0, qdes_has = 0, qflags2 = 0, qalloc_has = 0;
+    double qshare = 0.0, qalloc_l = 0.0, qdes_l = 0.0;
+    HeapKey *h = heap;
+    int task_off = 0, task_end = 0, role_base = 0, nroles = 0, minav = 0, pbe = 0, taskmintotal = 0, ntasks_total = 0;
+    uint32_t jflags = 0;
+    unsigned long long jkey_pre = 0, jkey_post = 0;
+    int cursor = 0, ready = 0, waiting = 0, n_ops = 0;
+    double jshare = 0.0, jalloc_l = 0.0;
+    bool role_min_active = false, pure = false;
+    int4 meta = make_int4(0, 0, 0, 0);
+
     for (;;) {
       // ---- queues.Pop(): arg-min by ssn.QueueOrderFn over the active queues ----
       int bq = -1, bprio = 0;
       double bshare = 0.0;
       uint32_t brank = 0;
       for (int q = lane; q < Q; q += 32) {
-        if (!qdyn[q].active) continue;
+        if (!(q_mirror ? F.q_active[q] : qdyn[q].active)) continue;
         int pr = f_qorder_prop ? __ldg(&fp.qstat[q].prio) : 0;
-        double sh = f_qorder_prop ? qdyn[q].share : 0.0;
+        double sh = f_qorder_prop ? (q_mirror ? F.q_share[q] : qdyn[q].share) : 0.0;
         uint32_t rk = __ldg(&fp.qstat[q].rank);
         bool lt = bq < 0 || pr > bprio || (pr == bprio && (sh < bshare || (sh == bshare && rk < brank)));
         if (lt) { bq = q; bprio = pr; bshare = sh; brank = rk; }
@@ -628,17 +652,21 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       if (q < 0) break;
       __syncwarp();
       // ---- queue records (one coalesced access each), head of the static job list, heap top ----
-      load_record(&F.qs, &fp.qstat[q], sizeof(QueueStatic) / 4, true);
-      load_record(&F.qd, &qdyn[q], sizeof(QueueDyn) / 4, false);
-      const int sbeg = __ldg(&p.qjobs_off[q]), send = __ldg(&p.qjobs_off[q + 1]);
-      __syncwarp();
-      const uint32_t qflags = F.qs.flags, qdes_has = F.qs.des_has;
-      uint32_t qflags2 = F.qd.flags2, qalloc_has = F.qd.alloc_has;
-      int q_scursor = F.qd.scursor, q_hsize = F.qd.hsize;
-      double qshare = F.qd.share;
-      // one dimension per lane
-      double qalloc_l = lane < R ? F.qd.alloc[lane] : 0.0;
-      const double qdes_l = lane < R ? F.qs.des[lane] : 0.0;
+      if (q != last_q) {
+        load_record(&F.qs, &fp.qstat[q], sizeof(QueueStatic) / 4, true);
+        load_record(&F.qd, &qdyn[q], sizeof(QueueDyn) / 4, false);
+        sbeg = __ldg(&p.qjobs_off[q]); send = __ldg(&p.qjobs_off[q + 1]);
+        h = heap + __ldg(&fp.heap_off[q]);
+        __syncwarp();
+        qflags = F.qs.flags; qdes_has = F.qs.des_has;
+        qflags2 = F.qd.flags2; qalloc_has = F.qd.alloc_has;
+        q_scursor = F.qd.scursor; q_hsize = F.qd.hsize;
+        qshare = F.qd.share;
+        // one dimension per lane
+        qalloc_l = lane < R ? F.qd.alloc[lane] : 0.0;
+        qdes_l = lane < R ? F.qs.des[lane] : 0.0;
+        last_q = q; last_j = -1; cand_tag = -1; cand_sc = -1;
+      }
       // ssn.Overused: attr.deserved.LessEqual(attr.allocated, Zero), proportion.go:319-331
       bool over = false;
       if (f_over_prop && (qflags2 & 1u)) {
@@ -650,15 +678,23 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         over = __all_sync(0xffffffffu, ok);
       }
       int j = -1;
+      bool job_loaded = false;  // F.js / F.jd hold records that differ from the register state
       if (!over) {
-        HeapKey *h = heap + __ldg(&fp.heap_off[q]);
         const int sc = sbeg + q_scursor;
         const int hs = q_hsize;
         const bool have_s = sc < send, have_h = hs > 0;
-        const int js = have_s ? __ldg(&p.qjobs[sc]) : -1;
-        if (have_s) {  // records of the static candidate: needed for the comparison and, if chosen, as the job state
-          load_record(&F.js, &fp.jstat[js], sizeof(JobStatic) / 4, true);
-          load_record(&F.jd, &jdyn[js], sizeof(JobDyn) / 4, false);
+        int js = -1;
+        if (have_s) {
+          if (sc != cand_sc) { cand_js = __ldg(&p.qjobs[sc]); cand_sc = sc; }
+          js = cand_js;
+        }
+        if (have_s && cand_tag != js) {
+          // records of the static candidate: needed for the comparison and, if chosen, as the job state; a job
+          // at the head of the static list has not been visited yet, so its records cannot go stale
+          __syncwarp();
+          load_record(&F.js2, &fp.jstat[js], sizeof(JobStatic) / 4, true);
+          load_record(&F.jd2, &jdyn[js], sizeof(JobDyn) / 4, false);
+          cand_tag = js;
         }
         HeapKey top;
         if (have_h) top = h[0];
@@ -666,11 +702,11 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         bool from_heap = false;
         if (have_s && have_h) {
           HeapKey ks;
-          ks.pre = F.js.key_pre; ks.post = F.js.key_post;
-          const bool rdy = F.jd.ready + F.js.pending_besteffort >= F.js.min_available;
+          ks.pre = F.js2.key_pre; ks.post = F.js2.key_post;
+          const bool rdy = F.jd2.ready + F.js2.pending_besteffort >= F.js2.min_available;
           if (rdy && fp.ready_word == 1) ks.pre |= 1ull << fp.ready_shift;
           if (rdy && fp.ready_word == 2) ks.post |= 1ull << fp.ready_shift;
-          ks.share = fp.share_on ? (unsigned long long)__double_as_longlong(F.jd.share) : 0ull;
+          ks.share = fp.share_on ? (unsigned long long)__double_as_longlong(F.jd2.share) : 0ull;
           from_heap = hk_less(top, ks);
         } else if (have_h) {
           from_heap = true;
@@ -697,48 +733,65 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           }
           q_hsize = hs - 1;
           __syncwarp();
-          load_record(&F.js, &fp.jstat[j], sizeof(JobStatic) / 4, true);
-          load_record(&F.jd, &jdyn[j], sizeof(JobDyn) / 4, false);
+          if (j != last_j) {  // otherwise the registers still hold this job's state from its previous visit
+            load_record(&F.js, &fp.jstat[j], sizeof(JobStatic) / 4, true);
+            load_record(&F.jd, &jdyn[j], sizeof(JobDyn) / 4, false);
+            job_loaded = true;
+          }
         } else if (have_s) {
           j = js;
           q_scursor += 1;
+          __syncwarp();
+          for (int w = lane; w < (int)(sizeof(JobStatic) / 4); w += 32)
+            reinterpret_cast<int *>(&F.js)[w] = reinterpret_cast<const int *>(&F.js2)[w];
+          for (int w = lane; w < (int)(sizeof(JobDyn) / 4); w += 32)
+            reinterpret_cast<int *>(&F.jd)[w] = reinterpret_cast<const int *>(&F.jd2)[w];
+          cand_tag = -1;
+          job_loaded = true;
         }
       }
       __syncwarp();
       if (j < 0) {  // queue dropped: overused, or no jobs left (allocate.go:295-305)
-        if (lane == 0) { qdyn[q].active = 0; qdyn[q].scursor = q_scursor; qdyn[q].hsize = q_hsize; }
+        if (lane == 0) {
+          qdyn[q].active = 0; qdyn[q].scursor = q_scursor; qdyn[q].hsize = q_hsize;
+          if (q_mirror) F.q_active[q] = 0;
+        }
         __syncwarp();
         continue;
       }
       // ---- job state into registers; roles into the shared role tables ----
-      const int task_off = F.js.task_off, task_end = F.js.task_end;
-      const int role_base = F.js.role_off, nroles = F.js.n_roles;
-      const int minav = F.js.min_available, pbe = F.js.pending_besteffort, taskmintotal = F.js.task_min_total;
-      const int ntasks_total = F.js.n_tasks_total;
-      const uint32_t jflags = F.js.flags;
-      const unsigned long long jkey_pre = F.js.key_pre, jkey_post = F.js.key_post;
-      int cursor = task_off + F.jd.cursor, ready = F.jd.ready, waiting = F.jd.waiting, n_ops = 0;
-      double jshare = F.jd.share;
-      double jalloc_l = lane < R ? F.jd.alloc[lane] : 0.0;
-      bool role_min_any = false;
-      for (int r = lane; r < nroles; r += 32) {
-        const RoleStatic rs = fp.rstat[role_base + r];
-        const RoleDyn rd = rdyn[role_base + r];
-        S.r_occ[r] = rd.occ; S.r_pip[r] = rd.pip; S.r_pending[r] = rd.pending; S.r_failed[r] = (uint8_t)rd.failed;
-        S.r_min[r] = rs.min; S.r_flags[r] = rs.flags;
-        if (rs.flags & VC_ROLE_IN_MIN_MAP) role_min_any = true;
+      n_ops = 0;
+      if (job_loaded) {
+        task_off = F.js.task_off; task_end = F.js.task_end;
+        role_base = F.js.role_off; nroles = F.js.n_roles;
+        minav = F.js.min_available; pbe = F.js.pending_besteffort; taskmintotal = F.js.task_min_total;
+        ntasks_total = F.js.n_tasks_total;
+        jflags = F.js.flags;
+        jkey_pre = F.js.key_pre; jkey_post = F.js.key_post;
+        cursor = task_off + F.jd.cursor; ready = F.jd.ready; waiting = F.jd.waiting;
+        jshare = F.jd.share;
+        jalloc_l = lane < R ? F.jd.alloc[lane] : 0.0;
+        bool role_min_any = false;
+        for (int r = lane; r < nroles; r += 32) {
+          const RoleStatic rs = fp.rstat[role_base + r];
+          const RoleDyn rd = rdyn[role_base + r];
+          S.r_occ[r] = rd.occ; S.r_pip[r] = rd.pip; S.r_pending[r] = rd.pending; S.r_failed[r] = (uint8_t)rd.failed;
+          S.r_min[r] = rs.min; S.r_flags[r] = rs.flags;
+          if (rs.flags & VC_ROLE_IN_MIN_MAP) role_min_any = true;
+        }
+        role_min_any = __any_sync(0xffffffffu, role_min_any);
+        // CheckTaskReady (job_info.go:1024-1036) can only fail when role minima are in force
+        role_min_active = role_min_any && !(minav < taskmintotal);
+        if (lane == 0) {
+          S.minav = minav; S.taskmintotal = taskmintotal; S.nroles = nroles; S.pbe = pbe; S.ntasks_total = ntasks_total;
+          S.role_base = role_base;
+        }
+        pure = (jflags & VC_JOBX_PURE) != 0;
+        meta = __ldg(&p.tmeta[cursor]);
       }
-      role_min_any = __any_sync(0xffffffffu, role_min_any);
-      // CheckTaskReady (job_info.go:1024-1036) can only fail when role minima are in force
-      const bool role_min_active = role_min_any && !(minav < taskmintotal);
-      if (lane == 0) {
-        S.minav = minav; S.taskmintotal = taskmintotal; S.nroles = nroles; S.pbe = pbe; S.ntasks_total = ntasks_total;
-        S.role_base = role_base;
-      }
+      last_j = j;
       visit_id += 1;  // util.NewPredicateHelper(): a fresh error cache per visit
       __syncwarp();
-      const bool pure = (jflags & VC_JOBX_PURE) != 0;
-      int4 meta = __ldg(&p.tmeta[cursor]);
       // ssn.JobReady (session_plugins.go:428-446) on the register state
       auto job_ready_now = [&]() -> bool {
         if (!f_gang_ready) return true;
@@ -1044,7 +1097,6 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           if (rdy && fp.ready_word == 1) e.pre |= 1ull << fp.ready_shift;
           if (rdy && fp.ready_word == 2) e.post |= 1ull << fp.ready_shift;
           e.share = fp.share_on ? (unsigned long long)__double_as_longlong(jshare) : 0ull;
-          HeapKey *h = heap + __ldg(&fp.heap_off[q]);
           int i = q_hsize;
           while (i > 0) {
             int par = (i - 1) / 2;
@@ -1065,6 +1117,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         QueueDyn *qd = &qdyn[q];
         qd->alloc_has = qalloc_has; qd->flags2 = qflags2; qd->active = 1;  // queues.Push(queue), allocate.go:346
         qd->scursor = q_scursor; qd->hsize = q_hsize; qd->share = qshare;
+        if (q_mirror) { F.q_active[q] = 1; F.q_share[q] = qshare; }
       }
       if (lane < R) { jdyn[j].alloc[lane] = jalloc_l; qdyn[q].alloc[lane] = qalloc_l; }
       for (int r = lane; r < nroles; r += 32) {
