@@ -118,14 +118,20 @@ __device__ __forceinline__ void best_fold(Best &a, double s, int n, int cnt) {
   if (n >= 0 && (a.node < 0 || better(s, n, a.score, a.node))) { a.score = s; a.node = n; }
   a.cnt += cnt;
 }
+// warp arg-max with the hardware reductions: order-preserving 64-bit key as two 32-bit maxima, then the lowest
+// node among the lanes that hold the maximum (see local_warp_reduce in vc_commit.cuh)
 __device__ __forceinline__ void best_warp_reduce(Best &b) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    double os = __shfl_xor_sync(0xffffffffu, b.score, o);
-    int on = __shfl_xor_sync(0xffffffffu, b.node, o);
-    int oc = __shfl_xor_sync(0xffffffffu, b.cnt, o);
-    best_fold(b, os, on, oc);
-  }
+  constexpr unsigned FULLM = 0xffffffffu;
+  const bool valid = b.node >= 0;
+  const unsigned long long key = valid ? score_key(b.score) : 0ull;
+  const unsigned hi = (unsigned)(key >> 32);
+  const unsigned mhi = __reduce_max_sync(FULLM, hi);
+  const unsigned mlo = __reduce_max_sync(FULLM, hi == mhi ? (unsigned)key : 0u);
+  const unsigned long long mkey = ((unsigned long long)mhi << 32) | mlo;
+  const unsigned mnode = __reduce_min_sync(FULLM, (valid && key == mkey) ? (unsigned)b.node : 0xffffffffu);
+  b.cnt = (int)__reduce_add_sync(FULLM, (unsigned)b.cnt);
+  if (mnode == 0xffffffffu) { b.node = -1; b.score = 0.0; }
+  else { b.node = (int)mnode; b.score = score_of_key(mkey); }
 }
 __device__ __forceinline__ uint4 pack_best(const Best &b, unsigned tag) {
   unsigned long long sb = (unsigned long long)__double_as_longlong(b.score);
@@ -190,17 +196,10 @@ __device__ __forceinline__ Best fold_slots(const FastSmem &fs, int G, int *owner
     best_fold(g, fs.sl_score[s], fs.sl_node[s], fs.sl_cnt[s]);
     if (g.node != before) owner = s;
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    double os = __shfl_xor_sync(0xffffffffu, g.score, o);
-    int on = __shfl_xor_sync(0xffffffffu, g.node, o);
-    int oc = __shfl_xor_sync(0xffffffffu, g.cnt, o);
-    int oo = __shfl_xor_sync(0xffffffffu, owner, o);
-    const int before = g.node;
-    best_fold(g, os, on, oc);
-    if (g.node != before) owner = oo;
-  }
-  *owner_out = owner;
+  const int my_node = g.node;
+  best_warp_reduce(g);
+  // the winning node sits in exactly one slot: the lane whose local best it is knows the owner
+  *owner_out = (int)__reduce_max_sync(0xffffffffu, (unsigned)((g.node >= 0 && my_node == g.node) ? owner + 1 : 0)) - 1;
   return g;
 }
 
