@@ -541,11 +541,16 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   double *hn_used = c.nta_tables ? p.rep_hn_used + (size_t)cta * R * hn_cap : nullptr;
   const double *hn_alloc_l = nullptr;  // [R][hn_cap] allocatable of the local hypernodes (shared-memory copy)
   const int32_t *hn_ids = p.cta_hn + hn_base;
+  double *hn_term = nullptr;  // [hn_cap][R] scratch of the per-step hypernode scores
+  uint8_t *hn_flag = nullptr;
   if (c.nta_tables && p.hn_smem) {
     sp = reinterpret_cast<unsigned char *>(((uintptr_t)(s_chain + cap) + 7) & ~(uintptr_t)7);
     hn_used = reinterpret_cast<double *>(sp); sp += (size_t)R * hn_cap * 8;
     double *al = reinterpret_cast<double *>(sp); sp += (size_t)R * hn_cap * 8;
-    int32_t *ids = reinterpret_cast<int32_t *>(sp);
+    int32_t *ids = reinterpret_cast<int32_t *>(sp); sp += (size_t)hn_cap * 4;
+    sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 7) & ~(uintptr_t)7);
+    hn_term = reinterpret_cast<double *>(sp); sp += (size_t)R * hn_cap * 8;
+    hn_flag = reinterpret_cast<uint8_t *>(sp);
     for (int k = tid; k < hn_n; k += blockDim.x) {
       const int h = p.cta_hn[hn_base + k];
       ids[k] = h;
@@ -882,11 +887,45 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
         return code;
       };
       if (c.nta_on && !topo_task) {  // getPodHyperNodeBinPackingScore(task, hypernode) for the CTA's hypernodes
-        for (int k = tid; k < hn_n; k += blockDim.x) {
-          const int h = hn_ids[k];
-          hn_score[k] = hn_binpack_score(
-              c, R, trec, [&](int d) { return hn_used[d * hn_cap + k]; },
-              [&](int d) { return hn_alloc_l ? hn_alloc_l[d * hn_cap + k] : p.hn_alloc[(size_t)d * p.hn_H + h]; });
+        if (hn_term) {
+          // one thread per (hypernode, resource): the division of every term in parallel, then the terms are
+          // summed per hypernode in resource order exactly as the scalar loop does
+          for (int idx = tid; idx < hn_n * R; idx += blockDim.x) {
+            const int k = idx / R, d = idx - k * R;
+            const double request = trec.req[d];
+            const int w = c.nta_dim_weight[d];
+            const bool on = (d < 2 || (trec.has & (1u << d))) && request >= VC_MIN_RESOURCE && w >= 0;
+            double term = 0.0;
+            uint8_t flag = 0;
+            if (on) {
+              const double u = hn_used[d * hn_cap + k], al = hn_alloc_l[d * hn_cap + k];
+              if (u + request > al) flag = 3;
+              else { flag = 1; term = (double)w * ((u + request) / al); }
+            }
+            hn_term[idx] = term;
+            hn_flag[idx] = flag;
+          }
+          __syncthreads();
+          for (int k = tid; k < hn_n; k += blockDim.x) {
+            double total = 0.0;
+            int wsum = 0;
+            bool over = false;
+            for (int d = 0; d < R; ++d) {
+              const uint8_t f = hn_flag[k * R + d];
+              if (!(f & 1)) continue;
+              if (f & 2) { over = true; break; }
+              total += hn_term[k * R + d];
+              wsum += c.nta_dim_weight[d];
+            }
+            hn_score[k] = (over || wsum <= 0) ? 0.0 : total / (double)wsum;
+          }
+        } else {
+          for (int k = tid; k < hn_n; k += blockDim.x) {
+            const int h = hn_ids[k];
+            hn_score[k] = hn_binpack_score(
+                c, R, trec, [&](int d) { return hn_used[d * hn_cap + k]; },
+                [&](int d) { return hn_alloc_l ? hn_alloc_l[d * hn_cap + k] : p.hn_alloc[(size_t)d * p.hn_H + h]; });
+          }
         }
         __syncthreads();
         for (int k = tid; k < chain_n; k += blockDim.x) {  // batchNodeOrderFnForNormalPods per distinct chain
@@ -1037,42 +1076,63 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       }
       if (c.nta_on) hn_account(best, trec.req, 1, trec.has, 1.0);
       __syncthreads();
-      if (tid == 0) {
-        // job.UpdateTaskStatus (job_info.go:651-660) + event handlers (drf.go:391-418, proportion.go:475-497)
-        S.r_pending[rl] -= 1;
-        if (kind == VC_OP_ALLOCATE) { S.r_occ[rl] += 1; S.ready += 1; }
-        else { S.r_pip[rl] += 1; S.waiting += 1; }
+      // job.UpdateTaskStatus (job_info.go:651-660) + event handlers (drf.go:391-418, proportion.go:475-497):
+      // warp 0, one resource dimension per lane (the same IEEE operations as the scalar helpers drf_share /
+      // queue_share: every share is >= 0, so the running `if (sh > res)` maximum is a lane-wise fmax)
+      if (warp == 0) {
+        if (lane == 0) {
+          S.r_pending[rl] -= 1;
+          if (kind == VC_OP_ALLOCATE) { S.r_occ[rl] += 1; S.ready += 1; }
+          else { S.r_pip[rl] += 1; S.waiting += 1; }
+          const int k = S.n_ops;
+          ops[k * 3 + 0] = t; ops[k * 3 + 1] = best; ops[k * 3 + 2] = kind;
+          ops_score[k] = score;
+          S.n_ops = k + 1;
+        }
         if (c.has_drf) {
-          for (int d = 0; d < R; ++d) S.jalloc[d] += trec.req[d];
-          S.jshare = drf_share(p, S.jalloc);
+          double sh = 0.0;
+          if (lane < R) {
+            const double a = S.jalloc[lane] + trec.req[lane];
+            S.jalloc[lane] = a;
+            if ((lane < 2 || (p.total_has & (1u << lane))) && p.total[lane] >= VC_MIN_RESOURCE) sh = share_of(a, p.total[lane]);
+          }
+          for (int o = 16; o; o >>= 1) sh = fmax(sh, __shfl_xor_sync(0xffffffffu, sh, o));
+          if (lane == 0) S.jshare = sh;
         }
         if (c.has_proportion && (S.qflags2 & 1u)) {
-          S.qalloc[0] += trec.req[0];
-          S.qalloc[1] += trec.req[1];
-          for (int d = 2; d < R; ++d)
-            if (trec.has & (1u << d)) { S.qalloc[d] += trec.req[d]; S.qalloc_has |= 1u << d; S.qflags2 &= ~2u; }
-          S.qshare = queue_share(R, S.qalloc, S.qalloc_has, S.qdes, S.qdes_has);
-        }
-        if (TOPO && S.job_soft) {
-          placed[p.placed_off[j] + S.nplaced] = best;  // task.NodeName = hostname
-          S.nplaced += 1;
-          // getNewAllocatedHyperNode, allocate.go:697-707
-          const int hn = p.hn_member[best];
-          if (hn >= 0) {
-            if (S.topo_A < 0) {
-              S.topo_A = hn;
-            } else {
-              int lca = -1;
-              for (int a = S.topo_A, guard = 0; a >= 0 && guard < VC_MAX_TIERS + 2; a = p.hn_parent[a], ++guard)
-                if (p.hn_up[(size_t)(p.hn_tier[a] - p.hn_min_tier) * p.hn_H + hn] == a) { lca = a; break; }
-              S.topo_A = lca;
-            }
+          const uint32_t add_has = trec.has & ~3u & ((R >= 32) ? ~0u : ((1u << R) - 1u));
+          const uint32_t new_has = S.qalloc_has | add_has;
+          double sh = 0.0;
+          if (lane < R) {
+            double al = S.qalloc[lane];
+            if (lane < 2 || (add_has & (1u << lane))) { al += trec.req[lane]; S.qalloc[lane] = al; }
+            if ((lane < 2 || (S.qdes_has & (1u << lane))) && S.qdes[lane] >= VC_MIN_RESOURCE)
+              sh = share_of((lane < 2 || (new_has & (1u << lane))) ? al : 0.0, S.qdes[lane]);
+          }
+          for (int o = 16; o; o >>= 1) sh = fmax(sh, __shfl_xor_sync(0xffffffffu, sh, o));
+          __syncwarp();
+          if (lane == 0) {
+            S.qalloc_has = new_has;
+            if (add_has) S.qflags2 &= ~2u;
+            S.qshare = sh;
           }
         }
-        const int k = S.n_ops;
-        ops[k * 3 + 0] = t; ops[k * 3 + 1] = best; ops[k * 3 + 2] = kind;
-        ops_score[k] = score;
-        S.n_ops = k + 1;
+      }
+      if (TOPO && tid == 32 && S.job_soft) {
+        placed[p.placed_off[j] + S.nplaced] = best;  // task.NodeName = hostname
+        S.nplaced += 1;
+        // getNewAllocatedHyperNode, allocate.go:697-707
+        const int hn = p.hn_member[best];
+        if (hn >= 0) {
+          if (S.topo_A < 0) {
+            S.topo_A = hn;
+          } else {
+            int lca = -1;
+            for (int a = S.topo_A, guard = 0; a >= 0 && guard < VC_MAX_TIERS + 2; a = p.hn_parent[a], ++guard)
+              if (p.hn_up[(size_t)(p.hn_tier[a] - p.hn_min_tier) * p.hn_H + hn] == a) { lca = a; break; }
+            S.topo_A = lca;
+          }
+        }
       }
       __syncthreads();
       if (ctl_job_ready(c, S)) break;  // ssn.SubJobReady, allocate.go:676-678

@@ -809,7 +809,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
       s->chain_cap = std::max<int>(s->chain_cap, (int)chains.size());
     }
     s->hn_smem = (!s->fast && s->hn_cap <= 96) ? 1 : 0;
-    if (s->hn_smem) s->smem_bytes += 2 * R * (size_t)s->hn_cap * 8 + (size_t)s->hn_cap * 4 + 32;
+    if (s->hn_smem) s->smem_bytes += 3 * R * (size_t)s->hn_cap * 8 + R * (size_t)s->hn_cap + (size_t)s->hn_cap * 4 + 64;
   }
 
   // ---- plan + stage + one H2D copy ------------------------------------------------------

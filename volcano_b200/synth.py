@@ -65,6 +65,10 @@ CONFIGS = {
                               soft_taint_p=0.08),
     "small_fut_soft": SynthConfig("small_fut_soft", 300, 1500, 4, "priority+gang+drf+predicates+proportion+nodeorder+binpack",
                                   n_classes=16, utilisation=0.99, min_util=0.88, releasing_frac=0.5, soft_taint_p=0.08),
+    # cfg4's plugin set on a size that profiles in seconds
+    "mid_topo": SynthConfig("mid_topo", 20_000, 40_000, 16,
+                            "priority+gang+drf+predicates+proportion+nodeorder+binpack+network-topology-aware", topology=(16, 20),
+                            soft_topology_frac=0.1),
     "tiny_topo": SynthConfig("tiny_topo", 96, 400, 2, "priority+gang+drf+predicates+proportion+nodeorder+binpack+network-topology-aware",
                              n_classes=8, topology=(2, 3), topology_scatter=0.1, soft_topology_frac=0.3),
     "small_topo": SynthConfig("small_topo", 600, 3000, 3, "priority+gang+predicates+nodeorder+binpack+network-topology-aware",
