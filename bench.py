@@ -106,6 +106,13 @@ def run_oracle(snap, threads):
     return len(dec), dt
 
 
+def workload_desc(name):
+    from volcano_b200.synth import CONFIGS
+    cfg = CONFIGS[name]
+    return (f"{name}: {cfg.n_nodes} nodes x {cfg.n_tasks} tasks, R=8, {cfg.plugins}, "
+            "percentage-nodes-to-find=100 (parity mode)")
+
+
 def reference_arm(args, rank, world):
     """The reference's CPU implementation of the path = oracle port (kind "port"), all usable host threads
     (the reference runs 16 workers per task: util/predicate_helper.go:133)."""
@@ -127,8 +134,7 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "pods/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD}: 10k nodes x 100k tasks, R=8, gang+predicates+nodeorder+binpack, "
-                               "percentage-nodes-to-find=100 (parity mode)"},
+        "config": {"workload": workload_desc(WORKLOAD)},
         "cpu_baseline": {"value": val, "unit": "pods/s", "cores": threads, "kind": "port",
                          "sample": "full workload, one allocate cycle per step"},
         "e2e": {"value": val, "unit": "pods/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -260,8 +266,7 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": 1e3 * t_dev / args.steps,
             "cycle_ms_p50": statistics.median(dev_ms), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {cfg.n_nodes} nodes x {cfg.n_tasks} tasks, R=8, {cfg.plugins}, "
-                                   "percentage-nodes-to-find=100 (parity mode)",
+            "config": {"workload": workload_desc(args.workload),
                        "parallelism": "1 scheduler shard per GPU" if world > 1 else "1 GPU",
                        "l2": "256 MB buffer written between timed iterations",
                        "timed_region": "k_commit (CUDA events on its stream); e2e = upload + run + fetch wall time",
