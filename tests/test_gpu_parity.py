@@ -194,11 +194,13 @@ def test_deserved_vs_oracle(gpu):
     assert np.array_equal(des, odes) and np.array_equal(share, oshare)
 
 
-def test_full_size_properties(gpu):
-    """BASELINE configs[1] (10k x 100k): size-independent properties — every decision respects capacity,
-    re-running is idempotent, gang minAvailable holds for every committed job."""
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4"])
+def test_full_size_properties(cfg, gpu):
+    """BASELINE configs[1..3] at full size (10k x 100k; + drf / proportion over 16 queues; 50k x 1M with the HyperNode
+    tree and network-topology-aware): size-independent properties — every decision respects capacity, re-running is
+    idempotent, gang minAvailable holds for every committed job."""
     from volcano_b200.synth import make_snapshot
-    snap = make_snapshot("cfg2")
+    snap = make_snapshot(cfg)
     e = gpu.Engine(snap)
     e.upload()
     r1 = e.allocate()
