@@ -160,6 +160,10 @@ def main():
             print(f"seed {seed}: {e}")
             continue
         ok = (np.array_equal(dec, r.decisions) and np.array_equal(vis, r.visits) and np.array_equal(fe, r.fit_errors))
+        if snap.hn_job_soft is not None and snap.hn_job_soft.any():
+            from oracle import pyoracle
+            ja = np.array([pyoracle.lib().vco_job_allocated_hypernode(o.h, j) for j in range(snap.J)], np.int32)
+            ok = ok and r.job_allocated_hypernodes is not None and np.array_equal(ja, r.job_allocated_hypernodes)
         if not ok:
             bad += 1
             k = next((i for i in range(min(len(dec), len(r.decisions))) if dec[i] != r.decisions[i]), -1)

@@ -686,12 +686,15 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   }
   // per-queue heap capacity: only jobs that can be Ready with tasks left are ever re-pushed (allocate.go:334-336)
   std::vector<int32_t> heap_off(Q + 1, 0);
+  const bool gang_ready = vch::plugin_enabled(*conf, VC_PLUGIN_GANG, VC_EN_JOB_READY);
   for (size_t q = 0; q < Q; ++q) {
     int cnt = 0;
     for (int k = qjobs_off[q]; k < qjobs_off[q + 1]; ++k) {
       const int j = qjobs[k];
       const int scope = job_task_off[j + 1] - job_task_off[j];
-      if (jb->ready_num[j] + jb->pending_besteffort[j] + scope > jb->min_available[j]) ++cnt;
+      // with gang's JobReadyFn: Ready with a task left needs ready + bestEffort + (scope - 1) >= minAvailable;
+      // without it ssn.JobReady is always true and every job with a second task comes back
+      if (gang_ready ? (jb->ready_num[j] + jb->pending_besteffort[j] + scope > jb->min_available[j]) : (scope >= 2)) ++cnt;
     }
     heap_off[q + 1] = heap_off[q] + cnt;
   }
@@ -1105,6 +1108,34 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   if (s->topo_any) {
     r->job_alloc.resize(J);
     CUDA_TRY(cudaMemcpy(r->job_alloc.data(), s->d_job_alloc, J * 4, cudaMemcpyDeviceToHost));
+  } else if (!s->h_job_soft.empty() && !s->h_member.empty()) {
+    // soft-mode topology jobs without the plugin: allocate.go still tracks the allocated hypernode
+    // (:572, :672-674, :681-686); nothing on the device reads it, so replay the visits on the host
+    bool any = false;
+    for (uint8_t f : s->h_job_soft) any = any || f;
+    if (any) {
+      r->job_alloc = s->h_job_alloc;
+      const int H = s->hn_H;
+      auto ancestor_of = [&](int a, int hn) {  // is `a` on the Parent chain of hn (hn included)?
+        for (int x = hn, g = 0; x >= 0 && g < VC_MAX_TIERS + 2; x = s->h_parent[x], ++g)
+          if (x == a) return true;
+        return false;
+      };
+      for (const vc_visit &v : r->visits) {
+        if (!s->h_job_soft[v.job] || v.n_ops == 0) continue;
+        int a = r->job_alloc[v.job];
+        for (int k = v.first_op; k < v.first_op + v.n_ops; ++k) {
+          const int hn = s->h_member[r->decisions[k].node];  // util.FindHyperNodeForNode: lowest tier only
+          if (hn < 0 || hn >= H) continue;
+          if (a < 0) { a = hn; continue; }
+          int lca = -1;  // GetLCAHyperNode(hn, a): first ancestor of `a` that is an ancestor of hn
+          for (int x = a, g = 0; x >= 0 && g < VC_MAX_TIERS + 2; x = s->h_parent[x], ++g)
+            if (ancestor_of(x, hn)) { lca = x; break; }
+          a = lca;
+        }
+        if (v.outcome == VC_VISIT_COMMIT) r->job_alloc[v.job] = a;
+      }
+    }
   }
   float kms = 0;
   cudaEventElapsedTime(&kms, s->ev0, s->ev1);
