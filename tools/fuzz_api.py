@@ -21,11 +21,11 @@ ZONES = ["za", "zb", "zc"]
 POOLS = ["p0", "p1"]
 
 
-def make_case(seed):
+def make_case(seed, big=False):
     rnd = random.Random(seed)
-    n_nodes = rnd.randint(3, 40)
+    n_nodes = rnd.randint(3, 40) if not big else rnd.randint(40, 400)
     nodes = []
-    leaves = rnd.randint(2, 5)
+    leaves = rnd.randint(2, 5) if not big else rnd.randint(3, 12)
     for i in range(n_nodes):
         cpu = rnd.choice(["4", "8", "16", "32"])
         mem = rnd.choice(["8Gi", "16Gi", "64Gi"])
@@ -69,9 +69,9 @@ def make_case(seed):
             if rnd.random() < 0.6:
                 hypernodes.append(BuildHyperNode("root", 3, [("midA", "HyperNode"), ("midB", "HyperNode")]))
     pods, pgs = [], []
-    n_jobs = rnd.randint(1, 8)
+    n_jobs = rnd.randint(1, 8) if not big else rnd.randint(5, 40)
     for j in range(n_jobs):
-        size = rnd.choice([1, 1, 2, 3, 4, 6, 8])
+        size = rnd.choice([1, 1, 2, 3, 4, 6, 8]) if not big else rnd.choice([1, 2, 4, 8, 16, 32])
         min_member = rnd.choice([1, size, max(1, size // 2)])
         roles = rnd.random() < 0.3 and size >= 2
         tmm = {"master": 1, "worker": max(0, min_member - 1)} if roles and rnd.random() < 0.7 else None
@@ -141,10 +141,11 @@ def make_case(seed):
 def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    big = len(sys.argv) > 3 and sys.argv[3] == "big"
     engine.init(0)
     bad = unsupported = dense_bad = 0
     for seed in range(first, first + n_cases):
-        tc, tiers, actions = make_case(seed)
+        tc, tiers, actions = make_case(seed, big)
         if not tiers:
             continue
         snap = tc.RegisterSession(tiers, actions=actions)
