@@ -52,6 +52,10 @@ def make_case(seed, big=False):
         cap = BuildResourceList(str(rnd.choice([8, 16, 64])), rnd.choice(["16Gi", "64Gi", "256Gi"])) if rnd.random() < 0.3 else None
         qu = BuildQueue(f"q{q}", rnd.randint(1, 4), cap)
         qu.priority = rnd.choice([0, 0, 1, 5])
+        if rnd.random() < 0.08:
+            qu.state = "Closed"
+        if rnd.random() < 0.15:
+            qu.guarantee = BuildResourceList(str(rnd.choice([1, 4])), rnd.choice(["2Gi", "8Gi"]))
         queues.append(qu)
     use_topo = rnd.random() < 0.5
     hypernodes = None
@@ -72,7 +76,7 @@ def make_case(seed, big=False):
     n_jobs = rnd.randint(1, 8) if not big else rnd.randint(5, 40)
     for j in range(n_jobs):
         size = rnd.choice([1, 1, 2, 3, 4, 6, 8]) if not big else rnd.choice([1, 2, 4, 8, 16, 32])
-        min_member = rnd.choice([1, size, max(1, size // 2)])
+        min_member = rnd.choice([1, size, max(1, size // 2), size + (1 if rnd.random() < 0.1 else 0)])
         roles = rnd.random() < 0.3 and size >= 2
         tmm = {"master": 1, "worker": max(0, min_member - 1)} if roles and rnd.random() < 0.7 else None
         qname = f"q{rnd.randrange(n_queues)}"
@@ -82,6 +86,7 @@ def make_case(seed, big=False):
         else:
             pg = BuildPodGroup(f"pg{j}", "ns", qname, min_member, tmm, phase)
         pg.priority = rnd.choice([0, 0, 1, 2])
+        pg.preemptable = rnd.random() < 0.2
         pg.creation_ts = rnd.randint(0, 5)
         pgs.append(pg)
         req = BuildResourceList(rnd.choice(["500m", "1", "2", "4"]), rnd.choice(["1Gi", "2Gi", "8Gi"]),
@@ -111,6 +116,8 @@ def make_case(seed, big=False):
                 p.deleting = True  # Releasing on its node
             if rnd.random() < 0.2:
                 p.priority = rnd.randint(0, 3)
+            if rnd.random() < 0.05:
+                p.requests = {}  # BestEffort: stays out of the allocate action, counts as pending best-effort
             pods.append(p)
     # plugin set
     names = ["priority", "gang", "drf", "predicates", "proportion", "nodeorder", "binpack", "tdm", "network-topology-aware"]

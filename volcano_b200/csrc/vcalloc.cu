@@ -146,7 +146,7 @@ struct vc_snapshot {
   HeapEnt *rep_heap = nullptr;
   size_t rep_i32_stride = 0, rep_f64_stride = 0, rep_heap_stride = 0;
   uint4 *mbox = nullptr;
-  long long *d_prof = nullptr;
+  long long *d_prof = nullptr, *d_wait = nullptr;
   long long h_prof[16] = {0};
   vc_decision *d_decisions = nullptr;
   vc_visit *d_visits = nullptr;
@@ -352,7 +352,7 @@ void vc_snapshot_destroy(vc_snapshot *s) {
   if (!s) return;
   free_dense(s);
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
-                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_prof, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
+                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_prof, s->d_wait, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
   for (void *p : dptrs) if (p) cudaFree(p);
   void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters};
   for (void *p : hptrs) if (p) cudaFreeHost(p);
@@ -421,6 +421,7 @@ int vc_snapshot_set_shard(vc_snapshot *s, int32_t node_begin, int32_t node_end) 
 int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, const vc_classes *cl,
                        const vc_jobs *jb, const vc_queues *qu, const vc_conf *conf) {
   if (!s || !nd || !tk || !cl || !jb || !qu || !conf) return fail(VC_EINVAL, "null argument");
+  s->uploaded = false;  // a failed upload must not leave a half-described session runnable
   const double t0 = now_ms();
   const vc_dims &D = s->dims;
   const size_t N = D.n_nodes, T = D.n_tasks, J = D.n_jobs, Q = D.n_queues, C = D.n_classes, R = D.n_dims,
@@ -1062,7 +1063,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
 
   long long *d_wait = nullptr;
   if (getenv("VC_PROF_WAIT")) {
-    CUDA_TRY(cudaMalloc(&d_wait, 1024 * 8));
+    if (!s->d_wait) CUDA_TRY(cudaMalloc(&s->d_wait, 1024 * 8));
+    d_wait = s->d_wait;
     CUDA_TRY(cudaMemsetAsync(d_wait, 0, 1024 * 8, s->stream));
   }
   p.cta_wait = d_wait;
@@ -1090,7 +1092,6 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   if (d_wait) {
     std::vector<long long> w(G);
     cudaMemcpy(w.data(), d_wait, G * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_wait);
     fprintf(stderr, "all-gather wait per CTA (Mcycles):");
     for (int i = 0; i < G; ++i) fprintf(stderr, " %.0f", w[i] / 1e6);
     fprintf(stderr, "\n");
