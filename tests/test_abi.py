@@ -57,3 +57,9 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in src and "oracle/" not in src and "import oracle" not in src, f
+
+
+def test_graft_entry_build_is_consistent():
+    """build() is what the driver runs on CPU every round: it must agree with the header's ABI version."""
+    import __graft_entry__ as g
+    g.build()
