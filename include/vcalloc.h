@@ -236,6 +236,8 @@ typedef struct vc_conf {
   int32_t percentage_nodes_to_find;     /* options.go:48-54; 100 = parity mode */
   int32_t min_nodes_to_find;            /* 100 */
   int32_t min_percentage_nodes_to_find; /* 5 */
+  int32_t last_processed_node_index;    /* util.lastProcessedNodeIndex (util/scheduler_helper.go:50) carried over from
+                                           the previous cycle; only read when the sampling above is in force */
   /* network-topology-aware arguments (plugins/network-topology-aware/network_topology_aware.go:155-229) */
   int32_t nta_weight;                   /* "weight", default 1 */
   int32_t nta_dim_weight[VC_MAX_DIMS];  /* hypernode.binpack.{cpu,memory,resources.*}; -1: not in the weight map */
@@ -296,6 +298,8 @@ typedef struct vc_stats {
   int32_t n_steps;    /* node sweeps executed */
   int64_t prof_cycles[8]; /* commit kernel phase timers (SM cycles of CTA 0): 0 queue/job control, 1 task fetch +
                              gates, 2 node sweep, 3 mailbox exchange, 4 apply + bookkeeping */
+  int32_t last_processed_node_index; /* util.lastProcessedNodeIndex after the cycle (to carry into the next one) */
+  int32_t reserved;
 } vc_stats;
 
 typedef struct vc_snapshot vc_snapshot;

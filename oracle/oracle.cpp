@@ -1537,6 +1537,7 @@ Session *load(const vc_dims *dims, const vc_nodes *nd, const vc_tasks *tk, const
     if (d >= 2 && s.N > 0) { s.total.has |= 1u << d; s.total.nilmap = false; }
   }
   nta_init(s, nullptr);
+  s.last_processed_node_index = s.N > 0 ? ((conf->last_processed_node_index % s.N) + s.N) % s.N : 0;
   s.j_share.assign(J, 0.0);
   if (s.has_plugin[VC_PLUGIN_DRF])
     for (int j = 0; j < s.J; ++j) drf_update_share(s, j);  // drf.go:186-214
@@ -1592,6 +1593,7 @@ void vco_nta_topo_scores(void *h, int t, int allocated_hn, const int32_t *nodes,
   for (int i = 0; i < n_nodes; ++i) out[i] = has[i] ? (double)kMaxNodeScore * (double)s.conf.nta_weight * sc[i] : 0.0;
 }
 int vco_job_allocated_hypernode(void *h, int j) { return ((Session *)h)->job_alloc_hn[j]; }
+int64_t vco_last_processed_node_index(void *h) { return ((Session *)h)->last_processed_node_index; }
 double vco_go_pow_uint(double x, unsigned n) { return go_pow_uint(x, n); }
 void vco_score_matrix(void *h, uint64_t *mask_out, double *score_out, double *best_score, int32_t *best_node) {
   score_matrix(*(Session *)h, mask_out, score_out, best_score, best_node);

@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
         L.vco_nta_topo_scores.argtypes = [_vp, C.c_int, C.c_int, _i32p, C.c_int, _dp]
         L.vco_job_allocated_hypernode.restype = C.c_int
         L.vco_job_allocated_hypernode.argtypes = [_vp, C.c_int]
+        L.vco_last_processed_node_index.restype = C.c_int64
+        L.vco_last_processed_node_index.argtypes = [_vp]
         L.vco_go_pow_uint.restype = C.c_double
         L.vco_go_pow_uint.argtypes = [C.c_double, C.c_uint]
         L.vco_allocate_run.argtypes = [_vp]

@@ -33,7 +33,7 @@ def test_struct_sizes_match_header(lib):
     from volcano_b200 import abi
     assert C.sizeof(abi.vc_decision) == 24 and C.sizeof(abi.vc_visit) == 16
     assert C.sizeof(abi.vc_dims) == 12 * 4
-    assert C.sizeof(abi.vc_conf) == 4 + 16 * 12 + 4 + 16 * 4 + 5 * 4 + 4 * 4 + 4 + 5 * 4 + (4 + 16 * 4 + 4) + 4 + 8  # 408
+    assert C.sizeof(abi.vc_conf) == 4 + 16 * 12 + 4 + 16 * 4 + 5 * 4 + 4 * 4 + 4 + 5 * 4 + 4 + (4 + 16 * 4 + 4) + 8  # 408
     assert C.sizeof(abi.vc_hypernodes) == 16 + 7 * 8
 
 

@@ -86,12 +86,6 @@ def test_unsupported_features_fail_loudly():
     from volcano_b200 import abi, engine
     from volcano_b200.synth import make_snapshot
     snap = make_snapshot("tiny", 1)
-    snap.conf.percentage_nodes_to_find = 50
-    snap.conf.min_nodes_to_find = 10
-    with pytest.raises(engine.VcError) as ei:
-        engine.gpu_engine(snap)
-    assert ei.value.code == abi.VC_EUNSUPPORTED
-    snap = make_snapshot("tiny", 1)
     snap.j_flags[0] |= abi.VC_JOB_UNSUPPORTED
     with pytest.raises(engine.VcError) as ei:
         engine.gpu_engine(snap)

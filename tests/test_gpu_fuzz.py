@@ -28,7 +28,7 @@ def test_random_clusters_match_oracle(block, oracle_engine):
         tc, tiers, actions = make_case(seed)
         if not tiers:
             continue
-        snap = tc.RegisterSession(tiers, actions=actions)
+        snap = tc.RegisterSession(tiers, actions=actions, **tc.conf_kw)
         if snap.T == 0 or snap.N == 0:
             continue
         ref = oracle_engine(snap)

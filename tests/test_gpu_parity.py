@@ -217,3 +217,29 @@ def test_full_size_properties(cfg, gpu):
     per_job = np.bincount(snap.t_job[dec["task"][committed]], minlength=snap.J)
     jobs_committed = np.unique(r1.visits["job"][r1.visits["outcome"] == 0])
     assert (per_job[jobs_committed] >= snap.j_min_available[jobs_committed]).all()
+
+
+SAMPLING_CASES = [("tiny", 1, 50, 10, 0), ("tiny", 2, 20, 5, 17), ("small", 7, 0, 100, 0), ("small", 3, 30, 50, 333),
+                  ("tiny_fut", 2, 40, 8, 5), ("small_fut_soft", None, 25, 30, 0), ("small_roles", None, 35, 20, 11),
+                  ("small_topo", None, 30, 40, 100), ("small_topo_fut_soft", 4, 50, 20, 7), ("cfg1", None, 0, 20, 0)]
+
+
+@pytest.mark.parametrize("cfg,seed,pct,min_nodes,start", SAMPLING_CASES)
+def test_feasible_node_sampling_vs_oracle(cfg, seed, pct, min_nodes, start, gpu, oracle_engine):
+    """util.PredicateNodes with percentage-nodes-to-find < 100 (predicate_helper.go:43-140, scheduler_helper.go:54-73)
+    in its single-worker reading: stop after numNodesToFind feasible nodes, rotating start index carried across tasks."""
+    from oracle.pyoracle import OracleSession
+    from oracle import pyoracle
+    from volcano_b200.synth import make_snapshot
+    snap = make_snapshot(cfg, seed)
+    snap.conf.percentage_nodes_to_find = pct
+    snap.conf.min_nodes_to_find = min_nodes
+    snap.conf.last_processed_node_index = start
+    res = gpu.gpu_engine(snap)
+    o = OracleSession(snap, threads=1)
+    dec, vis, fe = o.allocate()
+    last = pyoracle.lib().vco_last_processed_node_index(o.h)
+    o.close()
+    assert np.array_equal(res.decisions, dec) and np.array_equal(res.visits, vis) and np.array_equal(res.fit_errors, fe)
+    assert res.stats["last_processed_node_index"] == last
+    assert len(dec) > 0

@@ -142,6 +142,10 @@ def make_case(seed, big=False):
     tc = TestCommonStruct(Name=f"fuzz{seed}", Nodes=nodes, Pods=pods, PodGroups=pgs, Queues=queues, HyperNodes=hypernodes,
                           TdmZoneActive={"rz1": rnd.random() < 0.7, "rz2": rnd.random() < 0.3})
     actions = ("enqueue", "allocate") if rnd.random() < 0.5 else ("allocate",)
+    tc.conf_kw = {}
+    if rnd.random() < 0.3:  # feasible-node sampling with a rotating start index
+        tc.conf_kw = dict(percentage_nodes_to_find=rnd.choice([0, 10, 30, 60]), min_nodes_to_find=rnd.choice([1, 3, 10, 50]),
+                          min_percentage_nodes_to_find=rnd.choice([5, 20]), last_processed_node_index=rnd.randint(0, 500))
     return tc, tiers, actions
 
 
@@ -155,10 +159,10 @@ def main():
         tc, tiers, actions = make_case(seed, big)
         if not tiers:
             continue
-        snap = tc.RegisterSession(tiers, actions=actions)
+        snap = tc.RegisterSession(tiers, actions=actions, **tc.conf_kw)
         if snap.T == 0 or snap.N == 0:
             continue
-        o = OracleSession(snap, threads=2)
+        o = OracleSession(snap, threads=1)
         dec, vis, fe = o.allocate()
         try:
             r = engine.gpu_engine(snap)
@@ -168,6 +172,8 @@ def main():
             print(f"seed {seed}: {e}")
             continue
         ok = (np.array_equal(dec, r.decisions) and np.array_equal(vis, r.visits) and np.array_equal(fe, r.fit_errors))
+        from oracle import pyoracle as _po
+        ok = ok and r.stats["last_processed_node_index"] == _po.lib().vco_last_processed_node_index(o.h)
         if snap.hn_job_soft is not None and snap.hn_job_soft.any():
             from oracle import pyoracle
             ja = np.array([pyoracle.lib().vco_job_allocated_hypernode(o.h, j) for j in range(snap.J)], np.int32)

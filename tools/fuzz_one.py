@@ -7,7 +7,7 @@ from oracle.pyoracle import OracleSession
 from volcano_b200 import engine
 seed = int(sys.argv[1])
 tc, tiers, actions = fz.make_case(seed)
-snap = tc.RegisterSession(tiers, actions=actions)
+snap = tc.RegisterSession(tiers, actions=actions, **tc.conf_kw)
 print("N", snap.N, "T", snap.T, "J", snap.J, "Q", snap.Q, "actions", actions)
 print("tiers", [[(p.name, hex(p.enabled)) for p in t] for t in tiers])
 print("soft", None if snap.hn_job_soft is None else snap.hn_job_soft.tolist(), "alloc0", None if snap.hn_job_allocated is None else snap.hn_job_allocated.tolist())

@@ -168,6 +168,7 @@ class vc_conf(C.Structure):
         ("percentage_nodes_to_find", C.c_int32),
         ("min_nodes_to_find", C.c_int32),
         ("min_percentage_nodes_to_find", C.c_int32),
+        ("last_processed_node_index", C.c_int32),
         ("nta_weight", C.c_int32),
         ("nta_dim_weight", C.c_int32 * VC_MAX_DIMS),
         ("nta_normal_pod_enable", C.c_int32),
@@ -194,7 +195,8 @@ class vc_visit(C.Structure):
 class vc_stats(C.Structure):
     _fields_ = [("upload_ms", C.c_double), ("commit_ms", C.c_double), ("download_ms", C.c_double),
                 ("total_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("kernel_launches", C.c_int32), ("n_steps", C.c_int32), ("prof_cycles", C.c_int64 * 8)]
+                ("kernel_launches", C.c_int32), ("n_steps", C.c_int32), ("prof_cycles", C.c_int64 * 8),
+                ("last_processed_node_index", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/vcalloc.h declares: name -> (restype, argtypes)

@@ -64,6 +64,7 @@ struct K2Params {
   size_t rep_heap_stride;
   // mailbox [2 parity][3 units][n_cta]
   uint4 *mbox;
+  uint4 *mbox2;  // same layout: the per-CTA count all-gather of feasible-node sampling
   // outputs
   vc_decision *decisions;
   vc_visit *visits;
@@ -156,6 +157,10 @@ struct Ctl {
   int job_soft, topo_A, n_anc, nplaced;
   int anc[VC_MAX_TIERS + 2], anc_lvl[VC_MAX_TIERS + 2];
   int tk[2];
+  // feasible-node sampling: util.lastProcessedNodeIndex, per-warp counts of the selection pass, its result
+  int last_idx, samp_proc, samp_total, samp_prefA, samp_prefB;
+  unsigned seq2;
+  int samp_w[4][8][2];   // [row of nodes][warp][segment] feasible counts
   // exchange result
   int cnt[2], best_node[2], max_soft[2];
   double best_score[2];
@@ -198,6 +203,7 @@ struct Local {  // what one CTA (or one lane while folding) contributes per cate
   int node[2];
   int cnt[2];
   int soft[2];
+  int proc;   // sampling: rotated position + 1 of the to_find-th feasible node (0 = not in this part)
   int tk[2];  // topology pods: (1 + code of the best networkTopologyAwareScore) << 2 | min(nodes at that score, 2); 0 = none
 };
 __device__ __forceinline__ int tk_fold(int a, int b) {
@@ -212,6 +218,7 @@ __device__ __forceinline__ void local_init(Local &l) {
   l.cnt[0] = l.cnt[1] = 0;
   l.soft[0] = l.soft[1] = 0;
   l.tk[0] = l.tk[1] = 0;
+  l.proc = 0;
 }
 __device__ __forceinline__ void local_fold(Local &a, const Local &b) {
 #pragma unroll
@@ -224,6 +231,7 @@ __device__ __forceinline__ void local_fold(Local &a, const Local &b) {
     a.soft[k] = max(a.soft[k], b.soft[k]);
     a.tk[k] = tk_fold(a.tk[k], b.tk[k]);
   }
+  a.proc = max(a.proc, b.proc);
 }
 // Warp-wide fold with the hardware reductions (redux.sync) instead of 5 shuffle rounds over 12 words: the
 // (score, node) arg-max goes through an order-preserving 64-bit key reduced as two 32-bit maxima, then the
@@ -261,6 +269,7 @@ __device__ __forceinline__ void local_warp_reduce(Local &l) {
     l.tk[k] = (int)((mcode << 2) | min(2u, tcnt));
     l.soft[k] = (int)__reduce_max_sync(FULLM, (unsigned)l.soft[k]);
   }
+  l.proc = (int)__reduce_max_sync(FULLM, (unsigned)l.proc);
 }
 
 // All-gather of one Local per CTA through the L2-resident mailbox. Called by warp 0 of every CTA with the
@@ -270,7 +279,8 @@ __device__ __forceinline__ void local_warp_reduce(Local &l) {
 // carries its own sequence number, so readers validate each 16-byte unit on its own: no fence needed.
 //   FULL = false: one unit  {score0, node0, seq<<2 | min(cnt0,2)}            (no FutureIdle gradient, no
 //                                                                              normalising batch scorer)
-//   FULL = true : three units {score0,node0,seq} {score1,node1,seq} {cnt0,cnt1,soft0|soft1<<8|tk0<<16|tk1<<24,seq}
+//   FULL = true : four units {score0,node0,seq} {score1,node1,seq} {cnt0,cnt1,soft0|soft1<<8|tk0<<16|tk1<<24,seq}
+//                 {sampling: processed position,0,0,seq}
 #define MBOX_STRIDE 16  // uint4 per slot = 256 bytes
 template <bool FULL>
 __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigned seq) {
@@ -278,6 +288,7 @@ __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigne
   const int G = p.n_cta;
   uint4 *base = p.mbox + (size_t)(seq & 1u) * G * MBOX_STRIDE;
   if (FULL) {
+    if (lane == 3) mbox_store(base + (size_t)blockIdx.x * MBOX_STRIDE + 3, make_uint4((unsigned)mine.proc, 0u, 0u, seq));
     if (lane < 3) {
       uint4 v;
       if (lane < 2) {
@@ -298,7 +309,7 @@ __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigne
   Local acc;
   local_init(acc);
   for (int s0 = 0; s0 < G; s0 += 32 * 4) {  // up to 4 slots per lane in flight
-    uint4 a[4], b[4], c[4];
+    uint4 a[4], b[4], c[4], e[4];
     bool need[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) need[k] = (s0 + k * 32 + lane) < G;
@@ -310,12 +321,13 @@ __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigne
         if (need[k]) {  // the three units of a slot share one 128-byte line: issue them together
           const uint4 *sl = base + (size_t)(s0 + k * 32 + lane) * MBOX_STRIDE;
           a[k] = mbox_load(sl);
-          if (FULL) { b[k] = mbox_load(sl + 1); c[k] = mbox_load(sl + 2); }
+          if (FULL) { b[k] = mbox_load(sl + 1); c[k] = mbox_load(sl + 2); e[k] = mbox_load(sl + 3); }
         }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (!need[k]) continue;
-        const bool ok = FULL ? (a[k].w == seq && b[k].w == seq && c[k].w == seq) : ((a[k].w >> 2) == (seq & 0x3fffffffu));
+        const bool ok = FULL ? (a[k].w == seq && b[k].w == seq && c[k].w == seq && e[k].w == seq)
+                             : ((a[k].w >> 2) == (seq & 0x3fffffffu));
         if (!ok) { pending = true; continue; }
         Local o;
         local_init(o);
@@ -327,6 +339,7 @@ __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigne
           o.cnt[0] = (int)c[k].x; o.cnt[1] = (int)c[k].y;
           o.soft[0] = (int)(c[k].z & 0xffu); o.soft[1] = (int)((c[k].z >> 8) & 0xffu);
           o.tk[0] = (int)((c[k].z >> 16) & 0xffu); o.tk[1] = (int)(c[k].z >> 24);
+          o.proc = (int)e[k].x;
         } else {
           o.cnt[0] = (int)(a[k].w & 3u);
         }
@@ -338,6 +351,29 @@ __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigne
   local_warp_reduce<FULL>(acc);
   if (!FULL) acc.cnt[0] = min(acc.cnt[0], 2);
   return acc;
+}
+
+// All-gather of two counts per CTA (feasible nodes at / after the scan start, and before it) for the feasible-node
+// sampling: returns in every lane of warp 0 the sums over the CTAs with a lower index, and the totals.
+struct CountFold { int prefA, prefB, totA, totB; };
+__device__ __forceinline__ CountFold exchange_counts(const K2Params &p, int cA, int cB, unsigned seq) {
+  const int lane = threadIdx.x & 31;
+  const int G = p.n_cta, me = blockIdx.x;
+  uint4 *base = p.mbox2 + (size_t)(seq & 1u) * G * MBOX_STRIDE;
+  if (lane == 0) mbox_store(base + (size_t)me * MBOX_STRIDE, make_uint4((unsigned)cA, (unsigned)cB, 0u, seq));
+  int pa = 0, pb = 0, ta = 0, tb = 0;
+  for (int s = lane; s < G; s += 32) {
+    uint4 v;
+    do { v = mbox_load(base + (size_t)s * MBOX_STRIDE); } while (v.w != seq);
+    ta += (int)v.x; tb += (int)v.y;
+    if (s < me) { pa += (int)v.x; pb += (int)v.y; }
+  }
+  CountFold r;
+  r.prefA = (int)__reduce_add_sync(0xffffffffu, (unsigned)pa);
+  r.prefB = (int)__reduce_add_sync(0xffffffffu, (unsigned)pb);
+  r.totA = (int)__reduce_add_sync(0xffffffffu, (unsigned)ta);
+  r.totB = (int)__reduce_add_sync(0xffffffffu, (unsigned)tb);
+  return r;
 }
 
 // ---- replicated control helpers (executed by every thread on shared Ctl; mutations by thread 0) ----
@@ -491,9 +527,10 @@ extern __shared__ __align__(16) unsigned char k2_smem[];
     }                                                 \
   } while (0)
 
-template <bool FUT, bool SOFT, bool TOPO = false>
+template <bool FUT, bool SOFT, bool TOPO = false, bool SAMP = false>
 __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   static_assert(!TOPO || (FUT && SOFT), "the topology variant rides on the two-pass, three-unit exchange");
+  static_assert(!SAMP || (FUT && SOFT), "the sampling variant rides on the full exchange");
   const DevConf &c = p.c;
   const int R = p.d.R, K = p.d.K, N = p.d.N, J = p.d.J, Q = p.d.Q, NR = p.d.NR, T = p.d.T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -522,6 +559,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   double *c_order = reinterpret_cast<double *>(sp); sp += (size_t)cap * 8;
   int32_t *c_group = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
   uint8_t *c_cat = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;
+  uint8_t *s_samp = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;  // sampling: 1 candidate / feasible, 2 evaluated infeasible, 4 skipped
   for (int i = tid; i < cap; i += blockDim.x) c_group[i] = -1;
   // network-topology-aware: per-step binpack score of each local hypernode for the task under evaluation, and
   // the plugin's score of each distinct per-tier hypernode tuple ("chain") among the CTA's nodes
@@ -653,6 +691,8 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   }
   if (tid == 0) {
     S.seq = 0;
+    S.seq2 = 0;
+    S.last_idx = c.last_idx0;
     S.n_dec = S.n_vis = S.n_fit = S.n_steps = 0;
     for (int k = 0; k < 8; ++k) S.prof[k] = 0;
     S.prof_last = clock64();
@@ -934,6 +974,88 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
         }
         __syncthreads();
       }
+      // cached or fresh (fit category, NodeOrderFn sum) of node i for the staged group
+      auto verdict = [&](int i, uint32_t cs, int *cat, bool *has_order, double *order) {
+        *cat = 2; *has_order = false; *order = 0.0;
+        if (c_group[i] == cur_group) {
+          const uint8_t cw = c_cat[i];
+          *cat = cw & 3; *has_order = (cw & 0x80) != 0; *order = c_order[i];
+          return;
+        }
+        SmemNodeView nv{sn, i};
+        bool ok = (cs & CS_STATIC_OK) != 0;
+        if (c.pred_predicates && sn.max_tasks[i] <= sn.pod_count[i]) ok = false;
+        const int fc = fit_category_t<FUT>(R, trec, nv);
+        if (ok && fc != 2) {
+          *cat = fc;
+          *has_order = node_order(c, R, K, trec, nv, cs, order);
+        }
+        c_group[i] = cur_group; c_cat[i] = (uint8_t)(*cat | (*has_order ? 0x80 : 0)); c_order[i] = *order;
+      };
+      // ---- feasible-node sampling, util/predicate_helper.go:43-140 in its single-worker reading: scan the nodes in
+      // index order starting at lastProcessedNodeIndex, stop after `to_find` feasible ones; nodes skipped through the
+      // error cache count as processed, predicate failures of processed nodes enter the cache ----
+      const bool sampling = SAMP && c.to_find > 0;
+      if (SAMP && sampling) {
+        const int start = S.last_idx, Kf = c.to_find;
+        const int rows = (cap + (int)blockDim.x - 1) / (int)blockDim.x;
+        const unsigned lt = (1u << lane) - 1u;
+        for (int row = 0; row < rows; ++row) {
+          const int i = row * blockDim.x + tid;
+          int flag = 0;
+          if (i < nmine) {
+            if (use_cache && ((sn.nerr[i] >> rl) & 1ull)) {
+              flag = 4;
+            } else {
+              int cat; bool ho; double od;
+              verdict(i, c_group[i] != cur_group ? cs_row[i] : 0u, &cat, &ho, &od);
+              flag = cat != 2 ? 1 : 2;
+            }
+            s_samp[i] = (uint8_t)flag;
+          }
+          const bool inA = nbase + i >= start;
+          const unsigned mA = __ballot_sync(0xffffffffu, flag == 1 && inA), mB = __ballot_sync(0xffffffffu, flag == 1 && !inA);
+          if (lane == 0) { S.samp_w[row][warp][0] = __popc(mA); S.samp_w[row][warp][1] = __popc(mB); }
+        }
+        __syncthreads();
+        if (warp == 0) {
+          int a = 0, b = 0;
+          for (int e = lane; e < rows * nwarps; e += 32) { a += S.samp_w[e / nwarps][e % nwarps][0]; b += S.samp_w[e / nwarps][e % nwarps][1]; }
+          a = (int)__reduce_add_sync(0xffffffffu, (unsigned)a);
+          b = (int)__reduce_add_sync(0xffffffffu, (unsigned)b);
+          const unsigned seq2 = S.seq2 + 1;
+          __syncwarp();
+          const CountFold f = exchange_counts(p, a, b, seq2);
+          if (lane == 0) {
+            S.seq2 = seq2;
+            S.samp_prefA = f.prefA;            // feasible nodes before this CTA's part of the [start, N) segment
+            S.samp_prefB = f.totA + f.prefB;   // ... of the [0, start) segment, which is scanned second
+            S.samp_total = f.totA + f.totB;
+            S.samp_proc = 0;
+          }
+        }
+        __syncthreads();
+        for (int row = 0; row < rows; ++row) {
+          const int i = row * blockDim.x + tid;
+          const int flag = i < nmine ? s_samp[i] : 0;
+          const bool inA = nbase + i >= start;
+          const unsigned mA = __ballot_sync(0xffffffffu, flag == 1 && inA), mB = __ballot_sync(0xffffffffu, flag == 1 && !inA);
+          if (i >= nmine || flag == 4) continue;
+          // feasible nodes scanned before this one: lower-index CTAs, earlier rows / warps of this CTA, lower lanes
+          const int seg = inA ? 0 : 1;
+          int before = (inA ? S.samp_prefA : S.samp_prefB) + __popc((inA ? mA : mB) & lt);
+          for (int r2 = 0; r2 <= row; ++r2)
+            for (int w2 = 0; w2 < (r2 < row ? nwarps : warp); ++w2) before += S.samp_w[r2][w2][seg];
+          if (flag == 1) {
+            const bool cand = before < Kf;
+            s_samp[i] = cand ? 1 : 0;
+            if (before == Kf - 1) S.samp_proc = (nbase + i - start + N) % N + 1;  // the scan stops here
+          } else if (before < Kf && use_cache) {
+            sn.nerr[i] |= (1ull << rl);  // a processed node that failed the predicate
+          }
+        }
+        __syncthreads();
+      }
       // the first pass is only needed when something is normalised over the candidate set
       const bool two_pass = SOFT && (c.soft_active || (TOPO && topo_scored));
       const int n_pass = two_pass ? 2 : 1;
@@ -941,26 +1063,16 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
         Local mine;
         local_init(mine);
         for (int i = tid; i < nmine; i += blockDim.x) {
-          SmemNodeView nv{sn, i};
           // the class x node word is only needed to (re)evaluate the node or for the soft-taint count
           const uint32_t cs = ((SOFT && c.soft_active) || c_group[i] != cur_group) ? cs_row[i] : 0u;
           int cat = 2;
           bool has_order = false;
           double order = 0.0;
-          if (!(use_cache && ((sn.nerr[i] >> rl) & 1ull))) {
-            if (c_group[i] == cur_group) {
-              const uint8_t cw = c_cat[i];
-              cat = cw & 3; has_order = (cw & 0x80) != 0; order = c_order[i];
-            } else {
-              bool ok = (cs & CS_STATIC_OK) != 0;
-              if (c.pred_predicates && sn.max_tasks[i] <= sn.pod_count[i]) ok = false;
-              int fc = fit_category_t<FUT>(R, trec, nv);
-              if (ok && fc != 2) {
-                cat = fc;
-                has_order = node_order(c, R, K, trec, nv, cs, &order);
-              }
-              c_group[i] = cur_group; c_cat[i] = (uint8_t)(cat | (has_order ? 0x80 : 0)); c_order[i] = order;
-            }
+          if (SAMP && sampling) {
+            if (s_samp[i] != 1) continue;  // outside the sampled candidate set
+            verdict(i, cs, &cat, &has_order, &order);
+          } else if (!(use_cache && ((sn.nerr[i] >> rl) & 1ull))) {
+            verdict(i, cs, &cat, &has_order, &order);
             if (cat == 2 && use_cache && pass == 0) sn.nerr[i] |= (1ull << rl);
           }
           if (cat == 2) continue;
@@ -1019,6 +1131,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
             }
           }
           local_warp_reduce<FUT>(l);
+          if (SAMP && sampling) l.proc = S.samp_proc;
           const unsigned seq = S.seq + 1;
           __syncwarp();  // every lane has read S.seq before lane 0 advances it below
           const long long tw0 = p.cta_wait ? clock64() : 0;
@@ -1030,6 +1143,10 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
             for (int k = 0; k < 2; ++k) {
               S.cnt[k] = g.cnt[k]; S.best_node[k] = g.node[k]; S.best_score[k] = g.score[k]; S.max_soft[k] = g.soft[k];
               if (two_pass && pass == 0) S.tk[k] = g.tk[k];
+            }
+            if (SAMP && sampling && pass == n_pass - 1) {  // lastProcessedNodeIndex = (start + processedNodes) % N
+              const int processed = S.samp_total >= c.to_find ? g.proc : N;
+              S.last_idx = (S.last_idx + processed) % N;
             }
           }
           PROF_MARK(3);
@@ -1266,6 +1383,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
     p.counters[1] = S.n_vis;
     p.counters[2] = S.n_fit;
     p.counters[3] = S.n_steps;
+    p.counters[4] = S.last_idx;
     for (int k = 0; k < 8; ++k) p.prof[k] = S.prof[k];
   }
 }

@@ -42,6 +42,10 @@ struct DevConf {
   int batch_any;        // some BatchNodeOrderFn yields entries
   int has_future;       // any Releasing/Pipelined resource at open -> FutureIdle != Idle possible
   int soft_active;      // taint_batch && some node carries a PreferNoSchedule taint
+  // feasible-node sampling (util/predicate_helper.go:43-140 with CalculateNumOfFeasibleNodesToFind): stop after
+  // `to_find` feasible nodes, scanning from lastProcessedNodeIndex; 0 = every node is evaluated (parity mode)
+  int to_find;
+  int last_idx0;
   // network-topology-aware, hypernode-level binpacking of pods without a network topology
   int nta_plugin;       // plugin has EnabledNodeOrder (its BatchNodeOrderFn is registered)
   int nta_tables;       // per-CTA hypernode lists are built (nta_on, or soft-mode topology jobs exist)

@@ -192,6 +192,19 @@ inline double go_pow_uint(double x, unsigned n) {
   return std::ldexp(a1, ae);
 }
 
+// CalculateNumOfFeasibleNodesToFind, util/scheduler_helper.go:54-73
+inline int32_t num_feasible_nodes_to_find(int32_t num_all, int32_t pct, int32_t min_nodes, int32_t min_pct) {
+  if (num_all <= min_nodes || pct >= 100) return num_all;
+  int32_t adaptive = pct;
+  if (adaptive <= 0) {
+    adaptive = 50 - num_all / 125;
+    if (adaptive < min_pct) adaptive = min_pct;
+  }
+  int32_t num = num_all * adaptive / 100;
+  if (num < min_nodes) num = min_nodes;
+  return num;
+}
+
 inline bool has_plugin(const vc_conf &c, int id) {
   for (int i = 0; i < c.n_plugins; ++i) if (c.plugins[i].plugin == id) return true;
   return false;

@@ -240,7 +240,15 @@ int build_devconf(vc_snapshot *s, const vc_nodes *nd) {
   int fut = 0;
   for (size_t i = 0; i < RN && !fut; ++i)
     if ((nd->releasing && nd->releasing[i] != 0.0) || (nd->pipelined && nd->pipelined[i] != 0.0)) fut = 1;
-  d.has_future = fut || s->topo_any;  // the topology variant of the commit kernel is the <FUT, SOFT> one
+  {
+    const int32_t n_all = s->dims.n_nodes;
+    const int32_t tf = vch::num_feasible_nodes_to_find(n_all, c.percentage_nodes_to_find, c.min_nodes_to_find,
+                                                       c.min_percentage_nodes_to_find);
+    d.to_find = tf < n_all ? tf : 0;
+    d.last_idx0 = n_all > 0 ? ((c.last_processed_node_index % n_all) + n_all) % n_all : 0;
+  }
+  // the topology and sampling variants of the commit kernel are <FUT, SOFT> instances
+  d.has_future = fut || s->topo_any || d.to_find > 0;
   int soft = 0;
   const size_t WN = (size_t)s->dims.taint_words * s->dims.n_nodes;
   for (size_t i = 0; i < WN && !soft; ++i)
@@ -266,7 +274,7 @@ void choose_geometry(vc_snapshot *s) {
   s->block = block;
   const int R = s->dims.n_dims, K = s->dims.n_kdims;
   // hypernode-level scores change for every node after every placement: per-step full sweeps (k_commit)
-  s->fast = !s->dc.has_future && !s->dc.soft_active && !s->dc.nta_on && R <= 8 && K <= VC_MAX_KDIMS && !getenv("VC_COMMIT_GENERIC");
+  s->fast = !s->dc.has_future && !s->dc.soft_active && !s->dc.nta_on && s->dc.to_find == 0 && R <= 8 && K <= VC_MAX_KDIMS && !getenv("VC_COMMIT_GENERIC");
   if (s->fast) {
     size_t rows = 3 * (size_t)R + 2 * (size_t)K + 2 + 1;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + ((sizeof(CtlFast) + 15) & ~(size_t)15) + rows * npc * 8 +
@@ -277,7 +285,7 @@ void choose_geometry(vc_snapshot *s) {
   } else {
     size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 + 4) + 64;
-    s->smem_bytes += (size_t)npc * (8 + 4 + 1) + 32;  // verdict cache
+    s->smem_bytes += (size_t)npc * (8 + 4 + 1 + 1) + 32;  // verdict cache + sampling flags
     // hn_score (at most npc * L local hypernodes) + chain_val (at most npc chains); hn_cap is set after this call
     if (s->dc.nta_tables) s->smem_bytes += (size_t)npc * (s->hn_L + 1) * 8 + (size_t)npc * 4 + 32;
   }
@@ -427,9 +435,6 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   const size_t N = D.n_nodes, T = D.n_tasks, J = D.n_jobs, Q = D.n_queues, C = D.n_classes, R = D.n_dims,
                K = D.n_kdims, Wl = D.label_words, Wt = D.taint_words, NR = D.n_roles, Z = D.n_zones;
   s->conf = *conf;
-  if (conf->percentage_nodes_to_find < 100 && (int)N > conf->min_nodes_to_find)
-    return fail(VC_EUNSUPPORTED, "feasible-node sampling (percentage_nodes_to_find < 100) is not implemented on the "
-                                 "device path; the parity contract runs with 100 (SURVEY §8c)");
   for (size_t j = 0; j < J; ++j) {
     if (jb->flags[j] & VC_JOB_UNSUPPORTED) return fail(VC_EUNSUPPORTED, "job %zu uses hard topology / subjob policy", j);
     if (jb->role_off[j + 1] - jb->role_off[j] > VC_MAX_JOB_ROLES) return fail(VC_EUNSUPPORTED, "job %zu has too many roles", j);
@@ -713,6 +718,8 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   // network-topology-aware: hyperNodeResourceCache at open (network_topology_aware.go:106-125) and, for the
   // commit kernel, the hypernodes each CTA's node slice belongs to
   choose_geometry(s);
+  if (s->dc.to_find > 0 && (s->npc + s->block - 1) / s->block > 4)
+    return fail(VC_EUNSUPPORTED, "feasible-node sampling: more than 4 node rows per CTA (%d nodes per CTA)", s->npc);
   std::vector<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn, node_chain, cta_chain_off, cta_chain;
   std::vector<double> hn_alloc, hn_used0;
   s->hn_cap = 1;
@@ -989,7 +996,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
       s->rep_hn_used_count = cnt;
     }
   }
-  const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024;
+  const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024 * 2;  // second half: the count all-gather of sampling
   if (!s->mbox) CUDA_TRY(cudaMalloc(&s->mbox, mbox_bytes));
   if (!s->d_prof) CUDA_TRY(cudaMalloc(&s->d_prof, 16 * sizeof(long long)));
   CUDA_TRY(cudaMemsetAsync(s->d_prof, 0, 16 * sizeof(long long), s->stream));
@@ -1041,6 +1048,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   p.rep_i32 = s->rep_i32; p.rep_i32_stride = i32_stride; p.rep_f64 = s->rep_f64; p.rep_f64_stride = f64_stride;
   p.rep_heap = s->rep_heap; p.rep_heap_stride = std::max<size_t>(heap_stride, 1);
   p.mbox = s->mbox;
+  p.mbox2 = s->mbox + (size_t)MBOX_STRIDE * 2 * 1024;
   p.decisions = s->d_decisions; p.visits = s->d_visits; p.fit_errors = s->d_fit; p.counters = s->d_counters;
   p.prof = s->d_prof;
   p.tmeta = reinterpret_cast<const int4 *>(s->tmeta.d(s->in)); p.n_groups = s->n_groups;
@@ -1069,7 +1077,9 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   }
   p.cta_wait = d_wait;
   if (G > 1024) return fail(VC_EUNSUPPORTED, "too many CTAs");
-  const void *kfn = s->fast ? (const void *)k_commit_fast : s->topo_any ? (const void *)k_commit<true, true, true> : s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
+  const void *kfn = s->fast ? (const void *)k_commit_fast
+                  : s->dc.to_find > 0 ? (s->topo_any ? (const void *)k_commit<true, true, true, true> : (const void *)k_commit<true, true, false, true>)
+                  : s->topo_any ? (const void *)k_commit<true, true, true> : s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
                                      : (s->dc.soft_active ? (const void *)k_commit<false, true> : (const void *)k_commit<false, false>);
   CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
   int max_blocks = 0;
@@ -1148,6 +1158,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->stats.d2h_bytes = 32 + (int64_t)n_dec * sizeof(vc_decision) + (int64_t)n_vis * sizeof(vc_visit) + (int64_t)n_fit * 4;
   r->stats.kernel_launches = 2;  // k_class_static + k_commit
   r->stats.n_steps = s->h_counters[3];
+  r->stats.last_processed_node_index = s->dc.to_find > 0 ? s->h_counters[4] : s->dc.last_idx0;
   for (int k = 0; k < 8; ++k) r->stats.prof_cycles[k] = s->h_prof[k];
   r->stats.prof_cycles[6] = s->h_counters[5];  // full sweeps (fast kernel)
   r->stats.prof_cycles[7] = s->h_counters[6];  // incremental steps (fast kernel)

@@ -57,6 +57,7 @@ class SchedulerConf:
     percentage_nodes_to_find: int = 100        # parity mode; reference default 0 = adaptive
     min_nodes_to_find: int = 100               # options.go:48-51
     min_percentage_nodes_to_find: int = 5
+    last_processed_node_index: int = 0         # util.lastProcessedNodeIndex carried over from the previous cycle
 
     @staticmethod
     def default() -> "SchedulerConf":
@@ -173,6 +174,7 @@ def build_conf(conf: SchedulerConf, dim_names: Sequence[str], kdim_names: Sequen
     c.percentage_nodes_to_find = conf.percentage_nodes_to_find
     c.min_nodes_to_find = conf.min_nodes_to_find
     c.min_percentage_nodes_to_find = conf.min_percentage_nodes_to_find
+    c.last_processed_node_index = conf.last_processed_node_index
     return c
 
 
