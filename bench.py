@@ -257,7 +257,14 @@ def main():
             n2, dt2 = run_oracle(snap, threads)
             cpu["reference_defaults"] = {"value": n2 / dt2, "unit": "pods/s", "placed": n2, "seconds": dt2,
                                          "note": "adaptive feasible-node sampling (deterministic single-worker reading); "
-                                                 "different placements, not implemented on the GPU path"}
+                                                 "different placements than parity mode"}
+            # the same mode on the device (general commit kernel with the selection pass), informational
+            eng.upload()
+            eng.allocate()
+            r2 = eng.allocate()
+            cpu["reference_defaults"]["gpu_same_mode"] = {
+                "value": len(r2.decisions) / (r2.stats["commit_ms"] * 1e-3), "unit": "pods/s", "placed": len(r2.decisions),
+                "ms": r2.stats["commit_ms"]}
         finally:
             snap.conf.percentage_nodes_to_find = 100
     if rank == 0:
