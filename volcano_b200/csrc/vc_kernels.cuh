@@ -335,3 +335,83 @@ __global__ void __launch_bounds__(256) k_group_expand(K1Params p) {
     }
   }
 }
+
+// K1f: final score + feasibility word of every (group, node) of the shard — what every task row of the group holds.
+// grid (ceil(Nloc/256), G).
+__global__ void __launch_bounds__(256) k_group_final(K1Params p, double *g_final, uint32_t *g_maskw, int mwg) {
+  const int N = p.d.N;
+  const int nloc = p.d.node_end - p.d.node_begin;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
+  const int chosen = p.g_stats[g * 4 + 0] ? 0 : (p.g_stats[g * 4 + 1] ? 1 : 2);
+  const int max_soft = chosen == 0 ? p.g_stats[g * 4 + 2] : p.g_stats[g * 4 + 3];
+  double sc = 0.0;
+  bool feas = false;
+  if (li < nloc) {
+    const int soft = (p.cstat[(size_t)p.g_class[g] * N + p.d.node_begin + li] >> CS_SOFT_SHIFT) & 0xff;
+    k1_final(p, g, li, nloc, chosen, max_soft, soft, &sc, &feas);
+    g_final[(size_t)g * nloc + li] = sc;
+  }
+  const unsigned bits = __ballot_sync(0xffffffffu, feas);
+  if ((threadIdx.x & 31) == 0 && (li >> 5) < mwg) g_maskw[(size_t)g * mwg + (li >> 5)] = bits;
+}
+
+// K1b (bulk variant): a CTA stages the (group, node-chunk) piece of the group's final row and mask words in shared
+// memory and streams it to every task row of the work item with the bulk asynchronous copy engine (cp.async.bulk
+// shared -> global; one elected thread issues one 16-byte-aligned store of the whole chunk per row, plus one for its
+// mask bytes), so HBM sees long contiguous write bursts and no partial-line stores.
+// grid (ceil(Nloc/chunk), n_work), 256 threads; chunk is a multiple of 128 nodes; dynamic smem = chunk*8 + chunk/8.
+// Needs an even N (16-byte row alignment of the score matrix); mask rows have a 16-byte pitch (p.mw32 words).
+__global__ void __launch_bounds__(256) k_group_expand_bulk(K1Params p, int chunk, const double *g_final, const uint32_t *g_maskw,
+                                                          int mwg) {
+  extern __shared__ __align__(128) unsigned char k1_smem[];
+  double *tile = reinterpret_cast<double *>(k1_smem);
+  uint32_t *mwords = reinterpret_cast<uint32_t *>(k1_smem + (size_t)chunk * 8);
+  const int N = p.d.N;
+  const int nloc = p.d.node_end - p.d.node_begin;
+  const int w = blockIdx.y;
+  const int g = p.work_group[w];
+  const int c0 = blockIdx.x * chunk;
+  const int cn = min(chunk, nloc - c0);
+  const int cn2 = cn & ~1;
+  // stage: 16-byte loads of the group's final row, 4-byte loads of its mask words (zero padding past the row)
+  const double2 *src2 = reinterpret_cast<const double2 *>(g_final + (size_t)g * nloc + c0);
+  const bool al = (((size_t)g * nloc + c0) & 1) == 0;
+  if (al) {
+    for (int k = threadIdx.x; k < cn2 / 2; k += blockDim.x) reinterpret_cast<double2 *>(tile)[k] = __ldg(src2 + k);
+    if ((cn & 1) && threadIdx.x == 0) tile[cn - 1] = g_final[(size_t)g * nloc + c0 + cn - 1];
+  } else {
+    for (int k = threadIdx.x; k < cn; k += blockDim.x) tile[k] = g_final[(size_t)g * nloc + c0 + k];
+  }
+  const int nwords = chunk >> 5;
+  for (int k = threadIdx.x; k < nwords; k += blockDim.x) {
+    const int gw = (c0 >> 5) + k;
+    mwords[k] = gw < mwg ? g_maskw[(size_t)g * mwg + gw] : 0u;
+  }
+  __syncthreads();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the copy engine
+  const int tb = p.work_begin[w], te = p.work_end[w];
+  const int gnode0 = p.d.node_begin + c0;
+  if (threadIdx.x == 0) {
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile);
+    const uint32_t msrc = (uint32_t)__cvta_generic_to_shared(mwords);
+    const int bytes = cn2 * 8;
+    // mask bytes of the chunk, rounded up to 16 and clipped to the row pitch
+    const int mrow_bytes = p.mw32 * 4, moff = gnode0 >> 3;
+    int mbytes = ((((cn + 7) >> 3) + 15) & ~15);
+    if (moff + mbytes > mrow_bytes) mbytes = mrow_bytes - moff;
+    for (int i = tb; i < te; ++i) {
+      const int t = p.group_tasks[i];
+      double *dst = p.score_out + (size_t)t * N + gnode0;
+      if (bytes > 0)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+      unsigned char *mdst = reinterpret_cast<unsigned char *>(p.mask_out) + (size_t)t * mrow_bytes + moff;
+      if (mbytes > 0)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mdst), "r"(msrc), "r"(mbytes) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  } else if ((cn & 1) && threadIdx.x == 1) {
+    for (int i = tb; i < te; ++i) p.score_out[(size_t)p.group_tasks[i] * N + gnode0 + cn - 1] = tile[cn - 1];
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the reads
+}

@@ -175,7 +175,11 @@ struct vc_snapshot {
   uint32_t *mask_out = nullptr;
   double *score_out = nullptr, *best_score = nullptr;
   int32_t *best_node = nullptr;
-  int mw32 = 0;
+  int mw32 = 0;        // 32-bit words per mask row on the device (16-byte pitch)
+  int mw32_logical = 0;  // ... of the uint64 row the ABI hands out
+  double *g_final = nullptr;   // [G][Nloc] final score of every (group, node)
+  uint32_t *g_maskw = nullptr; // [G][mwg] feasibility words
+  int mwg = 0;
   bool matrix_allocated = false;
   double last_expand_ms = 0, last_dense_ms = 0;
   // host copies kept for the dense-pass grouping
@@ -292,6 +296,9 @@ void choose_geometry(vc_snapshot *s) {
 }
 
 int free_dense(vc_snapshot *s) {
+  if (s->g_final) cudaFree(s->g_final);
+  if (s->g_maskw) cudaFree(s->g_maskw);
+  s->g_final = nullptr; s->g_maskw = nullptr;
   void *ptrs[] = {s->g_req, s->g_kreq, s->g_knz, s->g_order, s->g_best_score, s->g_has, s->g_class, s->g_stats,
                   s->g_best_node, s->g_cat, s->work_group, s->work_begin, s->work_end, s->group_tasks, s->task_group,
                   s->part_score, s->part_node, s->mask_out, s->score_out, s->best_score, s->best_node};
@@ -1213,13 +1220,24 @@ static int dense_prepare(vc_snapshot *s) {
   for (size_t g = 0; g < G; ++g) g_count[g + 1] += g_count[g];
   std::vector<int32_t> group_tasks(T), fill(g_count.begin(), g_count.end() - 1);
   for (size_t t = 0; t < T; ++t) group_tasks[fill[group_of[t]]++] = (int32_t)t;
-  // work items: <= 64 rows of one group each
-  const int chunk = 64;
+  // work items: a few rows of one group each
+  int chunk = 16;  // rows per work item: more, smaller CTAs keep the copy engines of all SMs busy to the end
+  if (const char *e = getenv("VC_EXPAND_ROWS")) chunk = std::max(1, atoi(e));
   std::vector<int32_t> wg, wb, we;
   for (size_t g = 0; g < G; ++g)
     for (int b = g_count[g]; b < g_count[g + 1]; b += chunk) {
       wg.push_back((int32_t)g); wb.push_back(b); we.push_back(std::min(b + chunk, g_count[g + 1]));
     }
+  // launch order = row order of the matrix: concurrent CTAs then write one contiguous band of task rows (tasks of a
+  // job are consecutive and share their group), which keeps the HBM write stream and the TLB local
+  {
+    std::vector<int> ord(wg.size());
+    for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
+    std::sort(ord.begin(), ord.end(), [&](int a, int b) { return group_tasks[wb[a]] < group_tasks[wb[b]]; });
+    std::vector<int32_t> wg2(wg.size()), wb2(wg.size()), we2(wg.size());
+    for (size_t i = 0; i < ord.size(); ++i) { wg2[i] = wg[ord[i]]; wb2[i] = wb[ord[i]]; we2[i] = we[ord[i]]; }
+    wg.swap(wg2); wb.swap(wb2); we.swap(we2);
+  }
   s->n_work = (int)wg.size();
   auto up = [&](auto *&dptr, const auto &vec) -> int {
     using E = typename std::remove_reference_t<decltype(vec)>::value_type;
@@ -1250,7 +1268,8 @@ static int dense_prepare(vc_snapshot *s) {
     s->hn_score = nullptr;
     CUDA_TRY(cudaMalloc(&s->hn_score, std::max<size_t>(16, G * (size_t)s->hn_H * 8)));
   }
-  s->mw32 = (int)(2 * ((N + 63) / 64));
+  s->mw32_logical = (int)(2 * ((N + 63) / 64));
+  s->mw32 = (s->mw32_logical + 3) & ~3;
   s->dense_ready = true;
   return VC_OK;
 }
@@ -1335,9 +1354,32 @@ int vc_dense_finish(vc_snapshot *s, int materialize) {
     CUDA_TRY(cudaGetLastError());
   }
   if (materialize && s->n_work > 0 && nloc > 0) {
-    dim3 grid((unsigned)((nloc + 511) / 512), (unsigned)s->n_work);
-    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
-    k_group_expand<<<grid, 256, 0, s->stream>>>(p);
+    if ((N % 2) == 0 && (s->dd.node_begin % 128) == 0 && !getenv("VC_EXPAND_PLAIN")) {
+      // bulk-copy variant: final rows of the groups first (G x Nloc evaluations), then one streaming kernel
+      s->mwg = ((nloc + 127) / 128) * 4;
+      if (!s->g_final) {
+        CUDA_TRY(cudaMalloc(&s->g_final, std::max<size_t>(16, (size_t)s->n_groups * nloc * 8)));
+        CUDA_TRY(cudaMalloc(&s->g_maskw, std::max<size_t>(16, (size_t)s->n_groups * s->mwg * 4)));
+      }
+      CUDA_TRY(cudaMemsetAsync(s->g_maskw, 0, std::max<size_t>(16, (size_t)s->n_groups * s->mwg * 4), s->stream));
+      dim3 fgrid((unsigned)((nloc + 255) / 256), (unsigned)s->n_groups);
+      k_group_final<<<fgrid, 256, 0, s->stream>>>(p, s->g_final, s->g_maskw, s->mwg);
+      g_launches++;
+      // node chunks of <= 8192 nodes (64 KB of scores) so several CTAs share an SM
+      int max_chunk = 8192;
+      if (const char *e = getenv("VC_EXPAND_CHUNK")) max_chunk = std::max(128, atoi(e) / 128 * 128);
+      const int nchunks = (nloc + max_chunk - 1) / max_chunk;
+      const int chunk = (((nloc + nchunks - 1) / nchunks) + 127) & ~127;
+      const size_t smem = (size_t)chunk * 8 + (size_t)chunk / 8 + 16;
+      CUDA_TRY(cudaFuncSetAttribute(k_group_expand_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 grid((unsigned)((nloc + chunk - 1) / chunk), (unsigned)s->n_work);
+      CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+      k_group_expand_bulk<<<grid, 256, smem, s->stream>>>(p, chunk, s->g_final, s->g_maskw, s->mwg);
+    } else {
+      dim3 grid((unsigned)((nloc + 511) / 512), (unsigned)s->n_work);
+      CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+      k_group_expand<<<grid, 256, 0, s->stream>>>(p);
+    }
     g_launches++;
     CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
     CUDA_TRY(cudaGetLastError());
@@ -1374,7 +1416,9 @@ int vc_dense_fetch(vc_snapshot *s, uint64_t *mask_out, double *score_out, double
   const size_t T = s->dims.n_tasks, N = s->dims.n_nodes;
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   if ((mask_out || score_out) && !s->matrix_allocated) return fail(VC_EINVAL, "matrix was not materialised");
-  if (mask_out) CUDA_TRY(cudaMemcpy(mask_out, s->mask_out, T * (size_t)s->mw32 * 4, cudaMemcpyDeviceToHost));
+  if (mask_out && T > 0)
+    CUDA_TRY(cudaMemcpy2D(mask_out, (size_t)s->mw32_logical * 4, s->mask_out, (size_t)s->mw32 * 4, (size_t)s->mw32_logical * 4, T,
+                          cudaMemcpyDeviceToHost));
   if (score_out) CUDA_TRY(cudaMemcpy(score_out, s->score_out, T * N * 8, cudaMemcpyDeviceToHost));
   if (best_score) CUDA_TRY(cudaMemcpy(best_score, s->best_score, T * 8, cudaMemcpyDeviceToHost));
   if (best_node) CUDA_TRY(cudaMemcpy(best_node, s->best_node, T * 4, cudaMemcpyDeviceToHost));
