@@ -4,6 +4,8 @@ import os
 import sys
 import time
 
+os.environ.setdefault("VC_PROF", "1")  # the instrumented instance of the incremental kernel
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from volcano_b200 import engine  # noqa: E402
 from volcano_b200.synth import make_snapshot  # noqa: E402

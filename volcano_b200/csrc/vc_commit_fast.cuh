@@ -232,6 +232,10 @@ struct CtlFast {  // shared-memory state of the fast kernel next to Ctl
   unsigned ev_tag;
 };
 
+// PROF = true keeps the phase / owner-path cycle counters (tools/prof_commit.py, VC_PROF=1); the production
+// instance carries no clock reads on the control warp's critical path.
+#define FPROF_MARK(k) do { if (PROF) { PROF_MARK(k); } } while (0)
+template <bool PROF>
 __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams fp) {
   const DevConf &c = p.c;
   const int R = p.d.R, K = p.d.K, N = p.d.N, J = p.d.J, Q = p.d.Q, NR = p.d.NR, T = p.d.T;
@@ -532,7 +536,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   };
   // CMD_EVAL (warp 1): re-evaluate node F.ev_i for the cached group, maintain this CTA's best incrementally
   // (rescan only when the holder got worse) and publish the CTA's new best in the ring.
-  int spec_i = -1, spec_group = -2, spec_cat = 2, n_spec_hit = 0;
+  int spec_i = -1, spec_group = -2, spec_cat = 2, n_spec_hit = 0, n_rescan = 0, n_eval = 0;
   double spec_sc = 0.0;
   auto eval_and_publish = [&](int my_group) {
     const int i = F.ev_i;
@@ -555,7 +559,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       bs = sc; bn = dn;
     }
     __syncwarp();
-    if (rescan) { Best r = scan_cache(fs, nmine, nbase); bs = r.score; bn = r.node; cnt = r.cnt; }
+    n_eval += 1;
+    if (rescan) { n_rescan += 1; Best r = scan_cache(fs, nmine, nbase); bs = r.score; bn = r.node; cnt = r.cnt; }
     if (lane == 0) {
       F.cta_best_score = bs; F.cta_best_node = bn; F.cta_cnt = cnt;
       Best nb{bs, bn, cnt};
@@ -575,7 +580,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     for (;;) {
       __syncthreads();  // B1: command posted
       const int cmd = S.cmd;
-      if (cmd == CMD_EXIT) break;
+      if (cmd == CMD_EXIT) {
+        if (warp == 1 && lane == 0) { atomicAdd(&p.counters[8], n_spec_hit); atomicAdd(&p.counters[9], n_rescan); atomicAdd(&p.counters[10], n_eval); }
+        break;
+      }
       if (cmd == CMD_SWEEP) sweep_part();
       else if (cmd == CMD_DISCARD) discard_part();
       else if (cmd == CMD_EVAL) {  // no block-wide B2: warp 1 signals warp 0 on named barrier 1
@@ -802,7 +810,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         }
         return ready + pbe >= minav;
       };
-      PROF_MARK(0);
+      FPROF_MARK(0);
       // Consume the publication of the last placement (made while the verdict cache was valid): the owner CTA
       // joins its evaluator warp (B2 of CMD_EVAL), every other CTA reads the one ring record; then the global
       // best is maintained incrementally (refolded only when its holder got worse).
@@ -813,10 +821,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         if (o != last_owner) { n_owner_change += 1; last_owner = o; }
         Best nb;
         if (o == cta) {
-          const long long t0_ = clock64();
+          const long long t0_ = PROF ? clock64() : 0;
           asm volatile("bar.sync 1, 64;" ::: "memory");  // join the evaluator warp
-          t_join = clock64();
-          acc_post_to_joinstart += t0_ - t_post; acc_join_wait += t_join - t0_; acc_n += 1;
+          if (PROF) { t_join = clock64(); acc_post_to_joinstart += t0_ - t_post; acc_join_wait += t_join - t0_; acc_n += 1; }
           nb.score = F.ev_score; nb.node = F.ev_node; nb.cnt = F.ev_cnt;
         } else {
           t_join = 0;
@@ -853,12 +860,12 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       // ---- allocateResourcesForTasks, allocate.go:558-694 ----
       for (;;) {
         if (cursor >= task_end || N == 0) break;  // no nodes: return nil before touching the tasks (allocate.go:563-567)
-        PROF_MARK(4);
+        FPROF_MARK(4);
         const int t = meta.x, grp = meta.y, rl = meta.z - role_base;
         cursor += 1;
         if (cursor < task_end) meta = __ldg(&p.tmeta[cursor]);  // prefetch the next task's record
         resolve();
-        t_a = clock64();
+        if (PROF) t_a = clock64();
         if (grp != cur_group) {  // stage the group's request record (shared: workers read it in sweeps)
           __syncwarp();
           if (lane < R) S.trec.req[lane] = __ldg(&p.g_req[(size_t)lane * p.n_groups + grp]);
@@ -898,8 +905,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         // For a 'pure' job the role-level error cache can never change a verdict (same record, node
         // resources only shrink inside a visit), so it is skipped; other jobs take exact full sweeps.
         const bool use_cache = c.enable_ecache && named_role && !pure;
-        PROF_MARK(1);
-        t_b = clock64();
+        FPROF_MARK(1);
+        if (PROF) t_b = clock64();
 
         if (pure && grp == cache_group) {
           // -------- incremental step: verdict cache, slot table and global best are already current --------
@@ -910,14 +917,14 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             ag += 1; since_sync = 0;
           }
           n_incr += 1;
-          PROF_MARK(2);
+          FPROF_MARK(2);
         } else {
           // -------- full sweep --------
           if (lane == 0) { S.cmd = CMD_SWEEP; S.sweep_rl = rl; S.sweep_use_cache = use_cache ? 1 : 0; S.visit_id = visit_id; }
           __syncthreads();  // B1
           sweep_part();
           __syncthreads();  // B2
-          PROF_MARK(2);
+          FPROF_MARK(2);
           Best mine{0.0, -1, 0};
           if (lane < nwarps) best_fold(mine, S.w_score[0][lane], S.w_node[0][lane], S.w_cnt[0][lane]);
           best_warp_reduce(mine);
@@ -929,8 +936,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           g_best_score = g.score; g_best_node = g.node; g_cnt = g.cnt;
         }
         n_steps += 1;
-        PROF_MARK(3);
-        t_c = clock64();
+        FPROF_MARK(3);
+        if (PROF) t_c = clock64();
 
         if (g_cnt == 0) {  // no feasible node, allocate.go:639-659
           __syncwarp();
@@ -984,8 +991,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
               S.cmd = CMD_EVAL;
             }
             __syncthreads();  // B1 of CMD_EVAL
-            t_post = clock64();
-            if (t_join != 0) { acc_join_to_post += t_post - t_join; acc_ja += t_a - t_join; acc_ab += t_b - t_a; acc_bc += t_c - t_b; acc_cp += t_post - t_c; }
+            if (PROF) t_post = clock64();
+            if (PROF && t_join != 0) { acc_join_to_post += t_post - t_join; acc_ja += t_a - t_join; acc_ab += t_b - t_a; acc_bc += t_c - t_b; acc_cp += t_post - t_c; }
           }
         }
         // job.UpdateTaskStatus + event handlers: drf (drf.go:391-418), proportion (proportion.go:475-497)
@@ -1019,7 +1026,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         if (role_min_active) __syncwarp();
         if (job_ready_now()) break;  // ssn.SubJobReady, allocate.go:676-678
       }
-      PROF_MARK(4);
+      FPROF_MARK(4);
       resolve();
 
       // ---- statement outcome, allocate.go:681-693 and :330-337 ----
@@ -1125,12 +1132,13 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         rdyn[role_base + r] = rd;
       }
       __syncwarp();
-      PROF_MARK(0);
+      FPROF_MARK(0);
     }
     if (lane == 0) {
       S.cmd = CMD_EXIT;
       S.n_dec = n_dec; S.n_vis = n_vis; S.n_fit = n_fit; S.n_steps = n_steps; S.n_full = n_full; S.n_incr = n_incr;
       S.pick2 = n_owner_change;
+      if (PROF) {
       atomicAdd((unsigned long long *)&p.prof[8], (unsigned long long)acc_post_to_joinstart);
       atomicAdd((unsigned long long *)&p.prof[9], (unsigned long long)acc_n);
       atomicAdd((unsigned long long *)&p.prof[10], (unsigned long long)acc_join_wait);
@@ -1139,6 +1147,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       atomicAdd((unsigned long long *)&p.prof[13], (unsigned long long)acc_ab);
       atomicAdd((unsigned long long *)&p.prof[14], (unsigned long long)acc_bc);
       atomicAdd((unsigned long long *)&p.prof[15], (unsigned long long)acc_cp);
+      }
 
     }
     __syncthreads();  // B1 of the exit command

@@ -1014,14 +1014,14 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
     CUDA_TRY(cudaMalloc(&s->d_decisions, std::max<size_t>(1, T) * sizeof(vc_decision)));
     CUDA_TRY(cudaMalloc(&s->d_visits, (T + J + 1) * sizeof(vc_visit)));
     CUDA_TRY(cudaMalloc(&s->d_fit, std::max<size_t>(1, T) * 4));
-    CUDA_TRY(cudaMalloc(&s->d_counters, 8 * 4));
+    CUDA_TRY(cudaMalloc(&s->d_counters, 16 * 4));
     CUDA_TRY(cudaMallocHost(&s->h_decisions, std::max<size_t>(1, T) * sizeof(vc_decision)));
     CUDA_TRY(cudaMallocHost(&s->h_visits, (T + J + 1) * sizeof(vc_visit)));
     CUDA_TRY(cudaMallocHost(&s->h_fit, std::max<size_t>(1, T) * 4));
-    CUDA_TRY(cudaMallocHost(&s->h_counters, 8 * 4));
+    CUDA_TRY(cudaMallocHost(&s->h_counters, 16 * 4));
   }
   CUDA_TRY(cudaMemsetAsync(s->mbox, 0, mbox_bytes, s->stream));
-  CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 8 * 4, s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 16 * 4, s->stream));
   // working copies of the mutable node state (the uploaded snapshot stays intact for re-runs / K1)
   CUDA_TRY(cudaMemcpyAsync(s->w_idle, s->n_idle.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
   CUDA_TRY(cudaMemcpyAsync(s->w_used, s->n_used.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
@@ -1084,7 +1084,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   }
   p.cta_wait = d_wait;
   if (G > 1024) return fail(VC_EUNSUPPORTED, "too many CTAs");
-  const void *kfn = s->fast ? (const void *)k_commit_fast
+  const void *kfn = s->fast ? (getenv("VC_PROF") ? (const void *)k_commit_fast<true> : (const void *)k_commit_fast<false>)
                   : s->dc.to_find > 0 ? (s->topo_any ? (const void *)k_commit<true, true, true, true> : (const void *)k_commit<true, true, false, true>)
                   : s->topo_any ? (const void *)k_commit<true, true, true> : s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
                                      : (s->dc.soft_active ? (const void *)k_commit<false, true> : (const void *)k_commit<false, false>);
@@ -1103,7 +1103,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(G), dim3(s->block), args, s->smem_bytes, s->stream));
   g_launches++;
   CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, 8 * 4, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, 16 * 4, cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaMemcpyAsync(s->h_prof, s->d_prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   if (d_wait) {
@@ -1170,6 +1170,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->stats.prof_cycles[6] = s->h_counters[5];  // full sweeps (fast kernel)
   r->stats.prof_cycles[7] = s->h_counters[6];  // incremental steps (fast kernel)
   r->stats.prof_cycles[5] = s->h_counters[7];  // owner changes between consecutive publications
+  if (getenv("VC_PROF_OWNER"))
+    fprintf(stderr, "evaluator (all CTAs): %d evaluations, %d speculation hits, %d cache rescans\n", s->h_counters[10], s->h_counters[8], s->h_counters[9]);
   if (getenv("VC_PROF_OWNER") && s->h_prof[9]) fprintf(stderr, "owner steps=%lld: post->join-start %.0f, join wait %.0f, join->next post (same owner) %.0f cycles [join->a %.0f, a->b %.0f, b->c %.0f, c->post %.0f]\n",
       s->h_prof[9], (double)s->h_prof[8] / s->h_prof[9], (double)s->h_prof[10] / s->h_prof[9], (double)s->h_prof[11] / s->h_prof[9], (double)s->h_prof[12] / s->h_prof[9], (double)s->h_prof[13] / s->h_prof[9], (double)s->h_prof[14] / s->h_prof[9], (double)s->h_prof[15] / s->h_prof[9]);
   *out = r;
