@@ -360,13 +360,12 @@ __global__ void __launch_bounds__(256) k_group_final(K1Params p, double *g_final
 // memory and streams it to every task row of the work item with the bulk asynchronous copy engine (cp.async.bulk
 // shared -> global; one elected thread issues one 16-byte-aligned store of the whole chunk per row, plus one for its
 // mask bytes), so HBM sees long contiguous write bursts and no partial-line stores.
-// grid (ceil(Nloc/chunk), n_work), 256 threads; chunk is a multiple of 128 nodes; dynamic smem = chunk*8 + chunk/8.
-// Needs an even N (16-byte row alignment of the score matrix); mask rows have a 16-byte pitch (p.mw32 words).
+// grid (ceil(Nloc/chunk), n_work), 256 threads; chunk is a multiple of 128 nodes; dynamic smem = chunk*8.
+// Needs an even N (16-byte row alignment of the score matrix). The mask rows go out through k_mask_expand_bulk.
 __global__ void __launch_bounds__(256) k_group_expand_bulk(K1Params p, int chunk, const double *g_final, const uint32_t *g_maskw,
                                                           int mwg) {
   extern __shared__ __align__(128) unsigned char k1_smem[];
   double *tile = reinterpret_cast<double *>(k1_smem);
-  uint32_t *mwords = reinterpret_cast<uint32_t *>(k1_smem + (size_t)chunk * 8);
   const int N = p.d.N;
   const int nloc = p.d.node_end - p.d.node_begin;
   const int w = blockIdx.y;
@@ -383,35 +382,59 @@ __global__ void __launch_bounds__(256) k_group_expand_bulk(K1Params p, int chunk
   } else {
     for (int k = threadIdx.x; k < cn; k += blockDim.x) tile[k] = g_final[(size_t)g * nloc + c0 + k];
   }
-  const int nwords = chunk >> 5;
-  for (int k = threadIdx.x; k < nwords; k += blockDim.x) {
-    const int gw = (c0 >> 5) + k;
-    mwords[k] = gw < mwg ? g_maskw[(size_t)g * mwg + gw] : 0u;
-  }
   __syncthreads();
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the copy engine
   const int tb = p.work_begin[w], te = p.work_end[w];
   const int gnode0 = p.d.node_begin + c0;
   if (threadIdx.x == 0) {
     const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile);
-    const uint32_t msrc = (uint32_t)__cvta_generic_to_shared(mwords);
     const int bytes = cn2 * 8;
-    // mask bytes of the chunk, rounded up to 16 and clipped to the row pitch
-    const int mrow_bytes = p.mw32 * 4, moff = gnode0 >> 3;
-    int mbytes = ((((cn + 7) >> 3) + 15) & ~15);
-    if (moff + mbytes > mrow_bytes) mbytes = mrow_bytes - moff;
     for (int i = tb; i < te; ++i) {
-      const int t = p.group_tasks[i];
-      double *dst = p.score_out + (size_t)t * N + gnode0;
+      double *dst = p.score_out + (size_t)p.group_tasks[i] * N + gnode0;
       if (bytes > 0)
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-      unsigned char *mdst = reinterpret_cast<unsigned char *>(p.mask_out) + (size_t)t * mrow_bytes + moff;
-      if (mbytes > 0)
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(mdst), "r"(msrc), "r"(mbytes) : "memory");
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   } else if ((cn & 1) && threadIdx.x == 1) {
     for (int i = tb; i < te; ++i) p.score_out[(size_t)p.group_tasks[i] * N + gnode0 + cn - 1] = tile[cn - 1];
   }
   if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the reads
+}
+
+// K1m: the feasibility-mask rows of a work item. The rows of one group are identical and mask rows have a 16-byte
+// pitch, so the CTA replicates the group's row in shared memory and covers every run of consecutive task ids with
+// ONE bulk store (tasks of a job are consecutive and share their group). grid n_work, 128 threads,
+// dynamic smem = rows_per_item * pitch bytes.
+__global__ void __launch_bounds__(128) k_mask_expand_bulk(K1Params p, const uint32_t *g_maskw, int mwg, int rows_cap) {
+  extern __shared__ __align__(128) unsigned char k1m_smem[];
+  uint32_t *rows = reinterpret_cast<uint32_t *>(k1m_smem);
+  const int w = blockIdx.x;
+  const int g = p.work_group[w];
+  const int tb = p.work_begin[w], te = p.work_end[w];
+  const int nr = min(te - tb, rows_cap);
+  const int pitch = p.mw32;  // 32-bit words per row
+  const int w0 = p.d.node_begin >> 5;
+  for (int k = threadIdx.x; k < pitch; k += blockDim.x) {
+    const int gw = k - w0;
+    rows[k] = (gw >= 0 && gw < mwg) ? g_maskw[(size_t)g * mwg + gw] : 0u;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < (nr - 1) * pitch; k += blockDim.x) rows[pitch + k] = rows[k % pitch];
+  __syncthreads();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (threadIdx.x == 0) {
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(rows);
+    int i = tb;
+    while (i < te) {
+      const int t0 = p.group_tasks[i];
+      int j = i + 1;
+      while (j < te && j - i < nr && p.group_tasks[j] == t0 + (j - i)) ++j;
+      unsigned char *dst = reinterpret_cast<unsigned char *>(p.mask_out) + (size_t)t0 * pitch * 4;
+      const int bytes = (j - i) * pitch * 4;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+      i = j;
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
 }

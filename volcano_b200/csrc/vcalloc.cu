@@ -175,6 +175,7 @@ struct vc_snapshot {
   uint32_t *mask_out = nullptr;
   double *score_out = nullptr, *best_score = nullptr;
   int32_t *best_node = nullptr;
+  int rows_per_item = 16;
   int mw32 = 0;        // 32-bit words per mask row on the device (16-byte pitch)
   int mw32_logical = 0;  // ... of the uint64 row the ABI hands out
   double *g_final = nullptr;   // [G][Nloc] final score of every (group, node)
@@ -1241,6 +1242,7 @@ static int dense_prepare(vc_snapshot *s) {
     wg.swap(wg2); wb.swap(wb2); we.swap(we2);
   }
   s->n_work = (int)wg.size();
+  s->rows_per_item = chunk;
   auto up = [&](auto *&dptr, const auto &vec) -> int {
     using E = typename std::remove_reference_t<decltype(vec)>::value_type;
     void *q = nullptr;
@@ -1372,11 +1374,16 @@ int vc_dense_finish(vc_snapshot *s, int materialize) {
       if (const char *e = getenv("VC_EXPAND_CHUNK")) max_chunk = std::max(128, atoi(e) / 128 * 128);
       const int nchunks = (nloc + max_chunk - 1) / max_chunk;
       const int chunk = (((nloc + nchunks - 1) / nchunks) + 127) & ~127;
-      const size_t smem = (size_t)chunk * 8 + (size_t)chunk / 8 + 16;
+      const size_t smem = (size_t)chunk * 8 + 16;
       CUDA_TRY(cudaFuncSetAttribute(k_group_expand_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       dim3 grid((unsigned)((nloc + chunk - 1) / chunk), (unsigned)s->n_work);
+      const int rows_cap = std::max(1, std::min(s->rows_per_item, (int)(96 * 1024 / std::max(16, s->mw32 * 4))));
+      const size_t msmem = (size_t)rows_cap * s->mw32 * 4 + 16;
+      CUDA_TRY(cudaFuncSetAttribute(k_mask_expand_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
       CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
       k_group_expand_bulk<<<grid, 256, smem, s->stream>>>(p, chunk, s->g_final, s->g_maskw, s->mwg);
+      k_mask_expand_bulk<<<(unsigned)s->n_work, 128, msmem, s->stream>>>(p, s->g_maskw, s->mwg, rows_cap);
+      g_launches++;
     } else {
       dim3 grid((unsigned)((nloc + 511) / 512), (unsigned)s->n_work);
       CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
