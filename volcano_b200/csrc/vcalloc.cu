@@ -449,6 +449,15 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   }
   int rc = build_devconf(s, nd);
   if (rc) return rc;
+  const bool tprof = getenv("VC_PROF_UPLOAD") != nullptr;
+  double tlast = now_ms();
+  auto tick = [&](const char *what) {
+    if (!tprof) return;
+    const double t = now_ms();
+    fprintf(stderr, "upload: %-28s %.3f ms\n", what, t - tlast);
+    tlast = t;
+  };
+  tick("devconf (scans node arrays)");
 
   // ---- host session-open logic ---------------------------------------------------------
   // ssn.TotalResource (framework/session.go:272-274)
@@ -506,6 +515,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     }
   }
   s->max_job_tasks = max_job_tasks;
+  tick("totals, shares, task order");
   // buildAllocateContext (allocate.go:142-206): jobs that enter the per-queue PQs, in JobOrderFn order
   std::vector<uint32_t> j_rank(J);
   {
@@ -568,29 +578,76 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     qjobs_off[q + 1] = qjobs_off[q] + (int32_t)qlists[q].size();
     qjobs.insert(qjobs.end(), qlists[q].begin(), qlists[q].end());
   }
+  tick("job / queue order");
   // (class, request) groups: tasks of one pod template share their whole verdict / score row
   std::vector<int32_t> group_of(T);
   {
-    std::unordered_map<std::string, int> index;
+    // (1) one 64-bit hash per task, built in dimension-major passes (the inputs are dimension-major: sequential reads)
+    auto mix = [](uint64_t h, uint64_t v) {
+      h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+      h *= 0xff51afd7ed558ccdull;
+      return h ^ (h >> 33);
+    };
+    auto bits = [](double x) { uint64_t u; std::memcpy(&u, &x, 8); return u; };
+    std::vector<uint64_t> hsh(T, 0x243f6a8885a308d3ull);
+    std::vector<uint32_t> has_x(T);
+    for (size_t t = 0; t < T; ++t) {
+      has_x[t] = tk->req_has[t] | ((s->topo_any && s->h_job_soft[tk->job[t]]) ? VC_HAS_TOPO_TASK : 0u);
+      hsh[t] = mix(mix(hsh[t], (uint32_t)tk->klass[t]), has_x[t]);
+    }
+    for (size_t d = 0; d < R; ++d) { const double *col = tk->resreq + d * T; for (size_t t = 0; t < T; ++t) hsh[t] = mix(hsh[t], bits(col[t])); }
+    for (size_t k = 0; k < K; ++k) { const double *col = tk->k8s_req + k * T; for (size_t t = 0; t < T; ++t) hsh[t] = mix(hsh[t], bits(col[t])); }
+    for (size_t k = 0; k < 2; ++k) { const double *col = tk->k8s_nonzero_req + k * T; for (size_t t = 0; t < T; ++t) hsh[t] = mix(hsh[t], bits(col[t])); }
+    // (2) tentative groups by hash (tasks of a job are adjacent and usually share their record)
+    std::unordered_map<uint64_t, int> index;
     index.reserve(1024);
     s->group_rep.clear();
-    std::string key;
     for (size_t t = 0; t < T; ++t) {
-      key.clear();
-      key.append(reinterpret_cast<const char *>(&tk->klass[t]), 4);
-      const uint32_t has_x = tk->req_has[t] | ((s->topo_any && s->h_job_soft[tk->job[t]]) ? VC_HAS_TOPO_TASK : 0u);
-      key.append(reinterpret_cast<const char *>(&has_x), 4);
-      for (size_t d = 0; d < R; ++d) key.append(reinterpret_cast<const char *>(&tk->resreq[d * T + t]), 8);
-      for (size_t k = 0; k < K; ++k) key.append(reinterpret_cast<const char *>(&tk->k8s_req[k * T + t]), 8);
-      for (size_t k = 0; k < 2; ++k) key.append(reinterpret_cast<const char *>(&tk->k8s_nonzero_req[k * T + t]), 8);
-      auto it = index.find(key);
+      if (t > 0 && hsh[t] == hsh[t - 1]) { group_of[t] = group_of[t - 1]; continue; }
+      auto it = index.find(hsh[t]);
       if (it == index.end()) {
-        it = index.emplace(key, (int)s->group_rep.size()).first;
+        it = index.emplace(hsh[t], (int)s->group_rep.size()).first;
         s->group_rep.push_back((int32_t)t);
       }
       group_of[t] = it->second;
     }
+    // (3) exact verification against the group representative, again in dimension-major passes; a hash collision
+    //     (never observed) falls back to exact keys
+    bool exact = true;
+    const std::vector<int32_t> &rep = s->group_rep;
+    for (size_t t = 0; t < T && exact; ++t) {
+      const int r = rep[group_of[t]];
+      if (tk->klass[t] != tk->klass[r] || has_x[t] != has_x[r]) exact = false;
+    }
+    auto verify = [&](const double *col) {
+      for (size_t t = 0; t < T; ++t)
+        if (bits(col[t]) != bits(col[rep[group_of[t]]])) return false;
+      return true;
+    };
+    for (size_t d = 0; d < R && exact; ++d) exact = verify(tk->resreq + d * T);
+    for (size_t k = 0; k < K && exact; ++k) exact = verify(tk->k8s_req + k * T);
+    for (size_t k = 0; k < 2 && exact; ++k) exact = verify(tk->k8s_nonzero_req + k * T);
+    if (!exact) {
+      std::unordered_map<std::string, int> sindex;
+      s->group_rep.clear();
+      std::string key;
+      for (size_t t = 0; t < T; ++t) {
+        key.clear();
+        key.append(reinterpret_cast<const char *>(&tk->klass[t]), 4);
+        key.append(reinterpret_cast<const char *>(&has_x[t]), 4);
+        for (size_t d = 0; d < R; ++d) key.append(reinterpret_cast<const char *>(&tk->resreq[d * T + t]), 8);
+        for (size_t k = 0; k < K; ++k) key.append(reinterpret_cast<const char *>(&tk->k8s_req[k * T + t]), 8);
+        for (size_t k = 0; k < 2; ++k) key.append(reinterpret_cast<const char *>(&tk->k8s_nonzero_req[k * T + t]), 8);
+        auto it = sindex.find(key);
+        if (it == sindex.end()) {
+          it = sindex.emplace(key, (int)s->group_rep.size()).first;
+          s->group_rep.push_back((int32_t)t);
+        }
+        group_of[t] = it->second;
+      }
+    }
   }
+  tick("group dedup");
   const size_t NG = s->group_rep.size();
   s->n_groups = (int)NG;
   s->h_group_of = group_of;
@@ -831,6 +888,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     if (s->hn_smem) s->smem_bytes += 3 * R * (size_t)s->hn_cap * 8 + R * (size_t)s->hn_cap + (size_t)s->hn_cap * 4 + 64;
   }
 
+  tick("records, heap sizes, topology");
   // ---- plan + stage + one H2D copy ------------------------------------------------------
   for (int pass = 0; pass < 2; ++pass) {
     const bool plan = pass == 0;
@@ -898,6 +956,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
       }
     }
   }
+  tick("staging memcpy");
   CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
   CUDA_TRY(cudaMemcpyAsync(s->in.dev, s->in.pin, s->in.used, cudaMemcpyHostToDevice, s->stream));
   s->h2d_bytes = (int64_t)s->in.used;
@@ -931,6 +990,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   }
   CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
+  tick("H2D + K0 + sync");
   s->uploaded = true;
   s->dense_ready = false;
   // keep what the dense pass needs to group tasks
@@ -940,6 +1000,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   s->h_has.assign(tk->req_has, tk->req_has + T);
   s->h_class.assign(tk->klass, tk->klass + T);
   s->h_task_job.assign(tk->job, tk->job + T);
+  tick("host copies for the dense pass");
   s->upload_ms = now_ms() - t0;
   return VC_OK;
 }
