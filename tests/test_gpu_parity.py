@@ -43,6 +43,17 @@ def test_allocate_goldens(case, gpu, oracle_engine):
     _assert_same(case.result, oracle_engine(snap))
 
 
+def test_action_interface_like_the_reference(gpu):
+    """test.RegisterSession(tiers, nil); test.Run([]framework.Action{allocate.New()}); test.CheckAll(i)"""
+    from volcano_b200 import action
+    case = G.allocate_cases()[3]
+    case.RegisterSession(G.allocate_tiers())
+    act = action.New()
+    assert act.Name() == "allocate"
+    case.Run([act])
+    assert case.CheckAll() is None, case.CheckAll()
+
+
 @pytest.mark.parametrize("case", G.fareshare_cases(), ids=lambda c: c.Name[:40])
 def test_fareshare_goldens(case, gpu, oracle_engine):
     snap = case.RegisterSession(G.fareshare_tiers())

@@ -50,8 +50,19 @@ class TestCommonStruct:
                                    tdm_zone_active=self.TdmZoneActive, hypernodes=self.HyperNodes)
         return self.snap
 
-    def Run(self, engine: Callable[[Snapshot], AllocateResult]) -> AllocateResult:
-        self.result = engine(self.snap)
+    def Run(self, engine) -> AllocateResult:
+        """`engine`: a Snapshot -> AllocateResult callable, or a list of Action objects like the reference's
+        test.Run(actions) (uthelper/helper.go:225-236)."""
+        if isinstance(engine, (list, tuple)):
+            from .action import Session
+            ssn = Session(self.snap)
+            for act in engine:
+                act.Initialize()
+                act.Execute(ssn)
+                act.UnInitialize()
+            self.result = ssn.result
+        else:
+            self.result = engine(self.snap)
         # FakeBinder: Statement.Commit -> cache.AddBindTask for every Allocate op (statement.go:309-325)
         self.binds: Dict[str, str] = {}
         self.pipelined: Dict[str, List[str]] = {}
