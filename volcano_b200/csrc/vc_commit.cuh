@@ -566,11 +566,14 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 7) & ~(uintptr_t)7);
   double *hn_score = reinterpret_cast<double *>(sp); sp += (size_t)p.hn_cap * 8;
   double *chain_val = reinterpret_cast<double *>(sp); sp += (size_t)p.chain_cap * 8;
-  int32_t *s_chain = reinterpret_cast<int32_t *>(sp);  // node -> chain of the CTA
+  int32_t *s_chain = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;  // node -> chain of the CTA
+  int32_t *s_chain_slots = reinterpret_cast<int32_t *>(sp);                 // [chain][L] local hypernode slots
   const int chain_base = c.nta_on ? p.cta_chain_off[cta] : 0;
   const int chain_n = c.nta_on ? p.cta_chain_off[cta + 1] - chain_base : 0;
-  if (c.nta_on)
+  if (c.nta_on) {
     for (int i = tid; i < nmine; i += blockDim.x) s_chain[i] = p.node_chain[nbase + i];
+    for (int k = tid; k < chain_n * c.nta_L; k += blockDim.x) s_chain_slots[k] = p.cta_chain[(size_t)chain_base * c.nta_L + k];
+  }
   const int hn_cap = p.hn_cap;
   const int hn_base = c.nta_tables ? p.cta_hn_off[cta] : 0;
   const int hn_n = c.nta_tables ? p.cta_hn_off[cta + 1] - hn_base : 0;
@@ -582,7 +585,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
   double *hn_term = nullptr;  // [hn_cap][R] scratch of the per-step hypernode scores
   uint8_t *hn_flag = nullptr;
   if (c.nta_tables && p.hn_smem) {
-    sp = reinterpret_cast<unsigned char *>(((uintptr_t)(s_chain + cap) + 7) & ~(uintptr_t)7);
+    sp = reinterpret_cast<unsigned char *>(((uintptr_t)(s_chain_slots + (size_t)p.chain_cap * c.nta_L) + 7) & ~(uintptr_t)7);
     hn_used = reinterpret_cast<double *>(sp); sp += (size_t)R * hn_cap * 8;
     double *al = reinterpret_cast<double *>(sp); sp += (size_t)R * hn_cap * 8;
     int32_t *ids = reinterpret_cast<int32_t *>(sp); sp += (size_t)hn_cap * 4;
@@ -607,7 +610,9 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
     for (int k = tid; k < hn_n; k += blockDim.x) {
       const int h = hn_ids[k];
       bool hit = false;
-      for (int l = 0; l < c.nta_L; ++l) hit = hit || p.hn_member[(size_t)l * N + node] == h;
+#pragma unroll
+      for (int l = 0; l < VC_MAX_TIERS; ++l)  // independent loads: no short-circuit between the tier levels
+        if (l < c.nta_L) hit |= __ldg(&p.hn_member[(size_t)l * N + node]) == h;
       if (!hit) continue;
       for (int d = 0; d < R; ++d) {
         if (d >= 2 && !(has & (1u << d))) continue;
@@ -969,7 +974,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
         }
         __syncthreads();
         for (int k = tid; k < chain_n; k += blockDim.x) {  // batchNodeOrderFnForNormalPods per distinct chain
-          const int32_t *sl = p.cta_chain + (size_t)(chain_base + k) * c.nta_L;
+          const int32_t *sl = s_chain_slots + (size_t)k * c.nta_L;
           chain_val[k] = nta_node_score(c, [&](int l) { return sl[l] < 0 ? 1.0 : hn_score[sl[l]]; });
         }
         __syncthreads();

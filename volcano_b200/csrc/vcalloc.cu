@@ -292,7 +292,8 @@ void choose_geometry(vc_snapshot *s) {
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + rows * npc * 8 + (size_t)npc * (8 + 4 + 4) + 64;
     s->smem_bytes += (size_t)npc * (8 + 4 + 1 + 1) + 32;  // verdict cache + sampling flags
     // hn_score (at most npc * L local hypernodes) + chain_val (at most npc chains); hn_cap is set after this call
-    if (s->dc.nta_tables) s->smem_bytes += (size_t)npc * (s->hn_L + 1) * 8 + (size_t)npc * 4 + 32;
+    // ... + node -> chain (npc ints) + chain slots (at most npc chains x L)
+    if (s->dc.nta_tables) s->smem_bytes += (size_t)npc * (s->hn_L + 1) * 8 + (size_t)npc * 4 + (size_t)npc * s->hn_L * 4 + 64;
   }
 }
 
