@@ -222,3 +222,17 @@ def test_nta_soft_topology_allocate(oracle_engine):
     leaf = {k: v.split("-")[0] for k, v in tc.binds.items()}
     mine = [leaf[f"c1/p{i}"] for i in range(1, 7)]
     assert mine.count("s3") == 3 and mine.count("s4") == 3, mine  # s3 has room for 3 more, then the sibling leaf
+
+
+@pytest.mark.parametrize("name,alloc,pods,idle,used", G.NODE_INFO_ADD_POD, ids=[c[0][:30] for c in G.NODE_INFO_ADD_POD])
+def test_node_accounting_at_session_open(name, alloc, pods, idle, used):
+    """api/node_info_test.go:36-131: Idle / Used of a node given the pods the cache holds on it (incl. an Unknown-phase
+    pod, which still occupies the node, and an Idle that goes negative)."""
+    from volcano_b200.api import BuildNode, BuildPod, BuildPodGroup, BuildQueue, BuildResourceList
+    node = BuildNode("n1", BuildResourceList(alloc[0], alloc[1], ("pods", alloc[2])))
+    ps = [BuildPod("c1", n, "n1", phase, BuildResourceList(*req), "pg1") for n, phase, req in pods]
+    ps.append(BuildPod("c1", "pending", "", "Pending", BuildResourceList("1", "1G"), "pg1"))
+    snap = encode_cluster([node], ps, [BuildPodGroup("pg1", "c1", "q1", 1)], [BuildQueue("q1", 1)], SchedulerConf.default())
+    dims = [snap.dim_names.index(d) for d in ("cpu", "memory", "pods")]
+    assert tuple(snap.n_idle[dims, 0]) == idle
+    assert tuple(snap.n_used[dims, 0]) == used

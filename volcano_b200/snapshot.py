@@ -716,8 +716,9 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
         if not p.node_name or p.node_name not in nidx:
             continue
         st = get_task_status(p)
-        if st in ("Succeeded", "Failed", "Unknown"):
-            # terminated pods hold no resources (cache event handlers drop them from the node)
+        if st in ("Succeeded", "Failed"):
+            # terminated pods hold no resources: the cache adds a pod to its node unless isTerminated(status)
+            # (cache/event_handlers.go:65-67,228-233); a pod in Unknown phase still occupies the node
             continue
         i = nidx[p.node_name]
         v, _ = pod_req(p)
