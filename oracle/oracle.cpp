@@ -1647,5 +1647,11 @@ int64_t vco_balanced_allocation(void *h, int t, int n) { return balanced_allocat
 int vco_predicate(void *h, int t, int n) { return predicate(*(Session *)h, t, n) ? 1 : 0; }
 double vco_job_share(void *h, int j) { return ((Session *)h)->j_share[j]; }
 int vco_job_ready(void *h, int j) { return job_ready(*(Session *)h, j) ? 1 : 0; }
+// JobInfo.IsReady / IsPipelined (api/job_info.go:1169-1175) on the opening counters
+int vco_job_is_ready(void *h, int j) { Session &s = *(Session *)h; return s.j_ready[j] + s.j_pbe[j] >= s.j_min[j]; }
+int vco_job_is_pipelined(void *h, int j) {
+  Session &s = *(Session *)h;
+  return s.j_waiting[j] + s.j_ready[j] + s.j_pbe[j] >= s.j_min[j];
+}
 
 }  // extern "C"

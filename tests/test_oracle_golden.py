@@ -236,3 +236,34 @@ def test_node_accounting_at_session_open(name, alloc, pods, idle, used):
     dims = [snap.dim_names.index(d) for d in ("cpu", "memory", "pods")]
     assert tuple(snap.n_idle[dims, 0]) == idle
     assert tuple(snap.n_used[dims, 0]) == used
+
+
+@pytest.mark.parametrize("min_available,is_ready,is_pipelined", G.JOB_INFO_CASES)
+def test_job_readiness_counters(min_available, is_ready, is_pipelined):
+    """api/job_info_test.go:400-487 TestJobInfo (IsReady / IsPipelined from the status counters)."""
+    from volcano_b200.synth import make_snapshot
+    snap = make_snapshot("tiny", 1)
+    snap.j_ready_num[0] = G.JOB_INFO_COUNTS["ready"]
+    snap.j_waiting_num[0] = G.JOB_INFO_COUNTS["waiting"]
+    snap.j_pending_besteffort[0] = G.JOB_INFO_COUNTS["pending_besteffort"]
+    snap.j_min_available[0] = min_available
+    o = OracleSession(snap)
+    L = pyoracle.lib()
+    assert bool(L.vco_job_is_ready(o.h, 0)) == is_ready
+    assert bool(L.vco_job_is_pipelined(o.h, 0)) == is_pipelined
+    o.close()
+
+
+def test_best_effort_and_status_counters_from_pods():
+    """The counters themselves as the host mirror derives them from pods: a best-effort pending pod counts in
+    PendingBestEffortTaskNum and stays out of the allocate task list (allocate.go:255-271); Running pods are Ready."""
+    from volcano_b200.api import BuildNode, BuildPod, BuildPodGroup, BuildQueue, BuildResourceList
+    cpu = BuildResourceList("100m", "0")
+    pods = [BuildPod("c1", "pending-besteffort", "", "Pending", None, "pg1"),
+            BuildPod("c1", "running-besteffort", "n1", "Running", None, "pg1"),
+            BuildPod("c1", "pending", "", "Pending", cpu, "pg1"),
+            BuildPod("c1", "running", "n1", "Running", cpu, "pg1")]
+    snap = encode_cluster([BuildNode("n1", BuildResourceList("4", "8Gi", ("pods", "10")))], pods,
+                          [BuildPodGroup("pg1", "c1", "q1", 3)], [BuildQueue("q1", 1)], SchedulerConf.default())
+    assert snap.T == 1 and snap.task_keys == ["c1/pending"]
+    assert snap.j_pending_besteffort[0] == 1 and snap.j_ready_num[0] == 2 and snap.j_n_tasks_total[0] == 4
