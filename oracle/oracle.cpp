@@ -1648,6 +1648,17 @@ int vco_predicate(void *h, int t, int n) { return predicate(*(Session *)h, t, n)
 double vco_job_share(void *h, int j) { return ((Session *)h)->j_share[j]; }
 int vco_job_ready(void *h, int j) { return job_ready(*(Session *)h, j) ? 1 : 0; }
 // JobInfo.IsReady / IsPipelined (api/job_info.go:1169-1175) on the opening counters
+// util.SelectBestNodeAndScore (util/scheduler_helper.go:191-206) with the canonical tie-break, on explicit (score, node)
+// pairs; returns the node index or -1 for an empty map
+int vco_select_best(const double *scores, const int32_t *nodes, int n, double *best_score) {
+  int best = -1;
+  double bs = -std::numeric_limits<double>::infinity();
+  for (int i = 0; i < n; ++i)
+    if (scores[i] > bs || (scores[i] == bs && best >= 0 && nodes[i] < nodes[best])) { bs = scores[i]; best = i; }
+  if (best < 0) { *best_score = 0.0; return -1; }
+  *best_score = bs;
+  return nodes[best];
+}
 int vco_job_is_ready(void *h, int j) { Session &s = *(Session *)h; return s.j_ready[j] + s.j_pbe[j] >= s.j_min[j]; }
 int vco_job_is_pipelined(void *h, int j) {
   Session &s = *(Session *)h;

@@ -88,6 +88,8 @@ def lib() -> C.CDLL:
         L.vco_job_share.argtypes = [_vp, C.c_int]
         L.vco_job_ready.restype = C.c_int
         L.vco_job_ready.argtypes = [_vp, C.c_int]
+        L.vco_select_best.restype = C.c_int
+        L.vco_select_best.argtypes = [_dp, _i32p, C.c_int, _dp]
         for n in ("vco_job_is_ready", "vco_job_is_pipelined"):
             getattr(L, n).restype = C.c_int
             getattr(L, n).argtypes = [_vp, C.c_int]

@@ -267,3 +267,18 @@ def test_best_effort_and_status_counters_from_pods():
                           [BuildPodGroup("pg1", "c1", "q1", 3)], [BuildQueue("q1", 1)], SchedulerConf.default())
     assert snap.T == 1 and snap.task_keys == ["c1/pending"]
     assert snap.j_pending_besteffort[0] == 1 and snap.j_ready_num[0] == 2 and snap.j_n_tasks_total[0] == 4
+
+
+@pytest.mark.parametrize("score_map,expected_nodes,expected_score", G.SELECT_BEST_NODE)
+def test_select_best_node(score_map, expected_nodes, expected_score):
+    """util/scheduler_helper_test.go:34-90: the canonical tie-break (lowest index) is one of the reference's choices."""
+    pairs = [(sc, n) for sc, ns in score_map.items() for n in ns]
+    scores = np.array([p[0] for p in pairs] or [0.0], np.float64)
+    nodes = np.array([p[1] for p in pairs] or [0], np.int32)
+    bs = C.c_double(0.0)
+    got = pyoracle.lib().vco_select_best(scores.ctypes.data_as(pyoracle._dp), nodes.ctypes.data_as(pyoracle._i32p), len(pairs),
+                                         C.byref(bs))
+    assert got in expected_nodes
+    assert bs.value == expected_score
+    if len(expected_nodes) > 1:
+        assert got == min(expected_nodes)

@@ -127,7 +127,7 @@ def make_case(seed, big=False):
     args = {
         "binpack": {"binpack.weight": rnd.choice([1, 5, 10]), "binpack.cpu": rnd.choice([1, 5]), "binpack.memory": rnd.choice([1, 2]),
                     "binpack.resources": "nvidia.com/gpu, example.com/foo", "binpack.resources.nvidia.com/gpu": rnd.choice([0, 2, 7])},
-        "nodeorder": {"leastrequested.weight": rnd.choice([0, 1, 2]), "mostrequested.weight": rnd.choice([0, 0, 1]),
+        "nodeorder": {"leastrequested.weight": rnd.choice([0, 1, 2, -1]), "mostrequested.weight": rnd.choice([0, 0, 1, -2]),
                       "balancedresource.weight": rnd.choice([0, 1]), "nodeaffinity.weight": rnd.choice([0, 2]),
                       "tainttoleration.weight": rnd.choice([0, 3])},
         "network-topology-aware": {"weight": rnd.choice([1, 10]), "hypernode.binpack.cpu": rnd.choice([1, 5]),
