@@ -1,6 +1,6 @@
 // vcalloc.cu — libvcalloc.so: C ABI (include/vcalloc.h) + host orchestration of the CUDA kernels.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 \
-//             -Xcompiler -fPIC -shared vcalloc.cu -o libvcalloc.so
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17
+//             -Xcompiler -fPIC -shared vcalloc.cu -o libvcalloc.so          (volcano_b200/build.py)
 // There is no CPU path in this library: every entry point that computes needs a CUDA device.
 #include <cuda_runtime.h>
 
