@@ -226,6 +226,9 @@ struct CtlFast {  // shared-memory state of the fast kernel next to Ctl
   RoleDyn rd[VC_MAX_JOB_ROLES];
   double cta_best_score, g_best_score;
   int cta_best_node, cta_cnt, g_best_node, g_cnt;
+  // run-ahead results of warp 2, double-buffered by the parity of the CMD_EVAL count
+  double spec_sc[2];
+  int spec_i[2], spec_group[2], spec_cat[2];
   // CMD_EVAL mailbox between warp 0 (control) and warp 1 (evaluator)
   double ev_score;
   int ev_i, ev_ring, ev_node, ev_cnt, cur_group;
@@ -332,6 +335,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     S.cmd = 0; S.visit_id = 0; S.cur_group = -1; S.cache_group = -1; S.dirty_node = -1;
     S.ag = 0; S.pc = 0; S.since_sync = 0; S.n_full = 0; S.n_incr = 0;
     F.cta_best_node = -1; F.cta_cnt = 0; F.g_best_node = -1; F.g_cnt = 0; F.cta_best_score = F.g_best_score = 0.0;
+    F.spec_i[0] = F.spec_i[1] = -1;
   }
   __syncthreads();
 
@@ -536,15 +540,18 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   };
   // CMD_EVAL (warp 1): re-evaluate node F.ev_i for the cached group, maintain this CTA's best incrementally
   // (rescan only when the holder got worse) and publish the CTA's new best in the ring.
-  int spec_i = -1, spec_group = -2, spec_cat = 2, n_spec_hit = 0, n_rescan = 0, n_eval = 0;
-  double spec_sc = 0.0;
+  int n_spec_hit = 0, n_rescan = 0, n_eval = 0;
+  unsigned ev_count = 0;  // CMD_EVAL commands seen by this warp (warps 1 and 2 count alike)
+  long long ev_acc_pub = 0, ev_acc_spec = 0;
   auto eval_and_publish = [&](int my_group) {
+    const long long ev_t0 = PROF ? clock64() : 0;
     const int i = F.ev_i;
     const int dn = nbase + i;
     const int old_cat = fs.c_cat[i];
     double sc = 0.0;
     int cat;
-    if (spec_i == i && spec_group == my_group) { cat = spec_cat; sc = spec_sc; n_spec_hit += 1; }
+    const int rs = (int)(ev_count & 1u);  // written by warp 2 while the previous command was served
+    if (F.spec_i[rs] == i && F.spec_group[rs] == my_group) { cat = F.spec_cat[rs]; sc = F.spec_sc[rs]; n_spec_hit += 1; }
     else cat = eval_dirty(i, 0, &sc);
     __syncwarp();
     if (lane == 0) { fs.c_cat[i] = cat; fs.c_score[i] = sc; }
@@ -569,9 +576,19 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     }
     __syncwarp();
     asm volatile("bar.arrive 1, 64;" ::: "memory");  // results ready: warp 0 joins with bar.sync 1, 64
-    // run ahead: the same node after one more placement of this group
-    spec_i = -1;
-    if (cat == 0) { spec_cat = eval_dirty(i, 1, &spec_sc); spec_i = i; spec_group = my_group; }
+    if (PROF) ev_acc_pub += clock64() - ev_t0;
+  };
+  // CMD_EVAL (warp 2), concurrently with warp 1: run ahead — the same node after ONE MORE placement of this group. Under
+  // best-fit scoring the node that just won usually wins again, and then the next command finds its answer here.
+  auto run_ahead = [&](int my_group) {
+    const long long t0 = PROF ? clock64() : 0;
+    const int i = F.ev_i;
+    double sc = 0.0;
+    const int cat = eval_dirty(i, 1, &sc);
+    const int ws = (int)((ev_count + 1u) & 1u);
+    __syncwarp();
+    if (lane == 0) { F.spec_sc[ws] = sc; F.spec_cat[ws] = cat; F.spec_group[ws] = my_group; F.spec_i[ws] = i; }
+    if (PROF) ev_acc_spec += clock64() - t0;
   };
 
   if (warp != 0) {
@@ -581,19 +598,26 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       __syncthreads();  // B1: command posted
       const int cmd = S.cmd;
       if (cmd == CMD_EXIT) {
-        if (warp == 1 && lane == 0) { atomicAdd(&p.counters[8], n_spec_hit); atomicAdd(&p.counters[9], n_rescan); atomicAdd(&p.counters[10], n_eval); }
+        if (warp == 1 && lane == 0) {
+          atomicAdd(&p.counters[8], n_spec_hit); atomicAdd(&p.counters[9], n_rescan); atomicAdd(&p.counters[10], n_eval);
+          if (PROF && n_eval > 0) atomicAdd(&p.counters[11], (int)(ev_acc_pub >> 10));
+        }
+        if (PROF && warp == 2 && lane == 0) atomicAdd(&p.counters[12], (int)(ev_acc_spec >> 10));
         break;
       }
       if (cmd == CMD_SWEEP) sweep_part();
       else if (cmd == CMD_DISCARD) discard_part();
       else if (cmd == CMD_EVAL) {  // no block-wide B2: warp 1 signals warp 0 on named barrier 1
-        if (warp == 1) {
-          if (F.cur_group != my_group) { stage_ops(); my_group = F.cur_group; spec_i = -1; }
-          eval_and_publish(my_group);
+        if (warp == 1 || warp == 2) {
+          if (F.cur_group != my_group) { stage_ops(); my_group = F.cur_group; }
+          if (warp == 1) eval_and_publish(my_group);
+          else run_ahead(my_group);
+          ev_count += 1;
         }
         continue;
       }
-      if (cmd == CMD_DISCARD) spec_i = -1;  // rolled-back nodes invalidate the speculation
+      // sweeps and rollbacks change node state without a CMD_EVAL: whatever was computed ahead is void
+      if (warp == 1 && lane == 0) { F.spec_i[0] = -1; F.spec_i[1] = -1; }
       __syncthreads();  // B2: command done
     }
   } else {

@@ -1234,7 +1234,9 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->stats.prof_cycles[7] = s->h_counters[6];  // incremental steps (fast kernel)
   r->stats.prof_cycles[5] = s->h_counters[7];  // owner changes between consecutive publications
   if (getenv("VC_PROF_OWNER"))
-    fprintf(stderr, "evaluator (all CTAs): %d evaluations, %d speculation hits, %d cache rescans\n", s->h_counters[10], s->h_counters[8], s->h_counters[9]);
+    fprintf(stderr, "evaluator (all CTAs): %d evaluations, %d speculation hits, %d cache rescans; command -> publish %.0f cycles, "
+                    "speculative run-ahead %.0f cycles per evaluation (VC_PROF instance only)\n", s->h_counters[10], s->h_counters[8],
+            s->h_counters[9], 1024.0 * s->h_counters[11] / std::max(1, s->h_counters[10]), 1024.0 * s->h_counters[12] / std::max(1, s->h_counters[10]));
   if (getenv("VC_PROF_OWNER") && s->h_prof[9]) fprintf(stderr, "owner steps=%lld: post->join-start %.0f, join wait %.0f, join->next post (same owner) %.0f cycles [join->a %.0f, a->b %.0f, b->c %.0f, c->post %.0f]\n",
       s->h_prof[9], (double)s->h_prof[8] / s->h_prof[9], (double)s->h_prof[10] / s->h_prof[9], (double)s->h_prof[11] / s->h_prof[9], (double)s->h_prof[12] / s->h_prof[9], (double)s->h_prof[13] / s->h_prof[9], (double)s->h_prof[14] / s->h_prof[9], (double)s->h_prof[15] / s->h_prof[9]);
   *out = r;
