@@ -847,8 +847,14 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         if (o == cta) {
           const long long t0_ = PROF ? clock64() : 0;
           asm volatile("bar.sync 1, 64;" ::: "memory");  // join the evaluator warp
-          if (PROF) { t_join = clock64(); acc_post_to_joinstart += t0_ - t_post; acc_join_wait += t_join - t0_; acc_n += 1; }
           nb.score = F.ev_score; nb.node = F.ev_node; nb.cnt = F.ev_cnt;
+          if (PROF) {
+            // the barrier blocks lazily: read the clock only after a value that needs it has arrived
+            long long tj;
+            asm volatile("{ .reg .b32 t; mov.b32 t, %1; mov.u64 %0, %%clock64; }" : "=l"(tj) : "r"(nb.node) : "memory");
+            t_join = tj;
+            acc_post_to_joinstart += t0_ - t_post; acc_join_wait += t_join - t0_; acc_n += 1;
+          }
         } else {
           t_join = 0;
           const unsigned tag = (pub_pc + 1u) & 0x3fffffffu;
@@ -1051,7 +1057,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         if (job_ready_now()) break;  // ssn.SubJobReady, allocate.go:676-678
       }
       FPROF_MARK(4);
-      resolve();
+      // The publication of the visit's last placement is NOT awaited here: the statement bookkeeping and the next
+      // queue / job pop below do not depend on it, so they overlap the evaluator; the next task's resolve() (or the
+      // rollback just below, or the exit path) consumes it.
 
       // ---- statement outcome, allocate.go:681-693 and :330-337 ----
       __syncwarp();
@@ -1063,6 +1071,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         stmt = ctl_job_pipelined(c, S);
       }
       if (!stmt && n_ops > 0) {
+        resolve();  // the evaluator must be idle and the slot table current before nodes are rolled back
         if (lane == 0) { S.cmd = CMD_DISCARD; S.n_ops = n_ops; }
         __syncthreads();  // B1
         discard_part();
@@ -1158,6 +1167,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       __syncwarp();
       FPROF_MARK(0);
     }
+    if (pub_pending && pub_owner == cta) asm volatile("bar.sync 1, 64;" ::: "memory");  // pair the evaluator's last arrive
     if (lane == 0) {
       S.cmd = CMD_EXIT;
       S.n_dec = n_dec; S.n_vis = n_vis; S.n_fit = n_fit; S.n_steps = n_steps; S.n_full = n_full; S.n_incr = n_incr;
