@@ -894,9 +894,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         const int t = meta.x, grp = meta.y, rl = meta.z - role_base;
         cursor += 1;
         if (cursor < task_end) meta = __ldg(&p.tmeta[cursor]);  // prefetch the next task's record
-        resolve();
         if (PROF) t_a = clock64();
         if (grp != cur_group) {  // stage the group's request record (shared: workers read it in sweeps)
+          resolve();  // the evaluator works from the record being replaced
           __syncwarp();
           if (lane < R) S.trec.req[lane] = __ldg(&p.g_req[(size_t)lane * p.n_groups + grp]);
           if (lane >= 16 && lane < 16 + K) S.trec.kreq[lane - 16] = __ldg(&p.g_kreq[(size_t)(lane - 16) * p.n_groups + grp]);
@@ -936,6 +936,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         // resources only shrink inside a visit), so it is skipped; other jobs take exact full sweeps.
         const bool use_cache = c.enable_ecache && named_role && !pure;
         FPROF_MARK(1);
+        // the gates above do not need the last publication; everything below (global best, sweeps) does
+        resolve();
         if (PROF) t_b = clock64();
 
         if (pure && grp == cache_group) {
