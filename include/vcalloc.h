@@ -13,6 +13,8 @@
  *   Action.Execute for "allocate"                        vc_allocate_run
  *     (actions/allocate/allocate.go:122-140, :283-348,
  *      :558-694, :709-824; framework/interface.go:41-51)
+ *   Action.Execute for "backfill"                        vc_snapshot_set_backfill +
+ *     (actions/backfill/backfill.go:58-116, :118-199)      vc_backfill_run
  *   util.PredicateNodes + util.PrioritizeNodes for one    vc_score_matrix
  *     task over []*NodeInfo, i.e. what a PredicateFn /
  *     BatchNodeOrderFn / BestNodeFn plugin would serve
@@ -46,7 +48,7 @@
 extern "C" {
 #endif
 
-#define VC_ABI_VERSION 2
+#define VC_ABI_VERSION 3
 #define VC_MAX_DIMS 16   /* R  */
 #define VC_MAX_KDIMS 4   /* dims seen by the upstream kube-scheduler scorers (cpu, memory, nvidia.com/gpu, ...) */
 #define VC_MAX_WORDS 4   /* 64-bit words per label / taint bitset */
@@ -326,12 +328,30 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nodes, const vc_tasks *ta
    network-topology-aware plugin scores against the cluster top hypernode only (no HyperNode CRs). */
 int vc_snapshot_set_topology(vc_snapshot *s, const vc_hypernodes *topo);
 
+/* Optional, before vc_snapshot_upload: the BestEffort pending tasks of the session (TaskInfo.BestEffort,
+   api/job_info.go:188: Resreq empty but for pods:1; not scheduling-gated) — the tasks the backfill action
+   places (backfill.go:140-151). Same SoA as vc_tasks with its own index space [0, n_tasks); job / klass / role
+   index the session's job, class and role tables; uid_rank ranks within this list. They are NOT part of
+   vc_dims.n_tasks (allocate skips them, allocate.go:255-271) but stay counted in vc_jobs.pending_besteffort. */
+int vc_snapshot_set_backfill(vc_snapshot *s, int32_t n_tasks, const vc_tasks *tasks);
+
 /* Restrict the node axis of this process to [node_begin, node_end) for node-sharded
    multi-GPU runs; tasks/jobs/queues stay replicated. Default: all nodes. */
 int vc_snapshot_set_shard(vc_snapshot *s, int32_t node_begin, int32_t node_end);
 
 /* The allocate action on the uploaded snapshot: exact sequential greedy assignment. */
 int vc_allocate_run(vc_snapshot *s, vc_result **out);
+
+/* The backfill action (actions/backfill/backfill.go:58-116) on the session state vc_allocate_run left (or the
+   opening state when allocate was not run): pickUpPendingTasks order (queues by QueueOrderFn, jobs by
+   JobOrderFn, tasks by TaskOrderFn, all evaluated once at the start), then per task the plugin predicates
+   (no resource fit), util.PrioritizeNodes + arg-max over every feasible node (skipped when there is exactly
+   one), and Session.Allocate (framework/session.go:746-796) at once. In the result, decision.task indexes
+   the BACKFILL task list; there is one visit per job in pick order, outcome VC_VISIT_COMMIT when ssn.JobReady
+   held (the tasks were dispatched to the binder) else VC_VISIT_KEEP (Allocated in the session only); tasks
+   without a feasible node are listed in fit_errors. VC_EUNSUPPORTED: feasible-node sampling
+   (percentage-nodes-to-find < 100) or a registered network-topology-aware plugin together with backfill tasks. */
+int vc_backfill_run(vc_snapshot *s, vc_result **out);
 
 /* Dense task x node pass on the opening snapshot: feasibility bit (allocate.predicate,
    allocate.go:816-824), total score (util.PrioritizeNodes) of every feasible pair and

@@ -277,6 +277,7 @@ struct Session {
   vc_dims d{};
   vc_conf conf{};
   int N = 0, T = 0, J = 0, Q = 0, C = 0, R = 0, K = 0, Wl = 0, Wt = 0, NR = 0;
+  int T_alloc = 0;  // tasks [0, T_alloc) are allocate's; [T_alloc, T) the BestEffort tasks of the backfill action
   // nodes
   std::vector<double> alloc, idle, used, rel, pip, kalloc, kreq, knz;
   std::vector<int32_t> max_tasks, pod_count, zone;
@@ -1369,7 +1370,7 @@ int allocate_execute(Session &s) {
     if (s.j_flags[j] & VC_JOB_UNSUPPORTED) return VC_EUNSUPPORTED;
   std::vector<GoHeap> task_pq(s.J);
   for (int j = 0; j < s.J; ++j) task_pq[j].less = [&s](int l, int r) { return task_order_less(s, l, r); };
-  for (int t = 0; t < s.T; ++t) task_pq[s.t_job[t]].push(t);  // organizeJobWorksheet :208-281
+  for (int t = 0; t < s.T_alloc; ++t) task_pq[s.t_job[t]].push(t);  // organizeJobWorksheet :208-281
   GoHeap queues;
   queues.less = [&s](int l, int r) { return queue_order_less(s, l, r); };
   std::vector<GoHeap> jobs_by_queue(s.Q);
@@ -1425,10 +1426,132 @@ int allocate_execute(Session &s) {
 }
 
 // ---------------------------------------------------------------------------------------
+// The backfill action (actions/backfill/backfill.go)
+// ---------------------------------------------------------------------------------------
+// ssn.PredicateForAllocateAction (framework/session.go:657-674) alone: backfill passes it to PredicateNodes without
+// allocate's resource-fit wrapper (backfill.go:66,83)
+bool plugin_predicates(const Session &s, int t, int n) {
+  for (int i = 0; i < s.conf.n_plugins; ++i) {
+    const vc_plugin_option &p = s.conf.plugins[i];
+    if (!(p.enabled & VC_EN_PREDICATE)) continue;
+    if (p.plugin == VC_PLUGIN_PREDICATES && !predicates_plugin_ok(s, t, n)) return false;
+    if (p.plugin == VC_PLUGIN_TDM && !tdm_predicate_ok(s, t, n)) return false;
+  }
+  return true;
+}
+
+// pickUpPendingTasks, backfill.go:118-199: every PQ is filled first and drained afterwards, so the three order
+// functions are evaluated on the state the action starts from
+std::vector<int> backfill_pick_up_pending_tasks(Session &s, std::vector<int> *job_order) {
+  std::vector<GoHeap> task_pq(s.J);
+  for (int j = 0; j < s.J; ++j) task_pq[j].less = [&s](int l, int r) { return task_order_less(s, l, r); };
+  for (int t = s.T_alloc; t < s.T; ++t)
+    if (s.t_status[t] == kPending) task_pq[s.t_job[t]].push(t);
+  GoHeap queues;
+  queues.less = [&s](int l, int r) { return queue_order_less(s, l, r); };
+  std::vector<GoHeap> jobs_by_queue(s.Q);
+  std::vector<uint8_t> queue_seen(s.Q, 0);
+  for (int q = 0; q < s.Q; ++q) jobs_by_queue[q].less = [&s](int l, int r) { return job_order_less(s, l, r); };
+  for (int j = 0; j < s.J; ++j) {
+    if (s.j_flags[j] & VC_JOB_PENDING_PHASE) continue;  // job.IsPending() :124-126 (no enqueue-action condition here)
+    if (!job_valid(s, j)) continue;
+    int q = s.j_queue[j];
+    if (q < 0) continue;
+    if (task_pq[j].empty()) continue;
+    if (!queue_seen[q]) {
+      queue_seen[q] = 1;
+      queues.push(q);
+    }
+    jobs_by_queue[q].push(j);
+  }
+  std::vector<int> pending;
+  while (!queues.empty()) {
+    int q = queues.pop();
+    while (!jobs_by_queue[q].empty()) {
+      int j = jobs_by_queue[q].pop();
+      if (job_order) job_order->push_back(j);
+      while (!task_pq[j].empty()) pending.push_back(task_pq[j].pop());
+    }
+  }
+  return pending;
+}
+
+// Action.Execute, backfill.go:58-116
+int backfill_execute(Session &s) {
+  s.decisions.clear(); s.visits.clear(); s.fit_errors.clear();
+  if (s.T == s.T_alloc) return VC_OK;
+  for (int j = 0; j < s.J; ++j)
+    if (s.j_flags[j] & VC_JOB_UNSUPPORTED) return VC_EUNSUPPORTED;
+  if (s.has_plugin[VC_PLUGIN_NETWORK_TOPOLOGY_AWARE]) return VC_EUNSUPPORTED;
+  if (num_feasible_nodes_to_find(s.N, s.conf.percentage_nodes_to_find, s.conf.min_nodes_to_find,
+                                 s.conf.min_percentage_nodes_to_find) < s.N)
+    return VC_EUNSUPPORTED;
+  std::vector<int> pending = backfill_pick_up_pending_tasks(s, nullptr);
+  std::vector<int> feasible;
+  int cur_job = -1;
+  for (int t : pending) {
+    const int j = s.t_job[t], r = s.t_role[t];
+    if (j != cur_job) {  // one visit record per job, in pick order
+      vc_visit v;
+      v.job = j; v.first_op = (int32_t)s.decisions.size(); v.n_ops = 0; v.outcome = VC_VISIT_KEEP;
+      s.visits.push_back(v);
+      cur_job = j;
+    }
+    // ssn.PrePredicateFn: nil for pods in scope.  ph := util.NewPredicateHelper() per task (:71): the error cache is
+    // always empty, every node is evaluated
+    feasible.clear();
+    s.sweeps++;
+    {
+      std::vector<uint8_t> ok(s.N, 0);
+      s.pool->parallel_for(s.N, [&](int b, int e) {
+        for (int n = b; n < e; ++n) ok[n] = plugin_predicates(s, t, n) ? 1 : 0;
+      });
+      for (int n = 0; n < s.N; ++n)
+        if (ok[n]) feasible.push_back(n);
+    }
+    if (feasible.empty()) {  // job.NodesFitErrors[task.UID] = fitErrors :84-87
+      s.fit_errors.push_back(t - s.T_alloc);
+      continue;
+    }
+    int node = feasible[0];
+    double score = 0.0;
+    if (feasible.size() > 1) {  // :90-103 (sharding mode none: one candidate group; ssn.BestNodeFn unregistered)
+      s.task_alloc_hn = -1;
+      double sc = 0.0;
+      int best = prioritize_and_select(s, t, feasible, &sc, nullptr);
+      if (best >= 0) { node = best; score = sc; }
+    }
+    // ssn.Allocate, framework/session.go:746-796
+    s.t_status[t] = kAllocated;  // job.UpdateTaskStatus(task, Allocated): leaves PendingBestEffortTaskNum, joins ReadyTaskNum
+    s.r_pending[r] -= 1;
+    s.j_pbe[j] -= 1;
+    s.j_ready[j] += 1;
+    s.t_node[t] = node;
+    for (int d = 0; d < s.R; ++d) {  // node.AddTask default branch, api/node_info.go:467-471 (Idle may go negative)
+      at(s.idle, d, s.N, node) -= at(s.req, d, s.T, t);
+      at(s.used, d, s.N, node) += at(s.req, d, s.T, t);
+    }
+    on_allocate_event(s, t, node);
+    s.job_placed[j].push_back(node);
+    vc_decision dcs;
+    dcs.task = t - s.T_alloc; dcs.node = node; dcs.kind = VC_OP_ALLOCATE;
+    dcs.visit = (int32_t)s.visits.size() - 1; dcs.score = score;
+    s.decisions.push_back(dcs);
+    s.visits.back().n_ops += 1;
+    if (job_ready(s, j)) {  // :785-793: every Allocated task of the job is dispatched
+      s.visits.back().outcome = VC_VISIT_COMMIT;
+      for (int u = 0; u < s.T; ++u)
+        if (s.t_job[u] == j && s.t_status[u] == kAllocated) s.t_status[u] = kBinding;
+    }
+  }
+  return VC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // Dense pass on the opening snapshot (the oracle for vc_score_matrix)
 // ---------------------------------------------------------------------------------------
 void score_matrix(Session &s, uint64_t *mask_out, double *score_out, double *best_score, int32_t *best_node) {
-  const int N = s.N, T = s.T;
+  const int N = s.N, T = s.T_alloc;
   const size_t mw = ((size_t)N + 63) / 64;
   std::vector<int> idle_c, fut_c;
   std::vector<double> sc;
@@ -1477,7 +1600,7 @@ Session *load(const vc_dims *dims, const vc_nodes *nd, const vc_tasks *tk, const
   Session &s = *sp;
   s.d = *dims;
   s.conf = *conf;
-  s.N = dims->n_nodes; s.T = dims->n_tasks; s.J = dims->n_jobs; s.Q = dims->n_queues; s.C = dims->n_classes;
+  s.N = dims->n_nodes; s.T = s.T_alloc = dims->n_tasks; s.J = dims->n_jobs; s.Q = dims->n_queues; s.C = dims->n_classes;
   s.R = dims->n_dims; s.K = dims->n_kdims; s.Wl = dims->label_words; s.Wt = dims->taint_words; s.NR = dims->n_roles;
   const size_t N = s.N, T = s.T, J = s.J, Q = s.Q, C = s.C, R = s.R, K = s.K;
   copy_in(s.alloc, nd->allocatable, R * N); copy_in(s.idle, nd->idle, R * N); copy_in(s.used, nd->used, R * N);
@@ -1558,6 +1681,38 @@ void *vco_session_create(const vc_dims *dims, const vc_nodes *nd, const vc_tasks
   return load(dims, nd, tk, cl, jb, qu, conf, threads);
 }
 void vco_session_destroy(void *h) { delete (Session *)h; }
+// vc_snapshot_set_backfill for the oracle: the BestEffort tasks are appended to the session's task arrays
+int vco_session_set_backfill(void *h, int32_t n, const vc_tasks *bt) {
+  Session &s = *(Session *)h;
+  if (n <= 0 || !bt || s.T != s.T_alloc) return n == 0 ? VC_OK : VC_EINVAL;
+  const size_t T0 = s.T, B = (size_t)n, T1 = T0 + B;
+  auto widen = [&](std::vector<double> &v, size_t rows, const double *extra) {
+    std::vector<double> w(rows * T1, 0.0);
+    for (size_t r = 0; r < rows; ++r) {
+      for (size_t t = 0; t < T0; ++t) w[r * T1 + t] = v[r * T0 + t];
+      for (size_t t = 0; t < B; ++t) w[r * T1 + T0 + t] = extra ? extra[r * B + t] : 0.0;
+    }
+    v.swap(w);
+  };
+  widen(s.req, s.R, bt->resreq); widen(s.tkreq, s.K, bt->k8s_req); widen(s.tknz, s.K, bt->k8s_nonzero_req);
+  for (size_t t = 0; t < B; ++t) {
+    s.req_has.push_back(bt->req_has[t]); s.t_job.push_back(bt->job[t]); s.t_class.push_back(bt->klass[t]);
+    s.t_role.push_back(bt->role[t]); s.t_prio.push_back(bt->priority[t]);
+    s.t_podidx.push_back(bt->pod_index ? bt->pod_index[t] : -1); s.t_ts.push_back(bt->creation_ts ? bt->creation_ts[t] : 0);
+    s.t_uid.push_back(bt->uid_rank[t]);
+    s.t_status.push_back(kPending); s.t_node.push_back(-1);
+  }
+  s.T = (int)T1;
+  return VC_OK;
+}
+int vco_backfill(void *h) { return backfill_execute(*(Session *)h); }
+// pickUpPendingTasks order only (backfill_test.go:39-154): indices into the backfill task list
+int vco_backfill_pick_order(void *h, int32_t *out) {
+  Session &s = *(Session *)h;
+  std::vector<int> p = backfill_pick_up_pending_tasks(s, nullptr);
+  for (size_t i = 0; i < p.size(); ++i) out[i] = p[i] - s.T_alloc;
+  return (int)p.size();
+}
 int vco_allocate_run(void *h) { return allocate_execute(*(Session *)h); }
 size_t vco_num_decisions(void *h) { return ((Session *)h)->decisions.size(); }
 const vc_decision *vco_decisions(void *h) { return ((Session *)h)->decisions.data(); }

@@ -55,6 +55,9 @@ def lib() -> C.CDLL:
         L.vco_go_pow_uint.restype = C.c_double
         L.vco_go_pow_uint.argtypes = [C.c_double, C.c_uint]
         L.vco_allocate_run.argtypes = [_vp]
+        L.vco_session_set_backfill.argtypes = [_vp, C.c_int32, C.POINTER(abi.vc_tasks)]
+        L.vco_backfill.argtypes = [_vp]
+        L.vco_backfill_pick_order.argtypes = [_vp, _i32p]
         for n in ("vco_num_decisions", "vco_num_visits", "vco_num_fit_errors"):
             getattr(L, n).restype = C.c_size_t
             getattr(L, n).argtypes = [_vp]
@@ -113,6 +116,9 @@ class OracleSession:
         topo = snap.topology()
         if topo is not None:
             L.vco_session_set_topology(self.h, C.byref(topo))
+        bt = snap.backfill_tasks()
+        if bt is not None and L.vco_session_set_backfill(self.h, snap.B, C.byref(bt)) != 0:
+            raise RuntimeError("oracle set_backfill failed")
 
     def close(self):
         if self.h:
@@ -129,6 +135,21 @@ class OracleSession:
         rc = lib().vco_allocate_run(self.h)
         if rc != 0:
             raise RuntimeError(f"oracle allocate rc={rc}")
+        return self._results()
+
+    def backfill(self):
+        """The backfill action on the state the session is in (after allocate(), or the opening state)."""
+        rc = lib().vco_backfill(self.h)
+        if rc != 0:
+            raise RuntimeError(f"oracle backfill rc={rc}")
+        return self._results()
+
+    def backfill_pick_order(self):
+        out = np.zeros(max(self.snap.B, 1), np.int32)
+        n = lib().vco_backfill_pick_order(self.h, out.ctypes.data_as(_i32p))
+        return out[:n].copy()
+
+    def _results(self):
         L = lib()
         nd = L.vco_num_decisions(self.h)
         nv = L.vco_num_visits(self.h)

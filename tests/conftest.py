@@ -22,6 +22,8 @@ def oracle_engine():
         s = OracleSession(snap, threads=threads)
         dec, vis, fe = s.allocate()
         res = AllocateResult(dec, vis, fe)
+        if snap.B > 0 and "backfill" in snap.actions:
+            res.backfill = AllocateResult(*s.backfill())
         if snap.hn_job_soft is not None and snap.hn_job_soft.any():
             import numpy as np
             from oracle import pyoracle

@@ -15,24 +15,33 @@ def _generator():
     spec = importlib.util.spec_from_file_location("fuzz_api", os.path.join(ROOT, "tools", "fuzz_api.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    return mod.make_case
+    return mod
 
 
 @pytest.mark.parametrize("block", range(6))
 def test_random_clusters_match_oracle(block, oracle_engine):
     from volcano_b200 import engine
     engine.init(0)
-    make_case = _generator()
-    checked = 0
+    gen = _generator()
+    make_case = gen.make_case
+    checked = backfilled = 0
     for seed in range(1000 + 40 * block, 1000 + 40 * (block + 1)):
         tc, tiers, actions = make_case(seed)
         if not tiers:
             continue
+        if not gen.backfill_supported(tiers, tc.conf_kw):
+            actions = tuple(a for a in actions if a != "backfill")
         snap = tc.RegisterSession(tiers, actions=actions, **tc.conf_kw)
         if snap.T == 0 or snap.N == 0:
             continue
         ref = oracle_engine(snap)
         res = engine.gpu_engine(snap)
+        assert (res.backfill is None) == (ref.backfill is None), seed
+        if ref.backfill is not None:  # the backfill action on the state allocate left
+            assert np.array_equal(res.backfill.decisions, ref.backfill.decisions), seed
+            assert np.array_equal(res.backfill.visits, ref.backfill.visits), seed
+            assert np.array_equal(res.backfill.fit_errors, ref.backfill.fit_errors), seed
+            backfilled += len(ref.backfill.decisions)
         assert np.array_equal(res.decisions, ref.decisions), seed  # tasks, nodes, kinds, visits AND fp64 scores bit-equal
         assert np.array_equal(res.visits, ref.visits), seed
         assert np.array_equal(res.fit_errors, ref.fit_errors), seed

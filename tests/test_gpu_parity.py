@@ -119,6 +119,18 @@ def test_nta_soft_topology_allocate(gpu, oracle_engine):
     assert leaf.count("s3") == 3 and leaf.count("s4") == 3, leaf
 
 
+@pytest.mark.parametrize("case", G.NTA_SOFT_ALLOCATE_CASES, ids=[c[0][24:70] for c in G.NTA_SOFT_ALLOCATE_CASES])
+def test_allocate_with_network_topologies_soft(case, gpu, oracle_engine):
+    """allocate_test.go:359-747, soft-mode rows of TestAllocateWithNetWorkTopologies through the CUDA engine."""
+    tc = G.nta_soft_allocate_golden(case)
+    snap = tc.RegisterSession(G.nta_soft_allocate_golden_tiers())
+    tc.Run(gpu.gpu_engine)
+    assert len(tc.binds) == tc.ExpectBindsNum, tc.binds
+    if tc.ExpectBindMap:
+        assert tc.CheckBind() is None, tc.CheckBind()
+    _assert_same(tc.result, oracle_engine(snap))
+
+
 @pytest.mark.parametrize("args,expected", G.BINPACK_CASES)
 def test_binpack_goldens(args, expected, gpu):
     """binpack_test.go:100-238: exact scores through the dense pass (only binpack registered)."""
@@ -160,6 +172,102 @@ def test_allocate_vs_oracle(cfg, seed, gpu, oracle_engine):
     ref = oracle_engine(snap, threads=4)
     _assert_same(res, ref)
     assert len(res.decisions) > 0
+
+
+# ---- the backfill action (actions/backfill/backfill.go) on the state allocate left ----
+@pytest.mark.parametrize("cfg,seed", [("tiny_bf", None), ("tiny_bf", 3), ("small_bf", None), ("small_bf", 5),
+                                      ("small_soft_bf", None), ("small_soft_bf", 2)])
+def test_allocate_then_backfill_vs_oracle(cfg, seed, gpu, oracle_engine):
+    from volcano_b200.synth import make_snapshot
+    snap = make_snapshot(cfg, seed)
+    res = gpu.gpu_engine(snap)
+    ref = oracle_engine(snap, threads=4)
+    _assert_same(res, ref)
+    assert res.backfill is not None and ref.backfill is not None
+    _assert_same(res.backfill, ref.backfill)
+    assert np.array_equal(res.backfill.decisions["score"], ref.backfill.decisions["score"])  # bit-equal fp64 totals
+    assert len(res.backfill.decisions) > 0
+    # every BestEffort task is either placed or carries fit errors; pod caps hold on every node after both actions
+    assert len(res.backfill.decisions) + len(res.backfill.fit_errors) == snap.B
+    placed = np.bincount(res.backfill.decisions["node"], minlength=snap.N)
+    alloc_ops = res.decisions[res.decisions["kind"] == abi_mod().VC_OP_ALLOCATE]
+    kept = np.isin(alloc_ops["visit"], np.nonzero(res.visits["outcome"] != abi_mod().VC_VISIT_DISCARD)[0])
+    placed += np.bincount(alloc_ops["node"][kept], minlength=snap.N)
+    pip = res.decisions[res.decisions["kind"] == abi_mod().VC_OP_PIPELINE]
+    placed += np.bincount(pip["node"], minlength=snap.N)  # the predicates plugin counts pipelined pods too
+    assert np.all(snap.n_pod_count + placed <= snap.n_max_tasks)
+
+
+def abi_mod():
+    from volcano_b200 import abi
+    return abi
+
+
+def test_backfill_alone_on_the_opening_state(gpu):
+    """A cycle configured with backfill only: vc_backfill_run without vc_allocate_run starts from the opening node state."""
+    from oracle.pyoracle import OracleSession
+    from volcano_b200.synth import make_snapshot
+    snap = make_snapshot("small_bf", 11)
+    e = gpu.Engine(snap)
+    e.upload()
+    res = e.backfill()
+    with pytest.raises(gpu.VcError):  # once per session state
+        e.backfill()
+    e.close()
+    o = OracleSession(snap, threads=4)
+    dec, vis, fe = o.backfill()
+    o.close()
+    assert np.array_equal(res.decisions, dec) and np.array_equal(res.visits, vis) and np.array_equal(res.fit_errors, fe)
+
+
+def test_backfill_pick_up_pending_tasks_golden(gpu):
+    """backfill_test.go:39-154 TestPickUpPendingTasks through the C ABI: the session has no node, so every BestEffort task
+    records fit errors - in pick order."""
+    tc = G.backfill_pick_case()
+    snap = tc.RegisterSession(G.backfill_pick_tiers(), actions=("allocate", "backfill"))
+    res = gpu.gpu_engine(snap)
+    assert res.backfill is not None and len(res.backfill.decisions) == 0
+    assert [snap.backfill_task_keys[t] for t in res.backfill.fit_errors] == G.BACKFILL_PICK_EXPECTED
+    assert [snap.job_names[j] for j in res.backfill.visits["job"]] == ["default/pg2", "default/pg1"]
+
+
+def test_backfill_action_interface(gpu, oracle_engine):
+    """test.Run([]framework.Action{allocate.New(), backfill.New()}) with the reference's default plugin set: BestEffort pods
+    are bound next to the regular ones; unsupported configurations fail loudly."""
+    from volcano_b200 import action, backfill
+    from volcano_b200.api import BuildNode, BuildPod, BuildPodGroup, BuildQueue, BuildResourceList
+    from volcano_b200.snapshot import PluginOption, SchedulerConf
+    from volcano_b200.uthelper import TestCommonStruct
+    nodes = [BuildNode(f"n{i}", BuildResourceList("4", "8Gi", ("pods", "3"))) for i in range(3)]
+    pods = [BuildPod("c1", f"w{i}", "", "Pending", BuildResourceList("1", "1Gi"), "pg1") for i in range(3)]
+    pods += [BuildPod("c1", f"be{i}", "", "Pending", {}, "pg1") for i in range(4)]
+    pods += [BuildPod("c1", f"xbe{i}", "", "Pending", {}, "pg2") for i in range(4)]
+    pods += [BuildPod("c1", "xw0", "", "Pending", BuildResourceList("64", "1Gi"), "pg2")]  # never fits: pg2 stays unready
+    tc = TestCommonStruct(Name="allocate+backfill", Nodes=nodes, Pods=pods, Queues=[BuildQueue("q1", 1, None)],
+                          PodGroups=[BuildPodGroup("pg1", "c1", "q1", 2), BuildPodGroup("pg2", "c1", "q1", 5)])
+    conf = SchedulerConf.default()
+    snap = tc.RegisterSession(conf.tiers, actions=("allocate", "backfill"))
+    assert snap.B == 8
+    tc.Run([action.New(), backfill.New()])
+    ref = oracle_engine(snap)
+    _assert_same(tc.result, ref)
+    _assert_same(tc.result.backfill, ref.backfill)
+    # 9 pod slots, 3 taken by allocate. gang's JobOrderFn visits the unready pg2 (0 + 4 < 5) first: its four BestEffort
+    # pods take four slots but stay Allocated in the session (ssn.JobReady false, no dispatch); pg1 is ready: two of its
+    # BestEffort pods get the last two slots and are bound, the other two carry fit errors (pod-count predicate)
+    bf = tc.result.backfill
+    assert [snap.job_names[j] for j in bf.visits["job"]] == ["c1/pg2", "c1/pg1"]
+    assert list(bf.visits["outcome"]) == [abi_mod().VC_VISIT_KEEP, abi_mod().VC_VISIT_COMMIT]
+    assert len(bf.decisions) == 6 and [snap.backfill_task_keys[t] for t in bf.fit_errors] == ["c1/be2", "c1/be3"]
+    assert sorted(tc.binds) == ["c1/be0", "c1/be1", "c1/w0", "c1/w1", "c1/w2"]
+    assert bf.decisions["score"][-1] == 0.0  # one candidate left: taken without scoring (backfill.go:89-90)
+    # sampling and the topology plugin are outside vc_backfill_run
+    tc2 = TestCommonStruct(Name="unsupported", Nodes=nodes, Pods=pods, Queues=[BuildQueue("q1", 1, None)],
+                           PodGroups=[BuildPodGroup("pg1", "c1", "q1", 2), BuildPodGroup("pg2", "c1", "q1", 5)])
+    tc2.RegisterSession(conf.tiers, actions=("allocate", "backfill"), percentage_nodes_to_find=50, min_nodes_to_find=1)
+    with pytest.raises(gpu.VcError) as ei:
+        tc2.Run([action.New(), backfill.New()])
+    assert ei.value.code == abi_mod().VC_EUNSUPPORTED
 
 
 @pytest.mark.parametrize("cfg,seed", [("tiny", 1), ("small", 7), ("small_roles", None)])

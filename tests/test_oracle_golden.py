@@ -224,6 +224,29 @@ def test_nta_soft_topology_allocate(oracle_engine):
     assert mine.count("s3") == 3 and mine.count("s4") == 3, mine  # s3 has room for 3 more, then the sibling leaf
 
 
+@pytest.mark.parametrize("case", G.NTA_SOFT_ALLOCATE_CASES, ids=[c[0][24:70] for c in G.NTA_SOFT_ALLOCATE_CASES])
+def test_allocate_with_network_topologies_soft(case, oracle_engine):
+    """allocate_test.go:359-747: the soft-mode rows of TestAllocateWithNetWorkTopologies (bind count; bind map where the
+    reference pins it).  Rescheduled rows also keep the new pod next to the job's allocated hypernode when it has room."""
+    tc = G.nta_soft_allocate_golden(case)
+    tc.RegisterSession(G.nta_soft_allocate_golden_tiers())
+    tc.Run(oracle_engine)
+    assert len(tc.binds) == tc.ExpectBindsNum, tc.binds
+    if tc.ExpectBindMap:
+        assert tc.CheckBind() is None, tc.CheckBind()
+
+
+def test_backfill_pick_up_pending_tasks():
+    """backfill_test.go:39-154 TestPickUpPendingTasks."""
+    tc = G.backfill_pick_case()
+    snap = tc.RegisterSession(G.backfill_pick_tiers(), actions=("allocate", "backfill"))
+    assert snap.B == 8 and snap.T == 8
+    o = OracleSession(snap)
+    order = o.backfill_pick_order()
+    o.close()
+    assert [snap.backfill_task_keys[t] for t in order] == G.BACKFILL_PICK_EXPECTED
+
+
 @pytest.mark.parametrize("name,alloc,pods,idle,used", G.NODE_INFO_ADD_POD, ids=[c[0][:30] for c in G.NODE_INFO_ADD_POD])
 def test_node_accounting_at_session_open(name, alloc, pods, idle, used):
     """api/node_info_test.go:36-131: Idle / Used of a node given the pods the cache holds on it (incl. an Unknown-phase

@@ -23,6 +23,7 @@ POOLS = ["p0", "p1"]
 
 def make_case(seed, big=False):
     rnd = random.Random(seed)
+    be_p = rnd.choice([0.05, 0.05, 0.3])  # share of BestEffort pods (the backfill action's tasks)
     n_nodes = rnd.randint(3, 40) if not big else rnd.randint(40, 400)
     nodes = []
     leaves = rnd.randint(2, 5) if not big else rnd.randint(3, 12)
@@ -116,12 +117,15 @@ def make_case(seed, big=False):
                 p.deleting = True  # Releasing on its node
             if rnd.random() < 0.2:
                 p.priority = rnd.randint(0, 3)
-            if rnd.random() < 0.05:
+            if rnd.random() < be_p:
                 p.requests = {}  # BestEffort: stays out of the allocate action, counts as pending best-effort
             pods.append(p)
     # plugin set
     names = ["priority", "gang", "drf", "predicates", "proportion", "nodeorder", "binpack", "tdm", "network-topology-aware"]
     chosen = [n for n in names if rnd.random() < 0.75]
+    want_backfill = rnd.random() < 0.7
+    if want_backfill and "network-topology-aware" in chosen and rnd.random() < 0.75:
+        chosen.remove("network-topology-aware")  # vc_backfill_run does not take the plugin (documented limit)
     if "gang" not in chosen and rnd.random() < 0.7:
         chosen.append("gang")
     args = {
@@ -142,11 +146,20 @@ def make_case(seed, big=False):
     tc = TestCommonStruct(Name=f"fuzz{seed}", Nodes=nodes, Pods=pods, PodGroups=pgs, Queues=queues, HyperNodes=hypernodes,
                           TdmZoneActive={"rz1": rnd.random() < 0.7, "rz2": rnd.random() < 0.3})
     actions = ("enqueue", "allocate") if rnd.random() < 0.5 else ("allocate",)
+    if want_backfill:
+        actions += ("backfill",)
     tc.conf_kw = {}
-    if rnd.random() < 0.3:  # feasible-node sampling with a rotating start index
+    if rnd.random() < (0.1 if want_backfill else 0.3):  # feasible-node sampling with a rotating start index
         tc.conf_kw = dict(percentage_nodes_to_find=rnd.choice([0, 10, 30, 60]), min_nodes_to_find=rnd.choice([1, 3, 10, 50]),
                           min_percentage_nodes_to_find=rnd.choice([5, 20]), last_processed_node_index=rnd.randint(0, 500))
     return tc, tiers, actions
+
+
+def backfill_supported(tiers, conf_kw):
+    """vc_backfill_run's documented limits: no network-topology-aware plugin, no feasible-node sampling."""
+    if any(po.name == "network-topology-aware" for t in tiers for po in t):
+        return False
+    return conf_kw.get("percentage_nodes_to_find", 100) >= 100
 
 
 def main():
@@ -154,7 +167,7 @@ def main():
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     big = len(sys.argv) > 3 and sys.argv[3] == "big"
     engine.init(0)
-    bad = unsupported = dense_bad = 0
+    bad = unsupported = dense_bad = bf_bad = bf_runs = bf_placed = 0
     for seed in range(first, first + n_cases):
         tc, tiers, actions = make_case(seed, big)
         if not tiers:
@@ -164,11 +177,14 @@ def main():
             continue
         o = OracleSession(snap, threads=1)
         dec, vis, fe = o.allocate()
+        eng = engine.Engine(snap)
         try:
-            r = engine.gpu_engine(snap)
+            eng.upload()
+            r = eng.allocate()
         except engine.VcError as e:
             unsupported += 1
             o.close()
+            eng.close()
             print(f"seed {seed}: {e}")
             continue
         ok = (np.array_equal(dec, r.decisions) and np.array_equal(vis, r.visits) and np.array_equal(fe, r.fit_errors))
@@ -183,6 +199,23 @@ def main():
             k = next((i for i in range(min(len(dec), len(r.decisions))) if dec[i] != r.decisions[i]), -1)
             print(f"MISMATCH seed={seed}: oracle {len(dec)} dec / {len(vis)} visits, gpu {len(r.decisions)} / {len(r.visits)}; first diff {k}"
                   + (f" oracle={dec[k]} gpu={r.decisions[k]}" if k >= 0 else ""))
+        # the backfill action on the state allocate left
+        if "backfill" in actions and snap.B > 0:
+            try:
+                rb = eng.backfill()
+            except engine.VcError as e:
+                rb = None
+                if e.code != -4:
+                    raise
+            if rb is not None:
+                bdec, bvis, bfe = o.backfill()
+                bf_runs += 1
+                bf_placed += len(bdec)
+                if not (np.array_equal(bdec, rb.decisions) and np.array_equal(bvis, rb.visits) and np.array_equal(bfe, rb.fit_errors)):
+                    bf_bad += 1
+                    print(f"BACKFILL MISMATCH seed={seed}: oracle {len(bdec)} dec / {len(bvis)} visits / {len(bfe)} fit errors, "
+                          f"gpu {len(rb.decisions)} / {len(rb.visits)} / {len(rb.fit_errors)}")
+        eng.close()
         # dense pass on the opening snapshot
         o2 = OracleSession(snap)
         om, osc, obs, obn = o2.score_matrix()
@@ -198,7 +231,8 @@ def main():
                 print(f"DENSE MISMATCH seed={seed}")
         except engine.VcError:
             pass
-    print(f"{n_cases} cases: {bad} allocate mismatches, {dense_bad} dense mismatches, {unsupported} unsupported")
+    print(f"{n_cases} cases: {bad} allocate mismatches, {dense_bad} dense mismatches, {unsupported} unsupported; "
+          f"backfill: {bf_runs} runs, {bf_placed} placements, {bf_bad} mismatches")
 
 
 if __name__ == "__main__":

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-VC_ABI_VERSION = 2
+VC_ABI_VERSION = 3
 VC_MAX_DIMS = 16
 VC_MAX_KDIMS = 4
 VC_MAX_WORDS = 4
@@ -210,8 +210,10 @@ SYMBOLS = {
     "vc_snapshot_upload": (C.c_int, [_vp, C.POINTER(vc_nodes), C.POINTER(vc_tasks), C.POINTER(vc_classes),
                                      C.POINTER(vc_jobs), C.POINTER(vc_queues), C.POINTER(vc_conf)]),
     "vc_snapshot_set_topology": (C.c_int, [_vp, C.POINTER(vc_hypernodes)]),
+    "vc_snapshot_set_backfill": (C.c_int, [_vp, C.c_int32, C.POINTER(vc_tasks)]),
     "vc_snapshot_set_shard": (C.c_int, [_vp, C.c_int32, C.c_int32]),
     "vc_allocate_run": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "vc_backfill_run": (C.c_int, [_vp, C.POINTER(_vp)]),
     "vc_score_matrix": (C.c_int, [_vp, _u64p, _dp, _dp, _i32p]),
     "vc_score_matrix_device": (C.c_int, [_vp, C.c_int, _dp, _i64p]),
     "vc_dense_begin": (C.c_int, [_vp]),

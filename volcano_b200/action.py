@@ -27,6 +27,18 @@ class Session:
     binds: Dict[str, str] = field(default_factory=dict)            # task key -> node (FakeBinder channel)
     pipelined: Dict[str, List[str]] = field(default_factory=dict)  # job -> nodes of pipelined tasks
     fit_errors: List[str] = field(default_factory=list)            # tasks with job.NodesFitErrors entries
+    _engine: Optional[engine.Engine] = None                        # device-side session shared by the actions of a cycle
+
+    def device_session(self, device: int = 0) -> engine.Engine:
+        if self._engine is None:
+            self._engine = engine.Engine(self.snapshot, device)
+            self._engine.upload()
+        return self._engine
+
+    def close(self) -> None:
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
 
     def replay(self, result: AllocateResult) -> None:
         """Statement.Allocate / Pipeline + Commit for every kept visit (framework/statement.go:146-412)."""
@@ -41,6 +53,19 @@ class Session:
                     self.pipelined.setdefault(snap.job_names[v["job"]], []).append(node)
         self.fit_errors = [snap.task_keys[t] for t in result.fit_errors]
 
+    def replay_backfill(self, result: AllocateResult) -> None:
+        """Session.Allocate for every backfilled task (framework/session.go:746-796): bound when ssn.JobReady held."""
+        snap = self.snapshot
+        if self.result is None:
+            self.result = AllocateResult(result.decisions[:0], result.visits[:0], result.fit_errors[:0])
+        self.result.backfill = result
+        for v in result.visits:
+            if v["outcome"] != abi.VC_VISIT_COMMIT:
+                continue
+            for op in result.decisions[v["first_op"]: v["first_op"] + v["n_ops"]]:
+                self.binds[snap.backfill_task_keys[op["task"]]] = snap.node_names[op["node"]]
+        self.fit_errors += [snap.backfill_task_keys[t] for t in result.fit_errors]
+
 
 class Action:
     def __init__(self, device: int = 0):
@@ -53,7 +78,7 @@ class Action:
         engine.init(self.device)
 
     def Execute(self, ssn: Session) -> None:
-        ssn.replay(engine.gpu_engine(ssn.snapshot, self.device))
+        ssn.replay(ssn.device_session(self.device).allocate())
 
     def UnInitialize(self) -> None:
         pass

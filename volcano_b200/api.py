@@ -256,6 +256,21 @@ def BuildPod(namespace, name, node_name, phase, req, group_name, labels=None, se
                group_name=group_name, labels=dict(labels or {}), node_selector=dict(selector or {}))
 
 
+def BuildPodWithPriority(namespace, name, node_name, phase, req, group_name, labels=None, selector=None,
+                         priority: Optional[int] = None) -> Pod:
+    """util/test_utils.go:128-158."""
+    p = BuildPod(namespace, name, node_name, phase, req, group_name, labels, selector)
+    p.priority = priority
+    return p
+
+
+def BuildPodGroupWithPrio(name, ns, queue, min_member, task_min_member, phase, priority: int) -> "PodGroup":
+    """util/test_utils.go:368-382; `priority` is the resolved PriorityClass value (cache/cache.go:1526-1532)."""
+    pg = BuildPodGroup(name, ns, queue, min_member, task_min_member, phase)
+    pg.priority = priority
+    return pg
+
+
 def BuildPodGroup(name, ns, queue, min_member, task_min_member=None, phase="Inqueue") -> PodGroup:
     return PodGroup(name=name, namespace=ns, queue=queue, min_member=min_member,
                     min_task_member=dict(task_min_member) if task_min_member else None, phase=phase)

@@ -1,0 +1,189 @@
+// vc_backfill.cuh — the backfill action (actions/backfill/backfill.go:58-116) as one persistent cooperative launch.
+//
+// The host has already fixed the visiting order (pickUpPendingTasks :118-199 evaluates its three order functions once,
+// before the first placement), so the device loop is flat: for every BestEffort task in pick order
+//   * every thread evaluates the plugin predicates of its node (ssn.PredicateForAllocateAction without allocate's
+//     resource-fit wrapper, :66,83) and, when feasible, the node's util.PrioritizeNodes total;
+//   * one mailbox all-gather (the commit kernel's `exchange`) gives every CTA the same arg-max
+//     (util.SelectBestNodeAndScore, canonical tie-break) and the feasible-node count (one candidate: no scoring, :89-90);
+//   * the owner thread applies Session.Allocate (framework/session.go:746-796): node.AddTask (Idle may go negative,
+//     api/node_info.go:467-471) and the predicates plugin's AllocateFunc (pod count, k8s requested sums).
+// The node axis is partitioned exactly as in k_commit (same CTA count, same shared-memory node slices, read from and
+// written back to the working copies the allocate action left in HBM). A per-node verdict cache keyed by the task's
+// (class, request) group makes a sweep re-evaluate only the node the previous placement touched.
+// Bound: latency (one L2 mailbox round trip per task), like k_commit.
+#pragma once
+#include "vc_commit.cuh"
+
+struct BackfillParams {
+  int n;                  // tasks in pick order
+  int B;                  // stride of the task arrays
+  const int32_t *order;   // [n] index into the backfill task list
+  const double *req;      // [R][B] Resreq (pods:1 only, but kept general)
+  const double *kreq;     // [K][B]
+  const double *knz;      // [2][B]
+  const uint32_t *has;    // [B]
+  const int32_t *klass;   // [B]
+  const int32_t *group;   // [B] (class, request) group of the task
+  int32_t *out_node;      // [n] chosen node per pick position, -1 = no feasible node
+  double *out_score;      // [n] its util.PrioritizeNodes total (0.0 when it was the only candidate)
+};
+
+struct BfCtl {
+  TaskRec trec;
+  int group;
+  int cnt, best_node, max_soft;
+  double best_score;
+  unsigned seq;
+  double w_score[32];
+  int w_node[32], w_cnt[32], w_soft[32];
+};
+
+// SOFT: nodeorder's TaintToleration batch score is live (normalised over the candidate set: two passes per task)
+template <bool SOFT>
+__global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams b) {
+  const DevConf &c = p.c;
+  const int R = p.d.R, K = p.d.K, N = p.d.N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int cta = blockIdx.x;
+  const int nbase = p.d.node_begin + cta * p.npc;
+  const int nmine = max(0, min(p.npc, p.d.node_end - nbase));
+  const int cap = p.npc;
+
+  unsigned char *sp = k2_smem;
+  BfCtl &S = *reinterpret_cast<BfCtl *>(sp);
+  sp += (sizeof(BfCtl) + 15) & ~(size_t)15;
+  SmemNodes sn;
+  sn.cap = cap;
+  auto take = [&](int rows) { double *q = reinterpret_cast<double *>(sp); sp += (size_t)rows * cap * sizeof(double); return q; };
+  sn.alloc = take(R); sn.idle = take(R); sn.used = take(R);
+  sn.rel = nullptr; sn.pip = nullptr;  // FutureIdle plays no part: backfill has no resource-fit gradient
+  sn.kalloc = take(K); sn.kreq = take(K); sn.knz = take(2);
+  sn.nerr = nullptr;
+  sn.max_tasks = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
+  sn.pod_count = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;
+  sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 7) & ~(uintptr_t)7);
+  double *c_order = reinterpret_cast<double *>(sp); sp += (size_t)cap * 8;   // verdict cache: NodeOrderFn sum,
+  int32_t *c_group = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;  // the group it was computed for,
+  uint8_t *c_flag = reinterpret_cast<uint8_t *>(sp);                          // bit0 feasible, bit1 has order score
+
+  for (int i = tid; i < nmine; i += blockDim.x) {
+    const int n = nbase + i;
+    for (int d = 0; d < R; ++d) {
+      sn.alloc[d * cap + i] = p.alloc[(size_t)d * N + n];
+      sn.idle[d * cap + i] = p.idle[(size_t)d * N + n];
+      sn.used[d * cap + i] = p.used[(size_t)d * N + n];
+    }
+    for (int k = 0; k < K; ++k) {
+      sn.kalloc[k * cap + i] = p.kalloc[(size_t)k * N + n];
+      sn.kreq[k * cap + i] = p.kreq[(size_t)k * N + n];
+    }
+    for (int k = 0; k < 2; ++k) sn.knz[k * cap + i] = p.knz[(size_t)k * N + n];
+    sn.max_tasks[i] = p.max_tasks[n];
+    sn.pod_count[i] = p.pod_count[n];
+  }
+  for (int i = tid; i < cap; i += blockDim.x) c_group[i] = -1;
+  if (tid == 0) S.seq = 0;
+  __syncthreads();
+
+  const bool two_pass = SOFT && c.soft_active;
+  for (int pos = 0; pos < b.n; ++pos) {
+    const int t = b.order[pos];
+    __syncthreads();
+    if (tid < R) S.trec.req[tid] = b.req[(size_t)tid * b.B + t];
+    if (tid >= 32 && tid < 32 + K) S.trec.kreq[tid - 32] = b.kreq[(size_t)(tid - 32) * b.B + t];
+    if (tid >= 64 && tid < 66) S.trec.knz[tid - 64] = b.knz[(size_t)(tid - 64) * b.B + t];
+    if (tid == 96 % blockDim.x) {
+      S.trec.has = b.has[t];
+      S.trec.klass = b.klass[t];
+      S.group = b.group[t];
+    }
+    __syncthreads();
+    const TaskRec &trec = S.trec;
+    const int group = S.group;
+    const uint32_t *cs_row = p.cstat + (size_t)trec.klass * N + nbase;
+    int g_soft = 0;
+    for (int pass = 0; pass < (two_pass ? 2 : 1); ++pass) {
+      Local mine;
+      local_init(mine);
+      for (int i = tid; i < nmine; i += blockDim.x) {
+        const bool fresh = c_group[i] != group;
+        const uint32_t cs = (two_pass || fresh) ? cs_row[i] : 0u;
+        bool ok, has_order;
+        double order;
+        if (fresh) {
+          SmemNodeView nv{sn, i};
+          ok = (cs & CS_STATIC_OK) != 0;
+          if (c.pred_predicates && sn.max_tasks[i] <= sn.pod_count[i]) ok = false;  // predicates.go:662-671
+          has_order = false;
+          order = 0.0;
+          if (ok) has_order = node_order(c, R, K, trec, nv, cs, &order);
+          c_group[i] = group; c_flag[i] = (uint8_t)((ok ? 1 : 0) | (has_order ? 2 : 0)); c_order[i] = order;
+        } else {
+          ok = (c_flag[i] & 1) != 0; has_order = (c_flag[i] & 2) != 0; order = c_order[i];
+        }
+        if (!ok) continue;
+        const int soft = SOFT ? (int)((cs >> CS_SOFT_SHIFT) & 0xff) : 0;
+        mine.cnt[0] += 1;
+        mine.soft[0] = max(mine.soft[0], soft);
+        if (two_pass && pass == 0) continue;
+        const double sc = total_score(c, has_order, order, soft, g_soft);
+        const int n = nbase + i;
+        if (mine.node[0] < 0 || better(sc, n, mine.score[0], mine.node[0])) { mine.score[0] = sc; mine.node[0] = n; }
+      }
+      local_warp_reduce<false>(mine);
+      if (lane == 0) { S.w_score[warp] = mine.score[0]; S.w_node[warp] = mine.node[0]; S.w_cnt[warp] = mine.cnt[0]; S.w_soft[warp] = mine.soft[0]; }
+      __syncthreads();
+      if (warp == 0) {
+        Local l;
+        local_init(l);
+        if (lane < nwarps) { l.score[0] = S.w_score[lane]; l.node[0] = S.w_node[lane]; l.cnt[0] = S.w_cnt[lane]; l.soft[0] = S.w_soft[lane]; }
+        local_warp_reduce<false>(l);
+        const unsigned seq = S.seq + 1;
+        __syncwarp();  // every lane has read S.seq before lane 0 advances it
+        const Local g = exchange<SOFT>(p, l, seq);
+        if (lane == 0) {
+          S.seq = seq;
+          S.cnt = g.cnt[0]; S.best_node = g.node[0]; S.best_score = g.score[0]; S.max_soft = g.soft[0];
+        }
+      }
+      __syncthreads();
+      g_soft = S.max_soft;
+      if (S.cnt == 0) break;
+    }
+    const int cnt = S.cnt, best = S.best_node;
+    const double score = cnt == 1 ? 0.0 : S.best_score;
+    if (cta == 0 && tid == 0) {
+      b.out_node[pos] = cnt == 0 ? -1 : best;
+      b.out_score[pos] = cnt == 0 ? 0.0 : score;
+    }
+    if (cnt == 0) continue;  // job.NodesFitErrors[task.UID] = fitErrors, :84-87
+    if (best >= nbase && best < nbase + nmine) {
+      const int i = best - nbase;
+      if ((i % blockDim.x) == tid) {
+        c_group[i] = -1;
+        for (int d = 0; d < R; ++d) {
+          sn.idle[d * cap + i] -= trec.req[d];
+          sn.used[d * cap + i] += trec.req[d];
+        }
+        if (c.has_predicates) {  // predicates AllocateFunc, predicates.go:212-256
+          sn.pod_count[i] += 1;
+          for (int k = 0; k < K; ++k) sn.kreq[k * cap + i] += trec.kreq[k];
+          for (int k = 0; k < 2; ++k) sn.knz[k * cap + i] += trec.knz[k];
+        }
+      }
+    }
+  }
+
+  __syncthreads();
+  for (int i = tid; i < nmine; i += blockDim.x) {
+    const int n = nbase + i;
+    for (int d = 0; d < R; ++d) {
+      p.idle[(size_t)d * N + n] = sn.idle[d * cap + i];
+      p.used[(size_t)d * N + n] = sn.used[d * cap + i];
+    }
+    for (int k = 0; k < K; ++k) p.kreq[(size_t)k * N + n] = sn.kreq[k * cap + i];
+    for (int k = 0; k < 2; ++k) p.knz[(size_t)k * N + n] = sn.knz[k * cap + i];
+    p.pod_count[n] = sn.pod_count[i];
+  }
+}

@@ -15,6 +15,7 @@
 
 #include "../../include/vcalloc.h"
 #include "vc_commit.cuh"
+#include "vc_backfill.cuh"
 #include "vc_commit_fast.cuh"
 #include "vc_device.cuh"
 #include "vc_host.hpp"
@@ -187,6 +188,24 @@ struct vc_snapshot {
   std::vector<double> h_req, h_kreq, h_knz;
   std::vector<uint32_t> h_has;
   std::vector<int32_t> h_class, h_task_job;
+  // ---- backfill action (vc_snapshot_set_backfill / vc_backfill_run) ----
+  struct BackfillTasks {  // host copy of the BestEffort task list
+    int n = 0;
+    std::vector<double> req, kreq, knz;
+    std::vector<uint32_t> has, uid;
+    std::vector<int32_t> job, klass, role, prio;
+    std::vector<int64_t> podidx, ts;
+  } bf;
+  struct BackfillKeep {  // session-open state pickUpPendingTasks needs, kept at upload when bf.n > 0
+    std::vector<int32_t> j_queue, j_min, j_prio, j_ready0, j_pbe, j_taskmintotal, j_roleoff, r_min, r_occ0, q_prio, t_role;
+    std::vector<uint32_t> j_flags, j_rank, r_flags, q_rank;
+    std::vector<uint8_t> j_valid;
+    std::vector<double> j_alloc0;  // [R][J]
+  } bk;
+  std::vector<vc_decision> last_dec;  // operations of the last vc_allocate_run (kept visits only)
+  bool alloc_ran = false, bf_ran = false;
+  void *d_bf = nullptr;   // device slab of the backfill inputs / outputs
+  size_t d_bf_bytes = 0;
 };
 
 namespace {
@@ -369,7 +388,7 @@ void vc_snapshot_destroy(vc_snapshot *s) {
   if (!s) return;
   free_dense(s);
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
-                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_prof, s->d_wait, s->d_decisions, s->d_visits, s->d_fit, s->d_counters};
+                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_prof, s->d_wait, s->d_decisions, s->d_visits, s->d_fit, s->d_counters, s->d_bf};
   for (void *p : dptrs) if (p) cudaFree(p);
   void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters};
   for (void *p : hptrs) if (p) cudaFreeHost(p);
@@ -1002,6 +1021,31 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   s->h_class.assign(tk->klass, tk->klass + T);
   s->h_task_job.assign(tk->job, tk->job + T);
   tick("host copies for the dense pass");
+  s->alloc_ran = false; s->bf_ran = false;
+  s->last_dec.clear();
+  if (s->bf.n > 0) {  // what pickUpPendingTasks (backfill.go:118-199) orders by, as of session open
+    vc_snapshot::BackfillKeep &k = s->bk;
+    k.j_queue.assign(jb->queue, jb->queue + J); k.j_min.assign(jb->min_available, jb->min_available + J);
+    k.j_prio.assign(jb->priority, jb->priority + J); k.j_ready0.assign(jb->ready_num, jb->ready_num + J);
+    k.j_pbe.assign(jb->pending_besteffort, jb->pending_besteffort + J);
+    k.j_taskmintotal.assign(jb->task_min_total, jb->task_min_total + J);
+    k.j_roleoff.assign(jb->role_off, jb->role_off + J + 1);
+    k.r_min.assign(jb->role_min, jb->role_min + NR); k.r_occ0.assign(jb->role_occupied, jb->role_occupied + NR);
+    k.r_flags.assign(jb->role_flags, jb->role_flags + NR);
+    k.q_prio.assign(qu->priority, qu->priority + Q);
+    k.t_role.assign(tk->role, tk->role + T);
+    k.j_flags.assign(jb->flags, jb->flags + J);
+    k.j_rank = j_rank; k.q_rank = q_rank;
+    k.j_valid.resize(J);
+    for (size_t j = 0; j < J; ++j) k.j_valid[j] = vch::job_valid(*conf, *jb, (int)j) ? 1 : 0;
+    k.j_alloc0.assign(jb->allocated, jb->allocated + R * J);
+    for (int t = 0; t < s->bf.n; ++t) {
+      if (s->bf.job[t] < 0 || (size_t)s->bf.job[t] >= J) return fail(VC_EINVAL, "backfill task %d: bad job index", t);
+      if (s->bf.klass[t] < 0 || (size_t)s->bf.klass[t] >= C) return fail(VC_EINVAL, "backfill task %d: bad class index", t);
+      const int j = s->bf.job[t], r = s->bf.role[t];
+      if (r < jb->role_off[j] || r >= jb->role_off[j + 1]) return fail(VC_EINVAL, "backfill task %d: role row outside its job", t);
+    }
+  }
   s->upload_ms = now_ms() - t0;
   return VC_OK;
 }
@@ -1186,6 +1230,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->decisions.assign(s->h_decisions, s->h_decisions + n_dec);
   r->visits.assign(s->h_visits, s->h_visits + n_vis);
   r->fit_errors.assign(s->h_fit, s->h_fit + n_fit);
+  s->alloc_ran = true; s->bf_ran = false;
+  if (s->bf.n > 0) s->last_dec = r->decisions;  // discarded visits carry no operations
   if (s->topo_any) {
     r->job_alloc.resize(J);
     CUDA_TRY(cudaMemcpy(r->job_alloc.data(), s->d_job_alloc, J * 4, cudaMemcpyDeviceToHost));
@@ -1255,6 +1301,272 @@ const int32_t *vc_result_job_allocated_hypernodes(const vc_result *r, size_t *n_
   return (r && !r->job_alloc.empty()) ? r->job_alloc.data() : nullptr;
 }
 void vc_result_free(vc_result *r) { delete r; }
+
+// ---------------------------------------------------------------------------------------
+// backfill (actions/backfill/backfill.go)
+// ---------------------------------------------------------------------------------------
+int vc_snapshot_set_backfill(vc_snapshot *s, int32_t n_tasks, const vc_tasks *bt) {
+  if (!s) return fail(VC_EINVAL, "null snapshot");
+  if (n_tasks < 0 || (n_tasks > 0 && !bt)) return fail(VC_EINVAL, "backfill task list: negative size / null pointer");
+  s->uploaded = false;  // the list is validated against the job / class tables by the next upload
+  vc_snapshot::BackfillTasks &b = s->bf;
+  const size_t B = (size_t)n_tasks, R = s->dims.n_dims, K = s->dims.n_kdims;
+  b.n = n_tasks;
+  if (B == 0) return VC_OK;
+  if (!bt->resreq || !bt->req_has || !bt->k8s_req || !bt->k8s_nonzero_req || !bt->job || !bt->klass || !bt->role ||
+      !bt->priority || !bt->uid_rank)
+    return fail(VC_EINVAL, "backfill task list: null array");
+  b.req.assign(bt->resreq, bt->resreq + R * B); b.kreq.assign(bt->k8s_req, bt->k8s_req + K * B);
+  b.knz.assign(bt->k8s_nonzero_req, bt->k8s_nonzero_req + 2 * B);
+  b.has.assign(bt->req_has, bt->req_has + B); b.uid.assign(bt->uid_rank, bt->uid_rank + B);
+  b.job.assign(bt->job, bt->job + B); b.klass.assign(bt->klass, bt->klass + B); b.role.assign(bt->role, bt->role + B);
+  b.prio.assign(bt->priority, bt->priority + B);
+  if (bt->pod_index) b.podidx.assign(bt->pod_index, bt->pod_index + B); else b.podidx.assign(B, -1);
+  if (bt->creation_ts) b.ts.assign(bt->creation_ts, bt->creation_ts + B); else b.ts.assign(B, 0);
+  return VC_OK;
+}
+
+int vc_backfill_run(vc_snapshot *s, vc_result **out) {
+  if (!s || !out) return fail(VC_EINVAL, "null argument");
+  if (!s->uploaded) return fail(VC_EINVAL, "vc_snapshot_upload must precede vc_backfill_run");
+  if (s->bf_ran) return fail(VC_EINVAL, "vc_backfill_run already ran on this session state (run vc_allocate_run or upload again)");
+  const double t0 = now_ms();
+  const vc_dims &D = s->dims;
+  const size_t N = D.n_nodes, T = D.n_tasks, J = D.n_jobs, Q = D.n_queues, R = D.n_dims, K = D.n_kdims, NR = D.n_roles;
+  const size_t B = (size_t)s->bf.n;
+  vc_result *r = new vc_result();
+  r->stats.upload_ms = s->upload_ms;
+  if (B > 0 && s->dc.to_find > 0) { delete r; return fail(VC_EUNSUPPORTED, "backfill with feasible-node sampling (percentage-nodes-to-find < 100)"); }
+  if (B > 0 && vch::has_plugin(s->conf, VC_PLUGIN_NETWORK_TOPOLOGY_AWARE)) { delete r; return fail(VC_EUNSUPPORTED, "backfill with the network-topology-aware plugin"); }
+  if (s->dd.node_begin != 0 || s->dd.node_end != (int)N) { delete r; return fail(VC_EUNSUPPORTED, "the backfill engine runs on the full node axis"); }
+  if (B == 0) { *out = r; return VC_OK; }
+  const vc_snapshot::BackfillTasks &bf = s->bf;
+  const vc_snapshot::BackfillKeep &bk = s->bk;
+  const vc_conf &conf = s->conf;
+
+  // ---- 1. the session state the allocate action left: ready counts, role occupancy, drf / proportion shares ----
+  std::vector<int32_t> j_ready = bk.j_ready0, r_occ = bk.r_occ0;
+  std::vector<double> j_alloc = bk.j_alloc0;
+  std::vector<vch::QAttr> qattr = s->qattr;
+  for (const vc_decision &op : s->last_dec) {  // Statement.Allocate / Pipeline of every kept visit, in order
+    const int t = op.task, j = s->h_task_job[t];
+    if (op.kind == VC_OP_ALLOCATE) { j_ready[j] += 1; r_occ[bk.t_role[t]] += 1; }
+    if (s->dc.has_drf)  // drf AllocateFunc, drf.go:391-418
+      for (size_t d = 0; d < R; ++d) j_alloc[d * J + j] += s->h_req[d * T + t];
+    const int q = bk.j_queue[j];
+    if (s->dc.has_proportion && q >= 0 && qattr[q].exists)  // proportion AllocateFunc, proportion.go:475-497
+      qattr[q].allocated.add(vch::HRes::load(s->h_req.data(), (int)T, t, (int)R, s->h_has[t]), (int)R);
+  }
+  std::vector<double> j_share(J, 0.0);
+  if (s->dc.has_drf)
+    for (size_t j = 0; j < J; ++j) {  // drf.calculateShare, drf.go:566-578
+      double res = 0;
+      for (size_t d = 0; d < R; ++d) {
+        if (d >= 2 && !((s->total_has >> d) & 1u)) continue;
+        if (!(s->total[d] >= vch::kMinRes)) continue;
+        const double sh = vch::share_of(j_alloc[d * J + j], s->total[d]);
+        if (sh > res) res = sh;
+      }
+      j_share[j] = res;
+    }
+  std::vector<double> q_share(Q, 0.0);
+  for (size_t q = 0; q < Q; ++q)
+    if (qattr[q].exists) q_share[q] = vch::queue_share(qattr[q], (int)R);
+  auto is_ready = [&](int j) { return j_ready[j] + bk.j_pbe[j] >= bk.j_min[j]; };  // job_info.go:1169
+  auto job_less = [&](int l, int rr) {  // ssn.JobOrderFn, session_plugins.go:660-683
+    for (int i = 0; i < conf.n_plugins; ++i) {
+      const vc_plugin_option &po = conf.plugins[i];
+      if (!(po.enabled & VC_EN_JOB_ORDER)) continue;
+      int c = 0;
+      switch (po.plugin) {
+        case VC_PLUGIN_PRIORITY: c = bk.j_prio[l] > bk.j_prio[rr] ? -1 : (bk.j_prio[l] < bk.j_prio[rr] ? 1 : 0); break;
+        case VC_PLUGIN_GANG: {
+          const bool lr = is_ready(l), r2 = is_ready(rr);
+          c = (lr && r2) ? 0 : (lr ? 1 : (r2 ? -1 : 0));
+          break;
+        }
+        case VC_PLUGIN_DRF: c = j_share[l] == j_share[rr] ? 0 : (j_share[l] < j_share[rr] ? -1 : 1); break;
+        case VC_PLUGIN_TDM: {
+          const bool lp = bk.j_flags[l] & VC_JOB_PREEMPTABLE, rp = bk.j_flags[rr] & VC_JOB_PREEMPTABLE;
+          c = lp == rp ? 0 : (!lp ? -1 : 1);
+          break;
+        }
+        default: break;
+      }
+      if (c != 0) return c < 0;
+    }
+    return bk.j_rank[l] < bk.j_rank[rr];
+  };
+  const bool qorder_prop = vch::plugin_enabled(conf, VC_PLUGIN_PROPORTION, VC_EN_QUEUE_ORDER);
+  auto queue_less = [&](int l, int rr) {  // ssn.QueueOrderFn :709-731; proportion.go:266-284
+    if (qorder_prop) {
+      if (bk.q_prio[l] != bk.q_prio[rr]) return bk.q_prio[l] > bk.q_prio[rr];
+      if (q_share[l] != q_share[rr]) return q_share[l] < q_share[rr];
+    }
+    return bk.q_rank[l] < bk.q_rank[rr];
+  };
+
+  // ---- 2. pickUpPendingTasks, backfill.go:118-199 ----
+  vc_tasks view;
+  std::memset(&view, 0, sizeof view);
+  view.priority = bf.prio.data(); view.pod_index = bf.podidx.data(); view.creation_ts = bf.ts.data(); view.uid_rank = bf.uid.data();
+  const vch::TaskLess task_less{&view, vch::plugin_enabled(conf, VC_PLUGIN_PRIORITY, VC_EN_TASK_ORDER)};
+  std::vector<std::vector<int>> job_tasks(J), queue_jobs(Q);
+  for (size_t t = 0; t < B; ++t) job_tasks[bf.job[t]].push_back((int)t);
+  std::vector<int> queues;
+  for (size_t j = 0; j < J; ++j) {
+    if (bk.j_flags[j] & VC_JOB_PENDING_PHASE) continue;  // job.IsPending(), :124-126
+    if (!bk.j_valid[j]) continue;                         // ssn.JobValid, :128-131
+    const int q = bk.j_queue[j];
+    if (q < 0 || job_tasks[j].empty()) continue;
+    if (queue_jobs[q].empty()) queues.push_back(q);
+    queue_jobs[q].push_back((int)j);
+  }
+  vch::go_heap_order(queues, queue_less);
+  std::vector<int32_t> order;  // backfill task ids in visiting order
+  std::vector<int> visit_job, visit_begin;
+  for (int q : queues) {
+    vch::go_heap_order(queue_jobs[q], job_less);
+    for (int j : queue_jobs[q]) {
+      vch::go_heap_order(job_tasks[j], task_less);
+      visit_job.push_back(j);
+      visit_begin.push_back((int)order.size());
+      for (int t : job_tasks[j]) order.push_back(t);
+    }
+  }
+  visit_begin.push_back((int)order.size());
+  const size_t n = order.size();
+
+  // ---- 3. (class, request) groups of the verdict cache ----
+  std::vector<int32_t> group(B, 0);
+  {
+    std::unordered_map<std::string, int> index;
+    std::string key;
+    for (size_t t = 0; t < B; ++t) {
+      key.clear();
+      key.append(reinterpret_cast<const char *>(&bf.klass[t]), 4);
+      key.append(reinterpret_cast<const char *>(&bf.has[t]), 4);
+      for (size_t d = 0; d < R; ++d) key.append(reinterpret_cast<const char *>(&bf.req[d * B + t]), 8);
+      for (size_t k = 0; k < K; ++k) key.append(reinterpret_cast<const char *>(&bf.kreq[k * B + t]), 8);
+      for (size_t k = 0; k < 2; ++k) key.append(reinterpret_cast<const char *>(&bf.knz[k * B + t]), 8);
+      group[t] = index.emplace(key, (int)index.size()).first->second;
+    }
+  }
+
+  // ---- 4. device buffers: one slab ----
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t off = 0;
+  const size_t o_req = off; off += al(R * B * 8);
+  const size_t o_kreq = off; off += al(K * B * 8);
+  const size_t o_knz = off; off += al(2 * B * 8);
+  const size_t o_has = off; off += al(B * 4);
+  const size_t o_klass = off; off += al(B * 4);
+  const size_t o_group = off; off += al(B * 4);
+  const size_t o_order = off; off += al(std::max<size_t>(n, 1) * 4);
+  const size_t in_bytes = off;
+  const size_t o_node = off; off += al(std::max<size_t>(n, 1) * 4);
+  const size_t o_score = off; off += al(std::max<size_t>(n, 1) * 8);
+  if (s->d_bf_bytes < off) {
+    if (s->d_bf) cudaFree(s->d_bf);
+    s->d_bf = nullptr; s->d_bf_bytes = 0;
+    if (cudaMalloc(&s->d_bf, off) != cudaSuccess) { delete r; return fail(VC_ENOMEM, "backfill buffers (%zu bytes)", off); }
+    s->d_bf_bytes = off;
+  }
+  std::vector<unsigned char> stage(in_bytes, 0);
+  std::memcpy(stage.data() + o_req, bf.req.data(), R * B * 8);
+  std::memcpy(stage.data() + o_kreq, bf.kreq.data(), K * B * 8);
+  std::memcpy(stage.data() + o_knz, bf.knz.data(), 2 * B * 8);
+  std::memcpy(stage.data() + o_has, bf.has.data(), B * 4);
+  std::memcpy(stage.data() + o_klass, bf.klass.data(), B * 4);
+  std::memcpy(stage.data() + o_group, group.data(), B * 4);
+  if (n) std::memcpy(stage.data() + o_order, order.data(), n * 4);
+  auto bail = [&](cudaError_t e, const char *what) { delete r; return fail(VC_ECUDA, "%s: %s", what, cudaGetErrorString(e)); };
+  cudaError_t e = cudaMemcpyAsync(s->d_bf, stage.data(), in_bytes, cudaMemcpyHostToDevice, s->stream);
+  if (e != cudaSuccess) return bail(e, "backfill H2D");
+  if (!s->alloc_ran) {  // no allocate action in this cycle: start from the opening node state
+    const struct { void *dst; const void *src; size_t bytes; } cp[] = {
+        {s->w_idle, s->n_idle.d(s->in), R * N * 8}, {s->w_used, s->n_used.d(s->in), R * N * 8},
+        {s->w_pip, s->n_pip.d(s->in), R * N * 8},   {s->w_kreq, s->n_kreq.d(s->in), K * N * 8},
+        {s->w_knz, s->n_knz.d(s->in), 2 * N * 8},   {s->w_pod_count, s->n_pod_count.d(s->in), N * 4}};
+    for (const auto &c : cp)
+      if ((e = cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToDevice, s->stream)) != cudaSuccess) return bail(e, "node state copy");
+  }
+  float kms = 0;
+  std::vector<int32_t> h_node(n, -1);
+  std::vector<double> h_score(n, 0.0);
+  if (n > 0) {
+    const int G = s->n_cta;
+    const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024 * 2;
+    if (!s->mbox && (e = cudaMalloc(&s->mbox, mbox_bytes)) != cudaSuccess) return bail(e, "mailbox");
+    if ((e = cudaMemsetAsync(s->mbox, 0, mbox_bytes, s->stream)) != cudaSuccess) return bail(e, "mailbox reset");
+    K2Params p;
+    std::memset(&p, 0, sizeof p);
+    p.d = s->dd; p.c = s->dc; p.npc = s->npc; p.n_cta = G;
+    p.alloc = s->n_alloc.d(s->in); p.kalloc = s->n_kalloc.d(s->in);
+    p.idle = s->w_idle; p.used = s->w_used; p.kreq = s->w_kreq; p.knz = s->w_knz;
+    p.max_tasks = s->n_max_tasks.d(s->in); p.pod_count = s->w_pod_count; p.cstat = s->cstat;
+    p.mbox = s->mbox;
+    BackfillParams bp;
+    unsigned char *base = static_cast<unsigned char *>(s->d_bf);
+    bp.n = (int)n; bp.B = (int)B;
+    bp.order = reinterpret_cast<const int32_t *>(base + o_order);
+    bp.req = reinterpret_cast<const double *>(base + o_req); bp.kreq = reinterpret_cast<const double *>(base + o_kreq);
+    bp.knz = reinterpret_cast<const double *>(base + o_knz); bp.has = reinterpret_cast<const uint32_t *>(base + o_has);
+    bp.klass = reinterpret_cast<const int32_t *>(base + o_klass); bp.group = reinterpret_cast<const int32_t *>(base + o_group);
+    bp.out_node = reinterpret_cast<int32_t *>(base + o_node); bp.out_score = reinterpret_cast<double *>(base + o_score);
+    const void *kfn = s->dc.soft_active ? (const void *)k_backfill<true> : (const void *)k_backfill<false>;
+    const size_t smem = ((sizeof(BfCtl) + 15) & ~(size_t)15) + (3 * R + 2 * K + 2) * (size_t)s->npc * 8 +
+                        (size_t)s->npc * (4 + 4) + 8 + (size_t)s->npc * (8 + 4 + 1) + 64;
+    if ((e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return bail(e, "backfill smem");
+    int max_blocks = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, kfn, s->block, smem)) != cudaSuccess) return bail(e, "occupancy");
+    if (max_blocks * g_sm_count < G) { delete r; return fail(VC_EUNSUPPORTED, "backfill kernel cannot be co-resident: %d CTAs x %zu B smem", G, smem); }
+    void *args[] = {&p, &bp};
+    cudaEventRecord(s->ev0, s->stream);
+    if ((e = cudaLaunchCooperativeKernel(kfn, dim3(G), dim3(s->block), args, smem, s->stream)) != cudaSuccess) return bail(e, "backfill launch");
+    g_launches++;
+    cudaEventRecord(s->ev1, s->stream);
+    if ((e = cudaMemcpyAsync(h_node.data(), base + o_node, n * 4, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
+    if ((e = cudaMemcpyAsync(h_score.data(), base + o_score, n * 8, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
+  }
+  if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return bail(e, "backfill kernel");
+  if (n > 0) cudaEventElapsedTime(&kms, s->ev0, s->ev1);
+  s->bf_ran = true;
+
+  // ---- 5. the result: one visit per job in pick order ----
+  const bool gang_ready = vch::plugin_enabled(conf, VC_PLUGIN_GANG, VC_EN_JOB_READY);
+  for (size_t v = 0; v < visit_job.size(); ++v) {
+    const int j = visit_job[v];
+    bool ready = true;  // ssn.JobReady (session_plugins.go:428-446; gang.go:183-189): unchanged by backfill itself, a
+    if (gang_ready) {   // placed BestEffort task moves from PendingBestEffortTaskNum to ReadyTaskNum
+      bool task_ready = true;  // CheckTaskReady, job_info.go:1024-1036
+      if (!(bk.j_min[j] < bk.j_taskmintotal[j]))
+        for (int rr = bk.j_roleoff[j]; rr < bk.j_roleoff[j + 1] && task_ready; ++rr)
+          if ((bk.r_flags[rr] & VC_ROLE_IN_MIN_MAP) && r_occ[rr] < bk.r_min[rr]) task_ready = false;
+      ready = task_ready && is_ready(j);
+    }
+    vc_visit vis;
+    vis.job = j; vis.outcome = ready ? VC_VISIT_COMMIT : VC_VISIT_KEEP;
+    vis.first_op = (int32_t)r->decisions.size(); vis.n_ops = 0;
+    for (int k = visit_begin[v]; k < visit_begin[v + 1]; ++k) {
+      if (h_node[k] < 0) { r->fit_errors.push_back(order[k]); continue; }
+      vc_decision dcs;
+      dcs.task = order[k]; dcs.node = h_node[k]; dcs.kind = VC_OP_ALLOCATE; dcs.visit = (int32_t)r->visits.size(); dcs.score = h_score[k];
+      r->decisions.push_back(dcs);
+      vis.n_ops += 1;
+    }
+    r->visits.push_back(vis);
+  }
+  r->stats.commit_ms = kms;
+  r->stats.total_ms = now_ms() - t0;
+  r->stats.h2d_bytes = (int64_t)in_bytes;
+  r->stats.d2h_bytes = (int64_t)n * 12;
+  r->stats.kernel_launches = n > 0 ? 1 : 0;
+  r->stats.n_steps = (int32_t)n;
+  *out = r;
+  (void)NR;
+  return VC_OK;
+}
 
 // ---------------------------------------------------------------------------------------
 // dense pass (K1)

@@ -84,6 +84,9 @@ class Engine:
         topo = s.topology()
         if topo is not None:
             _check(self.L.vc_snapshot_set_topology(self.h, C.byref(topo)))
+        bt = s.backfill_tasks()
+        if bt is not None:
+            _check(self.L.vc_snapshot_set_backfill(self.h, s.B, C.byref(bt)))
         _check(self.L.vc_snapshot_upload(self.h, C.byref(n), C.byref(t), C.byref(c), C.byref(j), C.byref(q),
                                          C.byref(s.conf)))
         self._uploaded = True
@@ -93,6 +96,17 @@ class Engine:
             self.upload()
         r = C.c_void_p()
         _check(self.L.vc_allocate_run(self.h, C.byref(r)))
+        return self._result(r)
+
+    def backfill(self) -> AllocateResult:
+        """The backfill action on the session state allocate() left (decision.task indexes snap.backfill_task_keys)."""
+        if not self._uploaded:
+            self.upload()
+        r = C.c_void_p()
+        _check(self.L.vc_backfill_run(self.h, C.byref(r)))
+        return self._result(r)
+
+    def _result(self, r) -> AllocateResult:
         try:
             nd = self.L.vc_result_num_decisions(r)
             nv = self.L.vc_result_num_visits(r)
@@ -167,6 +181,9 @@ def gpu_engine(snap: Snapshot, device: int = 0) -> AllocateResult:
     e = Engine(snap, device)
     try:
         e.upload()
-        return e.allocate()
+        res = e.allocate()
+        if snap.B > 0 and "backfill" in snap.actions:  # the configured action list, scheduler.go:124-153
+            res.backfill = e.backfill()
+        return res
     finally:
         e.close()

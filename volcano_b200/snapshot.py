@@ -197,8 +197,9 @@ class Snapshot:
     NODE_F = ("allocatable", "idle", "used", "releasing", "pipelined")
     NODE_K = ("k8s_allocatable", "k8s_requested", "k8s_nonzero_requested")
 
-    def __init__(self, N, T, J, Q, C_, NR, R, K=3, Wl=1, Wt=1, Z=0, pods_dim=-1):
+    def __init__(self, N, T, J, Q, C_, NR, R, K=3, Wl=1, Wt=1, Z=0, pods_dim=-1, B=0):
         self.N, self.T, self.J, self.Q, self.C, self.NR, self.R, self.K = N, T, J, Q, C_, NR, R, K
+        self.B = B  # BestEffort pending tasks (the backfill action's tasks; not part of T)
         self.Wl, self.Wt, self.Z, self.pods_dim = Wl, Wt, Z, pods_dim
         f8, i4, i8, u4, u8 = np.float64, np.int32, np.int64, np.uint32, np.uint64
         # nodes
@@ -214,18 +215,19 @@ class Snapshot:
         self.n_flags = np.zeros(N, u4)
         self.n_revocable_zone = np.full(N, -1, i4)
         self.zone_active = np.zeros(max(Z, 1), np.uint8)
-        # tasks
-        self.t_resreq = np.zeros((R, T), f8)
-        self.t_req_has = np.zeros(T, u4)
-        self.t_k8s_req = np.zeros((K, T), f8)
-        self.t_k8s_nonzero_req = np.zeros((K, T), f8)
-        self.t_job = np.zeros(T, i4)
-        self.t_klass = np.zeros(T, i4)
-        self.t_role = np.zeros(T, i4)
-        self.t_priority = np.ones(T, i4)
-        self.t_pod_index = np.full(T, -1, i8)
-        self.t_creation_ts = np.zeros(T, i8)
-        self.t_uid_rank = np.arange(T, dtype=u4)
+        # tasks (t_*: allocate's tasks; b_*: the BestEffort tasks of the backfill action, same fields)
+        for pre, n in (("t_", T), ("b_", B)):
+            setattr(self, pre + "resreq", np.zeros((R, n), f8))
+            setattr(self, pre + "req_has", np.zeros(n, u4))
+            setattr(self, pre + "k8s_req", np.zeros((K, n), f8))
+            setattr(self, pre + "k8s_nonzero_req", np.zeros((K, n), f8))
+            setattr(self, pre + "job", np.zeros(n, i4))
+            setattr(self, pre + "klass", np.zeros(n, i4))
+            setattr(self, pre + "role", np.zeros(n, i4))
+            setattr(self, pre + "priority", np.ones(n, i4))
+            setattr(self, pre + "pod_index", np.full(n, -1, i8))
+            setattr(self, pre + "creation_ts", np.zeros(n, i8))
+            setattr(self, pre + "uid_rank", np.arange(n, dtype=u4))
         # classes
         MT = abi.VC_MAX_TERMS
         self.c_selector = np.zeros((C_, Wl), u8)
@@ -273,6 +275,7 @@ class Snapshot:
         self.q_request_has = np.zeros(Q, u4)
         self.q_allocated_has = np.zeros(Q, u4)
         self.conf: Optional[abi.vc_conf] = None
+        self.actions: Sequence[str] = ("allocate",)  # the configured action list (which Action objects the host runs)
         # HyperNode tree (None: no HyperNode objects in the session)
         self.hn_names: List[str] = []
         self.hn_min_tier = 1
@@ -288,6 +291,7 @@ class Snapshot:
         self.dim_names: List[str] = []
         self.node_names: List[str] = []
         self.task_keys: List[str] = []
+        self.backfill_task_keys: List[str] = []
         self.job_names: List[str] = []
         self.queue_names: List[str] = []
 
@@ -313,12 +317,17 @@ class Snapshot:
             _ptr(self.n_taint_hard, _U64), _ptr(self.n_taint_soft, _U64), _ptr(self.n_flags, _U32),
             _ptr(self.n_revocable_zone, _I32), _ptr(self.zone_active, _U8))
 
-    def tasks(self) -> abi.vc_tasks:
+    def tasks(self, pre: str = "t_") -> abi.vc_tasks:
+        g = lambda name: getattr(self, pre + name)
         return abi.vc_tasks(
-            _ptr(self.t_resreq, _F64), _ptr(self.t_req_has, _U32), _ptr(self.t_k8s_req, _F64),
-            _ptr(self.t_k8s_nonzero_req, _F64), _ptr(self.t_job, _I32), _ptr(self.t_klass, _I32),
-            _ptr(self.t_role, _I32), _ptr(self.t_priority, _I32), _ptr(self.t_pod_index, _I64),
-            _ptr(self.t_creation_ts, _I64), _ptr(self.t_uid_rank, _U32))
+            _ptr(g("resreq"), _F64), _ptr(g("req_has"), _U32), _ptr(g("k8s_req"), _F64),
+            _ptr(g("k8s_nonzero_req"), _F64), _ptr(g("job"), _I32), _ptr(g("klass"), _I32),
+            _ptr(g("role"), _I32), _ptr(g("priority"), _I32), _ptr(g("pod_index"), _I64),
+            _ptr(g("creation_ts"), _I64), _ptr(g("uid_rank"), _U32))
+
+    def backfill_tasks(self) -> Optional[abi.vc_tasks]:
+        """The argument of vc_snapshot_set_backfill, or None when the session has no BestEffort pending task."""
+        return self.tasks("b_") if self.B > 0 else None
 
     def classes(self) -> abi.vc_classes:
         return abi.vc_classes(
@@ -554,6 +563,8 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
     # ---- tasks in scope + role tables -------------------------------------------------------
     task_pods: List[Pod] = []
     task_job: List[int] = []
+    bf_pods: List[Pod] = []  # Pending BestEffort pods: backfill's tasks (backfill.go:140-151)
+    bf_job: List[int] = []
     role_rows: List[Dict[str, int]] = []  # per job: role name -> row
     role_tables = {k: [] for k in ("min", "occ", "pip", "pending_other", "valid", "flags")}
     role_off = [0]
@@ -600,6 +611,8 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
                 if be:
                     snap_j["pbe"][j] += 1
                     role_tables["pending_other"][r] += 1
+                    bf_pods.append(p)
+                    bf_job.append(j)
                 else:
                     task_pods.append(p)
                     task_job.append(j)
@@ -631,7 +644,7 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
     class_keys: Dict[tuple, int] = {}
     class_defs: List[dict] = []
     task_class: List[int] = []
-    for p in task_pods:
+    for p in task_pods + bf_pods:
         sel = tuple(sorted(bit_of(NodeSelectorRequirement(k, "In", (v,))) for k, v in p.node_selector.items()))
         aff = tuple(tuple(sorted(bit_of(r) for r in term)) for term in p.affinity_required)
         pref = tuple((int(w), tuple(sorted(bit_of(r) for r in term))) for w, term in p.affinity_preferred)
@@ -654,10 +667,11 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
 
     N, T, Q = len(nodes), len(task_pods), len(queues)
     s = Snapshot(N, T, J, Q, len(class_defs), role_off[-1], R, K=len(KDIM_NAMES), Wl=Wl, Wt=Wt, Z=len(zones),
-                 pods_dim=pods_dim)
+                 pods_dim=pods_dim, B=len(bf_pods))
     s.dim_names = dim_names
     s.node_names = [n.name for n in nodes]
     s.task_keys = [p.key for p in task_pods]
+    s.backfill_task_keys = [p.key for p in bf_pods]
     s.job_names = job_ids
     s.queue_names = [q.name for q in queues]
 
@@ -736,30 +750,35 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
         s.n_k8s_nonzero_requested[:, i] += _k8s_vector(p.requests, True)
 
     # ---- tasks -------------------------------------------------------------------------------
-    uid_order = np.argsort(np.array([p.uid for p in task_pods], dtype=object), kind="stable") if T else []
-    for rank, t in enumerate(uid_order):
-        s.t_uid_rank[t] = rank
-    for t, p in enumerate(task_pods):
-        v, has = pod_req(p)
-        s.t_resreq[:, t] = v
-        s.t_req_has[t] = has
-        s.t_k8s_req[:, t] = _k8s_vector(p.requests, False)
-        s.t_k8s_nonzero_req[:, t] = _k8s_vector(p.requests, True)
-        j = task_job[t]
-        s.t_job[t] = j
-        s.t_klass[t] = task_class[t]
-        s.t_role[t] = role_rows[j][get_task_role(p)]
-        prio = 1  # api/job_info.go:203,219-227
-        if p.priority is not None:
-            prio = p.priority
-        if TASK_PRIORITY_ANNOTATION in p.annotations:
-            try:
-                prio = int(p.annotations[TASK_PRIORITY_ANNOTATION])
-            except ValueError:
-                pass
-        s.t_priority[t] = prio
-        s.t_pod_index[t] = pod_index_under_task(p.name)
-        s.t_creation_ts[t] = p.creation_ts
+    def fill_tasks(pre, plist, pjob, pclass):
+        g = lambda name: getattr(s, pre + name)
+        uid_order = np.argsort(np.array([p.uid for p in plist], dtype=object), kind="stable") if plist else []
+        for rank, t in enumerate(uid_order):
+            g("uid_rank")[t] = rank
+        for t, p in enumerate(plist):
+            v, has = pod_req(p)
+            g("resreq")[:, t] = v
+            g("req_has")[t] = has
+            g("k8s_req")[:, t] = _k8s_vector(p.requests, False)
+            g("k8s_nonzero_req")[:, t] = _k8s_vector(p.requests, True)
+            j = pjob[t]
+            g("job")[t] = j
+            g("klass")[t] = pclass[t]
+            g("role")[t] = role_rows[j][get_task_role(p)]
+            prio = 1  # api/job_info.go:203,219-227
+            if p.priority is not None:
+                prio = p.priority
+            if TASK_PRIORITY_ANNOTATION in p.annotations:
+                try:
+                    prio = int(p.annotations[TASK_PRIORITY_ANNOTATION])
+                except ValueError:
+                    pass
+            g("priority")[t] = prio
+            g("pod_index")[t] = pod_index_under_task(p.name)
+            g("creation_ts")[t] = p.creation_ts
+
+    fill_tasks("t_", task_pods, task_job, task_class[:T])
+    fill_tasks("b_", bf_pods, bf_job, task_class[T:])
 
     # ---- jobs --------------------------------------------------------------------------------
     uid_order = sorted(range(J), key=lambda j: job_ids[j])
@@ -826,6 +845,7 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
                 s.q_request[:, qi] += v
                 s.q_request_has[qi] |= has
     s.conf = build_conf(conf, dim_names, KDIM_NAMES)
+    s.actions = tuple(conf.actions)
     if hypernodes is not None:
         encode_hypernodes(s, hypernodes, podgroups, job_pods)
     return s

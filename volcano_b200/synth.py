@@ -39,6 +39,7 @@ class SynthConfig:
     topology: Optional[tuple] = None  # HyperNode tree fan-outs below the single root, e.g. (32, 40): 32 tier-2 x 40 tier-1 each
     topology_scatter: float = 0.0     # fraction of nodes assigned to a random leaf / left outside the tree (tests)
     soft_topology_frac: float = 0.0   # fraction of jobs whose PodGroup carries a soft-mode network topology
+    n_besteffort: int = 0             # extra BestEffort pending pods spread over the jobs (the backfill action's tasks)
 
 
 CONFIGS = {
@@ -80,6 +81,14 @@ CONFIGS = {
     # hypernode binpacking only (no topology-constrained jobs)
     "small_topo_normal": SynthConfig("small_topo_normal", 600, 3000, 3, "priority+gang+predicates+nodeorder+binpack+network-topology-aware",
                                      n_classes=16, topology=(4, 6), topology_scatter=0.15),
+    # allocate + backfill: BestEffort pods next to the regular ones
+    "tiny_bf": SynthConfig("tiny_bf", 64, 300, 3, "priority+gang+drf+predicates+proportion+nodeorder+binpack", n_classes=12,
+                           n_besteffort=150),
+    "small_bf": SynthConfig("small_bf", 700, 4000, 4, "priority+gang+drf+predicates+proportion+nodeorder+binpack", n_classes=24,
+                            n_besteffort=3000),
+    "small_soft_bf": SynthConfig("small_soft_bf", 300, 1500, 2, "priority+gang+predicates+nodeorder+binpack", n_classes=16,
+                                 soft_taint_p=0.08, n_besteffort=1200),
+    "cfg2_bf": SynthConfig("cfg2_bf", 10_000, 100_000, 1, "priority+gang+predicates+nodeorder+binpack", n_besteffort=20_000),
     "small_roles": SynthConfig("small_roles", 200, 1200, 2, "priority+gang+predicates+nodeorder+binpack", n_classes=8,
                                utilisation=0.85, mixed_roles=True),
 }
@@ -97,7 +106,8 @@ def scheduler_conf(cfg: SynthConfig) -> SchedulerConf:
     }
     tier1 = [PluginOption.defaults(n, args.get(n)) for n in names if n in ("priority", "gang")]
     tier2 = [PluginOption.defaults(n, args.get(n)) for n in names if n not in ("priority", "gang")]
-    return SchedulerConf(tiers=[t for t in (tier1, tier2) if t], actions=("allocate",))
+    return SchedulerConf(tiers=[t for t in (tier1, tier2) if t],
+                         actions=("allocate", "backfill") if cfg.n_besteffort > 0 else ("allocate",))
 
 
 def make_snapshot(cfg: SynthConfig | str, seed: Optional[int] = None) -> Snapshot:
@@ -120,7 +130,7 @@ def make_snapshot(cfg: SynthConfig | str, seed: Optional[int] = None) -> Snapsho
     job_sizes_a = np.array(job_sizes, np.int64)
     J = len(job_sizes_a)
     C_ = cfg.n_classes
-    s = Snapshot(N, T, J, Q, C_, J, R, K=len(KDIMS), Wl=1, Wt=1, Z=0, pods_dim=D_PODS)
+    s = Snapshot(N, T, J, Q, C_, J, R, K=len(KDIMS), Wl=1, Wt=1, Z=0, pods_dim=D_PODS, B=cfg.n_besteffort)
     s.dim_names = list(DIMS)
     s.node_names = [f"node-{i:06d}" for i in range(N)] if N <= 20000 else []
     s.queue_names = [f"q{i:02d}" for i in range(Q)]
@@ -248,7 +258,7 @@ def make_snapshot(cfg: SynthConfig | str, seed: Optional[int] = None) -> Snapsho
     if cfg.mixed_roles:
         # two roles per job: role 0 = even pod index, role 1 = odd pod index with a different request type;
         # jobs with >= 4 tasks declare TaskMinAvailable {role0: 1, role1: 1}
-        s2 = Snapshot(N, T, J, Q, C_, 2 * J, R, K=len(KDIMS), Wl=1, Wt=1, Z=0, pods_dim=D_PODS)
+        s2 = Snapshot(N, T, J, Q, C_, 2 * J, R, K=len(KDIMS), Wl=1, Wt=1, Z=0, pods_dim=D_PODS, B=cfg.n_besteffort)
         for k, v in s.__dict__.items():
             if isinstance(v, np.ndarray) and not k.startswith("r_") and k != "j_role_off":
                 getattr(s2, k)[...] = v
@@ -288,10 +298,39 @@ def make_snapshot(cfg: SynthConfig | str, seed: Optional[int] = None) -> Snapsho
     for qi in range(Q):
         m = jq == qi
         s.q_request_has[qi] = np.bitwise_or.reduce(has[m]) if m.any() else 0
-    s.conf = build_conf(scheduler_conf(cfg), DIMS, KDIMS)
+    sconf = scheduler_conf(cfg)
+    s.conf = build_conf(sconf, DIMS, KDIMS)
+    s.actions = tuple(sconf.actions)
     if cfg.topology is not None:
         _make_topology(s, cfg, rng)
+    if cfg.n_besteffort > 0:
+        _make_besteffort(s, cfg, np.random.default_rng((cfg.seed if seed is None else seed) + 7919), job_class)
     return s
+
+
+def _make_besteffort(s: Snapshot, cfg: SynthConfig, rng, job_class) -> None:
+    """BestEffort pending pods (Resreq = pods:1 only; upstream non-zero defaults 100m / 200Mi for the scorers) attached to
+    random jobs: they count in PendingBestEffortTaskNum / the role's occupancy during allocate and are placed by backfill."""
+    B, J = cfg.n_besteffort, s.J
+    bj = np.sort(rng.integers(0, J, B)).astype(np.int32)
+    s.b_job[:] = bj
+    s.b_klass[:] = job_class[bj]
+    s.b_role[:] = s.j_role_off[bj]  # first role row of the job
+    s.b_resreq[D_PODS] = 1.0
+    s.b_req_has[:] = np.uint32(1 << D_PODS)
+    s.b_k8s_nonzero_req[0] = 100.0
+    s.b_k8s_nonzero_req[1] = 200.0 * MI
+    s.b_priority[:] = rng.integers(1, 4, B)
+    s.b_pod_index[:] = 1_000_000 + np.arange(B)
+    s.b_uid_rank[:] = rng.permutation(B).astype(np.uint32)
+    cnt = np.bincount(bj, minlength=J).astype(np.int32)
+    s.j_pending_besteffort[:] = cnt
+    s.j_n_tasks_total[:] += cnt
+    s.j_valid_num[:] += cnt
+    first = s.j_role_off[:-1]
+    np.add.at(s.r_valid, first, cnt)
+    np.add.at(s.r_occupied, first, cnt)       # occupied counts pending BestEffort tasks (job_info.go:1024-1036)
+    np.add.at(s.r_pending_other, first, cnt)
 
 
 def _make_topology(s: Snapshot, cfg: SynthConfig, rng) -> None:

@@ -27,6 +27,7 @@ class AllocateResult:
     fit_errors: np.ndarray  # int32 task indices
     stats: Optional[dict] = None
     job_allocated_hypernodes: Optional[np.ndarray] = None  # subJob.AllocatedHyperNode after the run (topology sessions)
+    backfill: Optional["AllocateResult"] = None  # the backfill action's result (task = index into backfill_task_keys)
 
 
 @dataclass
@@ -56,10 +57,13 @@ class TestCommonStruct:
         if isinstance(engine, (list, tuple)):
             from .action import Session
             ssn = Session(self.snap)
-            for act in engine:
-                act.Initialize()
-                act.Execute(ssn)
-                act.UnInitialize()
+            try:
+                for act in engine:
+                    act.Initialize()
+                    act.Execute(ssn)
+                    act.UnInitialize()
+            finally:
+                ssn.close()
             self.result = ssn.result
         else:
             self.result = engine(self.snap)
@@ -76,6 +80,13 @@ class TestCommonStruct:
                     self.binds[key] = node
                 elif op["kind"] == abi.VC_OP_PIPELINE:
                     self.pipelined.setdefault(self.snap.job_names[v["job"]], []).append(node)
+        bf = getattr(self.result, "backfill", None)
+        if bf is not None:  # Session.Allocate dispatches when ssn.JobReady holds (framework/session.go:785-793)
+            for v in bf.visits:
+                if v["outcome"] != abi.VC_VISIT_COMMIT:
+                    continue
+                for op in bf.decisions[v["first_op"]: v["first_op"] + v["n_ops"]]:
+                    self.binds[self.snap.backfill_task_keys[op["task"]]] = self.snap.node_names[op["node"]]
         return self.result
 
     def CheckBind(self) -> Optional[str]:
