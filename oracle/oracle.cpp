@@ -1493,7 +1493,10 @@ int backfill_execute(Session &s) {
     const int j = s.t_job[t], r = s.t_role[t];
     if (j != cur_job) {  // one visit record per job, in pick order
       vc_visit v;
-      v.job = j; v.first_op = (int32_t)s.decisions.size(); v.n_ops = 0; v.outcome = VC_VISIT_KEEP;
+      // ssn.JobReady is invariant under backfill itself (a placed BestEffort task moves from PendingBestEffortTaskNum
+      // to ReadyTaskNum, role occupancy counts it either way): COMMIT = the job's placed tasks are dispatched (:785-793)
+      v.job = j; v.first_op = (int32_t)s.decisions.size(); v.n_ops = 0;
+      v.outcome = job_ready(s, j) ? VC_VISIT_COMMIT : VC_VISIT_KEEP;
       s.visits.push_back(v);
       cur_job = j;
     }
@@ -1539,7 +1542,6 @@ int backfill_execute(Session &s) {
     s.decisions.push_back(dcs);
     s.visits.back().n_ops += 1;
     if (job_ready(s, j)) {  // :785-793: every Allocated task of the job is dispatched
-      s.visits.back().outcome = VC_VISIT_COMMIT;
       for (int u = 0; u < s.T; ++u)
         if (s.t_job[u] == j && s.t_status[u] == kAllocated) s.t_status[u] = kBinding;
     }
