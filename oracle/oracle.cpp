@@ -1483,9 +1483,8 @@ int backfill_execute(Session &s) {
   for (int j = 0; j < s.J; ++j)
     if (s.j_flags[j] & VC_JOB_UNSUPPORTED) return VC_EUNSUPPORTED;
   if (s.has_plugin[VC_PLUGIN_NETWORK_TOPOLOGY_AWARE]) return VC_EUNSUPPORTED;
-  if (num_feasible_nodes_to_find(s.N, s.conf.percentage_nodes_to_find, s.conf.min_nodes_to_find,
-                                 s.conf.min_percentage_nodes_to_find) < s.N)
-    return VC_EUNSUPPORTED;
+  const int32_t to_find = num_feasible_nodes_to_find(s.N, s.conf.percentage_nodes_to_find, s.conf.min_nodes_to_find,
+                                                     s.conf.min_percentage_nodes_to_find);
   std::vector<int> pending = backfill_pick_up_pending_tasks(s, nullptr);
   std::vector<int> feasible;
   int cur_job = -1;
@@ -1504,7 +1503,18 @@ int backfill_execute(Session &s) {
     // always empty, every node is evaluated
     feasible.clear();
     s.sweeps++;
-    {
+    if (to_find < s.N) {
+      // feasible-node sampling (util/predicate_helper.go:43-140, single-worker reading): scan from
+      // lastProcessedNodeIndex, stop after to_find feasible nodes
+      const int start = (int)s.last_processed_node_index;
+      int processed = 0;
+      for (int i = 0; i < s.N && (int)feasible.size() < to_find; ++i) {
+        const int n = (start + i) % s.N;
+        processed++;
+        if (plugin_predicates(s, t, n)) feasible.push_back(n);
+      }
+      s.last_processed_node_index = (start + processed) % s.N;
+    } else {
       std::vector<uint8_t> ok(s.N, 0);
       s.pool->parallel_for(s.N, [&](int b, int e) {
         for (int n = b; n < e; ++n) ok[n] = plugin_predicates(s, t, n) ? 1 : 0;

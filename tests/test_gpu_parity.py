@@ -261,12 +261,22 @@ def test_backfill_action_interface(gpu, oracle_engine):
     assert len(bf.decisions) == 6 and [snap.backfill_task_keys[t] for t in bf.fit_errors] == ["c1/be2", "c1/be3"]
     assert sorted(tc.binds) == ["c1/be0", "c1/be1", "c1/w0", "c1/w1", "c1/w2"]
     assert bf.decisions["score"][-1] == 0.0  # one candidate left: taken without scoring (backfill.go:89-90)
-    # sampling and the topology plugin are outside vc_backfill_run
-    tc2 = TestCommonStruct(Name="unsupported", Nodes=nodes, Pods=pods, Queues=[BuildQueue("q1", 1, None)],
+    # feasible-node sampling carries on from the index allocate left
+    tc2 = TestCommonStruct(Name="sampling", Nodes=nodes, Pods=pods, Queues=[BuildQueue("q1", 1, None)],
                            PodGroups=[BuildPodGroup("pg1", "c1", "q1", 2), BuildPodGroup("pg2", "c1", "q1", 5)])
-    tc2.RegisterSession(conf.tiers, actions=("allocate", "backfill"), percentage_nodes_to_find=50, min_nodes_to_find=1)
+    snap2 = tc2.RegisterSession(conf.tiers, actions=("allocate", "backfill"), percentage_nodes_to_find=50, min_nodes_to_find=1,
+                                last_processed_node_index=2)
+    tc2.Run([action.New(), backfill.New()])
+    ref2 = oracle_engine(snap2)
+    _assert_same(tc2.result, ref2)
+    _assert_same(tc2.result.backfill, ref2.backfill)
+    # the topology plugin is outside vc_backfill_run: fail loudly
+    tc3 = TestCommonStruct(Name="unsupported", Nodes=nodes, Pods=pods, Queues=[BuildQueue("q1", 1, None)],
+                           PodGroups=[BuildPodGroup("pg1", "c1", "q1", 2), BuildPodGroup("pg2", "c1", "q1", 5)])
+    tc3.RegisterSession([conf.tiers[0], conf.tiers[1] + [PluginOption.defaults("network-topology-aware")]],
+                        actions=("allocate", "backfill"))
     with pytest.raises(gpu.VcError) as ei:
-        tc2.Run([action.New(), backfill.New()])
+        tc3.Run([action.New(), backfill.New()])
     assert ei.value.code == abi_mod().VC_EUNSUPPORTED
 
 

@@ -149,17 +149,15 @@ def make_case(seed, big=False):
     if want_backfill:
         actions += ("backfill",)
     tc.conf_kw = {}
-    if rnd.random() < (0.1 if want_backfill else 0.3):  # feasible-node sampling with a rotating start index
+    if rnd.random() < 0.3:  # feasible-node sampling with a rotating start index
         tc.conf_kw = dict(percentage_nodes_to_find=rnd.choice([0, 10, 30, 60]), min_nodes_to_find=rnd.choice([1, 3, 10, 50]),
                           min_percentage_nodes_to_find=rnd.choice([5, 20]), last_processed_node_index=rnd.randint(0, 500))
     return tc, tiers, actions
 
 
 def backfill_supported(tiers, conf_kw):
-    """vc_backfill_run's documented limits: no network-topology-aware plugin, no feasible-node sampling."""
-    if any(po.name == "network-topology-aware" for t in tiers for po in t):
-        return False
-    return conf_kw.get("percentage_nodes_to_find", 100) >= 100
+    """vc_backfill_run's documented limit: no network-topology-aware plugin."""
+    return not any(po.name == "network-topology-aware" for t in tiers for po in t)
 
 
 def main():
@@ -211,7 +209,8 @@ def main():
                 bdec, bvis, bfe = o.backfill()
                 bf_runs += 1
                 bf_placed += len(bdec)
-                if not (np.array_equal(bdec, rb.decisions) and np.array_equal(bvis, rb.visits) and np.array_equal(bfe, rb.fit_errors)):
+                same_idx = rb.stats["last_processed_node_index"] == _po.lib().vco_last_processed_node_index(o.h)
+                if not (same_idx and np.array_equal(bdec, rb.decisions) and np.array_equal(bvis, rb.visits) and np.array_equal(bfe, rb.fit_errors)):
                     bf_bad += 1
                     print(f"BACKFILL MISMATCH seed={seed}: oracle {len(bdec)} dec / {len(bvis)} visits / {len(bfe)} fit errors, "
                           f"gpu {len(rb.decisions)} / {len(rb.visits)} / {len(rb.fit_errors)}")

@@ -27,6 +27,8 @@ struct BackfillParams {
   const int32_t *group;   // [B] (class, request) group of the task
   int32_t *out_node;      // [n] chosen node per pick position, -1 = no feasible node
   double *out_score;      // [n] its util.PrioritizeNodes total (0.0 when it was the only candidate)
+  int last_idx0;          // util.lastProcessedNodeIndex when the action starts (feasible-node sampling)
+  int32_t *out_last_idx;  // [1] ... and when it ends
 };
 
 struct BfCtl {
@@ -37,11 +39,20 @@ struct BfCtl {
   unsigned seq;
   double w_score[32];
   int w_node[32], w_cnt[32], w_soft[32];
+  // feasible-node sampling (same scheme as k_commit<.,.,.,SAMP>)
+  int last_idx, samp_proc, samp_total, samp_prefA, samp_prefB;
+  unsigned seq2;
+  int samp_w[4][8][2];
 };
 
-// SOFT: nodeorder's TaintToleration batch score is live (normalised over the candidate set: two passes per task)
-template <bool SOFT>
+// SOFT: the full (four-unit) mailbox record: needed when nodeorder's TaintToleration batch score is live (normalised
+//       over the candidate set: two passes per task) and by SAMP
+// SAMP: feasible-node sampling (util/predicate_helper.go:43-140 in its single-worker reading; a fresh PredicateHelper
+//       per task, backfill.go:71, so there is no error cache): the candidates are the first `to_find` feasible nodes in
+//       index order from lastProcessedNodeIndex, which then advances past the last node the scan looked at
+template <bool SOFT, bool SAMP = false>
 __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams b) {
+  static_assert(!SAMP || SOFT, "the sampling variant rides on the full exchange");
   const DevConf &c = p.c;
   const int R = p.d.R, K = p.d.K, N = p.d.N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -65,7 +76,8 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
   sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 7) & ~(uintptr_t)7);
   double *c_order = reinterpret_cast<double *>(sp); sp += (size_t)cap * 8;   // verdict cache: NodeOrderFn sum,
   int32_t *c_group = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;  // the group it was computed for,
-  uint8_t *c_flag = reinterpret_cast<uint8_t *>(sp);                          // bit0 feasible, bit1 has order score
+  uint8_t *c_flag = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;       // bit0 feasible, bit1 has order score
+  uint8_t *s_samp = reinterpret_cast<uint8_t *>(sp);                          // sampling: 1 = candidate
 
   for (int i = tid; i < nmine; i += blockDim.x) {
     const int n = nbase + i;
@@ -83,7 +95,7 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
     sn.pod_count[i] = p.pod_count[n];
   }
   for (int i = tid; i < cap; i += blockDim.x) c_group[i] = -1;
-  if (tid == 0) S.seq = 0;
+  if (tid == 0) { S.seq = 0; S.seq2 = 0; S.last_idx = b.last_idx0; }
   __syncthreads();
 
   const bool two_pass = SOFT && c.soft_active;
@@ -103,25 +115,80 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
     const int group = S.group;
     const uint32_t *cs_row = p.cstat + (size_t)trec.klass * N + nbase;
     int g_soft = 0;
+    // cached or fresh (feasible, NodeOrderFn sum) of node i for the staged group
+    auto verdict = [&](int i, uint32_t cs, bool *ok, bool *has_order, double *order) {
+      if (c_group[i] == group) {
+        *ok = (c_flag[i] & 1) != 0; *has_order = (c_flag[i] & 2) != 0; *order = c_order[i];
+        return;
+      }
+      SmemNodeView nv{sn, i};
+      *ok = (cs & CS_STATIC_OK) != 0;
+      if (c.pred_predicates && sn.max_tasks[i] <= sn.pod_count[i]) *ok = false;  // predicates.go:662-671
+      *has_order = false;
+      *order = 0.0;
+      if (*ok) *has_order = node_order(c, R, K, trec, nv, cs, order);
+      c_group[i] = group; c_flag[i] = (uint8_t)((*ok ? 1 : 0) | (*has_order ? 2 : 0)); c_order[i] = *order;
+    };
+    const bool sampling = SAMP && c.to_find > 0;
+    if (SAMP && sampling) {
+      const int start = S.last_idx, Kf = c.to_find;
+      const int rows = (cap + (int)blockDim.x - 1) / (int)blockDim.x;
+      const unsigned lt = (1u << lane) - 1u;
+      for (int row = 0; row < rows; ++row) {
+        const int i = row * blockDim.x + tid;
+        int flag = 0;
+        if (i < nmine) {
+          bool ok, ho; double od;
+          verdict(i, c_group[i] != group ? cs_row[i] : 0u, &ok, &ho, &od);
+          flag = ok ? 1 : 2;
+          s_samp[i] = (uint8_t)flag;
+        }
+        const bool inA = nbase + i >= start;
+        const unsigned mA = __ballot_sync(0xffffffffu, flag == 1 && inA), mB = __ballot_sync(0xffffffffu, flag == 1 && !inA);
+        if (lane == 0) { S.samp_w[row][warp][0] = __popc(mA); S.samp_w[row][warp][1] = __popc(mB); }
+      }
+      __syncthreads();
+      if (warp == 0) {
+        int a = 0, bb = 0;
+        for (int e = lane; e < rows * nwarps; e += 32) { a += S.samp_w[e / nwarps][e % nwarps][0]; bb += S.samp_w[e / nwarps][e % nwarps][1]; }
+        a = (int)__reduce_add_sync(0xffffffffu, (unsigned)a);
+        bb = (int)__reduce_add_sync(0xffffffffu, (unsigned)bb);
+        const unsigned seq2 = S.seq2 + 1;
+        __syncwarp();
+        const CountFold f = exchange_counts(p, a, bb, seq2);
+        if (lane == 0) {
+          S.seq2 = seq2;
+          S.samp_prefA = f.prefA;            // feasible nodes before this CTA's part of the [start, N) segment
+          S.samp_prefB = f.totA + f.prefB;   // ... of the [0, start) segment, which is scanned second
+          S.samp_total = f.totA + f.totB;
+          S.samp_proc = 0;
+        }
+      }
+      __syncthreads();
+      for (int row = 0; row < rows; ++row) {
+        const int i = row * blockDim.x + tid;
+        const int flag = i < nmine ? s_samp[i] : 0;
+        const bool inA = nbase + i >= start;
+        const unsigned mA = __ballot_sync(0xffffffffu, flag == 1 && inA), mB = __ballot_sync(0xffffffffu, flag == 1 && !inA);
+        if (i >= nmine || flag != 1) continue;
+        const int seg = inA ? 0 : 1;
+        int before = (inA ? S.samp_prefA : S.samp_prefB) + __popc((inA ? mA : mB) & lt);
+        for (int r2 = 0; r2 <= row; ++r2)
+          for (int w2 = 0; w2 < (r2 < row ? nwarps : warp); ++w2) before += S.samp_w[r2][w2][seg];
+        s_samp[i] = before < Kf ? 1 : 0;
+        if (before == Kf - 1) S.samp_proc = (nbase + i - start + N) % N + 1;  // the scan stops here
+      }
+      __syncthreads();
+    }
     for (int pass = 0; pass < (two_pass ? 2 : 1); ++pass) {
       Local mine;
       local_init(mine);
       for (int i = tid; i < nmine; i += blockDim.x) {
-        const bool fresh = c_group[i] != group;
-        const uint32_t cs = (two_pass || fresh) ? cs_row[i] : 0u;
+        const uint32_t cs = (two_pass || c_group[i] != group) ? cs_row[i] : 0u;
+        if (SAMP && sampling && s_samp[i] != 1) continue;  // outside the sampled candidate set
         bool ok, has_order;
         double order;
-        if (fresh) {
-          SmemNodeView nv{sn, i};
-          ok = (cs & CS_STATIC_OK) != 0;
-          if (c.pred_predicates && sn.max_tasks[i] <= sn.pod_count[i]) ok = false;  // predicates.go:662-671
-          has_order = false;
-          order = 0.0;
-          if (ok) has_order = node_order(c, R, K, trec, nv, cs, &order);
-          c_group[i] = group; c_flag[i] = (uint8_t)((ok ? 1 : 0) | (has_order ? 2 : 0)); c_order[i] = order;
-        } else {
-          ok = (c_flag[i] & 1) != 0; has_order = (c_flag[i] & 2) != 0; order = c_order[i];
-        }
+        verdict(i, cs, &ok, &has_order, &order);
         if (!ok) continue;
         const int soft = SOFT ? (int)((cs >> CS_SOFT_SHIFT) & 0xff) : 0;
         mine.cnt[0] += 1;
@@ -139,12 +206,17 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
         local_init(l);
         if (lane < nwarps) { l.score[0] = S.w_score[lane]; l.node[0] = S.w_node[lane]; l.cnt[0] = S.w_cnt[lane]; l.soft[0] = S.w_soft[lane]; }
         local_warp_reduce<false>(l);
+        if (SAMP && sampling) l.proc = S.samp_proc;
         const unsigned seq = S.seq + 1;
         __syncwarp();  // every lane has read S.seq before lane 0 advances it
         const Local g = exchange<SOFT>(p, l, seq);
         if (lane == 0) {
           S.seq = seq;
           S.cnt = g.cnt[0]; S.best_node = g.node[0]; S.best_score = g.score[0]; S.max_soft = g.soft[0];
+          if (SAMP && sampling && pass == (two_pass ? 1 : 0)) {  // lastProcessedNodeIndex = (start + processedNodes) % N
+            const int processed = S.samp_total >= c.to_find ? g.proc : N;
+            S.last_idx = (S.last_idx + processed) % N;
+          }
         }
       }
       __syncthreads();
@@ -186,4 +258,5 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
     for (int k = 0; k < 2; ++k) p.knz[(size_t)k * N + n] = sn.knz[k * cap + i];
     p.pod_count[n] = sn.pod_count[i];
   }
+  if (cta == 0 && tid == 0) b.out_last_idx[0] = S.last_idx;
 }

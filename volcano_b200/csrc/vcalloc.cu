@@ -204,6 +204,7 @@ struct vc_snapshot {
   } bk;
   std::vector<vc_decision> last_dec;  // operations of the last vc_allocate_run (kept visits only)
   bool alloc_ran = false, bf_ran = false;
+  int last_idx_cur = 0;   // util.lastProcessedNodeIndex as the last action of the cycle left it
   void *d_bf = nullptr;   // device slab of the backfill inputs / outputs
   size_t d_bf_bytes = 0;
 };
@@ -1022,6 +1023,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   s->h_task_job.assign(tk->job, tk->job + T);
   tick("host copies for the dense pass");
   s->alloc_ran = false; s->bf_ran = false;
+  s->last_idx_cur = s->dc.last_idx0;
   s->last_dec.clear();
   if (s->bf.n > 0) {  // what pickUpPendingTasks (backfill.go:118-199) orders by, as of session open
     vc_snapshot::BackfillKeep &k = s->bk;
@@ -1275,6 +1277,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->stats.kernel_launches = 2;  // k_class_static + k_commit
   r->stats.n_steps = s->h_counters[3];
   r->stats.last_processed_node_index = s->dc.to_find > 0 ? s->h_counters[4] : s->dc.last_idx0;
+  s->last_idx_cur = r->stats.last_processed_node_index;
   for (int k = 0; k < 8; ++k) r->stats.prof_cycles[k] = s->h_prof[k];
   r->stats.prof_cycles[6] = s->h_counters[5];  // full sweeps (fast kernel)
   r->stats.prof_cycles[7] = s->h_counters[6];  // incremental steps (fast kernel)
@@ -1336,7 +1339,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   const size_t B = (size_t)s->bf.n;
   vc_result *r = new vc_result();
   r->stats.upload_ms = s->upload_ms;
-  if (B > 0 && s->dc.to_find > 0) { delete r; return fail(VC_EUNSUPPORTED, "backfill with feasible-node sampling (percentage-nodes-to-find < 100)"); }
+  if (B > 0 && s->dc.to_find > 0 && s->npc > 4 * s->block) { delete r; return fail(VC_EUNSUPPORTED, "feasible-node sampling: more than 4 x blockDim nodes per CTA"); }
   if (B > 0 && vch::has_plugin(s->conf, VC_PLUGIN_NETWORK_TOPOLOGY_AWARE)) { delete r; return fail(VC_EUNSUPPORTED, "backfill with the network-topology-aware plugin"); }
   if (s->dd.node_begin != 0 || s->dd.node_end != (int)N) { delete r; return fail(VC_EUNSUPPORTED, "the backfill engine runs on the full node axis"); }
   if (B == 0) { *out = r; return VC_OK; }
@@ -1466,6 +1469,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   const size_t in_bytes = off;
   const size_t o_node = off; off += al(std::max<size_t>(n, 1) * 4);
   const size_t o_score = off; off += al(std::max<size_t>(n, 1) * 8);
+  const size_t o_last = off; off += al(4);
   if (s->d_bf_bytes < off) {
     if (s->d_bf) cudaFree(s->d_bf);
     s->d_bf = nullptr; s->d_bf_bytes = 0;
@@ -1494,6 +1498,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   float kms = 0;
   std::vector<int32_t> h_node(n, -1);
   std::vector<double> h_score(n, 0.0);
+  int32_t h_last = s->last_idx_cur;
   if (n > 0) {
     const int G = s->n_cta;
     const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024 * 2;
@@ -1506,6 +1511,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
     p.idle = s->w_idle; p.used = s->w_used; p.kreq = s->w_kreq; p.knz = s->w_knz;
     p.max_tasks = s->n_max_tasks.d(s->in); p.pod_count = s->w_pod_count; p.cstat = s->cstat;
     p.mbox = s->mbox;
+    p.mbox2 = s->mbox + (size_t)MBOX_STRIDE * 2 * 1024;
     BackfillParams bp;
     unsigned char *base = static_cast<unsigned char *>(s->d_bf);
     bp.n = (int)n; bp.B = (int)B;
@@ -1514,9 +1520,11 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
     bp.knz = reinterpret_cast<const double *>(base + o_knz); bp.has = reinterpret_cast<const uint32_t *>(base + o_has);
     bp.klass = reinterpret_cast<const int32_t *>(base + o_klass); bp.group = reinterpret_cast<const int32_t *>(base + o_group);
     bp.out_node = reinterpret_cast<int32_t *>(base + o_node); bp.out_score = reinterpret_cast<double *>(base + o_score);
-    const void *kfn = s->dc.soft_active ? (const void *)k_backfill<true> : (const void *)k_backfill<false>;
+    bp.last_idx0 = s->last_idx_cur; bp.out_last_idx = reinterpret_cast<int32_t *>(base + o_last);
+    const void *kfn = s->dc.to_find > 0 ? (const void *)k_backfill<true, true>
+                    : s->dc.soft_active ? (const void *)k_backfill<true> : (const void *)k_backfill<false>;
     const size_t smem = ((sizeof(BfCtl) + 15) & ~(size_t)15) + (3 * R + 2 * K + 2) * (size_t)s->npc * 8 +
-                        (size_t)s->npc * (4 + 4) + 8 + (size_t)s->npc * (8 + 4 + 1) + 64;
+                        (size_t)s->npc * (4 + 4) + 8 + (size_t)s->npc * (8 + 4 + 1 + 1) + 64;
     if ((e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return bail(e, "backfill smem");
     int max_blocks = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, kfn, s->block, smem)) != cudaSuccess) return bail(e, "occupancy");
@@ -1528,10 +1536,13 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
     cudaEventRecord(s->ev1, s->stream);
     if ((e = cudaMemcpyAsync(h_node.data(), base + o_node, n * 4, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
     if ((e = cudaMemcpyAsync(h_score.data(), base + o_score, n * 8, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
+    if ((e = cudaMemcpyAsync(&h_last, base + o_last, 4, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
   }
   if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return bail(e, "backfill kernel");
   if (n > 0) cudaEventElapsedTime(&kms, s->ev0, s->ev1);
   s->bf_ran = true;
+  if (s->dc.to_find > 0) s->last_idx_cur = h_last;
+  r->stats.last_processed_node_index = s->last_idx_cur;
 
   // ---- 5. the result: one visit per job in pick order ----
   const bool gang_ready = vch::plugin_enabled(conf, VC_PLUGIN_GANG, VC_EN_JOB_READY);
