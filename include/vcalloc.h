@@ -350,8 +350,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out);
    the BACKFILL task list; there is one visit per job in pick order, outcome VC_VISIT_COMMIT when ssn.JobReady
    held (the tasks were dispatched to the binder) else VC_VISIT_KEEP (Allocated in the session only); tasks
    without a feasible node are listed in fit_errors. Feasible-node sampling continues from the lastProcessedNodeIndex
-   the allocate run left (vc_stats.last_processed_node_index of this result carries it on). VC_EUNSUPPORTED: a
-   registered network-topology-aware plugin together with backfill tasks. */
+   the allocate run left (vc_stats.last_processed_node_index of this result carries it on). VC_EUNSUPPORTED: the
+   network-topology-aware plugin weighs a resource BestEffort pods request ("pods" in hypernode.binpack.resources). */
 int vc_backfill_run(vc_snapshot *s, vc_result **out);
 
 /* Dense task x node pass on the opening snapshot: feasibility bit (allocate.predicate,

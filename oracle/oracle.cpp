@@ -1482,7 +1482,6 @@ int backfill_execute(Session &s) {
   if (s.T == s.T_alloc) return VC_OK;
   for (int j = 0; j < s.J; ++j)
     if (s.j_flags[j] & VC_JOB_UNSUPPORTED) return VC_EUNSUPPORTED;
-  if (s.has_plugin[VC_PLUGIN_NETWORK_TOPOLOGY_AWARE]) return VC_EUNSUPPORTED;
   const int32_t to_find = num_feasible_nodes_to_find(s.N, s.conf.percentage_nodes_to_find, s.conf.min_nodes_to_find,
                                                      s.conf.min_percentage_nodes_to_find);
   std::vector<int> pending = backfill_pick_up_pending_tasks(s, nullptr);

@@ -176,7 +176,8 @@ def test_allocate_vs_oracle(cfg, seed, gpu, oracle_engine):
 
 # ---- the backfill action (actions/backfill/backfill.go) on the state allocate left ----
 @pytest.mark.parametrize("cfg,seed", [("tiny_bf", None), ("tiny_bf", 3), ("small_bf", None), ("small_bf", 5),
-                                      ("small_soft_bf", None), ("small_soft_bf", 2)])
+                                      ("small_soft_bf", None), ("small_soft_bf", 2),
+                                      ("small_topo_bf", None), ("small_topo_bf", 4)])
 def test_allocate_then_backfill_vs_oracle(cfg, seed, gpu, oracle_engine):
     from volcano_b200.synth import make_snapshot
     snap = make_snapshot(cfg, seed)
@@ -270,13 +271,23 @@ def test_backfill_action_interface(gpu, oracle_engine):
     ref2 = oracle_engine(snap2)
     _assert_same(tc2.result, ref2)
     _assert_same(tc2.result.backfill, ref2.backfill)
-    # the topology plugin is outside vc_backfill_run: fail loudly
-    tc3 = TestCommonStruct(Name="unsupported", Nodes=nodes, Pods=pods, Queues=[BuildQueue("q1", 1, None)],
+    # the topology plugin: fine (a BestEffort pod touches no weighted hypernode resource) ...
+    tc3 = TestCommonStruct(Name="nta", Nodes=nodes, Pods=pods, Queues=[BuildQueue("q1", 1, None)],
                            PodGroups=[BuildPodGroup("pg1", "c1", "q1", 2), BuildPodGroup("pg2", "c1", "q1", 5)])
-    tc3.RegisterSession([conf.tiers[0], conf.tiers[1] + [PluginOption.defaults("network-topology-aware")]],
-                        actions=("allocate", "backfill"))
+    snap3 = tc3.RegisterSession([conf.tiers[0], conf.tiers[1] + [PluginOption.defaults("network-topology-aware")]],
+                                actions=("allocate", "backfill"))
+    tc3.Run([action.New(), backfill.New()])
+    ref3 = oracle_engine(snap3)
+    _assert_same(tc3.result, ref3)
+    _assert_same(tc3.result.backfill, ref3.backfill)
+    # ... unless "pods" itself is weighed: outside vc_backfill_run, fail loudly
+    tc4 = TestCommonStruct(Name="unsupported", Nodes=nodes, Pods=pods, Queues=[BuildQueue("q1", 1, None)],
+                           PodGroups=[BuildPodGroup("pg1", "c1", "q1", 2), BuildPodGroup("pg2", "c1", "q1", 5)])
+    nta = PluginOption.defaults("network-topology-aware", {"hypernode.binpack.resources": "pods",
+                                                           "hypernode.binpack.resources.pods": 3})
+    tc4.RegisterSession([conf.tiers[0], conf.tiers[1] + [nta]], actions=("allocate", "backfill"))
     with pytest.raises(gpu.VcError) as ei:
-        tc3.Run([action.New(), backfill.New()])
+        tc4.Run([action.New(), backfill.New()])
     assert ei.value.code == abi_mod().VC_EUNSUPPORTED
 
 

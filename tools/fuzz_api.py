@@ -124,8 +124,6 @@ def make_case(seed, big=False):
     names = ["priority", "gang", "drf", "predicates", "proportion", "nodeorder", "binpack", "tdm", "network-topology-aware"]
     chosen = [n for n in names if rnd.random() < 0.75]
     want_backfill = rnd.random() < 0.7
-    if want_backfill and "network-topology-aware" in chosen and rnd.random() < 0.75:
-        chosen.remove("network-topology-aware")  # vc_backfill_run does not take the plugin (documented limit)
     if "gang" not in chosen and rnd.random() < 0.7:
         chosen.append("gang")
     args = {
@@ -156,8 +154,9 @@ def make_case(seed, big=False):
 
 
 def backfill_supported(tiers, conf_kw):
-    """vc_backfill_run's documented limit: no network-topology-aware plugin."""
-    return not any(po.name == "network-topology-aware" for t in tiers for po in t)
+    """vc_backfill_run's documented limit: "pods" must not be a weighted hypernode-binpacking resource."""
+    return not any(po.name == "network-topology-aware" and "pods" in str(po.arguments.get("hypernode.binpack.resources", ""))
+                   for t in tiers for po in t)
 
 
 def main():

@@ -27,6 +27,9 @@ struct BackfillParams {
   const int32_t *group;   // [B] (class, request) group of the task
   int32_t *out_node;      // [n] chosen node per pick position, -1 = no feasible node
   double *out_score;      // [n] its util.PrioritizeNodes total (0.0 when it was the only candidate)
+  const double *nta_static;  // [N] network-topology-aware entry of a pod WITHOUT a network topology whose request touches
+                             // no weighted hypernode-binpack resource (every hypernode scores 0, a tier without a
+                             // hypernode FullScore): state-independent; NULL when the plugin's map is empty
   int last_idx0;          // util.lastProcessedNodeIndex when the action starts (feasible-node sampling)
   int32_t *out_last_idx;  // [1] ... and when it ends
 };
@@ -194,8 +197,11 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
         mine.cnt[0] += 1;
         mine.soft[0] = max(mine.soft[0], soft);
         if (two_pass && pass == 0) continue;
-        const double sc = total_score(c, has_order, order, soft, g_soft);
         const int n = nbase + i;
+        // pods of a soft-mode topology job carry task.JobAllocatedHyperNode == "" here (only allocate.go:659 sets it):
+        // batchNodeOrderFnForNetworkAwarePods returns no entries (:544-547)
+        const double nta = (b.nta_static && !(trec.has & VC_HAS_TOPO_TASK)) ? b.nta_static[n] : 0.0;
+        const double sc = total_score(c, has_order, order, soft, g_soft, nta);
         if (mine.node[0] < 0 || better(sc, n, mine.score[0], mine.node[0])) { mine.score[0] = sc; mine.node[0] = n; }
       }
       local_warp_reduce<false>(mine);

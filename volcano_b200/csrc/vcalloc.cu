@@ -1340,7 +1340,16 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   vc_result *r = new vc_result();
   r->stats.upload_ms = s->upload_ms;
   if (B > 0 && s->dc.to_find > 0 && s->npc > 4 * s->block) { delete r; return fail(VC_EUNSUPPORTED, "feasible-node sampling: more than 4 x blockDim nodes per CTA"); }
-  if (B > 0 && vch::has_plugin(s->conf, VC_PLUGIN_NETWORK_TOPOLOGY_AWARE)) { delete r; return fail(VC_EUNSUPPORTED, "backfill with the network-topology-aware plugin"); }
+  if (B > 0 && s->dc.nta_on) {
+    // hypernode binpacking of a BestEffort pod: every term is skipped unless a weighted resource is requested
+    // (network_topology_aware.go:507-520), i.e. unless "pods" is listed in hypernode.binpack.resources
+    for (size_t t = 0; t < B; ++t)
+      for (size_t d = 0; d < R; ++d)
+        if ((d < 2 || ((s->bf.has[t] >> d) & 1u)) && s->bf.req[d * B + t] >= vch::kMinRes && s->dc.nta_dim_weight[d] >= 0) {
+          delete r;
+          return fail(VC_EUNSUPPORTED, "backfill: network-topology-aware weighs a resource (dimension %zu) BestEffort pods request", d);
+        }
+  }
   if (s->dd.node_begin != 0 || s->dd.node_end != (int)N) { delete r; return fail(VC_EUNSUPPORTED, "the backfill engine runs on the full node axis"); }
   if (B == 0) { *out = r; return VC_OK; }
   const vc_snapshot::BackfillTasks &bf = s->bf;
@@ -1440,7 +1449,25 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   visit_begin.push_back((int)order.size());
   const size_t n = order.size();
 
-  // ---- 3. (class, request) groups of the verdict cache ----
+  // ---- 3. (class, request) groups of the verdict cache; the plugin's state-independent entry per node ----
+  std::vector<uint32_t> has_x(bf.has);
+  if (s->dc.nta_plugin)
+    for (size_t t = 0; t < B; ++t)
+      if (!s->h_job_soft.empty() && s->h_job_soft[bf.job[t]]) has_x[t] |= VC_HAS_TOPO_TASK;
+  std::vector<double> nta_static;
+  if (s->dc.nta_on) {  // batchNodeOrderFnForNormalPods :462-496 with every hypernode score 0
+    nta_static.resize(N);
+    const int L = s->dc.nta_L;
+    for (size_t nn = 0; nn < N; ++nn) {
+      double total = 0.0;
+      for (int l = 0; l < L; ++l) {
+        const int h = s->has_topo ? s->h_member[(size_t)l * N + nn] : 0;
+        total += s->dc.tier_w[l] * (h < 0 ? 1.0 : 0.0);
+      }
+      const double sc = total / s->dc.tier_w_total;
+      nta_static[nn] = (double)VC_MAX_NODE_SCORE * (double)s->dc.nta_weight * sc;
+    }
+  }
   std::vector<int32_t> group(B, 0);
   {
     std::unordered_map<std::string, int> index;
@@ -1448,7 +1475,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
     for (size_t t = 0; t < B; ++t) {
       key.clear();
       key.append(reinterpret_cast<const char *>(&bf.klass[t]), 4);
-      key.append(reinterpret_cast<const char *>(&bf.has[t]), 4);
+      key.append(reinterpret_cast<const char *>(&has_x[t]), 4);
       for (size_t d = 0; d < R; ++d) key.append(reinterpret_cast<const char *>(&bf.req[d * B + t]), 8);
       for (size_t k = 0; k < K; ++k) key.append(reinterpret_cast<const char *>(&bf.kreq[k * B + t]), 8);
       for (size_t k = 0; k < 2; ++k) key.append(reinterpret_cast<const char *>(&bf.knz[k * B + t]), 8);
@@ -1466,6 +1493,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   const size_t o_klass = off; off += al(B * 4);
   const size_t o_group = off; off += al(B * 4);
   const size_t o_order = off; off += al(std::max<size_t>(n, 1) * 4);
+  const size_t o_nta = off; off += al(nta_static.size() * 8);
   const size_t in_bytes = off;
   const size_t o_node = off; off += al(std::max<size_t>(n, 1) * 4);
   const size_t o_score = off; off += al(std::max<size_t>(n, 1) * 8);
@@ -1480,7 +1508,8 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   std::memcpy(stage.data() + o_req, bf.req.data(), R * B * 8);
   std::memcpy(stage.data() + o_kreq, bf.kreq.data(), K * B * 8);
   std::memcpy(stage.data() + o_knz, bf.knz.data(), 2 * B * 8);
-  std::memcpy(stage.data() + o_has, bf.has.data(), B * 4);
+  std::memcpy(stage.data() + o_has, has_x.data(), B * 4);
+  if (!nta_static.empty()) std::memcpy(stage.data() + o_nta, nta_static.data(), nta_static.size() * 8);
   std::memcpy(stage.data() + o_klass, bf.klass.data(), B * 4);
   std::memcpy(stage.data() + o_group, group.data(), B * 4);
   if (n) std::memcpy(stage.data() + o_order, order.data(), n * 4);
@@ -1520,6 +1549,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
     bp.knz = reinterpret_cast<const double *>(base + o_knz); bp.has = reinterpret_cast<const uint32_t *>(base + o_has);
     bp.klass = reinterpret_cast<const int32_t *>(base + o_klass); bp.group = reinterpret_cast<const int32_t *>(base + o_group);
     bp.out_node = reinterpret_cast<int32_t *>(base + o_node); bp.out_score = reinterpret_cast<double *>(base + o_score);
+    bp.nta_static = nta_static.empty() ? nullptr : reinterpret_cast<const double *>(base + o_nta);
     bp.last_idx0 = s->last_idx_cur; bp.out_last_idx = reinterpret_cast<int32_t *>(base + o_last);
     const void *kfn = s->dc.to_find > 0 ? (const void *)k_backfill<true, true>
                     : s->dc.soft_active ? (const void *)k_backfill<true> : (const void *)k_backfill<false>;

@@ -88,6 +88,8 @@ CONFIGS = {
                             n_besteffort=3000),
     "small_soft_bf": SynthConfig("small_soft_bf", 300, 1500, 2, "priority+gang+predicates+nodeorder+binpack", n_classes=16,
                                  soft_taint_p=0.08, n_besteffort=1200),
+    "small_topo_bf": SynthConfig("small_topo_bf", 600, 3000, 3, "priority+gang+predicates+nodeorder+binpack+network-topology-aware",
+                                 n_classes=16, topology=(4, 6), topology_scatter=0.15, soft_topology_frac=0.2, n_besteffort=2500),
     "cfg2_bf": SynthConfig("cfg2_bf", 10_000, 100_000, 1, "priority+gang+predicates+nodeorder+binpack", n_besteffort=20_000),
     "small_roles": SynthConfig("small_roles", 200, 1200, 2, "priority+gang+predicates+nodeorder+binpack", n_classes=8,
                                utilisation=0.85, mixed_roles=True),
