@@ -35,8 +35,8 @@ struct BackfillParams {
 };
 
 struct BfCtl {
-  TaskRec trec;
-  int group;
+  TaskRec trec2[2];  // double-buffered: the record of task pos+1 is fetched while task pos is swept / exchanged
+  int group2[2];
   int cnt, best_node, max_soft;
   double best_score;
   unsigned seq;
@@ -102,20 +102,26 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
   __syncthreads();
 
   const bool two_pass = SOFT && c.soft_active;
-  for (int pos = 0; pos < b.n; ++pos) {
+  // stage the record of pick position `pos` into buffer pos & 1 (the last warp: it has the fewest nodes to sweep)
+  auto stage = [&](int pos) {
+    if (pos >= b.n || warp != nwarps - 1) return;
     const int t = b.order[pos];
-    __syncthreads();
-    if (tid < R) S.trec.req[tid] = b.req[(size_t)tid * b.B + t];
-    if (tid >= 32 && tid < 32 + K) S.trec.kreq[tid - 32] = b.kreq[(size_t)(tid - 32) * b.B + t];
-    if (tid >= 64 && tid < 66) S.trec.knz[tid - 64] = b.knz[(size_t)(tid - 64) * b.B + t];
-    if (tid == 96 % blockDim.x) {
-      S.trec.has = b.has[t];
-      S.trec.klass = b.klass[t];
-      S.group = b.group[t];
+    TaskRec &r = S.trec2[pos & 1];
+    if (lane < R) r.req[lane] = b.req[(size_t)lane * b.B + t];
+    if (lane < K) r.kreq[lane] = b.kreq[(size_t)lane * b.B + t];
+    if (lane < 2) r.knz[lane] = b.knz[(size_t)lane * b.B + t];
+    if (lane == 31) {
+      r.has = b.has[t];
+      r.klass = b.klass[t];
+      S.group2[pos & 1] = b.group[t];
     }
-    __syncthreads();
-    const TaskRec &trec = S.trec;
-    const int group = S.group;
+  };
+  stage(0);
+  for (int pos = 0; pos < b.n; ++pos) {
+    __syncthreads();  // record `pos` staged; the owner thread is done with record pos - 1
+    stage(pos + 1);   // overwrites the buffer of pos - 1
+    const TaskRec &trec = S.trec2[pos & 1];
+    const int group = S.group2[pos & 1];
     const uint32_t *cs_row = p.cstat + (size_t)trec.klass * N + nbase;
     int g_soft = 0;
     // cached or fresh (feasible, NodeOrderFn sum) of node i for the staged group
