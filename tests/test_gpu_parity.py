@@ -232,6 +232,18 @@ def test_backfill_pick_up_pending_tasks_golden(gpu):
     assert [snap.job_names[j] for j in res.backfill.visits["job"]] == ["default/pg2", "default/pg1"]
 
 
+def test_predicates_node_num_golden(gpu, oracle_engine):
+    """predicates_test.go:194-259 TestNodeNum through test.Run([allocate.New(), backfill.New()])."""
+    from volcano_b200 import action, backfill
+    tc = G.predicates_node_num_case()
+    snap = tc.RegisterSession(G.predicates_node_num_tiers(), actions=("allocate", "backfill"))
+    tc.Run([action.New(), backfill.New()])
+    assert tc.CheckBind() is None, tc.CheckBind()
+    ref = oracle_engine(snap)
+    _assert_same(tc.result, ref)
+    _assert_same(tc.result.backfill, ref.backfill)
+
+
 def test_backfill_action_interface(gpu, oracle_engine):
     """test.Run([]framework.Action{allocate.New(), backfill.New()}) with the reference's default plugin set: BestEffort pods
     are bound next to the regular ones; unsupported configurations fail loudly."""

@@ -236,6 +236,16 @@ def test_allocate_with_network_topologies_soft(case, oracle_engine):
         assert tc.CheckBind() is None, tc.CheckBind()
 
 
+def test_predicates_node_num_allocate_then_backfill(oracle_engine):
+    """predicates_test.go:194-259 TestNodeNum: the pod-count cap seen by the backfill action."""
+    tc = G.predicates_node_num_case()
+    snap = tc.RegisterSession(G.predicates_node_num_tiers(), actions=("allocate", "backfill"))
+    assert snap.T == 0 and snap.B == 3
+    tc.Run(oracle_engine)
+    assert tc.CheckBind() is None, tc.CheckBind()
+    assert [snap.backfill_task_keys[t] for t in tc.result.backfill.fit_errors] == ["ns1/worker-3"]
+
+
 def test_backfill_pick_up_pending_tasks():
     """backfill_test.go:39-154 TestPickUpPendingTasks."""
     tc = G.backfill_pick_case()
