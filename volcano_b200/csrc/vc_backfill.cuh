@@ -32,6 +32,7 @@ struct BackfillParams {
                              // hypernode FullScore): state-independent; NULL when the plugin's map is empty
   int last_idx0;          // util.lastProcessedNodeIndex when the action starts (feasible-node sampling)
   int32_t *out_last_idx;  // [1] ... and when it ends
+  long long *prof;        // [4] phase cycles of CTA 0 (record + sweep, CTA fold, mailbox exchange, apply) or NULL
 };
 
 struct BfCtl {
@@ -42,10 +43,30 @@ struct BfCtl {
   unsigned seq;
   double w_score[32];
   int w_node[32], w_cnt[32], w_soft[32];
+  // run-ahead: verdict of this CTA's best node for the NEXT task, assuming the current task lands on it
+  int spec_node, spec_group, spec_flag;
+  double spec_order;
   // feasible-node sampling (same scheme as k_commit<.,.,.,SAMP>)
   int last_idx, samp_proc, samp_total, samp_prefA, samp_prefB;
   unsigned seq2;
   int samp_w[4][8][2];
+};
+
+// A node's row as it will look once task `t` has been added to it (Session.Allocate + the predicates plugin's
+// AllocateFunc): the same IEEE operations the owner thread applies, evaluated on the fly.
+struct SpecNodeView {
+  const SmemNodes &s;
+  int i;
+  const TaskRec &t;
+  bool k8s;  // predicates plugin registered: k8s requested sums move too
+  __device__ __forceinline__ double alloc(int d) const { return s.alloc[d * s.cap + i]; }
+  __device__ __forceinline__ double idle(int d) const { return s.idle[d * s.cap + i] - t.req[d]; }
+  __device__ __forceinline__ double used(int d) const { return s.used[d * s.cap + i] + t.req[d]; }
+  __device__ __forceinline__ double rel(int) const { return 0.0; }
+  __device__ __forceinline__ double pip(int) const { return 0.0; }
+  __device__ __forceinline__ double kalloc(int k) const { return s.kalloc[k * s.cap + i]; }
+  __device__ __forceinline__ double kreq(int k) const { return k8s ? s.kreq[k * s.cap + i] + t.kreq[k] : s.kreq[k * s.cap + i]; }
+  __device__ __forceinline__ double knz(int k) const { return k8s ? s.knz[k * s.cap + i] + t.knz[k] : s.knz[k * s.cap + i]; }
 };
 
 // SOFT: the full (four-unit) mailbox record: needed when nodeorder's TaintToleration batch score is live (normalised
@@ -98,7 +119,7 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
     sn.pod_count[i] = p.pod_count[n];
   }
   for (int i = tid; i < cap; i += blockDim.x) c_group[i] = -1;
-  if (tid == 0) { S.seq = 0; S.seq2 = 0; S.last_idx = b.last_idx0; }
+  if (tid == 0) { S.seq = 0; S.seq2 = 0; S.last_idx = b.last_idx0; S.spec_node = -1; }
   __syncthreads();
 
   const bool two_pass = SOFT && c.soft_active;
@@ -117,8 +138,12 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
     }
   };
   stage(0);
+  long long pf[4] = {0, 0, 0, 0}, pf_last = clock64();
+  const bool profiling = b.prof != nullptr && cta == 0 && tid == 0;
+#define BF_MARK(k) do { if (profiling) { const long long now_ = clock64(); pf[k] += now_ - pf_last; pf_last = now_; } } while (0)
   for (int pos = 0; pos < b.n; ++pos) {
     __syncthreads();  // record `pos` staged; the owner thread is done with record pos - 1
+    BF_MARK(3);
     stage(pos + 1);   // overwrites the buffer of pos - 1
     const TaskRec &trec = S.trec2[pos & 1];
     const int group = S.group2[pos & 1];
@@ -212,7 +237,36 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
       }
       local_warp_reduce<false>(mine);
       if (lane == 0) { S.w_score[warp] = mine.score[0]; S.w_node[warp] = mine.node[0]; S.w_cnt[warp] = mine.cnt[0]; S.w_soft[warp] = mine.soft[0]; }
+      BF_MARK(0);
       __syncthreads();
+      BF_MARK(1);
+      if (warp == 1 && !two_pass && !(SAMP && sampling)) {
+        // run-ahead while warp 0 sits in the mailbox: if this CTA's best node wins, the next sweep would have to
+        // re-evaluate exactly that node before anybody can publish - do it now, against the row as it will be
+        Local l;
+        local_init(l);
+        if (lane < nwarps) { l.score[0] = S.w_score[lane]; l.node[0] = S.w_node[lane]; }
+        local_warp_reduce<false>(l);
+        if (lane == 0) {
+          int sn_node = -1;
+          if (l.node[0] >= 0 && pos + 1 < b.n) {
+            const int i = l.node[0] - nbase;
+            const TaskRec &nt = S.trec2[(pos + 1) & 1];
+            const uint32_t cs = p.cstat[(size_t)nt.klass * N + nbase + i];
+            SpecNodeView nv{sn, i, trec, c.has_predicates != 0};
+            bool ok = (cs & CS_STATIC_OK) != 0;
+            if (c.pred_predicates && sn.max_tasks[i] <= sn.pod_count[i] + (c.has_predicates ? 1 : 0)) ok = false;
+            bool ho = false;
+            double od = 0.0;
+            if (ok) ho = node_order(c, R, K, nt, nv, cs, &od);
+            S.spec_group = S.group2[(pos + 1) & 1];
+            S.spec_flag = (ok ? 1 : 0) | (ho ? 2 : 0);
+            S.spec_order = od;
+            sn_node = l.node[0];
+          }
+          S.spec_node = sn_node;
+        }
+      }
       if (warp == 0) {
         Local l;
         local_init(l);
@@ -232,6 +286,7 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
         }
       }
       __syncthreads();
+      BF_MARK(2);
       g_soft = S.max_soft;
       if (S.cnt == 0) break;
     }
@@ -245,7 +300,11 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
     if (best >= nbase && best < nbase + nmine) {
       const int i = best - nbase;
       if ((i % blockDim.x) == tid) {
-        c_group[i] = -1;
+        if (nwarps > 1 && !two_pass && !(SAMP && sampling) && S.spec_node == best) {  // the run-ahead verdict is this row's
+          c_group[i] = S.spec_group; c_flag[i] = (uint8_t)S.spec_flag; c_order[i] = S.spec_order;
+        } else {
+          c_group[i] = -1;
+        }
         for (int d = 0; d < R; ++d) {
           sn.idle[d * cap + i] -= trec.req[d];
           sn.used[d * cap + i] += trec.req[d];
@@ -271,4 +330,7 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
     p.pod_count[n] = sn.pod_count[i];
   }
   if (cta == 0 && tid == 0) b.out_last_idx[0] = S.last_idx;
+  if (profiling)
+    for (int k = 0; k < 4; ++k) b.prof[k] = pf[k];
+#undef BF_MARK
 }

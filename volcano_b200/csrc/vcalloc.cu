@@ -1498,6 +1498,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   const size_t o_node = off; off += al(std::max<size_t>(n, 1) * 4);
   const size_t o_score = off; off += al(std::max<size_t>(n, 1) * 8);
   const size_t o_last = off; off += al(4);
+  const size_t o_prof = off; off += al(4 * 8);
   if (s->d_bf_bytes < off) {
     if (s->d_bf) cudaFree(s->d_bf);
     s->d_bf = nullptr; s->d_bf_bytes = 0;
@@ -1550,6 +1551,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
     bp.klass = reinterpret_cast<const int32_t *>(base + o_klass); bp.group = reinterpret_cast<const int32_t *>(base + o_group);
     bp.out_node = reinterpret_cast<int32_t *>(base + o_node); bp.out_score = reinterpret_cast<double *>(base + o_score);
     bp.nta_static = nta_static.empty() ? nullptr : reinterpret_cast<const double *>(base + o_nta);
+    bp.prof = getenv("VC_PROF") ? reinterpret_cast<long long *>(base + o_prof) : nullptr;
     bp.last_idx0 = s->last_idx_cur; bp.out_last_idx = reinterpret_cast<int32_t *>(base + o_last);
     const void *kfn = s->dc.to_find > 0 ? (const void *)k_backfill<true, true>
                     : s->dc.soft_active ? (const void *)k_backfill<true> : (const void *)k_backfill<false>;
@@ -1567,6 +1569,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
     if ((e = cudaMemcpyAsync(h_node.data(), base + o_node, n * 4, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
     if ((e = cudaMemcpyAsync(h_score.data(), base + o_score, n * 8, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
     if ((e = cudaMemcpyAsync(&h_last, base + o_last, 4, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
+    if (bp.prof && (e = cudaMemcpyAsync(r->stats.prof_cycles, base + o_prof, 4 * 8, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
   }
   if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return bail(e, "backfill kernel");
   if (n > 0) cudaEventElapsedTime(&kms, s->ev0, s->ev1);
