@@ -13,9 +13,12 @@ e = engine.Engine(snap)
 e.upload()
 for _ in range(2):
     e.allocate()
-    r = e.backfill()
-pc = r.stats["prof_cycles"][:4]
+    r = e.backfill()  # libvcalloc prints two more sums on stderr: divide by the bystander / republisher step counts below
+pc = r.stats["prof_cycles"][:8]
 n = max(1, r.stats["n_steps"])
-print(f"{cfg}: {r.stats['commit_ms']:.2f} ms, {n} tasks; cycles/task: sweep {pc[0]/n:.0f}, fold barrier {pc[1]/n:.0f}, "
-      f"mailbox {pc[2]/n:.0f}, apply+top barrier {pc[3]/n:.0f}")
+n_full, n_own = max(1, pc[1]), max(1, pc[3])
+n_other = max(1, n - pc[1] - pc[3])
+print(f"{cfg}: {r.stats['commit_ms']:.2f} ms, {n} tasks ({pc[1]} gather steps, CTA 0 republished in {pc[3]}); cycles per step of its kind: "
+      f"gather sweep {pc[0]/n_full:.0f}, all-gather {pc[4]/n_full:.0f}; republisher sweep {pc[2]/n_own:.0f}, fold+publish {pc[6]/n_own:.0f}; "
+      f"bystander poll {pc[5]/n_other:.0f} ({n_other} steps); apply+barriers per task {pc[7]/n:.0f}")
 e.close()

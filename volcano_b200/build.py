@@ -7,7 +7,6 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvcalloc.so")
-SOURCES = ["vcalloc.cu", "vc_commit.cuh", "vc_kernels.cuh", "vc_device.cuh", "vc_host.hpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -16,7 +15,8 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES] + [os.path.join(HERE, "..", "include", "vcalloc.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h"))]  # every source
+    deps.append(os.path.join(HERE, "..", "include", "vcalloc.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -11,9 +11,15 @@
 // The node axis is partitioned exactly as in k_commit (same CTA count, same shared-memory node slices, read from and
 // written back to the working copies the allocate action left in HBM). A per-node verdict cache keyed by the task's
 // (class, request) group makes a sweep re-evaluate only the node the previous placement touched.
-// Bound: latency (one L2 mailbox round trip per task), like k_commit.
+// While consecutive tasks share their (class, request) group, only the CTA that received the previous placement can have
+// a different local best: every CTA keeps the table of all CTAs' last records, the previous owner alone re-sweeps and
+// publishes one record through a small ring, the others poll that one slot and fold the table (the full all-gather
+// runs on a group switch and every 24 publications, which also bounds the ring).
+// Bound: latency (one L2 round trip per task), like k_commit.
 #pragma once
 #include "vc_commit.cuh"
+
+#define BF_REPL 8  // copies of a single-CTA publication (one 256-byte line each)
 
 struct BackfillParams {
   int n;                  // tasks in pick order
@@ -30,22 +36,32 @@ struct BackfillParams {
   const double *nta_static;  // [N] network-topology-aware entry of a pod WITHOUT a network topology whose request touches
                              // no weighted hypernode-binpack resource (every hypernode scores 0, a tier without a
                              // hypernode FullScore): state-independent; NULL when the plugin's map is empty
+  int spec_depth;         // run-ahead depth: 32 when every quantity involved is integer-valued (row - m * request is then
+                          // exactly what m successive placements leave), else 1
   int last_idx0;          // util.lastProcessedNodeIndex when the action starts (feasible-node sampling)
   int32_t *out_last_idx;  // [1] ... and when it ends
-  long long *prof;        // [4] phase cycles of CTA 0 (record + sweep, CTA fold, mailbox exchange, apply) or NULL
+  long long *prof;        // [10] phase cycles of CTA 0 or NULL: sweep in gather steps, #gather steps, sweep as the republishing
+                          // CTA, #such steps, mailbox all-gather, single-slot poll, fold + publish as republisher, apply + barriers
 };
 
 struct BfCtl {
-  TaskRec trec2[2];  // double-buffered: the record of task pos+1 is fetched while task pos is swept / exchanged
-  int group2[2];
+  TaskRec trec2[3];  // ring of three: the record of task pos+2 is fetched while task pos waits in the mailbox, so that
+  int group2[3];     // neither the sweep nor the run-ahead (which reads record pos+1) ever waits for a global load
   int cnt, best_node, max_soft;
   double best_score;
   unsigned seq;
   double w_score[32];
   int w_node[32], w_cnt[32], w_soft[32];
+  // single-publisher steps: group the CTA table describes, CTA whose row changed in the previous step (-1 none),
+  // publications since the last all-gather / so far
+  int tb_group, prev_owner, since_sync;
+  unsigned pc;
   // run-ahead: verdict of this CTA's best node for the NEXT task, assuming the current task lands on it
-  int spec_node, spec_group, spec_flag;
-  double spec_order;
+  // ... and for up to 32 further placements of the same group on it (lane m-1 evaluates the row after m pods):
+  // entry spec_k is the next unused one
+  int spec_node, spec_group, spec_pgroup, spec_k;
+  int spec_flag[32];
+  double spec_order[32];
   // feasible-node sampling (same scheme as k_commit<.,.,.,SAMP>)
   int last_idx, samp_proc, samp_total, samp_prefA, samp_prefB;
   unsigned seq2;
@@ -59,15 +75,35 @@ struct SpecNodeView {
   int i;
   const TaskRec &t;
   bool k8s;  // predicates plugin registered: k8s requested sums move too
+  double m;  // pods added (1.0: bit-identical to one application for any input; > 1 only with integer-valued quantities)
   __device__ __forceinline__ double alloc(int d) const { return s.alloc[d * s.cap + i]; }
-  __device__ __forceinline__ double idle(int d) const { return s.idle[d * s.cap + i] - t.req[d]; }
-  __device__ __forceinline__ double used(int d) const { return s.used[d * s.cap + i] + t.req[d]; }
+  __device__ __forceinline__ double idle(int d) const { return s.idle[d * s.cap + i] - m * t.req[d]; }
+  __device__ __forceinline__ double used(int d) const { return s.used[d * s.cap + i] + m * t.req[d]; }
   __device__ __forceinline__ double rel(int) const { return 0.0; }
   __device__ __forceinline__ double pip(int) const { return 0.0; }
   __device__ __forceinline__ double kalloc(int k) const { return s.kalloc[k * s.cap + i]; }
-  __device__ __forceinline__ double kreq(int k) const { return k8s ? s.kreq[k * s.cap + i] + t.kreq[k] : s.kreq[k * s.cap + i]; }
-  __device__ __forceinline__ double knz(int k) const { return k8s ? s.knz[k * s.cap + i] + t.knz[k] : s.knz[k * s.cap + i]; }
+  __device__ __forceinline__ double kreq(int k) const { return k8s ? s.kreq[k * s.cap + i] + m * t.kreq[k] : s.kreq[k * s.cap + i]; }
+  __device__ __forceinline__ double knz(int k) const { return k8s ? s.knz[k * s.cap + i] + m * t.knz[k] : s.knz[k * s.cap + i]; }
 };
+
+// Warp arg-max of (score, node) with the canonical tie-break plus the candidate count, for the one-category record of
+// the plain instance: four hardware reductions instead of the eight of local_warp_reduce (no soft-taint maximum, no
+// topology pair, no sampling position). Measured on B200: every warp-wide collective on this path costs ~300 cycles
+// (a 20-shuffle butterfly 5.6 k, the eight-op version 2.4 k), and three reductions sit on the per-task critical path.
+__device__ __forceinline__ void simple_warp_reduce(Local &l) {
+  constexpr unsigned FULLM = 0xffffffffu;
+  const bool valid = l.node[0] >= 0;
+  const unsigned long long key = valid ? score_key(l.score[0]) : 0ull;
+  const unsigned hi = (unsigned)(key >> 32);
+  const unsigned mhi = __reduce_max_sync(FULLM, hi);
+  const unsigned lo = hi == mhi ? (unsigned)key : 0u;
+  const unsigned mlo = __reduce_max_sync(FULLM, lo);
+  const unsigned long long mkey = ((unsigned long long)mhi << 32) | mlo;
+  const unsigned mnode = __reduce_min_sync(FULLM, (valid && key == mkey) ? (unsigned)l.node[0] : 0xffffffffu);
+  if (mnode == 0xffffffffu) { l.node[0] = -1; l.score[0] = 0.0; }
+  else { l.node[0] = (int)mnode; l.score[0] = score_of_key(mkey); }
+  l.cnt[0] = (int)__reduce_add_sync(FULLM, (unsigned)l.cnt[0]);
+}
 
 // SOFT: the full (four-unit) mailbox record: needed when nodeorder's TaintToleration batch score is live (normalised
 //       over the candidate set: two passes per task) and by SAMP
@@ -101,7 +137,11 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
   double *c_order = reinterpret_cast<double *>(sp); sp += (size_t)cap * 8;   // verdict cache: NodeOrderFn sum,
   int32_t *c_group = reinterpret_cast<int32_t *>(sp); sp += (size_t)cap * 4;  // the group it was computed for,
   uint8_t *c_flag = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;       // bit0 feasible, bit1 has order score
-  uint8_t *s_samp = reinterpret_cast<uint8_t *>(sp);                          // sampling: 1 = candidate
+  uint8_t *s_samp = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;       // sampling: 1 = candidate
+  sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 7) & ~(uintptr_t)7);
+  double *tb_score = reinterpret_cast<double *>(sp); sp += (size_t)p.n_cta * 8;  // last record of every CTA for tb_group
+  int *tb_node = reinterpret_cast<int *>(sp); sp += (size_t)p.n_cta * 4;
+  int *tb_cnt = reinterpret_cast<int *>(sp);
 
   for (int i = tid; i < nmine; i += blockDim.x) {
     const int n = nbase + i;
@@ -119,7 +159,7 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
     sn.pod_count[i] = p.pod_count[n];
   }
   for (int i = tid; i < cap; i += blockDim.x) c_group[i] = -1;
-  if (tid == 0) { S.seq = 0; S.seq2 = 0; S.last_idx = b.last_idx0; S.spec_node = -1; }
+  if (tid == 0) { S.seq = 0; S.seq2 = 0; S.last_idx = b.last_idx0; S.spec_node = -1; S.tb_group = -1; S.prev_owner = -1; S.since_sync = 0; S.pc = 0; }
   __syncthreads();
 
   const bool two_pass = SOFT && c.soft_active;
@@ -127,26 +167,27 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
   auto stage = [&](int pos) {
     if (pos >= b.n || warp != nwarps - 1) return;
     const int t = b.order[pos];
-    TaskRec &r = S.trec2[pos & 1];
+    TaskRec &r = S.trec2[pos % 3];
     if (lane < R) r.req[lane] = b.req[(size_t)lane * b.B + t];
     if (lane < K) r.kreq[lane] = b.kreq[(size_t)lane * b.B + t];
     if (lane < 2) r.knz[lane] = b.knz[(size_t)lane * b.B + t];
     if (lane == 31) {
       r.has = b.has[t];
       r.klass = b.klass[t];
-      S.group2[pos & 1] = b.group[t];
+      S.group2[pos % 3] = b.group[t];
     }
   };
   stage(0);
-  long long pf[4] = {0, 0, 0, 0}, pf_last = clock64();
+  stage(1);
+  long long pf[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pf_last = clock64();
   const bool profiling = b.prof != nullptr && cta == 0 && tid == 0;
 #define BF_MARK(k) do { if (profiling) { const long long now_ = clock64(); pf[k] += now_ - pf_last; pf_last = now_; } } while (0)
   for (int pos = 0; pos < b.n; ++pos) {
-    __syncthreads();  // record `pos` staged; the owner thread is done with record pos - 1
-    BF_MARK(3);
-    stage(pos + 1);   // overwrites the buffer of pos - 1
-    const TaskRec &trec = S.trec2[pos & 1];
-    const int group = S.group2[pos & 1];
+    __syncthreads();  // records `pos`, `pos + 1` staged; the owner thread is done with record pos - 1
+    BF_MARK(7);
+    const long long t_top = profiling ? clock64() : 0;
+    const TaskRec &trec = S.trec2[pos % 3];
+    const int group = S.group2[pos % 3];
     const uint32_t *cs_row = p.cstat + (size_t)trec.klass * N + nbase;
     int g_soft = 0;
     // cached or fresh (feasible, NodeOrderFn sum) of node i for the staged group
@@ -164,6 +205,10 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
       c_group[i] = group; c_flag[i] = (uint8_t)((*ok ? 1 : 0) | (*has_order ? 2 : 0)); c_order[i] = *order;
     };
     const bool sampling = SAMP && c.to_find > 0;
+    // single-publisher step? (uniform over the grid: it only depends on replicated state)
+    const bool tracked = !SOFT && !SAMP;
+    const bool full = !tracked || S.tb_group != group || S.since_sync >= 24;
+    const bool sweeping = full || cta == S.prev_owner;
     if (SAMP && sampling) {
       const int start = S.last_idx, Kf = c.to_find;
       const int rows = (cap + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -217,7 +262,7 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
     for (int pass = 0; pass < (two_pass ? 2 : 1); ++pass) {
       Local mine;
       local_init(mine);
-      for (int i = tid; i < nmine; i += blockDim.x) {
+      for (int i = tid; sweeping && i < nmine; i += blockDim.x) {
         const uint32_t cs = (two_pass || c_group[i] != group) ? cs_row[i] : 0u;
         if (SAMP && sampling && s_samp[i] != 1) continue;  // outside the sampled candidate set
         bool ok, has_order;
@@ -235,49 +280,114 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
         const double sc = total_score(c, has_order, order, soft, g_soft, nta);
         if (mine.node[0] < 0 || better(sc, n, mine.score[0], mine.node[0])) { mine.score[0] = sc; mine.node[0] = n; }
       }
-      local_warp_reduce<false>(mine);
-      if (lane == 0) { S.w_score[warp] = mine.score[0]; S.w_node[warp] = mine.node[0]; S.w_cnt[warp] = mine.cnt[0]; S.w_soft[warp] = mine.soft[0]; }
-      BF_MARK(0);
+      if (sweeping) {
+        if (SOFT) local_warp_reduce<false>(mine); else simple_warp_reduce(mine);
+        if (lane == 0) { S.w_score[warp] = mine.score[0]; S.w_node[warp] = mine.node[0]; S.w_cnt[warp] = mine.cnt[0]; S.w_soft[warp] = mine.soft[0]; }
+      }
+      if (profiling && sweeping) { pf[full ? 1 : 3] += 1; }
+      BF_MARK(full ? 0 : (sweeping ? 2 : 7));
       __syncthreads();
-      BF_MARK(1);
+      if (pass == 0) stage(pos + 2);  // into the buffer of pos - 1, while the mailbox is being waited on
       if (warp == 1 && !two_pass && !(SAMP && sampling)) {
         // run-ahead while warp 0 sits in the mailbox: if this CTA's best node wins, the next sweep would have to
         // re-evaluate exactly that node before anybody can publish - do it now, against the row as it will be
         Local l;
         local_init(l);
-        if (lane < nwarps) { l.score[0] = S.w_score[lane]; l.node[0] = S.w_node[lane]; }
-        local_warp_reduce<false>(l);
-        if (lane == 0) {
-          int sn_node = -1;
-          if (l.node[0] >= 0 && pos + 1 < b.n) {
+        bool go = true;
+        if (sweeping) {
+          if (lane < nwarps) { l.score[0] = S.w_score[lane]; l.node[0] = S.w_node[lane]; }
+          if (SOFT) local_warp_reduce<false>(l); else simple_warp_reduce(l);
+        } else {
+          l.node[0] = tb_node[cta];  // unchanged since this CTA last published
+          l.score[0] = tb_score[cta];
+        }
+        // The verdict depends on (node row, group of the pod added, group evaluated), not on the task index: once
+        // computed for the CTA's best node it stays valid until that node changes, i.e. until this CTA wins - so a CTA
+        // pays for it once, long before its turn, and the winner's next sweep is cache hits only.
+        const int group_next = pos + 1 < b.n ? S.group2[(pos + 1) % 3] : -1;
+        const int depth = b.spec_depth;
+        go = group_next == group &&
+             !(S.spec_node == l.node[0] && S.spec_pgroup == group && S.spec_group == group_next && S.spec_k < depth);
+        if (go) {
+          if (l.node[0] >= 0) {
             const int i = l.node[0] - nbase;
-            const TaskRec &nt = S.trec2[(pos + 1) & 1];
+            const TaskRec &nt = S.trec2[(pos + 1) % 3];
             const uint32_t cs = p.cstat[(size_t)nt.klass * N + nbase + i];
-            SpecNodeView nv{sn, i, trec, c.has_predicates != 0};
-            bool ok = (cs & CS_STATIC_OK) != 0;
-            if (c.pred_predicates && sn.max_tasks[i] <= sn.pod_count[i] + (c.has_predicates ? 1 : 0)) ok = false;
-            bool ho = false;
-            double od = 0.0;
-            if (ok) ho = node_order(c, R, K, nt, nv, cs, &od);
-            S.spec_group = S.group2[(pos + 1) & 1];
-            S.spec_flag = (ok ? 1 : 0) | (ho ? 2 : 0);
-            S.spec_order = od;
-            sn_node = l.node[0];
+            if (lane < depth) {
+              SpecNodeView nv{sn, i, trec, c.has_predicates != 0, (double)(lane + 1)};
+              bool ok = (cs & CS_STATIC_OK) != 0;
+              if (c.pred_predicates && sn.max_tasks[i] <= sn.pod_count[i] + (c.has_predicates ? lane + 1 : 0)) ok = false;
+              bool ho = false;
+              double od = 0.0;
+              if (ok) ho = node_order(c, R, K, nt, nv, cs, &od);
+              S.spec_flag[lane] = (ok ? 1 : 0) | (ho ? 2 : 0);
+              S.spec_order[lane] = od;
+            }
+            __syncwarp();
+            if (lane == 0) { S.spec_group = group_next; S.spec_pgroup = group; S.spec_k = 0; S.spec_node = l.node[0]; }
+          } else if (lane == 0) {
+            S.spec_node = -1;
           }
-          S.spec_node = sn_node;
         }
       }
       if (warp == 0) {
         Local l;
         local_init(l);
-        if (lane < nwarps) { l.score[0] = S.w_score[lane]; l.node[0] = S.w_node[lane]; l.cnt[0] = S.w_cnt[lane]; l.soft[0] = S.w_soft[lane]; }
-        local_warp_reduce<false>(l);
+        if (sweeping) {
+          if (lane < nwarps) { l.score[0] = S.w_score[lane]; l.node[0] = S.w_node[lane]; l.cnt[0] = S.w_cnt[lane]; l.soft[0] = S.w_soft[lane]; }
+          if (SOFT) local_warp_reduce<false>(l); else simple_warp_reduce(l);
+        }
         if (SAMP && sampling) l.proc = S.samp_proc;
         const unsigned seq = S.seq + 1;
-        __syncwarp();  // every lane has read S.seq before lane 0 advances it
-        const Local g = exchange<SOFT>(p, l, seq);
+        const unsigned pc = S.pc;
+        const int prev_owner = S.prev_owner;
+        __syncwarp();  // every lane has read S.seq / S.pc before lane 0 advances them
+        Local g;
+        if (full) {
+          g = tracked ? exchange<SOFT>(p, l, seq, tb_score, tb_node, tb_cnt) : exchange<SOFT>(p, l, seq);
+        } else {
+          if (prev_owner >= 0) {  // one row changed since the table was current: its owner publishes, the others read
+            // BF_REPL copies of the record in different lines: a single line polled by every CTA is a hot spot that
+            // holds the publishing store back
+            uint4 *slot = p.mbox2 + (size_t)(pc & 63u) * BF_REPL * MBOX_STRIDE;
+            const unsigned tag = pc + 1;
+            if (cta == prev_owner) {
+              if (lane < BF_REPL) {
+                const unsigned long long sb = (unsigned long long)__double_as_longlong(l.score[0]);
+                mbox_store(slot + (size_t)lane * MBOX_STRIDE,
+                           make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)l.node[0], (tag << 2) | (unsigned)min(l.cnt[0], 2)));
+              }
+              if (lane == 0) { tb_score[cta] = l.score[0]; tb_node[cta] = l.node[0]; tb_cnt[cta] = min(l.cnt[0], 2); }
+              if (profiling) pf[9] += clock64() - t_top;  // top barrier -> record on its way
+            } else if (lane == 0) {
+              uint4 v;
+              const uint4 *mine_slot = slot + (size_t)(cta % BF_REPL) * MBOX_STRIDE;
+              do { v = mbox_load(mine_slot); } while ((v.w >> 2) != (tag & 0x3fffffffu));
+              if (profiling) pf[8] += clock64() - t_top;  // top barrier -> record seen
+              tb_score[prev_owner] = __longlong_as_double((long long)((unsigned long long)v.x | ((unsigned long long)v.y << 32)));
+              tb_node[prev_owner] = (int)v.z;
+              tb_cnt[prev_owner] = (int)(v.w & 3u);
+            }
+            __syncwarp();
+          }
+          local_init(g);
+          for (int k = lane; k < p.n_cta; k += 32) {
+            Local o;
+            local_init(o);
+            o.score[0] = tb_score[k]; o.node[0] = tb_node[k]; o.cnt[0] = tb_cnt[k];
+            local_fold(g, o);
+          }
+          simple_warp_reduce(g);
+          g.cnt[0] = min(g.cnt[0], 2);
+        }
         if (lane == 0) {
-          S.seq = seq;
+          if (full) S.seq = seq;
+          if (tracked) {
+            S.tb_group = group;
+            if (full) S.since_sync = 0;
+            else if (prev_owner >= 0) { S.since_sync += 1; S.pc = pc + 1; }
+            S.prev_owner = g.cnt[0] > 0 ? (g.node[0] - p.d.node_begin) / p.npc : -1;
+          }
           S.cnt = g.cnt[0]; S.best_node = g.node[0]; S.best_score = g.score[0]; S.max_soft = g.soft[0];
           if (SAMP && sampling && pass == (two_pass ? 1 : 0)) {  // lastProcessedNodeIndex = (start + processedNodes) % N
             const int processed = S.samp_total >= c.to_find ? g.proc : N;
@@ -286,7 +396,7 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
         }
       }
       __syncthreads();
-      BF_MARK(2);
+      BF_MARK(full ? 4 : (sweeping ? 6 : 5));
       g_soft = S.max_soft;
       if (S.cnt == 0) break;
     }
@@ -300,10 +410,14 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
     if (best >= nbase && best < nbase + nmine) {
       const int i = best - nbase;
       if ((i % blockDim.x) == tid) {
-        if (nwarps > 1 && !two_pass && !(SAMP && sampling) && S.spec_node == best) {  // the run-ahead verdict is this row's
-          c_group[i] = S.spec_group; c_flag[i] = (uint8_t)S.spec_flag; c_order[i] = S.spec_order;
+        if (nwarps > 1 && !two_pass && !(SAMP && sampling) && S.spec_node == best && S.spec_pgroup == group &&
+            S.spec_k < b.spec_depth) {  // the run-ahead verdict of this row after one more pod of this group
+          const int k = S.spec_k;
+          c_group[i] = S.spec_group; c_flag[i] = (uint8_t)S.spec_flag[k]; c_order[i] = S.spec_order[k];
+          S.spec_k = k + 1;
         } else {
           c_group[i] = -1;
+          S.spec_node = -1;  // the row changes in a way the run-ahead did not assume
         }
         for (int d = 0; d < R; ++d) {
           sn.idle[d * cap + i] -= trec.req[d];
@@ -331,6 +445,6 @@ __global__ void __launch_bounds__(256, 1) k_backfill(K2Params p, BackfillParams 
   }
   if (cta == 0 && tid == 0) b.out_last_idx[0] = S.last_idx;
   if (profiling)
-    for (int k = 0; k < 4; ++k) b.prof[k] = pf[k];
+    for (int k = 0; k < 10; ++k) b.prof[k] = pf[k];
 #undef BF_MARK
 }

@@ -282,8 +282,11 @@ __device__ __forceinline__ void local_warp_reduce(Local &l) {
 //   FULL = true : four units {score0,node0,seq} {score1,node1,seq} {cnt0,cnt1,soft0|soft1<<8|tk0<<16|tk1<<24,seq}
 //                 {sampling: processed position,0,0,seq}
 #define MBOX_STRIDE 16  // uint4 per slot = 256 bytes
+// tb_* (optional, category 0 only): every CTA's record is also kept, indexed by CTA, for callers that afterwards
+// track single-CTA changes instead of gathering again (k_backfill).
 template <bool FULL>
-__device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigned seq) {
+__device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigned seq, double *tb_score = nullptr,
+                                          int *tb_node = nullptr, int *tb_cnt = nullptr) {
   const int lane = threadIdx.x & 31;
   const int G = p.n_cta;
   uint4 *base = p.mbox + (size_t)(seq & 1u) * G * MBOX_STRIDE;
@@ -342,6 +345,10 @@ __device__ __forceinline__ Local exchange(const K2Params &p, Local mine, unsigne
           o.proc = (int)e[k].x;
         } else {
           o.cnt[0] = (int)(a[k].w & 3u);
+        }
+        if (tb_score) {
+          const int slot = s0 + k * 32 + lane;
+          tb_score[slot] = o.score[0]; tb_node[slot] = o.node[0]; tb_cnt[slot] = o.cnt[0];
         }
         local_fold(acc, o);
         need[k] = false;

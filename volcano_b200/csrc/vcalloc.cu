@@ -205,6 +205,7 @@ struct vc_snapshot {
   std::vector<vc_decision> last_dec;  // operations of the last vc_allocate_run (kept visits only)
   bool alloc_ran = false, bf_ran = false;
   int last_idx_cur = 0;   // util.lastProcessedNodeIndex as the last action of the cycle left it
+  bool rows_integral = false;  // every quantity a placement adds to / subtracts from a node row is integer-valued
   void *d_bf = nullptr;   // device slab of the backfill inputs / outputs
   size_t d_bf_bytes = 0;
 };
@@ -1041,6 +1042,17 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     k.j_valid.resize(J);
     for (size_t j = 0; j < J; ++j) k.j_valid[j] = vch::job_valid(*conf, *jb, (int)j) ? 1 : 0;
     k.j_alloc0.assign(jb->allocated, jb->allocated + R * J);
+    // milli-units / bytes / counts are integers by construction (Quantity.MilliValue / Value); when that holds for the
+    // rows and every request, m placements leave exactly row -/+ m * request and k_backfill may run ahead m steps
+    auto integral = [](const double *v, size_t n) {
+      for (size_t i = 0; i < n; ++i)
+        if (!(std::fabs(v[i]) < 4e15) || v[i] != std::floor(v[i])) return false;
+      return true;
+    };
+    s->rows_integral = integral(nd->idle, R * N) && integral(nd->used, R * N) && integral(nd->k8s_requested, K * N) &&
+                       integral(nd->k8s_nonzero_requested, 2 * N) && integral(tk->resreq, R * T) && integral(tk->k8s_req, K * T) &&
+                       integral(tk->k8s_nonzero_req, 2 * T) && integral(s->bf.req.data(), s->bf.req.size()) &&
+                       integral(s->bf.kreq.data(), s->bf.kreq.size()) && integral(s->bf.knz.data(), s->bf.knz.size());
     for (int t = 0; t < s->bf.n; ++t) {
       if (s->bf.job[t] < 0 || (size_t)s->bf.job[t] >= J) return fail(VC_EINVAL, "backfill task %d: bad job index", t);
       if (s->bf.klass[t] < 0 || (size_t)s->bf.klass[t] >= C) return fail(VC_EINVAL, "backfill task %d: bad class index", t);
@@ -1498,7 +1510,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   const size_t o_node = off; off += al(std::max<size_t>(n, 1) * 4);
   const size_t o_score = off; off += al(std::max<size_t>(n, 1) * 8);
   const size_t o_last = off; off += al(4);
-  const size_t o_prof = off; off += al(4 * 8);
+  const size_t o_prof = off; off += al(10 * 8);
   if (s->d_bf_bytes < off) {
     if (s->d_bf) cudaFree(s->d_bf);
     s->d_bf = nullptr; s->d_bf_bytes = 0;
@@ -1529,6 +1541,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   std::vector<int32_t> h_node(n, -1);
   std::vector<double> h_score(n, 0.0);
   int32_t h_last = s->last_idx_cur;
+  long long h_prof[10] = {0};
   if (n > 0) {
     const int G = s->n_cta;
     const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024 * 2;
@@ -1552,11 +1565,12 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
     bp.out_node = reinterpret_cast<int32_t *>(base + o_node); bp.out_score = reinterpret_cast<double *>(base + o_score);
     bp.nta_static = nta_static.empty() ? nullptr : reinterpret_cast<const double *>(base + o_nta);
     bp.prof = getenv("VC_PROF") ? reinterpret_cast<long long *>(base + o_prof) : nullptr;
+    bp.spec_depth = (s->rows_integral && !getenv("VC_BACKFILL_DEPTH1")) ? 32 : 1;
     bp.last_idx0 = s->last_idx_cur; bp.out_last_idx = reinterpret_cast<int32_t *>(base + o_last);
     const void *kfn = s->dc.to_find > 0 ? (const void *)k_backfill<true, true>
                     : s->dc.soft_active ? (const void *)k_backfill<true> : (const void *)k_backfill<false>;
     const size_t smem = ((sizeof(BfCtl) + 15) & ~(size_t)15) + (3 * R + 2 * K + 2) * (size_t)s->npc * 8 +
-                        (size_t)s->npc * (4 + 4) + 8 + (size_t)s->npc * (8 + 4 + 1 + 1) + 64;
+                        (size_t)s->npc * (4 + 4) + 8 + (size_t)s->npc * (8 + 4 + 1 + 1) + 8 + (size_t)G * (8 + 4 + 4) + 64;
     if ((e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return bail(e, "backfill smem");
     int max_blocks = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, kfn, s->block, smem)) != cudaSuccess) return bail(e, "occupancy");
@@ -1569,10 +1583,14 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
     if ((e = cudaMemcpyAsync(h_node.data(), base + o_node, n * 4, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
     if ((e = cudaMemcpyAsync(h_score.data(), base + o_score, n * 8, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
     if ((e = cudaMemcpyAsync(&h_last, base + o_last, 4, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
-    if (bp.prof && (e = cudaMemcpyAsync(r->stats.prof_cycles, base + o_prof, 4 * 8, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
+    if (bp.prof && (e = cudaMemcpyAsync(h_prof, base + o_prof, 10 * 8, cudaMemcpyDeviceToHost, s->stream)) != cudaSuccess) return bail(e, "backfill D2H");
   }
   if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return bail(e, "backfill kernel");
   if (n > 0) cudaEventElapsedTime(&kms, s->ev0, s->ev1);
+  for (int k = 0; k < 8; ++k) r->stats.prof_cycles[k] = h_prof[k];
+  if (getenv("VC_PROF") && n > 0)
+    fprintf(stderr, "k_backfill CTA 0: top barrier -> record seen (bystander, summed) %lld cycles, top barrier -> record sent "
+                    "(republisher, summed) %lld cycles\n", h_prof[8], h_prof[9]);
   s->bf_ran = true;
   if (s->dc.to_find > 0) s->last_idx_cur = h_last;
   r->stats.last_processed_node_index = s->last_idx_cur;
