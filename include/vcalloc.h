@@ -332,7 +332,8 @@ int vc_snapshot_set_topology(vc_snapshot *s, const vc_hypernodes *topo);
    api/job_info.go:188: Resreq empty but for pods:1; not scheduling-gated) — the tasks the backfill action
    places (backfill.go:140-151). Same SoA as vc_tasks with its own index space [0, n_tasks); job / klass / role
    index the session's job, class and role tables; uid_rank ranks within this list. They are NOT part of
-   vc_dims.n_tasks (allocate skips them, allocate.go:255-271) but stay counted in vc_jobs.pending_besteffort. */
+   vc_dims.n_tasks (allocate skips them, allocate.go:255-271) but stay counted in vc_jobs.pending_besteffort. The list is
+   copied; it stays in effect for later uploads of this snapshot until replaced (n_tasks = 0 clears it). */
 int vc_snapshot_set_backfill(vc_snapshot *s, int32_t n_tasks, const vc_tasks *tasks);
 
 /* Restrict the node axis of this process to [node_begin, node_end) for node-sharded

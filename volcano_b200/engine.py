@@ -84,9 +84,8 @@ class Engine:
         topo = s.topology()
         if topo is not None:
             _check(self.L.vc_snapshot_set_topology(self.h, C.byref(topo)))
-        bt = s.backfill_tasks()
-        if bt is not None:
-            _check(self.L.vc_snapshot_set_backfill(self.h, s.B, C.byref(bt)))
+        bt = s.backfill_tasks()  # the list stays in effect until replaced: always (re)state it, an empty one clears it
+        _check(self.L.vc_snapshot_set_backfill(self.h, s.B, C.byref(bt) if bt is not None else None))
         _check(self.L.vc_snapshot_upload(self.h, C.byref(n), C.byref(t), C.byref(c), C.byref(j), C.byref(q),
                                          C.byref(s.conf)))
         self._uploaded = True
