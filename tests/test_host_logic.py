@@ -37,6 +37,9 @@ def shim():
                                      C.POINTER(abi.vc_queues), _dp, _dp]
     L.vh_task_heap_order.argtypes = [C.POINTER(abi.vc_tasks), C.c_int, _i32p, C.c_int]
     L.vh_less_equal_zero.argtypes = [_dp, C.c_uint32, _dp, C.c_uint32, C.c_int]
+    L.vh_backfill_pick.argtypes = [C.POINTER(abi.vc_dims), C.POINTER(abi.vc_conf), C.POINTER(abi.vc_nodes), C.POINTER(abi.vc_tasks),
+                                   C.POINTER(abi.vc_jobs), C.POINTER(abi.vc_queues), C.POINTER(abi.vc_tasks), C.c_int,
+                                   C.POINTER(abi.vc_decision), C.c_int, _i32p]
     return L
 
 
@@ -202,3 +205,43 @@ def test_job_valid_gang(shim):
     # 2 < minAvailable 3; 3 >= 3; enough tasks but role "w" has none against its minimum 1 (CheckTaskValid,
     # job_info.go:993-1019); MinAvailable 1 < sum of the role minima 2: the role check is skipped
     assert got == [0, 1, 0, 1]
+
+
+def _pick_vs_oracle(shim, snap):
+    o = OracleSession(snap)
+    dec, vis, fe = o.allocate()
+    want = o.backfill_pick_order()  # on the state allocate left
+    o.close()
+    d, n, t, j, q, bt = snap.dims(), snap.nodes(), snap.tasks(), snap.jobs(), snap.queues(), snap.backfill_tasks()
+    ops = np.ascontiguousarray(dec)
+    out = np.zeros(max(snap.B, 1), np.int32)
+    got_n = shim.vh_backfill_pick(C.byref(d), C.byref(snap.conf), C.byref(n), C.byref(t), C.byref(j), C.byref(q), C.byref(bt),
+                                  snap.B, ops.ctypes.data_as(C.POINTER(abi.vc_decision)), len(ops), out.ctypes.data_as(_i32p))
+    assert list(out[:got_n]) == list(want)
+    return got_n
+
+
+@pytest.mark.parametrize("cfg,seed", [("tiny_bf", None), ("tiny_bf", 5), ("small_bf", None), ("small_soft_bf", 3)])
+def test_backfill_pick_order_matches_the_oracle(shim, cfg, seed):
+    """pickUpPendingTasks (backfill.go:118-199) as vc_backfill_run computes it on the host - session state rebuilt from
+    allocate's operation list, queues / jobs / tasks in Go-heap pop order - against the oracle, which walks its own live
+    session after its own allocate pass."""
+    snap = make_snapshot(cfg, seed)
+    assert _pick_vs_oracle(shim, snap) == snap.B
+
+
+def test_backfill_pick_order_on_api_level_clusters(shim):
+    spec = importlib.util.spec_from_file_location("fuzz_api", os.path.join(HERE, "..", "tools", "fuzz_api.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    checked = picked = 0
+    for seed in range(500, 700):
+        tc, tiers, actions = mod.make_case(seed)
+        if not tiers or "backfill" not in actions:
+            continue
+        snap = tc.RegisterSession(tiers, actions=actions, **tc.conf_kw)
+        if snap.B == 0 or snap.N == 0 or snap.T == 0:
+            continue
+        picked += _pick_vs_oracle(shim, snap)
+        checked += 1
+    assert checked >= 40 and picked >= 60

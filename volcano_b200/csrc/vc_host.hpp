@@ -276,4 +276,137 @@ inline void go_heap_order(std::vector<int> &items, Less less) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// backfill: pickUpPendingTasks (actions/backfill/backfill.go:118-199) on the state the allocate action left
+// ---------------------------------------------------------------------------------------
+struct BackfillTasks {  // host copy of the BestEffort task list (vc_snapshot_set_backfill)
+  int n = 0;
+  std::vector<double> req, kreq, knz;
+  std::vector<uint32_t> has, uid;
+  std::vector<int32_t> job, klass, role, prio;
+  std::vector<int64_t> podidx, ts;
+};
+struct BackfillKeep {  // session-open state the pick order needs, kept at upload when the list is not empty
+  std::vector<int32_t> j_queue, j_min, j_prio, j_ready0, j_pbe, j_taskmintotal, j_roleoff, r_min, r_occ0, q_prio, t_role;
+  std::vector<uint32_t> j_flags, j_rank, r_flags, q_rank;
+  std::vector<uint8_t> j_valid;
+  std::vector<double> j_alloc0;  // [R][J]
+};
+struct BackfillPick {
+  std::vector<int32_t> order;             // backfill task ids in visiting order
+  std::vector<int> visit_job, visit_begin;  // one visit per job: its slice of `order` is [visit_begin[v], visit_begin[v+1])
+  std::vector<int32_t> j_ready, r_occ;    // ReadyTaskNum per job / occupancy per role row after allocate
+};
+// rank of every object in (CreationTimestamp, UID) order: the fallback of ssn.JobOrderFn / QueueOrderFn
+inline void rank_by(const int64_t *ts, const uint32_t *uid, size_t n, std::vector<uint32_t> &rank) {
+  std::vector<int> idx(n);
+  for (size_t i = 0; i < n; ++i) idx[i] = (int)i;
+  std::sort(idx.begin(), idx.end(), [&](int a, int b) { return ts[a] != ts[b] ? ts[a] < ts[b] : uid[a] < uid[b]; });
+  rank.resize(n);
+  for (size_t r = 0; r < n; ++r) rank[idx[r]] = (uint32_t)r;
+}
+// `ops`: the operations of the preceding allocate action (kept visits only, in order); task_*: allocate's task arrays
+inline BackfillPick backfill_pick(const vc_conf &conf, size_t R, size_t T, size_t J, size_t Q, size_t B, bool has_drf,
+                                  bool has_proportion, const double *total, uint32_t total_has, const BackfillTasks &bf,
+                                  const BackfillKeep &bk, const vc_decision *ops_p, size_t n_ops, const int32_t *task_job,
+                                  const double *task_req, const uint32_t *task_has, std::vector<QAttr> qattr) {
+  struct OpsView { const vc_decision *b, *e; const vc_decision *begin() const { return b; } const vc_decision *end() const { return e; } };
+  const OpsView ops{ops_p, ops_p + n_ops};
+  // ---- 1. the session state the allocate action left: ready counts, role occupancy, drf / proportion shares ----
+  BackfillPick out;
+  std::vector<int32_t> &j_ready = out.j_ready, &r_occ = out.r_occ;
+  j_ready = bk.j_ready0; r_occ = bk.r_occ0;
+  std::vector<double> j_alloc = bk.j_alloc0;
+  
+  for (const vc_decision &op : ops) {  // Statement.Allocate / Pipeline of every kept visit, in order
+    const int t = op.task, j = task_job[t];
+    if (op.kind == VC_OP_ALLOCATE) { j_ready[j] += 1; r_occ[bk.t_role[t]] += 1; }
+    if (has_drf)  // drf AllocateFunc, drf.go:391-418
+      for (size_t d = 0; d < R; ++d) j_alloc[d * J + j] += task_req[d * T + t];
+    const int q = bk.j_queue[j];
+    if (has_proportion && q >= 0 && qattr[q].exists)  // proportion AllocateFunc, proportion.go:475-497
+      qattr[q].allocated.add(HRes::load(task_req, (int)T, t, (int)R, task_has[t]), (int)R);
+  }
+  std::vector<double> j_share(J, 0.0);
+  if (has_drf)
+    for (size_t j = 0; j < J; ++j) {  // drf.calculateShare, drf.go:566-578
+      double res = 0;
+      for (size_t d = 0; d < R; ++d) {
+        if (d >= 2 && !((total_has >> d) & 1u)) continue;
+        if (!(total[d] >= kMinRes)) continue;
+        const double sh = share_of(j_alloc[d * J + j], total[d]);
+        if (sh > res) res = sh;
+      }
+      j_share[j] = res;
+    }
+  std::vector<double> q_share(Q, 0.0);
+  for (size_t q = 0; q < Q; ++q)
+    if (qattr[q].exists) q_share[q] = queue_share(qattr[q], (int)R);
+  auto is_ready = [&](int j) { return j_ready[j] + bk.j_pbe[j] >= bk.j_min[j]; };  // job_info.go:1169
+  auto job_less = [&](int l, int rr) {  // ssn.JobOrderFn, session_plugins.go:660-683
+    for (int i = 0; i < conf.n_plugins; ++i) {
+      const vc_plugin_option &po = conf.plugins[i];
+      if (!(po.enabled & VC_EN_JOB_ORDER)) continue;
+      int c = 0;
+      switch (po.plugin) {
+        case VC_PLUGIN_PRIORITY: c = bk.j_prio[l] > bk.j_prio[rr] ? -1 : (bk.j_prio[l] < bk.j_prio[rr] ? 1 : 0); break;
+        case VC_PLUGIN_GANG: {
+          const bool lr = is_ready(l), r2 = is_ready(rr);
+          c = (lr && r2) ? 0 : (lr ? 1 : (r2 ? -1 : 0));
+          break;
+        }
+        case VC_PLUGIN_DRF: c = j_share[l] == j_share[rr] ? 0 : (j_share[l] < j_share[rr] ? -1 : 1); break;
+        case VC_PLUGIN_TDM: {
+          const bool lp = bk.j_flags[l] & VC_JOB_PREEMPTABLE, rp = bk.j_flags[rr] & VC_JOB_PREEMPTABLE;
+          c = lp == rp ? 0 : (!lp ? -1 : 1);
+          break;
+        }
+        default: break;
+      }
+      if (c != 0) return c < 0;
+    }
+    return bk.j_rank[l] < bk.j_rank[rr];
+  };
+  const bool qorder_prop = plugin_enabled(conf, VC_PLUGIN_PROPORTION, VC_EN_QUEUE_ORDER);
+  auto queue_less = [&](int l, int rr) {  // ssn.QueueOrderFn :709-731; proportion.go:266-284
+    if (qorder_prop) {
+      if (bk.q_prio[l] != bk.q_prio[rr]) return bk.q_prio[l] > bk.q_prio[rr];
+      if (q_share[l] != q_share[rr]) return q_share[l] < q_share[rr];
+    }
+    return bk.q_rank[l] < bk.q_rank[rr];
+  };
+
+  // ---- 2. pickUpPendingTasks, backfill.go:118-199 ----
+  vc_tasks view;
+  std::memset(&view, 0, sizeof view);
+  view.priority = bf.prio.data(); view.pod_index = bf.podidx.data(); view.creation_ts = bf.ts.data(); view.uid_rank = bf.uid.data();
+  const TaskLess task_less{&view, plugin_enabled(conf, VC_PLUGIN_PRIORITY, VC_EN_TASK_ORDER)};
+  std::vector<std::vector<int>> job_tasks(J), queue_jobs(Q);
+  for (size_t t = 0; t < B; ++t) job_tasks[bf.job[t]].push_back((int)t);
+  std::vector<int> queues;
+  for (size_t j = 0; j < J; ++j) {
+    if (bk.j_flags[j] & VC_JOB_PENDING_PHASE) continue;  // job.IsPending(), :124-126
+    if (!bk.j_valid[j]) continue;                         // ssn.JobValid, :128-131
+    const int q = bk.j_queue[j];
+    if (q < 0 || job_tasks[j].empty()) continue;
+    if (queue_jobs[q].empty()) queues.push_back(q);
+    queue_jobs[q].push_back((int)j);
+  }
+  go_heap_order(queues, queue_less);
+  std::vector<int32_t> &order = out.order;  // backfill task ids in visiting order
+  std::vector<int> &visit_job = out.visit_job, &visit_begin = out.visit_begin;
+  for (int q : queues) {
+    go_heap_order(queue_jobs[q], job_less);
+    for (int j : queue_jobs[q]) {
+      go_heap_order(job_tasks[j], task_less);
+      visit_job.push_back(j);
+      visit_begin.push_back((int)order.size());
+      for (int t : job_tasks[j]) order.push_back(t);
+    }
+  }
+  visit_begin.push_back((int)order.size());
+  return out;
+}
+
 }  // namespace vch

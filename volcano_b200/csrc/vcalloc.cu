@@ -189,19 +189,8 @@ struct vc_snapshot {
   std::vector<uint32_t> h_has;
   std::vector<int32_t> h_class, h_task_job;
   // ---- backfill action (vc_snapshot_set_backfill / vc_backfill_run) ----
-  struct BackfillTasks {  // host copy of the BestEffort task list
-    int n = 0;
-    std::vector<double> req, kreq, knz;
-    std::vector<uint32_t> has, uid;
-    std::vector<int32_t> job, klass, role, prio;
-    std::vector<int64_t> podidx, ts;
-  } bf;
-  struct BackfillKeep {  // session-open state pickUpPendingTasks needs, kept at upload when bf.n > 0
-    std::vector<int32_t> j_queue, j_min, j_prio, j_ready0, j_pbe, j_taskmintotal, j_roleoff, r_min, r_occ0, q_prio, t_role;
-    std::vector<uint32_t> j_flags, j_rank, r_flags, q_rank;
-    std::vector<uint8_t> j_valid;
-    std::vector<double> j_alloc0;  // [R][J]
-  } bk;
+  vch::BackfillTasks bf;  // host copy of the BestEffort task list
+  vch::BackfillKeep bk;   // session-open state pickUpPendingTasks needs, kept at upload when bf.n > 0
   std::vector<vc_decision> last_dec;  // operations of the last vc_allocate_run (kept visits only)
   bool alloc_ran = false, bf_ran = false;
   int last_idx_cur = 0;   // util.lastProcessedNodeIndex as the last action of the cycle left it
@@ -1027,7 +1016,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   s->last_idx_cur = s->dc.last_idx0;
   s->last_dec.clear();
   if (s->bf.n > 0) {  // what pickUpPendingTasks (backfill.go:118-199) orders by, as of session open
-    vc_snapshot::BackfillKeep &k = s->bk;
+    vch::BackfillKeep &k = s->bk;
     k.j_queue.assign(jb->queue, jb->queue + J); k.j_min.assign(jb->min_available, jb->min_available + J);
     k.j_prio.assign(jb->priority, jb->priority + J); k.j_ready0.assign(jb->ready_num, jb->ready_num + J);
     k.j_pbe.assign(jb->pending_besteffort, jb->pending_besteffort + J);
@@ -1324,7 +1313,7 @@ int vc_snapshot_set_backfill(vc_snapshot *s, int32_t n_tasks, const vc_tasks *bt
   if (!s) return fail(VC_EINVAL, "null snapshot");
   if (n_tasks < 0 || (n_tasks > 0 && !bt)) return fail(VC_EINVAL, "backfill task list: negative size / null pointer");
   s->uploaded = false;  // the list is validated against the job / class tables by the next upload
-  vc_snapshot::BackfillTasks &b = s->bf;
+  vch::BackfillTasks &b = s->bf;
   const size_t B = (size_t)n_tasks, R = s->dims.n_dims, K = s->dims.n_kdims;
   b.n = n_tasks;
   if (B == 0) return VC_OK;
@@ -1364,101 +1353,17 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   }
   if (s->dd.node_begin != 0 || s->dd.node_end != (int)N) { delete r; return fail(VC_EUNSUPPORTED, "the backfill engine runs on the full node axis"); }
   if (B == 0) { *out = r; return VC_OK; }
-  const vc_snapshot::BackfillTasks &bf = s->bf;
-  const vc_snapshot::BackfillKeep &bk = s->bk;
+  const vch::BackfillTasks &bf = s->bf;
+  const vch::BackfillKeep &bk = s->bk;
   const vc_conf &conf = s->conf;
 
-  // ---- 1. the session state the allocate action left: ready counts, role occupancy, drf / proportion shares ----
-  std::vector<int32_t> j_ready = bk.j_ready0, r_occ = bk.r_occ0;
-  std::vector<double> j_alloc = bk.j_alloc0;
-  std::vector<vch::QAttr> qattr = s->qattr;
-  for (const vc_decision &op : s->last_dec) {  // Statement.Allocate / Pipeline of every kept visit, in order
-    const int t = op.task, j = s->h_task_job[t];
-    if (op.kind == VC_OP_ALLOCATE) { j_ready[j] += 1; r_occ[bk.t_role[t]] += 1; }
-    if (s->dc.has_drf)  // drf AllocateFunc, drf.go:391-418
-      for (size_t d = 0; d < R; ++d) j_alloc[d * J + j] += s->h_req[d * T + t];
-    const int q = bk.j_queue[j];
-    if (s->dc.has_proportion && q >= 0 && qattr[q].exists)  // proportion AllocateFunc, proportion.go:475-497
-      qattr[q].allocated.add(vch::HRes::load(s->h_req.data(), (int)T, t, (int)R, s->h_has[t]), (int)R);
-  }
-  std::vector<double> j_share(J, 0.0);
-  if (s->dc.has_drf)
-    for (size_t j = 0; j < J; ++j) {  // drf.calculateShare, drf.go:566-578
-      double res = 0;
-      for (size_t d = 0; d < R; ++d) {
-        if (d >= 2 && !((s->total_has >> d) & 1u)) continue;
-        if (!(s->total[d] >= vch::kMinRes)) continue;
-        const double sh = vch::share_of(j_alloc[d * J + j], s->total[d]);
-        if (sh > res) res = sh;
-      }
-      j_share[j] = res;
-    }
-  std::vector<double> q_share(Q, 0.0);
-  for (size_t q = 0; q < Q; ++q)
-    if (qattr[q].exists) q_share[q] = vch::queue_share(qattr[q], (int)R);
+  // ---- 1 + 2. session state after allocate and pickUpPendingTasks (backfill.go:118-199): vc_host.hpp ----
+  vch::BackfillPick pick = vch::backfill_pick(conf, R, T, J, Q, B, s->dc.has_drf != 0, s->dc.has_proportion != 0, s->total,
+                                              s->total_has, bf, bk, s->last_dec.data(), s->last_dec.size(), s->h_task_job.data(),
+                                              s->h_req.data(), s->h_has.data(), s->qattr);
+  const std::vector<int32_t> &order = pick.order, &j_ready = pick.j_ready, &r_occ = pick.r_occ;
+  const std::vector<int> &visit_job = pick.visit_job, &visit_begin = pick.visit_begin;
   auto is_ready = [&](int j) { return j_ready[j] + bk.j_pbe[j] >= bk.j_min[j]; };  // job_info.go:1169
-  auto job_less = [&](int l, int rr) {  // ssn.JobOrderFn, session_plugins.go:660-683
-    for (int i = 0; i < conf.n_plugins; ++i) {
-      const vc_plugin_option &po = conf.plugins[i];
-      if (!(po.enabled & VC_EN_JOB_ORDER)) continue;
-      int c = 0;
-      switch (po.plugin) {
-        case VC_PLUGIN_PRIORITY: c = bk.j_prio[l] > bk.j_prio[rr] ? -1 : (bk.j_prio[l] < bk.j_prio[rr] ? 1 : 0); break;
-        case VC_PLUGIN_GANG: {
-          const bool lr = is_ready(l), r2 = is_ready(rr);
-          c = (lr && r2) ? 0 : (lr ? 1 : (r2 ? -1 : 0));
-          break;
-        }
-        case VC_PLUGIN_DRF: c = j_share[l] == j_share[rr] ? 0 : (j_share[l] < j_share[rr] ? -1 : 1); break;
-        case VC_PLUGIN_TDM: {
-          const bool lp = bk.j_flags[l] & VC_JOB_PREEMPTABLE, rp = bk.j_flags[rr] & VC_JOB_PREEMPTABLE;
-          c = lp == rp ? 0 : (!lp ? -1 : 1);
-          break;
-        }
-        default: break;
-      }
-      if (c != 0) return c < 0;
-    }
-    return bk.j_rank[l] < bk.j_rank[rr];
-  };
-  const bool qorder_prop = vch::plugin_enabled(conf, VC_PLUGIN_PROPORTION, VC_EN_QUEUE_ORDER);
-  auto queue_less = [&](int l, int rr) {  // ssn.QueueOrderFn :709-731; proportion.go:266-284
-    if (qorder_prop) {
-      if (bk.q_prio[l] != bk.q_prio[rr]) return bk.q_prio[l] > bk.q_prio[rr];
-      if (q_share[l] != q_share[rr]) return q_share[l] < q_share[rr];
-    }
-    return bk.q_rank[l] < bk.q_rank[rr];
-  };
-
-  // ---- 2. pickUpPendingTasks, backfill.go:118-199 ----
-  vc_tasks view;
-  std::memset(&view, 0, sizeof view);
-  view.priority = bf.prio.data(); view.pod_index = bf.podidx.data(); view.creation_ts = bf.ts.data(); view.uid_rank = bf.uid.data();
-  const vch::TaskLess task_less{&view, vch::plugin_enabled(conf, VC_PLUGIN_PRIORITY, VC_EN_TASK_ORDER)};
-  std::vector<std::vector<int>> job_tasks(J), queue_jobs(Q);
-  for (size_t t = 0; t < B; ++t) job_tasks[bf.job[t]].push_back((int)t);
-  std::vector<int> queues;
-  for (size_t j = 0; j < J; ++j) {
-    if (bk.j_flags[j] & VC_JOB_PENDING_PHASE) continue;  // job.IsPending(), :124-126
-    if (!bk.j_valid[j]) continue;                         // ssn.JobValid, :128-131
-    const int q = bk.j_queue[j];
-    if (q < 0 || job_tasks[j].empty()) continue;
-    if (queue_jobs[q].empty()) queues.push_back(q);
-    queue_jobs[q].push_back((int)j);
-  }
-  vch::go_heap_order(queues, queue_less);
-  std::vector<int32_t> order;  // backfill task ids in visiting order
-  std::vector<int> visit_job, visit_begin;
-  for (int q : queues) {
-    vch::go_heap_order(queue_jobs[q], job_less);
-    for (int j : queue_jobs[q]) {
-      vch::go_heap_order(job_tasks[j], task_less);
-      visit_job.push_back(j);
-      visit_begin.push_back((int)order.size());
-      for (int t : job_tasks[j]) order.push_back(t);
-    }
-  }
-  visit_begin.push_back((int)order.size());
   const size_t n = order.size();
 
   // ---- 3. (class, request) groups of the verdict cache; the plugin's state-independent entry per node ----
