@@ -592,7 +592,22 @@ bool overused(const Session &s, int q) {
   return false;
 }
 // ssn.Allocatable :350-366 -> proportion queueAllocatable, proportion.go:333-348, using
-// LessEqualWithDimensionAndResourcesName, api/resource_info.go:469-514
+// LessEqualWithDimensionAndResourcesName with a non-nil req, api/resource_info.go:469-514: only the dimensions `req`
+// asks for (> 0) are compared, strictly (no epsilon); `pods` is an ignored scalar (IsIgnoredScalarResource :219)
+bool res_less_equal_with_dimension(const Res &l, const Res &r, const Res &req, int R, int pods_dim) {
+  bool ok = true;
+  if (req.v[0] > 0 && l.v[0] > r.v[0]) ok = false;
+  if (req.v[1] > 0 && l.v[1] > r.v[1]) ok = false;
+  if (l.nilmap) return ok;  // r.ScalarResources == nil: whatever rr holds, the scalars pass
+  for (int d = 2; d < R; ++d) {
+    if (!(req.has & (1u << d)) || d == pods_dim) continue;
+    double lq = (l.has & (1u << d)) ? l.v[d] : 0.0;
+    double rq = (r.has & (1u << d)) ? r.v[d] : 0.0;
+    if (req.v[d] > 0 && lq > rq) ok = false;
+  }
+  return ok;
+}
+// proportion's AllocatableFn through ssn.Allocatable: queueAllocatable, proportion.go:333-348
 bool allocatable(const Session &s, int q, int t) {
   for (int i = 0; i < s.conf.n_plugins; ++i) {
     const vc_plugin_option &p = s.conf.plugins[i];
@@ -603,18 +618,7 @@ bool allocatable(const Session &s, int q, int t) {
     Res fu = a.allocated;
     Res rq = task_res(s, t);
     res_add(fu, rq, s.R);
-    bool ok = true;
-    if (rq.v[0] > 0 && fu.v[0] > a.deserved.v[0]) ok = false;
-    if (rq.v[1] > 0 && fu.v[1] > a.deserved.v[1]) ok = false;
-    if (!fu.nilmap) {
-      for (int d = 2; d < s.R; ++d) {
-        if (!(rq.has & (1u << d)) || d == s.d.pods_dim) continue;
-        double rquant = (fu.has & (1u << d)) ? fu.v[d] : 0.0;
-        double rrquant = (a.deserved.has & (1u << d)) ? a.deserved.v[d] : 0.0;
-        if (rq.v[d] > 0 && rquant > rrquant) ok = false;
-      }
-    }
-    if (!ok) return false;
+    if (!res_less_equal_with_dimension(fu, a.deserved, rq, s.R, s.d.pods_dim)) return false;
   }
   return true;
 }
@@ -1783,6 +1787,27 @@ void vco_node_state(void *h, double *idle, double *used, double *pipelined) {
 
 // ---- primitives for the reference's known-answer tests ---------------------------------
 // Resource.LessEqual (api/resource_info_test.go:609 TestLessEqual)
+// Resource.Diff(rr, Zero) and MinDimensionResource(rr, Zero | Infinity) on plain vectors (api/resource_info_test.go:315-487,
+// :1562-1693): outputs are value vectors + key-presence masks
+int vco_less_equal_with_dimension(const double *l, uint32_t l_has, const double *r, uint32_t r_has, const double *req,
+                                  uint32_t req_has, int R, int pods_dim) {
+  return res_less_equal_with_dimension(res_from_soa(l, 1, 0, R, l_has), res_from_soa(r, 1, 0, R, r_has),
+                                       res_from_soa(req, 1, 0, R, req_has), R, pods_dim) ? 1 : 0;
+}
+void vco_diff_zero(const double *l, uint32_t l_has, const double *r, uint32_t r_has, int R, double *inc_out, uint32_t *inc_has,
+                   double *dec_out, uint32_t *dec_has) {
+  Res a = res_from_soa(l, 1, 0, R, l_has), b = res_from_soa(r, 1, 0, R, r_has), inc, dec;
+  res_diff_zero(a, b, inc, dec, R);
+  for (int d = 0; d < R; ++d) { inc_out[d] = inc.v[d]; dec_out[d] = dec.v[d]; }
+  *inc_has = inc.has; *dec_has = dec.has;
+}
+void vco_min_dimension(const double *l, uint32_t l_has, const double *r, uint32_t r_has, int R, int infinity, double *out,
+                       uint32_t *out_has) {
+  Res a = res_from_soa(l, 1, 0, R, l_has), b = res_from_soa(r, 1, 0, R, r_has);
+  res_min_dimension(a, b, infinity != 0, R);
+  for (int d = 0; d < R; ++d) out[d] = a.v[d];
+  *out_has = a.has;
+}
 int vco_less_equal(const double *l, uint32_t l_has, const double *r, uint32_t r_has, int R, int infinity) {
   if (!le_eps(l[0], r[0])) return 0;
   if (!le_eps(l[1], r[1])) return 0;

@@ -74,6 +74,10 @@ def lib() -> C.CDLL:
         L.vco_node_state.argtypes = [_vp, _dp, _dp, _dp]
         L.vco_less_equal.restype = C.c_int
         L.vco_less_equal.argtypes = [_dp, C.c_uint32, _dp, C.c_uint32, C.c_int, C.c_int]
+        _u32p = C.POINTER(C.c_uint32)
+        L.vco_diff_zero.argtypes = [_dp, C.c_uint32, _dp, C.c_uint32, C.c_int, _dp, _u32p, _dp, _u32p]
+        L.vco_less_equal_with_dimension.argtypes = [_dp, C.c_uint32, _dp, C.c_uint32, _dp, C.c_uint32, C.c_int, C.c_int]
+        L.vco_min_dimension.argtypes = [_dp, C.c_uint32, _dp, C.c_uint32, C.c_int, C.c_int, _dp, _u32p]
         L.vco_num_feasible_nodes.restype = C.c_int32
         L.vco_num_feasible_nodes.argtypes = [C.c_int32] * 4
         for n in ("vco_least_requested_score", "vco_most_requested_score"):

@@ -45,6 +45,21 @@ int vh_less_equal_zero(const double *l, uint32_t l_has, const double *r, uint32_
   return a.less_equal_zero(b, R) ? 1 : 0;
 }
 
+void vh_diff_zero(const double *l, uint32_t l_has, const double *r, uint32_t r_has, int R, double *inc_out, uint32_t *inc_has,
+                  double *dec_out, uint32_t *dec_has) {
+  vch::HRes a = vch::HRes::load(l, 1, 0, R, l_has), b = vch::HRes::load(r, 1, 0, R, r_has), inc, dec;
+  vch::hdiff(a, b, inc, dec, R);
+  for (int d = 0; d < R; ++d) { inc_out[d] = inc.v[d]; dec_out[d] = dec.v[d]; }
+  *inc_has = inc.has; *dec_has = dec.has;
+}
+void vh_min_dimension(const double *l, uint32_t l_has, const double *r, uint32_t r_has, int R, int infinity, double *out,
+                      uint32_t *out_has) {
+  vch::HRes a = vch::HRes::load(l, 1, 0, R, l_has), b = vch::HRes::load(r, 1, 0, R, r_has);
+  a.min_dim(b, infinity != 0, R);
+  for (int d = 0; d < R; ++d) out[d] = a.v[d];
+  *out_has = a.has;
+}
+
 // pickUpPendingTasks of the backfill action after `ops` (allocate's kept operations): the Keep record is filled exactly
 // as vc_snapshot_upload fills it
 int vh_backfill_pick(const vc_dims *d, const vc_conf *conf, const vc_nodes *nd, const vc_tasks *tk, const vc_jobs *jb,

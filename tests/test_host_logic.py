@@ -37,6 +37,9 @@ def shim():
                                      C.POINTER(abi.vc_queues), _dp, _dp]
     L.vh_task_heap_order.argtypes = [C.POINTER(abi.vc_tasks), C.c_int, _i32p, C.c_int]
     L.vh_less_equal_zero.argtypes = [_dp, C.c_uint32, _dp, C.c_uint32, C.c_int]
+    _u32p = C.POINTER(C.c_uint32)
+    L.vh_diff_zero.argtypes = [_dp, C.c_uint32, _dp, C.c_uint32, C.c_int, _dp, _u32p, _dp, _u32p]
+    L.vh_min_dimension.argtypes = [_dp, C.c_uint32, _dp, C.c_uint32, C.c_int, C.c_int, _dp, _u32p]
     L.vh_backfill_pick.argtypes = [C.POINTER(abi.vc_dims), C.POINTER(abi.vc_conf), C.POINTER(abi.vc_nodes), C.POINTER(abi.vc_tasks),
                                    C.POINTER(abi.vc_jobs), C.POINTER(abi.vc_queues), C.POINTER(abi.vc_tasks), C.c_int,
                                    C.POINTER(abi.vc_decision), C.c_int, _i32p]
@@ -68,6 +71,12 @@ def test_less_equal_zero_golden(shim):
         lv, lh = res(l)
         rv, rh = res(r)
         assert bool(shim.vh_less_equal_zero(lv.ctypes.data_as(_dp), lh, rv.ctypes.data_as(_dp), rh, 4)) == want, (l, r)
+
+
+def test_resource_diff_and_min_dimension_golden(shim):
+    """api/resource_info_test.go:315-421, :1562-1693 against the product's HRes (hdiff, min_dim)."""
+    from tests.test_oracle_golden import resource_ops
+    resource_ops(shim.vh_diff_zero, shim.vh_min_dimension)
 
 
 def test_go_pow_matches_the_oracle_and_exact_cases(shim):

@@ -83,6 +83,54 @@ def test_less_equal(table, infinity):
         assert bool(got) == want, (l, r, infinity)
 
 
+_RNAMES = ["hugepages-test", "scalar.test/scalar1"]
+
+
+def _res_out(v, has):
+    return (v[0], v[1], {nm: v[2 + i] for i, nm in enumerate(_RNAMES) if has & (1 << (2 + i))})
+
+
+def _expect(r):
+    return (float(r[0]), float(r[1]), {k: float(x) for k, x in (r[2] or {}).items()})
+
+
+def resource_ops(diff_fn, min_fn):
+    """Shared by the oracle test below and tests/test_host_logic.py (same goldens against the product's host code)."""
+    dp, u32 = C.POINTER(C.c_double), C.c_uint32
+    for l, r, inc_w, dec_w in G.DIFF_ZERO:
+        lv, lh = _res(l, _RNAMES)
+        rv, rh = _res(r, _RNAMES)
+        inc, dec = np.zeros(4), np.zeros(4)
+        ih, dh = u32(0), u32(0)
+        diff_fn(lv.ctypes.data_as(dp), lh, rv.ctypes.data_as(dp), rh, 4, inc.ctypes.data_as(dp), C.byref(ih), dec.ctypes.data_as(dp),
+                C.byref(dh))
+        assert _res_out(inc, ih.value) == _expect(inc_w) and _res_out(dec, dh.value) == _expect(dec_w), (l, r)
+    for table, infinity in ((G.MIN_DIMENSION_ZERO, 0), (G.MIN_DIMENSION_INFINITY, 1)):
+        for l, r, want in table:
+            lv, lh = _res(l, _RNAMES)
+            rv, rh = _res(r, _RNAMES)
+            out = np.zeros(4)
+            oh = u32(0)
+            min_fn(lv.ctypes.data_as(dp), lh, rv.ctypes.data_as(dp), rh, 4, infinity, out.ctypes.data_as(dp), C.byref(oh))
+            assert _res_out(out, oh.value) == _expect(want), (l, r, infinity)
+
+
+def test_less_equal_with_dimension():
+    """api/resource_info_test.go:773-883 (non-nil req): the comparison inside proportion's queueAllocatable."""
+    dp = C.POINTER(C.c_double)
+    for l, r, req, want in G.LESS_EQUAL_WITH_DIMENSION:
+        (lv, lh), (rv, rh), (qv, qh) = (_res(x, G.LE_DIM_NAMES) for x in (l, r, req))
+        got = pyoracle.lib().vco_less_equal_with_dimension(lv.ctypes.data_as(dp), lh, rv.ctypes.data_as(dp), rh,
+                                                           qv.ctypes.data_as(dp), qh, 2 + len(G.LE_DIM_NAMES), -1)
+        assert bool(got) == want, (l, r, req)
+
+
+def test_resource_diff_and_min_dimension():
+    """api/resource_info_test.go:315-421 TestDiff (Zero) and :1562-1693 TestMinDimensionResourceZero / Infinity: the two
+    Resource operations proportion's water-filling is built from (proportion.go:180-250)."""
+    resource_ops(pyoracle.lib().vco_diff_zero, pyoracle.lib().vco_min_dimension)
+
+
 def test_upstream_score_sanity():
     """recalled kube-scheduler formulas vs the reference's placement goldens."""
     L = pyoracle.lib()
