@@ -254,3 +254,25 @@ def test_backfill_pick_order_on_api_level_clusters(shim):
         picked += _pick_vs_oracle(shim, snap)
         checked += 1
     assert checked >= 40 and picked >= 60
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_proportion_deserved_properties(shim, seed):
+    """Size-independent properties of the water-filling (proportion.go:180-250) on the product's host code: a queue never
+    deserves more than it requests or than the cluster holds, the queues together never more than the cluster, and a queue
+    with pending requests and no cap gets a positive share of cpu."""
+    snap = make_snapshot("small", seed)
+    d, n, j, q = snap.dims(), snap.nodes(), snap.jobs(), snap.queues()
+    des = np.zeros((snap.R, snap.Q))
+    share = np.zeros(snap.Q)
+    shim.vh_proportion_open(C.byref(d), C.byref(n), C.byref(j), C.byref(q), des.ctypes.data_as(_dp), share.ctypes.data_as(_dp))
+    total = snap.n_allocatable.sum(axis=1)
+    assert np.all(des >= 0)
+    assert np.all(des <= snap.q_request + 1e-6)             # MinDimensionResource(request)
+    assert np.all(des.sum(axis=1) <= total * (1 + 1e-12))    # remaining never goes negative
+    for qi in range(snap.Q):
+        if snap.q_request[0, qi] > 0 and not (snap.q_capability_has[qi] & abi.VC_RES_HAS_ANY):
+            assert des[0, qi] > 0
+        if snap.q_capability_has[qi] & abi.VC_RES_HAS_ANY:    # capped queues stay under their capability
+            assert np.all(des[:2, qi] <= snap.q_capability[:2, qi] + 1e-6)
+    assert np.all(share >= 0)
