@@ -96,14 +96,51 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
-def run_oracle(snap, threads):
+def run_oracle(snap, threads, want_results=False):
     from oracle.pyoracle import OracleSession
     o = OracleSession(snap, threads=threads)
     t0 = time.perf_counter()
     dec, vis, fe = o.allocate()
     dt = time.perf_counter() - t0
     o.close()
+    if want_results:
+        return len(dec), dt, (dec, vis, fe)
     return len(dec), dt
+
+
+def compare_placements(res, oracle_results):
+    """GPU result vs the cpu_baseline leg's result on the SAME snapshot: identical placements (task, node, kind, visit,
+    in order), visit outcomes and fit errors; fp64 scores within 1e-6 (north_star). -> dict for the JSON line."""
+    dec, vis, fe = oracle_results
+    out = {"placements_identical": False, "first_difference": None, "compared": int(len(dec)),
+           "max_abs_score_diff": None}
+    if len(res.decisions) != len(dec):
+        out["first_difference"] = {"what": "number of decisions", "gpu": int(len(res.decisions)), "cpu": int(len(dec))}
+        return out
+    for f in ("task", "node", "kind", "visit"):
+        ne = np.nonzero(res.decisions[f] != dec[f])[0]
+        if len(ne):
+            out["first_difference"] = {"what": f"decision.{f}", "index": int(ne[0])}
+            return out
+    if not np.array_equal(res.visits, vis):
+        out["first_difference"] = {"what": "visits"}
+        return out
+    if not np.array_equal(res.fit_errors, fe):
+        out["first_difference"] = {"what": "fit_errors"}
+        return out
+    diff = float(np.max(np.abs(res.decisions["score"] - dec["score"]))) if len(dec) else 0.0
+    out["max_abs_score_diff"] = diff
+    out["placements_identical"] = diff <= 1e-6
+    return out
+
+
+def config_dict(name, world):
+    """The same keys in both arms (the driver compares the dicts)."""
+    return {"workload": workload_desc(name),
+            "parallelism": "1 scheduler shard per GPU" if world > 1 else "1 GPU",
+            "l2": "256 MB buffer written between timed iterations (GPU arm)",
+            "timed_region": "GPU arm: per-cycle resets + k_commit (CUDA events on its stream), e2e = upload + run + fetch "
+                            "wall time; reference arm: the allocate action, wall time"}
 
 
 def workload_desc(name):
@@ -134,7 +171,7 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "pods/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_desc(WORKLOAD)},
+        "config": config_dict(WORKLOAD, world),
         "cpu_baseline": {"value": val, "unit": "pods/s", "cores": threads, "kind": "port",
                          "sample": "full workload, one allocate cycle per step"},
         "e2e": {"value": val, "unit": "pods/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -258,12 +295,14 @@ def main():
     value = placed / t_dev
     e2e_value = e2e_placed / t_e2e
     cpu = None
+    parity = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = max(1, min(16, cpu_cores()))
-        n, dt = run_oracle(snap, threads)
+        n, dt, oracle_results = run_oracle(snap, threads, want_results=True)
+        parity = compare_placements(res, oracle_results)  # `res`: the last e2e cycle of the GPU arm, same snapshot
         cpu = {"value": n / dt, "unit": "pods/s", "cores": threads, "kind": "port",
-               "sample": "full workload, one allocate cycle (%.1f s), percentage-nodes-to-find=100 (same placements "
-                         "as the GPU path)" % dt}
+               "sample": "full workload, one allocate cycle (%.1f s), percentage-nodes-to-find=100; its decisions are "
+                         "compared with the GPU arm's (placements_identical)" % dt}
         # the reference's DEFAULT search-space reduction (adaptive 5 %% of 10k nodes = 500 feasible nodes per task,
         # util/scheduler_helper.go:54-73) makes its CPU path ~20x cheaper per task and yields different placements;
         # reported so that the parity-mode ratio is not mistaken for the production-default ratio
@@ -288,11 +327,10 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": 1e3 * t_dev / args.steps,
             "cycle_ms_p50": statistics.median(dev_ms), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_desc(args.workload),
-                       "parallelism": "1 scheduler shard per GPU" if world > 1 else "1 GPU",
-                       "l2": "256 MB buffer written between timed iterations",
-                       "timed_region": "k_commit (CUDA events on its stream); e2e = upload + run + fetch wall time",
-                       "sweeps_per_step": n_steps / args.steps},
+            "config": config_dict(args.workload, world),
+            "sweeps_per_step": n_steps / args.steps,
+            "placements_identical": parity["placements_identical"] if parity else None,
+            "parity": parity,
             "e2e": {"value": e2e_value, "unit": "pods/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": 2 * args.steps,  # k_class_static + k_commit per e2e step (1 per device-timed step)
@@ -305,6 +343,9 @@ def main():
                               "hbm_traffic": "inputs once (17 MB); node state is shared-memory resident"},
         }
         print(json.dumps(line), flush=True)
+        if parity is not None and not parity["placements_identical"]:
+            eng.close()
+            raise SystemExit("bench.py: GPU placements differ from the cpu_baseline leg's: %s" % json.dumps(parity))
     eng.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -311,8 +311,12 @@ typedef struct vc_result vc_result;
 int vc_abi_version(void);
 const char *vc_last_error(void);
 
-/* Bind the calling process to CUDA device `device` (one process per GPU). */
+/* Bind the calling process to CUDA device `device` (one process per GPU). The diagnostic switches (environment
+   variables VC_PROF, VC_COMMIT_GENERIC, ... listed in README.md) are read here, once, never per cycle. */
 int vc_init(int device);
+/* Set one diagnostic switch by its environment-variable name at run time (tests, tools/). Switches select
+   instrumented or alternative kernel instances; none changes a result. VC_EINVAL for an unknown name. */
+int vc_debug_option(const char *name, int value);
 
 /* Device memory for one scheduling session of the given size. */
 int vc_snapshot_create(const vc_dims *dims, vc_snapshot **out);

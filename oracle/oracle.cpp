@@ -1381,7 +1381,10 @@ int allocate_execute(Session &s) {
   std::vector<uint8_t> queue_seen(s.Q, 0);
   for (int q = 0; q < s.Q; ++q) jobs_by_queue[q].less = [&s](int l, int r) { return job_order_less(s, l, r); };
   for (int j = 0; j < s.J; ++j) {
-    if ((s.j_flags[j] & VC_JOB_PENDING_PHASE) && s.conf.enqueue_action_enabled) continue;
+    if (s.j_flags[j] & VC_JOB_PENDING_PHASE) {  // allocate.go:154-164
+      if (s.conf.enqueue_action_enabled) continue;
+      s.j_flags[j] &= ~VC_JOB_PENDING_PHASE;  // job.PodGroup.Status.Phase = PodGroupInqueue: later actions see it
+    }
     if (!job_valid(s, j)) continue;
     int q = s.j_queue[j];
     if (q < 0) continue;
@@ -1457,7 +1460,7 @@ std::vector<int> backfill_pick_up_pending_tasks(Session &s, std::vector<int> *jo
   std::vector<uint8_t> queue_seen(s.Q, 0);
   for (int q = 0; q < s.Q; ++q) jobs_by_queue[q].less = [&s](int l, int r) { return job_order_less(s, l, r); };
   for (int j = 0; j < s.J; ++j) {
-    if (s.j_flags[j] & VC_JOB_PENDING_PHASE) continue;  // job.IsPending() :124-126 (no enqueue-action condition here)
+    if (s.j_flags[j] & VC_JOB_PENDING_PHASE) continue;  // job.IsPending() :124-126 — on the phase allocate may have rewritten
     if (!job_valid(s, j)) continue;
     int q = s.j_queue[j];
     if (q < 0) continue;
@@ -1729,6 +1732,61 @@ int vco_backfill_pick_order(void *h, int32_t *out) {
   return (int)p.size();
 }
 int vco_allocate_run(void *h) { return allocate_execute(*(Session *)h); }
+// Sampled replay ("parity on a 1 % task sample replayed through the oracle"): the caller's
+// decision list (any implementation's) is applied in order to this fresh session through Statement.Allocate /
+// Pipeline; every decision whose index == offset (mod stride) is first re-derived here on the state reached so
+// far — ph.PredicateNodes over all nodes (allocate.go:634) + alloc.prioritizeNodes (:661) — and compared (node,
+// kind, score within 1e-6). The role-level predicate-error cache only skips nodes that failed earlier in the same
+// visit; node resources only shrink inside a visit, so leaving it out cannot change a verdict. Returns the number
+// of sampled decisions that differ; *first_bad = index of the first one (-1 when none).
+int64_t vco_replay_check(void *h, const vc_decision *dec, size_t n_dec, const vc_visit *vis, size_t n_vis, int64_t stride,
+                         int64_t offset, int64_t *first_bad, int64_t *n_checked) {
+  Session &s = *(Session *)h;
+  int64_t bad = 0, checked = 0;
+  *first_bad = -1;
+  std::vector<Op> ops;
+  std::vector<int> feasible;
+  PredicateHelper ph;
+  int cur_visit = -1, allocated_hn = -1;
+  for (size_t i = 0; i < n_dec; ++i) {
+    const vc_decision &d = dec[i];
+    const int t = d.task, j = s.t_job[t];
+    if (d.visit != cur_visit) {
+      if (cur_visit >= 0 && (size_t)cur_visit < n_vis && vis[cur_visit].outcome == VC_VISIT_COMMIT) {
+        const int pj = vis[cur_visit].job;
+        if (s.job_soft[pj]) s.job_alloc_hn[pj] = allocated_hn;  // allocate.go:681-686
+      }
+      cur_visit = d.visit;
+      allocated_hn = s.job_alloc_hn[j];  // allocate.go:572
+      ops.clear();
+    }
+    s.task_alloc_hn = s.job_soft[j] ? allocated_hn : -1;
+    if (stride > 0 && (int64_t)(i % (size_t)stride) == offset) {
+      ph.role_base = s.j_roleoff[j];
+      const int nroles = s.j_roleoff[j + 1] - s.j_roleoff[j];
+      ph.node_err.assign(nroles, {});
+      ph.exists.assign(nroles, 0);
+      const int32_t pct = s.conf.percentage_nodes_to_find;
+      s.conf.percentage_nodes_to_find = 100;
+      predicate_nodes(s, ph, t, feasible);
+      s.conf.percentage_nodes_to_find = pct;
+      double score = 0;
+      const int best = feasible.empty() ? -1 : prioritize_nodes(s, t, feasible, &score);
+      const int kind = best >= 0 && !fits_idle(s, t, best) ? VC_OP_PIPELINE : VC_OP_ALLOCATE;
+      checked += 1;
+      if (best != d.node || kind != d.kind || !(std::fabs(score - d.score) <= 1e-6)) {
+        if (*first_bad < 0) *first_bad = (int64_t)i;
+        bad += 1;
+      }
+    }
+    if (d.node < 0 || d.node >= s.N) { if (*first_bad < 0) *first_bad = (int64_t)i; return bad + 1; }
+    if (d.kind == VC_OP_ALLOCATE) stmt_allocate(s, ops, t, d.node, d.score);
+    else stmt_pipeline(s, ops, t, d.node, d.score);
+    if (s.job_soft[j]) allocated_hn = new_allocated_hypernode(s, d.node, allocated_hn);  // :672-674
+  }
+  *n_checked = checked;
+  return bad;
+}
 size_t vco_num_decisions(void *h) { return ((Session *)h)->decisions.size(); }
 const vc_decision *vco_decisions(void *h) { return ((Session *)h)->decisions.data(); }
 size_t vco_num_visits(void *h) { return ((Session *)h)->visits.size(); }

@@ -55,6 +55,9 @@ def lib() -> C.CDLL:
         L.vco_go_pow_uint.restype = C.c_double
         L.vco_go_pow_uint.argtypes = [C.c_double, C.c_uint]
         L.vco_allocate_run.argtypes = [_vp]
+        L.vco_replay_check.restype = C.c_int64
+        L.vco_replay_check.argtypes = [_vp, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int64, C.c_int64,
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.vco_session_set_backfill.argtypes = [_vp, C.c_int32, C.POINTER(abi.vc_tasks)]
         L.vco_backfill.argtypes = [_vp]
         L.vco_backfill_pick_order.argtypes = [_vp, _i32p]
@@ -140,6 +143,16 @@ class OracleSession:
         if rc != 0:
             raise RuntimeError(f"oracle allocate rc={rc}")
         return self._results()
+
+    def replay_check(self, decisions, visits, stride: int, offset: int = 0):
+        """Apply `decisions` (any implementation's) to this FRESH session in order and re-derive every stride-th one on
+        the state reached so far (feasible nodes + prioritizeNodes). -> (mismatches, first bad index or -1, checked)."""
+        dec = np.ascontiguousarray(decisions, DECISION_DTYPE)
+        vis = np.ascontiguousarray(visits, VISIT_DTYPE)
+        first, checked = C.c_int64(-1), C.c_int64(0)
+        bad = lib().vco_replay_check(self.h, dec.ctypes.data, len(dec), vis.ctypes.data, len(vis), stride, offset,
+                                     C.byref(first), C.byref(checked))
+        return int(bad), int(first.value), int(checked.value)
 
     def backfill(self):
         """The backfill action on the state the session is in (after allocate(), or the opening state)."""

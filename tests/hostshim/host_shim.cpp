@@ -63,7 +63,7 @@ void vh_min_dimension(const double *l, uint32_t l_has, const double *r, uint32_t
 // pickUpPendingTasks of the backfill action after `ops` (allocate's kept operations): the Keep record is filled exactly
 // as vc_snapshot_upload fills it
 int vh_backfill_pick(const vc_dims *d, const vc_conf *conf, const vc_nodes *nd, const vc_tasks *tk, const vc_jobs *jb,
-                     const vc_queues *qu, const vc_tasks *bt, int n_bf, const vc_decision *ops, int n_ops, int32_t *order_out) {
+                     const vc_queues *qu, const vc_tasks *bt, int n_bf, const vc_decision *ops, int n_ops, int alloc_ran, int32_t *order_out) {
   const size_t R = d->n_dims, K = d->n_kdims, N = d->n_nodes, T = d->n_tasks, J = d->n_jobs, Q = d->n_queues, NR = d->n_roles,
                B = (size_t)n_bf;
   vch::HRes total;
@@ -99,7 +99,7 @@ int vh_backfill_pick(const vc_dims *d, const vc_conf *conf, const vc_nodes *nd, 
   k.j_valid.resize(J);
   for (size_t j = 0; j < J; ++j) k.j_valid[j] = vch::job_valid(*conf, *jb, (int)j) ? 1 : 0;
   k.j_alloc0.assign(jb->allocated, jb->allocated + R * J);
-  vch::BackfillPick p = vch::backfill_pick(*conf, R, T, J, Q, B, has_drf, has_prop, total.v, total.has, bf, k, ops, (size_t)n_ops,
+  vch::BackfillPick p = vch::backfill_pick(*conf, alloc_ran != 0, R, T, J, Q, B, has_drf, has_prop, total.v, total.has, bf, k, ops, (size_t)n_ops,
                                            tk->job, tk->resreq, tk->req_has, qattr);
   for (size_t i = 0; i < p.order.size(); ++i) order_out[i] = p.order[i];
   return (int)p.order.size();

@@ -64,3 +64,35 @@ def test_backfill_alone_and_synthetic_configs():
     assert len(dec) + len(fe) == snap.B and vis["n_ops"].sum() == len(dec)
     res = AllocateResult(dec, vis, fe)
     assert np.all(np.diff(res.decisions["visit"]) >= 0)
+
+
+def _pending_phase_cluster():
+    """Two PodGroups still in phase Pending (no enqueue action has promoted them), BestEffort pods only in pg2."""
+    nodes = [BuildNode("n0", BuildResourceList("4", "8Gi", ("pods", "8")))]
+    pods = [BuildPod("c1", "w0", "", "Pending", BuildResourceList("1", "1Gi"), "pg1")]
+    pods += [BuildPod("c1", f"be{i}", "", "Pending", {}, "pg2") for i in range(2)]
+    pods += [BuildPod("c1", "w1", "", "Pending", BuildResourceList("1", "1Gi"), "pg2")]
+    return TestCommonStruct(Name="pending phase", Nodes=nodes, Pods=pods, Queues=[BuildQueue("q1", 1, None)],
+                            PodGroups=[BuildPodGroup("pg1", "c1", "q1", 1, None, "Pending"),
+                                       BuildPodGroup("pg2", "c1", "q1", 1, None, "Pending")])
+
+
+def test_pending_podgroups_without_the_enqueue_action(oracle_engine):
+    """allocate.go:154-164: with no enqueue action configured buildAllocateContext rewrites the phase of every Pending
+    PodGroup to Inqueue, so the backfill action that follows (backfill.go:124 job.IsPending()) places their BestEffort
+    pods; with enqueue configured both actions skip such jobs."""
+    tc = _pending_phase_cluster()
+    snap = tc.RegisterSession(SchedulerConf.default().tiers, actions=("allocate", "backfill"))
+    assert snap.conf.enqueue_action_enabled == 0 and (snap.j_flags & abi.VC_JOB_PENDING_PHASE).all()
+    tc.Run(oracle_engine)
+    assert sorted(tc.binds) == ["c1/be0", "c1/be1", "c1/w0", "c1/w1"]
+    tc = _pending_phase_cluster()
+    tc.RegisterSession(SchedulerConf.default().tiers, actions=("enqueue", "allocate", "backfill"))
+    tc.Run(oracle_engine)
+    assert tc.binds == {}
+    # backfill alone (allocate did not run, nothing rewrote the phase): Pending jobs are skipped
+    tc = _pending_phase_cluster()
+    snap = tc.RegisterSession(SchedulerConf.default().tiers, actions=("backfill",))
+    o = OracleSession(snap)
+    assert len(o.backfill_pick_order()) == 0
+    o.close()

@@ -371,6 +371,60 @@ def test_full_size_properties(cfg, gpu):
     assert (per_job[jobs_committed] >= snap.j_min_available[jobs_committed]).all()
 
 
+def _host_threads():
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(16, n))  # the reference runs 16 workers per task (util/predicate_helper.go:133)
+
+
+FULL_SIZE = [("cfg2", "fast"), ("cfg2", "fast_norun"), ("cfg2", "generic"), ("cfg2", "sampling"), ("cfg3", "fast"), ("cfg3", "generic")]
+
+
+@pytest.mark.parametrize("cfg,mode", FULL_SIZE, ids=[f"{c}-{m}" for c, m in FULL_SIZE])
+def test_full_size_vs_oracle(cfg, mode, gpu, oracle_engine):
+    """BASELINE configs[1] / [2] at FULL size (10k nodes x 100k tasks) — the configuration bench.py measures: every
+    decision (task, node, kind, visit, fp64 score), every visit outcome and every fit error against the oracle
+    (actions/allocate/allocate.go:283-348, :558-694). Modes: the incremental kernel with and without run-length
+    batches, the general kernel (VC_COMMIT_GENERIC), and the reference's default feasible-node sampling
+    (percentage-nodes-to-find=0 -> adaptive 5 %, util/scheduler_helper.go:54-73)."""
+    from volcano_b200.synth import make_snapshot
+    snap = make_snapshot(cfg)
+    threads = _host_threads()
+    if mode == "sampling":
+        snap.conf.percentage_nodes_to_find = 0
+        threads = 1  # the single-worker reading of the early-stop loop
+    gpu.debug_option("VC_COMMIT_GENERIC", 1 if mode == "generic" else 0)
+    gpu.debug_option("VC_COMMIT_NORUN", 1 if mode == "fast_norun" else 0)
+    try:
+        res = gpu.gpu_engine(snap)
+    finally:
+        gpu.debug_option("VC_COMMIT_GENERIC", 0)
+        gpu.debug_option("VC_COMMIT_NORUN", 0)
+    ref = oracle_engine(snap, threads=threads)
+    assert len(ref.decisions) > 90_000 or mode == "sampling"
+    _assert_same(res, ref)
+    assert np.array_equal(res.decisions["score"], ref.decisions["score"]), "scores are expected to be bit-identical"
+
+
+def test_cfg4_sampled_replay(gpu):
+    """BASELINE config 4 (50k nodes x 1M tasks, 3-tier HyperNode tree, network-topology-aware, drf + proportion over 16
+    queues) — BASELINE.md section 3: the GPU's decision list is replayed through the oracle session and every 100th
+    decision (1 %) is re-derived on the state reached so far: feasible nodes, prioritizeNodes arg-max, fp64 score."""
+    from oracle.pyoracle import OracleSession
+    from volcano_b200.synth import make_snapshot
+    snap = make_snapshot("cfg4")
+    res = gpu.gpu_engine(snap)
+    assert len(res.decisions) > 500_000
+    o = OracleSession(snap, threads=_host_threads())
+    bad, first, checked = o.replay_check(res.decisions, res.visits, 100, 37)
+    o.close()
+    assert checked >= len(res.decisions) // 100 - 1
+    assert bad == 0, f"{bad} of {checked} sampled decisions differ, first at index {first}"
+
+
 SAMPLING_CASES = [("tiny", 1, 50, 10, 0), ("tiny", 2, 20, 5, 17), ("small", 7, 0, 100, 0), ("small", 3, 30, 50, 333),
                   ("tiny_fut", 2, 40, 8, 5), ("small_fut_soft", None, 25, 30, 0), ("small_roles", None, 35, 20, 11),
                   ("small_topo", None, 30, 40, 100), ("small_topo_fut_soft", 4, 50, 20, 7), ("cfg1", None, 0, 20, 0)]

@@ -42,7 +42,7 @@ def shim():
     L.vh_min_dimension.argtypes = [_dp, C.c_uint32, _dp, C.c_uint32, C.c_int, C.c_int, _dp, _u32p]
     L.vh_backfill_pick.argtypes = [C.POINTER(abi.vc_dims), C.POINTER(abi.vc_conf), C.POINTER(abi.vc_nodes), C.POINTER(abi.vc_tasks),
                                    C.POINTER(abi.vc_jobs), C.POINTER(abi.vc_queues), C.POINTER(abi.vc_tasks), C.c_int,
-                                   C.POINTER(abi.vc_decision), C.c_int, _i32p]
+                                   C.POINTER(abi.vc_decision), C.c_int, C.c_int, _i32p]
     return L
 
 
@@ -225,7 +225,7 @@ def _pick_vs_oracle(shim, snap):
     ops = np.ascontiguousarray(dec)
     out = np.zeros(max(snap.B, 1), np.int32)
     got_n = shim.vh_backfill_pick(C.byref(d), C.byref(snap.conf), C.byref(n), C.byref(t), C.byref(j), C.byref(q), C.byref(bt),
-                                  snap.B, ops.ctypes.data_as(C.POINTER(abi.vc_decision)), len(ops), out.ctypes.data_as(_i32p))
+                                  snap.B, ops.ctypes.data_as(C.POINTER(abi.vc_decision)), len(ops), 1, out.ctypes.data_as(_i32p))
     assert list(out[:got_n]) == list(want)
     return got_n
 

@@ -23,6 +23,8 @@ POOLS = ["p0", "p1"]
 
 def make_case(seed, big=False):
     rnd = random.Random(seed)
+    rnd2 = random.Random(seed * 7919 + 13)  # later additions draw from their own stream: earlier seeds keep their clusters
+    mix_names = rnd2.random() < 0.3  # jobs mixing pods with and without a numeric name index (CompareTask is intransitive there)
     be_p = rnd.choice([0.05, 0.05, 0.3])  # share of BestEffort pods (the backfill action's tasks)
     n_nodes = rnd.randint(3, 40) if not big else rnd.randint(40, 400)
     nodes = []
@@ -101,6 +103,12 @@ def make_case(seed, big=False):
             p = BuildPod("ns", f"j{j}-{role}-{k}", node_name, "Running" if running else "Pending",
                          req if role == "worker" or rnd.random() < 0.5 else BuildResourceList("1", "1Gi"),
                          f"pg{j}", {"volcano.sh/task-spec": role}, sel)
+            if mix_names and rnd2.random() < 0.4:
+                p.name = f"j{j}-{role}-x{k}"  # no numeric suffix: ordered by creation time, then UID
+                p.uid = f"ns-{p.name}"
+                p.creation_ts = rnd2.randint(0, 3)
+            elif mix_names:
+                p.creation_ts = rnd2.randint(0, 3)
             if rnd.random() < 0.3:
                 p.tolerations.append(Toleration(rnd.choice(["dedicated", "gpu", "spot", ""]), rnd.choice(["Equal", "Exists"]),
                                                 rnd.choice(["a", "b"]), rnd.choice(["", "NoSchedule", "PreferNoSchedule"])))

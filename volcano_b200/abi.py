@@ -205,6 +205,7 @@ SYMBOLS = {
     "vc_abi_version": (C.c_int, []),
     "vc_last_error": (C.c_char_p, []),
     "vc_init": (C.c_int, [C.c_int]),
+    "vc_debug_option": (C.c_int, [C.c_char_p, C.c_int]),
     "vc_snapshot_create": (C.c_int, [C.POINTER(vc_dims), C.POINTER(_vp)]),
     "vc_snapshot_destroy": (None, [_vp]),
     "vc_snapshot_upload": (C.c_int, [_vp, C.POINTER(vc_nodes), C.POINTER(vc_tasks), C.POINTER(vc_classes),

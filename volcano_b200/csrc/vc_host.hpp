@@ -306,8 +306,10 @@ inline void rank_by(const int64_t *ts, const uint32_t *uid, size_t n, std::vecto
   rank.resize(n);
   for (size_t r = 0; r < n; ++r) rank[idx[r]] = (uint32_t)r;
 }
-// `ops`: the operations of the preceding allocate action (kept visits only, in order); task_*: allocate's task arrays
-inline BackfillPick backfill_pick(const vc_conf &conf, size_t R, size_t T, size_t J, size_t Q, size_t B, bool has_drf,
+// `ops`: the operations of the preceding allocate action (kept visits only, in order); task_*: allocate's task arrays.
+// `alloc_ran`: allocate ran before in this session. Without the enqueue action its buildAllocateContext rewrites the phase of
+// every Pending PodGroup to Inqueue (allocate.go:154-164), so job.IsPending() (backfill.go:124) is false afterwards.
+inline BackfillPick backfill_pick(const vc_conf &conf, bool alloc_ran, size_t R, size_t T, size_t J, size_t Q, size_t B, bool has_drf,
                                   bool has_proportion, const double *total, uint32_t total_has, const BackfillTasks &bf,
                                   const BackfillKeep &bk, const vc_decision *ops_p, size_t n_ops, const int32_t *task_job,
                                   const double *task_req, const uint32_t *task_has, std::vector<QAttr> qattr) {
@@ -386,7 +388,8 @@ inline BackfillPick backfill_pick(const vc_conf &conf, size_t R, size_t T, size_
   for (size_t t = 0; t < B; ++t) job_tasks[bf.job[t]].push_back((int)t);
   std::vector<int> queues;
   for (size_t j = 0; j < J; ++j) {
-    if (bk.j_flags[j] & VC_JOB_PENDING_PHASE) continue;  // job.IsPending(), :124-126
+    const bool phase_flipped = alloc_ran && !conf.enqueue_action_enabled;
+    if ((bk.j_flags[j] & VC_JOB_PENDING_PHASE) && !phase_flipped) continue;  // job.IsPending(), :124-126
     if (!bk.j_valid[j]) continue;                         // ssn.JobValid, :128-131
     const int q = bk.j_queue[j];
     if (q < 0 || job_tasks[j].empty()) continue;

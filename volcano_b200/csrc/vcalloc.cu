@@ -44,6 +44,39 @@ int g_device = -1;
 int g_sm_count = 0;
 int g_launches = 0;
 
+// Diagnostic switches: read from the environment ONCE, in vc_init (never on the per-cycle entry points), and
+// overridable at run time through vc_debug_option (tests and tools/). None of them changes a result.
+struct Tunables {
+  int commit_ctas = 0;      // VC_COMMIT_CTAS: CTAs of the commit kernels (0 = one per SM)
+  int commit_threads = 0;   // VC_COMMIT_THREADS: minimum block size
+  int commit_generic = 0;   // VC_COMMIT_GENERIC: always the general commit kernel (k_commit)
+  int commit_norun = 0;     // VC_COMMIT_NORUN: the incremental kernel without run-length placement batches
+  int prof = 0;             // VC_PROF: instrumented kernel instances (phase timers)
+  int prof_owner = 0;       // VC_PROF_OWNER: owner-path statistics on stderr
+  int prof_wait = 0;        // VC_PROF_WAIT: per-CTA all-gather wait of the general kernel on stderr
+  int prof_upload = 0;      // VC_PROF_UPLOAD: host checkpoints of vc_snapshot_upload on stderr
+  int backfill_depth1 = 0;  // VC_BACKFILL_DEPTH1: k_backfill run-ahead depth 1
+  int expand_rows = 0;      // VC_EXPAND_ROWS: task rows per work item of the expand kernel
+  int expand_plain = 0;     // VC_EXPAND_PLAIN: warp-store expand kernel
+  int expand_chunk = 0;     // VC_EXPAND_CHUNK: nodes per staged piece
+};
+Tunables g_tun;
+struct TunName { const char *name; int Tunables::*field; };
+const TunName kTunNames[] = {
+    {"VC_COMMIT_CTAS", &Tunables::commit_ctas}, {"VC_COMMIT_THREADS", &Tunables::commit_threads},
+    {"VC_COMMIT_GENERIC", &Tunables::commit_generic}, {"VC_COMMIT_NORUN", &Tunables::commit_norun},
+    {"VC_PROF", &Tunables::prof}, {"VC_PROF_OWNER", &Tunables::prof_owner}, {"VC_PROF_WAIT", &Tunables::prof_wait},
+    {"VC_PROF_UPLOAD", &Tunables::prof_upload}, {"VC_BACKFILL_DEPTH1", &Tunables::backfill_depth1},
+    {"VC_EXPAND_ROWS", &Tunables::expand_rows}, {"VC_EXPAND_PLAIN", &Tunables::expand_plain},
+    {"VC_EXPAND_CHUNK", &Tunables::expand_chunk}};
+void read_tunables() {
+  for (const TunName &t : kTunNames)
+    if (const char *e = getenv(t.name)) {
+      const int v = atoi(e);
+      g_tun.*(t.field) = (v == 0 && e[0] != '0') ? 1 : v;  // "VC_PROF=yes" counts as set
+    }
+}
+
 double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
@@ -146,6 +179,7 @@ struct vc_snapshot {
   double *rep_f64 = nullptr;
   HeapEnt *rep_heap = nullptr;
   size_t rep_i32_stride = 0, rep_f64_stride = 0, rep_heap_stride = 0;
+  int rep_ctas = 0;  // CTA count the replica buffers were sized for
   uint4 *mbox = nullptr;
   long long *d_prof = nullptr, *d_wait = nullptr;
   long long h_prof[16] = {0};
@@ -276,9 +310,9 @@ int build_devconf(vc_snapshot *s, const vc_nodes *nd) {
 void choose_geometry(vc_snapshot *s) {
   const int nloc = s->dd.node_end - s->dd.node_begin;
   int ctas = g_sm_count > 0 ? g_sm_count : 148;
-  if (const char *e = getenv("VC_COMMIT_CTAS")) ctas = std::max(1, atoi(e));
+  if (g_tun.commit_ctas > 0) ctas = g_tun.commit_ctas;
   int block = 128;
-  if (const char *e = getenv("VC_COMMIT_THREADS")) block = std::max(128, std::min(256, atoi(e) / 32 * 32));
+  if (g_tun.commit_threads > 0) block = std::max(128, std::min(256, g_tun.commit_threads / 32 * 32));
   ctas = std::max(1, std::min(ctas, (nloc + 31) / 32));  // at least a warp of nodes per CTA
   int npc = (nloc + ctas - 1) / ctas;
   npc = std::max(32, (npc + 31) / 32 * 32);
@@ -289,7 +323,7 @@ void choose_geometry(vc_snapshot *s) {
   s->block = block;
   const int R = s->dims.n_dims, K = s->dims.n_kdims;
   // hypernode-level scores change for every node after every placement: per-step full sweeps (k_commit)
-  s->fast = !s->dc.has_future && !s->dc.soft_active && !s->dc.nta_on && s->dc.to_find == 0 && R <= 8 && K <= VC_MAX_KDIMS && !getenv("VC_COMMIT_GENERIC");
+  s->fast = !s->dc.has_future && !s->dc.soft_active && !s->dc.nta_on && s->dc.to_find == 0 && R <= 8 && K <= VC_MAX_KDIMS && !g_tun.commit_generic;
   if (s->fast) {
     size_t rows = 3 * (size_t)R + 2 * (size_t)K + 2 + 1;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + ((sizeof(CtlFast) + 15) & ~(size_t)15) + rows * npc * 8 +
@@ -346,8 +380,16 @@ int vc_init(int device) {
   if (!prop.cooperativeLaunch) return fail(VC_ENODEV, "device lacks cooperative launch");
   g_sm_count = prop.multiProcessorCount;
   g_device = device;
+  if (!g_inited) read_tunables();
   g_inited = true;
   return VC_OK;
+}
+
+int vc_debug_option(const char *name, int value) {
+  if (!name) return fail(VC_EINVAL, "null option name");
+  for (const TunName &t : kTunNames)
+    if (!std::strcmp(name, t.name)) { g_tun.*(t.field) = value; return VC_OK; }
+  return fail(VC_EINVAL, "unknown diagnostic option %s", name);
 }
 
 int vc_snapshot_create(const vc_dims *dims, vc_snapshot **out) {
@@ -454,13 +496,28 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   const size_t N = D.n_nodes, T = D.n_tasks, J = D.n_jobs, Q = D.n_queues, C = D.n_classes, R = D.n_dims,
                K = D.n_kdims, Wl = D.label_words, Wt = D.taint_words, NR = D.n_roles, Z = D.n_zones;
   s->conf = *conf;
+  // ---- every caller-supplied index is range-checked here, before any session-open logic reads through it ----
+  if (conf->n_plugins < 0 || conf->n_plugins > VC_MAX_PLUGINS) return fail(VC_EINVAL, "n_plugins out of range");
+  if (J > 0 && jb->role_off[0] != 0) return fail(VC_EINVAL, "role_off[0] must be 0");
+  for (size_t j = 0; j < J; ++j) {
+    if (jb->role_off[j + 1] < jb->role_off[j] || (size_t)jb->role_off[j + 1] > NR)
+      return fail(VC_EINVAL, "job %zu: role_off not monotone / beyond n_roles", j);
+    if (jb->queue[j] < -1 || jb->queue[j] >= (int32_t)Q) return fail(VC_EINVAL, "job %zu: bad queue index", j);
+  }
+  for (size_t t = 0; t < T; ++t) {
+    const int32_t j = tk->job[t];
+    if (j < 0 || (size_t)j >= J) return fail(VC_EINVAL, "task %zu: bad job index", t);
+    if (tk->klass[t] < 0 || (size_t)tk->klass[t] >= C) return fail(VC_EINVAL, "task %zu: bad class index", t);
+    if (tk->role[t] < jb->role_off[j] || tk->role[t] >= jb->role_off[j + 1])
+      return fail(VC_EINVAL, "task %zu: role row outside its job", t);
+  }
   for (size_t j = 0; j < J; ++j) {
     if (jb->flags[j] & VC_JOB_UNSUPPORTED) return fail(VC_EUNSUPPORTED, "job %zu uses hard topology / subjob policy", j);
     if (jb->role_off[j + 1] - jb->role_off[j] > VC_MAX_JOB_ROLES) return fail(VC_EUNSUPPORTED, "job %zu has too many roles", j);
   }
   int rc = build_devconf(s, nd);
   if (rc) return rc;
-  const bool tprof = getenv("VC_PROF_UPLOAD") != nullptr;
+  const bool tprof = g_tun.prof_upload != 0;
   double tlast = now_ms();
   auto tick = [&](const char *what) {
     if (!tprof) return;
@@ -516,10 +573,17 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     std::vector<int> tmp;
     for (size_t j = 0; j < J; ++j) {
       int b = job_task_off[j], e = job_task_off[j + 1];
-      bool sorted = true;
+      // helpers.CompareTask is transitive only among pods that all carry a numeric name index or all lack one
+      // (index order between indexed pods, creation time otherwise): the shortcut is taken for such jobs alone
+      bool sorted = true, any_idx = false, any_noidx = false;
+      for (int i = b; i < e; ++i) {
+        const bool has_idx = tk->pod_index && tk->pod_index[task_order[i]] >= 0;
+        any_idx |= has_idx; any_noidx |= !has_idx;
+      }
+      if (any_idx && any_noidx) sorted = false;
       for (int i = b + 1; i < e && sorted; ++i)
         if (!less(task_order[i - 1], task_order[i])) sorted = false;
-      if (sorted) continue;  // a strictly increasing run is its own heap-pop order
+      if (sorted) continue;  // a strictly increasing run under a transitive order is its own heap-pop order
       tmp.assign(task_order.begin() + b, task_order.begin() + e);
       vch::go_heap_order(tmp, less);
       std::copy(tmp.begin(), tmp.end(), task_order.begin() + b);
@@ -794,6 +858,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   // network-topology-aware: hyperNodeResourceCache at open (network_topology_aware.go:106-125) and, for the
   // commit kernel, the hypernodes each CTA's node slice belongs to
   choose_geometry(s);
+  if (s->n_cta > 1024) return fail(VC_EUNSUPPORTED, "too many CTAs (%d)", s->n_cta);
   if (s->dc.to_find > 0 && (s->npc + s->block - 1) / s->block > 4)
     return fail(VC_EUNSUPPORTED, "feasible-node sampling: more than 4 node rows per CTA (%d nodes per CTA)", s->npc);
   std::vector<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn, node_chain, cta_chain_off, cta_chain;
@@ -1084,7 +1149,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   // per-CTA heap replica: HeapEnt entries for k_commit, HeapKey (32 B) entries for k_commit_fast; stride in entries of
   // the kernel's own type, sized for the larger one
   const size_t heap_stride = (s->qjobs.count + 7) & ~(size_t)7;
-  if (!s->rep_i32 || s->rep_i32_stride != i32_stride || s->rep_f64_stride != f64_stride || s->rep_heap_stride != heap_stride) {
+  if (!s->rep_i32 || s->rep_i32_stride != i32_stride || s->rep_f64_stride != f64_stride || s->rep_heap_stride != heap_stride ||
+      s->rep_ctas < G) {
     if (s->rep_i32) cudaFree(s->rep_i32);
     if (s->rep_f64) cudaFree(s->rep_f64);
     if (s->rep_heap) cudaFree(s->rep_heap);
@@ -1093,6 +1159,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
     CUDA_TRY(cudaMalloc(&s->rep_f64, std::max<size_t>(16, f64_stride * G * 8)));
     CUDA_TRY(cudaMalloc(&s->rep_heap, std::max<size_t>(16, std::max<size_t>(heap_stride, 1) * G * sizeof(HeapKey))));
     s->rep_i32_stride = i32_stride; s->rep_f64_stride = f64_stride; s->rep_heap_stride = heap_stride;
+    s->rep_ctas = G;
   }
   if (s->topo_any && !s->d_job_alloc) CUDA_TRY(cudaMalloc(&s->d_job_alloc, std::max<size_t>(16, J * 4)));
   if (s->topo_any) {
@@ -1116,10 +1183,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024 * 2;  // second half: the count all-gather of sampling
   if (!s->mbox) CUDA_TRY(cudaMalloc(&s->mbox, mbox_bytes));
   if (!s->d_prof) CUDA_TRY(cudaMalloc(&s->d_prof, 16 * sizeof(long long)));
-  CUDA_TRY(cudaMemsetAsync(s->d_prof, 0, 16 * sizeof(long long), s->stream));
   const size_t ring_bytes = sizeof(uint4) * RING_STRIDE * RING_DEPTH;
   if (!s->ring) CUDA_TRY(cudaMalloc(&s->ring, ring_bytes));
-  CUDA_TRY(cudaMemsetAsync(s->ring, 0, ring_bytes, s->stream));
   if (!s->d_decisions) {
     CUDA_TRY(cudaMalloc(&s->d_decisions, std::max<size_t>(1, T) * sizeof(vc_decision)));
     CUDA_TRY(cudaMalloc(&s->d_visits, (T + J + 1) * sizeof(vc_visit)));
@@ -1130,16 +1195,6 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
     CUDA_TRY(cudaMallocHost(&s->h_fit, std::max<size_t>(1, T) * 4));
     CUDA_TRY(cudaMallocHost(&s->h_counters, 16 * 4));
   }
-  CUDA_TRY(cudaMemsetAsync(s->mbox, 0, mbox_bytes, s->stream));
-  CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 16 * 4, s->stream));
-  // working copies of the mutable node state (the uploaded snapshot stays intact for re-runs / K1)
-  CUDA_TRY(cudaMemcpyAsync(s->w_idle, s->n_idle.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->w_used, s->n_used.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->w_pip, s->n_pip.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->w_kreq, s->n_kreq.d(s->in), K * N * 8, cudaMemcpyDeviceToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->w_knz, s->n_knz.d(s->in), 2 * N * 8, cudaMemcpyDeviceToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->w_pod_count, s->n_pod_count.d(s->in), N * 4, cudaMemcpyDeviceToDevice, s->stream));
-
   K2Params p;
   std::memset(&p, 0, sizeof p);
   p.d = s->dd; p.c = s->dc; p.npc = s->npc; p.n_cta = G; p.max_job_tasks = s->max_job_tasks;
@@ -1187,14 +1242,13 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   for (int i = 0; i < VC_MAX_TIERS + 2; ++i) p.topo_val[i] = s->topo_val[i];
 
   long long *d_wait = nullptr;
-  if (getenv("VC_PROF_WAIT")) {
+  if (g_tun.prof_wait) {
     if (!s->d_wait) CUDA_TRY(cudaMalloc(&s->d_wait, 1024 * 8));
     d_wait = s->d_wait;
     CUDA_TRY(cudaMemsetAsync(d_wait, 0, 1024 * 8, s->stream));
   }
   p.cta_wait = d_wait;
-  if (G > 1024) return fail(VC_EUNSUPPORTED, "too many CTAs");
-  const void *kfn = s->fast ? (getenv("VC_PROF") ? (const void *)k_commit_fast<true> : (const void *)k_commit_fast<false>)
+  const void *kfn = s->fast ? (g_tun.prof ? (const void *)k_commit_fast<true> : (const void *)k_commit_fast<false>)
                   : s->dc.to_find > 0 ? (s->topo_any ? (const void *)k_commit<true, true, true, true> : (const void *)k_commit<true, true, false, true>)
                   : s->topo_any ? (const void *)k_commit<true, true, true> : s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
                                      : (s->dc.soft_active ? (const void *)k_commit<false, true> : (const void *)k_commit<false, false>);
@@ -1208,8 +1262,22 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   fp.q_share0 = s->q_share0.d(s->in);
   fp.heap_off = s->s_heap_off.d(s->in); fp.ready_word = s->fast_ready_word; fp.ready_shift = s->fast_ready_shift;
   fp.share_on = s->fast_share_on; fp.heap_in_smem = s->heap_in_smem; fp.heap_total = s->heap_total;
-  void *args[] = {&p, &fp};
+  // ---- the timed region (vc_stats.commit_ms) starts here: the per-cycle resets and working copies are work
+  //      every cycle does, so they are inside it ----
   CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->d_prof, 0, 16 * sizeof(long long), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->ring, 0, ring_bytes, s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->mbox, 0, mbox_bytes, s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 16 * 4, s->stream));
+  // working copies of the mutable node state (the uploaded snapshot stays intact for re-runs / K1)
+  CUDA_TRY(cudaMemcpyAsync(s->w_idle, s->n_idle.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->w_used, s->n_used.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->w_pip, s->n_pip.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->w_kreq, s->n_kreq.d(s->in), K * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->w_knz, s->n_knz.d(s->in), 2 * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->w_pod_count, s->n_pod_count.d(s->in), N * 4, cudaMemcpyDeviceToDevice, s->stream));
+
+  void *args[] = {&p, &fp};
   CUDA_TRY(cudaLaunchCooperativeKernel(kfn, dim3(G), dim3(s->block), args, s->smem_bytes, s->stream));
   g_launches++;
   CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
@@ -1283,11 +1351,11 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->stats.prof_cycles[6] = s->h_counters[5];  // full sweeps (fast kernel)
   r->stats.prof_cycles[7] = s->h_counters[6];  // incremental steps (fast kernel)
   r->stats.prof_cycles[5] = s->h_counters[7];  // owner changes between consecutive publications
-  if (getenv("VC_PROF_OWNER"))
+  if (g_tun.prof_owner)
     fprintf(stderr, "evaluator (all CTAs): %d evaluations, %d speculation hits, %d cache rescans; command -> publish %.0f cycles, "
                     "speculative run-ahead %.0f cycles per evaluation (VC_PROF instance only)\n", s->h_counters[10], s->h_counters[8],
             s->h_counters[9], 1024.0 * s->h_counters[11] / std::max(1, s->h_counters[10]), 1024.0 * s->h_counters[12] / std::max(1, s->h_counters[10]));
-  if (getenv("VC_PROF_OWNER") && s->h_prof[9]) fprintf(stderr, "owner steps=%lld: post->join-start %.0f, join wait %.0f, join->next post (same owner) %.0f cycles [join->a %.0f, a->b %.0f, b->c %.0f, c->post %.0f]\n",
+  if (g_tun.prof_owner && s->h_prof[9]) fprintf(stderr, "owner steps=%lld: post->join-start %.0f, join wait %.0f, join->next post (same owner) %.0f cycles [join->a %.0f, a->b %.0f, b->c %.0f, c->post %.0f]\n",
       s->h_prof[9], (double)s->h_prof[8] / s->h_prof[9], (double)s->h_prof[10] / s->h_prof[9], (double)s->h_prof[11] / s->h_prof[9], (double)s->h_prof[12] / s->h_prof[9], (double)s->h_prof[13] / s->h_prof[9], (double)s->h_prof[14] / s->h_prof[9], (double)s->h_prof[15] / s->h_prof[9]);
   *out = r;
   return VC_OK;
@@ -1358,7 +1426,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   const vc_conf &conf = s->conf;
 
   // ---- 1 + 2. session state after allocate and pickUpPendingTasks (backfill.go:118-199): vc_host.hpp ----
-  vch::BackfillPick pick = vch::backfill_pick(conf, R, T, J, Q, B, s->dc.has_drf != 0, s->dc.has_proportion != 0, s->total,
+  vch::BackfillPick pick = vch::backfill_pick(conf, s->alloc_ran, R, T, J, Q, B, s->dc.has_drf != 0, s->dc.has_proportion != 0, s->total,
                                               s->total_has, bf, bk, s->last_dec.data(), s->last_dec.size(), s->h_task_job.data(),
                                               s->h_req.data(), s->h_has.data(), s->qattr);
   const std::vector<int32_t> &order = pick.order, &j_ready = pick.j_ready, &r_occ = pick.r_occ;
@@ -1469,8 +1537,8 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
     bp.klass = reinterpret_cast<const int32_t *>(base + o_klass); bp.group = reinterpret_cast<const int32_t *>(base + o_group);
     bp.out_node = reinterpret_cast<int32_t *>(base + o_node); bp.out_score = reinterpret_cast<double *>(base + o_score);
     bp.nta_static = nta_static.empty() ? nullptr : reinterpret_cast<const double *>(base + o_nta);
-    bp.prof = getenv("VC_PROF") ? reinterpret_cast<long long *>(base + o_prof) : nullptr;
-    bp.spec_depth = (s->rows_integral && !getenv("VC_BACKFILL_DEPTH1")) ? 32 : 1;
+    bp.prof = g_tun.prof ? reinterpret_cast<long long *>(base + o_prof) : nullptr;
+    bp.spec_depth = (s->rows_integral && !g_tun.backfill_depth1) ? 32 : 1;
     bp.last_idx0 = s->last_idx_cur; bp.out_last_idx = reinterpret_cast<int32_t *>(base + o_last);
     const void *kfn = s->dc.to_find > 0 ? (const void *)k_backfill<true, true>
                     : s->dc.soft_active ? (const void *)k_backfill<true> : (const void *)k_backfill<false>;
@@ -1493,7 +1561,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) return bail(e, "backfill kernel");
   if (n > 0) cudaEventElapsedTime(&kms, s->ev0, s->ev1);
   for (int k = 0; k < 8; ++k) r->stats.prof_cycles[k] = h_prof[k];
-  if (getenv("VC_PROF") && n > 0)
+  if (g_tun.prof && n > 0)
     fprintf(stderr, "k_backfill CTA 0: top barrier -> record seen (bystander, summed) %lld cycles, top barrier -> record sent "
                     "(republisher, summed) %lld cycles\n", h_prof[8], h_prof[9]);
   s->bf_ran = true;
@@ -1568,7 +1636,7 @@ static int dense_prepare(vc_snapshot *s) {
   for (size_t t = 0; t < T; ++t) group_tasks[fill[group_of[t]]++] = (int32_t)t;
   // work items: a few rows of one group each
   int chunk = 16;  // rows per work item: more, smaller CTAs keep the copy engines of all SMs busy to the end
-  if (const char *e = getenv("VC_EXPAND_ROWS")) chunk = std::max(1, atoi(e));
+  if (g_tun.expand_rows > 0) chunk = g_tun.expand_rows;
   std::vector<int32_t> wg, wb, we;
   for (size_t g = 0; g < G; ++g)
     for (int b = g_count[g]; b < g_count[g + 1]; b += chunk) {
@@ -1701,7 +1769,7 @@ int vc_dense_finish(vc_snapshot *s, int materialize) {
     CUDA_TRY(cudaGetLastError());
   }
   if (materialize && s->n_work > 0 && nloc > 0) {
-    if ((N % 2) == 0 && (s->dd.node_begin % 128) == 0 && !getenv("VC_EXPAND_PLAIN")) {
+    if ((N % 2) == 0 && (s->dd.node_begin % 128) == 0 && !g_tun.expand_plain) {
       // bulk-copy variant: final rows of the groups first (G x Nloc evaluations), then one streaming kernel
       s->mwg = ((nloc + 127) / 128) * 4;
       if (!s->g_final) {
@@ -1714,7 +1782,7 @@ int vc_dense_finish(vc_snapshot *s, int materialize) {
       g_launches++;
       // node chunks of <= 8192 nodes (64 KB of scores) so several CTAs share an SM
       int max_chunk = 8192;
-      if (const char *e = getenv("VC_EXPAND_CHUNK")) max_chunk = std::max(128, atoi(e) / 128 * 128);
+      if (g_tun.expand_chunk > 0) max_chunk = std::max(128, g_tun.expand_chunk / 128 * 128);
       const int nchunks = (nloc + max_chunk - 1) / max_chunk;
       const int chunk = (((nloc + nchunks - 1) / nchunks) + 127) & ~127;
       const size_t smem = (size_t)chunk * 8 + 16;

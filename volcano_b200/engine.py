@@ -46,6 +46,11 @@ def init(device: int = 0):
     _check(load_library().vc_init(device))
 
 
+def debug_option(name: str, value: int):
+    """Diagnostic switch by its environment-variable name (kernel instance selection, timers); results never change."""
+    _check(load_library().vc_debug_option(name.encode(), int(value)))
+
+
 def _struct_array(ptr, n, dtype):
     if n == 0:
         return np.zeros(0, dtype)
