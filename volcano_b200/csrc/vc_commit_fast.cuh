@@ -28,6 +28,8 @@
 #define CMD_DISCARD 2
 #define CMD_EXIT 3
 #define CMD_EVAL 4
+#define CMD_RUN 5
+#define RUN_MAX 32  // placements one publication can cover (one lane of the evaluator warp per node state)
 #define VC_JOBX_PURE 0x100u  // host-computed: every named role of the job maps to a single group
 #define FAST_R 8
 
@@ -86,6 +88,8 @@ struct FastParams {  // extra kernel arguments of the fast kernel
   const RoleStatic *rstat;
   const QueueStatic *qstat;
   const double *q_share0;  // [Q]
+  int run_max;             // 1: one placement per publication; RUN_MAX: run-length batches (rows integer-valued)
+  double *score_log;       // [T] score of the chosen node per placement attempt (written by the owner CTA of a run)
 };
 
 struct FastSmem {
@@ -144,6 +148,13 @@ __device__ __forceinline__ Best unpack_best(const uint4 &v) {
   b.cnt = (int)(v.w & 3u);
   return b;
 }
+
+// ring record of a publication: the owner CTA's new best + how many placements the record covers (1..RUN_MAX)
+__device__ __forceinline__ uint4 pack_run(const Best &b, unsigned tag, int m) {
+  unsigned long long sb = (unsigned long long)__double_as_longlong(b.score);
+  return make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)b.node, (tag << 10) | ((unsigned)m << 2) | (unsigned)min(b.cnt, 2));
+}
+#define RUN_TAG_MASK 0x3fffffu
 
 // all-gather of the CTA bests (warp 0 of every CTA); fills the slot table
 __device__ __forceinline__ void exchange_all_fast(const K2Params &p, const Best &mine, unsigned ag, FastSmem &fs) {
@@ -233,6 +244,28 @@ struct CtlFast {  // shared-memory state of the fast kernel next to Ctl
   double ev_score;
   int ev_i, ev_ring, ev_node, ev_cnt, cur_group;
   unsigned ev_tag;
+  // CMD_RUN: placements the control program allows on node ev_i in a row (run_L), attempt index of the first one,
+  // result (run_m placements made), runner-up computed by warp 2
+  int run_L, run_att0, run_m;
+  double ru_score, rl_score;
+  int ru_node, rl_node, rl_cnt;
+};
+// node view of row i after `k` further placements of the staged group (k as a double): what eval_pair_fast sees for
+// the states a run walks through. Every quantity is integer-valued (checked at upload), so row -/+ k * request is
+// exactly what k sequential placements leave (node_info.go:467-471, predicates.go:254-255).
+struct RunNodeView {
+  const FastSmem &s;
+  const TaskRec &t;
+  int i;
+  double k, kk;  // kk = k when the predicates plugin maintains the upstream NodeInfo, else 0
+  __device__ __forceinline__ double alloc(int d) const { return s.alloc[d * s.cap + i]; }
+  __device__ __forceinline__ double idle(int d) const { return s.idle[d * s.cap + i] - k * t.req[d]; }
+  __device__ __forceinline__ double used(int d) const { return s.used[d * s.cap + i] + k * t.req[d]; }
+  __device__ __forceinline__ double rel(int) const { return 0.0; }  // no Releasing / Pipelined resources in this kernel
+  __device__ __forceinline__ double pip(int) const { return 0.0; }
+  __device__ __forceinline__ double kalloc(int kd) const { return s.kalloc[kd * s.cap + i]; }
+  __device__ __forceinline__ double kreq(int kd) const { return s.kreq[kd * s.cap + i] + kk * t.kreq[kd]; }
+  __device__ __forceinline__ double knz(int kd) const { return s.knz[kd * s.cap + i] + kk * t.knz[kd]; }
 };
 
 // PROF = true keeps the phase / owner-path cycle counters (tools/prof_commit.py, VC_PROF=1); the production
@@ -571,8 +604,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     if (lane == 0) {
       F.cta_best_score = bs; F.cta_best_node = bn; F.cta_cnt = cnt;
       Best nb{bs, bn, cnt};
-      mbox_store(p.ring + (size_t)F.ev_ring * RING_STRIDE, pack_best(nb, F.ev_tag));
-      F.ev_score = bs; F.ev_node = bn; F.ev_cnt = min(cnt, 2);
+      mbox_store(p.ring + (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, 1));
+      F.ev_score = bs; F.ev_node = bn; F.ev_cnt = min(cnt, 2); F.run_m = 1;
     }
     __syncwarp();
     asm volatile("bar.arrive 1, 64;" ::: "memory");  // results ready: warp 0 joins with bar.sync 1, 64
@@ -591,6 +624,95 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     if (PROF) ev_acc_spec += clock64() - t0;
   };
 
+  // CMD_RUN (warp 2): the runner-up the run is measured against — the best candidate of this CTA other than node
+  // F.ev_i, and the best of every other CTA's slot. Neither changes while placements keep landing on F.ev_i.
+  auto run_runner_up = [&]() {
+    const int i = F.ev_i;
+    Best rl{0.0, -1, 0};
+    for (int k = lane; k < nmine; k += 32)
+      if (k != i && fs.c_cat[k] == 0) best_fold(rl, fs.c_score[k], nbase + k, 1);
+    best_warp_reduce(rl);
+    Best ro{0.0, -1, 0};
+    for (int sl = lane; sl < G; sl += 32)
+      if (sl != cta) best_fold(ro, fs.sl_score[sl], fs.sl_node[sl], 0);
+    best_warp_reduce(ro);
+    if (lane == 0) {
+      F.rl_score = rl.score; F.rl_node = rl.node; F.rl_cnt = rl.cnt;
+      Best ru = rl;
+      best_fold(ru, ro.score, ro.node, 0);
+      F.ru_score = ru.score; F.ru_node = ru.node;
+    }
+    __syncwarp();
+    asm volatile("bar.sync 2, 64;" ::: "memory");  // pairs with warp 1
+  };
+  // CMD_RUN (warp 1): lane l evaluates node F.ev_i as it will be after l further placements of the staged group
+  // (state 0 = the row as the control warp's placement left it), with the sweep's own evaluator. The node keeps
+  // winning while its state is feasible and beats the runner-up; the run covers those placements, one publication.
+  int n_runs = 0, n_run_place = 0;
+  long long run_cycles = 0;
+  auto run_eval_and_publish = [&]() {
+    const long long run_t0 = clock64();
+    const int i = F.ev_i;
+    const int dn = nbase + i;
+    const int L = F.run_L;  // placements the control program allows in a row, the one already applied included
+    const int old_cat = fs.c_cat[i];
+    const TaskRec &trec = S.trec;
+    const uint32_t cs = fs.c_cs[i];
+    const int kx = c.has_predicates ? lane : 0;
+    double sc = 0.0;
+    int cat = 2;
+    if (lane < L) {
+      // the loop-based evaluator of the general kernel (same IEEE operations in the same order as eval_pair_fast, a
+      // few hundred instructions instead of its fully unrolled few thousand: this warp runs it cold)
+      const RunNodeView nv{fs, trec, i, (double)lane, (double)kx};
+      const bool ok = (cs & CS_STATIC_OK) != 0 && !(c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i] + kx);
+      const int fc = fit_category_t<false>(R, trec, nv);
+      double order = 0.0;
+      const bool has_order = node_order(c, R, K, trec, nv, cs, &order);
+      sc = total_score(c, has_order, has_order ? order : 0.0, 0, 0);
+      cat = (ok && fc == 0) ? 0 : 2;
+    }
+    asm volatile("bar.sync 2, 64;" ::: "memory");  // runner-up ready (warp 2)
+    const double ru_s = F.ru_score;
+    const int ru_n = F.ru_node;
+    // lane l < L-1: does the node still win in state l (i.e. does placement l+1 of the run land on it too)?
+    const bool win = lane < L - 1 && cat == 0 && (ru_n < 0 || better(sc, dn, ru_s, ru_n));
+    const unsigned wmask = __ballot_sync(0xffffffffu, win);
+    const int m = min(L, __ffs(~wmask));  // 1 + leading wins; state m-1 is the row after the run
+    const double sc_m = __shfl_sync(0xffffffffu, sc, m - 1);
+    const int cat_m = __shfl_sync(0xffffffffu, cat, m - 1);
+    // scores of placements 1..m-1 of the run (placement j is chosen in state j-1 ... of the row BEFORE it: lane j-1)
+    if (lane < m - 1) { fp.score_log[F.run_att0 + 1 + lane] = sc; __threadfence(); }  // visible before the record below
+    // the remaining m-1 placements on the row (Statement.Allocate: node_info.go:467-471, predicates.go:254-255)
+    const double km = (double)(m - 1);
+    if (m > 1) {
+      if (lane < R) {
+        fs.idle[lane * cap + i] -= km * trec.req[lane];
+        fs.used[lane * cap + i] += km * trec.req[lane];
+      }
+      if (c.has_predicates) {
+        if (lane == 16) fs.pod_count[i] += m - 1;
+        if (lane >= 17 && lane < 17 + K) fs.kreq[(lane - 17) * cap + i] += km * trec.kreq[lane - 17];
+        if (lane >= 24 && lane < 26) fs.knz[(lane - 24) * cap + i] += km * trec.knz[lane - 24];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      fs.c_cat[i] = cat_m; fs.c_score[i] = sc_m;
+      Best nb{F.rl_score, F.rl_node, F.rl_cnt};
+      if (cat_m == 0) best_fold(nb, sc_m, dn, 1);
+      F.cta_best_score = nb.score; F.cta_best_node = nb.node; F.cta_cnt = nb.cnt;
+      mbox_store(p.ring + (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, m));
+      F.ev_score = nb.score; F.ev_node = nb.node; F.ev_cnt = min(nb.cnt, 2); F.run_m = m;
+      F.spec_i[0] = -1; F.spec_i[1] = -1;  // whatever was computed ahead describes an older state of the row
+    }
+    (void)old_cat;
+    n_runs += 1; n_run_place += m;
+    __syncwarp();
+    asm volatile("bar.arrive 1, 64;" ::: "memory");  // results ready: warp 0 joins with bar.sync 1, 64
+    run_cycles += clock64() - run_t0;
+  };
+
   if (warp != 0) {
     // ---- worker warps: serve block-wide commands ----
     int my_group = -1;
@@ -600,6 +722,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       if (cmd == CMD_EXIT) {
         if (warp == 1 && lane == 0) {
           atomicAdd(&p.counters[8], n_spec_hit); atomicAdd(&p.counters[9], n_rescan); atomicAdd(&p.counters[10], n_eval);
+          atomicAdd(&p.counters[13], n_runs); atomicAdd(&p.counters[14], n_run_place);
+          atomicAdd(&p.counters[15], (int)(run_cycles >> 10));
           if (PROF && n_eval > 0) atomicAdd(&p.counters[11], (int)(ev_acc_pub >> 10));
         }
         if (PROF && warp == 2 && lane == 0) atomicAdd(&p.counters[12], (int)(ev_acc_spec >> 10));
@@ -607,6 +731,11 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       }
       if (cmd == CMD_SWEEP) sweep_part();
       else if (cmd == CMD_DISCARD) discard_part();
+      else if (cmd == CMD_RUN) {  // warps 1 and 2, paired on named barrier 2; warp 1 signals warp 0 on barrier 1
+        if (warp == 1) run_eval_and_publish();
+        else if (warp == 2) run_runner_up();
+        continue;
+      }
       else if (cmd == CMD_EVAL) {  // no block-wide B2: warp 1 signals warp 0 on named barrier 1
         if (warp == 1 || warp == 2) {
           if (F.cur_group != my_group) { stage_ops(); my_group = F.cur_group; }
@@ -639,6 +768,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     long long t_post = 0, t_join = 0, acc_post_to_joinstart = 0, acc_join_wait = 0, acc_join_to_post = 0; int acc_n = 0;
     int pub_owner = -1, pub_node = -1;
     unsigned pub_pc = 0;
+    int n_att = 0;   // placement attempts so far (index into the score log; every task is attempted at most once)
+    int pub_m = 1;   // placements covered by the publication resolve() consumed last
 
     // Visit state that survives from one visit to the next: a re-pushed job is usually popped again right away
     // (one task per visit once it is Ready, allocate.go:676), and a session often has few queues — so the queue
@@ -710,6 +841,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       }
       int j = -1;
       bool job_loaded = false;  // F.js / F.jd hold records that differ from the register state
+      bool visit_from_heap = false;  // the job of this visit was popped from the heap of re-pushed jobs
       if (!over) {
         const int sc = sbeg + q_scursor;
         const int hs = q_hsize;
@@ -742,6 +874,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         } else if (have_h) {
           from_heap = true;
         }
+        visit_from_heap = from_heap;
         if (from_heap) {
           j = top.job;
           if (lane == 0) {  // heap pop: sift-down (only jobs that were re-pushed live here)
@@ -792,6 +925,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       }
       // ---- job state into registers; roles into the shared role tables ----
       n_ops = 0;
+      int vrun_extra = 0;  // further single-task visits of this (Ready) job folded into this pass of the loop
       if (job_loaded) {
         task_off = F.js.task_off; task_end = F.js.task_end;
         role_base = F.js.role_off; nroles = F.js.n_roles;
@@ -847,7 +981,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         if (o == cta) {
           const long long t0_ = PROF ? clock64() : 0;
           asm volatile("bar.sync 1, 64;" ::: "memory");  // join the evaluator warp
-          nb.score = F.ev_score; nb.node = F.ev_node; nb.cnt = F.ev_cnt;
+          nb.score = F.ev_score; nb.node = F.ev_node; nb.cnt = F.ev_cnt; pub_m = F.run_m;
           if (PROF) {
             // the barrier blocks lazily: read the clock only after a value that needs it has arrived
             long long tj;
@@ -857,11 +991,12 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           }
         } else {
           t_join = 0;
-          const unsigned tag = (pub_pc + 1u) & 0x3fffffffu;
+          const unsigned tag = (pub_pc + 1u) & RUN_TAG_MASK;
           const uint4 *ent = p.ring + (size_t)(pub_pc % RING_DEPTH) * RING_STRIDE;
           uint4 v;
-          do { v = mbox_load(ent); } while ((v.w >> 2) != tag);
+          do { v = mbox_load(ent); } while ((v.w >> 10) != tag);
           nb = unpack_best(v);
+          pub_m = (int)((v.w >> 2) & 0xffu);
         }
         const int old_cnt = fs.sl_cnt[o];
         g_cnt += nb.cnt - old_cnt;
@@ -1014,13 +1149,77 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         // every placement made while the verdict cache is valid is followed by exactly one publication of the
         // owner CTA's new best; the owner's evaluator warp starts on it now, overlapping the bookkeeping below
         pub_pending = pure && cache_group == grp;
+        // ---- run length: how many placements in a row the control program would make on the winning node if it kept
+        //      winning — the following tasks of this visit that share the group and the role, pass the queue's
+        //      Allocatable gate, and come before ssn.JobReady turns true (the loop breaks there, allocate.go:676) ----
+        int run_L = 1;
+        bool vrun = false;  // the run's placements are one visit each (a Ready job gets one task per visit, allocate.go:676)
+        if (pub_pending && fp.run_max > 1) {
+          // placements (this one included) until ssn.JobReady turns true; <= 0: the job is Ready already
+          int need = 0;
+          if (f_gang_ready) {
+            need = minav - pbe - ready;
+            if (role_min_active) {  // CheckTaskReady: every role of the minimum map at its minimum (job_info.go:1024-1036)
+              bool other_short = false;
+              int need_rl = 0;
+              for (int r = 0; r < nroles; ++r)
+                if ((S.r_flags[r] & VC_ROLE_IN_MIN_MAP) && S.r_occ[r] < S.r_min[r]) {
+                  if (r == rl) need_rl = S.r_min[r] - S.r_occ[r];
+                  else other_short = true;  // placements of this role never make the job Ready
+                }
+              need = other_short ? RUN_MAX + 1 : max(need, need_rl);
+            }
+          }
+          int lim = 0;
+          if (need > 1) {
+            lim = need;
+          } else if (need <= 0 && visit_from_heap && !fp.share_on && q_mirror && !(f_over_prop && (qflags2 & 1u))) {
+            // The visit ends with this placement, the statement commits and the job is pushed back with the key it was
+            // popped with (Ready bit set, no drf share in ssn.JobOrderFn): it is the head of its queue again. The
+            // queue is popped again when ssn.QueueOrderFn does not depend on the share or no other queue is active.
+            bool again = !f_qorder_prop;
+            if (!again) {
+              const int na = __popc(__ballot_sync(0xffffffffu, lane < Q && F.q_active[lane] != 0)) +
+                             __popc(__ballot_sync(0xffffffffu, lane + 32 < Q && F.q_active[lane + 32] != 0));
+              again = na <= 1;  // (the queue of this visit is marked inactive while it is being served or is the one)
+            }
+            if (again) { lim = RUN_MAX; vrun = true; }
+          }
+          if (lim > 1) {
+            const int4 mk = (cursor + lane < task_end) ? __ldg(&p.tmeta[cursor + lane]) : make_int4(-1, -1, -1, 0);
+            const bool same = mk.y == grp && mk.z - role_base == rl;  // lane l: task l+1 of the run
+            const unsigned same_m = __ballot_sync(0xffffffffu, same);
+            const int n_same = same_m == 0xffffffffu ? 32 : __ffs(~same_m) - 1;
+            run_L = min(min(1 + n_same, lim), fp.run_max);
+            if (f_alloc_prop && run_L > 1) {  // queueAllocatable for the placements after this one, per dimension
+              int cdim = run_L;
+              if (lane < R) {
+                const int d = lane;
+                const uint32_t rq_has = t_has & ~3u;
+                const bool counted = d < 2 || ((rq_has & (1u << d)) && d != p.d.pods_dim);
+                // after the first placement attr.allocated carries every requested dimension (proportion.go:475-497)
+                if (counted && req_l > 0.0) {
+                  double qa = qalloc_l + req_l;  // allocated as the gate of placement 1 sees it
+                  const double de = (d < 2 || (qdes_has & (1u << d))) ? qdes_l : 0.0;
+                  int cnt_ok = 1;
+                  while (cnt_ok < run_L && !(qa + req_l > de)) { qa += req_l; cnt_ok += 1; }
+                  cdim = cnt_ok;
+                }
+              }
+              run_L = (int)__reduce_min_sync(0xffffffffu, (unsigned)cdim);
+            }
+          }
+          if (run_L <= 1) vrun = false;
+        }
+        const int att0 = n_att;
         if (pub_pending) {
           pub_owner = g_best_owner; pub_node = best; pub_pc = pc; pc += 1;
           if (pub_owner == cta) {
             __syncwarp();
             if (lane == 0) {
-              F.ev_i = best - nbase; F.ev_ring = (int)(pub_pc % RING_DEPTH); F.ev_tag = (pub_pc + 1u) & 0x3fffffffu;
-              S.cmd = CMD_EVAL;
+              F.ev_i = best - nbase; F.ev_ring = (int)(pub_pc % RING_DEPTH); F.ev_tag = (pub_pc + 1u) & RUN_TAG_MASK;
+              F.run_L = run_L; F.run_att0 = att0;
+              S.cmd = run_L > 1 ? CMD_RUN : CMD_EVAL;
             }
             __syncthreads();  // B1 of CMD_EVAL
             if (PROF) t_post = clock64();
@@ -1036,15 +1235,36 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           ops_score[n_ops] = score;
         }
         n_ops += 1;
+        n_att += 1;
+        int extra = 0;  // further placements of a run on the same node (same group, same role), announced by its publication
+        if (run_L > 1) {
+          const int cnt_run = g_cnt;  // candidates at every placement of the run (only the winner's row changes)
+          resolve();
+          extra = pub_m - 1;
+          if (extra > 0) {
+            if (out_cta && cnt_run != 1) __threadfence();  // the score log entries precede the record that was just read
+            if (lane < extra) {
+              const int tj = __ldg(&p.tmeta[cursor + lane]).x;
+              const int k = n_ops + lane;
+              ops[k * 3 + 0] = tj; ops[k * 3 + 1] = best; ops[k * 3 + 2] = VC_OP_ALLOCATE;
+              if (out_cta) ops_score[k] = cnt_run == 1 ? 0.0 : __ldcg(&fp.score_log[att0 + 1 + lane]);
+            }
+            if (lane == 0) { S.r_pending[rl] -= extra; S.r_occ[rl] += extra; }
+            ready += extra; n_ops += extra; n_att += extra; cursor += extra; n_steps += extra; n_incr += extra;
+            if (vrun) vrun_extra = extra;
+            if (cursor < task_end) meta = __ldg(&p.tmeta[cursor]);
+          }
+        }
         if (c.has_drf) {
-          jalloc_l += req_l;
+          for (int e = 0; e <= extra; ++e) jalloc_l += req_l;
           double sh = 0.0;
           if (lane < R && (lane < 2 || (p.total_has & (1u << lane))) && p.total[lane] >= VC_MIN_RESOURCE) sh = share_of(jalloc_l, p.total[lane]);
           for (int o = 16; o; o >>= 1) sh = fmax(sh, __shfl_xor_sync(0xffffffffu, sh, o));
           jshare = sh;
         }
         if (c.has_proportion && (qflags2 & 1u)) {
-          if (lane < 2 || (lane < R && (t_has & (1u << lane)))) qalloc_l += req_l;
+          if (lane < 2 || (lane < R && (t_has & (1u << lane))))
+            for (int e = 0; e <= extra; ++e) qalloc_l += req_l;
           const uint32_t add = t_has & ~3u & ((1u << R) - 1u);
           if (add) { qalloc_has |= add; qflags2 &= ~2u; }
           double sh = 0.0;
@@ -1115,20 +1335,21 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         for (int k = lane; k < n_ops; k += 32) {
           vc_decision dcs;
           dcs.task = ops[k * 3 + 0]; dcs.node = ops[k * 3 + 1]; dcs.kind = ops[k * 3 + 2];
-          dcs.visit = n_vis; dcs.score = ops_score[k];
+          dcs.visit = n_vis + (vrun_extra ? k : 0); dcs.score = ops_score[k];
           p.decisions[n_dec + k] = dcs;
         }
       }
-      if (out_cta && lane == 0) {
+      if (out_cta && lane <= vrun_extra) {  // one record per visit; a folded run of visits carries one operation each
         vc_visit v;
         v.job = j;
         v.outcome = stmt ? (jready ? VC_VISIT_COMMIT : VC_VISIT_KEEP) : VC_VISIT_DISCARD;
-        v.first_op = n_dec;
-        v.n_ops = stmt ? n_ops : 0;
-        p.visits[n_vis] = v;
+        v.first_op = n_dec + lane;
+        v.n_ops = vrun_extra ? 1 : (stmt ? n_ops : 0);
+        p.visits[n_vis + lane] = v;
       }
       if (stmt) n_dec += n_ops;
-      n_vis += 1;
+      n_vis += 1 + vrun_extra;
+      visit_id += vrun_extra;
       // jobs.Push(job) when committed and tasks remain (allocate.go:334-336)
       if (stmt && jready && cursor < task_end) {
         if (lane == 0) {

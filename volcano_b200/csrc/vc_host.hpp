@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <initializer_list>
 #include <limits>
 #include <vector>
 
@@ -298,6 +299,30 @@ struct BackfillPick {
   std::vector<int> visit_job, visit_begin;  // one visit per job: its slice of `order` is [visit_begin[v], visit_begin[v+1])
   std::vector<int32_t> j_ready, r_occ;    // ReadyTaskNum per job / occupancy per role row after allocate
 };
+// Exactness precondition of the run-length batches: for dimension-major arrays rows[d][n] (node rows a placement
+// updates) and reqs[d][t] (what it adds / subtracts), every value is an integer and max|row_d| + 32 * max|req_d| stays
+// below 2^53 — then row -/+ k * req (k <= 32) and the k sequential updates are the same exactly-representable integers.
+inline bool max_abs_integral(const double *v, size_t n, double &mx) {
+  if (!v) return true;
+  for (size_t i = 0; i < n; ++i) {
+    const double a = std::fabs(v[i]);
+    if (!(a < 9.0e15) || v[i] != std::floor(v[i])) return false;
+    if (a > mx) mx = a;
+  }
+  return true;
+}
+inline bool runs_exact(size_t D, size_t N, size_t T, std::initializer_list<const double *> rows,
+                       std::initializer_list<const double *> reqs) {
+  for (size_t d = 0; d < D; ++d) {
+    double mrow = 0.0, mreq = 0.0;
+    for (const double *r : rows)
+      if (!max_abs_integral(r ? r + d * N : nullptr, N, mrow)) return false;
+    for (const double *q : reqs)
+      if (!max_abs_integral(q ? q + d * T : nullptr, T, mreq)) return false;
+    if (!(mrow + 32.0 * mreq < 9.0e15)) return false;
+  }
+  return true;
+}
 // rank of every object in (CreationTimestamp, UID) order: the fallback of ssn.JobOrderFn / QueueOrderFn
 inline void rank_by(const int64_t *ts, const uint32_t *uid, size_t n, std::vector<uint32_t> &rank) {
   std::vector<int> idx(n);

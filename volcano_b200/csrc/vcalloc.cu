@@ -152,6 +152,7 @@ struct vc_snapshot {
   int fast_ready_word = 0, fast_ready_shift = 0, fast_share_on = 0, heap_total = 0, heap_in_smem = 0;
   bool fast = false;
   uint4 *ring = nullptr;
+  double *d_score_log = nullptr;  // [T] chosen-node score per placement attempt of the run-length batches
   int last_full = 0, last_incr = 0;
   // ---- HyperNode tree (vc_snapshot_set_topology) ----
   bool has_topo = false;
@@ -421,7 +422,7 @@ void vc_snapshot_destroy(vc_snapshot *s) {
   if (!s) return;
   free_dense(s);
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
-                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_prof, s->d_wait, s->d_decisions, s->d_visits, s->d_fit, s->d_counters, s->d_bf};
+                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_score_log, s->d_prof, s->d_wait, s->d_decisions, s->d_visits, s->d_fit, s->d_counters, s->d_bf};
   for (void *p : dptrs) if (p) cudaFree(p);
   void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters};
   for (void *p : hptrs) if (p) cudaFreeHost(p);
@@ -1077,6 +1078,13 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   s->h_class.assign(tk->klass, tk->klass + T);
   s->h_task_job.assign(tk->job, tk->job + T);
   tick("host copies for the dense pass");
+  // milli-units / bytes / counts are integers by construction (Quantity.MilliValue / Value); when that holds for the
+  // rows and every request, m placements leave exactly row -/+ m * request: the commit kernel may cover a run of
+  // placements on one node with one publication and k_backfill may run ahead m steps
+  s->rows_integral = vch::runs_exact(R, N, T, {nd->idle, nd->used}, {tk->resreq}) &&
+                     vch::runs_exact(K, N, T, {nd->k8s_requested}, {tk->k8s_req}) &&
+                     vch::runs_exact(2, N, T, {nd->k8s_nonzero_requested}, {tk->k8s_nonzero_req});
+  tick("integrality scan");
   s->alloc_ran = false; s->bf_ran = false;
   s->last_idx_cur = s->dc.last_idx0;
   s->last_dec.clear();
@@ -1096,17 +1104,10 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     k.j_valid.resize(J);
     for (size_t j = 0; j < J; ++j) k.j_valid[j] = vch::job_valid(*conf, *jb, (int)j) ? 1 : 0;
     k.j_alloc0.assign(jb->allocated, jb->allocated + R * J);
-    // milli-units / bytes / counts are integers by construction (Quantity.MilliValue / Value); when that holds for the
-    // rows and every request, m placements leave exactly row -/+ m * request and k_backfill may run ahead m steps
-    auto integral = [](const double *v, size_t n) {
-      for (size_t i = 0; i < n; ++i)
-        if (!(std::fabs(v[i]) < 4e15) || v[i] != std::floor(v[i])) return false;
-      return true;
-    };
-    s->rows_integral = integral(nd->idle, R * N) && integral(nd->used, R * N) && integral(nd->k8s_requested, K * N) &&
-                       integral(nd->k8s_nonzero_requested, 2 * N) && integral(tk->resreq, R * T) && integral(tk->k8s_req, K * T) &&
-                       integral(tk->k8s_nonzero_req, 2 * T) && integral(s->bf.req.data(), s->bf.req.size()) &&
-                       integral(s->bf.kreq.data(), s->bf.kreq.size()) && integral(s->bf.knz.data(), s->bf.knz.size());
+    const size_t Bn = (size_t)s->bf.n;
+    s->rows_integral = s->rows_integral && vch::runs_exact(R, N, Bn, {nd->idle, nd->used}, {s->bf.req.data()}) &&
+                       vch::runs_exact(K, N, Bn, {nd->k8s_requested}, {s->bf.kreq.data()}) &&
+                       vch::runs_exact(2, N, Bn, {nd->k8s_nonzero_requested}, {s->bf.knz.data()});
     for (int t = 0; t < s->bf.n; ++t) {
       if (s->bf.job[t] < 0 || (size_t)s->bf.job[t] >= J) return fail(VC_EINVAL, "backfill task %d: bad job index", t);
       if (s->bf.klass[t] < 0 || (size_t)s->bf.klass[t] >= C) return fail(VC_EINVAL, "backfill task %d: bad class index", t);
@@ -1185,6 +1186,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   if (!s->d_prof) CUDA_TRY(cudaMalloc(&s->d_prof, 16 * sizeof(long long)));
   const size_t ring_bytes = sizeof(uint4) * RING_STRIDE * RING_DEPTH;
   if (!s->ring) CUDA_TRY(cudaMalloc(&s->ring, ring_bytes));
+  if (!s->d_score_log) CUDA_TRY(cudaMalloc(&s->d_score_log, (T + 64) * sizeof(double)));
   if (!s->d_decisions) {
     CUDA_TRY(cudaMalloc(&s->d_decisions, std::max<size_t>(1, T) * sizeof(vc_decision)));
     CUDA_TRY(cudaMalloc(&s->d_visits, (T + J + 1) * sizeof(vc_visit)));
@@ -1262,6 +1264,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   fp.q_share0 = s->q_share0.d(s->in);
   fp.heap_off = s->s_heap_off.d(s->in); fp.ready_word = s->fast_ready_word; fp.ready_shift = s->fast_ready_shift;
   fp.share_on = s->fast_share_on; fp.heap_in_smem = s->heap_in_smem; fp.heap_total = s->heap_total;
+  fp.run_max = (s->rows_integral && !g_tun.commit_norun) ? RUN_MAX : 1;
+  fp.score_log = s->d_score_log;
   // ---- the timed region (vc_stats.commit_ms) starts here: the per-cycle resets and working copies are work
   //      every cycle does, so they are inside it ----
   CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
@@ -1351,6 +1355,10 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->stats.prof_cycles[6] = s->h_counters[5];  // full sweeps (fast kernel)
   r->stats.prof_cycles[7] = s->h_counters[6];  // incremental steps (fast kernel)
   r->stats.prof_cycles[5] = s->h_counters[7];  // owner changes between consecutive publications
+  if (g_tun.prof_owner)
+    fprintf(stderr, "runs: %d publications covering %d placements (%.2f per run), command -> publish %.0f cycles per run\n",
+            s->h_counters[13], s->h_counters[14], (double)s->h_counters[14] / std::max(1, s->h_counters[13]),
+            1024.0 * s->h_counters[15] / std::max(1, s->h_counters[13]));
   if (g_tun.prof_owner)
     fprintf(stderr, "evaluator (all CTAs): %d evaluations, %d speculation hits, %d cache rescans; command -> publish %.0f cycles, "
                     "speculative run-ahead %.0f cycles per evaluation (VC_PROF instance only)\n", s->h_counters[10], s->h_counters[8],
