@@ -249,6 +249,8 @@ struct CtlFast {  // shared-memory state of the fast kernel next to Ctl
   int run_L, run_att0, run_m;
   double ru_score, rl_score;
   int ru_node, rl_node, rl_cnt;
+  double run_sc[RUN_MAX];  // state k of the row (after k further placements): total score, fit category
+  int run_cat[RUN_MAX];
 };
 // node view of row i after `k` further placements of the staged group (k as a double): what eval_pair_fast sees for
 // the states a run walks through. Every quantity is integer-valued (checked at upload), so row -/+ k * request is
@@ -435,13 +437,15 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   }
   // ---- lane roles of the warp-cooperative single-node evaluation (see eval_dirty below) ----
   enum { ROLE_NONE = 0, ROLE_BP = 1, ROLE_LEAST = 2, ROLE_MOST = 3, ROLE_BAL = 4 };
-  const int role = lane < 8 ? ROLE_BP : lane < 10 ? ROLE_LEAST : lane < 12 ? ROLE_MOST : lane < 16 ? ROLE_BAL : ROLE_NONE;
-  const int dk = role == ROLE_BP ? lane : role == ROLE_LEAST ? lane - 8 : role == ROLE_MOST ? lane - 10 : role == ROLE_BAL ? lane - 12 : 0;
+  // both half-warps carry the 16 roles: one call evaluates the node in two states (lanes 0-15 / 16-31)
+  const int hl = lane & 15, half = lane >> 4;
+  const int role = hl < 8 ? ROLE_BP : hl < 10 ? ROLE_LEAST : hl < 12 ? ROLE_MOST : ROLE_BAL;
+  const int dk = role == ROLE_BP ? hl : role == ROLE_LEAST ? hl - 8 : role == ROLE_MOST ? hl - 10 : hl - 12;
   const bool lane_valid = (role == ROLE_BP && dk < R) || role == ROLE_LEAST || role == ROLE_MOST || (role == ROLE_BAL && dk < K);
   const int dk_c = lane_valid ? dk : 0;
   const double *a_base = role == ROLE_BP ? fs.used + dk_c * cap : role == ROLE_BAL ? fs.kreq + dk_c * cap : fs.knz + dk_c * cap;
   const double *al_base = role == ROLE_BP ? fs.alloc + dk_c * cap : fs.kalloc + dk_c * cap;
-  const double *idle_base = fs.idle + ((lane < 8 && lane < R) ? lane : 0) * cap;
+  const double *idle_base = fs.idle + ((hl < 8 && hl < R) ? hl : 0) * cap;
   const int w_d = (role == ROLE_BP && lane_valid) ? c.binpack_dim_weight[dk_c] : 0;
   const double mul_const = role == ROLE_BP ? (double)w_d : (role == ROLE_LEAST || role == ROLE_MOST) ? 100.0 : 1.0;
   // per-group lane operands (refreshed when the staged group record changes)
@@ -462,14 +466,19 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   // `extra` = 1 evaluates the node as it will be after ONE more placement of this same group (speculation: under
   // best-fit scoring the node that just won usually wins again); the adds are the same IEEE operations the real
   // placement performs (node_info.go:467-471, predicates.go:254-255), so the speculative score is bit-identical.
-  auto eval_dirty = [&](int i, int extra, double *score_out) -> int {
-    const uint32_t cs = fs.c_cs[i];
-    const int kx = (extra && c.has_predicates) ? 1 : 0;
+  auto eval_dirty = [&](int i0, int i1, int k0, int k1, uint32_t cs, double *score_out) -> int {
+    // lanes 0-15 evaluate row i0 after k0 further placements of this group, lanes 16-31 row i1 after k1 (0 = as it
+    // is); cs = the static word of the lane's row
+    const int i = half ? i1 : i0;
+    const int k = half ? k1 : k0;
+    const double kf = (double)k;
+    const int hs = half << 4;
+    const int kx = c.has_predicates ? k : 0;
     const bool pod_cap = c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i] + kx;
-    const bool bump = extra && (role == ROLE_BP || kx);
+    const bool bump = k > 0 && (role == ROLE_BP || c.has_predicates);
     const double a0 = a_base[i], alloc = al_base[i], idle0 = idle_base[i];
-    const double a = bump ? a0 + b_val : a0;
-    const double idle = extra ? idle0 - req_fit : idle0;
+    const double a = bump ? a0 + kf * b_val : a0;
+    const double idle = k > 0 ? idle0 - kf * req_fit : idle0;
     const bool bad_fit = fit_on && !le_eps(req_fit, idle);
     const double s = a + b_val;
     const bool nz = alloc != 0.0;
@@ -488,14 +497,14 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     }
     if (role == ROLE_BAL) q = fmin(q, 1.0);
     const double val = scored ? q : 0.0;
-    const unsigned m_bad = __ballot_sync(0xffffffffu, bad_fit);
-    const unsigned m_over = __ballot_sync(0xffffffffu, over);
-    const unsigned m_on = __ballot_sync(0xffffffffu, scored);
+    const unsigned m_bad = (__ballot_sync(0xffffffffu, bad_fit) >> hs) & 0xffffu;
+    const unsigned m_over = (__ballot_sync(0xffffffffu, over) >> hs) & 0xffffu;
+    const unsigned m_on = (__ballot_sync(0xffffffffu, scored) >> hs) & 0xffffu;
     const bool fit = (cs & CS_STATIC_OK) != 0 && !pod_cap && m_bad == 0;
-    // gather the 16 lane results (adding the 0.0 of an inactive lane is exact)
+    // gather the 16 lane results of this half (adding the 0.0 of an inactive lane is exact)
     double v[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = __shfl_sync(0xffffffffu, val, k);
+    for (int kk = 0; kk < 16; ++kk) v[kk] = __shfl_sync(0xffffffffu, val, kk, 16);
     double bp_sum = 0.0;
 #pragma unroll
     for (int d = 0; d < 8; ++d) bp_sum += v[d];
@@ -507,23 +516,23 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     const double total = ((0.0 + v[12]) + v[13]) + (v[14] + 0.0) * 1.0 + v[15];
     const int nf = __popc(fonm);
     // second-level divisions, one per lane
-    const double num2 = lane == 0 ? bp_sum : lane == 1 ? ls : lane == 2 ? ms : total;
-    const double den2 = lane == 0 ? (wsum_g > 0 ? (double)wsum_g : 1.0) : lane == 1 ? (wl > 0.0 ? wl : 1.0)
-                      : lane == 2 ? (wm > 0.0 ? wm : 1.0) : (nf > 0 ? (double)nf : 1.0);
+    const double num2 = hl == 0 ? bp_sum : hl == 1 ? ls : hl == 2 ? ms : total;
+    const double den2 = hl == 0 ? (wsum_g > 0 ? (double)wsum_g : 1.0) : hl == 1 ? (wl > 0.0 ? wl : 1.0)
+                      : hl == 2 ? (wm > 0.0 ? wm : 1.0) : (nf > 0 ? (double)nf : 1.0);
     double q2 = num2 / den2;
     {
       double qq = trunc(q2);
       const double r = fma(-qq, den2, num2);
       qq = r < 0.0 ? qq - 1.0 : (r >= den2 ? qq + 1.0 : qq);
-      if (lane == 1 || lane == 2) q2 = qq;
+      if (hl == 1 || hl == 2) q2 = qq;
     }
-    double bp = __shfl_sync(0xffffffffu, q2, 0);
+    double bp = __shfl_sync(0xffffffffu, q2, 0, 16);
     bp = wsum_g > 0 ? bp : bp_sum;
     bp *= bp_scale;
     bp = (m_over & 0xffu) ? 0.0 : bp;
-    const double least = wl > 0.0 ? __shfl_sync(0xffffffffu, q2, 1) : 0.0;
-    const double most = wm > 0.0 ? __shfl_sync(0xffffffffu, q2, 2) : 0.0;
-    const double mean = __shfl_sync(0xffffffffu, q2, 3);
+    const double least = wl > 0.0 ? __shfl_sync(0xffffffffu, q2, 1, 16) : 0.0;
+    const double most = wm > 0.0 ? __shfl_sync(0xffffffffu, q2, 2, 16) : 0.0;
+    const double mean = __shfl_sync(0xffffffffu, q2, 3, 16);
     double stdv = 0.0;
     if (nf == 2) {
       // the two active fractions in dimension order
@@ -534,9 +543,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     } else if (nf > 2) {
       double sum = 0.0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const double dlt = v[12 + k] - mean;
-        sum = ((fonm >> k) & 1u) ? sum + dlt * dlt : sum;
+      for (int kk = 0; kk < 4; ++kk) {
+        const double dlt = v[12 + kk] - mean;
+        sum = ((fonm >> kk) & 1u) ? sum + dlt * dlt : sum;
       }
       stdv = sqrt(sum / (double)nf);
     }
@@ -549,10 +558,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     const double tdm_sc = (cs & CS_TDM_ORDER_MAX) ? (double)VC_MAX_NODE_SCORE : 0.0;
     double order = 0.0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int kind = ord_kind[k];
+    for (int kk = 0; kk < 3; ++kk) {
+      const int kind = ord_kind[kk];
       const double term = kind == VC_PLUGIN_BINPACK ? bp : kind == VC_PLUGIN_NODEORDER ? no : tdm_sc;
-      order = k < ord_n ? order + term : order;
+      order = kk < ord_n ? order + term : order;
     }
     const bool has_order = !(ord_has_tdm && (cs & CS_TDM_ORDER_ERR));
     *score_out = total_score(c, has_order, has_order ? order : 0.0, 0, 0);
@@ -561,14 +570,14 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   // per-lane operands of eval_dirty for the group record staged in S.trec
   auto stage_ops = [&]() {
     t_has = S.trec.has;
-    req_fit = lane < 8 && lane < R ? S.trec.req[lane] : 0.0;
-    fit_on = lane < R && lane < 8 && (lane < 2 || (t_has & (1u << lane)));
+    req_fit = hl < 8 && hl < R ? S.trec.req[hl] : 0.0;
+    fit_on = hl < R && hl < 8 && (hl < 2 || (t_has & (1u << hl)));
     b_val = !lane_valid ? 0.0 : role == ROLE_BP ? S.trec.req[dk_c] : role == ROLE_BAL ? S.trec.kreq[dk_c] : S.trec.knz[dk_c];
     on_task = role == ROLE_BP ? (lane_valid && (dk_c < 2 || (t_has & (1u << dk_c))) && b_val >= VC_MIN_RESOURCE && w_d >= 0)
             : role == ROLE_BAL ? (lane_valid && !(dk_c >= 2 && b_val == 0.0))
             : (role != ROLE_NONE);
     int wv = (role == ROLE_BP && on_task) ? w_d : 0;
-    for (int o = 4; o; o >>= 1) wv += __shfl_xor_sync(0xffffffffu, wv, o);  // lane 0: sum over lanes 0-7
+    for (int o = 4; o; o >>= 1) wv += __shfl_xor_sync(0xffffffffu, wv, o);  // lane 0: sum over lanes 0-7 (every 8-lane group sums its own)
     wsum_g = __shfl_sync(0xffffffffu, wv, 0);
   };
   // CMD_EVAL (warp 1): re-evaluate node F.ev_i for the cached group, maintain this CTA's best incrementally
@@ -585,7 +594,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     int cat;
     const int rs = (int)(ev_count & 1u);  // written by warp 2 while the previous command was served
     if (F.spec_i[rs] == i && F.spec_group[rs] == my_group) { cat = F.spec_cat[rs]; sc = F.spec_sc[rs]; n_spec_hit += 1; }
-    else cat = eval_dirty(i, 0, &sc);
+    else cat = eval_dirty(i, i, 0, 0, fs.c_cs[i], &sc);
     __syncwarp();
     if (lane == 0) { fs.c_cat[i] = cat; fs.c_score[i] = sc; }
     double bs = F.cta_best_score;
@@ -617,7 +626,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     const long long t0 = PROF ? clock64() : 0;
     const int i = F.ev_i;
     double sc = 0.0;
-    const int cat = eval_dirty(i, 1, &sc);
+    const int cat = eval_dirty(i, i, 1, 1, fs.c_cs[i], &sc);
     const int ws = (int)((ev_count + 1u) & 1u);
     __syncwarp();
     if (lane == 0) { F.spec_sc[ws] = sc; F.spec_cat[ws] = cat; F.spec_group[ws] = my_group; F.spec_i[ws] = i; }
@@ -643,7 +652,25 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       F.ru_score = ru.score; F.ru_node = ru.node;
     }
     __syncwarp();
-    asm volatile("bar.sync 2, 64;" ::: "memory");  // pairs with warp 1
+  };
+  // CMD_RUN, every worker warp: worker e evaluates states 2e and 2e+1 of the row (warp 2 takes the last pair, after
+  // the runner-up), one half-warp per state, with the evaluator of the single-node steps
+  auto run_states = [&]() {
+    const int L = F.run_L;
+    // Evaluation slots in an order that fills the four SM sub-partitions one warp each before doubling up (a warp's
+    // sub-partition is warp % 4; fp64 instructions cost the sub-partition's pipe ~8 cycles each whatever the number of
+    // active lanes, tools/micro/fp64_latency.cu): warps 1, 3, 6, 4, then 5, 7; warp 2 (runner-up first) comes last.
+    int e = warp - 1;
+    if (nwarps == 8) e = warp == 1 ? 0 : warp == 3 ? 1 : warp == 6 ? 2 : warp == 4 ? 3 : warp == 5 ? 4 : warp == 7 ? 5 : 6;
+    else if (warp == 2) e = nwarps - 2;
+    else if (warp > 2) e = warp - 2;
+    if (warp == 2) run_runner_up();
+    if (2 * e < L) {
+      double sc = 0.0;
+      const int cat = eval_dirty(F.ev_i, F.ev_i, 2 * e, 2 * e + 1, fs.c_cs[F.ev_i], &sc);
+      if (hl == 0) { F.run_sc[2 * e + half] = sc; F.run_cat[2 * e + half] = cat; }
+    }
+    asm volatile("bar.sync 2, %0;" ::"r"((nwarps - 1) * 32) : "memory");  // all worker warps
   };
   // CMD_RUN (warp 1): lane l evaluates node F.ev_i as it will be after l further placements of the staged group
   // (state 0 = the row as the control warp's placement left it), with the sweep's own evaluator. The node keeps
@@ -657,22 +684,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     const int L = F.run_L;  // placements the control program allows in a row, the one already applied included
     const int old_cat = fs.c_cat[i];
     const TaskRec &trec = S.trec;
-    const uint32_t cs = fs.c_cs[i];
-    const int kx = c.has_predicates ? lane : 0;
-    double sc = 0.0;
-    int cat = 2;
-    if (lane < L) {
-      // the loop-based evaluator of the general kernel (same IEEE operations in the same order as eval_pair_fast, a
-      // few hundred instructions instead of its fully unrolled few thousand: this warp runs it cold)
-      const RunNodeView nv{fs, trec, i, (double)lane, (double)kx};
-      const bool ok = (cs & CS_STATIC_OK) != 0 && !(c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i] + kx);
-      const int fc = fit_category_t<false>(R, trec, nv);
-      double order = 0.0;
-      const bool has_order = node_order(c, R, K, trec, nv, cs, &order);
-      sc = total_score(c, has_order, has_order ? order : 0.0, 0, 0);
-      cat = (ok && fc == 0) ? 0 : 2;
-    }
-    asm volatile("bar.sync 2, 64;" ::: "memory");  // runner-up ready (warp 2)
+    // states computed by the worker warps (run_states): lane l holds the row after l further placements
+    const double sc = lane < L ? F.run_sc[lane] : 0.0;
+    const int cat = lane < L ? F.run_cat[lane] : 2;
     const double ru_s = F.ru_score;
     const int ru_n = F.ru_node;
     // lane l < L-1: does the node still win in state l (i.e. does placement l+1 of the run land on it too)?
@@ -731,9 +745,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       }
       if (cmd == CMD_SWEEP) sweep_part();
       else if (cmd == CMD_DISCARD) discard_part();
-      else if (cmd == CMD_RUN) {  // warps 1 and 2, paired on named barrier 2; warp 1 signals warp 0 on barrier 1
+      else if (cmd == CMD_RUN) {  // all worker warps, joined on named barrier 2; warp 1 signals warp 0 on barrier 1
+        if (F.cur_group != my_group) { stage_ops(); my_group = F.cur_group; }
+        run_states();
         if (warp == 1) run_eval_and_publish();
-        else if (warp == 2) run_runner_up();
         continue;
       }
       else if (cmd == CMD_EVAL) {  // no block-wide B2: warp 1 signals warp 0 on named barrier 1
@@ -1029,6 +1044,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         const int t = meta.x, grp = meta.y, rl = meta.z - role_base;
         cursor += 1;
         if (cursor < task_end) meta = __ldg(&p.tmeta[cursor]);  // prefetch the next task's record
+        // ... and, one per lane, the records of the next 32 tasks (run length below); the gates hide the latency
+        const int4 mk = (fp.run_max > 1 && cursor + lane < task_end) ? __ldg(&p.tmeta[cursor + lane]) : make_int4(-1, -1, -1, 0);
         if (PROF) t_a = clock64();
         if (grp != cur_group) {  // stage the group's request record (shared: workers read it in sweeps)
           resolve();  // the evaluator works from the record being replaced
@@ -1186,7 +1203,6 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             if (again) { lim = RUN_MAX; vrun = true; }
           }
           if (lim > 1) {
-            const int4 mk = (cursor + lane < task_end) ? __ldg(&p.tmeta[cursor + lane]) : make_int4(-1, -1, -1, 0);
             const bool same = mk.y == grp && mk.z - role_base == rl;  // lane l: task l+1 of the run
             const unsigned same_m = __ballot_sync(0xffffffffu, same);
             const int n_same = same_m == 0xffffffffu ? 32 : __ffs(~same_m) - 1;
@@ -1244,7 +1260,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           if (extra > 0) {
             if (out_cta && cnt_run != 1) __threadfence();  // the score log entries precede the record that was just read
             if (lane < extra) {
-              const int tj = __ldg(&p.tmeta[cursor + lane]).x;
+              const int tj = mk.x;  // lane l: task l+1 of the run
               const int k = n_ops + lane;
               ops[k * 3 + 0] = tj; ops[k * 3 + 1] = best; ops[k * 3 + 2] = VC_OP_ALLOCATE;
               if (out_cta) ops_score[k] = cnt_run == 1 ? 0.0 : __ldcg(&fp.score_log[att0 + 1 + lane]);
@@ -1252,7 +1268,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             if (lane == 0) { S.r_pending[rl] -= extra; S.r_occ[rl] += extra; }
             ready += extra; n_ops += extra; n_att += extra; cursor += extra; n_steps += extra; n_incr += extra;
             if (vrun) vrun_extra = extra;
-            if (cursor < task_end) meta = __ldg(&p.tmeta[cursor]);
+            // the record of the task after the run sits in lane `extra` (31 at most; a lane past the job's end holds -1s)
+            meta.x = __shfl_sync(0xffffffffu, mk.x, extra); meta.y = __shfl_sync(0xffffffffu, mk.y, extra);
+            meta.z = __shfl_sync(0xffffffffu, mk.z, extra); meta.w = __shfl_sync(0xffffffffu, mk.w, extra);
           }
         }
         if (c.has_drf) {

@@ -51,6 +51,7 @@ struct Tunables {
   int commit_threads = 0;   // VC_COMMIT_THREADS: minimum block size
   int commit_generic = 0;   // VC_COMMIT_GENERIC: always the general commit kernel (k_commit)
   int commit_norun = 0;     // VC_COMMIT_NORUN: the incremental kernel without run-length placement batches
+  int run_max = 0;          // VC_RUN_MAX: placements per publication (0 = default: two node states per worker warp, 14)
   int prof = 0;             // VC_PROF: instrumented kernel instances (phase timers)
   int prof_owner = 0;       // VC_PROF_OWNER: owner-path statistics on stderr
   int prof_wait = 0;        // VC_PROF_WAIT: per-CTA all-gather wait of the general kernel on stderr
@@ -65,6 +66,7 @@ struct TunName { const char *name; int Tunables::*field; };
 const TunName kTunNames[] = {
     {"VC_COMMIT_CTAS", &Tunables::commit_ctas}, {"VC_COMMIT_THREADS", &Tunables::commit_threads},
     {"VC_COMMIT_GENERIC", &Tunables::commit_generic}, {"VC_COMMIT_NORUN", &Tunables::commit_norun},
+    {"VC_RUN_MAX", &Tunables::run_max},
     {"VC_PROF", &Tunables::prof}, {"VC_PROF_OWNER", &Tunables::prof_owner}, {"VC_PROF_WAIT", &Tunables::prof_wait},
     {"VC_PROF_UPLOAD", &Tunables::prof_upload}, {"VC_BACKFILL_DEPTH1", &Tunables::backfill_depth1},
     {"VC_EXPAND_ROWS", &Tunables::expand_rows}, {"VC_EXPAND_PLAIN", &Tunables::expand_plain},
@@ -326,6 +328,7 @@ void choose_geometry(vc_snapshot *s) {
   // hypernode-level scores change for every node after every placement: per-step full sweeps (k_commit)
   s->fast = !s->dc.has_future && !s->dc.soft_active && !s->dc.nta_on && s->dc.to_find == 0 && R <= 8 && K <= VC_MAX_KDIMS && !g_tun.commit_generic;
   if (s->fast) {
+    if (g_tun.commit_threads <= 0) s->block = 256;  // 7 worker warps: a run's node states are evaluated two per warp
     size_t rows = 3 * (size_t)R + 2 * (size_t)K + 2 + 1;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + ((sizeof(CtlFast) + 15) & ~(size_t)15) + rows * npc * 8 +
                     (size_t)npc * (8 + 4 * 5) + (size_t)ctas * (8 + 4 + 4) + 64;
@@ -1264,7 +1267,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   fp.q_share0 = s->q_share0.d(s->in);
   fp.heap_off = s->s_heap_off.d(s->in); fp.ready_word = s->fast_ready_word; fp.ready_shift = s->fast_ready_shift;
   fp.share_on = s->fast_share_on; fp.heap_in_smem = s->heap_in_smem; fp.heap_total = s->heap_total;
-  fp.run_max = (s->rows_integral && !g_tun.commit_norun) ? RUN_MAX : 1;
+  fp.run_max = (s->rows_integral && !g_tun.commit_norun)
+                   ? std::max(1, std::min(g_tun.run_max > 0 ? g_tun.run_max : RUN_MAX, std::min(RUN_MAX, 2 * (s->block / 32 - 1)))) : 1;
   fp.score_log = s->d_score_log;
   // ---- the timed region (vc_stats.commit_ms) starts here: the per-cycle resets and working copies are work
   //      every cycle does, so they are inside it ----
