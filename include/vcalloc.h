@@ -15,6 +15,10 @@
  *      :558-694, :709-824; framework/interface.go:41-51)
  *   Action.Execute for "backfill"                        vc_snapshot_set_backfill +
  *     (actions/backfill/backfill.go:58-116, :118-199)      vc_backfill_run
+ *   Action.Execute for "preempt"                         vc_snapshot_set_running +
+ *     (actions/preempt/preempt.go:101-434)                 vc_preempt_run
+ *   Action.Execute for "reclaim"                         vc_snapshot_set_running +
+ *     (actions/reclaim/reclaim.go:56-258)                  vc_reclaim_run
  *   util.PredicateNodes + util.PrioritizeNodes for one    vc_score_matrix
  *     task over []*NodeInfo, i.e. what a PredicateFn /
  *     BatchNodeOrderFn / BestNodeFn plugin would serve
@@ -48,7 +52,7 @@
 extern "C" {
 #endif
 
-#define VC_ABI_VERSION 3
+#define VC_ABI_VERSION 4
 #define VC_MAX_DIMS 16   /* R  */
 #define VC_MAX_KDIMS 4   /* dims seen by the upstream kube-scheduler scorers (cpu, memory, nvidia.com/gpu, ...) */
 #define VC_MAX_WORDS 4   /* 64-bit words per label / taint bitset */
@@ -169,6 +173,7 @@ typedef struct vc_jobs {
 
 /* ---- api.QueueInfo (api/queue_info.go:36-51) + proportion inputs ------------------- */
 #define VC_QUEUE_OPEN 1u
+#define VC_QUEUE_NOT_RECLAIMABLE 2u /* !QueueInfo.Reclaimable(): Queue.Spec.Reclaimable == false (api/queue_info.go) */
 #define VC_RES_HAS_ANY 0x80000000u /* in a *_has word: the ResourceList itself is non-empty */
 typedef struct vc_queues {
   const int32_t *weight;        /* [Q] */
@@ -197,6 +202,7 @@ enum vc_plugin {
   VC_PLUGIN_BINPACK = 7,
   VC_PLUGIN_TDM = 8,
   VC_PLUGIN_NETWORK_TOPOLOGY_AWARE = 9,
+  VC_PLUGIN_CONFORMANCE = 10, /* evictableFn: never evict critical pods (plugins/conformance/conformance.go:46-66) */
   VC_PLUGIN_OTHER = 99 /* conformance, overcommit, ...: no effect on this path */
 };
 /* PluginOption enable flags (conf/scheduler_conf.go:60-107); nil == false unless
@@ -211,7 +217,11 @@ enum vc_plugin {
 #define VC_EN_BEST_NODE 0x080u
 #define VC_EN_OVERUSED 0x100u
 #define VC_EN_ALLOCATABLE 0x200u
-#define VC_EN_ALL 0x3ffu
+#define VC_EN_PREEMPTABLE 0x400u
+#define VC_EN_RECLAIMABLE 0x800u
+#define VC_EN_JOB_STARVING 0x1000u
+#define VC_EN_PREEMPTIVE 0x2000u /* EnablePreemptive: ssn.Preemptive (reclaim.go:145), proportion.go:376-380 */
+#define VC_EN_ALL 0x3fffu
 typedef struct vc_plugin_option {
   int32_t plugin;   /* enum vc_plugin */
   int32_t tier;     /* 0-based tier index; options are listed in tier, then plugin order */
@@ -269,9 +279,36 @@ typedef struct vc_hypernodes {
                                        (FindJobTaskNumOfHyperNode counts subJob.Tasks by NodeName) */
 } vc_hypernodes;
 
+/* ---- node.Tasks: the pods that occupy nodes (api/node_info.go:88) — candidate victims of the preempt and
+   reclaim actions. Their resources are already part of vc_nodes.{idle,used,...}; this table adds what victim
+   selection reads per task. Index space of its own ("running task" r). ---- */
+#define VC_RT_PREEMPTABLE 1u  /* TaskInfo.Preemptable (volcano.sh/preemptable annotation / label) */
+#define VC_RT_RUNNING 2u      /* Status == Running */
+#define VC_RT_BOUND 4u        /* Status == Bound (api.PreemptableStatus: Bound | Running, api/helpers.go:70-77) */
+#define VC_RT_BEST_EFFORT 8u  /* TaskInfo.BestEffort */
+#define VC_RT_CRITICAL 16u    /* conformance: system-cluster-critical / system-node-critical PriorityClassName or
+                                 namespace kube-system (plugins/conformance/conformance.go:50-56) */
+typedef struct vc_running_tasks {
+  int32_t n_tasks;
+  const int32_t *node;           /* [n] node index (TaskInfo.NodeName) */
+  const int32_t *job;            /* [n] job index, -1 when ssn.Jobs lacks it */
+  const int32_t *role;           /* [n] row in the job's role tables (or -1 with job == -1) */
+  const int32_t *priority;       /* [n] TaskInfo.Priority */
+  const int64_t *pod_index;      /* [n] as vc_tasks.pod_index */
+  const int64_t *creation_ts;    /* [n] */
+  const uint32_t *uid_rank;      /* [n] rank of TaskInfo.UID among the running tasks */
+  const double *resreq;          /* [R][n] TaskInfo.Resreq */
+  const uint32_t *req_has;       /* [n] */
+  const double *k8s_req;         /* [K][n] what the predicates plugin's event handler subtracts on eviction */
+  const double *k8s_nonzero_req; /* [K][n] (rows >= 2 unused) */
+  const uint32_t *flags;         /* [n] VC_RT_* */
+} vc_running_tasks;
+#define VC_TASK_PREEMPT_NEVER 1u /* pod.Spec.PreemptionPolicy == Never (preempt.go:437-441, reclaim.go:140-143) */
+
 /* ---- results ----------------------------------------------------------------------- */
 #define VC_OP_ALLOCATE 0 /* Statement.Allocate (framework/statement.go:242-302) */
 #define VC_OP_PIPELINE 1 /* Statement.Pipeline (framework/statement.go:146-200) */
+#define VC_OP_EVICT 2    /* Statement.Evict (framework/statement.go:72-99): decision.task indexes vc_running_tasks */
 typedef struct vc_decision {
   int32_t task;
   int32_t node;
@@ -340,6 +377,11 @@ int vc_snapshot_set_topology(vc_snapshot *s, const vc_hypernodes *topo);
    copied; it stays in effect for later uploads of this snapshot until replaced (n_tasks = 0 clears it). */
 int vc_snapshot_set_backfill(vc_snapshot *s, int32_t n_tasks, const vc_tasks *tasks);
 
+/* Optional, before vc_snapshot_upload: the tasks that occupy nodes (victim candidates of preempt / reclaim) and,
+   per pending task of vc_tasks, VC_TASK_* flags (task_flags may be NULL = all zero). Copied; stays in effect for
+   later uploads until replaced (rt == NULL or n_tasks == 0 clears it). */
+int vc_snapshot_set_running(vc_snapshot *s, const vc_running_tasks *rt, const uint32_t *task_flags);
+
 /* Restrict the node axis of this process to [node_begin, node_end) for node-sharded
    multi-GPU runs; tasks/jobs/queues stay replicated. Default: all nodes. */
 int vc_snapshot_set_shard(vc_snapshot *s, int32_t node_begin, int32_t node_end);
@@ -358,6 +400,22 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out);
    the allocate run left (vc_stats.last_processed_node_index of this result carries it on). VC_EUNSUPPORTED: the
    network-topology-aware plugin weighs a resource BestEffort pods request ("pods" in hypernode.binpack.resources). */
 int vc_backfill_run(vc_snapshot *s, vc_result **out);
+
+/* The preempt action (actions/preempt/preempt.go:101-283, normalPreempt :333-434; topology-aware preemption is not
+   enabled by default and not built) and the reclaim action (actions/reclaim/reclaim.go:56-258) on the session state the
+   preceding actions left (vc_allocate_run, each other). Preemptors are the tasks of vc_tasks that are still Pending.
+   Per preemptor every node is evaluated at once on the device: plugin predicates in their preempt reading
+   (ssn.PredicateForPreemptAction, framework/session.go:679-697: only unresolvable failures reject a node — the
+   pod-count cap does not), total score (util.PrioritizeNodes), victims (filter, ssn.Preemptable / ssn.Reclaimable tier
+   votes, util.ValidateVictims, victim queue order, evict until the preemptor fits FutureIdle) — and the best-ranked
+   node whose attempt succeeds is taken, which is what walking util.SortNodes' order until the first success yields
+   (attempts that fail are discarded without a trace, preempt.go:400-430); reclaim walks the nodes in NodeList order
+   (reclaim.go:180-257). Result: decisions of kind VC_OP_EVICT (task = running-task index) and VC_OP_PIPELINE (task =
+   vc_tasks index) in statement order; one visit per Statement (preempt: per preemptor job and per intra-job
+   preemptor; reclaim: per job), VC_VISIT_COMMIT or VC_VISIT_DISCARD (discarded operations are not reported).
+   VC_EUNSUPPORTED: BestEffort pending tasks in the session (vc_snapshot_set_backfill), soft-topology jobs, sampling. */
+int vc_preempt_run(vc_snapshot *s, vc_result **out);
+int vc_reclaim_run(vc_snapshot *s, vc_result **out);
 
 /* Dense task x node pass on the opening snapshot: feasibility bit (allocate.predicate,
    allocate.go:816-824), total score (util.PrioritizeNodes) of every feasible pair and

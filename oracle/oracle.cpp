@@ -262,7 +262,7 @@ struct Pool {
 // ---------------------------------------------------------------------------------------
 // Session: the snapshot plus everything the plugins keep (framework/session.go:66-164)
 // ---------------------------------------------------------------------------------------
-enum TaskStatus : int8_t { kPending = 0, kAllocated = 1, kPipelined = 2, kBinding = 3 };
+enum TaskStatus : int8_t { kPending = 0, kAllocated = 1, kPipelined = 2, kBinding = 3, kRunning = 4, kBound = 5, kReleasing = 6 };
 
 struct Op { int task; int node; int kind; double score; };  // Statement.operations (framework/statement.go:47-52)
 
@@ -277,7 +277,11 @@ struct Session {
   vc_dims d{};
   vc_conf conf{};
   int N = 0, T = 0, J = 0, Q = 0, C = 0, R = 0, K = 0, Wl = 0, Wt = 0, NR = 0;
-  int T_alloc = 0;  // tasks [0, T_alloc) are allocate's; [T_alloc, T) the BestEffort tasks of the backfill action
+  int T_alloc = 0;  // tasks [0, T_alloc) are allocate's; [T_alloc, T_run0) the BestEffort tasks of the backfill action
+  int T_run0 = -1;  // tasks [T_run0, T) are node.Tasks entries (vc_running_tasks): victim candidates of preempt / reclaim
+  std::vector<uint32_t> rt_flags;           // [T - T_run0] VC_RT_*
+  std::vector<uint32_t> t_flags;            // [T_alloc] VC_TASK_*
+  std::vector<std::vector<int>> node_tasks;  // node.Tasks restricted to those entries, ascending index (canonical order)
   // nodes
   std::vector<double> alloc, idle, used, rel, pip, kalloc, kreq, knz;
   std::vector<int32_t> max_tasks, pod_count, zone;
@@ -608,17 +612,30 @@ bool res_less_equal_with_dimension(const Res &l, const Res &r, const Res &req, i
   return ok;
 }
 // proportion's AllocatableFn through ssn.Allocatable: queueAllocatable, proportion.go:333-348
+bool queue_allocatable(const Session &s, int q, int t) {  // proportion.go:333-348
+  if (!(s.q_flags[q] & VC_QUEUE_OPEN)) return false;
+  const QueueAttr &a = s.qattr[q];
+  Res fu = a.allocated;
+  Res rq = task_res(s, t);
+  res_add(fu, rq, s.R);
+  return res_less_equal_with_dimension(fu, a.deserved, rq, s.R, s.d.pods_dim);
+}
 bool allocatable(const Session &s, int q, int t) {
   for (int i = 0; i < s.conf.n_plugins; ++i) {
     const vc_plugin_option &p = s.conf.plugins[i];
     if (!(p.enabled & VC_EN_ALLOCATABLE)) continue;
     if (p.plugin != VC_PLUGIN_PROPORTION) continue;
-    if (!(s.q_flags[q] & VC_QUEUE_OPEN)) return false;
-    const QueueAttr &a = s.qattr[q];
-    Res fu = a.allocated;
-    Res rq = task_res(s, t);
-    res_add(fu, rq, s.R);
-    if (!res_less_equal_with_dimension(fu, a.deserved, rq, s.R, s.d.pods_dim)) return false;
+    if (!queue_allocatable(s, q, t)) return false;
+  }
+  return true;
+}
+// ssn.Preemptive, framework/session_plugins.go:330-347: proportion's PreemptiveFn is queueAllocatable (proportion.go:376-380)
+bool preemptive(const Session &s, int q, int t) {
+  for (int i = 0; i < s.conf.n_plugins; ++i) {
+    const vc_plugin_option &p = s.conf.plugins[i];
+    if (!(p.enabled & VC_EN_PREEMPTIVE)) continue;
+    if (p.plugin != VC_PLUGIN_PROPORTION) continue;
+    if (!queue_allocatable(s, q, t)) return false;
   }
   return true;
 }
@@ -1566,6 +1583,485 @@ int backfill_execute(Session &s) {
 }
 
 // ---------------------------------------------------------------------------------------
+// The preempt and reclaim actions (actions/preempt/preempt.go, actions/reclaim/reclaim.go)
+//
+// Canonical determinism on top of the allocate contract: node.Tasks (a Go map) is walked in ascending
+// running-task index; util.SortNodes' buckets of equal score keep NodeList order; reclaim's predicateNodes keep
+// NodeList order (the reference's order there is whatever its 16 workers produced).
+// ---------------------------------------------------------------------------------------
+struct EOp { int kind; int task; int node; };  // VC_OP_EVICT / VC_OP_PIPELINE
+
+// ssn.JobStarving, framework/session_plugins.go:482-506
+bool job_starving(const Session &s, int j) {
+  bool has_found = false;
+  int i = 0;
+  while (i < s.conf.n_plugins) {
+    const int tier = s.conf.plugins[i].tier;
+    for (; i < s.conf.n_plugins && s.conf.plugins[i].tier == tier; ++i) {
+      const vc_plugin_option &p = s.conf.plugins[i];
+      if (!(p.enabled & VC_EN_JOB_STARVING)) continue;
+      bool res;
+      if (p.plugin == VC_PLUGIN_GANG) res = s.j_waiting[j] + s.j_ready[j] < s.j_min[j];  // IsStarving, job_info.go:1176-1178
+      else if (p.plugin == VC_PLUGIN_PRIORITY) res = s.j_ready[j] + s.j_waiting[j] < s.j_ntasks[j];  // priority.go:151-154
+      else continue;
+      has_found = true;
+      if (!res) return false;
+    }
+    if (has_found) return true;
+  }
+  return false;
+}
+inline bool rt_flag(const Session &s, int t, uint32_t f) { return (s.rt_flags[t - s.T_run0] & f) != 0; }
+inline bool preemptable_status(const Session &s, int t) { return s.t_status[t] == kRunning || s.t_status[t] == kBound; }
+
+// Statement.Evict, framework/statement.go:72-99
+void stmt_evict(Session &s, std::vector<EOp> &ops, int t) {
+  const int j = s.t_job[t], n = s.t_node[t];
+  if (j >= 0) {  // job.UpdateTaskStatus(reclaimee, Releasing): leaves ReadyTaskNum / the allocated roles
+    s.j_ready[j] -= 1;
+    s.r_occ[s.t_role[t]] -= 1;
+  }
+  s.t_status[t] = kReleasing;
+  // node.UpdateTask = RemoveTask + AddTask(Releasing): Idle and Used end where they were, Releasing grows (node_info.go:435-517)
+  for (int d = 0; d < s.R; ++d) at(s.rel, d, s.N, n) += at(s.req, d, s.T, t);
+  if (j >= 0) on_deallocate_event(s, t, n);
+  ops.push_back({VC_OP_EVICT, t, n});
+}
+// Statement.unevict, framework/statement.go:119-143
+void stmt_unevict(Session &s, int t, int8_t status_before) {
+  const int j = s.t_job[t], n = s.t_node[t];
+  if (j >= 0) {
+    s.j_ready[j] += 1;
+    s.r_occ[s.t_role[t]] += 1;
+  }
+  s.t_status[t] = status_before;
+  for (int d = 0; d < s.R; ++d) at(s.rel, d, s.N, n) -= at(s.req, d, s.T, t);
+  if (j >= 0) on_allocate_event(s, t, n);
+}
+void estmt_pipeline(Session &s, std::vector<EOp> &ops, int t, int n) {  // Statement.Pipeline :146-200
+  std::vector<Op> tmp;
+  stmt_pipeline(s, tmp, t, n, 0.0);
+  ops.push_back({VC_OP_PIPELINE, t, n});
+}
+void estmt_discard(Session &s, std::vector<EOp> &ops) {  // Statement.Discard :357-381, reverse order
+  for (int i = (int)ops.size() - 1; i >= 0; --i) {
+    if (ops[i].kind == VC_OP_EVICT) {
+      stmt_unevict(s, ops[i].task, rt_flag(s, ops[i].task, VC_RT_BOUND) ? kBound : kRunning);
+    } else {
+      std::vector<Op> tmp{{ops[i].task, ops[i].node, VC_OP_PIPELINE, 0.0}};
+      stmt_discard(s, tmp);
+    }
+  }
+  ops.clear();
+}
+
+// ---- plugin victim functions (candidates in the order given) ----
+std::vector<int> gang_victims(const Session &s, const std::vector<int> &cands) {  // gang.go:97-129
+  std::vector<int> out;
+  std::vector<std::pair<int, int>> occ;  // jobOccupiedMap
+  for (int t : cands) {
+    const int j = s.t_job[t];
+    if (j < 0) continue;
+    int *o = nullptr;
+    for (auto &e : occ) if (e.first == j) o = &e.second;
+    if (!o) { occ.push_back({j, s.j_ready[j]}); o = &occ.back().second; }
+    if (*o > s.j_min[j]) { *o -= 1; out.push_back(t); }
+  }
+  return out;
+}
+std::vector<int> priority_victims(const Session &s, int preemptor, const std::vector<int> &cands) {  // priority.go:110-148
+  std::vector<int> out;
+  const int pj = s.t_job[preemptor];
+  for (int t : cands) {
+    const int j = s.t_job[t];
+    if (j < 0) continue;
+    if (j != pj) { if (s.j_prio[j] < s.j_prio[pj]) out.push_back(t); }
+    else if (s.t_prio[t] < s.t_prio[preemptor]) out.push_back(t);
+  }
+  return out;
+}
+double drf_share_of(const Session &s, const std::vector<double> &alloc) {  // drf.calculateShare :566-578
+  double res = 0;
+  for (int d = 0; d < s.R; ++d) {
+    if (d >= 2 && !(s.total.has & (1u << d))) continue;
+    if (!(s.total.v[d] >= kMinResource)) continue;
+    const double sh = share_of(alloc[d], s.total.v[d]);
+    if (sh > res) res = sh;
+  }
+  return res;
+}
+std::vector<int> drf_victims(const Session &s, int preemptor, const std::vector<int> &cands) {  // drf.go:222-261
+  std::vector<int> out;
+  const int pj = s.t_job[preemptor];
+  std::vector<double> lalloc(s.R);
+  for (int d = 0; d < s.R; ++d) lalloc[d] = at(s.j_alloc, d, s.J, pj) + at(s.req, d, s.T, preemptor);
+  const double ls = drf_share_of(s, lalloc);
+  std::vector<std::pair<int, std::vector<double>>> allocations;
+  for (int t : cands) {
+    const int j = s.t_job[t];
+    if (j < 0) continue;
+    std::vector<double> *ra = nullptr;
+    for (auto &e : allocations) if (e.first == j) ra = &e.second;
+    if (!ra) {
+      allocations.push_back({j, std::vector<double>(s.R)});
+      ra = &allocations.back().second;
+      for (int d = 0; d < s.R; ++d) (*ra)[d] = at(s.j_alloc, d, s.J, j);
+    }
+    for (int d = 0; d < s.R; ++d) (*ra)[d] -= at(s.req, d, s.T, t);  // allocations[job].Sub(preemptee.Resreq): mutates the entry
+    const double rs = drf_share_of(s, *ra);
+    if (ls < rs || std::fabs(ls - rs) <= 0.000001) out.push_back(t);  // shareDelta
+  }
+  return out;
+}
+std::vector<int> proportion_victims(const Session &s, const std::vector<int> &cands) {  // proportion.go:286-317
+  std::vector<int> out;
+  std::vector<std::pair<int, Res>> allocations;
+  for (int t : cands) {
+    const int j = s.t_job[t];
+    if (j < 0) continue;
+    const int q = s.j_queue[j];
+    if (q < 0 || !s.qattr[q].exists) continue;
+    Res *al = nullptr;
+    for (auto &e : allocations) if (e.first == q) al = &e.second;
+    if (!al) { allocations.push_back({q, s.qattr[q].allocated}); al = &allocations.back().second; }
+    if (!res_less_equal_zero(*al, s.qattr[q].deserved, s.R)) {
+      const Res rq = task_res(s, t);  // allocated.Sub(reclaimee.Resreq)
+      al->v[0] -= rq.v[0]; al->v[1] -= rq.v[1];
+      if (!al->nilmap)
+        for (int d = 2; d < s.R; ++d)
+          if (rq.has & (1u << d)) { al->has |= 1u << d; al->v[d] -= rq.v[d]; }
+      out.push_back(t);
+    }
+  }
+  return out;
+}
+std::vector<int> conformance_victims(const Session &s, const std::vector<int> &cands) {  // conformance.go:46-63
+  std::vector<int> out;
+  for (int t : cands)
+    if (!rt_flag(s, t, VC_RT_CRITICAL)) out.push_back(t);
+  return out;
+}
+// ssn.Preemptable / ssn.Reclaimable, framework/session_plugins.go:211-307: per tier the plugins' candidate lists are
+// intersected (a nil list re-initialises from the next plugin; an empty answer voids the tier)
+std::vector<int> tier_victims(const Session &s, int preemptor, const std::vector<int> &cands, bool reclaim) {
+  std::vector<int> victims;
+  bool nil = true;
+  int i = 0;
+  while (i < s.conf.n_plugins) {
+    const int tier = s.conf.plugins[i].tier;
+    int k = i;
+    for (; k < s.conf.n_plugins && s.conf.plugins[k].tier == tier; ++k) {
+      const vc_plugin_option &p = s.conf.plugins[k];
+      if (!(p.enabled & (reclaim ? VC_EN_RECLAIMABLE : VC_EN_PREEMPTABLE))) continue;
+      std::vector<int> c;
+      if (p.plugin == VC_PLUGIN_GANG) c = gang_victims(s, cands);
+      else if (p.plugin == VC_PLUGIN_CONFORMANCE) c = conformance_victims(s, cands);
+      else if (p.plugin == VC_PLUGIN_PRIORITY && !reclaim) c = priority_victims(s, preemptor, cands);
+      else if (p.plugin == VC_PLUGIN_DRF && !reclaim) c = drf_victims(s, preemptor, cands);
+      else if (p.plugin == VC_PLUGIN_PROPORTION && reclaim) c = proportion_victims(s, cands);
+      else continue;  // no function registered under this name
+      if (c.empty()) { victims.clear(); nil = true; break; }
+      if (nil) { victims = c; nil = false; }
+      else {
+        std::vector<int> inter;
+        for (int v : victims)
+          for (int x : c)
+            if (v == x) inter.push_back(v);
+        victims = inter;
+        nil = inter.empty();  // `var intersection []*TaskInfo` stays nil without an append
+      }
+    }
+    while (i < s.conf.n_plugins && s.conf.plugins[i].tier == tier) ++i;
+    if (!nil) return victims;
+  }
+  return victims;
+}
+// util.ValidateVictims, util/scheduler_helper.go:313-329
+bool validate_victims(const Session &s, int preemptor, int n, const std::vector<int> &victims) {
+  for (int d = 0; d < s.R; ++d) {
+    double fi = future_idle(s, d, n);
+    for (int v : victims) fi += at(s.req, d, s.T, v);
+    if (d >= 2 && !(s.req_has[preemptor] & (1u << d))) continue;
+    if (!le_eps(at(s.req, d, s.T, preemptor), fi)) return false;
+  }
+  return true;
+}
+// the order ssn.BuildVictimsPriorityQueue pops in (framework/session_plugins.go:1092-1135), no VictimQueueOrderFn registered
+bool victim_less(const Session &s, int l, int r) {
+  const int lj = s.t_job[l], rj = s.t_job[r];
+  if (lj == rj) return !task_order_less(s, l, r);
+  if (lj < 0 || rj < 0) {
+    if (lj < 0 && rj < 0) return !task_order_less(s, l, r);
+    return lj < 0;
+  }
+  if (s.j_queue[lj] != s.j_queue[rj]) return !queue_order_less(s, s.j_queue[lj], s.j_queue[rj]);  // ssn.VictimQueueOrderFn :735-749
+  return !job_order_less(s, lj, rj);
+}
+// plugin predicates as ssn.PredicateForPreemptAction reads them (framework/session.go:679-697): only
+// UnschedulableAndUnresolvable / error statuses reject a node; the pod-count cap is Unschedulable and passes
+bool preempt_predicate(const Session &s, int t, int n) {
+  for (int i = 0; i < s.conf.n_plugins; ++i) {
+    const vc_plugin_option &p = s.conf.plugins[i];
+    if (!(p.enabled & VC_EN_PREDICATE)) continue;
+    if (p.plugin == VC_PLUGIN_PREDICATES) {
+      Session &ms = const_cast<Session &>(s);
+      const int32_t pc = ms.pod_count[n];
+      ms.pod_count[n] = INT32_MIN / 2;  // the cap never binds here
+      const bool ok = predicates_plugin_ok(s, t, n);
+      ms.pod_count[n] = pc;
+      if (!ok) return false;
+    }
+    if (p.plugin == VC_PLUGIN_TDM && !tdm_predicate_ok(s, t, n)) return false;
+  }
+  return true;
+}
+bool preempt_supported(const Session &s) {
+  if (s.T_run0 >= 0 && s.T_run0 != s.T_alloc) return false;  // BestEffort pending tasks in the session
+  for (int j = 0; j < s.J; ++j)
+    if ((s.j_flags[j] & VC_JOB_UNSUPPORTED) || s.job_soft[j]) return false;
+  if (s.has_plugin[VC_PLUGIN_TDM] || s.has_plugin[VC_PLUGIN_NETWORK_TOPOLOGY_AWARE]) return false;
+  return true;
+}
+bool task_fits_future_idle(const Session &s, int t, int n) { return fits_future_idle(s, t, n); }
+
+// pmpt.preempt -> normalPreempt, preempt.go:285-434
+bool preempt_one(Session &s, std::vector<EOp> &stmt, int preemptor, int phase_job /* -1: inter-job phase */) {
+  if (s.t_flags[preemptor] & VC_TASK_PREEMPT_NEVER) return false;  // taskEligibleToPreempt :436-441
+  const int pj = s.t_job[preemptor], q = s.j_queue[pj];
+  std::vector<int> nodes;
+  for (int n = 0; n < s.N; ++n)
+    if (preempt_predicate(s, preemptor, n)) nodes.push_back(n);
+  if (nodes.empty()) return false;
+  std::vector<double> scores;
+  double bs;
+  s.task_alloc_hn = -1;
+  prioritize_and_select(s, preemptor, nodes, &bs, &scores);
+  std::vector<int> order(nodes.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return scores[a] > scores[b]; });  // util.SortNodes
+  for (int oi : order) {
+    const int n = nodes[oi];
+    std::vector<int> preemptees;
+    for (int t : s.node_tasks[n]) {
+      if (!preemptable_status(s, t)) continue;
+      if (!rt_flag(s, t, VC_RT_PREEMPTABLE)) continue;
+      const int j = s.t_job[t];
+      if (phase_job < 0) {
+        if (j < 0) continue;
+        if (!(s.j_queue[j] == q && j != pj)) continue;
+      } else if (j != pj) {
+        continue;
+      }
+      preemptees.push_back(t);
+    }
+    std::vector<int> victims = tier_victims(s, preemptor, preemptees, false);
+    if (!validate_victims(s, preemptor, n, victims)) continue;
+    std::vector<EOp> node_stmt;
+    GoHeap vq;
+    vq.less = [&s](int l, int r) { return victim_less(s, l, r); };
+    for (int v : victims) vq.push(v);
+    while (!vq.empty()) {
+      if (allocatable(s, q, preemptor) && task_fits_future_idle(s, preemptor, n)) break;
+      stmt_evict(s, node_stmt, vq.pop());
+    }
+    if (allocatable(s, q, preemptor) && task_fits_future_idle(s, preemptor, n)) {
+      estmt_pipeline(s, node_stmt, preemptor, n);
+      stmt.insert(stmt.end(), node_stmt.begin(), node_stmt.end());  // stmt.Merge(nodeStmt)
+      return true;
+    }
+    estmt_discard(s, node_stmt);
+  }
+  return false;
+}
+void emit_statement(Session &s, int job, const std::vector<EOp> &ops, bool commit) {
+  vc_visit v;
+  v.job = job; v.first_op = (int32_t)s.decisions.size();
+  v.outcome = commit ? VC_VISIT_COMMIT : VC_VISIT_DISCARD;
+  v.n_ops = commit ? (int32_t)ops.size() : 0;
+  if (commit)
+    for (const EOp &op : ops) {
+      vc_decision d;
+      d.task = op.kind == VC_OP_EVICT ? op.task - s.T_run0 : op.task;
+      d.node = op.node; d.kind = op.kind; d.visit = (int32_t)s.visits.size(); d.score = 0.0;
+      s.decisions.push_back(d);
+    }
+  s.visits.push_back(v);
+}
+// Action.Execute, preempt.go:101-283
+void ensure_running_table(Session &s) {  // a session without vc_running_tasks: no task occupies a node
+  if (s.T_run0 >= 0) return;
+  s.T_run0 = s.T;
+  s.node_tasks.assign(s.N, {});
+  s.t_flags.assign(s.T_alloc, 0u);
+}
+int preempt_execute(Session &s) {
+  s.decisions.clear(); s.visits.clear(); s.fit_errors.clear();
+  ensure_running_table(s);
+  if (!preempt_supported(s)) return VC_EUNSUPPORTED;
+  std::vector<GoHeap> preemptors(s.Q), ptasks(s.J);
+  std::vector<std::vector<int>> under_request(s.Q);
+  std::vector<uint8_t> has_q(s.Q, 0);
+  for (int q = 0; q < s.Q; ++q) preemptors[q].less = [&s](int l, int r) { return job_order_less(s, l, r); };
+  for (int j = 0; j < s.J; ++j) ptasks[j].less = [&s](int l, int r) { return task_order_less(s, l, r); };
+  for (int j = 0; j < s.J; ++j) {
+    if (s.j_flags[j] & VC_JOB_PENDING_PHASE) continue;
+    if (!job_valid(s, j)) continue;
+    const int q = s.j_queue[j];
+    if (q < 0) continue;
+    if (!job_starving(s, j)) continue;
+    has_q[q] = 1;
+    preemptors[q].push(j);
+    under_request[q].push_back(j);
+    for (int t = 0; t < s.T_alloc; ++t)
+      if (s.t_job[t] == j && s.t_status[t] == kPending) ptasks[j].push(t);
+  }
+  GoHeap queues;
+  queues.less = [&s](int l, int r) { return queue_order_less(s, l, r); };
+  for (int q = 0; q < s.Q; ++q)
+    if (has_q[q]) queues.push(q);
+  while (!queues.empty()) {
+    const int q = queues.pop();
+    // preemption between jobs within the queue
+    while (!preemptors[q].empty()) {
+      const int pj = preemptors[q].pop();
+      std::vector<EOp> stmt;
+      bool assigned = false;
+      for (;;) {
+        if (!job_starving(s, pj)) break;
+        if (ptasks[pj].empty()) break;
+        const int preemptor = ptasks[pj].pop();
+        assigned = preempt_one(s, stmt, preemptor, -1);
+      }
+      if (job_pipelined(s, pj)) {
+        emit_statement(s, pj, stmt, true);
+      } else {
+        estmt_discard(s, stmt);
+        emit_statement(s, pj, stmt, false);
+        continue;
+      }
+      if (assigned) preemptors[q].push(pj);
+    }
+    // preemption between tasks within a job
+    for (int j : under_request[q]) {
+      GoHeap intra;
+      intra.less = [&s](int l, int r) { return task_order_less(s, l, r); };
+      for (int t = 0; t < s.T_alloc; ++t)
+        if (s.t_job[t] == j && s.t_status[t] == kPending) intra.push(t);
+      while (!intra.empty()) {
+        const int preemptor = intra.pop();
+        std::vector<EOp> stmt;
+        const bool assigned = preempt_one(s, stmt, preemptor, j);
+        if (!assigned) {
+          estmt_discard(s, stmt);
+          emit_statement(s, j, stmt, false);
+          break;
+        }
+        emit_statement(s, j, stmt, true);
+      }
+    }
+  }
+  return VC_OK;
+}
+
+// ra.reclaimForTask, reclaim.go:170-258
+void reclaim_for_task(Session &s, std::vector<EOp> &stmt, int task, int job) {
+  const int jq = s.j_queue[job];
+  for (int n = 0; n < s.N; ++n) {
+    if (!preempt_predicate(s, task, n)) continue;
+    std::vector<int> reclaimees;
+    for (int t : s.node_tasks[n]) {
+      if (s.t_status[t] != kRunning || !rt_flag(s, t, VC_RT_PREEMPTABLE)) continue;
+      const int j = s.t_job[t];
+      if (j < 0) continue;
+      if (s.j_queue[j] == jq) continue;
+      const int q = s.j_queue[j];
+      if (q < 0 || (s.q_flags[q] & VC_QUEUE_NOT_RECLAIMABLE)) continue;
+      reclaimees.push_back(t);
+    }
+    if (reclaimees.empty()) continue;
+    std::vector<int> victims = tier_victims(s, task, reclaimees, true);
+    if (!validate_victims(s, task, n, victims)) continue;
+    GoHeap vq;
+    vq.less = [&s](int l, int r) { return victim_less(s, l, r); };
+    for (int v : victims) vq.push(v);
+    std::vector<double> avail(s.R);
+    for (int d = 0; d < s.R; ++d) avail[d] = future_idle(s, d, n);
+    auto fits = [&]() {
+      for (int d = 0; d < s.R; ++d) {
+        if (d >= 2 && !(s.req_has[task] & (1u << d))) continue;
+        if (!le_eps(at(s.req, d, s.T, task), avail[d])) return false;
+      }
+      return true;
+    };
+    std::vector<EOp> node_stmt;
+    while (!vq.empty()) {
+      if (fits()) break;
+      const int v = vq.pop();
+      stmt_evict(s, node_stmt, v);
+      for (int d = 0; d < s.R; ++d) avail[d] += at(s.req, d, s.T, v);
+    }
+    if (fits()) {
+      estmt_pipeline(s, node_stmt, task, n);
+      stmt.insert(stmt.end(), node_stmt.begin(), node_stmt.end());
+      return;
+    }
+    estmt_discard(s, node_stmt);
+  }
+}
+// Action.Execute, reclaim.go:56-168
+int reclaim_execute(Session &s) {
+  s.decisions.clear(); s.visits.clear(); s.fit_errors.clear();
+  ensure_running_table(s);
+  if (!preempt_supported(s)) return VC_EUNSUPPORTED;
+  GoHeap queues;
+  queues.less = [&s](int l, int r) { return queue_order_less(s, l, r); };
+  std::vector<uint8_t> q_seen(s.Q, 0);
+  std::vector<GoHeap> preemptors(s.Q), ptasks(s.J);
+  std::vector<uint8_t> has_pre(s.Q, 0), has_tasks(s.J, 0);
+  for (int q = 0; q < s.Q; ++q) preemptors[q].less = [&s](int l, int r) { return job_order_less(s, l, r); };
+  for (int j = 0; j < s.J; ++j) ptasks[j].less = [&s](int l, int r) { return task_order_less(s, l, r); };
+  for (int j = 0; j < s.J; ++j) {
+    if (s.j_flags[j] & VC_JOB_PENDING_PHASE) continue;
+    if (!job_valid(s, j)) continue;
+    const int q = s.j_queue[j];
+    if (q < 0) continue;
+    if (!q_seen[q]) { q_seen[q] = 1; queues.push(q); }
+    if (job_starving(s, j)) {
+      has_pre[q] = 1;
+      preemptors[q].push(j);
+      has_tasks[j] = 1;
+      for (int t = 0; t < s.T_alloc; ++t)
+        if (s.t_job[t] == j && s.t_status[t] == kPending) ptasks[j].push(t);
+    }
+  }
+  while (!queues.empty()) {
+    const int q = queues.pop();
+    if (overused(s, q)) continue;
+    for (;;) {
+      if (!has_pre[q] || preemptors[q].empty()) break;
+      const int job = preemptors[q].pop();
+      std::vector<EOp> stmt;
+      for (;;) {
+        if (!job_starving(s, job)) break;
+        if (!has_tasks[job] || ptasks[job].empty()) break;
+        const int task = ptasks[job].pop();
+        if (s.t_flags[task] & VC_TASK_PREEMPT_NEVER) continue;
+        if (!preemptive(s, q, task)) continue;  // ssn.Preemptive(queue, task); ssn.PrePredicateFn: nil for pods in scope
+        reclaim_for_task(s, stmt, task, job);
+      }
+      if (job_pipelined(s, job)) {
+        emit_statement(s, job, stmt, true);
+      } else {
+        estmt_discard(s, stmt);
+        emit_statement(s, job, stmt, false);
+      }
+      if (!preemptors[q].empty()) queues.push(q);
+    }
+  }
+  return VC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // Dense pass on the opening snapshot (the oracle for vc_score_matrix)
 // ---------------------------------------------------------------------------------------
 void score_matrix(Session &s, uint64_t *mask_out, double *score_out, double *best_score, int32_t *best_node) {
@@ -1724,6 +2220,40 @@ int vco_session_set_backfill(void *h, int32_t n, const vc_tasks *bt) {
   return VC_OK;
 }
 int vco_backfill(void *h) { return backfill_execute(*(Session *)h); }
+// vc_snapshot_set_running for the oracle: node.Tasks entries are appended to the session's task arrays
+int vco_session_set_running(void *h, const vc_running_tasks *rt, const uint32_t *task_flags) {
+  Session &s = *(Session *)h;
+  if (s.T_run0 >= 0) return VC_EINVAL;
+  s.t_flags.assign(s.T_alloc, 0u);
+  if (task_flags) s.t_flags.assign(task_flags, task_flags + s.T_alloc);
+  const size_t T0 = s.T, B = rt ? (size_t)rt->n_tasks : 0, T1 = T0 + B;
+  s.T_run0 = (int)T0;
+  s.node_tasks.assign(s.N, {});
+  if (B == 0) return VC_OK;
+  auto widen = [&](std::vector<double> &v, size_t rows, const double *extra) {
+    std::vector<double> w(rows * T1, 0.0);
+    for (size_t r = 0; r < rows; ++r) {
+      for (size_t t = 0; t < T0; ++t) w[r * T1 + t] = v[r * T0 + t];
+      for (size_t t = 0; t < B; ++t) w[r * T1 + T0 + t] = extra ? extra[r * B + t] : 0.0;
+    }
+    v.swap(w);
+  };
+  widen(s.req, s.R, rt->resreq); widen(s.tkreq, s.K, rt->k8s_req); widen(s.tknz, s.K, rt->k8s_nonzero_req);
+  for (size_t t = 0; t < B; ++t) {
+    s.req_has.push_back(rt->req_has[t]); s.t_job.push_back(rt->job[t]); s.t_class.push_back(0);
+    s.t_role.push_back(rt->role[t]); s.t_prio.push_back(rt->priority[t]);
+    s.t_podidx.push_back(rt->pod_index ? rt->pod_index[t] : -1); s.t_ts.push_back(rt->creation_ts ? rt->creation_ts[t] : 0);
+    s.t_uid.push_back(rt->uid_rank[t]);
+    s.t_status.push_back((rt->flags[t] & VC_RT_RUNNING) ? kRunning : kBound); s.t_node.push_back(rt->node[t]);
+    s.rt_flags.push_back(rt->flags[t]);
+    if (rt->node[t] < 0 || rt->node[t] >= s.N) return VC_EINVAL;
+    s.node_tasks[rt->node[t]].push_back((int)(T0 + t));
+  }
+  s.T = (int)T1;
+  return VC_OK;
+}
+int vco_preempt(void *h) { return preempt_execute(*(Session *)h); }
+int vco_reclaim(void *h) { return reclaim_execute(*(Session *)h); }
 // pickUpPendingTasks order only (backfill_test.go:39-154): indices into the backfill task list
 int vco_backfill_pick_order(void *h, int32_t *out) {
   Session &s = *(Session *)h;

@@ -60,6 +60,9 @@ def lib() -> C.CDLL:
                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.vco_session_set_backfill.argtypes = [_vp, C.c_int32, C.POINTER(abi.vc_tasks)]
         L.vco_backfill.argtypes = [_vp]
+        L.vco_session_set_running.argtypes = [_vp, C.POINTER(abi.vc_running_tasks), C.POINTER(C.c_uint32)]
+        L.vco_preempt.argtypes = [_vp]
+        L.vco_reclaim.argtypes = [_vp]
         L.vco_backfill_pick_order.argtypes = [_vp, _i32p]
         for n in ("vco_num_decisions", "vco_num_visits", "vco_num_fit_errors"):
             getattr(L, n).restype = C.c_size_t
@@ -126,6 +129,11 @@ class OracleSession:
         bt = snap.backfill_tasks()
         if bt is not None and L.vco_session_set_backfill(self.h, snap.B, C.byref(bt)) != 0:
             raise RuntimeError("oracle set_backfill failed")
+        rt = snap.running_tasks()
+        if rt is not None or snap.t_flags.any():
+            tf = snap.t_flags.ctypes.data_as(C.POINTER(C.c_uint32)) if snap.T else None
+            if L.vco_session_set_running(self.h, C.byref(rt) if rt is not None else None, tf) != 0:
+                raise RuntimeError("oracle set_running failed")
 
     def close(self):
         if self.h:
@@ -159,6 +167,19 @@ class OracleSession:
         rc = lib().vco_backfill(self.h)
         if rc != 0:
             raise RuntimeError(f"oracle backfill rc={rc}")
+        return self._results()
+
+    def preempt(self):
+        """The preempt action on the state the session is in (decision.task of VC_OP_EVICT indexes running_task_keys)."""
+        rc = lib().vco_preempt(self.h)
+        if rc != 0:
+            raise RuntimeError(f"oracle preempt rc={rc}")
+        return self._results()
+
+    def reclaim(self):
+        rc = lib().vco_reclaim(self.h)
+        if rc != 0:
+            raise RuntimeError(f"oracle reclaim rc={rc}")
         return self._results()
 
     def backfill_pick_order(self):

@@ -19,11 +19,22 @@ def oracle_engine():
     from volcano_b200.uthelper import AllocateResult
 
     def run(snap, threads=1):
+        import numpy as np
+        from oracle import pyoracle
         s = OracleSession(snap, threads=threads)
-        dec, vis, fe = s.allocate()
+        actions = [a for a in snap.actions if a != "enqueue"]
+        if "allocate" in actions or not any(a in ("preempt", "reclaim") for a in actions):
+            dec, vis, fe = s.allocate()
+        else:  # an action list without allocate (the reference's preempt / reclaim unit tests)
+            dec, vis, fe = np.zeros(0, pyoracle.DECISION_DTYPE), np.zeros(0, pyoracle.VISIT_DTYPE), np.zeros(0, np.int32)
         res = AllocateResult(dec, vis, fe)
-        if snap.B > 0 and "backfill" in snap.actions:
-            res.backfill = AllocateResult(*s.backfill())
+        for a in actions:  # the configured order (scheduler.go:124-153)
+            if a == "backfill" and snap.B > 0:
+                res.backfill = AllocateResult(*s.backfill())
+            elif a == "preempt":
+                res.preempt = AllocateResult(*s.preempt())
+            elif a == "reclaim":
+                res.reclaim = AllocateResult(*s.reclaim())
         if snap.hn_job_soft is not None and snap.hn_job_soft.any():
             import numpy as np
             from oracle import pyoracle

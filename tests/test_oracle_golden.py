@@ -363,3 +363,19 @@ def test_select_best_node(score_map, expected_nodes, expected_score):
     assert bs.value == expected_score
     if len(expected_nodes) > 1:
         assert got == min(expected_nodes)
+
+
+@pytest.mark.parametrize("case", G.preempt_cases(), ids=lambda c: c.Name[:50])
+def test_preempt_goldens(case, oracle_engine):
+    """actions/preempt/preempt_test.go:54-425 TestPreempt on the oracle's restatement of the preempt action."""
+    case.RegisterSession(G.preempt_tiers(), actions=("preempt",))
+    case.Run(oracle_engine)
+    assert case.CheckAll() is None, case.CheckAll()
+
+
+@pytest.mark.parametrize("plugins,case", G.reclaim_cases(), ids=lambda c: getattr(c, "Name", "p")[:50])
+def test_reclaim_goldens(plugins, case, oracle_engine):
+    """actions/reclaim/reclaim_test.go:47-388 TestReclaim on the oracle's restatement of the reclaim action."""
+    case.RegisterSession(G.reclaim_tiers(plugins), actions=("reclaim",))
+    case.Run(oracle_engine)
+    assert case.CheckAll() is None, case.CheckAll()

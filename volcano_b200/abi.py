@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-VC_ABI_VERSION = 3
+VC_ABI_VERSION = 4
 VC_MAX_DIMS = 16
 VC_MAX_KDIMS = 4
 VC_MAX_WORDS = 4
@@ -32,6 +32,7 @@ VC_JOB_UNSUPPORTED = 4
 VC_ROLE_EMPTY_NAME = 1
 VC_ROLE_IN_MIN_MAP = 2
 VC_QUEUE_OPEN = 1
+VC_QUEUE_NOT_RECLAIMABLE = 2
 VC_RES_HAS_ANY = 0x80000000
 
 VC_PLUGIN_PRIORITY = 1
@@ -43,6 +44,7 @@ VC_PLUGIN_NODEORDER = 6
 VC_PLUGIN_BINPACK = 7
 VC_PLUGIN_TDM = 8
 VC_PLUGIN_NETWORK_TOPOLOGY_AWARE = 9
+VC_PLUGIN_CONFORMANCE = 10
 VC_PLUGIN_OTHER = 99
 PLUGIN_IDS = {
     "priority": VC_PLUGIN_PRIORITY,
@@ -54,6 +56,7 @@ PLUGIN_IDS = {
     "binpack": VC_PLUGIN_BINPACK,
     "tdm": VC_PLUGIN_TDM,
     "network-topology-aware": VC_PLUGIN_NETWORK_TOPOLOGY_AWARE,
+    "conformance": VC_PLUGIN_CONFORMANCE,
 }
 
 VC_EN_JOB_ORDER = 0x001
@@ -66,7 +69,11 @@ VC_EN_NODE_ORDER = 0x040
 VC_EN_BEST_NODE = 0x080
 VC_EN_OVERUSED = 0x100
 VC_EN_ALLOCATABLE = 0x200
-VC_EN_ALL = 0x3FF
+VC_EN_PREEMPTABLE = 0x400
+VC_EN_RECLAIMABLE = 0x800
+VC_EN_JOB_STARVING = 0x1000
+VC_EN_PREEMPTIVE = 0x2000
+VC_EN_ALL = 0x3FFF
 # conf.PluginOption field name -> flag (conf/scheduler_conf.go:60-107)
 ENABLE_FLAGS = {
     "EnabledJobOrder": VC_EN_JOB_ORDER,
@@ -79,6 +86,10 @@ ENABLE_FLAGS = {
     "EnabledBestNode": VC_EN_BEST_NODE,
     "EnabledOverused": VC_EN_OVERUSED,
     "EnabledAllocatable": VC_EN_ALLOCATABLE,
+    "EnabledPreemptable": VC_EN_PREEMPTABLE,
+    "EnabledReclaimable": VC_EN_RECLAIMABLE,
+    "EnabledJobStarving": VC_EN_JOB_STARVING,
+    "EnablePreemptive": VC_EN_PREEMPTIVE,
 }
 
 VC_PRED_NODE_AFFINITY = 1
@@ -86,6 +97,9 @@ VC_PRED_TAINT_TOLERATION = 2
 
 VC_OP_ALLOCATE = 0
 VC_OP_PIPELINE = 1
+VC_OP_EVICT = 2
+VC_RT_PREEMPTABLE, VC_RT_RUNNING, VC_RT_BOUND, VC_RT_BEST_EFFORT, VC_RT_CRITICAL = 1, 2, 4, 8, 16
+VC_TASK_PREEMPT_NEVER = 1
 VC_VISIT_COMMIT = 0
 VC_VISIT_KEEP = 1
 VC_VISIT_DISCARD = 2
@@ -183,6 +197,13 @@ class vc_hypernodes(C.Structure):
                 ("job_placed_off", C.POINTER(C.c_int32)), ("job_placed_node", C.POINTER(C.c_int32))]
 
 
+class vc_running_tasks(C.Structure):
+    _fields_ = [("n_tasks", C.c_int32), ("node", _i32p), ("job", _i32p), ("role", _i32p), ("priority", _i32p),
+                ("pod_index", _i64p), ("creation_ts", _i64p), ("uid_rank", C.POINTER(C.c_uint32)), ("resreq", _dp),
+                ("req_has", C.POINTER(C.c_uint32)), ("k8s_req", _dp), ("k8s_nonzero_req", _dp),
+                ("flags", C.POINTER(C.c_uint32))]
+
+
 class vc_decision(C.Structure):
     _fields_ = [("task", C.c_int32), ("node", C.c_int32), ("kind", C.c_int32), ("visit", C.c_int32),
                 ("score", C.c_double)]
@@ -212,9 +233,12 @@ SYMBOLS = {
                                      C.POINTER(vc_jobs), C.POINTER(vc_queues), C.POINTER(vc_conf)]),
     "vc_snapshot_set_topology": (C.c_int, [_vp, C.POINTER(vc_hypernodes)]),
     "vc_snapshot_set_backfill": (C.c_int, [_vp, C.c_int32, C.POINTER(vc_tasks)]),
+    "vc_snapshot_set_running": (C.c_int, [_vp, C.POINTER(vc_running_tasks), C.POINTER(C.c_uint32)]),
     "vc_snapshot_set_shard": (C.c_int, [_vp, C.c_int32, C.c_int32]),
     "vc_allocate_run": (C.c_int, [_vp, C.POINTER(_vp)]),
     "vc_backfill_run": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "vc_preempt_run": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "vc_reclaim_run": (C.c_int, [_vp, C.POINTER(_vp)]),
     "vc_score_matrix": (C.c_int, [_vp, _u64p, _dp, _dp, _i32p]),
     "vc_score_matrix_device": (C.c_int, [_vp, C.c_int, _dp, _i64p]),
     "vc_dense_begin": (C.c_int, [_vp]),

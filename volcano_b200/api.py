@@ -144,6 +144,7 @@ class NodeSelectorRequirement:
         return (self.key, self.operator, tuple(self.values))
 
 
+PREEMPTABLE_KEY = "volcano.sh/preemptable"
 REVOCABLE_ZONE = "volcano.sh/revocable-zone"  # v1beta1.RevocableZone
 
 
@@ -184,6 +185,8 @@ class Pod:
     uid: str = ""
     preemptable: bool = False
     revocable_zone: str = ""  # annotation volcano.sh/revocable-zone
+    preemption_policy: str = ""    # pod.Spec.PreemptionPolicy ("Never": the pod never preempts / reclaims)
+    priority_class_name: str = ""  # pod.Spec.PriorityClassName (conformance: system-*-critical pods are never evicted)
 
     def __post_init__(self):
         if not self.uid:
@@ -228,6 +231,7 @@ class Queue:
     priority: int = 0
     state: str = "Open"
     creation_ts: int = 0
+    reclaimable: bool = True  # Queue.Spec.Reclaimable (nil = true, api/queue_info.go:80-95)
 
 
 @dataclass
@@ -254,6 +258,31 @@ def BuildNode(name: str, alloc: ResourceList, labels: Optional[Dict[str, str]] =
 def BuildPod(namespace, name, node_name, phase, req, group_name, labels=None, selector=None) -> Pod:
     return Pod(namespace=namespace, name=name, node_name=node_name, phase=phase, requests=dict(req or {}),
                group_name=group_name, labels=dict(labels or {}), node_selector=dict(selector or {}))
+
+
+def pod_preemptable(pod: "Pod") -> bool:
+    """GetPodPreemptable, api/pod_info.go:125-151: annotation, then label volcano.sh/preemptable (strconv.ParseBool);
+    absent = true."""
+    for src in (pod.annotations, pod.labels):
+        if PREEMPTABLE_KEY in src:
+            v = str(src[PREEMPTABLE_KEY])
+            if v in ("1", "t", "T", "TRUE", "true", "True"):
+                return True
+            return False  # "0", "f", ... and unparsable values
+    return True
+
+
+def pod_critical(pod: "Pod") -> bool:
+    """conformance evictableFn, plugins/conformance/conformance.go:50-56."""
+    return pod.priority_class_name in ("system-cluster-critical", "system-node-critical") or pod.namespace == "kube-system"
+
+
+def BuildPodWithPreemptionPolicy(namespace, name, node_name, phase, req, group_name, labels=None, selector=None,
+                                 preemption_policy: str = "") -> Pod:
+    """util/test_utils.go:328-333."""
+    p = BuildPod(namespace, name, node_name, phase, req, group_name, labels, selector)
+    p.preemption_policy = preemption_policy
+    return p
 
 
 def BuildPodWithPriority(namespace, name, node_name, phase, req, group_name, labels=None, selector=None,

@@ -19,7 +19,7 @@ import numpy as np
 from . import abi
 from .api import (HyperNode, Node, Pod, PodGroup, Queue, TASK_PRIORITY_ANNOTATION, allocated_status, get_task_role,
                   get_task_status, pod_index_under_task, quantity_milli, quantity_value, Taint, Toleration,
-                  NodeSelectorRequirement)
+                  NodeSelectorRequirement, pod_critical, pod_preemptable)
 
 
 # ---------------------------------------------------------------------------------------
@@ -200,6 +200,8 @@ class Snapshot:
     def __init__(self, N, T, J, Q, C_, NR, R, K=3, Wl=1, Wt=1, Z=0, pods_dim=-1, B=0):
         self.N, self.T, self.J, self.Q, self.C, self.NR, self.R, self.K = N, T, J, Q, C_, NR, R, K
         self.B = B  # BestEffort pending tasks (the backfill action's tasks; not part of T)
+        self.RT = 0  # tasks that occupy nodes (victim candidates of preempt / reclaim), see set_running
+        self.t_flags = np.zeros(T, np.uint32)  # VC_TASK_* per pending task
         self.Wl, self.Wt, self.Z, self.pods_dim = Wl, Wt, Z, pods_dim
         f8, i4, i8, u4, u8 = np.float64, np.int32, np.int64, np.uint32, np.uint64
         # nodes
@@ -324,6 +326,28 @@ class Snapshot:
             _ptr(g("k8s_nonzero_req"), _F64), _ptr(g("job"), _I32), _ptr(g("klass"), _I32),
             _ptr(g("role"), _I32), _ptr(g("priority"), _I32), _ptr(g("pod_index"), _I64),
             _ptr(g("creation_ts"), _I64), _ptr(g("uid_rank"), _U32))
+
+    def set_running(self, n: int):
+        """Allocate the node.Tasks table (vc_running_tasks) for n occupying tasks."""
+        f8, i4, i8, u4 = np.float64, np.int32, np.int64, np.uint32
+        self.RT = n
+        self.rt_node = np.zeros(n, i4); self.rt_job = np.full(n, -1, i4); self.rt_role = np.full(n, -1, i4)
+        self.rt_priority = np.ones(n, i4); self.rt_pod_index = np.full(n, -1, i8); self.rt_creation_ts = np.zeros(n, i8)
+        self.rt_uid_rank = np.arange(n, dtype=u4)
+        self.rt_resreq = np.zeros((self.R, n), f8); self.rt_req_has = np.zeros(n, u4)
+        self.rt_k8s_req = np.zeros((self.K, n), f8); self.rt_k8s_nonzero_req = np.zeros((self.K, n), f8)
+        self.rt_flags = np.zeros(n, u4)
+        self.running_task_keys = [""] * n
+
+    def running_tasks(self) -> Optional[abi.vc_running_tasks]:
+        """The argument of vc_snapshot_set_running, or None when no task occupies a node."""
+        if getattr(self, "RT", 0) <= 0:
+            return None
+        return abi.vc_running_tasks(
+            self.RT, _ptr(self.rt_node, _I32), _ptr(self.rt_job, _I32), _ptr(self.rt_role, _I32),
+            _ptr(self.rt_priority, _I32), _ptr(self.rt_pod_index, _I64), _ptr(self.rt_creation_ts, _I64),
+            _ptr(self.rt_uid_rank, _U32), _ptr(self.rt_resreq, _F64), _ptr(self.rt_req_has, _U32),
+            _ptr(self.rt_k8s_req, _F64), _ptr(self.rt_k8s_nonzero_req, _F64), _ptr(self.rt_flags, _U32))
 
     def backfill_tasks(self) -> Optional[abi.vc_tasks]:
         """The argument of vc_snapshot_set_backfill, or None when the session has no BestEffort pending task."""
@@ -779,6 +803,45 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
 
     fill_tasks("t_", task_pods, task_job, task_class[:T])
     fill_tasks("b_", bf_pods, bf_job, task_class[T:])
+    for t, p in enumerate(task_pods):
+        if p.preemption_policy == "Never":
+            s.t_flags[t] |= abi.VC_TASK_PREEMPT_NEVER
+    # node.Tasks: the pods that can become victims (api.PreemptableStatus: Bound | Running, api/helpers.go:70-77)
+    run_pods = [p for p in pods if p.node_name in nidx and get_task_status(p) in ("Running", "Bound")]
+    s.set_running(len(run_pods))
+    uid_order = np.argsort(np.array([p.uid for p in run_pods], dtype=object), kind="stable") if run_pods else []
+    for rank, r in enumerate(uid_order):
+        s.rt_uid_rank[r] = rank
+    for r, p in enumerate(run_pods):
+        v, has = pod_req(p)
+        s.running_task_keys[r] = p.key
+        s.rt_node[r] = nidx[p.node_name]
+        j = jidx.get(f"{p.namespace}/{p.group_name}", -1)
+        s.rt_job[r] = j
+        s.rt_role[r] = role_rows[j][get_task_role(p)] if j >= 0 else -1
+        prio = 1
+        if p.priority is not None:
+            prio = p.priority
+        if TASK_PRIORITY_ANNOTATION in p.annotations:
+            try:
+                prio = int(p.annotations[TASK_PRIORITY_ANNOTATION])
+            except ValueError:
+                pass
+        s.rt_priority[r] = prio
+        s.rt_pod_index[r] = pod_index_under_task(p.name)
+        s.rt_creation_ts[r] = p.creation_ts
+        s.rt_resreq[:, r] = v
+        s.rt_req_has[r] = has
+        s.rt_k8s_req[:, r] = _k8s_vector(p.requests, False)
+        s.rt_k8s_nonzero_req[:, r] = _k8s_vector(p.requests, True)
+        fl = abi.VC_RT_RUNNING if get_task_status(p) == "Running" else abi.VC_RT_BOUND
+        if pod_preemptable(p):
+            fl |= abi.VC_RT_PREEMPTABLE
+        if is_best_effort(v):
+            fl |= abi.VC_RT_BEST_EFFORT
+        if pod_critical(p):
+            fl |= abi.VC_RT_CRITICAL
+        s.rt_flags[r] = fl
 
     # ---- jobs --------------------------------------------------------------------------------
     uid_order = sorted(range(J), key=lambda j: job_ids[j])
@@ -820,7 +883,7 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
         s.q_weight[qi] = q.weight
         s.q_priority[qi] = q.priority
         s.q_creation_ts[qi] = q.creation_ts
-        s.q_flags[qi] = abi.VC_QUEUE_OPEN if q.state == "Open" else 0
+        s.q_flags[qi] = (abi.VC_QUEUE_OPEN if q.state == "Open" else 0) | (0 if q.reclaimable else abi.VC_QUEUE_NOT_RECLAIMABLE)
         if q.capability:
             v, has = _resource_vector(q.capability, dim_names)
             s.q_capability[:, qi] = v

@@ -28,6 +28,8 @@ class AllocateResult:
     stats: Optional[dict] = None
     job_allocated_hypernodes: Optional[np.ndarray] = None  # subJob.AllocatedHyperNode after the run (topology sessions)
     backfill: Optional["AllocateResult"] = None  # the backfill action's result (task = index into backfill_task_keys)
+    preempt: Optional["AllocateResult"] = None   # the preempt action's result (VC_OP_EVICT: task = index into running_task_keys)
+    reclaim: Optional["AllocateResult"] = None   # the reclaim action's result
 
 
 @dataclass
@@ -42,6 +44,8 @@ class TestCommonStruct:
     ExpectBindMap: Dict[str, str] = field(default_factory=dict)
     ExpectBindsNum: Optional[int] = None
     ExpectPipeLined: Optional[Dict[str, List[str]]] = None  # job -> node names
+    ExpectEvicted: Optional[List[str]] = None   # pod keys handed to the evictor (compared as a multiset, helper.go:299-337)
+    ExpectEvictNum: Optional[int] = None
     TdmZoneActive: Optional[Dict[str, bool]] = None
     HyperNodes: Optional[List[HyperNode]] = None  # HyperNodesMap of the reference harness
 
@@ -80,6 +84,20 @@ class TestCommonStruct:
                     self.binds[key] = node
                 elif op["kind"] == abi.VC_OP_PIPELINE:
                     self.pipelined.setdefault(self.snap.job_names[v["job"]], []).append(node)
+        # FakeEvictor: Statement.Commit -> cache.Evict for every Evict op of a committed statement (statement.go:384-412)
+        self.evicts: List[str] = []
+        for name in ("preempt", "reclaim"):
+            ar = getattr(self.result, name, None)
+            if ar is None:
+                continue
+            for v in ar.visits:
+                if v["outcome"] != abi.VC_VISIT_COMMIT:
+                    continue
+                for op in ar.decisions[v["first_op"]: v["first_op"] + v["n_ops"]]:
+                    if op["kind"] == abi.VC_OP_EVICT:
+                        self.evicts.append(self.snap.running_task_keys[op["task"]])
+                    elif op["kind"] == abi.VC_OP_PIPELINE:
+                        self.pipelined.setdefault(self.snap.job_names[v["job"]], []).append(self.snap.node_names[op["node"]])
         bf = getattr(self.result, "backfill", None)
         if bf is not None:  # Session.Allocate dispatches when ssn.JobReady holds (framework/session.go:785-793)
             for v in bf.visits:
@@ -105,5 +123,15 @@ class TestCommonStruct:
             return f"case {self.Name!r}: expected pipelined {want}, got {got}"
         return None
 
+    def CheckEvict(self) -> Optional[str]:
+        if self.ExpectEvictNum is None and self.ExpectEvicted is None:
+            return None
+        want = sorted(self.ExpectEvicted or [])
+        if self.ExpectEvictNum is not None and self.ExpectEvictNum != len(want):
+            return f"case {self.Name!r}: invalid setting: ExpectEvictNum {self.ExpectEvictNum} vs {want}"
+        if sorted(self.evicts) != want:
+            return f"case {self.Name!r}: expected evictions {want}, got {sorted(self.evicts)}"
+        return None
+
     def CheckAll(self) -> Optional[str]:
-        return self.CheckBind() or self.CheckPipelined()
+        return self.CheckBind() or self.CheckEvict() or self.CheckPipelined()
