@@ -49,3 +49,25 @@ def test_random_clusters_match_oracle(block, oracle_engine):
             assert np.array_equal(res.job_allocated_hypernodes, ref.job_allocated_hypernodes), seed
         checked += 1
     assert checked >= 30
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_random_preempt_reclaim_match_oracle(block, oracle_engine):
+    """The preempt and reclaim actions (alone, after allocate, in either order) on random clusters of running and pending
+    pods (tools/fuzz_evict.py): every statement (evictions, pipelines, commit / discard) identical to the oracle's."""
+    from volcano_b200 import engine
+    engine.init(0)
+    spec = importlib.util.spec_from_file_location("fuzz_evict", os.path.join(ROOT, "tools", "fuzz_evict.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    checked = ops = 0
+    for seed in range(3000 + 60 * block, 3000 + 60 * (block + 1)):
+        tc, tiers, actions = gen.make_case(seed)
+        snap = tc.RegisterSession(tiers, actions=actions)
+        if snap.T == 0 or snap.N == 0 or snap.B > 0:
+            continue
+        ref = oracle_engine(snap)
+        res = engine.gpu_engine(snap)
+        ops += gen.compare(res, ref, seed)
+        checked += 1
+    assert checked >= 40 and ops >= 10

@@ -449,3 +449,41 @@ def test_feasible_node_sampling_vs_oracle(cfg, seed, pct, min_nodes, start, gpu,
     assert np.array_equal(res.decisions, dec) and np.array_equal(res.visits, vis) and np.array_equal(res.fit_errors, fe)
     assert res.stats["last_processed_node_index"] == last
     assert len(dec) > 0
+
+
+def _assert_same_evict(a, b):
+    assert (a is None) == (b is None)
+    if a is None:
+        return
+    assert np.array_equal(a.visits, b.visits), (a.visits, b.visits)
+    for f in ("task", "node", "kind", "visit"):
+        assert np.array_equal(a.decisions[f], b.decisions[f]), f
+
+
+@pytest.mark.parametrize("case", G.preempt_cases(), ids=lambda c: c.Name[:50])
+def test_preempt_goldens(case, gpu, oracle_engine):
+    """actions/preempt/preempt_test.go:54-425 TestPreempt through vc_preempt_run; statements compared with the oracle's."""
+    snap = case.RegisterSession(G.preempt_tiers(), actions=("preempt",))
+    case.Run(gpu.gpu_engine)
+    assert case.CheckAll() is None, case.CheckAll()
+    _assert_same_evict(case.result.preempt, oracle_engine(snap).preempt)
+
+
+@pytest.mark.parametrize("plugins,case", G.reclaim_cases(), ids=lambda c: getattr(c, "Name", "p")[:50])
+def test_reclaim_goldens(plugins, case, gpu, oracle_engine):
+    """actions/reclaim/reclaim_test.go:47-388 TestReclaim through vc_reclaim_run."""
+    snap = case.RegisterSession(G.reclaim_tiers(plugins), actions=("reclaim",))
+    case.Run(gpu.gpu_engine)
+    assert case.CheckAll() is None, case.CheckAll()
+    _assert_same_evict(case.result.reclaim, oracle_engine(snap).reclaim)
+
+
+def test_preempt_action_interface(gpu):
+    """test.Run([]framework.Action{preempt.New()}) like the reference's TestPreempt."""
+    from volcano_b200 import preempt
+    case = G.preempt_cases()[3]
+    case.RegisterSession(G.preempt_tiers(), actions=("preempt",))
+    act = preempt.New("preempt")
+    assert act.Name() == "preempt"
+    case.Run([act])
+    assert case.CheckAll() is None, case.CheckAll()

@@ -1,0 +1,189 @@
+// vc_evict.cuh — device side of the preempt and reclaim actions (actions/preempt/preempt.go, actions/reclaim/reclaim.go).
+//
+// Per preemptor the node-wide part of the action runs here, one thread per node:
+//   k_evict_rank   plugin predicates in their preempt reading (ssn.PredicateForPreemptAction, framework/session.go:
+//                  679-697: only the static, unresolvable failures reject a node; the pod-count cap does not), the
+//                  util.PrioritizeNodes total of the node, and an exact necessary condition of util.ValidateVictims
+//                  (util/scheduler_helper.go:313-329): FutureIdle plus the requests of EVERY task the action's filter
+//                  lets through must cover the preemptor — any victim set the plugins return is a subset of those.
+//   k_evict_pick   preempt: util.SortNodes' first not-yet-tried candidate = arg-max (score, lowest index); reclaim: the
+//                  lowest-index candidate (NodeList order, reclaim.go:180).
+//   k_evict_apply  Statement.Evict / Statement.Pipeline on the node rows the ranking reads (Releasing, Pipelined, the
+//                  upstream NodeInfo sums of the predicates plugin) once the host committed to a node.
+// The victim selection on the one node under trial (tier votes, victim queue order, evict-until-fit) is O(tasks on the
+// node) and runs in the host control loop (vc_evict.hpp), like the reference's action goroutine.
+#pragma once
+#include "vc_device.cuh"
+
+#define EV_MODE_PREEMPT_INTER 0  // victims: other jobs of the preemptor's queue (preempt.go:198-214)
+#define EV_MODE_PREEMPT_INTRA 1  // victims: the preemptor's own job (preempt.go:252-268)
+#define EV_MODE_RECLAIM 2        // victims: Running tasks of other, reclaimable queues (reclaim.go:184-199)
+#define EV_MAX_VICTIMS 256
+
+struct EvictTask {  // the preemptor, staged per launch
+  TaskRec rec;
+  int klass, job, queue, mode;
+};
+struct EvictParams {
+  DevDims d;
+  DevConf c;
+  // node rows: Allocatable / upstream allocatable are inputs; the rest are the working copies the actions share
+  const double *alloc, *kalloc;
+  double *idle, *used, *rel, *pip, *kreq, *knz;
+  int32_t *pod_count;
+  const uint32_t *cstat;  // [C][N]
+  // node.Tasks as CSR over nodes
+  const int32_t *rt_off, *rt_idx;  // [N+1], [RT] running-task ids grouped by node, ascending
+  const double *rt_req;            // [R][RT]
+  const double *rt_kreq, *rt_knz;  // [K][RT]
+  const uint32_t *rt_flags;        // [RT] VC_RT_*
+  const int32_t *rt_job;           // [RT]
+  uint8_t *rt_evicted;             // [RT] 1 = Releasing (evicted in this session)
+  const int32_t *j_queue;          // [J]
+  const uint32_t *q_flags;         // [Q]
+  int RT;
+  // per-preemptor scratch
+  unsigned long long *key;  // [N] order-preserving score key of a candidate
+  uint8_t *cand;            // [N] 1 = candidate, 2 = tried
+  // pick result (mapped pinned memory): node (-1 none), score bits
+  int32_t *pick_node;
+  double *pick_score;
+  // apply command (mapped pinned memory): [0] node, [1] n_victims, [2..] victim running-task ids
+  const int32_t *cmd;
+};
+
+struct EvNodeView {
+  const EvictParams &p;
+  int n;
+  __device__ __forceinline__ double alloc(int d) const { return p.alloc[(size_t)d * p.d.N + n]; }
+  __device__ __forceinline__ double idle(int d) const { return p.idle[(size_t)d * p.d.N + n]; }
+  __device__ __forceinline__ double used(int d) const { return p.used[(size_t)d * p.d.N + n]; }
+  __device__ __forceinline__ double rel(int d) const { return p.rel[(size_t)d * p.d.N + n]; }
+  __device__ __forceinline__ double pip(int d) const { return p.pip[(size_t)d * p.d.N + n]; }
+  __device__ __forceinline__ double kalloc(int k) const { return p.kalloc[(size_t)k * p.d.N + n]; }
+  __device__ __forceinline__ double kreq(int k) const { return p.kreq[(size_t)k * p.d.N + n]; }
+  __device__ __forceinline__ double knz(int k) const { return p.knz[(size_t)k * p.d.N + n]; }
+};
+
+__device__ __forceinline__ unsigned long long ev_score_key(double x) {  // monotone double -> u64
+  unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+
+// the action's candidate filter on one task of node.Tasks
+__device__ __forceinline__ bool ev_filter(const EvictParams &p, const EvictTask &t, int r) {
+  if (p.rt_evicted[r]) return false;
+  const uint32_t f = p.rt_flags[r];
+  if (!(f & VC_RT_PREEMPTABLE)) return false;
+  const int j = p.rt_job[r];
+  if (t.mode == EV_MODE_RECLAIM) {
+    if (!(f & VC_RT_RUNNING) || j < 0) return false;
+    const int q = p.j_queue[j];
+    return q >= 0 && q != t.queue && !(p.q_flags[q] & VC_QUEUE_NOT_RECLAIMABLE);
+  }
+  if (!(f & (VC_RT_RUNNING | VC_RT_BOUND))) return false;
+  if (t.mode == EV_MODE_PREEMPT_INTRA) return j == t.job;
+  return j >= 0 && j != t.job && p.j_queue[j] == t.queue;
+}
+
+__global__ void k_evict_rank(EvictParams p, EvictTask t) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = p.d.N, R = p.d.R, K = p.d.K;
+  if (n >= N) return;
+  const uint32_t cs = p.cstat[(size_t)t.klass * N + n];
+  uint8_t cand = 0;
+  unsigned long long key = 0ull;
+  if (cs & CS_STATIC_OK) {
+    // ValidateVictims can only pass when FutureIdle + every filter-passing task covers the request
+    double pot[VC_MAX_DIMS];
+    for (int d = 0; d < R; ++d)
+      pot[d] = (p.idle[(size_t)d * N + n] + p.rel[(size_t)d * N + n]) - p.pip[(size_t)d * N + n];
+    int n_pass = 0;
+    for (int k = p.rt_off[n]; k < p.rt_off[n + 1]; ++k) {
+      const int r = p.rt_idx[k];
+      if (!ev_filter(p, t, r)) continue;
+      n_pass += 1;
+      for (int d = 0; d < R; ++d) pot[d] += p.rt_req[(size_t)d * p.RT + r];
+    }
+    bool fits = true;
+    for (int d = 0; d < R; ++d) {
+      if (d >= 2 && !(t.rec.has & (1u << d))) continue;
+      if (!le_eps(t.rec.req[d], pot[d])) fits = false;
+    }
+    if (fits && (t.mode != EV_MODE_RECLAIM || n_pass > 0)) {
+      cand = 1;
+      if (t.mode != EV_MODE_RECLAIM) {  // reclaim walks NodeList order, no scores (reclaim.go:172-180)
+        const EvNodeView nv{p, n};
+        double order = 0.0;
+        const bool has_order = node_order(p.c, R, K, t.rec, nv, cs, &order);
+        key = ev_score_key(total_score(p.c, has_order, has_order ? order : 0.0, 0, 0));
+      }
+    }
+  }
+  p.cand[n] = cand;
+  p.key[n] = key;
+}
+
+// one block: the next candidate in the action's node order; `exclude` (>= 0) is marked tried first
+__global__ void k_evict_pick(EvictParams p, int mode, int exclude) {
+  __shared__ unsigned long long s_key[32];
+  __shared__ int s_node[32];
+  const int N = p.d.N;
+  if (exclude >= 0 && threadIdx.x == 0) p.cand[exclude] = 2;
+  __syncthreads();
+  unsigned long long bk = 0ull;
+  int bn = -1;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    if (p.cand[n] != 1) continue;
+    const unsigned long long k = mode == EV_MODE_RECLAIM ? 0ull : p.key[n];
+    if (bn < 0 || k > bk) { bk = k; bn = n; }  // ascending n per thread: the first of equal keys stays
+  }
+  for (int o = 16; o; o >>= 1) {
+    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
+    const int on = __shfl_xor_sync(0xffffffffu, bn, o);
+    if (on >= 0 && (bn < 0 || ok > bk || (ok == bk && on < bn))) { bk = ok; bn = on; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_key[threadIdx.x >> 5] = bk; s_node[threadIdx.x >> 5] = bn; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = (blockDim.x + 31) >> 5;
+    bk = threadIdx.x < nw ? s_key[threadIdx.x] : 0ull;
+    bn = threadIdx.x < nw ? s_node[threadIdx.x] : -1;
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int on = __shfl_xor_sync(0xffffffffu, bn, o);
+      if (on >= 0 && (bn < 0 || ok > bk || (ok == bk && on < bn))) { bk = ok; bn = on; }
+    }
+    if (threadIdx.x == 0) {
+      *p.pick_node = bn;
+      unsigned long long u = (bk & 0x8000000000000000ull) ? (bk & 0x7fffffffffffffffull) : ~bk;
+      *p.pick_score = bn >= 0 && mode != EV_MODE_RECLAIM ? __longlong_as_double((long long)u) : 0.0;
+    }
+  }
+}
+
+// Statement.Evict for every victim (node.UpdateTask: Releasing += Resreq; predicates DeallocateFunc: RemovePod), then
+// Statement.Pipeline of the preemptor (Pipelined += Resreq; predicates AllocateFunc: AddPod) on node cmd[0]
+// `undo` != 0: the inverse (Statement.Discard: UnPipeline, then unevict in reverse order; the sums are integer-valued
+// doubles, so the order of the subtractions does not show)
+__global__ void k_evict_apply(EvictParams p, EvictTask t, int undo) {
+  const int n = p.cmd[0], nv = p.cmd[1];
+  const int N = p.d.N, R = p.d.R, K = p.d.K;
+  const int d = threadIdx.x;
+  const double sg = undo ? -1.0 : 1.0;
+  for (int k = 0; k < nv; ++k) {
+    const int r = p.cmd[2 + k];
+    if (d < R) p.rel[(size_t)d * N + n] += sg * p.rt_req[(size_t)d * p.RT + r];
+    if (p.c.has_predicates) {
+      if (d >= 32 && d < 32 + K) p.kreq[(size_t)(d - 32) * N + n] -= sg * p.rt_kreq[(size_t)(d - 32) * p.RT + r];
+      if (d >= 48 && d < 50) p.knz[(size_t)(d - 48) * N + n] -= sg * p.rt_knz[(size_t)(d - 48) * p.RT + r];
+    }
+    if (d == 63) p.rt_evicted[r] = undo ? 0 : 1;
+  }
+  if (d < R) p.pip[(size_t)d * N + n] += sg * t.rec.req[d];
+  if (p.c.has_predicates) {
+    if (d >= 32 && d < 32 + K) p.kreq[(size_t)(d - 32) * N + n] += sg * t.rec.kreq[d - 32];
+    if (d >= 48 && d < 50) p.knz[(size_t)(d - 48) * N + n] += sg * t.rec.knz[d - 48];
+    if (d == 62) p.pod_count[n] += undo ? nv - 1 : 1 - nv;
+  }
+}

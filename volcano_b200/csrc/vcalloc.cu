@@ -18,6 +18,8 @@
 #include "vc_backfill.cuh"
 #include "vc_commit_fast.cuh"
 #include "vc_device.cuh"
+#include "vc_evict.cuh"
+#include "vc_evict.hpp"
 #include "vc_host.hpp"
 #include "vc_kernels.cuh"
 
@@ -234,6 +236,17 @@ struct vc_snapshot {
   bool rows_integral = false;  // every quantity a placement adds to / subtracts from a node row is integer-valued
   void *d_bf = nullptr;   // device slab of the backfill inputs / outputs
   size_t d_bf_bytes = 0;
+  // ---- preempt / reclaim actions (vc_snapshot_set_running / vc_preempt_run / vc_reclaim_run) ----
+  vch::RunningTasks rt;            // host copy of node.Tasks
+  std::vector<uint32_t> t_flags;   // VC_TASK_* per pending task
+  vch::EvictKeep ek;               // session-open state, kept at every upload
+  vch::EvictSession es;            // session state as the actions so far left it
+  bool es_built = false;
+  std::vector<vc_visit> last_vis;  // visits of the last vc_allocate_run
+  double *w_rel = nullptr;         // working copy of Releasing (Statement.Evict adds to it)
+  void *d_ev = nullptr;            // device slab: running-task table + per-preemptor scratch
+  size_t d_ev_bytes = 0;
+  int32_t *h_ev = nullptr;         // mapped pinned: [0] pick node, [2..3] pick score, [16..] apply command
 };
 
 namespace {
@@ -425,9 +438,9 @@ void vc_snapshot_destroy(vc_snapshot *s) {
   if (!s) return;
   free_dense(s);
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
-                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_score_log, s->d_prof, s->d_wait, s->d_decisions, s->d_visits, s->d_fit, s->d_counters, s->d_bf};
+                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_score_log, s->d_prof, s->d_wait, s->d_decisions, s->d_visits, s->d_fit, s->d_counters, s->d_bf, s->w_rel, s->d_ev};
   for (void *p : dptrs) if (p) cudaFree(p);
-  void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters};
+  void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters, s->h_ev};
   for (void *p : hptrs) if (p) cudaFreeHost(p);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -1090,7 +1103,42 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   tick("integrality scan");
   s->alloc_ran = false; s->bf_ran = false;
   s->last_idx_cur = s->dc.last_idx0;
-  s->last_dec.clear();
+  s->last_dec.clear(); s->last_vis.clear();
+  s->es_built = false;
+  {  // what the preempt / reclaim actions read of the opening session
+    vch::EvictKeep &k = s->ek;
+    k.j_queue.assign(jb->queue, jb->queue + J); k.j_min.assign(jb->min_available, jb->min_available + J);
+    k.j_prio.assign(jb->priority, jb->priority + J); k.j_ntasks.assign(jb->n_tasks_total, jb->n_tasks_total + J);
+    k.j_ready0.assign(jb->ready_num, jb->ready_num + J); k.j_waiting0.assign(jb->waiting_num, jb->waiting_num + J);
+    k.j_pbe.assign(jb->pending_besteffort, jb->pending_besteffort + J);
+    k.j_taskmintotal.assign(jb->task_min_total, jb->task_min_total + J);
+    k.j_roleoff.assign(jb->role_off, jb->role_off + J + 1);
+    k.j_flags.assign(jb->flags, jb->flags + J); k.j_rank = j_rank;
+    k.j_valid.resize(J);
+    for (size_t j = 0; j < J; ++j) k.j_valid[j] = vch::job_valid(*conf, *jb, (int)j) ? 1 : 0;
+    k.j_alloc0.assign(jb->allocated, jb->allocated + R * J);
+    k.r_min.assign(jb->role_min, jb->role_min + NR); k.r_occ0.assign(jb->role_occupied, jb->role_occupied + NR);
+    k.r_pip0.assign(jb->role_pipelined, jb->role_pipelined + NR); k.r_flags.assign(jb->role_flags, jb->role_flags + NR);
+    k.q_prio.assign(qu->priority, qu->priority + Q); k.q_rank = q_rank; k.q_flags.assign(qu->flags, qu->flags + Q);
+    k.t_job.assign(tk->job, tk->job + T); k.t_role.assign(tk->role, tk->role + T);
+    k.t_prio.assign(tk->priority, tk->priority + T); k.t_class.assign(tk->klass, tk->klass + T);
+    if (tk->pod_index) k.t_podidx.assign(tk->pod_index, tk->pod_index + T); else k.t_podidx.assign(T, -1);
+    if (tk->creation_ts) k.t_ts.assign(tk->creation_ts, tk->creation_ts + T); else k.t_ts.assign(T, 0);
+    k.t_uid.assign(tk->uid_rank, tk->uid_rank + T); k.t_has.assign(tk->req_has, tk->req_has + T);
+    k.t_req.assign(tk->resreq, tk->resreq + R * T); k.t_kreq.assign(tk->k8s_req, tk->k8s_req + K * T);
+    k.t_knz.assign(tk->k8s_nonzero_req, tk->k8s_nonzero_req + 2 * T);
+    k.n_idle.assign(nd->idle, nd->idle + R * N);
+    if (nd->releasing) k.n_rel.assign(nd->releasing, nd->releasing + R * N); else k.n_rel.assign(R * N, 0.0);
+    if (nd->pipelined) k.n_pip.assign(nd->pipelined, nd->pipelined + R * N); else k.n_pip.assign(R * N, 0.0);
+    for (int r = 0; r < s->rt.n; ++r) {  // the table of vc_snapshot_set_running against this session's sizes
+      if (s->rt.node[r] < 0 || (size_t)s->rt.node[r] >= N) return fail(VC_EINVAL, "running task %d: bad node index", r);
+      const int j = s->rt.job[r];
+      if (j < -1 || j >= (int)J) return fail(VC_EINVAL, "running task %d: bad job index", r);
+      if (j >= 0 && (s->rt.role[r] < jb->role_off[j] || s->rt.role[r] >= jb->role_off[j + 1]))
+        return fail(VC_EINVAL, "running task %d: role row outside its job", r);
+    }
+    if (!s->t_flags.empty() && s->t_flags.size() != T) return fail(VC_EINVAL, "task flags: %zu entries for %zu tasks", s->t_flags.size(), T);
+  }
   if (s->bf.n > 0) {  // what pickUpPendingTasks (backfill.go:118-199) orders by, as of session open
     vch::BackfillKeep &k = s->bk;
     k.j_queue.assign(jb->queue, jb->queue + J); k.j_min.assign(jb->min_available, jb->min_available + J);
@@ -1310,7 +1358,9 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->visits.assign(s->h_visits, s->h_visits + n_vis);
   r->fit_errors.assign(s->h_fit, s->h_fit + n_fit);
   s->alloc_ran = true; s->bf_ran = false;
-  if (s->bf.n > 0) s->last_dec = r->decisions;  // discarded visits carry no operations
+  s->last_dec = r->decisions;  // discarded visits carry no operations
+  s->last_vis = r->visits;
+  s->es_built = false;  // the session state of the evicting actions is rebuilt from this run's operations
   if (s->topo_any) {
     r->job_alloc.resize(J);
     CUDA_TRY(cudaMemcpy(r->job_alloc.data(), s->d_job_alloc, J * 4, cudaMemcpyDeviceToHost));
@@ -1385,6 +1435,345 @@ const int32_t *vc_result_job_allocated_hypernodes(const vc_result *r, size_t *n_
   return (r && !r->job_alloc.empty()) ? r->job_alloc.data() : nullptr;
 }
 void vc_result_free(vc_result *r) { delete r; }
+
+// ---------------------------------------------------------------------------------------
+// preempt / reclaim (actions/preempt/preempt.go, actions/reclaim/reclaim.go)
+// ---------------------------------------------------------------------------------------
+int vc_snapshot_set_running(vc_snapshot *s, const vc_running_tasks *rt, const uint32_t *task_flags) {
+  if (!s) return fail(VC_EINVAL, "null snapshot");
+  s->uploaded = false;  // validated against the job / role tables by the next upload
+  const size_t T = s->dims.n_tasks, R = s->dims.n_dims, K = s->dims.n_kdims, N = s->dims.n_nodes;
+  s->t_flags.clear();
+  if (task_flags) s->t_flags.assign(task_flags, task_flags + T);
+  vch::RunningTasks &b = s->rt;
+  b = vch::RunningTasks();
+  if (!rt || rt->n_tasks <= 0) return VC_OK;
+  const size_t B = (size_t)rt->n_tasks;
+  if (!rt->node || !rt->job || !rt->role || !rt->priority || !rt->uid_rank || !rt->resreq || !rt->req_has || !rt->k8s_req ||
+      !rt->k8s_nonzero_req || !rt->flags)
+    return fail(VC_EINVAL, "running task table: null array");
+  b.n = (int)B;
+  b.node.assign(rt->node, rt->node + B); b.job.assign(rt->job, rt->job + B); b.role.assign(rt->role, rt->role + B);
+  b.prio.assign(rt->priority, rt->priority + B); b.uid.assign(rt->uid_rank, rt->uid_rank + B);
+  if (rt->pod_index) b.podidx.assign(rt->pod_index, rt->pod_index + B); else b.podidx.assign(B, -1);
+  if (rt->creation_ts) b.ts.assign(rt->creation_ts, rt->creation_ts + B); else b.ts.assign(B, 0);
+  b.has.assign(rt->req_has, rt->req_has + B); b.flags.assign(rt->flags, rt->flags + B);
+  b.req.assign(rt->resreq, rt->resreq + R * B); b.kreq.assign(rt->k8s_req, rt->k8s_req + K * B);
+  b.knz.assign(rt->k8s_nonzero_req, rt->k8s_nonzero_req + K * B);
+  // node.Tasks as CSR, ascending running-task id inside a node (the canonical walk order of the Go map)
+  b.off.assign(N + 1, 0);
+  for (size_t r = 0; r < B; ++r) {
+    if (b.node[r] < 0 || (size_t)b.node[r] >= N) return fail(VC_EINVAL, "running task %zu: bad node index", r);
+    b.off[b.node[r] + 1] += 1;
+  }
+  for (size_t n = 0; n < N; ++n) b.off[n + 1] += b.off[n];
+  b.idx.resize(B);
+  std::vector<int32_t> fill(b.off.begin(), b.off.end() - 1);
+  for (size_t r = 0; r < B; ++r) b.idx[fill[b.node[r]]++] = (int32_t)r;
+  return VC_OK;
+}
+
+namespace {
+
+// session state of the evicting actions: the opening session plus whatever vc_allocate_run did
+int ensure_evict_session(vc_snapshot *s) {
+  const vc_dims &D = s->dims;
+  const size_t N = D.n_nodes, T = D.n_tasks, J = D.n_jobs, Q = D.n_queues, R = D.n_dims, K = D.n_kdims, NR = D.n_roles;
+  if (s->bf.n > 0 || s->bf_ran) return fail(VC_EUNSUPPORTED, "preempt / reclaim: BestEffort pending tasks in the session");
+  if (s->dc.to_find > 0) return fail(VC_EUNSUPPORTED, "preempt / reclaim: feasible-node sampling");
+  if (s->dc.soft_active || s->dc.nta_plugin || vch::has_plugin(s->conf, VC_PLUGIN_TDM))
+    return fail(VC_EUNSUPPORTED, "preempt / reclaim: PreferNoSchedule taints, network-topology-aware and tdm are outside the path");
+  for (uint8_t f : s->h_job_soft)
+    if (f) return fail(VC_EUNSUPPORTED, "preempt / reclaim: jobs with a network topology (preempt.go:131-135)");
+  if (s->es_built) return VC_OK;
+  vch::EvictSession &e = s->es;
+  e = vch::EvictSession();
+  e.conf = &s->conf; e.k = &s->ek; e.rt = &s->rt; e.t_flags = &s->t_flags;
+  if (s->t_flags.empty()) s->t_flags.assign(T, 0u);
+  e.R = (int)R; e.K = (int)K; e.N = (int)N; e.T = (int)T; e.J = (int)J; e.Q = (int)Q; e.pods_dim = D.pods_dim;
+  for (int d = 0; d < VC_MAX_DIMS; ++d) e.total[d] = s->total[d];
+  e.total_has = s->total_has;
+  const vch::EvictKeep &k = s->ek;
+  e.t_status.assign(T, 0);
+  e.j_ready = k.j_ready0; e.j_waiting = k.j_waiting0; e.r_occ = k.r_occ0; e.r_pip = k.r_pip0;
+  e.j_alloc = k.j_alloc0; e.j_share.assign(J, 0.0);
+  e.qattr = s->qattr;
+  e.n_idle = k.n_idle; e.n_rel = k.n_rel; e.n_pip = k.n_pip;
+  e.rt_evicted.assign((size_t)std::max(s->rt.n, 1), 0);
+  e.phase_flipped = s->alloc_ran && !s->conf.enqueue_action_enabled;
+  if (s->dc.has_drf)
+    for (size_t j = 0; j < J; ++j) e.drf_share((int)j);
+  // Statement.Allocate / Pipeline of every kept visit of the allocate action, in order
+  std::vector<double> &idle = e.n_idle;  // the host mirror of Idle moves with allocate's placements
+  for (const vc_decision &op : s->last_dec) {
+    const int t = op.task, j = k.t_job[t], n = op.node;
+    if (op.kind == VC_OP_ALLOCATE) {
+      e.t_status[t] = 1; e.j_ready[j] += 1; e.r_occ[k.t_role[t]] += 1;
+      for (size_t d = 0; d < R; ++d) idle[d * N + n] -= k.t_req[d * T + t];
+    } else {
+      e.t_status[t] = 2; e.j_waiting[j] += 1; e.r_pip[k.t_role[t]] += 1;
+      for (size_t d = 0; d < R; ++d) e.n_pip[d * N + n] += k.t_req[d * T + t];
+    }
+    e.on_allocate(j, e.task_res(t), k.t_req.data(), (int)T, t);
+  }
+  s->last_dec.clear();  // applied (a second evicting action continues from e)
+  // device: working rows (left by allocate, or the opening ones), Releasing, the running-task table, scratch
+  cudaError_t ce;
+  auto ensure = [&](auto *&ptr, size_t bytes) -> cudaError_t {
+    if (ptr) return cudaSuccess;
+    void *q = nullptr;
+    cudaError_t x = cudaMalloc(&q, std::max<size_t>(bytes, 16));
+    ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(q);
+    return x;
+  };
+  if ((ce = ensure(s->w_rel, R * N * 8)) != cudaSuccess) return fail(VC_ECUDA, "cudaMalloc: %s", cudaGetErrorString(ce));
+  CUDA_TRY(cudaMemcpyAsync(s->w_rel, s->n_rel.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+  if (!s->alloc_ran) {
+    CUDA_TRY(cudaMemcpyAsync(s->w_idle, s->n_idle.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->w_used, s->n_used.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->w_pip, s->n_pip.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->w_kreq, s->n_kreq.d(s->in), K * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->w_knz, s->n_knz.d(s->in), 2 * N * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->w_pod_count, s->n_pod_count.d(s->in), N * 4, cudaMemcpyDeviceToDevice, s->stream));
+  }
+  const size_t B = (size_t)std::max(s->rt.n, 1);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_off = take((N + 1) * 4), o_idx = take(B * 4), o_req = take(R * B * 8), o_kreq = take(K * B * 8),
+               o_knz = take(K * B * 8), o_flags = take(B * 4), o_job = take(B * 4), o_ev = take(B), o_key = take(N * 8),
+               o_cand = take(N);
+  if (off > s->d_ev_bytes) {
+    if (s->d_ev) cudaFree(s->d_ev);
+    s->d_ev = nullptr;
+    CUDA_TRY(cudaMalloc(&s->d_ev, off));
+    s->d_ev_bytes = off;
+  }
+  if (!s->h_ev) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&s->h_ev), (16 + 2 + EV_MAX_VICTIMS) * 4, cudaHostAllocMapped));
+  unsigned char *base = reinterpret_cast<unsigned char *>(s->d_ev);
+  CUDA_TRY(cudaMemsetAsync(base, 0, off, s->stream));
+  if (s->rt.n > 0) {
+    const vch::RunningTasks &b = s->rt;
+    CUDA_TRY(cudaMemcpyAsync(base + o_off, b.off.data(), (N + 1) * 4, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_idx, b.idx.data(), B * 4, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_req, b.req.data(), R * B * 8, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_kreq, b.kreq.data(), K * B * 8, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_knz, b.knz.data(), K * B * 8, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_flags, b.flags.data(), B * 4, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_job, b.job.data(), B * 4, cudaMemcpyHostToDevice, s->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  s->es_built = true;
+  (void)NR; (void)o_ev; (void)o_key; (void)o_cand;
+  return VC_OK;
+}
+
+// Action.Execute of preempt (preempt.go:101-283) / reclaim (reclaim.go:56-168)
+int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
+  if (!s || !out) return fail(VC_EINVAL, "null argument");
+  if (!s->uploaded) return fail(VC_EINVAL, "vc_snapshot_upload must precede the action");
+  const double t0 = now_ms();
+  int rc = ensure_evict_session(s);
+  if (rc) return rc;
+  const vc_dims &D = s->dims;
+  const size_t N = D.n_nodes, T = D.n_tasks, J = D.n_jobs, Q = D.n_queues, R = D.n_dims, K = D.n_kdims;
+  vch::EvictSession &e = s->es;
+  const vch::EvictKeep &k = s->ek;
+  const size_t B = (size_t)std::max(s->rt.n, 1);
+  // device parameter block (same slab layout as ensure_evict_session)
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_off = take((N + 1) * 4), o_idx = take(B * 4), o_req = take(R * B * 8), o_kreq = take(K * B * 8),
+               o_knz = take(K * B * 8), o_flags = take(B * 4), o_job = take(B * 4), o_ev = take(B), o_key = take(N * 8),
+               o_cand = take(N);
+  unsigned char *base = reinterpret_cast<unsigned char *>(s->d_ev);
+  EvictParams p;
+  std::memset(&p, 0, sizeof p);
+  p.d = s->dd; p.c = s->dc;
+  p.alloc = s->n_alloc.d(s->in); p.kalloc = s->n_kalloc.d(s->in);
+  p.idle = s->w_idle; p.used = s->w_used; p.rel = s->w_rel; p.pip = s->w_pip; p.kreq = s->w_kreq; p.knz = s->w_knz;
+  p.pod_count = s->w_pod_count; p.cstat = s->cstat;
+  p.rt_off = reinterpret_cast<const int32_t *>(base + o_off); p.rt_idx = reinterpret_cast<const int32_t *>(base + o_idx);
+  p.rt_req = reinterpret_cast<const double *>(base + o_req); p.rt_kreq = reinterpret_cast<const double *>(base + o_kreq);
+  p.rt_knz = reinterpret_cast<const double *>(base + o_knz); p.rt_flags = reinterpret_cast<const uint32_t *>(base + o_flags);
+  p.rt_job = reinterpret_cast<const int32_t *>(base + o_job); p.rt_evicted = base + o_ev;
+  p.j_queue = s->j_queue.d(s->in); p.q_flags = s->q_flags.d(s->in); p.RT = (int)B;
+  p.key = reinterpret_cast<unsigned long long *>(base + o_key); p.cand = base + o_cand;
+  int32_t *dev_h = nullptr;
+  CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&dev_h), s->h_ev, 0));
+  p.pick_node = dev_h; p.pick_score = reinterpret_cast<double *>(dev_h + 2); p.cmd = dev_h + 16;
+  volatile int32_t *h_pick = s->h_ev;
+  int32_t *h_cmd = s->h_ev + 16;
+  int launches = 0, cur_mode = 0;
+  EvictTask et;
+  auto stage = [&](int t, int mode) {
+    std::memset(&et, 0, sizeof et);
+    for (size_t d = 0; d < R; ++d) et.rec.req[d] = k.t_req[d * T + t];
+    for (size_t x = 0; x < K; ++x) et.rec.kreq[x] = k.t_kreq[x * T + t];
+    for (size_t x = 0; x < 2; ++x) et.rec.knz[x] = k.t_knz[x * T + t];
+    et.rec.has = k.t_has[t]; et.rec.klass = k.t_class[t];
+    et.klass = k.t_class[t]; et.job = k.t_job[t]; et.queue = k.j_queue[k.t_job[t]]; et.mode = mode;
+  };
+  vch::Ranker rk;
+  rk.begin = [&](int t, int mode) -> int {
+    stage(t, mode);
+    cur_mode = mode;
+    if (N == 0) return VC_OK;
+    k_evict_rank<<<(unsigned)((N + 127) / 128), 128, 0, s->stream>>>(p, et);
+    launches++;
+    CUDA_TRY(cudaGetLastError());
+    return VC_OK;
+  };
+  rk.next = [&](int exclude, int *node) -> int {
+    *node = -1;
+    if (N == 0) return VC_OK;
+    k_evict_pick<<<1, 1024, 0, s->stream>>>(p, cur_mode, exclude);
+    launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *node = h_pick[0];
+    return VC_OK;
+  };
+  auto apply_cmd = [&](int t, int node, const std::vector<int> &victims, int undo) -> int {
+    if (victims.size() > EV_MAX_VICTIMS) return fail(VC_EUNSUPPORTED, "more than %d victims on one node", EV_MAX_VICTIMS);
+    stage(t, cur_mode);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));  // the previous command has been consumed
+    h_cmd[0] = node; h_cmd[1] = (int32_t)victims.size();
+    for (size_t i = 0; i < victims.size(); ++i) h_cmd[2 + i] = victims[i];
+    k_evict_apply<<<1, 64, 0, s->stream>>>(p, et, undo);
+    launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return VC_OK;
+  };
+  rk.apply = [&](int t, int node, const std::vector<int> &v) { return apply_cmd(t, node, v, 0); };
+  rk.revert = [&](int t, int node, const std::vector<int> &v) { return apply_cmd(t, node, v, 1); };
+
+  vc_result *r = new vc_result();
+  auto emit = [&](int job, const std::vector<vch::EvictOp> &ops, bool commit) {
+    vc_visit v;
+    v.job = job; v.first_op = (int32_t)r->decisions.size();
+    v.outcome = commit ? VC_VISIT_COMMIT : VC_VISIT_DISCARD;
+    v.n_ops = commit ? (int32_t)ops.size() : 0;
+    if (commit)
+      for (const vch::EvictOp &op : ops) {
+        vc_decision d;
+        d.task = op.task; d.node = op.node; d.kind = op.kind; d.visit = (int32_t)r->visits.size(); d.score = 0.0;
+        r->decisions.push_back(d);
+      }
+    r->visits.push_back(v);
+  };
+  auto bail = [&](int code) { delete r; return code; };
+  auto job_pending = [&](int j) { return (k.j_flags[j] & VC_JOB_PENDING_PHASE) && !e.phase_flipped; };
+  auto pending_tasks = [&](int j, vch::GoPQ &pq) {
+    pq.less = [&e](int l, int x) { return e.task_less(l, x); };
+    for (size_t t = 0; t < T; ++t)
+      if (k.t_job[t] == j && e.t_status[t] == 0) pq.push((int)t);
+  };
+  std::vector<vch::GoPQ> preemptors(Q), ptasks(J);
+  for (size_t q = 0; q < Q; ++q) preemptors[q].less = [&e](int l, int x) { return e.job_less(l, x); };
+  vch::GoPQ queues;
+  queues.less = [&e](int l, int x) { return e.queue_less(l, x); };
+  if (!reclaim) {
+    std::vector<std::vector<int>> under_request(Q);
+    std::vector<uint8_t> has_q(Q, 0);
+    for (size_t j = 0; j < J; ++j) {
+      if (job_pending((int)j) || !k.j_valid[j]) continue;
+      const int q = k.j_queue[j];
+      if (q < 0 || !e.job_starving((int)j)) continue;
+      has_q[q] = 1;
+      preemptors[q].push((int)j);
+      under_request[q].push_back((int)j);
+      pending_tasks((int)j, ptasks[j]);
+    }
+    for (size_t q = 0; q < Q; ++q)
+      if (has_q[q]) queues.push((int)q);
+    while (!queues.empty()) {
+      const int q = queues.pop();
+      while (!preemptors[q].empty()) {  // preemption between jobs within the queue, preempt.go:163-243
+        const int pj = preemptors[q].pop();
+        std::vector<vch::EvictOp> stmt;
+        bool assigned = false;
+        for (;;) {
+          if (!e.job_starving(pj) || ptasks[pj].empty()) break;
+          const int t = ptasks[pj].pop();
+          if ((rc = e.try_task(rk, stmt, t, EV_MODE_PREEMPT_INTER, &assigned))) return bail(rc);
+        }
+        if (e.job_pipelined(pj)) {
+          emit(pj, stmt, true);
+        } else {
+          if ((rc = e.discard_applied(rk, stmt))) return bail(rc);
+          emit(pj, stmt, false);
+          continue;
+        }
+        if (assigned) preemptors[q].push(pj);
+      }
+      for (int j : under_request[q]) {  // preemption between tasks within a job, preempt.go:246-280
+        vch::GoPQ intra;
+        pending_tasks(j, intra);
+        while (!intra.empty()) {
+          const int t = intra.pop();
+          std::vector<vch::EvictOp> stmt;
+          bool assigned = false;
+          if ((rc = e.try_task(rk, stmt, t, EV_MODE_PREEMPT_INTRA, &assigned))) return bail(rc);
+          if (!assigned) {
+            if ((rc = e.discard_applied(rk, stmt))) return bail(rc);
+            emit(j, stmt, false);
+            break;
+          }
+          emit(j, stmt, true);
+        }
+      }
+    }
+  } else {
+    std::vector<uint8_t> q_seen(Q, 0), has_pre(Q, 0);
+    for (size_t j = 0; j < J; ++j) {
+      if (job_pending((int)j) || !k.j_valid[j]) continue;
+      const int q = k.j_queue[j];
+      if (q < 0) continue;
+      if (!q_seen[q]) { q_seen[q] = 1; queues.push(q); }
+      if (e.job_starving((int)j)) {
+        has_pre[q] = 1;
+        preemptors[q].push((int)j);
+        pending_tasks((int)j, ptasks[j]);
+      }
+    }
+    while (!queues.empty()) {
+      const int q = queues.pop();
+      if (e.overused(q)) continue;
+      for (;;) {
+        if (!has_pre[q] || preemptors[q].empty()) break;
+        const int job = preemptors[q].pop();
+        std::vector<vch::EvictOp> stmt;
+        for (;;) {
+          if (!e.job_starving(job) || ptasks[job].empty()) break;
+          const int t = ptasks[job].pop();
+          if (s->t_flags[t] & VC_TASK_PREEMPT_NEVER) continue;     // reclaim.go:140-143
+          if (!e.gate(VC_EN_PREEMPTIVE, q, t)) continue;           // ssn.Preemptive, reclaim.go:145-148
+          bool assigned = false;
+          if ((rc = e.try_task(rk, stmt, t, EV_MODE_RECLAIM, &assigned))) return bail(rc);
+        }
+        if (e.job_pipelined(job)) {
+          emit(job, stmt, true);
+        } else {
+          if ((rc = e.discard_applied(rk, stmt))) return bail(rc);
+          emit(job, stmt, false);
+        }
+        if (!preemptors[q].empty()) queues.push(q);
+      }
+    }
+  }
+  r->stats.total_ms = now_ms() - t0;
+  r->stats.commit_ms = r->stats.total_ms;
+  r->stats.kernel_launches = launches;
+  r->stats.n_steps = launches;
+  *out = r;
+  return VC_OK;
+}
+
+}  // namespace
+
+int vc_preempt_run(vc_snapshot *s, vc_result **out) { return run_evict_action(s, false, out); }
+int vc_reclaim_run(vc_snapshot *s, vc_result **out) { return run_evict_action(s, true, out); }
 
 // ---------------------------------------------------------------------------------------
 // backfill (actions/backfill/backfill.go)

@@ -91,6 +91,9 @@ class Engine:
             _check(self.L.vc_snapshot_set_topology(self.h, C.byref(topo)))
         bt = s.backfill_tasks()  # the list stays in effect until replaced: always (re)state it, an empty one clears it
         _check(self.L.vc_snapshot_set_backfill(self.h, s.B, C.byref(bt) if bt is not None else None))
+        rt = s.running_tasks()  # node.Tasks (victim candidates of preempt / reclaim) + per-task flags; restated on every upload
+        tf = s.t_flags.ctypes.data_as(C.POINTER(C.c_uint32)) if s.T else None
+        _check(self.L.vc_snapshot_set_running(self.h, C.byref(rt) if rt is not None else None, tf))
         _check(self.L.vc_snapshot_upload(self.h, C.byref(n), C.byref(t), C.byref(c), C.byref(j), C.byref(q),
                                          C.byref(s.conf)))
         self._uploaded = True
@@ -108,6 +111,22 @@ class Engine:
             self.upload()
         r = C.c_void_p()
         _check(self.L.vc_backfill_run(self.h, C.byref(r)))
+        return self._result(r)
+
+    def preempt(self) -> AllocateResult:
+        """The preempt action on the session state the preceding actions left (VC_OP_EVICT: task indexes
+        snap.running_task_keys)."""
+        if not self._uploaded:
+            self.upload()
+        r = C.c_void_p()
+        _check(self.L.vc_preempt_run(self.h, C.byref(r)))
+        return self._result(r)
+
+    def reclaim(self) -> AllocateResult:
+        if not self._uploaded:
+            self.upload()
+        r = C.c_void_p()
+        _check(self.L.vc_reclaim_run(self.h, C.byref(r)))
         return self._result(r)
 
     def _result(self, r) -> AllocateResult:
@@ -185,9 +204,18 @@ def gpu_engine(snap: Snapshot, device: int = 0) -> AllocateResult:
     e = Engine(snap, device)
     try:
         e.upload()
-        res = e.allocate()
-        if snap.B > 0 and "backfill" in snap.actions:  # the configured action list, scheduler.go:124-153
-            res.backfill = e.backfill()
+        actions = [a for a in snap.actions if a != "enqueue"]  # the configured action list, scheduler.go:124-153
+        if "allocate" in actions or not any(a in ("preempt", "reclaim") for a in actions):
+            res = e.allocate()
+        else:  # an action list without allocate (the reference's preempt / reclaim unit tests)
+            res = AllocateResult(np.zeros(0, DECISION_DTYPE), np.zeros(0, VISIT_DTYPE), np.zeros(0, np.int32))
+        for a in actions:
+            if a == "backfill" and snap.B > 0:
+                res.backfill = e.backfill()
+            elif a == "preempt":
+                res.preempt = e.preempt()
+            elif a == "reclaim":
+                res.reclaim = e.reclaim()
         return res
     finally:
         e.close()
