@@ -401,19 +401,22 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out);
    network-topology-aware plugin weighs a resource BestEffort pods request ("pods" in hypernode.binpack.resources). */
 int vc_backfill_run(vc_snapshot *s, vc_result **out);
 
-/* The preempt action (actions/preempt/preempt.go:101-283, normalPreempt :333-434; topology-aware preemption is not
-   enabled by default and not built) and the reclaim action (actions/reclaim/reclaim.go:56-258) on the session state the
-   preceding actions left (vc_allocate_run, each other). Preemptors are the tasks of vc_tasks that are still Pending.
-   Per preemptor every node is evaluated at once on the device: plugin predicates in their preempt reading
-   (ssn.PredicateForPreemptAction, framework/session.go:679-697: only unresolvable failures reject a node — the
-   pod-count cap does not), total score (util.PrioritizeNodes), victims (filter, ssn.Preemptable / ssn.Reclaimable tier
-   votes, util.ValidateVictims, victim queue order, evict until the preemptor fits FutureIdle) — and the best-ranked
-   node whose attempt succeeds is taken, which is what walking util.SortNodes' order until the first success yields
-   (attempts that fail are discarded without a trace, preempt.go:400-430); reclaim walks the nodes in NodeList order
-   (reclaim.go:180-257). Result: decisions of kind VC_OP_EVICT (task = running-task index) and VC_OP_PIPELINE (task =
-   vc_tasks index) in statement order; one visit per Statement (preempt: per preemptor job and per intra-job
-   preemptor; reclaim: per job), VC_VISIT_COMMIT or VC_VISIT_DISCARD (discarded operations are not reported).
-   VC_EUNSUPPORTED: BestEffort pending tasks in the session (vc_snapshot_set_backfill), soft-topology jobs, sampling. */
+/* The preempt action (actions/preempt/preempt.go:101-283, normalPreempt :333-434; topology-aware preemption is off by
+   default and not built) and the reclaim action (actions/reclaim/reclaim.go:56-258) on the session state the preceding
+   actions left (vc_allocate_run, each other). Preemptors are the tasks of vc_tasks that are still Pending.
+   Split: per preemptor the device evaluates EVERY node at once — plugin predicates in their preempt reading
+   (ssn.PredicateForPreemptAction, framework/session.go:679-697: only unresolvable failures reject a node, the pod-count cap
+   does not), the util.PrioritizeNodes total, and exact necessary conditions of the attempt (util.ValidateVictims over every
+   task that could be a victim; the queue's Allocatable gate with all of them gone) — and hands out the surviving nodes in
+   the action's order (util.SortNodes for preempt, NodeList for reclaim). The victim selection on the node under trial
+   (ssn.Preemptable / ssn.Reclaimable tier votes, victim queue order, evict until the preemptor fits) is O(tasks on that
+   node) and runs in the library's host control loop, as on the reference's action goroutine; attempts that fail leave no
+   trace (nodeStmt.Discard, preempt.go:400-430). Canonical order of node.Tasks (a Go map): ascending running-task index.
+   Result: decisions of kind VC_OP_EVICT (task = running-task index) and VC_OP_PIPELINE (task = vc_tasks index) in
+   statement order; one visit per Statement (preempt: per preemptor job, then per intra-job preemptor; reclaim: per job),
+   VC_VISIT_COMMIT or VC_VISIT_DISCARD (discarded operations are not reported).
+   VC_EUNSUPPORTED: BestEffort pending tasks in the session (vc_snapshot_set_backfill), jobs with a network topology,
+   feasible-node sampling, PreferNoSchedule taints, the tdm / network-topology-aware plugins. */
 int vc_preempt_run(vc_snapshot *s, vc_result **out);
 int vc_reclaim_run(vc_snapshot *s, vc_result **out);
 

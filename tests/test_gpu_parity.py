@@ -487,3 +487,16 @@ def test_preempt_action_interface(gpu):
     assert act.Name() == "preempt"
     case.Run([act])
     assert case.CheckAll() is None, case.CheckAll()
+
+
+def test_cfg5_cycle_vs_oracle(gpu, oracle_engine):
+    """BASELINE configs[4] at a reduced size (1 000 nodes near capacity, ~1 500 pending tasks, 8 queues): the cycle
+    allocate -> preempt -> reclaim through the C ABI, every decision and statement against the oracle."""
+    from volcano_b200.synth import make_cfg5
+    snap = make_cfg5(seed=77, n_nodes=1000, n_pending=1500, n_queues=8, utilisation=0.9)
+    res = gpu.gpu_engine(snap)
+    ref = oracle_engine(snap, threads=_host_threads())
+    _assert_same(res, ref)
+    _assert_same_evict(res.preempt, ref.preempt)
+    _assert_same_evict(res.reclaim, ref.reclaim)
+    assert (ref.preempt.decisions["kind"] == 2).sum() + (ref.reclaim.decisions["kind"] == 2).sum() > 10

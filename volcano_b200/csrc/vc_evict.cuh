@@ -23,7 +23,14 @@
 struct EvictTask {  // the preemptor, staged per launch
   TaskRec rec;
   int klass, job, queue, mode;
+  int job_prio, task_prio;
+  // ssn.Allocatable of the preemptor's queue (proportion queueAllocatable, proportion.go:333-348) as a bound: with
+  // quota_on the queue must admit the preemptor once EVERY candidate of the node is gone (they all sit in that queue)
+  int quota_on, quota_open;
+  uint32_t qalloc_has, qdes_has;
+  double qalloc[VC_MAX_DIMS], qdes[VC_MAX_DIMS];
 };
+#define EV_PICK_K 8  // candidates one k_evict_pick launch hands to the host, in the action's node order
 struct EvictParams {
   DevDims d;
   DevConf c;
@@ -41,13 +48,17 @@ struct EvictParams {
   uint8_t *rt_evicted;             // [RT] 1 = Releasing (evicted in this session)
   const int32_t *j_queue;          // [J]
   const uint32_t *q_flags;         // [Q]
+  const int32_t *rt_prio;          // [RT] TaskInfo.Priority
+  const int32_t *j_prio, *j_min;   // [J]
+  const int32_t *j_ready;          // [J] ReadyTaskNum as the session stands (the host refreshes it after every eviction)
+  const uint8_t *q_over;           // [Q] proportion: !allocated.LessEqual(deserved) as the session stands
+  int exact_sums;                  // every request is an integer-valued double: sums of them are exact
   int RT;
   // per-preemptor scratch
   unsigned long long *key;  // [N] order-preserving score key of a candidate
   uint8_t *cand;            // [N] 1 = candidate, 2 = tried
-  // pick result (mapped pinned memory): node (-1 none), score bits
+  // pick result (mapped pinned memory): EV_PICK_K nodes in the action's order, -1 = no further candidate
   int32_t *pick_node;
-  double *pick_score;
   // apply command (mapped pinned memory): [0] node, [1] n_victims, [2..] victim running-task ids
   const int32_t *cmd;
 };
@@ -86,6 +97,38 @@ __device__ __forceinline__ bool ev_filter(const EvictParams &p, const EvictTask 
   return j >= 0 && j != t.job && p.j_queue[j] == t.queue;
 }
 
+// Could task r be among the victims ssn.Preemptable / ssn.Reclaimable returns (session_plugins.go:211-307)? Inside a
+// tier the plugins' answers are intersected, but an empty intersection resets the list to nil and the next plugin's answer
+// replaces it — so all that is certain about a victim is that it passed the LAST voting plugin of the tier that decided.
+// Used here, per voter, is the part of its test that does not depend on the other candidates: conformance (not critical),
+// gang (job above minAvailable, gang.go:97-129), priority (lower job / task priority, priority.go:110-148), proportion
+// (queue above deserved, proportion.go:286-317); drf's test depends on the walk and counts as a yes.
+__device__ __forceinline__ bool ev_may_be_victim(const EvictParams &p, const EvictTask &t, int r) {
+  const bool reclaim = t.mode == EV_MODE_RECLAIM;
+  const uint32_t flag = reclaim ? VC_EN_RECLAIMABLE : VC_EN_PREEMPTABLE;
+  const int j = p.rt_job[r];
+  int i = 0;
+  while (i < p.c.n_plugins) {
+    const int tier = p.c.tier[i];
+    bool any = false, last = false;
+    for (; i < p.c.n_plugins && p.c.tier[i] == tier; ++i) {
+      if (!(p.c.enabled[i] & flag)) continue;
+      const int pl = p.c.plugin[i];
+      bool vote;
+      if (pl == VC_PLUGIN_CONFORMANCE) vote = !(p.rt_flags[r] & VC_RT_CRITICAL);
+      else if (pl == VC_PLUGIN_GANG) vote = j >= 0 && p.j_ready[j] > p.j_min[j];
+      else if (pl == VC_PLUGIN_PRIORITY && !reclaim) vote = j >= 0 && (j != t.job ? p.j_prio[j] < t.job_prio : p.rt_prio[r] < t.task_prio);
+      else if (pl == VC_PLUGIN_DRF && !reclaim) vote = j >= 0;
+      else if (pl == VC_PLUGIN_PROPORTION && reclaim) vote = j >= 0 && p.j_queue[j] >= 0 && p.q_over[p.j_queue[j]];
+      else continue;
+      any = true;
+      last = vote;
+    }
+    if (any && last) return true;
+  }
+  return false;
+}
+
 __global__ void k_evict_rank(EvictParams p, EvictTask t) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = p.d.N, R = p.d.R, K = p.d.K;
@@ -98,17 +141,34 @@ __global__ void k_evict_rank(EvictParams p, EvictTask t) {
     double pot[VC_MAX_DIMS];
     for (int d = 0; d < R; ++d)
       pot[d] = (p.idle[(size_t)d * N + n] + p.rel[(size_t)d * N + n]) - p.pip[(size_t)d * N + n];
+    double freed[VC_MAX_DIMS];
+    for (int d = 0; d < R; ++d) freed[d] = 0.0;
     int n_pass = 0;
     for (int k = p.rt_off[n]; k < p.rt_off[n + 1]; ++k) {
       const int r = p.rt_idx[k];
       if (!ev_filter(p, t, r)) continue;
       n_pass += 1;
-      for (int d = 0; d < R; ++d) pot[d] += p.rt_req[(size_t)d * p.RT + r];
+      if (!ev_may_be_victim(p, t, r)) continue;
+      for (int d = 0; d < R; ++d) freed[d] += p.rt_req[(size_t)d * p.RT + r];
     }
     bool fits = true;
     for (int d = 0; d < R; ++d) {
       if (d >= 2 && !(t.rec.has & (1u << d))) continue;
-      if (!le_eps(t.rec.req[d], pot[d])) fits = false;
+      if (!le_eps(t.rec.req[d], pot[d] + freed[d])) fits = false;
+    }
+    if (t.quota_on && p.exact_sums && t.mode != EV_MODE_RECLAIM) {
+      // the evict loop ends with ssn.Allocatable(queue, preemptor) (preempt.go:380, :405): even with every possible
+      // victim of this node evicted the queue must stay within deserved on the requested dimensions
+      if (!t.quota_open) fits = false;
+      const uint32_t rq_has = t.rec.has & ~3u;
+      for (int d = 0; d < R; ++d) {
+        const double rq = t.rec.req[d];
+        if (!(rq > 0.0)) continue;
+        if (d >= 2 && (!(rq_has & (1u << d)) || d == p.d.pods_dim)) continue;
+        const double al = (d < 2 || (t.qalloc_has & (1u << d))) ? t.qalloc[d] : 0.0;
+        const double de = (d < 2 || (t.qdes_has & (1u << d))) ? t.qdes[d] : 0.0;
+        if ((al - freed[d]) + rq > de) fits = false;
+      }
     }
     if (fits && (t.mode != EV_MODE_RECLAIM || n_pass > 0)) {
       cand = 1;
@@ -124,40 +184,48 @@ __global__ void k_evict_rank(EvictParams p, EvictTask t) {
   p.key[n] = key;
 }
 
-// one block: the next candidate in the action's node order; `exclude` (>= 0) is marked tried first
-__global__ void k_evict_pick(EvictParams p, int mode, int exclude) {
+// one block: the next EV_PICK_K candidates in the action's node order (preempt: score descending, lowest index first
+// among equals; reclaim: index ascending); the nodes handed out are marked tried
+__global__ void k_evict_pick(EvictParams p, int mode) {
   __shared__ unsigned long long s_key[32];
   __shared__ int s_node[32];
+  __shared__ int s_best;
   const int N = p.d.N;
-  if (exclude >= 0 && threadIdx.x == 0) p.cand[exclude] = 2;
-  __syncthreads();
-  unsigned long long bk = 0ull;
-  int bn = -1;
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    if (p.cand[n] != 1) continue;
-    const unsigned long long k = mode == EV_MODE_RECLAIM ? 0ull : p.key[n];
-    if (bn < 0 || k > bk) { bk = k; bn = n; }  // ascending n per thread: the first of equal keys stays
-  }
-  for (int o = 16; o; o >>= 1) {
-    const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
-    const int on = __shfl_xor_sync(0xffffffffu, bn, o);
-    if (on >= 0 && (bn < 0 || ok > bk || (ok == bk && on < bn))) { bk = ok; bn = on; }
-  }
-  if ((threadIdx.x & 31) == 0) { s_key[threadIdx.x >> 5] = bk; s_node[threadIdx.x >> 5] = bn; }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int nw = (blockDim.x + 31) >> 5;
-    bk = threadIdx.x < nw ? s_key[threadIdx.x] : 0ull;
-    bn = threadIdx.x < nw ? s_node[threadIdx.x] : -1;
+  for (int it = 0; it < EV_PICK_K; ++it) {
+    unsigned long long bk = 0ull;
+    int bn = -1;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      if (p.cand[n] != 1) continue;
+      const unsigned long long k = mode == EV_MODE_RECLAIM ? 0ull : p.key[n];
+      if (bn < 0 || k > bk) { bk = k; bn = n; }  // ascending n per thread: the first of equal keys stays
+    }
     for (int o = 16; o; o >>= 1) {
       const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
       const int on = __shfl_xor_sync(0xffffffffu, bn, o);
       if (on >= 0 && (bn < 0 || ok > bk || (ok == bk && on < bn))) { bk = ok; bn = on; }
     }
-    if (threadIdx.x == 0) {
-      *p.pick_node = bn;
-      unsigned long long u = (bk & 0x8000000000000000ull) ? (bk & 0x7fffffffffffffffull) : ~bk;
-      *p.pick_score = bn >= 0 && mode != EV_MODE_RECLAIM ? __longlong_as_double((long long)u) : 0.0;
+    if ((threadIdx.x & 31) == 0) { s_key[threadIdx.x >> 5] = bk; s_node[threadIdx.x >> 5] = bn; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int nw = (blockDim.x + 31) >> 5;
+      bk = threadIdx.x < nw ? s_key[threadIdx.x] : 0ull;
+      bn = threadIdx.x < nw ? s_node[threadIdx.x] : -1;
+      for (int o = 16; o; o >>= 1) {
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        const int on = __shfl_xor_sync(0xffffffffu, bn, o);
+        if (on >= 0 && (bn < 0 || ok > bk || (ok == bk && on < bn))) { bk = ok; bn = on; }
+      }
+      if (threadIdx.x == 0) {
+        p.pick_node[it] = bn;
+        if (bn >= 0) p.cand[bn] = 2;
+        s_best = bn;
+      }
+    }
+    __syncthreads();
+    if (s_best < 0) {  // exhausted: the remaining slots say so
+      if (threadIdx.x == 0)
+        for (int r = it + 1; r < EV_PICK_K; ++r) p.pick_node[r] = -1;
+      break;
     }
   }
 }

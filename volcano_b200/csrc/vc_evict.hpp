@@ -74,9 +74,9 @@ struct EvictOp { int kind, task, node; };  // VC_OP_EVICT (task = running-task i
 
 // The device side as the control loop sees it
 struct Ranker {
-  // rank every node for preemptor `t` under `mode`; then next(exclude) yields the next candidate node or -1
+  // rank every node for preemptor `t` under `mode`; then next() yields the candidate nodes in the action's order, -1 at the end
   std::function<int(int t, int mode)> begin;     // returns 0 or a VC_E* code
-  std::function<int(int exclude, int *node)> next;
+  std::function<int(int *node)> next;
   std::function<int(int t, int node, const std::vector<int> &victims)> apply;
   std::function<int(int t, int node, const std::vector<int> &victims)> revert;  // the inverse, for a discarded statement
 };
@@ -331,18 +331,23 @@ struct EvictSession {
   // stmt.Discard() of a whole statement whose node attempts were already applied on the device: the operations come in
   // groups [evict ..., pipeline] per successful attempt (stmt.Merge, preempt.go:421); undo them last group first
   int discard_applied(const Ranker &rk, std::vector<EvictOp> &ops) {
+    struct Group { int task, node; std::vector<int> victims; };
+    std::vector<Group> groups;  // last group first
     int end = (int)ops.size();
     while (end > 0) {
       const int pi = end - 1;  // the group's pipeline op
       int b = pi;
       while (b > 0 && ops[b - 1].kind == VC_OP_EVICT) --b;
-      std::vector<int> victims;
-      for (int i = b; i < pi; ++i) victims.push_back(ops[i].task);
-      const int rc = rk.revert(ops[pi].task, ops[pi].node, victims);
-      if (rc) return rc;
+      Group g{ops[pi].task, ops[pi].node, {}};
+      for (int i = b; i < pi; ++i) g.victims.push_back(ops[i].task);
+      groups.push_back(std::move(g));
       end = b;
     }
-    discard(ops);
+    discard(ops);  // the host state first: the device refresh that follows every revert reads it
+    for (const Group &g : groups) {
+      const int rc = rk.revert(g.task, g.node, g.victims);
+      if (rc) return rc;
+    }
     return VC_OK;
   }
 
@@ -490,12 +495,10 @@ struct EvictSession {
     const int pj = k->t_job[t], q = k->j_queue[pj];
     int rc = rk.begin(t, mode);
     if (rc) return rc;
-    int exclude = -1;
     for (;;) {
       int n = -1;
-      if ((rc = rk.next(exclude, &n))) return rc;
+      if ((rc = rk.next(&n))) return rc;
       if (n < 0) return VC_OK;
-      exclude = n;
       std::vector<int> cands;
       for (int x = rt->off[n]; x < rt->off[n + 1]; ++x)
         if (run_filter(rt->idx[x], mode, pj, q)) cands.push_back(rt->idx[x]);

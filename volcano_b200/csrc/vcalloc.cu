@@ -1541,7 +1541,7 @@ int ensure_evict_session(vc_snapshot *s) {
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
   const size_t o_off = take((N + 1) * 4), o_idx = take(B * 4), o_req = take(R * B * 8), o_kreq = take(K * B * 8),
                o_knz = take(K * B * 8), o_flags = take(B * 4), o_job = take(B * 4), o_ev = take(B), o_key = take(N * 8),
-               o_cand = take(N);
+               o_cand = take(N), o_prio = take(B * 4), o_jready = take(std::max<size_t>(J, 1) * 4), o_qover = take(std::max<size_t>(Q, 1));
   if (off > s->d_ev_bytes) {
     if (s->d_ev) cudaFree(s->d_ev);
     s->d_ev = nullptr;
@@ -1560,10 +1560,11 @@ int ensure_evict_session(vc_snapshot *s) {
     CUDA_TRY(cudaMemcpyAsync(base + o_knz, b.knz.data(), K * B * 8, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(base + o_flags, b.flags.data(), B * 4, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(base + o_job, b.job.data(), B * 4, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_prio, b.prio.data(), B * 4, cudaMemcpyHostToDevice, s->stream));
   }
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   s->es_built = true;
-  (void)NR; (void)o_ev; (void)o_key; (void)o_cand;
+  (void)NR; (void)o_ev; (void)o_key; (void)o_cand; (void)o_jready; (void)o_qover;
   return VC_OK;
 }
 
@@ -1584,7 +1585,7 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
   const size_t o_off = take((N + 1) * 4), o_idx = take(B * 4), o_req = take(R * B * 8), o_kreq = take(K * B * 8),
                o_knz = take(K * B * 8), o_flags = take(B * 4), o_job = take(B * 4), o_ev = take(B), o_key = take(N * 8),
-               o_cand = take(N);
+               o_cand = take(N), o_prio = take(B * 4), o_jready = take(std::max<size_t>(J, 1) * 4), o_qover = take(std::max<size_t>(Q, 1));
   unsigned char *base = reinterpret_cast<unsigned char *>(s->d_ev);
   EvictParams p;
   std::memset(&p, 0, sizeof p);
@@ -1597,10 +1598,27 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
   p.rt_knz = reinterpret_cast<const double *>(base + o_knz); p.rt_flags = reinterpret_cast<const uint32_t *>(base + o_flags);
   p.rt_job = reinterpret_cast<const int32_t *>(base + o_job); p.rt_evicted = base + o_ev;
   p.j_queue = s->j_queue.d(s->in); p.q_flags = s->q_flags.d(s->in); p.RT = (int)B;
+  p.rt_prio = reinterpret_cast<const int32_t *>(base + o_prio); p.j_prio = s->j_prio.d(s->in); p.j_min = s->j_min.d(s->in);
+  p.j_ready = reinterpret_cast<const int32_t *>(base + o_jready); p.q_over = base + o_qover;
+  {
+    double m1 = 0, m2 = 0;  // sums of requests are exact when every request is an integer well below 2^53 / RT
+    p.exact_sums = (s->rows_integral && vch::max_abs_integral(s->rt.req.data(), s->rt.req.size(), m1) &&
+                    vch::max_abs_integral(k.t_req.data(), k.t_req.size(), m2) && m1 * 4096.0 < 9.0e15) ? 1 : 0;
+  }
+  // ReadyTaskNum per job and proportion's "queue above deserved" as the session stands; refreshed after every success
+  std::vector<uint8_t> q_over(std::max<size_t>(Q, 1), 0);
+  auto refresh_dynamic = [&]() -> int {
+    for (size_t q = 0; q < Q; ++q)
+      q_over[q] = (e.qattr[q].exists && !e.qattr[q].allocated.less_equal_zero(e.qattr[q].deserved, (int)R)) ? 1 : 0;
+    if (J) CUDA_TRY(cudaMemcpyAsync(base + o_jready, e.j_ready.data(), J * 4, cudaMemcpyHostToDevice, s->stream));
+    if (Q) CUDA_TRY(cudaMemcpyAsync(base + o_qover, q_over.data(), Q, cudaMemcpyHostToDevice, s->stream));
+    return VC_OK;
+  };
+  if ((rc = refresh_dynamic())) return rc;
   p.key = reinterpret_cast<unsigned long long *>(base + o_key); p.cand = base + o_cand;
   int32_t *dev_h = nullptr;
   CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&dev_h), s->h_ev, 0));
-  p.pick_node = dev_h; p.pick_score = reinterpret_cast<double *>(dev_h + 2); p.cmd = dev_h + 16;
+  p.pick_node = dev_h; p.cmd = dev_h + 16;
   volatile int32_t *h_pick = s->h_ev;
   int32_t *h_cmd = s->h_ev + 16;
   int launches = 0, cur_mode = 0;
@@ -1612,25 +1630,43 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
     for (size_t x = 0; x < 2; ++x) et.rec.knz[x] = k.t_knz[x * T + t];
     et.rec.has = k.t_has[t]; et.rec.klass = k.t_class[t];
     et.klass = k.t_class[t]; et.job = k.t_job[t]; et.queue = k.j_queue[k.t_job[t]]; et.mode = mode;
+    et.job_prio = k.j_prio[et.job]; et.task_prio = k.t_prio[t];
+    // ssn.Allocatable goes through proportion's queueAllocatable when the plugin has EnabledAllocatable
+    et.quota_on = vch::plugin_enabled(s->conf, VC_PLUGIN_PROPORTION, VC_EN_ALLOCATABLE) ? 1 : 0;
+    if (et.quota_on) {
+      const vch::QAttr &a = e.qattr[et.queue];
+      et.quota_open = (k.q_flags[et.queue] & VC_QUEUE_OPEN) ? 1 : 0;
+      et.qalloc_has = a.allocated.has; et.qdes_has = a.deserved.has;
+      for (size_t d = 0; d < R; ++d) { et.qalloc[d] = a.allocated.v[d]; et.qdes[d] = a.deserved.v[d]; }
+    }
   };
+  int pick_buf[EV_PICK_K], pick_pos = EV_PICK_K, pick_n = 0;
   vch::Ranker rk;
   rk.begin = [&](int t, int mode) -> int {
     stage(t, mode);
     cur_mode = mode;
+    pick_pos = pick_n = 0;
     if (N == 0) return VC_OK;
     k_evict_rank<<<(unsigned)((N + 127) / 128), 128, 0, s->stream>>>(p, et);
     launches++;
     CUDA_TRY(cudaGetLastError());
     return VC_OK;
   };
-  rk.next = [&](int exclude, int *node) -> int {
+  rk.next = [&](int *node) -> int {
     *node = -1;
     if (N == 0) return VC_OK;
-    k_evict_pick<<<1, 1024, 0, s->stream>>>(p, cur_mode, exclude);
-    launches++;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    *node = h_pick[0];
+    if (pick_pos >= pick_n) {
+      if (pick_n > 0 && pick_n < EV_PICK_K) return VC_OK;  // the last batch was short: no candidate is left
+      k_evict_pick<<<1, 1024, 0, s->stream>>>(p, cur_mode);
+      launches++;
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(s->stream));
+      pick_n = 0;
+      for (int i = 0; i < EV_PICK_K && h_pick[i] >= 0; ++i) pick_buf[pick_n++] = h_pick[i];
+      pick_pos = 0;
+      if (pick_n == 0) return VC_OK;
+    }
+    *node = pick_buf[pick_pos++];
     return VC_OK;
   };
   auto apply_cmd = [&](int t, int node, const std::vector<int> &victims, int undo) -> int {
@@ -1643,7 +1679,7 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
     launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return VC_OK;
+    return refresh_dynamic();  // ReadyTaskNum / queue shares moved (the host state is already updated)
   };
   rk.apply = [&](int t, int node, const std::vector<int> &v) { return apply_cmd(t, node, v, 0); };
   rk.revert = [&](int t, int node, const std::vector<int> &v) { return apply_cmd(t, node, v, 1); };

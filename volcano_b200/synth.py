@@ -367,3 +367,131 @@ def _make_topology(s: Snapshot, cfg: SynthConfig, rng) -> None:
     s.hn_job_allocated = np.full(s.J, -1, np.int32)
     s.hn_job_placed_off = np.zeros(s.J + 1, np.int32)
     s.hn_job_placed_node = np.zeros(1, np.int32)
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: 10k nodes near 85 % utilisation, 32 queues, ~10k pending tasks per cycle, actions
+# allocate + preempt + reclaim. One cycle of the churn: the cluster is full of running pods (node.Tasks, the victim
+# candidates), part of the jobs are starving (running below minAvailable with pending pods left), new jobs arrive.
+# ---------------------------------------------------------------------------------------
+CFG5_PLUGINS = "priority+gang+conformance+drf+predicates+proportion+nodeorder+binpack"
+
+
+def make_cfg5(seed: Optional[int] = None, n_nodes: int = 10_000, n_pending: int = 10_000, n_queues: int = 32,
+              utilisation: float = 0.85) -> Snapshot:
+    seed = DEFAULT_SEED if seed is None else seed
+    rng = np.random.default_rng(seed + 55)
+    # capacity of the cluster decides how many running tasks there are: avg task ~2.7 cores
+    cores = n_nodes * (0.4 * 32 + 0.3 * 64 + 0.2 * 96 + 0.1 * 128)
+    n_all = int(n_pending + utilisation * cores / 2.2)
+    base = make_snapshot(SynthConfig("cfg5", n_nodes, n_all, n_queues, CFG5_PLUGINS, utilisation=0.0, seed=seed))
+    N, R, K, J, Q = base.N, base.R, base.K, base.J, base.Q
+    alloc = base.n_allocatable
+    job = base.t_job
+    sizes = np.bincount(job, minlength=J)
+    # jobs in random order fill the cluster with running pods until the cpu target is reached; the last ones run partially
+    order = rng.permutation(J)
+    target = utilisation * alloc[D_CPU].sum()
+    idle = alloc.copy()
+    running = np.zeros(base.T, bool)
+    node_of = np.full(base.T, -1, np.int32)
+    task_ids = [np.nonzero(job == j)[0] for j in range(J)] if J < 200000 else None
+    used_cpu = 0.0
+    pend_left = n_pending
+    for j in order:
+        if used_cpu >= target:
+            break
+        ts = task_ids[j]
+        frac = 1.0 if rng.random() < 0.8 else rng.uniform(0.2, 0.9)  # 20 % of the running jobs are short of pods
+        n_run = max(1, int(round(frac * len(ts))))
+        for t in ts[:n_run]:
+            req = base.t_resreq[:, t]
+            for _ in range(32):  # a few random nodes; a task that finds none stays pending
+                n = int(rng.integers(0, N))
+                if (idle[:, n] >= req).all():
+                    idle[:, n] -= req
+                    running[t] = True
+                    node_of[t] = n
+                    used_cpu += req[D_CPU]
+                    break
+    pending = ~running
+    # keep about n_pending pending tasks: whole pending-only jobs beyond the budget are dropped
+    keep = pending.copy()
+    cnt = 0
+    for j in order[::-1]:
+        ts = task_ids[j]
+        p = ts[pending[ts]]
+        if len(p) == 0:
+            continue
+        if cnt >= n_pending and not running[ts].any():
+            keep[p] = False
+        else:
+            cnt += len(p)
+    pend_ids = np.nonzero(keep)[0]
+    run_ids = np.nonzero(running)[0]
+    T = len(pend_ids)
+    s = Snapshot(N, T, J, Q, base.C, J, R, K=K, Wl=1, Wt=1, Z=0, pods_dim=D_PODS, B=0)
+    for k, v in base.__dict__.items():
+        if isinstance(v, np.ndarray) and not k.startswith(("t_", "b_", "rt_")) and hasattr(s, k) and getattr(s, k).shape == v.shape:
+            getattr(s, k)[...] = v
+    s.dim_names, s.node_names, s.queue_names, s.job_names = base.dim_names, base.node_names, base.queue_names, []
+    for name in ("resreq", "req_has", "k8s_req", "k8s_nonzero_req", "job", "klass", "role", "priority", "pod_index",
+                 "creation_ts", "uid_rank"):
+        src = getattr(base, "t_" + name)
+        getattr(s, "t_" + name)[...] = src[..., pend_ids]
+    s.t_uid_rank[:] = np.argsort(np.argsort(s.t_uid_rank)).astype(np.uint32)
+    s.t_flags = np.zeros(T, np.uint32)
+    # node.Tasks
+    RT = len(run_ids)
+    s.set_running(RT)
+    s.rt_node[:] = node_of[run_ids]
+    s.rt_job[:] = base.t_job[run_ids]
+    s.rt_role[:] = base.t_role[run_ids]
+    s.rt_priority[:] = 1
+    s.rt_pod_index[:] = base.t_pod_index[run_ids]
+    s.rt_uid_rank[:] = np.arange(RT, dtype=np.uint32)
+    s.rt_resreq[:] = base.t_resreq[:, run_ids]
+    s.rt_req_has[:] = base.t_req_has[run_ids]
+    s.rt_k8s_req[:] = base.t_k8s_req[:, run_ids]
+    s.rt_k8s_nonzero_req[:] = base.t_k8s_nonzero_req[:, run_ids]
+    s.rt_flags[:] = abi.VC_RT_RUNNING | np.where(rng.random(RT) < 0.7, abi.VC_RT_PREEMPTABLE, 0).astype(np.uint32)
+    s.running_task_keys = []
+    # node rows
+    used = alloc - idle
+    s.n_used[:] = used
+    s.n_idle[:] = idle
+    s.n_pod_count[:] = np.bincount(s.rt_node, minlength=N).astype(np.int32)
+    for k in range(K):
+        s.n_k8s_requested[k] = np.bincount(s.rt_node, weights=s.rt_k8s_req[k], minlength=N)
+        s.n_k8s_nonzero_requested[k] = np.bincount(s.rt_node, weights=s.rt_k8s_nonzero_req[k], minlength=N)
+    # jobs / roles / queues as the cache would hand them over
+    n_run_j = np.bincount(s.rt_job, minlength=J).astype(np.int32)
+    n_pend_j = np.bincount(s.t_job, minlength=J).astype(np.int32)
+    total_j = n_run_j + n_pend_j
+    s.j_ready_num[:] = n_run_j
+    s.j_n_tasks_total[:] = total_j
+    s.j_valid_num[:] = total_j
+    s.r_valid[:] = total_j
+    s.r_occupied[:] = n_run_j
+    gang_full = rng.random(J) < 0.5
+    s.j_min_available[:] = np.where(gang_full, total_j, np.maximum(1, total_j // 2))
+    s.j_priority[:] = rng.choice([0, 10, 100], size=J, p=[0.5, 0.3, 0.2])
+    for d in range(R):
+        s.j_allocated[d] = np.bincount(s.rt_job, weights=s.rt_resreq[d], minlength=J)
+    jq_run, jq_pend = s.j_queue[s.rt_job], s.j_queue[s.t_job]
+    s.q_allocated[:] = 0
+    for d in range(R):
+        s.q_allocated[d] = np.bincount(jq_run, weights=s.rt_resreq[d], minlength=Q)
+        s.q_request[d] = s.q_allocated[d] + np.bincount(jq_pend, weights=s.t_resreq[d], minlength=Q)
+    for qi in range(Q):
+        mr, mp = jq_run == qi, jq_pend == qi
+        ah = np.bitwise_or.reduce(s.rt_req_has[mr]) if mr.any() else 0
+        s.q_allocated_has[qi] = ah
+        s.q_request_has[qi] = ah | (np.bitwise_or.reduce(s.t_req_has[mp]) if mp.any() else 0)
+    s.q_capability[:] = 0
+    s.q_capability_has[:] = 0
+    sconf = scheduler_conf(SynthConfig("cfg5", n_nodes, T, n_queues, CFG5_PLUGINS))
+    sconf.actions = ("allocate", "preempt", "reclaim")
+    s.conf = build_conf(sconf, DIMS, KDIMS)
+    s.actions = tuple(sconf.actions)
+    return s
