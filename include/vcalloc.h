@@ -382,6 +382,23 @@ int vc_snapshot_set_backfill(vc_snapshot *s, int32_t n_tasks, const vc_tasks *ta
    later uploads until replaced (rt == NULL or n_tasks == 0 clears it). */
 int vc_snapshot_set_running(vc_snapshot *s, const vc_running_tasks *rt, const uint32_t *task_flags);
 
+/* ONE session across the GPUs of a node, one process per GPU: the exact allocate loop with the node axis cut
+   over the CTAs of all ranks. Every rank uploads the same snapshot and runs the same replicated control program; a CTA's
+   per-step records (its best (score, node); the publication of a run of placements) are written into EVERY rank's mailbox
+   / ring through peer-mapped memory (CUDA IPC over NVLink) and polled locally. Rank 0 returns the decisions; the other
+   ranks return empty results. Incremental commit kernel only (VC_EUNSUPPORTED otherwise, at upload).
+     vc_comm_create   before vc_snapshot_upload: allocate this rank's slab, return its CUDA IPC handle (64 bytes)
+     vc_comm_attach   map the slabs of all ranks: handles = world x 64 bytes in rank order (exchanged by the caller, e.g.
+                      with torch.distributed.all_gather)
+     vc_comm_prepare  before EVERY vc_allocate_run: clear this rank's slab. The caller then barriers across the ranks
+                      (no rank may write into a slab that is still being cleared), calls vc_allocate_run on every rank,
+                      and barriers again before the next prepare.
+   A poll that sees nothing for ~10 s (a peer that never launched, diverged ranks) aborts the kernel with a CUDA error. */
+#define VC_COMM_HANDLE_BYTES 64
+int vc_comm_create(vc_snapshot *s, int world, int rank, void *handle_out);
+int vc_comm_attach(vc_snapshot *s, const void *handles);
+int vc_comm_prepare(vc_snapshot *s);
+
 /* Restrict the node axis of this process to [node_begin, node_end) for node-sharded
    multi-GPU runs; tasks/jobs/queues stay replicated. Default: all nodes. */
 int vc_snapshot_set_shard(vc_snapshot *s, int32_t node_begin, int32_t node_end);

@@ -98,6 +98,7 @@ VC_PRED_TAINT_TOLERATION = 2
 VC_OP_ALLOCATE = 0
 VC_OP_PIPELINE = 1
 VC_OP_EVICT = 2
+VC_COMM_HANDLE_BYTES = 64
 VC_RT_PREEMPTABLE, VC_RT_RUNNING, VC_RT_BOUND, VC_RT_BEST_EFFORT, VC_RT_CRITICAL = 1, 2, 4, 8, 16
 VC_TASK_PREEMPT_NEVER = 1
 VC_VISIT_COMMIT = 0
@@ -234,6 +235,9 @@ SYMBOLS = {
     "vc_snapshot_set_topology": (C.c_int, [_vp, C.POINTER(vc_hypernodes)]),
     "vc_snapshot_set_backfill": (C.c_int, [_vp, C.c_int32, C.POINTER(vc_tasks)]),
     "vc_snapshot_set_running": (C.c_int, [_vp, C.POINTER(vc_running_tasks), C.POINTER(C.c_uint32)]),
+    "vc_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_void_p]),
+    "vc_comm_attach": (C.c_int, [_vp, C.c_void_p]),
+    "vc_comm_prepare": (C.c_int, [_vp]),
     "vc_snapshot_set_shard": (C.c_int, [_vp, C.c_int32, C.c_int32]),
     "vc_allocate_run": (C.c_int, [_vp, C.POINTER(_vp)]),
     "vc_backfill_run": (C.c_int, [_vp, C.POINTER(_vp)]),

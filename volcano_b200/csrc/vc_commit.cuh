@@ -81,6 +81,13 @@ struct K2Params {
   const uint32_t *g_has;
   const int32_t *g_class;
   uint4 *ring;            // publication ring, RING_DEPTH entries of RING_STRIDE uint4
+  // ---- one session across several GPUs (k_commit_fast only): every rank runs the same control program over its slice
+  //      of the node axis; a CTA's records go into EVERY rank's mailbox / ring through peer-mapped memory (NVLink
+  //      stores), and are polled locally ----
+  int n_ranks;            // 1: single GPU
+  int cta_base;           // global index of this rank's CTA 0; n_cta counts the CTAs of all ranks
+  uint4 *peer_mbox[8];    // [n_ranks] the mailbox of every rank (own one included)
+  uint4 *peer_ring[8];    // [n_ranks]
   // ---- network-topology-aware (general kernel only) ----
   int hn_H, hn_cap;           // hypernodes; capacity of a CTA's local hypernode list
   const int32_t *hn_member;   // [L][N] global hypernode index per tier level, -1 none

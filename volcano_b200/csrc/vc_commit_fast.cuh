@@ -156,13 +156,28 @@ __device__ __forceinline__ uint4 pack_run(const Best &b, unsigned tag, int m) {
 }
 #define RUN_TAG_MASK 0x3fffffu
 
+// a record into the same slot of every rank's copy (one rank: the plain local store)
+__device__ __forceinline__ void store_all(const K2Params &p, uint4 *const *peers, uint4 *local, size_t off, uint4 v) {
+  if (p.n_ranks <= 1) { mbox_store(local + off, v); return; }
+  for (int r = 0; r < p.n_ranks; ++r) mbox_store(peers[r] + off, v);
+}
+// multi-GPU runs only: a poll that saw nothing for ~10 s means a peer never came up or the ranks diverged — abort the
+// kernel (the context dies with an error) instead of spinning until somebody kills the job
+#define PEER_WATCHDOG(spins, t0)                                                                  \
+  do {                                                                                            \
+    if (p.n_ranks > 1 && ((++(spins)) & 0x3ffffu) == 0 && clock64() - (t0) > 20000000000ll) __trap(); \
+  } while (0)
+
 // all-gather of the CTA bests (warp 0 of every CTA); fills the slot table
 __device__ __forceinline__ void exchange_all_fast(const K2Params &p, const Best &mine, unsigned ag, FastSmem &fs) {
   const int lane = threadIdx.x & 31;
   const int G = p.n_cta;
   const unsigned tag = (ag + 1u) & 0x3fffffffu;
-  uint4 *base = p.mbox + (size_t)(ag & 1u) * G * MBOX_STRIDE;
-  if (lane == 0) mbox_store(base + (size_t)blockIdx.x * MBOX_STRIDE, pack_best(mine, tag));
+  const size_t par = (size_t)(ag & 1u) * G * MBOX_STRIDE;
+  uint4 *base = p.mbox + par;
+  if (lane == 0) store_all(p, p.peer_mbox, p.mbox, par + (size_t)(p.cta_base + blockIdx.x) * MBOX_STRIDE, pack_best(mine, tag));
+  unsigned spins = 0;
+  const long long t0w = p.n_ranks > 1 ? clock64() : 0;
   for (int s0 = 0; s0 < G; s0 += 32 * 4) {
     uint4 a[4];
     bool need[4];
@@ -183,6 +198,7 @@ __device__ __forceinline__ void exchange_all_fast(const K2Params &p, const Best 
         fs.sl_score[s] = b.score; fs.sl_node[s] = b.node; fs.sl_cnt[s] = b.cnt;
         need[k] = false;
       }
+      if (pending) PEER_WATCHDOG(spins, t0w);
     } while (pending);
   }
   __syncwarp();
@@ -278,7 +294,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   const DevConf &c = p.c;
   const int R = p.d.R, K = p.d.K, N = p.d.N, J = p.d.J, Q = p.d.Q, NR = p.d.NR, T = p.d.T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int cta = blockIdx.x;
+  const int lcta = blockIdx.x;            // this rank's buffers are indexed locally
+  const int cta = p.cta_base + lcta;      // identity in the exchange: unique over all ranks
   const int nbase = p.d.node_begin + cta * p.npc;
   const int nmine = max(0, min(p.npc, p.d.node_end - nbase));
   const int cap = p.npc;
@@ -307,7 +324,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   fs.sl_cnt = reinterpret_cast<int32_t *>(sp); sp += (size_t)G * 4;
   sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 15) & ~(uintptr_t)15);
   HeapKey *heap = fp.heap_in_smem ? reinterpret_cast<HeapKey *>(sp)
-                                  : reinterpret_cast<HeapKey *>(p.rep_heap) + (size_t)cta * p.rep_heap_stride;
+                                  : reinterpret_cast<HeapKey *>(p.rep_heap) + (size_t)lcta * p.rep_heap_stride;
 
   for (int i = tid; i < nmine; i += blockDim.x) {
     const int n = nbase + i;
@@ -332,12 +349,12 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   for (int s = tid; s < G; s += blockDim.x) { fs.sl_score[s] = 0.0; fs.sl_node[s] = -1; fs.sl_cnt[s] = 0; }
 
   // ---- per-CTA replica of the mutable control state, packed records ----
-  unsigned char *rb = reinterpret_cast<unsigned char *>(p.rep_f64 + (size_t)cta * p.rep_f64_stride);
+  unsigned char *rb = reinterpret_cast<unsigned char *>(p.rep_f64 + (size_t)lcta * p.rep_f64_stride);
   JobDyn *jdyn = reinterpret_cast<JobDyn *>(rb); rb += (size_t)J * sizeof(JobDyn);
   QueueDyn *qdyn = reinterpret_cast<QueueDyn *>(rb); rb += (size_t)Q * sizeof(QueueDyn);
   RoleDyn *rdyn = reinterpret_cast<RoleDyn *>(rb); rb += (size_t)NR * sizeof(RoleDyn);
   double *ops_score = reinterpret_cast<double *>(rb);
-  int32_t *ops = p.rep_i32 + (size_t)cta * p.rep_i32_stride;  // task, node, kind
+  int32_t *ops = p.rep_i32 + (size_t)lcta * p.rep_i32_stride;  // task, node, kind
 
   for (int j = tid; j < J; j += blockDim.x) {
     JobDyn jd;
@@ -613,7 +630,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     if (lane == 0) {
       F.cta_best_score = bs; F.cta_best_node = bn; F.cta_cnt = cnt;
       Best nb{bs, bn, cnt};
-      mbox_store(p.ring + (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, 1));
+      store_all(p, p.peer_ring, p.ring, (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, 1));
       F.ev_score = bs; F.ev_node = bn; F.ev_cnt = min(cnt, 2); F.run_m = 1;
     }
     __syncwarp();
@@ -696,7 +713,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     const double sc_m = __shfl_sync(0xffffffffu, sc, m - 1);
     const int cat_m = __shfl_sync(0xffffffffu, cat, m - 1);
     // scores of placements 1..m-1 of the run (placement j is chosen in state j-1 ... of the row BEFORE it: lane j-1)
-    if (lane < m - 1) { fp.score_log[F.run_att0 + 1 + lane] = sc; __threadfence(); }  // visible before the record below
+    if (lane < m - 1) {  // visible before the record below (system scope: the reader may sit on another GPU)
+      fp.score_log[F.run_att0 + 1 + lane] = sc;
+      if (p.n_ranks > 1) __threadfence_system(); else __threadfence();
+    }
     // the remaining m-1 placements on the row (Statement.Allocate: node_info.go:467-471, predicates.go:254-255)
     const double km = (double)(m - 1);
     if (m > 1) {
@@ -716,7 +736,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       Best nb{F.rl_score, F.rl_node, F.rl_cnt};
       if (cat_m == 0) best_fold(nb, sc_m, dn, 1);
       F.cta_best_score = nb.score; F.cta_best_node = nb.node; F.cta_cnt = nb.cnt;
-      mbox_store(p.ring + (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, m));
+      store_all(p, p.peer_ring, p.ring, (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, m));
       F.ev_score = nb.score; F.ev_node = nb.node; F.ev_cnt = min(nb.cnt, 2); F.run_m = m;
       F.spec_i[0] = -1; F.spec_i[1] = -1;  // whatever was computed ahead describes an older state of the row
     }
@@ -1009,7 +1029,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           const unsigned tag = (pub_pc + 1u) & RUN_TAG_MASK;
           const uint4 *ent = p.ring + (size_t)(pub_pc % RING_DEPTH) * RING_STRIDE;
           uint4 v;
-          do { v = mbox_load(ent); } while ((v.w >> 10) != tag);
+          unsigned spins = 0;
+          const long long t0w = p.n_ranks > 1 ? clock64() : 0;
+          do { v = mbox_load(ent); PEER_WATCHDOG(spins, t0w); } while ((v.w >> 10) != tag);
           nb = unpack_best(v);
           pub_m = (int)((v.w >> 2) & 0xffu);
         }

@@ -246,7 +246,14 @@ struct vc_snapshot {
   double *w_rel = nullptr;         // working copy of Releasing (Statement.Evict adds to it)
   void *d_ev = nullptr;            // device slab: running-task table + per-preemptor scratch
   size_t d_ev_bytes = 0;
-  int32_t *h_ev = nullptr;         // mapped pinned: [0] pick node, [2..3] pick score, [16..] apply command
+  int32_t *h_ev = nullptr;         // mapped pinned: [0..7] picked nodes, [16..] apply command
+  // ---- one session across the GPUs of a node (vc_comm_create / vc_comm_attach) ----
+  int world = 1, rank = 0;
+  int n_cta_total = 0;             // CTAs of all ranks (the exchange); n_cta stays this rank's grid
+  unsigned char *comm = nullptr;   // this rank's slab: mailbox | ring | score log (cudaMalloc, exported over CUDA IPC)
+  size_t comm_bytes = 0, comm_mbox_bytes = 0, comm_ring_off = 0, comm_log_off = 0;
+  unsigned char *peer_comm[8] = {nullptr};  // every rank's slab as mapped into this process (own one included)
+  bool comm_attached = false;
 };
 
 namespace {
@@ -329,11 +336,18 @@ void choose_geometry(vc_snapshot *s) {
   if (g_tun.commit_ctas > 0) ctas = g_tun.commit_ctas;
   int block = 128;
   if (g_tun.commit_threads > 0) block = std::max(128, std::min(256, g_tun.commit_threads / 32 * 32));
+  const int per_rank_max = ctas;
+  ctas *= std::max(1, s->world);  // one session across `world` GPUs: the node axis is cut over all their CTAs
   ctas = std::max(1, std::min(ctas, (nloc + 31) / 32));  // at least a warp of nodes per CTA
   int npc = (nloc + ctas - 1) / ctas;
   npc = std::max(32, (npc + 31) / 32 * 32);
   ctas = std::max(1, (nloc + npc - 1) / npc);
   if (npc > block) block = std::min(256, (npc + 31) / 32 * 32);
+  s->n_cta_total = ctas;
+  if (s->world > 1) {  // equal grids on every rank (trailing CTAs may own no node)
+    ctas = std::min(per_rank_max, (ctas + s->world - 1) / s->world);
+    s->n_cta_total = ctas * s->world;
+  }
   s->n_cta = ctas;
   s->npc = npc;
   s->block = block;
@@ -344,7 +358,7 @@ void choose_geometry(vc_snapshot *s) {
     if (g_tun.commit_threads <= 0) s->block = 256;  // 7 worker warps: a run's node states are evaluated two per warp
     size_t rows = 3 * (size_t)R + 2 * (size_t)K + 2 + 1;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + ((sizeof(CtlFast) + 15) & ~(size_t)15) + rows * npc * 8 +
-                    (size_t)npc * (8 + 4 * 5) + (size_t)ctas * (8 + 4 + 4) + 64;
+                    (size_t)npc * (8 + 4 * 5) + (size_t)s->n_cta_total * (8 + 4 + 4) + 64;
     const size_t heap_bytes = (size_t)s->heap_total * sizeof(HeapKey);
     s->heap_in_smem = (heap_bytes <= 96 * 1024 && s->smem_bytes + heap_bytes <= 200 * 1024) ? 1 : 0;
     if (s->heap_in_smem) s->smem_bytes += heap_bytes + 16;
@@ -437,6 +451,9 @@ int vc_snapshot_create(const vc_dims *dims, vc_snapshot **out) {
 void vc_snapshot_destroy(vc_snapshot *s) {
   if (!s) return;
   free_dense(s);
+  for (int r = 0; r < s->world; ++r)
+    if (r != s->rank && s->peer_comm[r]) cudaIpcCloseMemHandle(s->peer_comm[r]);
+  if (s->comm) cudaFree(s->comm);
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
                    s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_score_log, s->d_prof, s->d_wait, s->d_decisions, s->d_visits, s->d_fit, s->d_counters, s->d_bf, s->w_rel, s->d_ev};
   for (void *p : dptrs) if (p) cudaFree(p);
@@ -494,10 +511,59 @@ int vc_snapshot_set_topology(vc_snapshot *s, const vc_hypernodes *topo) {
   return VC_OK;
 }
 
+// ---- one session across the GPUs of a node: CUDA IPC slabs, peer-mapped -----------------------------------------
+int vc_comm_create(vc_snapshot *s, int world, int rank, void *handle_out) {
+  if (!s || !handle_out) return fail(VC_EINVAL, "null argument");
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(VC_EINVAL, "world %d / rank %d out of range (1..8)", world, rank);
+  s->uploaded = false;  // the launch geometry depends on the number of ranks
+  s->world = world; s->rank = rank; s->comm_attached = false;
+  const size_t T = s->dims.n_tasks;
+  const size_t mbox = sizeof(uint4) * MBOX_STRIDE * 2 * 2048, ring = sizeof(uint4) * RING_STRIDE * RING_DEPTH;
+  s->comm_mbox_bytes = mbox;
+  s->comm_ring_off = (mbox + 255) & ~(size_t)255;
+  s->comm_log_off = (s->comm_ring_off + ring + 255) & ~(size_t)255;
+  const size_t bytes = s->comm_log_off + (T + 64) * sizeof(double);
+  if (!s->comm || s->comm_bytes < bytes) {
+    if (s->comm) cudaFree(s->comm);
+    s->comm = nullptr;
+    CUDA_TRY(cudaMalloc(&s->comm, bytes));
+    s->comm_bytes = bytes;
+  }
+  CUDA_TRY(cudaMemset(s->comm, 0, s->comm_bytes));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, s->comm));
+  static_assert(sizeof(cudaIpcMemHandle_t) == VC_COMM_HANDLE_BYTES, "IPC handle size");
+  std::memcpy(handle_out, &h, sizeof h);
+  return VC_OK;
+}
+
+int vc_comm_attach(vc_snapshot *s, const void *handles) {
+  if (!s || !handles) return fail(VC_EINVAL, "null argument");
+  if (!s->comm) return fail(VC_EINVAL, "vc_comm_create must precede vc_comm_attach");
+  for (int r = 0; r < s->world; ++r) {
+    if (r == s->rank) { s->peer_comm[r] = s->comm; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, reinterpret_cast<const unsigned char *>(handles) + (size_t)r * VC_COMM_HANDLE_BYTES, sizeof h);
+    void *ptr = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_comm[r] = reinterpret_cast<unsigned char *>(ptr);
+  }
+  s->comm_attached = true;
+  return VC_OK;
+}
+
+int vc_comm_prepare(vc_snapshot *s) {
+  if (!s || !s->comm) return fail(VC_EINVAL, "no communication slab (vc_comm_create)");
+  CUDA_TRY(cudaMemsetAsync(s->comm, 0, s->comm_log_off, s->stream));  // mailbox + ring; the score log needs no reset
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return VC_OK;
+}
+
 int vc_snapshot_set_shard(vc_snapshot *s, int32_t node_begin, int32_t node_end) {
   if (!s) return fail(VC_EINVAL, "null snapshot");
   if (node_begin < 0 || node_end > s->dims.n_nodes || node_begin > node_end || (node_begin % 64) != 0)
     return fail(VC_EINVAL, "shard [%d,%d) invalid (begin must be a multiple of 64)", node_begin, node_end);
+  if (s->dd.node_begin == node_begin && s->dd.node_end == node_end) return VC_OK;  // unchanged: the dense-pass tables stay
   s->dd.node_begin = node_begin;
   s->dd.node_end = node_end;
   s->dense_ready = false;
@@ -875,7 +941,10 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   // network-topology-aware: hyperNodeResourceCache at open (network_topology_aware.go:106-125) and, for the
   // commit kernel, the hypernodes each CTA's node slice belongs to
   choose_geometry(s);
-  if (s->n_cta > 1024) return fail(VC_EUNSUPPORTED, "too many CTAs (%d)", s->n_cta);
+  if (s->n_cta_total > 2048) return fail(VC_EUNSUPPORTED, "too many CTAs (%d)", s->n_cta_total);
+  if (s->world > 1 && !s->fast)
+    return fail(VC_EUNSUPPORTED, "one session across GPUs runs on the incremental commit kernel only (no Releasing / Pipelined "
+                                 "resources at open, no PreferNoSchedule taints, no topology plugin, no sampling)");
   if (s->dc.to_find > 0 && (s->npc + s->block - 1) / s->block > 4)
     return fail(VC_EUNSUPPORTED, "feasible-node sampling: more than 4 node rows per CTA (%d nodes per CTA)", s->npc);
   std::vector<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn, node_chain, cta_chain_off, cta_chain;
@@ -1192,7 +1261,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   const vc_dims &D = s->dims;
   const size_t N = D.n_nodes, T = D.n_tasks, J = D.n_jobs, Q = D.n_queues, R = D.n_dims, K = D.n_kdims, NR = D.n_roles;
   if (s->dd.node_begin != 0 || s->dd.node_end != (int)N)
-    return fail(VC_EUNSUPPORTED, "the commit engine runs on the full node axis (replicas only across GPUs, DESIGN.md)");
+    return fail(VC_EUNSUPPORTED, "the commit engine takes the full node axis (vc_comm_create cuts it over the ranks itself)");
+  if (s->world > 1 && !s->comm_attached) return fail(VC_EINVAL, "vc_comm_attach must precede vc_allocate_run");
   const int G = s->n_cta;
   // replicas, mailbox, outputs
   const size_t i32_stride = ((5 * J + 4 * NR + 5 * Q + 3 * (size_t)s->max_job_tasks) + 63) & ~(size_t)63;
@@ -1232,7 +1302,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
       s->rep_hn_used_count = cnt;
     }
   }
-  const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024 * 2;  // second half: the count all-gather of sampling
+  const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 2048 * 2;  // second half: the count all-gather of sampling
   if (!s->mbox) CUDA_TRY(cudaMalloc(&s->mbox, mbox_bytes));
   if (!s->d_prof) CUDA_TRY(cudaMalloc(&s->d_prof, 16 * sizeof(long long)));
   const size_t ring_bytes = sizeof(uint4) * RING_STRIDE * RING_DEPTH;
@@ -1250,7 +1320,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   }
   K2Params p;
   std::memset(&p, 0, sizeof p);
-  p.d = s->dd; p.c = s->dc; p.npc = s->npc; p.n_cta = G; p.max_job_tasks = s->max_job_tasks;
+  p.d = s->dd; p.c = s->dc; p.npc = s->npc; p.n_cta = s->world > 1 ? s->n_cta_total : G; p.max_job_tasks = s->max_job_tasks;
+  p.n_ranks = s->world; p.cta_base = s->rank * G;
   p.alloc = s->n_alloc.d(s->in); p.rel = s->n_rel.d(s->in); p.kalloc = s->n_kalloc.d(s->in);
   p.idle = s->w_idle; p.used = s->w_used; p.pip = s->w_pip; p.kreq = s->w_kreq; p.knz = s->w_knz;
   p.max_tasks = s->n_max_tasks.d(s->in); p.pod_count = s->w_pod_count; p.cstat = s->cstat;
@@ -1273,7 +1344,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   p.rep_i32 = s->rep_i32; p.rep_i32_stride = i32_stride; p.rep_f64 = s->rep_f64; p.rep_f64_stride = f64_stride;
   p.rep_heap = s->rep_heap; p.rep_heap_stride = std::max<size_t>(heap_stride, 1);
   p.mbox = s->mbox;
-  p.mbox2 = s->mbox + (size_t)MBOX_STRIDE * 2 * 1024;
+  p.mbox2 = s->mbox + (size_t)MBOX_STRIDE * 2 * 2048;
   p.decisions = s->d_decisions; p.visits = s->d_visits; p.fit_errors = s->d_fit; p.counters = s->d_counters;
   p.prof = s->d_prof;
   p.tmeta = reinterpret_cast<const int4 *>(s->tmeta.d(s->in)); p.n_groups = s->n_groups;
@@ -1318,12 +1389,23 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   fp.run_max = (s->rows_integral && !g_tun.commit_norun)
                    ? std::max(1, std::min(g_tun.run_max > 0 ? g_tun.run_max : RUN_MAX, std::min(RUN_MAX, 2 * (s->block / 32 - 1)))) : 1;
   fp.score_log = s->d_score_log;
+  if (s->world > 1) {  // mailbox, ring and score log live in the exported slabs; the score log is rank 0's (it writes the decisions)
+    p.mbox = reinterpret_cast<uint4 *>(s->comm);
+    p.ring = reinterpret_cast<uint4 *>(s->comm + s->comm_ring_off);
+    for (int r = 0; r < s->world; ++r) {
+      p.peer_mbox[r] = reinterpret_cast<uint4 *>(s->peer_comm[r]);
+      p.peer_ring[r] = reinterpret_cast<uint4 *>(s->peer_comm[r] + s->comm_ring_off);
+    }
+    fp.score_log = reinterpret_cast<double *>(s->peer_comm[0] + s->comm_log_off);
+  }
   // ---- the timed region (vc_stats.commit_ms) starts here: the per-cycle resets and working copies are work
   //      every cycle does, so they are inside it ----
   CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
   CUDA_TRY(cudaMemsetAsync(s->d_prof, 0, 16 * sizeof(long long), s->stream));
-  CUDA_TRY(cudaMemsetAsync(s->ring, 0, ring_bytes, s->stream));
-  CUDA_TRY(cudaMemsetAsync(s->mbox, 0, mbox_bytes, s->stream));
+  if (s->world <= 1) {  // with several ranks vc_comm_prepare cleared the exported slab before the ranks' barrier
+    CUDA_TRY(cudaMemsetAsync(s->ring, 0, ring_bytes, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->mbox, 0, mbox_bytes, s->stream));
+  }
   CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 16 * 4, s->stream));
   // working copies of the mutable node state (the uploaded snapshot stays intact for re-runs / K1)
   CUDA_TRY(cudaMemcpyAsync(s->w_idle, s->n_idle.d(s->in), R * N * 8, cudaMemcpyDeviceToDevice, s->stream));
@@ -1964,7 +2046,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
     p.idle = s->w_idle; p.used = s->w_used; p.kreq = s->w_kreq; p.knz = s->w_knz;
     p.max_tasks = s->n_max_tasks.d(s->in); p.pod_count = s->w_pod_count; p.cstat = s->cstat;
     p.mbox = s->mbox;
-    p.mbox2 = s->mbox + (size_t)MBOX_STRIDE * 2 * 1024;
+    p.mbox2 = s->mbox + (size_t)MBOX_STRIDE * 2 * 2048;
     BackfillParams bp;
     unsigned char *base = static_cast<unsigned char *>(s->d_bf);
     bp.n = (int)n; bp.B = (int)B;

@@ -148,6 +148,19 @@ class Engine:
         res.job_allocated_hypernodes = job_alloc
         return res
 
+    # one session across the GPUs of a node: see include/vcalloc.h vc_comm_*
+    def comm_create(self, world: int, rank: int) -> bytes:
+        buf = (C.c_ubyte * abi.VC_COMM_HANDLE_BYTES)()
+        _check(self.L.vc_comm_create(self.h, world, rank, buf))
+        self._uploaded = False
+        return bytes(buf)
+
+    def comm_attach(self, handles: bytes):
+        _check(self.L.vc_comm_attach(self.h, handles))
+
+    def comm_prepare(self):
+        _check(self.L.vc_comm_prepare(self.h))
+
     def set_shard(self, begin: int, end: int):
         _check(self.L.vc_snapshot_set_shard(self.h, begin, end))
 
