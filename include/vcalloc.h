@@ -365,6 +365,18 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nodes, const vc_tasks *ta
                        const vc_classes *classes, const vc_jobs *jobs, const vc_queues *queues,
                        const vc_conf *conf);
 
+/* Incremental upload: the rows of the nodes whose NodeInfo changed since the last upload of this snapshot
+   — the caller keeps the NodeInfo.Generation it uploaded per node (api/node_info.go:95-99) and lists the nodes whose
+   generation moved. `rows` holds the SAME arrays as vc_nodes but compact, [dim][n_dirty] instead of [dim][N], for the
+   accounting fields only: idle, used, releasing, pipelined, k8s_requested, k8s_nonzero_requested, pod_count (the other
+   pointers are ignored; a change of Allocatable, labels, taints or flags needs vc_snapshot_upload). Tasks, jobs, queues
+   and the configuration stay as uploaded: the session-open results that depend only on them (task / job order, groups,
+   proportion's deserved) are kept, so a cycle that re-runs on a moved cluster state costs the dirty rows, not the
+   snapshot. The session is reset to its (new) opening state. VC_EUNSUPPORTED: sessions with the topology tables
+   (hypernode `used` sums are part of session open) and a row that would move the session between the commit kernels
+   (first Releasing / Pipelined resource): do a full upload then. */
+int vc_snapshot_update_nodes(vc_snapshot *s, int32_t n_dirty, const int32_t *node_idx, const vc_nodes *rows);
+
 /* Optional, before vc_snapshot_upload: the HyperNode tree of the session. Without it a configured
    network-topology-aware plugin scores against the cluster top hypernode only (no HyperNode CRs). */
 int vc_snapshot_set_topology(vc_snapshot *s, const vc_hypernodes *topo);

@@ -90,3 +90,43 @@ def test_unsupported_features_fail_loudly():
     with pytest.raises(engine.VcError) as ei:
         engine.gpu_engine(snap)
     assert ei.value.code == abi.VC_EUNSUPPORTED
+
+
+def test_incremental_node_upload(oracle_engine):
+    """vc_snapshot_update_nodes: the accounting rows of the dirty nodes alone are uploaded; the next cycle must be the one a
+    full upload of the moved cluster gives (and the oracle's)."""
+    from volcano_b200 import engine
+    from volcano_b200.synth import make_snapshot
+    snap = make_snapshot("small", 11)
+    e = engine.Engine(snap)
+    e.upload()
+    first = e.allocate()
+    # the cluster moved: pods finished on 5 % of the nodes (Used -> Idle), pods started on another 5 %
+    rng = np.random.default_rng(5)
+    dirty = rng.choice(snap.N, size=max(2, snap.N // 10), replace=False).astype(np.int32)
+    half = len(dirty) // 2
+    for n in dirty[:half]:
+        freed = np.floor(snap.n_used[:, n] / 2)
+        snap.n_used[:, n] -= freed
+        snap.n_idle[:, n] += freed
+    for n in dirty[half:]:
+        taken = np.floor(snap.n_idle[:, n] / 3)
+        snap.n_used[:, n] += taken
+        snap.n_idle[:, n] -= taken
+    snap.n_pod_count[dirty] = snap.n_used[snap.pods_dim, dirty].astype(np.int32)
+    kd = [snap.dim_names.index(k) for k in ("cpu", "memory", "nvidia.com/gpu")]
+    for k, d in enumerate(kd):
+        scale = 1000.0 if k == 2 else 1.0
+        snap.n_k8s_requested[k, dirty] = snap.n_used[d, dirty] / scale
+        snap.n_k8s_nonzero_requested[k, dirty] = snap.n_used[d, dirty] / scale
+    e.update_nodes(dirty, snap.n_idle[:, dirty], snap.n_used[:, dirty], snap.n_releasing[:, dirty], snap.n_pipelined[:, dirty],
+                   snap.n_k8s_requested[:, dirty], snap.n_k8s_nonzero_requested[:, dirty], snap.n_pod_count[dirty])
+    inc = e.allocate()
+    e.close()
+    full = engine.gpu_engine(snap)
+    ref = oracle_engine(snap)
+    for a in (inc, full):
+        assert np.array_equal(a.decisions, ref.decisions) and np.array_equal(a.visits, ref.visits)
+        assert np.array_equal(a.fit_errors, ref.fit_errors)
+    assert not np.array_equal(first.decisions["node"][:200], inc.decisions["node"][:200]) or len(first.decisions) != len(inc.decisions)
+    assert inc.stats["h2d_bytes"] < full.stats["h2d_bytes"] / 5

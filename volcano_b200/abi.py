@@ -232,6 +232,7 @@ SYMBOLS = {
     "vc_snapshot_destroy": (None, [_vp]),
     "vc_snapshot_upload": (C.c_int, [_vp, C.POINTER(vc_nodes), C.POINTER(vc_tasks), C.POINTER(vc_classes),
                                      C.POINTER(vc_jobs), C.POINTER(vc_queues), C.POINTER(vc_conf)]),
+    "vc_snapshot_update_nodes": (C.c_int, [_vp, C.c_int32, _i32p, C.POINTER(vc_nodes)]),
     "vc_snapshot_set_topology": (C.c_int, [_vp, C.POINTER(vc_hypernodes)]),
     "vc_snapshot_set_backfill": (C.c_int, [_vp, C.c_int32, C.POINTER(vc_tasks)]),
     "vc_snapshot_set_running": (C.c_int, [_vp, C.POINTER(vc_running_tasks), C.POINTER(C.c_uint32)]),

@@ -438,3 +438,29 @@ __global__ void __launch_bounds__(128) k_mask_expand_bulk(K1Params p, const uint
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 }
+
+
+// vc_snapshot_update_nodes: scatter the compact rows of the dirty nodes into the [dim][N] arrays of the uploaded session
+struct NodeDeltaParams {
+  int N, R, K, n;
+  const int32_t *idx;   // [n] node index
+  const double *vals;   // [(4 * R + 2 * K)][n]: idle, used, releasing, pipelined, k8s_requested, k8s_nonzero_requested
+  const int32_t *pods;  // [n] pod_count
+  double *idle, *used, *rel, *pip, *kreq, *knz;
+  int32_t *pod_count;
+};
+__global__ void k_node_delta(NodeDeltaParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const int n = p.idx[i];
+  const size_t N = (size_t)p.N, m = (size_t)p.n;
+  for (int d = 0; d < p.R; ++d) {
+    p.idle[d * N + n] = p.vals[(size_t)d * m + i];
+    p.used[d * N + n] = p.vals[(size_t)(p.R + d) * m + i];
+    p.rel[d * N + n] = p.vals[(size_t)(2 * p.R + d) * m + i];
+    p.pip[d * N + n] = p.vals[(size_t)(3 * p.R + d) * m + i];
+  }
+  for (int k = 0; k < p.K; ++k) p.kreq[k * N + n] = p.vals[(size_t)(4 * p.R + k) * m + i];
+  for (int k = 0; k < 2; ++k) p.knz[k * N + n] = p.vals[(size_t)(4 * p.R + p.K + k) * m + i];
+  p.pod_count[n] = p.pods[i];
+}

@@ -254,6 +254,9 @@ struct vc_snapshot {
   size_t comm_bytes = 0, comm_mbox_bytes = 0, comm_ring_off = 0, comm_log_off = 0;
   unsigned char *peer_comm[8] = {nullptr};  // every rank's slab as mapped into this process (own one included)
   bool comm_attached = false;
+  // ---- incremental upload (vc_snapshot_update_nodes) ----
+  unsigned char *delta_pin = nullptr, *delta_dev = nullptr;
+  size_t delta_cap = 0;
 };
 
 namespace {
@@ -457,7 +460,8 @@ void vc_snapshot_destroy(vc_snapshot *s) {
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
                    s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_score_log, s->d_prof, s->d_wait, s->d_decisions, s->d_visits, s->d_fit, s->d_counters, s->d_bf, s->w_rel, s->d_ev};
   for (void *p : dptrs) if (p) cudaFree(p);
-  void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters, s->h_ev};
+  void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters, s->h_ev, s->delta_pin};
+  if (s->delta_dev) cudaFree(s->delta_dev);
   for (void *p : hptrs) if (p) cudaFreeHost(p);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -1236,6 +1240,88 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     }
   }
   s->upload_ms = now_ms() - t0;
+  return VC_OK;
+}
+
+int vc_snapshot_update_nodes(vc_snapshot *s, int32_t n_dirty, const int32_t *node_idx, const vc_nodes *rows) {
+  if (!s) return fail(VC_EINVAL, "null snapshot");
+  if (!s->uploaded) return fail(VC_EINVAL, "vc_snapshot_upload must precede vc_snapshot_update_nodes");
+  if (n_dirty < 0 || (n_dirty > 0 && (!node_idx || !rows))) return fail(VC_EINVAL, "null argument");
+  if (s->dc.nta_tables) return fail(VC_EUNSUPPORTED, "incremental upload: the session carries hypernode tables, upload it in full");
+  const double t0 = now_ms();
+  const size_t N = s->dims.n_nodes, R = s->dims.n_dims, K = s->dims.n_kdims, m = (size_t)n_dirty;
+  if (m > 0 && (!rows->idle || !rows->used || !rows->k8s_requested || !rows->k8s_nonzero_requested || !rows->pod_count))
+    return fail(VC_EINVAL, "incremental upload: idle, used, k8s_requested, k8s_nonzero_requested and pod_count are required");
+  for (size_t i = 0; i < m; ++i)
+    if (node_idx[i] < 0 || (size_t)node_idx[i] >= N) return fail(VC_EINVAL, "dirty node %zu: index out of range", i);
+  bool fut = false;
+  for (size_t i = 0; i < R * m && !fut; ++i)
+    if ((rows->releasing && rows->releasing[i] != 0.0) || (rows->pipelined && rows->pipelined[i] != 0.0)) fut = true;
+  if (fut && !s->dc.has_future)
+    return fail(VC_EUNSUPPORTED, "incremental upload: first Releasing / Pipelined resource of the session, upload it in full");
+  // every value the run-length batches rely on stays an integer of safe magnitude
+  if (s->rows_integral) {
+    double mx = 0.0;
+    s->rows_integral = vch::max_abs_integral(rows->idle, R * m, mx) && vch::max_abs_integral(rows->used, R * m, mx) &&
+                       vch::max_abs_integral(rows->k8s_requested, K * m, mx) &&
+                       vch::max_abs_integral(rows->k8s_nonzero_requested, 2 * m, mx) && mx < 8.0e15;
+  }
+  if (m > 0) {
+    const size_t rows_n = 4 * R + 2 * K, bytes = rows_n * m * 8 + m * 4 + m * 4;
+    if (bytes > s->delta_cap) {
+      if (s->delta_pin) cudaFreeHost(s->delta_pin);
+      if (s->delta_dev) cudaFree(s->delta_dev);
+      s->delta_pin = s->delta_dev = nullptr;
+      const size_t cap = std::max<size_t>(bytes * 2, 1 << 16);
+      CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&s->delta_pin), cap));
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->delta_dev), cap));
+      s->delta_cap = cap;
+    }
+    double *v = reinterpret_cast<double *>(s->delta_pin);
+    auto put_rows = [&](size_t row0, const double *src, size_t nrows) {
+      if (src) std::memcpy(v + row0 * m, src, nrows * m * 8);
+      else std::memset(v + row0 * m, 0, nrows * m * 8);
+    };
+    put_rows(0, rows->idle, R); put_rows(R, rows->used, R); put_rows(2 * R, rows->releasing, R); put_rows(3 * R, rows->pipelined, R);
+    put_rows(4 * R, rows->k8s_requested, K); put_rows(4 * R + K, rows->k8s_nonzero_requested, 2);
+    int32_t *pi = reinterpret_cast<int32_t *>(s->delta_pin + rows_n * m * 8);
+    std::memcpy(pi, rows->pod_count, m * 4);
+    std::memcpy(pi + m, node_idx, m * 4);
+    CUDA_TRY(cudaMemcpyAsync(s->delta_dev, s->delta_pin, bytes, cudaMemcpyHostToDevice, s->stream));
+    NodeDeltaParams p;
+    p.N = (int)N; p.R = (int)R; p.K = (int)K; p.n = (int)m;
+    p.vals = reinterpret_cast<const double *>(s->delta_dev);
+    p.pods = reinterpret_cast<const int32_t *>(s->delta_dev + rows_n * m * 8);
+    p.idx = p.pods + m;
+    p.idle = s->n_idle.d(s->in); p.used = s->n_used.d(s->in); p.rel = s->n_rel.d(s->in); p.pip = s->n_pip.d(s->in);
+    p.kreq = s->n_kreq.d(s->in); p.knz = s->n_knz.d(s->in); p.pod_count = s->n_pod_count.d(s->in);
+    k_node_delta<<<(unsigned)((m + 127) / 128), 128, 0, s->stream>>>(p);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    // host mirrors the later actions read (pinned staging copy of the inputs, the evicting actions' opening rows)
+    double *h_idle = s->n_idle.h(s->in), *h_used = s->n_used.h(s->in), *h_rel = s->n_rel.h(s->in), *h_pip = s->n_pip.h(s->in);
+    double *h_kreq = s->n_kreq.h(s->in), *h_knz = s->n_knz.h(s->in);
+    int32_t *h_pods = s->n_pod_count.h(s->in);
+    for (size_t i = 0; i < m; ++i) {
+      const size_t n = (size_t)node_idx[i];
+      for (size_t d = 0; d < R; ++d) {
+        h_idle[d * N + n] = rows->idle[d * m + i]; h_used[d * N + n] = rows->used[d * m + i];
+        h_rel[d * N + n] = rows->releasing ? rows->releasing[d * m + i] : 0.0;
+        h_pip[d * N + n] = rows->pipelined ? rows->pipelined[d * m + i] : 0.0;
+        s->ek.n_idle[d * N + n] = h_idle[d * N + n]; s->ek.n_rel[d * N + n] = h_rel[d * N + n]; s->ek.n_pip[d * N + n] = h_pip[d * N + n];
+      }
+      for (size_t kk = 0; kk < K; ++kk) h_kreq[kk * N + n] = rows->k8s_requested[kk * m + i];
+      for (size_t kk = 0; kk < 2; ++kk) h_knz[kk * N + n] = rows->k8s_nonzero_requested[kk * m + i];
+      h_pods[n] = rows->pod_count[i];
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+  }
+  // the session is at its (new) opening state
+  s->alloc_ran = false; s->bf_ran = false; s->es_built = false; s->dense_ready = false;
+  s->last_idx_cur = s->dc.last_idx0;
+  s->last_dec.clear(); s->last_vis.clear();
+  s->upload_ms = now_ms() - t0;
+  s->h2d_bytes = (int64_t)((4 * R + 2 * K) * m * 8 + m * 8);
   return VC_OK;
 }
 

@@ -98,6 +98,17 @@ class Engine:
                                          C.byref(s.conf)))
         self._uploaded = True
 
+    def update_nodes(self, idx, idle, used, releasing, pipelined, k8s_requested, k8s_nonzero_requested, pod_count):
+        """Incremental upload of the accounting rows of the nodes `idx` (arrays compact: [dim][len(idx)])."""
+        idx = np.ascontiguousarray(idx, np.int32)
+        arrs = [np.ascontiguousarray(a, np.float64) for a in (idle, used, releasing, pipelined, k8s_requested, k8s_nonzero_requested)]
+        pods = np.ascontiguousarray(pod_count, np.int32)
+        rows = abi.vc_nodes()
+        rows.idle, rows.used, rows.releasing, rows.pipelined = (a.ctypes.data_as(_dp) for a in arrs[:4])
+        rows.k8s_requested, rows.k8s_nonzero_requested = arrs[4].ctypes.data_as(_dp), arrs[5].ctypes.data_as(_dp)
+        rows.pod_count = pods.ctypes.data_as(_i32p)
+        _check(self.L.vc_snapshot_update_nodes(self.h, len(idx), idx.ctypes.data_as(_i32p), C.byref(rows)))
+
     def allocate(self) -> AllocateResult:
         if not self._uploaded:
             self.upload()

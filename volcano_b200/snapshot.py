@@ -349,6 +349,42 @@ class Snapshot:
             _ptr(self.rt_uid_rank, _U32), _ptr(self.rt_resreq, _F64), _ptr(self.rt_req_has, _U32),
             _ptr(self.rt_k8s_req, _F64), _ptr(self.rt_k8s_nonzero_req, _F64), _ptr(self.rt_flags, _U32))
 
+    def dump(self, path: str) -> None:
+        """The session as a flat binary file a C program can feed to the C ABI (tools/cdriver/vcalloc_driver.c):
+        magic "VCSNAP01", vc_dims, vc_conf, then the arrays of vc_nodes, vc_tasks, vc_classes, vc_jobs, vc_queues in the
+        field order of include/vcalloc.h, each as uint64 byte count + raw little-endian bytes."""
+        import ctypes as C
+        g = lambda name: getattr(self, "t_" + name)
+        arrays = [
+            # vc_nodes
+            self.n_allocatable, self.n_idle, self.n_used, self.n_releasing, self.n_pipelined, self.n_k8s_allocatable,
+            self.n_k8s_requested, self.n_k8s_nonzero_requested, self.n_max_tasks, self.n_pod_count, self.n_label_bits,
+            self.n_taint_hard, self.n_taint_soft, self.n_flags, self.n_revocable_zone, self.zone_active,
+            # vc_tasks
+            g("resreq"), g("req_has"), g("k8s_req"), g("k8s_nonzero_req"), g("job"), g("klass"), g("role"), g("priority"),
+            g("pod_index"), g("creation_ts"), g("uid_rank"),
+            # vc_classes
+            self.c_selector, self.c_n_affinity, self.c_affinity, self.c_tolerated_hard, self.c_tolerated_soft,
+            self.c_n_preferred, self.c_preferred, self.c_preferred_weight, self.c_flags,
+            # vc_jobs
+            self.j_queue, self.j_min_available, self.j_priority, self.j_creation_ts, self.j_uid_rank, self.j_flags,
+            self.j_n_tasks_total, self.j_ready_num, self.j_waiting_num, self.j_pending_besteffort, self.j_valid_num,
+            self.j_task_min_total, self.j_role_off, self.j_allocated, self.r_min, self.r_occupied, self.r_pipelined,
+            self.r_pending_other, self.r_valid, self.r_flags,
+            # vc_queues
+            self.q_weight, self.q_priority, self.q_creation_ts, self.q_uid_rank, self.q_flags, self.q_capability,
+            self.q_capability_has, self.q_guarantee, self.q_guarantee_has, self.q_allocated, self.q_request,
+            self.q_request_has, self.q_allocated_has,
+        ]
+        with open(path, "wb") as f:
+            f.write(b"VCSNAP01")
+            f.write(bytes(self.dims()))
+            f.write(bytes(self.conf))
+            for a in arrays:
+                b = np.ascontiguousarray(a).tobytes()
+                f.write(np.uint64(len(b)).tobytes())
+                f.write(b)
+
     def backfill_tasks(self) -> Optional[abi.vc_tasks]:
         """The argument of vc_snapshot_set_backfill, or None when the session has no BestEffort pending task."""
         return self.tasks("b_") if self.B > 0 else None
