@@ -379,6 +379,32 @@ def main():
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    # ---- steady state of a cluster whose pending set did not change: only the accounting rows of the nodes whose
+    #      NodeInfo.Generation moved go up (vc_snapshot_update_nodes; 5 % of the nodes here, same values) ----------
+    inc = None
+    try:
+        dirty = np.sort(np.random.default_rng(1).choice(snap.N, size=max(1, snap.N // 20), replace=False)).astype(np.int32)
+        rows = (snap.n_idle[:, dirty], snap.n_used[:, dirty], snap.n_releasing[:, dirty], snap.n_pipelined[:, dirty],
+                snap.n_k8s_requested[:, dirty], snap.n_k8s_nonzero_requested[:, dirty], snap.n_pod_count[dirty])
+        eng.update_nodes(dirty, *rows)
+        eng.allocate()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        inc_placed, inc_h2d = 0, 0
+        for _ in range(args.steps):
+            eng.update_nodes(dirty, *rows)
+            r_inc = eng.allocate()
+            inc_placed += len(r_inc.decisions)
+            inc_h2d = r_inc.stats["h2d_bytes"]
+        torch.cuda.synchronize()
+        t_inc = time.perf_counter() - t1
+        inc = {"value": inc_placed / t_inc, "unit": "pods/s", "ms_per_step": 1e3 * t_inc / args.steps,
+               "h2d_bytes_per_step": int(inc_h2d), "dirty_nodes": int(len(dirty)),
+               "same_placements_as_full_upload": bool(np.array_equal(r_inc.decisions, res.decisions)),
+               "note": "pending set unchanged since the last full upload; rows of 5 % of the nodes re-sent"}
+        eng.upload()
+    except Exception as ex:
+        inc = {"error": str(ex)}
     clocks = sampler.stop()
     # ---- roofline kernel: dense task x node mask + score matrix ---------------------------------
     roof = None
@@ -462,6 +488,7 @@ def main():
             "parity": parity,
             "e2e": {"value": e2e_value, "unit": "pods/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * t_e2e / args.steps},
+            "e2e_incremental": inc,
             "gpu_launches": 2 * args.steps,  # k_class_static + k_commit per e2e step (1 per device-timed step)
             "clocks": clocks,
             "roofline": roof,

@@ -2261,6 +2261,25 @@ int vco_backfill_pick_order(void *h, int32_t *out) {
   for (size_t i = 0; i < p.size(); ++i) out[i] = p[i] - s.T_alloc;
   return (int)p.size();
 }
+// ph.PredicateNodes for one task with a fresh PredicateHelper (util/predicate_helper.go:43-140), for the reference's
+// TestPredicateNodes (util/predicate_helper_test.go:31-220): nodes_out = the feasible nodes in scan order, cache_out[n] = the
+// node has an entry in taskPredicateErrorCache[job/role], *group_exists = the cache holds that group at all
+int vco_predicate_nodes(void *h, int t, int32_t *nodes_out, uint8_t *cache_out, int *group_exists) {
+  Session &s = *(Session *)h;
+  PredicateHelper ph;
+  const int j = s.t_job[t];
+  ph.role_base = s.j_roleoff[j];
+  const int nroles = s.j_roleoff[j + 1] - s.j_roleoff[j];
+  ph.node_err.resize(nroles);
+  ph.exists.assign(nroles, 0);
+  std::vector<int> feasible;
+  predicate_nodes(s, ph, t, feasible);
+  const int lr = s.t_role[t] - ph.role_base;
+  *group_exists = ph.exists[lr];
+  for (int n = 0; n < s.N; ++n) cache_out[n] = (!ph.node_err[lr].empty() && ph.node_err[lr][n]) ? 1 : 0;
+  for (size_t i = 0; i < feasible.size(); ++i) nodes_out[i] = feasible[i];
+  return (int)feasible.size();
+}
 int vco_allocate_run(void *h) { return allocate_execute(*(Session *)h); }
 // Sampled replay ("parity on a 1 % task sample replayed through the oracle"): the caller's
 // decision list (any implementation's) is applied in order to this fresh session through Statement.Allocate /

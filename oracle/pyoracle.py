@@ -55,6 +55,8 @@ def lib() -> C.CDLL:
         L.vco_go_pow_uint.restype = C.c_double
         L.vco_go_pow_uint.argtypes = [C.c_double, C.c_uint]
         L.vco_allocate_run.argtypes = [_vp]
+        L.vco_predicate_nodes.restype = C.c_int
+        L.vco_predicate_nodes.argtypes = [_vp, C.c_int, _i32p, C.POINTER(C.c_uint8), C.POINTER(C.c_int)]
         L.vco_replay_check.restype = C.c_int64
         L.vco_replay_check.argtypes = [_vp, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int64, C.c_int64,
                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -181,6 +183,15 @@ class OracleSession:
         if rc != 0:
             raise RuntimeError(f"oracle reclaim rc={rc}")
         return self._results()
+
+    def predicate_nodes(self, t: int):
+        """ph.PredicateNodes for task t with a fresh helper -> (feasible nodes, error-cache marks per node, group exists)."""
+        N = self.snap.N
+        nodes = np.zeros(max(N, 1), np.int32)
+        cache = np.zeros(max(N, 1), np.uint8)
+        ex = C.c_int(0)
+        n = lib().vco_predicate_nodes(self.h, t, nodes.ctypes.data_as(_i32p), cache.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(ex))
+        return nodes[:n].copy(), cache[:N].copy(), bool(ex.value)
 
     def backfill_pick_order(self):
         out = np.zeros(max(self.snap.B, 1), np.int32)

@@ -105,12 +105,14 @@ def test_incremental_node_upload(oracle_engine):
     rng = np.random.default_rng(5)
     dirty = rng.choice(snap.N, size=max(2, snap.N // 10), replace=False).astype(np.int32)
     half = len(dirty) // 2
+    unit = np.ones(snap.R)  # quantities stay whole: extended resources move in units of 1000 milli (one device)
+    unit[snap.dim_names.index("nvidia.com/gpu")] = 1000.0
     for n in dirty[:half]:
-        freed = np.floor(snap.n_used[:, n] / 2)
+        freed = np.floor(snap.n_used[:, n] / 2 / unit) * unit
         snap.n_used[:, n] -= freed
         snap.n_idle[:, n] += freed
     for n in dirty[half:]:
-        taken = np.floor(snap.n_idle[:, n] / 3)
+        taken = np.floor(snap.n_idle[:, n] / 3 / unit) * unit
         snap.n_used[:, n] += taken
         snap.n_idle[:, n] -= taken
     snap.n_pod_count[dirty] = snap.n_used[snap.pods_dim, dirty].astype(np.int32)
@@ -125,8 +127,8 @@ def test_incremental_node_upload(oracle_engine):
     e.close()
     full = engine.gpu_engine(snap)
     ref = oracle_engine(snap)
-    for a in (inc, full):
-        assert np.array_equal(a.decisions, ref.decisions) and np.array_equal(a.visits, ref.visits)
-        assert np.array_equal(a.fit_errors, ref.fit_errors)
+    assert np.array_equal(full.decisions, ref.decisions) and np.array_equal(full.visits, ref.visits), "full upload vs oracle"
+    assert np.array_equal(inc.decisions, full.decisions) and np.array_equal(inc.visits, full.visits), "incremental vs full upload"
+    assert np.array_equal(inc.fit_errors, ref.fit_errors) and np.array_equal(full.fit_errors, ref.fit_errors)
     assert not np.array_equal(first.decisions["node"][:200], inc.decisions["node"][:200]) or len(first.decisions) != len(inc.decisions)
     assert inc.stats["h2d_bytes"] < full.stats["h2d_bytes"] / 5

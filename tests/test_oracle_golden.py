@@ -379,3 +379,36 @@ def test_reclaim_goldens(plugins, case, oracle_engine):
     case.RegisterSession(G.reclaim_tiers(plugins), actions=("reclaim",))
     case.Run(oracle_engine)
     assert case.CheckAll() is None, case.CheckAll()
+
+
+def test_predicate_nodes_error_cache_goldens():
+    """util/predicate_helper_test.go:31-220 TestPredicateNodes, the three cases without node sharding, on the oracle's
+    ph.PredicateNodes: no nodes -> no result and no cache entry; every node failing the predicate -> no result and a
+    cache entry per node under "job/role" (written whatever enableErrorCache says, read only when it is set); a passing
+    node -> returned, nothing cached. The reference injects predicate closures; here a node selector nobody / somebody
+    satisfies plays that part. (Cases 4-6 exercise --scheduler-sharding-mode, which is outside the path.)"""
+    from oracle.pyoracle import OracleSession
+    from volcano_b200.api import BuildNode, BuildPod, BuildPodGroup, BuildQueue, BuildResourceList
+    from volcano_b200.snapshot import PluginOption, SchedulerConf, encode_cluster
+
+    def session(nodes, selector):
+        pods = [BuildPod("ns", "task", "", "Pending", BuildResourceList("1", "1G"), "job1", {"volcano.sh/task-spec": "worker"}, selector)]
+        conf = SchedulerConf(tiers=[[PluginOption.make("predicates", EnabledPredicate=True)]])
+        return encode_cluster(nodes, pods, [BuildPodGroup("job1", "ns", "q", 1)], [BuildQueue("q", 1)], conf)
+
+    big = BuildResourceList("8", "8G", ("pods", "10"))
+    # "empty nodes returns empty result"
+    o = OracleSession(session([], {}))
+    nodes, cache, exists = o.predicate_nodes(0)
+    o.close()
+    assert len(nodes) == 0 and not exists
+    # "predicate errors returns empty result": expectedErrCache {"job1/worker": {node1, node2}}
+    o = OracleSession(session([BuildNode("node1", big, {"zone": "a"}), BuildNode("node2", big, {"zone": "a"})], {"zone": "b"}))
+    nodes, cache, exists = o.predicate_nodes(0)
+    o.close()
+    assert len(nodes) == 0 and exists and list(cache) == [1, 1]
+    # "predicate success returns node": expectedErrCache {}
+    o = OracleSession(session([BuildNode("node1", big, {"zone": "b"})], {"zone": "b"}))
+    nodes, cache, exists = o.predicate_nodes(0)
+    o.close()
+    assert list(nodes) == [0] and not exists and list(cache) == [0]

@@ -306,7 +306,7 @@ inline bool max_abs_integral(const double *v, size_t n, double &mx) {
   if (!v) return true;
   for (size_t i = 0; i < n; ++i) {
     const double a = std::fabs(v[i]);
-    if (!(a < 9.0e15) || v[i] != std::floor(v[i])) return false;
+    if (!(a < 9.0e15) || (double)(long long)v[i] != v[i]) return false;  // below 2^63: the conversion is exact iff integral
     if (a > mx) mx = a;
   }
   return true;

@@ -41,6 +41,11 @@ int fail(int code, const char *fmt, ...) {
     if (e_ != cudaSuccess) return fail(VC_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
   } while (0)
 
+// mailbox: two parities x up to 2048 CTA slots (several ranks) of MBOX_STRIDE uint4; a second region of the same size serves
+// the count all-gather of feasible-node sampling
+constexpr size_t kMbox2Offset = (size_t)MBOX_STRIDE * 2 * 2048;                // in uint4
+constexpr size_t kMboxBytes = sizeof(uint4) * MBOX_STRIDE * 2 * 2048 * 2;
+
 bool g_inited = false;
 int g_device = -1;
 int g_sm_count = 0;
@@ -223,10 +228,7 @@ struct vc_snapshot {
   int mwg = 0;
   bool matrix_allocated = false;
   double last_expand_ms = 0, last_dense_ms = 0;
-  // host copies kept for the dense-pass grouping
-  std::vector<double> h_req, h_kreq, h_knz;
-  std::vector<uint32_t> h_has;
-  std::vector<int32_t> h_class, h_task_job;
+  // (the host copies of the task arrays the dense-pass grouping and the later actions read live in `ek`)
   // ---- backfill action (vc_snapshot_set_backfill / vc_backfill_run) ----
   vch::BackfillTasks bf;  // host copy of the BestEffort task list
   vch::BackfillKeep bk;   // session-open state pickUpPendingTasks needs, kept at upload when bf.n > 0
@@ -1159,14 +1161,6 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   tick("H2D + K0 + sync");
   s->uploaded = true;
   s->dense_ready = false;
-  // keep what the dense pass needs to group tasks
-  s->h_req.assign(tk->resreq, tk->resreq + R * T);
-  s->h_kreq.assign(tk->k8s_req, tk->k8s_req + K * T);
-  s->h_knz.assign(tk->k8s_nonzero_req, tk->k8s_nonzero_req + 2 * T);
-  s->h_has.assign(tk->req_has, tk->req_has + T);
-  s->h_class.assign(tk->klass, tk->klass + T);
-  s->h_task_job.assign(tk->job, tk->job + T);
-  tick("host copies for the dense pass");
   // milli-units / bytes / counts are integers by construction (Quantity.MilliValue / Value); when that holds for the
   // rows and every request, m placements leave exactly row -/+ m * request: the commit kernel may cover a run of
   // placements on one node with one publication and k_backfill may run ahead m steps
@@ -1212,6 +1206,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     }
     if (!s->t_flags.empty() && s->t_flags.size() != T) return fail(VC_EINVAL, "task flags: %zu entries for %zu tasks", s->t_flags.size(), T);
   }
+  tick("host copies for the later actions");
   if (s->bf.n > 0) {  // what pickUpPendingTasks (backfill.go:118-199) orders by, as of session open
     vch::BackfillKeep &k = s->bk;
     k.j_queue.assign(jb->queue, jb->queue + J); k.j_min.assign(jb->min_available, jb->min_available + J);
@@ -1388,7 +1383,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
       s->rep_hn_used_count = cnt;
     }
   }
-  const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 2048 * 2;  // second half: the count all-gather of sampling
+  const size_t mbox_bytes = kMboxBytes;
   if (!s->mbox) CUDA_TRY(cudaMalloc(&s->mbox, mbox_bytes));
   if (!s->d_prof) CUDA_TRY(cudaMalloc(&s->d_prof, 16 * sizeof(long long)));
   const size_t ring_bytes = sizeof(uint4) * RING_STRIDE * RING_DEPTH;
@@ -1430,7 +1425,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   p.rep_i32 = s->rep_i32; p.rep_i32_stride = i32_stride; p.rep_f64 = s->rep_f64; p.rep_f64_stride = f64_stride;
   p.rep_heap = s->rep_heap; p.rep_heap_stride = std::max<size_t>(heap_stride, 1);
   p.mbox = s->mbox;
-  p.mbox2 = s->mbox + (size_t)MBOX_STRIDE * 2 * 2048;
+  p.mbox2 = s->mbox + kMbox2Offset;
   p.decisions = s->d_decisions; p.visits = s->d_visits; p.fit_errors = s->d_fit; p.counters = s->d_counters;
   p.prof = s->d_prof;
   p.tmeta = reinterpret_cast<const int4 *>(s->tmeta.d(s->in)); p.n_groups = s->n_groups;
@@ -2032,8 +2027,8 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
 
   // ---- 1 + 2. session state after allocate and pickUpPendingTasks (backfill.go:118-199): vc_host.hpp ----
   vch::BackfillPick pick = vch::backfill_pick(conf, s->alloc_ran, R, T, J, Q, B, s->dc.has_drf != 0, s->dc.has_proportion != 0, s->total,
-                                              s->total_has, bf, bk, s->last_dec.data(), s->last_dec.size(), s->h_task_job.data(),
-                                              s->h_req.data(), s->h_has.data(), s->qattr);
+                                              s->total_has, bf, bk, s->last_dec.data(), s->last_dec.size(), s->ek.t_job.data(),
+                                              s->ek.t_req.data(), s->ek.t_has.data(), s->qattr);
   const std::vector<int32_t> &order = pick.order, &j_ready = pick.j_ready, &r_occ = pick.r_occ;
   const std::vector<int> &visit_job = pick.visit_job, &visit_begin = pick.visit_begin;
   auto is_ready = [&](int j) { return j_ready[j] + bk.j_pbe[j] >= bk.j_min[j]; };  // job_info.go:1169
@@ -2122,7 +2117,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
   long long h_prof[10] = {0};
   if (n > 0) {
     const int G = s->n_cta;
-    const size_t mbox_bytes = sizeof(uint4) * MBOX_STRIDE * 2 * 1024 * 2;
+    const size_t mbox_bytes = kMboxBytes;
     if (!s->mbox && (e = cudaMalloc(&s->mbox, mbox_bytes)) != cudaSuccess) return bail(e, "mailbox");
     if ((e = cudaMemsetAsync(s->mbox, 0, mbox_bytes, s->stream)) != cudaSuccess) return bail(e, "mailbox reset");
     K2Params p;
@@ -2132,7 +2127,7 @@ int vc_backfill_run(vc_snapshot *s, vc_result **out) {
     p.idle = s->w_idle; p.used = s->w_used; p.kreq = s->w_kreq; p.knz = s->w_knz;
     p.max_tasks = s->n_max_tasks.d(s->in); p.pod_count = s->w_pod_count; p.cstat = s->cstat;
     p.mbox = s->mbox;
-    p.mbox2 = s->mbox + (size_t)MBOX_STRIDE * 2 * 2048;
+    p.mbox2 = s->mbox + kMbox2Offset;
     BackfillParams bp;
     unsigned char *base = static_cast<unsigned char *>(s->d_bf);
     bp.n = (int)n; bp.B = (int)B;
@@ -2229,11 +2224,11 @@ static int dense_prepare(vc_snapshot *s) {
   std::vector<int32_t> g_class(G), g_count(G + 1, 0);
   for (size_t g = 0; g < G; ++g) {
     int t = rep[g];
-    for (size_t d = 0; d < R; ++d) g_req[d * G + g] = s->h_req[d * T + t];
-    for (size_t k = 0; k < K; ++k) g_kreq[k * G + g] = s->h_kreq[k * T + t];
-    for (size_t k = 0; k < 2; ++k) g_knz[k * G + g] = s->h_knz[k * T + t];
-    g_has[g] = s->h_has[t] | ((s->topo_any && s->h_job_soft[s->h_task_job[t]]) ? VC_HAS_TOPO_TASK : 0u);
-    g_class[g] = s->h_class[t];
+    for (size_t d = 0; d < R; ++d) g_req[d * G + g] = s->ek.t_req[d * T + t];
+    for (size_t k = 0; k < K; ++k) g_kreq[k * G + g] = s->ek.t_kreq[k * T + t];
+    for (size_t k = 0; k < 2; ++k) g_knz[k * G + g] = s->ek.t_knz[k * T + t];
+    g_has[g] = s->ek.t_has[t] | ((s->topo_any && s->h_job_soft[s->ek.t_job[t]]) ? VC_HAS_TOPO_TASK : 0u);
+    g_class[g] = s->ek.t_class[t];
   }
   for (size_t t = 0; t < T; ++t) g_count[group_of[t] + 1]++;
   for (size_t g = 0; g < G; ++g) g_count[g + 1] += g_count[g];
