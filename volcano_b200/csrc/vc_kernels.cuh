@@ -114,6 +114,7 @@ struct GlobalNodeView {  // node columns straight from the SoA in HBM/L2
 struct K1Params {
   DevDims d;
   DevConf c;
+  int y_off;  // added to blockIdx.y: launches over more than 65535 groups / work items go out in slices
   const double *alloc, *idle, *used, *rel, *pip, *kalloc, *kreq, *knz;
   const int32_t *max_tasks, *pod_count;
   const uint32_t *cstat;
@@ -151,7 +152,7 @@ struct K1Params {
 // K1h: grid (ceil(H/128), G). One thread per (group, hypernode).
 __global__ void __launch_bounds__(128) k_hn_scores(K1Params p) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  const int g = blockIdx.y;
+  const int g = blockIdx.y + p.y_off;
   if (h >= p.hn_H) return;
   TaskRec t;
   for (int d = 0; d < p.d.R; ++d) t.req[d] = p.g_req[(size_t)d * p.n_groups + g];
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256) k_group_eval(K1Params p) {
   const int N = p.d.N;
   const int nloc = p.d.node_end - p.d.node_begin;
   const int li = blockIdx.x * blockDim.x + threadIdx.x;
-  const int g = blockIdx.y;
+  const int g = blockIdx.y + p.y_off;
   __shared__ TaskRec trec;
   if (threadIdx.x < p.d.R) trec.req[threadIdx.x] = p.g_req[(size_t)threadIdx.x * p.n_groups + g];
   if (threadIdx.x >= 32 && threadIdx.x < 32 + p.d.K) trec.kreq[threadIdx.x - 32] = p.g_kreq[(size_t)(threadIdx.x - 32) * p.n_groups + g];
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(256) k_group_best_partial(K1Params p, double *
   const int N = p.d.N;
   const int nloc = p.d.node_end - p.d.node_begin;
   const int li = blockIdx.x * blockDim.x + threadIdx.x;
-  const int g = blockIdx.y;
+  const int g = blockIdx.y + p.y_off;
   const int chosen = p.g_stats[g * 4 + 0] ? 0 : (p.g_stats[g * 4 + 1] ? 1 : 2);
   const int max_soft = chosen == 0 ? p.g_stats[g * 4 + 2] : p.g_stats[g * 4 + 3];
   double bs = 0.0;
@@ -279,7 +280,7 @@ __global__ void k_group_best_final(K1Params p, const double *part_score, const i
 __global__ void __launch_bounds__(256) k_group_expand(K1Params p) {
   const int N = p.d.N;
   const int nloc = p.d.node_end - p.d.node_begin;
-  const int w = blockIdx.y;
+  const int w = blockIdx.y + p.y_off;
   const int g = p.work_group[w];
   const int chosen = p.g_stats[g * 4 + 0] ? 0 : (p.g_stats[g * 4 + 1] ? 1 : 2);
   const int max_soft = chosen == 0 ? p.g_stats[g * 4 + 2] : p.g_stats[g * 4 + 3];
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(256) k_group_final(K1Params p, double *g_final
   const int N = p.d.N;
   const int nloc = p.d.node_end - p.d.node_begin;
   const int li = blockIdx.x * blockDim.x + threadIdx.x;
-  const int g = blockIdx.y;
+  const int g = blockIdx.y + p.y_off;
   const int chosen = p.g_stats[g * 4 + 0] ? 0 : (p.g_stats[g * 4 + 1] ? 1 : 2);
   const int max_soft = chosen == 0 ? p.g_stats[g * 4 + 2] : p.g_stats[g * 4 + 3];
   double sc = 0.0;
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(256) k_group_expand_bulk(K1Params p, int chunk
   double *tile = reinterpret_cast<double *>(k1_smem);
   const int N = p.d.N;
   const int nloc = p.d.node_end - p.d.node_begin;
-  const int w = blockIdx.y;
+  const int w = blockIdx.y + p.y_off;
   const int g = p.work_group[w];
   const int c0 = blockIdx.x * chunk;
   const int cn = min(chunk, nloc - c0);

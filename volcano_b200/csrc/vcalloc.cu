@@ -46,6 +46,17 @@ int fail(int code, const char *fmt, ...) {
 constexpr size_t kMbox2Offset = (size_t)MBOX_STRIDE * 2 * 2048;                // in uint4
 constexpr size_t kMboxBytes = sizeof(uint4) * MBOX_STRIDE * 2 * 2048 * 2;
 
+// a launch whose grid.y runs over `count` groups / work items, in slices of at most 65535 (the limit of gridDim.y)
+#define LAUNCH_Y_SLICED(kernel, gx, count, block, smem, stream, P, ...)                         \
+  do {                                                                                           \
+    for (size_t y0_ = 0; y0_ < (size_t)(count); y0_ += 65535) {                                   \
+      (P).y_off = (int)y0_;                                                                      \
+      dim3 g_((unsigned)(gx), (unsigned)std::min<size_t>(65535, (size_t)(count) - y0_));          \
+      kernel<<<g_, block, smem, stream>>>((P), ##__VA_ARGS__);                                   \
+    }                                                                                            \
+    (P).y_off = 0;                                                                               \
+  } while (0)
+
 bool g_inited = false;
 int g_device = -1;
 int g_sm_count = 0;
@@ -2321,12 +2332,10 @@ int vc_dense_begin(vc_snapshot *s) {
   CUDA_TRY(cudaMemsetAsync(s->g_stats, 0, std::max<size_t>(16, (size_t)s->n_groups * 16), s->stream));
   if (nloc > 0 && s->n_groups > 0) {
     K1Params p = dense_params(s);
-    dim3 grid((unsigned)((nloc + 255) / 256), (unsigned)s->n_groups);
-    k_group_eval<<<grid, 256, 0, s->stream>>>(p);
+    LAUNCH_Y_SLICED(k_group_eval, (nloc + 255) / 256, s->n_groups, 256, 0, s->stream, p);
     g_launches++;
     if (s->dc.nta_on) {
-      dim3 hgrid((unsigned)((s->hn_H + 127) / 128), (unsigned)s->n_groups);
-      k_hn_scores<<<hgrid, 128, 0, s->stream>>>(p);
+      LAUNCH_Y_SLICED(k_hn_scores, (s->hn_H + 127) / 128, s->n_groups, 128, 0, s->stream, p);
       g_launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -2358,8 +2367,7 @@ int vc_dense_finish(vc_snapshot *s, int materialize) {
   const int nparts = std::max(1, (nloc + 255) / 256);
   if (s->n_groups > 0) {
     if (nloc > 0) {
-      dim3 grid((unsigned)nparts, (unsigned)s->n_groups);
-      k_group_best_partial<<<grid, 256, 0, s->stream>>>(p, s->part_score, s->part_node);
+      LAUNCH_Y_SLICED(k_group_best_partial, nparts, s->n_groups, 256, 0, s->stream, p, s->part_score, s->part_node);
       g_launches++;
     } else {
       CUDA_TRY(cudaMemsetAsync(s->part_node, 0xff, (size_t)s->n_groups * nparts * 4, s->stream));
@@ -2377,8 +2385,7 @@ int vc_dense_finish(vc_snapshot *s, int materialize) {
         CUDA_TRY(cudaMalloc(&s->g_maskw, std::max<size_t>(16, (size_t)s->n_groups * s->mwg * 4)));
       }
       CUDA_TRY(cudaMemsetAsync(s->g_maskw, 0, std::max<size_t>(16, (size_t)s->n_groups * s->mwg * 4), s->stream));
-      dim3 fgrid((unsigned)((nloc + 255) / 256), (unsigned)s->n_groups);
-      k_group_final<<<fgrid, 256, 0, s->stream>>>(p, s->g_final, s->g_maskw, s->mwg);
+      LAUNCH_Y_SLICED(k_group_final, (nloc + 255) / 256, s->n_groups, 256, 0, s->stream, p, s->g_final, s->g_maskw, s->mwg);
       g_launches++;
       // node chunks of <= 8192 nodes (64 KB of scores) so several CTAs share an SM
       int max_chunk = 8192;
@@ -2387,18 +2394,16 @@ int vc_dense_finish(vc_snapshot *s, int materialize) {
       const int chunk = (((nloc + nchunks - 1) / nchunks) + 127) & ~127;
       const size_t smem = (size_t)chunk * 8 + 16;
       CUDA_TRY(cudaFuncSetAttribute(k_group_expand_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      dim3 grid((unsigned)((nloc + chunk - 1) / chunk), (unsigned)s->n_work);
       const int rows_cap = std::max(1, std::min(s->rows_per_item, (int)(96 * 1024 / std::max(16, s->mw32 * 4))));
       const size_t msmem = (size_t)rows_cap * s->mw32 * 4 + 16;
       CUDA_TRY(cudaFuncSetAttribute(k_mask_expand_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
       CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
-      k_group_expand_bulk<<<grid, 256, smem, s->stream>>>(p, chunk, s->g_final, s->g_maskw, s->mwg);
+      LAUNCH_Y_SLICED(k_group_expand_bulk, (nloc + chunk - 1) / chunk, s->n_work, 256, smem, s->stream, p, chunk, s->g_final, s->g_maskw, s->mwg);
       k_mask_expand_bulk<<<(unsigned)s->n_work, 128, msmem, s->stream>>>(p, s->g_maskw, s->mwg, rows_cap);
       g_launches++;
     } else {
-      dim3 grid((unsigned)((nloc + 511) / 512), (unsigned)s->n_work);
       CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
-      k_group_expand<<<grid, 256, 0, s->stream>>>(p);
+      LAUNCH_Y_SLICED(k_group_expand, (nloc + 511) / 512, s->n_work, 256, 0, s->stream, p);
     }
     g_launches++;
     CUDA_TRY(cudaEventRecord(s->ev2, s->stream));

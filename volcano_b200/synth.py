@@ -40,6 +40,8 @@ class SynthConfig:
     topology_scatter: float = 0.0     # fraction of nodes assigned to a random leaf / left outside the tree (tests)
     soft_topology_frac: float = 0.0   # fraction of jobs whose PodGroup carries a soft-mode network topology
     n_besteffort: int = 0             # extra BestEffort pending pods spread over the jobs (the backfill action's tasks)
+    hetero: int = 0                   # > 0: every task draws its own request from `hetero` distinct cpu / memory sizes
+                                      # (heterogeneous pods: the (class, request) groups of the dense pass approach T)
 
 
 CONFIGS = {
@@ -237,6 +239,18 @@ def make_snapshot(cfg: SynthConfig | str, seed: Optional[int] = None) -> Snapsho
     for k, col in enumerate((0, 1, 2)):
         s.t_k8s_req[k] = types[tt, col]
         s.t_k8s_nonzero_req[k] = types[tt, col]
+    if cfg.hetero > 0:  # heterogeneous pods: per-task cpu in 100m steps, memory in 256Mi steps
+        kc = rng.integers(1, cfg.hetero + 1, T).astype(np.float64)
+        km = rng.integers(1, cfg.hetero + 1, T).astype(np.float64)
+        s.t_resreq[D_CPU] = kc * 100.0
+        s.t_resreq[D_MEM] = km * 256.0 * MI
+        s.t_resreq[D_GPU] = 0.0
+        s.t_req_has[:] = np.uint32(1 << D_PODS)
+        for k, d in enumerate((D_CPU, D_MEM)):
+            s.t_k8s_req[k] = s.t_resreq[d]
+            s.t_k8s_nonzero_req[k] = s.t_resreq[d]
+        s.t_k8s_req[2] = 0.0
+        s.t_k8s_nonzero_req[2] = 0.0
     s.t_job[:] = job_of_task
     s.t_klass[:] = job_class[job_of_task]
     s.t_role[:] = job_of_task  # one role row per job
