@@ -18,6 +18,10 @@ import (
 	"k8s.io/klog/v2"
 
 	"volcano.sh/volcano/cmd/scheduler/app/options"
+	stockallocate "volcano.sh/volcano/pkg/scheduler/actions/allocate"
+	stockbackfill "volcano.sh/volcano/pkg/scheduler/actions/backfill"
+	stockpreempt "volcano.sh/volcano/pkg/scheduler/actions/preempt"
+	stockreclaim "volcano.sh/volcano/pkg/scheduler/actions/reclaim"
 	"volcano.sh/volcano/pkg/scheduler/api"
 	"volcano.sh/volcano/pkg/scheduler/conf"
 	"volcano.sh/volcano/pkg/scheduler/framework"
@@ -192,6 +196,10 @@ func fail(what string) { klog.Errorf("vcalloc %s: %s", what, C.GoString(C.vc_las
 // openCycle: encode the session and bring the device session up to date — a full upload, or the dirty node rows only
 func openCycle(ssn *framework.Session) bool {
 	e := encodeSession(ssn, enqueueConfigured())
+	if e.outOfScope != "" {
+		klog.V(3).Infof("vcalloc: %s is outside the device path, the stock action runs this cycle", e.outOfScope)
+		return false
+	}
 	sig := signature(e)
 	if cur.snap != nil && cur.taskSig == sig && cur.enc != nil && cur.enc.dims == e.dims {
 		// same pending set, jobs, queues: upload the rows of the nodes whose Generation moved (api/node_info.go:95-99)
@@ -279,9 +287,32 @@ func (a *Action) Initialize() {
 }
 func (a *Action) UnInitialize() {}
 
+// runStock: the session is outside the device path (hdrf, an upload the library refused, ...): the reference's own action
+// runs this cycle, and so do the follow-up actions of the same session (the device session does not see what it did)
+var stockSession *framework.Session
+
+func runStock(name string, ssn *framework.Session) {
+	stockSession = ssn
+	var act framework.Action
+	switch name {
+	case "allocate":
+		act = stockallocate.New()
+	case "backfill":
+		act = stockbackfill.New()
+	case "preempt":
+		act = stockpreempt.New()
+	default:
+		act = stockreclaim.New()
+	}
+	act.Initialize()
+	act.Execute(ssn)
+	act.UnInitialize()
+}
+
 func (a *Action) Execute(ssn *framework.Session) {
 	if !openCycle(ssn) {
-		return // "allocate did nothing this cycle": the session is untouched until the replay
+		runStock("allocate", ssn) // the session is untouched by the device path at this point
+		return
 	}
 	e := cur.enc
 	// buildAllocateContext rewrites Pending PodGroups to Inqueue when no enqueue action is configured (allocate.go:154-164);
@@ -295,7 +326,8 @@ func (a *Action) Execute(ssn *framework.Session) {
 	}
 	var res *C.vc_result
 	if rc := C.vc_allocate_run(cur.snap, &res); rc != 0 {
-		fail("allocate")
+		fail("allocate") // e.g. VC_EUNSUPPORTED for hard-mode topology jobs: nothing was applied
+		runStock("allocate", ssn)
 		return
 	}
 	defer C.vc_result_free(res)
@@ -359,8 +391,13 @@ func (a *followUp) Name() string         { return a.name }
 func (a *followUp) Initialize()          {}
 func (a *followUp) UnInitialize()        {}
 func (a *followUp) Execute(ssn *framework.Session) {
+	if stockSession == ssn { // an earlier action of this cycle ran on the stock path
+		runStock(a.name, ssn)
+		return
+	}
 	if cur.snap == nil || cur.enc == nil || cur.enc.ssn != ssn {
 		if !openCycle(ssn) { // the action runs without allocate before it in the configured list
+			runStock(a.name, ssn)
 			return
 		}
 	}
@@ -376,7 +413,9 @@ func (a *followUp) Execute(ssn *framework.Session) {
 		rc = C.vc_reclaim_run(cur.snap, &res)
 	}
 	if rc != 0 {
-		fail(a.name) // VC_EUNSUPPORTED: the configuration is outside the path; the stock action can be run instead
+		fail(a.name) // VC_EUNSUPPORTED: the configuration is outside the path and nothing was applied; the session state is
+		// what the earlier replays left, so the reference's action can take over from here
+		runStock(a.name, ssn)
 		return
 	}
 	defer C.vc_result_free(res)

@@ -51,6 +51,8 @@ type session struct {
 	dims C.vc_dims
 	conf C.vc_conf
 
+	outOfScope string // non-empty: a feature the device path does not model; the shim runs the stock action instead
+
 	// vc_nodes
 	nAlloc, nIdle, nUsed, nRel, nPip, nKAlloc, nKReq, nKNz []float64
 	nMaxTasks, nPodCount, nZone                              []int32
@@ -749,6 +751,9 @@ func (e *session) encodeConf(tiers []conf.Tier, enqueueConfigured bool) {
 			id, ok := ids[p.Name]
 			if !ok {
 				id = C.VC_PLUGIN_OTHER
+			}
+			if p.Name == "drf" && on(p.EnabledHierarchy) { // hdrf: queue order from the hierarchy tree (drf/drf.go:147-156)
+				e.outOfScope = "drf with enableHierarchy"
 			}
 			var en C.uint32_t
 			for flag, b := range map[C.uint32_t]*bool{C.VC_EN_JOB_ORDER: p.EnabledJobOrder, C.VC_EN_JOB_READY: p.EnabledJobReady,

@@ -36,6 +36,9 @@ class PluginOption:
         """PluginOption{Name: ..., EnabledJobOrder: &trueValue, ...}."""
         flags = 0
         for k, v in enables.items():
+            if k.lower() in ("enabledhierarchy", "enablehierarchy") and v:
+                # hierarchical drf (plugins/drf/drf.go:147-156, hdrf) orders queues by a tree the path does not model
+                raise NotImplementedError("drf with enableHierarchy (hdrf) is outside the accelerated path")
             if k not in abi.ENABLE_FLAGS:
                 # extension points that do not touch the allocate path (EnabledPreemptable, ...)
                 continue
