@@ -338,8 +338,10 @@ typedef struct vc_stats {
   int64_t prof_cycles[8]; /* commit kernel phase timers (SM cycles of CTA 0): 0 queue/job control, 1 task fetch +
                              gates, 2 node sweep, 3 mailbox exchange, 4 apply + bookkeeping */
   int32_t last_processed_node_index; /* util.lastProcessedNodeIndex after the cycle (to carry into the next one) */
-  int32_t reserved;
+  int32_t commit_kernel; /* which instance of the commit kernel served the cycle: VC_KERNEL_* (diagnostic) */
 } vc_stats;
+#define VC_KERNEL_GENERAL 0      /* k_commit: full sweep + all-gather per placement */
+#define VC_KERNEL_INCREMENTAL 1  /* k_commit_fast: verdict cache, single-record publications, run-length batches */
 
 typedef struct vc_snapshot vc_snapshot;
 typedef struct vc_result vc_result;

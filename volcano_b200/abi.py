@@ -214,11 +214,14 @@ class vc_visit(C.Structure):
     _fields_ = [("job", C.c_int32), ("outcome", C.c_int32), ("first_op", C.c_int32), ("n_ops", C.c_int32)]
 
 
+VC_KERNEL_GENERAL, VC_KERNEL_INCREMENTAL = 0, 1
+
+
 class vc_stats(C.Structure):
     _fields_ = [("upload_ms", C.c_double), ("commit_ms", C.c_double), ("download_ms", C.c_double),
                 ("total_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("kernel_launches", C.c_int32), ("n_steps", C.c_int32), ("prof_cycles", C.c_int64 * 8),
-                ("last_processed_node_index", C.c_int32), ("reserved", C.c_int32)]
+                ("last_processed_node_index", C.c_int32), ("commit_kernel", C.c_int32)]
 
 
 # every symbol include/vcalloc.h declares: name -> (restype, argtypes)

@@ -85,6 +85,8 @@ struct K2Params {
   //      of the node axis; a CTA's records go into EVERY rank's mailbox / ring through peer-mapped memory (NVLink
   //      stores), and are polled locally ----
   int n_ranks;            // 1: single GPU
+  int *dbg;               // VC_PROF + VC_WATCHDOG_MS: [n_cta][8] progress words the watchdog prints (nullptr otherwise)
+  long long wd_cycles;    // watchdog of the exchange polls (k_commit_fast): SM cycles without an answer before the kernel aborts
   int cta_base;           // global index of this rank's CTA 0; n_cta counts the CTAs of all ranks
   uint4 *peer_mbox[8];    // [n_ranks] the mailbox of every rank (own one included)
   uint4 *peer_ring[8];    // [n_ranks]

@@ -1,8 +1,10 @@
 // vc_commit_fast.cuh — K2f, the incremental variant of the persistent commit kernel.
 //
-// Same exact semantics as k_commit (vc_commit.cuh), for the common session shape: no Releasing / Pipelined
-// resources at open (FutureIdle == Idle, so only the idle gradient exists), no normalising batch scorer,
-// R <= 8. It exploits the one structural fact of the greedy loop: a placement changes ONE node, so between
+// Same exact semantics as k_commit (vc_commit.cuh), for the common session shape: no normalising batch scorer, no
+// feasible-node sampling, no hypernode scores, R <= 8. The FUT instance serves sessions with Releasing / Pipelined
+// resources (terminating pods, pipelined tasks): a node's verdict is then 0 (fits Idle: allocate), 1 (fits only
+// FutureIdle = Idle + Releasing - Pipelined: pipeline) or 2, and a candidate of category 0 beats every candidate of
+// category 1 (prioritizeNodes' idle gradient first, allocate.go:750-776). It exploits the one structural fact of the greedy loop: a placement changes ONE node, so between
 // two consecutive tasks with the same (class, request) record every other (task, node) verdict and score
 // is unchanged. Per CTA it keeps, for the group being placed,
 //     c_cat[i], c_score[i], c_cs[i]   verdict, total score, static word of each of its nodes (shared memory)
@@ -94,12 +96,13 @@ struct FastParams {  // extra kernel arguments of the fast kernel
 
 struct FastSmem {
   double *alloc, *idle, *used, *kalloc, *kreq, *knz;
+  double *rel, *pip;  // FUT instance only
   int32_t *max_tasks, *pod_count, *nerr_stamp, *c_cat;
   uint32_t *c_cs;
   unsigned long long *nerr;
   double *c_score;
   double *sl_score;
-  int32_t *sl_node, *sl_cnt;
+  int32_t *sl_node, *sl_cnt, *sl_cat;
   int cap;
 };
 struct FastNodeView {
@@ -116,17 +119,32 @@ struct FastNodeView {
 struct Best {
   double score;
   int node;
-  int cnt;
+  int cnt;  // candidates of category `cat`
+  int cat;  // fit category of the candidate: 0 idle-fit, 1 future-idle-fit (always 0 outside the FUT instance)
 };
-__device__ __forceinline__ void best_fold(Best &a, double s, int n, int cnt) {
-  if (n >= 0 && (a.node < 0 || better(s, n, a.score, a.node))) { a.score = s; a.node = n; }
+// (cat, score, node) order: the idle gradient first, then the higher score, then the lower node index
+__device__ __forceinline__ bool better_c(int cat, double s, int n, int bcat, double bs, int bn) {
+  return cat < bcat || (cat == bcat && better(s, n, bs, bn));
+}
+__device__ __forceinline__ void best_fold(Best &a, double s, int n, int cnt, int cat = 0) {
+  if (n < 0) return;
+  if (a.node < 0 || cat < a.cat) { a.score = s; a.node = n; a.cnt = cnt; a.cat = cat; return; }
+  if (cat > a.cat) return;
+  if (better(s, n, a.score, a.node)) { a.score = s; a.node = n; }
   a.cnt += cnt;
 }
 // warp arg-max with the hardware reductions: order-preserving 64-bit key as two 32-bit maxima, then the lowest
 // node among the lanes that hold the maximum (see local_warp_reduce in vc_commit.cuh)
+template <bool FUT = false>
 __device__ __forceinline__ void best_warp_reduce(Best &b) {
   constexpr unsigned FULLM = 0xffffffffu;
-  const bool valid = b.node >= 0;
+  bool valid = b.node >= 0;
+  if (FUT) {  // only the lanes of the lowest category present take part
+    const unsigned mc = __reduce_min_sync(FULLM, valid ? (unsigned)b.cat : 3u);
+    valid = valid && (unsigned)b.cat == mc;
+    if (!valid) b.cnt = 0;
+    b.cat = mc == 3u ? 0 : (int)mc;
+  }
   const unsigned long long key = valid ? score_key(b.score) : 0ull;
   const unsigned hi = (unsigned)(key >> 32);
   const unsigned mhi = __reduce_max_sync(FULLM, hi);
@@ -139,20 +157,22 @@ __device__ __forceinline__ void best_warp_reduce(Best &b) {
 }
 __device__ __forceinline__ uint4 pack_best(const Best &b, unsigned tag) {
   unsigned long long sb = (unsigned long long)__double_as_longlong(b.score);
-  return make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)b.node, (tag << 2) | (unsigned)min(b.cnt, 2));
+  return make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)b.node, (tag << 3) | ((unsigned)b.cat << 2) | (unsigned)min(b.cnt, 2));
 }
 __device__ __forceinline__ Best unpack_best(const uint4 &v) {
   Best b;
   b.score = __longlong_as_double((long long)((unsigned long long)v.x | ((unsigned long long)v.y << 32)));
   b.node = (int)v.z;
   b.cnt = (int)(v.w & 3u);
+  b.cat = (int)((v.w >> 2) & 1u);
   return b;
 }
 
 // ring record of a publication: the owner CTA's new best + how many placements the record covers (1..RUN_MAX)
 __device__ __forceinline__ uint4 pack_run(const Best &b, unsigned tag, int m) {
   unsigned long long sb = (unsigned long long)__double_as_longlong(b.score);
-  return make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)b.node, (tag << 10) | ((unsigned)m << 2) | (unsigned)min(b.cnt, 2));
+  return make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)b.node,
+                    (tag << 10) | ((unsigned)m << 3) | ((unsigned)b.cat << 2) | (unsigned)min(b.cnt, 2));
 }
 #define RUN_TAG_MASK 0x3fffffu
 
@@ -161,23 +181,29 @@ __device__ __forceinline__ void store_all(const K2Params &p, uint4 *const *peers
   if (p.n_ranks <= 1) { mbox_store(local + off, v); return; }
   for (int r = 0; r < p.n_ranks; ++r) mbox_store(peers[r] + off, v);
 }
-// multi-GPU runs only: a poll that saw nothing for ~10 s means a peer never came up or the ranks diverged — abort the
-// kernel (the context dies with an error) instead of spinning until somebody kills the job
+// a poll that saw nothing for p.wd_cycles (~10 s by default) means a peer never came up or the replicas of the control
+// program diverged - abort the kernel (the launch fails with an error) instead of spinning until somebody kills the job
+#define WD_EXTRA
+#define DBG_STAGE(k, v) do { if (PROF && p.dbg && (threadIdx.x & 31) == 0) ((volatile int *)p.dbg)[(size_t)blockIdx.x * 8 + (k)] = (v); } while (0)
 #define PEER_WATCHDOG(spins, t0)                                                                  \
   do {                                                                                            \
-    if (p.n_ranks > 1 && ((++(spins)) & 0x3ffffu) == 0 && clock64() - (t0) > 20000000000ll) __trap(); \
+    if (((++(spins)) & 0x3ffffu) == 0 && clock64() - (t0) > p.wd_cycles) {                        \
+      if ((threadIdx.x & 31) == 0) printf("k_commit_fast watchdog: CTA %d line %d\n", (int)(p.cta_base + blockIdx.x), __LINE__); \
+      WD_EXTRA;                                                                                   \
+      __trap();                                                                                   \
+    }                                                                                             \
   } while (0)
 
 // all-gather of the CTA bests (warp 0 of every CTA); fills the slot table
 __device__ __forceinline__ void exchange_all_fast(const K2Params &p, const Best &mine, unsigned ag, FastSmem &fs) {
   const int lane = threadIdx.x & 31;
   const int G = p.n_cta;
-  const unsigned tag = (ag + 1u) & 0x3fffffffu;
+  const unsigned tag = (ag + 1u) & 0x1fffffffu;
   const size_t par = (size_t)(ag & 1u) * G * MBOX_STRIDE;
   uint4 *base = p.mbox + par;
   if (lane == 0) store_all(p, p.peer_mbox, p.mbox, par + (size_t)(p.cta_base + blockIdx.x) * MBOX_STRIDE, pack_best(mine, tag));
   unsigned spins = 0;
-  const long long t0w = p.n_ranks > 1 ? clock64() : 0;
+  const long long t0w = clock64();
   for (int s0 = 0; s0 < G; s0 += 32 * 4) {
     uint4 a[4];
     bool need[4];
@@ -192,10 +218,10 @@ __device__ __forceinline__ void exchange_all_fast(const K2Params &p, const Best 
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (!need[k]) continue;
-        if ((a[k].w >> 2) != tag) { pending = true; continue; }
+        if ((a[k].w >> 3) != tag) { pending = true; continue; }
         const int s = s0 + k * 32 + lane;
         Best b = unpack_best(a[k]);
-        fs.sl_score[s] = b.score; fs.sl_node[s] = b.node; fs.sl_cnt[s] = b.cnt;
+        fs.sl_score[s] = b.score; fs.sl_node[s] = b.node; fs.sl_cnt[s] = b.cnt; fs.sl_cat[s] = b.cat;
         need[k] = false;
       }
       if (pending) PEER_WATCHDOG(spins, t0w);
@@ -204,27 +230,38 @@ __device__ __forceinline__ void exchange_all_fast(const K2Params &p, const Best 
   __syncwarp();
 }
 
-// best of this CTA from its verdict/score cache (warp 0); cnt = exact number of candidates
-__device__ __forceinline__ Best scan_cache(const FastSmem &fs, int nmine, int nbase) {
+// best of this CTA from its verdict/score cache (a whole warp); cnt = exact number of candidates of the best's category;
+// the FUT instance also returns how many nodes sit in each category
+template <bool FUT>
+__device__ __forceinline__ Best scan_cache(const FastSmem &fs, int nmine, int nbase, int *cnt01 = nullptr) {
   const int lane = threadIdx.x & 31;
-  Best b{0.0, -1, 0};
-  for (int i = lane; i < nmine; i += 32)
-    if (fs.c_cat[i] == 0) best_fold(b, fs.c_score[i], nbase + i, 1);
-  best_warp_reduce(b);
+  Best b{0.0, -1, 0, 0};
+  int n0 = 0, n1 = 0;
+  for (int i = lane; i < nmine; i += 32) {
+    const int cc = fs.c_cat[i];
+    if (cc == 0 || (FUT && cc == 1)) best_fold(b, fs.c_score[i], nbase + i, 1, cc);
+    if (FUT) { n0 += cc == 0; n1 += cc == 1; }
+  }
+  best_warp_reduce<FUT>(b);
+  if (FUT && cnt01) {
+    cnt01[0] = (int)__reduce_add_sync(0xffffffffu, (unsigned)n0);
+    cnt01[1] = (int)__reduce_add_sync(0xffffffffu, (unsigned)n1);
+  }
   return b;
 }
 // arg-max over the slot table (warp 0)
+template <bool FUT>
 __device__ __forceinline__ Best fold_slots(const FastSmem &fs, int G, int *owner_out) {
   const int lane = threadIdx.x & 31;
-  Best g{0.0, -1, 0};
+  Best g{0.0, -1, 0, 0};
   int owner = -1;
   for (int s = lane; s < G; s += 32) {
     const int before = g.node;
-    best_fold(g, fs.sl_score[s], fs.sl_node[s], fs.sl_cnt[s]);
+    best_fold(g, fs.sl_score[s], fs.sl_node[s], fs.sl_cnt[s], FUT ? fs.sl_cat[s] : 0);
     if (g.node != before) owner = s;
   }
   const int my_node = g.node;
-  best_warp_reduce(g);
+  best_warp_reduce<FUT>(g);
   // the winning node sits in exactly one slot: the lane whose local best it is knows the owner
   *owner_out = (int)__reduce_max_sync(0xffffffffu, (unsigned)((g.node >= 0 && my_node == g.node) ? owner + 1 : 0)) - 1;
   return g;
@@ -253,18 +290,21 @@ struct CtlFast {  // shared-memory state of the fast kernel next to Ctl
   RoleDyn rd[VC_MAX_JOB_ROLES];
   double cta_best_score, g_best_score;
   int cta_best_node, cta_cnt, g_best_node, g_cnt;
+  int cta_best_cat, cta_cnt1;  // FUT: category of the CTA's best; cta_cnt / cta_cnt1 = nodes of category 0 / 1
   // run-ahead results of warp 2, double-buffered by the parity of the CMD_EVAL count
   double spec_sc[2];
-  int spec_i[2], spec_group[2], spec_cat[2];
+  int spec_i[2], spec_group[2], spec_cat[2], spec_kind[2];
   // CMD_EVAL mailbox between warp 0 (control) and warp 1 (evaluator)
   double ev_score;
-  int ev_i, ev_ring, ev_node, ev_cnt, cur_group;
+  int ev_i, ev_ring, ev_node, ev_cnt, ev_cat, cur_group;
+  int ev_kind;  // FUT: the placement just applied to row ev_i was an allocation (0) or a pipeline (1)
   unsigned ev_tag;
   // CMD_RUN: placements the control program allows on node ev_i in a row (run_L), attempt index of the first one,
   // result (run_m placements made), runner-up computed by warp 2
   int run_L, run_att0, run_m;
   double ru_score, rl_score;
   int ru_node, rl_node, rl_cnt;
+  int ru_cat, rl_cat, rl_cnt0, rl_cnt1;
   double run_sc[RUN_MAX];  // state k of the row (after k further placements): total score, fit category
   int run_cat[RUN_MAX];
 };
@@ -289,7 +329,7 @@ struct RunNodeView {
 // PROF = true keeps the phase / owner-path cycle counters (tools/prof_commit.py, VC_PROF=1); the production
 // instance carries no clock reads on the control warp's critical path.
 #define FPROF_MARK(k) do { if (PROF) { PROF_MARK(k); } } while (0)
-template <bool PROF>
+template <bool PROF, bool FUT = false>
 __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams fp) {
   const DevConf &c = p.c;
   const int R = p.d.R, K = p.d.K, N = p.d.N, J = p.d.J, Q = p.d.Q, NR = p.d.NR, T = p.d.T;
@@ -311,6 +351,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   fs.cap = cap;
   auto take = [&](int rows) { double *q = reinterpret_cast<double *>(sp); sp += (size_t)rows * cap * sizeof(double); return q; };
   fs.alloc = take(R); fs.idle = take(R); fs.used = take(R);
+  fs.rel = fs.pip = nullptr;
+  if (FUT) { fs.rel = take(R); fs.pip = take(R); }
   fs.kalloc = take(K); fs.kreq = take(K); fs.knz = take(2);
   fs.c_score = take(1);
   fs.nerr = reinterpret_cast<unsigned long long *>(sp); sp += (size_t)cap * 8;
@@ -322,6 +364,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   fs.c_cs = reinterpret_cast<uint32_t *>(sp); sp += (size_t)cap * 4;
   fs.sl_node = reinterpret_cast<int32_t *>(sp); sp += (size_t)G * 4;
   fs.sl_cnt = reinterpret_cast<int32_t *>(sp); sp += (size_t)G * 4;
+  fs.sl_cat = reinterpret_cast<int32_t *>(sp); sp += (size_t)G * 4;
   sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 15) & ~(uintptr_t)15);
   HeapKey *heap = fp.heap_in_smem ? reinterpret_cast<HeapKey *>(sp)
                                   : reinterpret_cast<HeapKey *>(p.rep_heap) + (size_t)lcta * p.rep_heap_stride;
@@ -332,6 +375,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       fs.alloc[d * cap + i] = p.alloc[(size_t)d * N + n];
       fs.idle[d * cap + i] = p.idle[(size_t)d * N + n];
       fs.used[d * cap + i] = p.used[(size_t)d * N + n];
+      if (FUT) { fs.rel[d * cap + i] = p.rel[(size_t)d * N + n]; fs.pip[d * cap + i] = p.pip[(size_t)d * N + n]; }
     }
     for (int k = 0; k < K; ++k) {
       fs.kalloc[k * cap + i] = p.kalloc[(size_t)k * N + n];
@@ -346,7 +390,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     fs.c_score[i] = 0.0;
     fs.c_cs[i] = 0u;
   }
-  for (int s = tid; s < G; s += blockDim.x) { fs.sl_score[s] = 0.0; fs.sl_node[s] = -1; fs.sl_cnt[s] = 0; }
+  for (int s = tid; s < G; s += blockDim.x) { fs.sl_score[s] = 0.0; fs.sl_node[s] = -1; fs.sl_cnt[s] = 0; fs.sl_cat[s] = 0; }
 
   // ---- per-CTA replica of the mutable control state, packed records ----
   unsigned char *rb = reinterpret_cast<unsigned char *>(p.rep_f64 + (size_t)lcta * p.rep_f64_stride);
@@ -387,6 +431,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     S.cmd = 0; S.visit_id = 0; S.cur_group = -1; S.cache_group = -1; S.dirty_node = -1;
     S.ag = 0; S.pc = 0; S.since_sync = 0; S.n_full = 0; S.n_incr = 0;
     F.cta_best_node = -1; F.cta_cnt = 0; F.g_best_node = -1; F.g_cnt = 0; F.cta_best_score = F.g_best_score = 0.0;
+    F.cta_best_cat = 0; F.cta_cnt1 = 0; F.ev_kind = 0; F.ev_cat = 0;
     F.spec_i[0] = F.spec_i[1] = -1;
   }
   __syncthreads();
@@ -398,7 +443,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     const int rl = S.sweep_rl;
     const bool use_cache = S.sweep_use_cache != 0;
     const int vid = S.visit_id;
-    Best b{0.0, -1, 0};
+    Best b{0.0, -1, 0, 0};
+    int n0 = 0, n1 = 0;
     for (int i = tid; i < nmine; i += blockDim.x) {
       FastNodeView nv{fs, i};
       const uint32_t cs = __ldg(cs_row + i);
@@ -406,26 +452,48 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       int cat = 2;
       double sc = 0.0;
       if (!(use_cache && ((fs.nerr[i] >> rl) & 1ull))) {
-        cat = eval_pair_fast(c, R, K, trec, nv, cs, c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i], &sc);
+        const bool pod_cap = c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i];
+        cat = eval_pair_fast(c, R, K, trec, nv, cs, pod_cap, &sc);
+        if (FUT) {
+          // alloc.predicate: InitResreq <= FutureIdle (allocate.go:816-824); the idle gradient is the subset that fits
+          // Idle as well (:722-733). eval_pair_fast answered 0 exactly when the static part, the pod count AND Idle pass.
+          bool fit_future = (cs & CS_STATIC_OK) != 0 && !pod_cap;
+          for (int d = 0; d < R; ++d) {
+            if (d >= 2 && !(trec.has & (1u << d))) continue;
+            const double fut = (fs.idle[d * cap + i] + fs.rel[d * cap + i]) - fs.pip[d * cap + i];
+            if (!le_eps(trec.req[d], fut)) fit_future = false;
+          }
+          cat = !fit_future ? 2 : (cat == 0 ? 0 : 1);
+        }
         if (cat == 2 && use_cache) fs.nerr[i] |= (1ull << rl);
       }
       fs.c_cat[i] = cat;
       fs.c_score[i] = sc;
       fs.c_cs[i] = cs;
-      if (cat == 0) best_fold(b, sc, nbase + i, 1);
+      if (cat == 0 || (FUT && cat == 1)) best_fold(b, sc, nbase + i, 1, cat);
+      if (FUT) { n0 += cat == 0; n1 += cat == 1; }
     }
-    best_warp_reduce(b);
-    if (lane == 0) { S.w_score[0][warp] = b.score; S.w_node[0][warp] = b.node; S.w_cnt[0][warp] = b.cnt; }
+    best_warp_reduce<FUT>(b);
+    if (FUT) {
+      n0 = (int)__reduce_add_sync(0xffffffffu, (unsigned)n0);
+      n1 = (int)__reduce_add_sync(0xffffffffu, (unsigned)n1);
+    }
+    if (lane == 0) {
+      S.w_score[0][warp] = b.score; S.w_node[0][warp] = b.node; S.w_cnt[0][warp] = FUT ? n0 : b.cnt;
+      if (FUT) { S.w_cnt[1][warp] = n1; S.w_node[1][warp] = b.cat; }
+    }
   };
   // stmt.Discard() for this thread's nodes (command CMD_DISCARD), statement.go:357-381
   auto discard_part = [&]() {
     const int n_ops = S.n_ops;
     for (int k = n_ops - 1; k >= 0; --k) {
       const int ot = ops[k * 3 + 0], on = ops[k * 3 + 1];
+      const bool was_pipe = FUT && ops[k * 3 + 2] == VC_OP_PIPELINE;
       if (on >= nbase && on < nbase + nmine && ((on - nbase) % blockDim.x) == tid) {
         const int i = on - nbase;
         for (int d = 0; d < R; ++d) {
           double rq = p.req[(size_t)d * T + ot];
+          if (was_pipe) { fs.pip[d * cap + i] -= rq; continue; }
           fs.idle[d * cap + i] += rq;
           fs.used[d * cap + i] -= rq;
         }
@@ -463,6 +531,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   const double *a_base = role == ROLE_BP ? fs.used + dk_c * cap : role == ROLE_BAL ? fs.kreq + dk_c * cap : fs.knz + dk_c * cap;
   const double *al_base = role == ROLE_BP ? fs.alloc + dk_c * cap : fs.kalloc + dk_c * cap;
   const double *idle_base = fs.idle + ((hl < 8 && hl < R) ? hl : 0) * cap;
+  const double *rel_base = FUT ? fs.rel + ((hl < 8 && hl < R) ? hl : 0) * cap : nullptr;
+  const double *pip_base = FUT ? fs.pip + ((hl < 8 && hl < R) ? hl : 0) * cap : nullptr;
   const int w_d = (role == ROLE_BP && lane_valid) ? c.binpack_dim_weight[dk_c] : 0;
   const double mul_const = role == ROLE_BP ? (double)w_d : (role == ROLE_LEAST || role == ROLE_MOST) ? 100.0 : 1.0;
   // per-group lane operands (refreshed when the staged group record changes)
@@ -483,20 +553,29 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   // `extra` = 1 evaluates the node as it will be after ONE more placement of this same group (speculation: under
   // best-fit scoring the node that just won usually wins again); the adds are the same IEEE operations the real
   // placement performs (node_info.go:467-471, predicates.go:254-255), so the speculative score is bit-identical.
-  auto eval_dirty = [&](int i0, int i1, int k0, int k1, uint32_t cs, double *score_out) -> int {
+  auto eval_dirty = [&](int i0, int i1, int k0, int k1, uint32_t cs, double *score_out, int kind = 0) -> int {
     // lanes 0-15 evaluate row i0 after k0 further placements of this group, lanes 16-31 row i1 after k1 (0 = as it
-    // is); cs = the static word of the lane's row
+    // is); cs = the static word of the lane's row; kind (FUT) = those further placements are allocations (0: Idle,
+    // Used move) or pipelines (1: only Pipelined moves, node_info.go:457-458) - the upstream NodeInfo follows both
     const int i = half ? i1 : i0;
     const int k = half ? k1 : k0;
     const double kf = (double)k;
     const int hs = half << 4;
     const int kx = c.has_predicates ? k : 0;
+    const bool pipe = FUT && kind == 1;
     const bool pod_cap = c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i] + kx;
-    const bool bump = k > 0 && (role == ROLE_BP || c.has_predicates);
+    const bool bump = k > 0 && (role == ROLE_BP ? !pipe : c.has_predicates);
     const double a0 = a_base[i], alloc = al_base[i], idle0 = idle_base[i];
     const double a = bump ? a0 + kf * b_val : a0;
-    const double idle = k > 0 ? idle0 - kf * req_fit : idle0;
+    const double idle = (k > 0 && !pipe) ? idle0 - kf * req_fit : idle0;
     const bool bad_fit = fit_on && !le_eps(req_fit, idle);
+    bool bad_fut = false;
+    if (FUT) {  // FutureIdle = Idle + Releasing - Pipelined, node_info.go:114-116
+      const double pip0 = pip_base[i];
+      const double pipv = (k > 0 && pipe) ? pip0 + kf * req_fit : pip0;
+      const double fut = (idle + rel_base[i]) - pipv;
+      bad_fut = fit_on && !le_eps(req_fit, fut);
+    }
     const double s = a + b_val;
     const bool nz = alloc != 0.0;
     const bool scored = role == ROLE_BP ? (on_task && nz && w_d != 0) : (on_task && nz);
@@ -518,6 +597,11 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     const unsigned m_over = (__ballot_sync(0xffffffffu, over) >> hs) & 0xffffu;
     const unsigned m_on = (__ballot_sync(0xffffffffu, scored) >> hs) & 0xffffu;
     const bool fit = (cs & CS_STATIC_OK) != 0 && !pod_cap && m_bad == 0;
+    bool fit_future = fit;
+    if (FUT) {  // (the ballot is evaluated by every lane: the two halves may differ in pod_cap)
+      const unsigned m_badf = (__ballot_sync(0xffffffffu, bad_fut) >> hs) & 0xffffu;
+      fit_future = (cs & CS_STATIC_OK) != 0 && !pod_cap && m_badf == 0;
+    }
     // gather the 16 lane results of this half (adding the 0.0 of an inactive lane is exact)
     double v[16];
 #pragma unroll
@@ -582,6 +666,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     }
     const bool has_order = !(ord_has_tdm && (cs & CS_TDM_ORDER_ERR));
     *score_out = total_score(c, has_order, has_order ? order : 0.0, 0, 0);
+    if (FUT) return !fit_future ? 2 : (fit ? 0 : 1);
     return fit ? 0 : 2;
   };
   // per-lane operands of eval_dirty for the group record staged in S.trec
@@ -610,28 +695,47 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     double sc = 0.0;
     int cat;
     const int rs = (int)(ev_count & 1u);  // written by warp 2 while the previous command was served
-    if (F.spec_i[rs] == i && F.spec_group[rs] == my_group) { cat = F.spec_cat[rs]; sc = F.spec_sc[rs]; n_spec_hit += 1; }
-    else cat = eval_dirty(i, i, 0, 0, fs.c_cs[i], &sc);
+    if (F.spec_i[rs] == i && F.spec_group[rs] == my_group && (!FUT || F.spec_kind[rs] == F.ev_kind)) {
+      cat = F.spec_cat[rs]; sc = F.spec_sc[rs]; n_spec_hit += 1;
+    } else cat = eval_dirty(i, i, 0, 0, fs.c_cs[i], &sc);
     __syncwarp();
     if (lane == 0) { fs.c_cat[i] = cat; fs.c_score[i] = sc; }
     double bs = F.cta_best_score;
     int bn = F.cta_best_node;
+    int bcat = FUT ? F.cta_best_cat : 0;
     int cnt = F.cta_cnt + (cat == 0 ? 1 : 0) - (old_cat == 0 ? 1 : 0);
+    int cnt1 = FUT ? F.cta_cnt1 + (cat == 1 ? 1 : 0) - (old_cat == 1 ? 1 : 0) : 0;
     bool rescan = false;
-    if (bn == dn) {
-      if (cat == 0 && sc >= bs) bs = sc;
-      else rescan = true;
-    } else if (cat == 0 && (bn < 0 || better(sc, dn, bs, bn))) {
-      bs = sc; bn = dn;
+    if (!FUT) {
+      if (bn == dn) {
+        if (cat == 0 && sc >= bs) bs = sc;
+        else rescan = true;
+      } else if (cat == 0 && (bn < 0 || better(sc, dn, bs, bn))) {
+        bs = sc; bn = dn;
+      }
+    } else {
+      if (bn == dn) {
+        if (cat == bcat && sc >= bs) bs = sc;
+        else rescan = true;
+      } else if (cat != 2 && (bn < 0 || better_c(cat, sc, dn, bcat, bs, bn))) {
+        bs = sc; bn = dn; bcat = cat;
+      }
     }
     __syncwarp();
     n_eval += 1;
-    if (rescan) { n_rescan += 1; Best r = scan_cache(fs, nmine, nbase); bs = r.score; bn = r.node; cnt = r.cnt; }
+    if (rescan) {
+      n_rescan += 1;
+      int c01[2] = {0, 0};
+      Best r = scan_cache<FUT>(fs, nmine, nbase, c01);
+      bs = r.score; bn = r.node; bcat = r.cat;
+      if (FUT) { cnt = c01[0]; cnt1 = c01[1]; } else cnt = r.cnt;
+    }
     if (lane == 0) {
       F.cta_best_score = bs; F.cta_best_node = bn; F.cta_cnt = cnt;
-      Best nb{bs, bn, cnt};
+      if (FUT) { F.cta_best_cat = bcat; F.cta_cnt1 = cnt1; }
+      Best nb{bs, bn, (FUT && bcat == 1) ? cnt1 : cnt, bcat};
       store_all(p, p.peer_ring, p.ring, (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, 1));
-      F.ev_score = bs; F.ev_node = bn; F.ev_cnt = min(cnt, 2); F.run_m = 1;
+      F.ev_score = bs; F.ev_node = bn; F.ev_cnt = min(nb.cnt, 2); F.ev_cat = bcat; F.run_m = 1;
     }
     __syncwarp();
     asm volatile("bar.arrive 1, 64;" ::: "memory");  // results ready: warp 0 joins with bar.sync 1, 64
@@ -643,10 +747,11 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     const long long t0 = PROF ? clock64() : 0;
     const int i = F.ev_i;
     double sc = 0.0;
-    const int cat = eval_dirty(i, i, 1, 1, fs.c_cs[i], &sc);
+    const int kind = FUT ? F.ev_kind : 0;  // one more placement of the kind the row just received
+    const int cat = eval_dirty(i, i, 1, 1, fs.c_cs[i], &sc, kind);
     const int ws = (int)((ev_count + 1u) & 1u);
     __syncwarp();
-    if (lane == 0) { F.spec_sc[ws] = sc; F.spec_cat[ws] = cat; F.spec_group[ws] = my_group; F.spec_i[ws] = i; }
+    if (lane == 0) { F.spec_sc[ws] = sc; F.spec_cat[ws] = cat; F.spec_group[ws] = my_group; F.spec_i[ws] = i; F.spec_kind[ws] = kind; }
     if (PROF) ev_acc_spec += clock64() - t0;
   };
 
@@ -654,19 +759,29 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   // F.ev_i, and the best of every other CTA's slot. Neither changes while placements keep landing on F.ev_i.
   auto run_runner_up = [&]() {
     const int i = F.ev_i;
-    Best rl{0.0, -1, 0};
-    for (int k = lane; k < nmine; k += 32)
-      if (k != i && fs.c_cat[k] == 0) best_fold(rl, fs.c_score[k], nbase + k, 1);
-    best_warp_reduce(rl);
-    Best ro{0.0, -1, 0};
+    Best rl{0.0, -1, 0, 0};
+    int n0 = 0, n1 = 0;
+    for (int k = lane; k < nmine; k += 32) {
+      const int cc = fs.c_cat[k];
+      if (k == i) continue;
+      if (cc == 0 || (FUT && cc == 1)) best_fold(rl, fs.c_score[k], nbase + k, 1, cc);
+      if (FUT) { n0 += cc == 0; n1 += cc == 1; }
+    }
+    best_warp_reduce<FUT>(rl);
+    if (FUT) {
+      n0 = (int)__reduce_add_sync(0xffffffffu, (unsigned)n0);
+      n1 = (int)__reduce_add_sync(0xffffffffu, (unsigned)n1);
+    }
+    Best ro{0.0, -1, 0, 0};
     for (int sl = lane; sl < G; sl += 32)
-      if (sl != cta) best_fold(ro, fs.sl_score[sl], fs.sl_node[sl], 0);
-    best_warp_reduce(ro);
+      if (sl != cta) best_fold(ro, fs.sl_score[sl], fs.sl_node[sl], 0, FUT ? fs.sl_cat[sl] : 0);
+    best_warp_reduce<FUT>(ro);
     if (lane == 0) {
-      F.rl_score = rl.score; F.rl_node = rl.node; F.rl_cnt = rl.cnt;
+      F.rl_score = rl.score; F.rl_node = rl.node; F.rl_cnt = rl.cnt; F.rl_cat = rl.cat;
+      if (FUT) { F.rl_cnt0 = n0; F.rl_cnt1 = n1; }
       Best ru = rl;
-      best_fold(ru, ro.score, ro.node, 0);
-      F.ru_score = ru.score; F.ru_node = ru.node;
+      best_fold(ru, ro.score, ro.node, 0, ro.cat);
+      F.ru_score = ru.score; F.ru_node = ru.node; F.ru_cat = ru.cat;
     }
     __syncwarp();
   };
@@ -681,12 +796,13 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     if (nwarps == 8) e = warp == 1 ? 0 : warp == 3 ? 1 : warp == 6 ? 2 : warp == 4 ? 3 : warp == 5 ? 4 : warp == 7 ? 5 : 6;
     else if (warp == 2) e = nwarps - 2;
     else if (warp > 2) e = warp - 2;
-    if (warp == 2) run_runner_up();
+    if (warp == 2) { run_runner_up(); DBG_STAGE(warp, 150); }
     if (2 * e < L) {
       double sc = 0.0;
       const int cat = eval_dirty(F.ev_i, F.ev_i, 2 * e, 2 * e + 1, fs.c_cs[F.ev_i], &sc);
       if (hl == 0) { F.run_sc[2 * e + half] = sc; F.run_cat[2 * e + half] = cat; }
     }
+    DBG_STAGE(warp, 180);
     asm volatile("bar.sync 2, %0;" ::"r"((nwarps - 1) * 32) : "memory");  // all worker warps
   };
   // CMD_RUN (warp 1): lane l evaluates node F.ev_i as it will be after l further placements of the staged group
@@ -707,7 +823,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     const double ru_s = F.ru_score;
     const int ru_n = F.ru_node;
     // lane l < L-1: does the node still win in state l (i.e. does placement l+1 of the run land on it too)?
-    const bool win = lane < L - 1 && cat == 0 && (ru_n < 0 || better(sc, dn, ru_s, ru_n));
+    // (runs are made of allocations: the row must stay in the idle gradient, which beats any future-idle runner-up)
+    const bool win = lane < L - 1 && cat == 0 && (ru_n < 0 || (FUT && F.ru_cat == 1) || better(sc, dn, ru_s, ru_n));
     const unsigned wmask = __ballot_sync(0xffffffffu, win);
     const int m = min(L, __ffs(~wmask));  // 1 + leading wins; state m-1 is the row after the run
     const double sc_m = __shfl_sync(0xffffffffu, sc, m - 1);
@@ -733,11 +850,14 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     __syncwarp();
     if (lane == 0) {
       fs.c_cat[i] = cat_m; fs.c_score[i] = sc_m;
-      Best nb{F.rl_score, F.rl_node, F.rl_cnt};
-      if (cat_m == 0) best_fold(nb, sc_m, dn, 1);
-      F.cta_best_score = nb.score; F.cta_best_node = nb.node; F.cta_cnt = nb.cnt;
+      Best nb{F.rl_score, F.rl_node, F.rl_cnt, FUT ? F.rl_cat : 0};
+      if (cat_m == 0 || (FUT && cat_m == 1)) best_fold(nb, sc_m, dn, 1, cat_m);
+      F.cta_best_score = nb.score; F.cta_best_node = nb.node;
+      if (FUT) {
+        F.cta_cnt = F.rl_cnt0 + (cat_m == 0 ? 1 : 0); F.cta_cnt1 = F.rl_cnt1 + (cat_m == 1 ? 1 : 0); F.cta_best_cat = nb.cat;
+      } else F.cta_cnt = nb.cnt;
       store_all(p, p.peer_ring, p.ring, (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, m));
-      F.ev_score = nb.score; F.ev_node = nb.node; F.ev_cnt = min(nb.cnt, 2); F.run_m = m;
+      F.ev_score = nb.score; F.ev_node = nb.node; F.ev_cnt = min(nb.cnt, 2); F.ev_cat = nb.cat; F.run_m = m;
       F.spec_i[0] = -1; F.spec_i[1] = -1;  // whatever was computed ahead describes an older state of the row
     }
     (void)old_cat;
@@ -767,15 +887,19 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       else if (cmd == CMD_DISCARD) discard_part();
       else if (cmd == CMD_RUN) {  // all worker warps, joined on named barrier 2; warp 1 signals warp 0 on barrier 1
         if (F.cur_group != my_group) { stage_ops(); my_group = F.cur_group; }
+        DBG_STAGE(warp, 100 + F.run_L);
         run_states();
-        if (warp == 1) run_eval_and_publish();
+        DBG_STAGE(warp, 200 + F.run_L);
+        if (warp == 1) { run_eval_and_publish(); DBG_STAGE(1, 300 + F.run_m); }
         continue;
       }
       else if (cmd == CMD_EVAL) {  // no block-wide B2: warp 1 signals warp 0 on named barrier 1
         if (warp == 1 || warp == 2) {
           if (F.cur_group != my_group) { stage_ops(); my_group = F.cur_group; }
+          DBG_STAGE(warp, 400);
           if (warp == 1) eval_and_publish(my_group);
           else run_ahead(my_group);
+          DBG_STAGE(warp, 500);
           ev_count += 1;
         }
         continue;
@@ -798,6 +922,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     int n_dec = 0, n_vis = 0, n_fit = 0, n_steps = 0, n_full = 0, n_incr = 0, visit_id = 0, n_owner_change = 0, last_owner = -1;
     double g_best_score = 0.0;
     int g_best_node = -1, g_cnt = 0, g_best_owner = -1;
+    int g_best_cat = 0, g_cnt1 = 0;  // FUT: g_cnt / g_cnt1 = candidates of category 0 / 1 over all CTAs (each clamped to 2 per CTA)
     bool pub_pending = false;
     long long t_a = 0, t_b = 0, t_c = 0, acc_ab = 0, acc_bc = 0, acc_cp = 0, acc_ja = 0;
     long long t_post = 0, t_join = 0, acc_post_to_joinstart = 0, acc_join_wait = 0, acc_join_to_post = 0; int acc_n = 0;
@@ -1015,8 +1140,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         Best nb;
         if (o == cta) {
           const long long t0_ = PROF ? clock64() : 0;
+          DBG_STAGE(0, (int)(pub_pc << 4) | 4);
           asm volatile("bar.sync 1, 64;" ::: "memory");  // join the evaluator warp
-          nb.score = F.ev_score; nb.node = F.ev_node; nb.cnt = F.ev_cnt; pub_m = F.run_m;
+          DBG_STAGE(0, (int)(pub_pc << 4) | 5);
+          nb.score = F.ev_score; nb.node = F.ev_node; nb.cnt = F.ev_cnt; nb.cat = FUT ? F.ev_cat : 0; pub_m = F.run_m;
           if (PROF) {
             // the barrier blocks lazily: read the clock only after a value that needs it has arrived
             long long tj;
@@ -1030,32 +1157,54 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           const uint4 *ent = p.ring + (size_t)(pub_pc % RING_DEPTH) * RING_STRIDE;
           uint4 v;
           unsigned spins = 0;
-          const long long t0w = p.n_ranks > 1 ? clock64() : 0;
+          const long long t0w = clock64();
+#undef WD_EXTRA
+#define WD_EXTRA do { if (PROF && p.dbg && lane == 0) { volatile int *dd = p.dbg + (size_t)(o - p.cta_base) * 8; \
+            printf("  waits for pub %u of CTA %d (node %d, ring word %08x); owner stages: ctl %d:%d w1-7 %d %d %d %d %d %d %d\n", pub_pc, o, pub_node, v.w, \
+                   dd[0] >> 4, dd[0] & 15, dd[1], dd[2], dd[3], dd[4], dd[5], dd[6], dd[7]); } } while (0)
           do { v = mbox_load(ent); PEER_WATCHDOG(spins, t0w); } while ((v.w >> 10) != tag);
+#undef WD_EXTRA
+#define WD_EXTRA
           nb = unpack_best(v);
-          pub_m = (int)((v.w >> 2) & 0xffu);
+          pub_m = (int)((v.w >> 3) & 0x7fu);
         }
         const int old_cnt = fs.sl_cnt[o];
-        g_cnt += nb.cnt - old_cnt;
         bool refold = false;
-        if (g_best_owner == o) {
-          if (nb.node >= 0 && (better(nb.score, nb.node, g_best_score, g_best_node) ||
-                               (nb.node == g_best_node && nb.score == g_best_score))) {
-            g_best_score = nb.score; g_best_node = nb.node;
-          } else {
-            refold = true;
+        if (!FUT) {
+          g_cnt += nb.cnt - old_cnt;
+          if (g_best_owner == o) {
+            if (nb.node >= 0 && (better(nb.score, nb.node, g_best_score, g_best_node) ||
+                                 (nb.node == g_best_node && nb.score == g_best_score))) {
+              g_best_score = nb.score; g_best_node = nb.node;
+            } else {
+              refold = true;
+            }
+          } else if (nb.node >= 0 && (g_best_node < 0 || better(nb.score, nb.node, g_best_score, g_best_node))) {
+            g_best_score = nb.score; g_best_node = nb.node; g_best_owner = o;
           }
-        } else if (nb.node >= 0 && (g_best_node < 0 || better(nb.score, nb.node, g_best_score, g_best_node))) {
-          g_best_score = nb.score; g_best_node = nb.node; g_best_owner = o;
+        } else {
+          if (fs.sl_cat[o] == 0) g_cnt -= old_cnt; else g_cnt1 -= old_cnt;
+          if (nb.cat == 0) g_cnt += nb.cnt; else g_cnt1 += nb.cnt;
+          if (g_best_owner == o) {
+            if (nb.node >= 0 && (better_c(nb.cat, nb.score, nb.node, g_best_cat, g_best_score, g_best_node) ||
+                                 (nb.node == g_best_node && nb.score == g_best_score && nb.cat == g_best_cat))) {
+              g_best_score = nb.score; g_best_node = nb.node; g_best_cat = nb.cat;
+            } else {
+              refold = true;
+            }
+          } else if (nb.node >= 0 && (g_best_node < 0 || better_c(nb.cat, nb.score, nb.node, g_best_cat, g_best_score, g_best_node))) {
+            g_best_score = nb.score; g_best_node = nb.node; g_best_cat = nb.cat; g_best_owner = o;
+          }
         }
         __syncwarp();
-        if (lane == 0) { fs.sl_score[o] = nb.score; fs.sl_node[o] = nb.node; fs.sl_cnt[o] = nb.cnt; }
+        if (lane == 0) { fs.sl_score[o] = nb.score; fs.sl_node[o] = nb.node; fs.sl_cnt[o] = nb.cnt; fs.sl_cat[o] = nb.cat; }
         __syncwarp();
         since_sync += 1;
         if (refold) {
           __syncwarp();
-          Best g = fold_slots(fs, G, &g_best_owner);
-          g_best_score = g.score; g_best_node = g.node; g_cnt = g.cnt;
+          Best g = fold_slots<FUT>(fs, G, &g_best_owner);
+          g_best_score = g.score; g_best_node = g.node; g_best_cat = g.cat;
+          if (!FUT) g_cnt = g.cnt;  // (FUT: the per-category totals were updated above)
         }
       };
 
@@ -1117,7 +1266,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         if (pure && grp == cache_group) {
           // -------- incremental step: verdict cache, slot table and global best are already current --------
           if (since_sync >= RING_DEPTH / 2) {  // keep the publication ring from being overrun
-            Best mine{F.cta_best_score, F.cta_best_node, F.cta_cnt};
+            Best mine{F.cta_best_score, F.cta_best_node, (FUT && F.cta_best_cat == 1) ? F.cta_cnt1 : F.cta_cnt, FUT ? F.cta_best_cat : 0};
             __syncwarp();
             exchange_all_fast(p, mine, ag, fs);
             ag += 1; since_sync = 0;
@@ -1131,21 +1280,43 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           sweep_part();
           __syncthreads();  // B2
           FPROF_MARK(2);
-          Best mine{0.0, -1, 0};
-          if (lane < nwarps) best_fold(mine, S.w_score[0][lane], S.w_node[0][lane], S.w_cnt[0][lane]);
-          best_warp_reduce(mine);
+          Best mine{0.0, -1, 0, 0};
+          int c0 = 0, c1 = 0;
+          if (!FUT) {
+            if (lane < nwarps) best_fold(mine, S.w_score[0][lane], S.w_node[0][lane], S.w_cnt[0][lane]);
+            best_warp_reduce(mine);
+          } else {  // per warp: best (score, node, category) + how many of its nodes sit in category 0 / 1
+            if (lane < nwarps) {
+              best_fold(mine, S.w_score[0][lane], S.w_node[0][lane], 0, S.w_node[1][lane]);
+              c0 = S.w_cnt[0][lane]; c1 = S.w_cnt[1][lane];
+            }
+            best_warp_reduce<true>(mine);
+            c0 = (int)__reduce_add_sync(0xffffffffu, (unsigned)c0);
+            c1 = (int)__reduce_add_sync(0xffffffffu, (unsigned)c1);
+            mine.cnt = mine.node < 0 ? 0 : (mine.cat == 0 ? c0 : c1);
+          }
           exchange_all_fast(p, mine, ag, fs);
-          Best g = fold_slots(fs, G, &g_best_owner);
+          Best g = fold_slots<FUT>(fs, G, &g_best_owner);
           ag += 1; since_sync = 0; n_full += 1;
           cache_group = pure ? grp : -1;  // verdicts taken under an error cache are not reusable
-          if (lane == 0) { F.cta_best_score = mine.score; F.cta_best_node = mine.node; F.cta_cnt = mine.cnt; }
-          g_best_score = g.score; g_best_node = g.node; g_cnt = g.cnt;
+          if (lane == 0) {
+            F.cta_best_score = mine.score; F.cta_best_node = mine.node;
+            if (FUT) { F.cta_cnt = c0; F.cta_cnt1 = c1; F.cta_best_cat = mine.cat; } else F.cta_cnt = mine.cnt;
+          }
+          g_best_score = g.score; g_best_node = g.node; g_best_cat = g.cat;
+          if (!FUT) g_cnt = g.cnt;
+          else {  // per-category totals over the slot table
+            int t0 = 0, t1 = 0;
+            for (int sl = lane; sl < G; sl += 32) { if (fs.sl_cat[sl] == 0) t0 += fs.sl_cnt[sl]; else t1 += fs.sl_cnt[sl]; }
+            g_cnt = (int)__reduce_add_sync(0xffffffffu, (unsigned)t0);
+            g_cnt1 = (int)__reduce_add_sync(0xffffffffu, (unsigned)t1);
+          }
         }
         n_steps += 1;
         FPROF_MARK(3);
         if (PROF) t_c = clock64();
 
-        if (g_cnt == 0) {  // no feasible node, allocate.go:639-659
+        if ((FUT ? g_cnt + g_cnt1 : g_cnt) == 0) {  // no feasible node, allocate.go:639-659
           __syncwarp();
           if (lane == 0) { if (out_cta) p.fit_errors[n_fit] = t; S.r_failed[rl] = 1; }
           n_fit += 1;
@@ -1171,13 +1342,20 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           break;
         }
         const int best = g_best_node;
-        const double score = g_cnt == 1 ? 0.0 : g_best_score;
-        // ---- Statement.Allocate: node.AddTask on the owner CTA (api/node_info.go:435-484) ----
+        // gradient choice (allocate.go:750-776): idle candidates if there are any, else the future-idle ones -> pipeline
+        const bool pipe = FUT && g_best_cat == 1;
+        const int cnt_sel = pipe ? g_cnt1 : g_cnt;
+        const double score = cnt_sel == 1 ? 0.0 : g_best_score;
+        // ---- Statement.Allocate / Pipeline: node.AddTask on the owner CTA (api/node_info.go:435-484) ----
         if (best >= nbase && best < nbase + nmine) {
           const int i = best - nbase;
           if (lane < R) {
-            fs.idle[lane * cap + i] -= req_l;
-            fs.used[lane * cap + i] += req_l;
+            if (pipe) {
+              fs.pip[lane * cap + i] += req_l;
+            } else {
+              fs.idle[lane * cap + i] -= req_l;
+              fs.used[lane * cap + i] += req_l;
+            }
           }
           if (c.has_predicates) {  // predicates AllocateFunc, predicates.go:212-256
             if (lane == 16) fs.pod_count[i] += 1;
@@ -1193,7 +1371,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         //      Allocatable gate, and come before ssn.JobReady turns true (the loop breaks there, allocate.go:676) ----
         int run_L = 1;
         bool vrun = false;  // the run's placements are one visit each (a Ready job gets one task per visit, allocate.go:676)
-        if (pub_pending && fp.run_max > 1) {
+        if (pub_pending && fp.run_max > 1 && !pipe) {
           // placements (this one included) until ssn.JobReady turns true; <= 0: the job is Ready already
           int need = 0;
           if (f_gang_ready) {
@@ -1257,26 +1435,29 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             if (lane == 0) {
               F.ev_i = best - nbase; F.ev_ring = (int)(pub_pc % RING_DEPTH); F.ev_tag = (pub_pc + 1u) & RUN_TAG_MASK;
               F.run_L = run_L; F.run_att0 = att0;
+              if (FUT) F.ev_kind = pipe ? 1 : 0;
               S.cmd = run_L > 1 ? CMD_RUN : CMD_EVAL;
             }
+            DBG_STAGE(0, (int)(pub_pc << 4) | (run_L > 1 ? 1 : 2));
             __syncthreads();  // B1 of CMD_EVAL
+            DBG_STAGE(0, (int)(pub_pc << 4) | 3);
             if (PROF) t_post = clock64();
             if (PROF && t_join != 0) { acc_join_to_post += t_post - t_join; acc_ja += t_a - t_join; acc_ab += t_b - t_a; acc_bc += t_c - t_b; acc_cp += t_post - t_c; }
           }
         }
         // job.UpdateTaskStatus + event handlers: drf (drf.go:391-418), proportion (proportion.go:475-497)
-        ready += 1;
+        if (pipe) waiting += 1; else ready += 1;
         if (lane == 0) {
           S.r_pending[rl] -= 1;
-          S.r_occ[rl] += 1;
-          ops[n_ops * 3 + 0] = t; ops[n_ops * 3 + 1] = best; ops[n_ops * 3 + 2] = VC_OP_ALLOCATE;
+          if (pipe) S.r_pip[rl] += 1; else S.r_occ[rl] += 1;
+          ops[n_ops * 3 + 0] = t; ops[n_ops * 3 + 1] = best; ops[n_ops * 3 + 2] = pipe ? VC_OP_PIPELINE : VC_OP_ALLOCATE;
           ops_score[n_ops] = score;
         }
         n_ops += 1;
         n_att += 1;
         int extra = 0;  // further placements of a run on the same node (same group, same role), announced by its publication
         if (run_L > 1) {
-          const int cnt_run = g_cnt;  // candidates at every placement of the run (only the winner's row changes)
+          const int cnt_run = cnt_sel;  // candidates at every placement of the run (only the winner's row changes)
           resolve();
           extra = pub_m - 1;
           if (extra > 0) {
@@ -1341,8 +1522,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         for (int k = n_ops - 1; k >= 0; --k) {  // unallocate + DeallocateFunc handlers, reverse order
           const int ot = ops[k * 3 + 0];
           const int orl = p.t_role[ot] - role_base;
-          if (lane == 0) { S.r_pending[orl] += 1; S.r_occ[orl] -= 1; }
-          ready -= 1;
+          const bool was_pipe = FUT && ops[k * 3 + 2] == VC_OP_PIPELINE;
+          if (lane == 0) { S.r_pending[orl] += 1; if (was_pipe) S.r_pip[orl] -= 1; else S.r_occ[orl] -= 1; }
+          if (was_pipe) waiting -= 1; else ready -= 1;
           const double orq = lane < R ? p.req[(size_t)lane * T + ot] : 0.0;
           if (c.has_drf) jalloc_l -= orq;
           if (c.has_proportion && (qflags2 & 1u)) {
@@ -1457,6 +1639,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     for (int d = 0; d < R; ++d) {
       p.idle[(size_t)d * N + n] = fs.idle[d * cap + i];
       p.used[(size_t)d * N + n] = fs.used[d * cap + i];
+      if (FUT) p.pip[(size_t)d * N + n] = fs.pip[d * cap + i];
     }
     for (int k = 0; k < K; ++k) p.kreq[(size_t)k * N + n] = fs.kreq[k * cap + i];
     for (int k = 0; k < 2; ++k) p.knz[(size_t)k * N + n] = fs.knz[k * cap + i];

@@ -323,6 +323,23 @@ inline bool runs_exact(size_t D, size_t N, size_t T, std::initializer_list<const
   }
   return true;
 }
+// FutureIdle = (Idle + Releasing) - Pipelined along a run: every intermediate value stays an exactly representable
+// integer when, per node and dimension, |Idle| + |Releasing| + |Pipelined| + 32 * max|req_d| < 2^53
+inline bool future_rows_exact(size_t D, size_t N, size_t T, const double *idle, const double *rel, const double *pip,
+                              const double *req) {
+  if (!rel && !pip) return true;
+  for (size_t d = 0; d < D; ++d) {
+    double mreq = 0.0, mrel = 0.0, msum = 0.0;
+    if (!max_abs_integral(req ? req + d * T : nullptr, T, mreq)) return false;
+    if (!max_abs_integral(rel ? rel + d * N : nullptr, N, mrel) || !max_abs_integral(pip ? pip + d * N : nullptr, N, mrel)) return false;
+    for (size_t n = 0; n < N; ++n) {
+      const double a = std::fabs(idle[d * N + n]) + (rel ? std::fabs(rel[d * N + n]) : 0.0) + (pip ? std::fabs(pip[d * N + n]) : 0.0);
+      if (a > msum) msum = a;
+    }
+    if (!(msum + 32.0 * mreq < 9.0e15)) return false;
+  }
+  return true;
+}
 // rank of every object in (CreationTimestamp, UID) order: the fallback of ssn.JobOrderFn / QueueOrderFn
 inline void rank_by(const int64_t *ts, const uint32_t *uid, size_t n, std::vector<uint32_t> &rank) {
   std::vector<int> idx(n);

@@ -69,6 +69,7 @@ struct Tunables {
   int commit_threads = 0;   // VC_COMMIT_THREADS: minimum block size
   int commit_generic = 0;   // VC_COMMIT_GENERIC: always the general commit kernel (k_commit)
   int commit_norun = 0;     // VC_COMMIT_NORUN: the incremental kernel without run-length placement batches
+  int watchdog_ms = 0;      // VC_WATCHDOG_MS: exchange polls of the incremental kernel give up after this long (0 = 10 s)
   int run_max = 0;          // VC_RUN_MAX: placements per publication (0 = default: two node states per worker warp, 14)
   int prof = 0;             // VC_PROF: instrumented kernel instances (phase timers)
   int prof_owner = 0;       // VC_PROF_OWNER: owner-path statistics on stderr
@@ -84,7 +85,7 @@ struct TunName { const char *name; int Tunables::*field; };
 const TunName kTunNames[] = {
     {"VC_COMMIT_CTAS", &Tunables::commit_ctas}, {"VC_COMMIT_THREADS", &Tunables::commit_threads},
     {"VC_COMMIT_GENERIC", &Tunables::commit_generic}, {"VC_COMMIT_NORUN", &Tunables::commit_norun},
-    {"VC_RUN_MAX", &Tunables::run_max},
+    {"VC_RUN_MAX", &Tunables::run_max}, {"VC_WATCHDOG_MS", &Tunables::watchdog_ms},
     {"VC_PROF", &Tunables::prof}, {"VC_PROF_OWNER", &Tunables::prof_owner}, {"VC_PROF_WAIT", &Tunables::prof_wait},
     {"VC_PROF_UPLOAD", &Tunables::prof_upload}, {"VC_BACKFILL_DEPTH1", &Tunables::backfill_depth1},
     {"VC_EXPAND_ROWS", &Tunables::expand_rows}, {"VC_EXPAND_PLAIN", &Tunables::expand_plain},
@@ -246,6 +247,7 @@ struct vc_snapshot {
   std::vector<vc_decision> last_dec;  // operations of the last vc_allocate_run (kept visits only)
   bool alloc_ran = false, bf_ran = false;
   int last_idx_cur = 0;   // util.lastProcessedNodeIndex as the last action of the cycle left it
+  int *d_dbg = nullptr;
   bool rows_integral = false;  // every quantity a placement adds to / subtracts from a node row is integer-valued
   void *d_bf = nullptr;   // device slab of the backfill inputs / outputs
   size_t d_bf_bytes = 0;
@@ -369,12 +371,13 @@ void choose_geometry(vc_snapshot *s) {
   s->block = block;
   const int R = s->dims.n_dims, K = s->dims.n_kdims;
   // hypernode-level scores change for every node after every placement: per-step full sweeps (k_commit)
-  s->fast = !s->dc.has_future && !s->dc.soft_active && !s->dc.nta_on && s->dc.to_find == 0 && R <= 8 && K <= VC_MAX_KDIMS && !g_tun.commit_generic;
+  // (Releasing / Pipelined resources alone keep the incremental kernel: its FUT instance)
+  s->fast = !s->topo_any && !s->dc.soft_active && !s->dc.nta_on && s->dc.to_find == 0 && R <= 8 && K <= VC_MAX_KDIMS && !g_tun.commit_generic;
   if (s->fast) {
     if (g_tun.commit_threads <= 0) s->block = 256;  // 7 worker warps: a run's node states are evaluated two per warp
-    size_t rows = 3 * (size_t)R + 2 * (size_t)K + 2 + 1;
+    size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2 + 1;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + ((sizeof(CtlFast) + 15) & ~(size_t)15) + rows * npc * 8 +
-                    (size_t)npc * (8 + 4 * 5) + (size_t)s->n_cta_total * (8 + 4 + 4) + 64;
+                    (size_t)npc * (8 + 4 * 5) + (size_t)s->n_cta_total * (8 + 4 + 4 + 4) + 64;
     const size_t heap_bytes = (size_t)s->heap_total * sizeof(HeapKey);
     s->heap_in_smem = (heap_bytes <= 96 * 1024 && s->smem_bytes + heap_bytes <= 200 * 1024) ? 1 : 0;
     if (s->heap_in_smem) s->smem_bytes += heap_bytes + 16;
@@ -1176,6 +1179,7 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   // rows and every request, m placements leave exactly row -/+ m * request: the commit kernel may cover a run of
   // placements on one node with one publication and k_backfill may run ahead m steps
   s->rows_integral = vch::runs_exact(R, N, T, {nd->idle, nd->used}, {tk->resreq}) &&
+                     vch::future_rows_exact(R, N, T, nd->idle, nd->releasing, nd->pipelined, tk->resreq) &&
                      vch::runs_exact(K, N, T, {nd->k8s_requested}, {tk->k8s_req}) &&
                      vch::runs_exact(2, N, T, {nd->k8s_nonzero_requested}, {tk->k8s_nonzero_req});
   tick("integrality scan");
@@ -1269,6 +1273,7 @@ int vc_snapshot_update_nodes(vc_snapshot *s, int32_t n_dirty, const int32_t *nod
   if (s->rows_integral) {
     double mx = 0.0;
     s->rows_integral = vch::max_abs_integral(rows->idle, R * m, mx) && vch::max_abs_integral(rows->used, R * m, mx) &&
+                       vch::max_abs_integral(rows->releasing, R * m, mx) && vch::max_abs_integral(rows->pipelined, R * m, mx) &&
                        vch::max_abs_integral(rows->k8s_requested, K * m, mx) &&
                        vch::max_abs_integral(rows->k8s_nonzero_requested, 2 * m, mx) && mx < 8.0e15;
   }
@@ -1414,6 +1419,13 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   std::memset(&p, 0, sizeof p);
   p.d = s->dd; p.c = s->dc; p.npc = s->npc; p.n_cta = s->world > 1 ? s->n_cta_total : G; p.max_job_tasks = s->max_job_tasks;
   p.n_ranks = s->world; p.cta_base = s->rank * G;
+  p.wd_cycles = (long long)(g_tun.watchdog_ms > 0 ? g_tun.watchdog_ms : 10000) * 2000000ll;  // ~2 GHz SM clock
+  p.dbg = nullptr;
+  if (g_tun.watchdog_ms > 0 && g_tun.prof) {  // diagnostics (VC_PROF=1 VC_WATCHDOG_MS=n): per-CTA progress words the watchdog prints
+    if (!s->d_dbg) CUDA_TRY(cudaMalloc(&s->d_dbg, 4096 * 32));
+    CUDA_TRY(cudaMemsetAsync(s->d_dbg, 0, 4096 * 32, s->stream));
+    p.dbg = s->d_dbg;
+  }
   p.alloc = s->n_alloc.d(s->in); p.rel = s->n_rel.d(s->in); p.kalloc = s->n_kalloc.d(s->in);
   p.idle = s->w_idle; p.used = s->w_used; p.pip = s->w_pip; p.kreq = s->w_kreq; p.knz = s->w_knz;
   p.max_tasks = s->n_max_tasks.d(s->in); p.pod_count = s->w_pod_count; p.cstat = s->cstat;
@@ -1464,7 +1476,8 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
     CUDA_TRY(cudaMemsetAsync(d_wait, 0, 1024 * 8, s->stream));
   }
   p.cta_wait = d_wait;
-  const void *kfn = s->fast ? (g_tun.prof ? (const void *)k_commit_fast<true> : (const void *)k_commit_fast<false>)
+  const void *kfn = s->fast ? (s->dc.has_future ? (g_tun.prof ? (const void *)k_commit_fast<true, true> : (const void *)k_commit_fast<false, true>)
+                                                : (g_tun.prof ? (const void *)k_commit_fast<true, false> : (const void *)k_commit_fast<false, false>))
                   : s->dc.to_find > 0 ? (s->topo_any ? (const void *)k_commit<true, true, true, true> : (const void *)k_commit<true, true, false, true>)
                   : s->topo_any ? (const void *)k_commit<true, true, true> : s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
                                      : (s->dc.soft_active ? (const void *)k_commit<false, true> : (const void *)k_commit<false, false>);
@@ -1578,6 +1591,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->stats.kernel_launches = 2;  // k_class_static + k_commit
   r->stats.n_steps = s->h_counters[3];
   r->stats.last_processed_node_index = s->dc.to_find > 0 ? s->h_counters[4] : s->dc.last_idx0;
+  r->stats.commit_kernel = s->fast ? VC_KERNEL_INCREMENTAL : VC_KERNEL_GENERAL;
   s->last_idx_cur = r->stats.last_processed_node_index;
   for (int k = 0; k < 8; ++k) r->stats.prof_cycles[k] = s->h_prof[k];
   r->stats.prof_cycles[6] = s->h_counters[5];  // full sweeps (fast kernel)

@@ -49,6 +49,14 @@ CONFIGS = {
     "cfg1": SynthConfig("cfg1", 128, 1024, 1, "gang+predicates+binpack"),
     # configs[1]: the headline single-GPU workload
     "cfg2": SynthConfig("cfg2", 10_000, 100_000, 1, "priority+gang+predicates+nodeorder+binpack"),
+    # cfg2 with terminating pods on 30 % of the nodes (Releasing resources: the FutureIdle gradient exists, most placements
+    # still land on idle resources) and a nearly full cluster where many tasks can only be pipelined
+    "cfg2_fut": SynthConfig("cfg2_fut", 10_000, 100_000, 1, "priority+gang+predicates+nodeorder+binpack", releasing_frac=0.3),
+    "cfg2_fut_tight": SynthConfig("cfg2_fut_tight", 10_000, 100_000, 1, "priority+gang+predicates+nodeorder+binpack",
+                                  utilisation=0.97, min_util=0.8, releasing_frac=0.5),
+    "mid_fut": SynthConfig("mid_fut", 2_000, 20_000, 1, "priority+gang+predicates+nodeorder+binpack", releasing_frac=0.3),
+    "cfg3_fut": SynthConfig("cfg3_fut", 10_000, 100_000, 16, "priority+gang+drf+predicates+proportion+nodeorder+binpack",
+                            utilisation=0.9, min_util=0.5, releasing_frac=0.4),
     # configs[2]: + DRF + proportion over 16 queues
     "cfg3": SynthConfig("cfg3", 10_000, 100_000, 16, "priority+gang+drf+predicates+proportion+nodeorder+binpack"),
     # configs[3]: 3-tier HyperNode tree (root -> 32 -> 40 each -> ~39 nodes), network-topology-aware weight 10
