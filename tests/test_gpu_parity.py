@@ -381,7 +381,7 @@ def _host_threads():
 
 
 FULL_SIZE = [("cfg2", "fast"), ("cfg2", "fast_norun"), ("cfg2", "generic"), ("cfg2", "sampling"), ("cfg3", "fast"), ("cfg3", "generic"),
-             ("cfg2_fut", "fast"), ("cfg2_fut_tight", "fast"), ("cfg3_fut", "fast")]
+             ("cfg2_fut", "fast"), ("cfg2_fut_tight", "fast"), ("cfg3_fut", "fast"), ("cfg2_soft", "fast"), ("cfg2_fut_soft", "fast")]
 
 
 @pytest.mark.parametrize("cfg,mode", FULL_SIZE, ids=[f"{c}-{m}" for c, m in FULL_SIZE])
@@ -406,8 +406,9 @@ def test_full_size_vs_oracle(cfg, mode, gpu, oracle_engine):
         gpu.debug_option("VC_COMMIT_NORUN", 0)
     ref = oracle_engine(snap, threads=threads)
     assert len(ref.decisions) > 90_000 or mode == "sampling" or "fut" in cfg
-    if "fut" in cfg:  # Releasing resources: the incremental kernel's FUT instance, pipelines included
+    if "fut" in cfg or "soft" in cfg:  # Releasing resources / PreferNoSchedule taints: the incremental kernel's FUT / SOFT instances
         assert res.stats["commit_kernel"] == 1, res.stats  # VC_KERNEL_INCREMENTAL
+    if "fut" in cfg:
         assert (ref.decisions["kind"] == 1).sum() > (1000 if "tight" in cfg else 0)
     _assert_same(res, ref)
     assert np.array_equal(res.decisions["score"], ref.decisions["score"]), "scores are expected to be bit-identical"

@@ -4,7 +4,11 @@
 // feasible-node sampling, no hypernode scores, R <= 8. The FUT instance serves sessions with Releasing / Pipelined
 // resources (terminating pods, pipelined tasks): a node's verdict is then 0 (fits Idle: allocate), 1 (fits only
 // FutureIdle = Idle + Releasing - Pipelined: pipeline) or 2, and a candidate of category 0 beats every candidate of
-// category 1 (prioritizeNodes' idle gradient first, allocate.go:750-776). It exploits the one structural fact of the greedy loop: a placement changes ONE node, so between
+// category 1 (prioritizeNodes' idle gradient first, allocate.go:750-776). The SOFT instance serves sessions with
+// PreferNoSchedule taints and the TaintToleration batch scorer: that score is normalised by the largest count of
+// intolerable soft taints over the candidate set (DefaultNormalizeScore, reverse), a constant per category that only
+// moves when a node holding the maximum leaves the set; the owner flags that event in its publication and the next
+// task takes a full (two-phase) sweep. It exploits the one structural fact of the greedy loop: a placement changes ONE node, so between
 // two consecutive tasks with the same (class, request) record every other (task, node) verdict and score
 // is unchanged. Per CTA it keeps, for the group being placed,
 //     c_cat[i], c_score[i], c_cs[i]   verdict, total score, static word of each of its nodes (shared memory)
@@ -31,6 +35,7 @@
 #define CMD_EXIT 3
 #define CMD_EVAL 4
 #define CMD_RUN 5
+#define CMD_SWEEP2 6  // SOFT: second phase of a full sweep (totals under the exchanged normalisation constants)
 #define RUN_MAX 32  // placements one publication can cover (one lane of the evaluator warp per node state)
 #define VC_JOBX_PURE 0x100u  // host-computed: every named role of the job maps to a single group
 #define FAST_R 8
@@ -169,10 +174,11 @@ __device__ __forceinline__ Best unpack_best(const uint4 &v) {
 }
 
 // ring record of a publication: the owner CTA's new best + how many placements the record covers (1..RUN_MAX)
-__device__ __forceinline__ uint4 pack_run(const Best &b, unsigned tag, int m) {
+// flag (SOFT): the placement changed the candidate set in a way that may move a normalisation constant
+__device__ __forceinline__ uint4 pack_run(const Best &b, unsigned tag, int m, bool flag = false) {
   unsigned long long sb = (unsigned long long)__double_as_longlong(b.score);
   return make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)b.node,
-                    (tag << 10) | ((unsigned)m << 3) | ((unsigned)b.cat << 2) | (unsigned)min(b.cnt, 2));
+                    (tag << 10) | (flag ? 0x200u : 0u) | ((unsigned)m << 3) | ((unsigned)b.cat << 2) | (unsigned)min(b.cnt, 2));
 }
 #define RUN_TAG_MASK 0x3fffffu
 
@@ -298,6 +304,8 @@ struct CtlFast {  // shared-memory state of the fast kernel next to Ctl
   double ev_score;
   int ev_i, ev_ring, ev_node, ev_cnt, ev_cat, cur_group;
   int ev_kind;  // FUT: the placement just applied to row ev_i was an allocation (0) or a pipeline (1)
+  int ev_flag;  // SOFT: the evaluator saw a change of the candidate set that may move g_soft (-> full sweep next)
+  int g_soft[2];  // SOFT: largest intolerable-soft-taint count over the candidates of category 0 / 1
   unsigned ev_tag;
   // CMD_RUN: placements the control program allows on node ev_i in a row (run_L), attempt index of the first one,
   // result (run_m placements made), runner-up computed by warp 2
@@ -329,7 +337,7 @@ struct RunNodeView {
 // PROF = true keeps the phase / owner-path cycle counters (tools/prof_commit.py, VC_PROF=1); the production
 // instance carries no clock reads on the control warp's critical path.
 #define FPROF_MARK(k) do { if (PROF) { PROF_MARK(k); } } while (0)
-template <bool PROF, bool FUT = false>
+template <bool PROF, bool FUT = false, bool SOFT = false>
 __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams fp) {
   const DevConf &c = p.c;
   const int R = p.d.R, K = p.d.K, N = p.d.N, J = p.d.J, Q = p.d.Q, NR = p.d.NR, T = p.d.T;
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     S.cmd = 0; S.visit_id = 0; S.cur_group = -1; S.cache_group = -1; S.dirty_node = -1;
     S.ag = 0; S.pc = 0; S.since_sync = 0; S.n_full = 0; S.n_incr = 0;
     F.cta_best_node = -1; F.cta_cnt = 0; F.g_best_node = -1; F.g_cnt = 0; F.cta_best_score = F.g_best_score = 0.0;
-    F.cta_best_cat = 0; F.cta_cnt1 = 0; F.ev_kind = 0; F.ev_cat = 0;
+    F.cta_best_cat = 0; F.cta_cnt1 = 0; F.ev_kind = 0; F.ev_cat = 0; F.ev_flag = 0; F.g_soft[0] = F.g_soft[1] = 0;
     F.spec_i[0] = F.spec_i[1] = -1;
   }
   __syncthreads();
@@ -445,6 +453,30 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     const int vid = S.visit_id;
     Best b{0.0, -1, 0, 0};
     int n0 = 0, n1 = 0;
+    if (SOFT && S.cmd == CMD_SWEEP2) {
+      // second phase: TaintToleration's normalised score joins the cached NodeOrderFn sums (scheduler_helper.go:117-129)
+      const int gs0 = F.g_soft[0], gs1 = F.g_soft[1];
+      for (int i = tid; i < nmine; i += blockDim.x) {
+        const int cat = fs.c_cat[i];
+        if (cat == 2) continue;
+        const int soft = (int)((fs.c_cs[i] >> CS_SOFT_SHIFT) & 0xffu);
+        const double sc = total_score(c, true, fs.c_score[i], soft, cat == 0 ? gs0 : gs1);
+        fs.c_score[i] = sc;
+        best_fold(b, sc, nbase + i, 1, cat);
+        if (FUT) { n0 += cat == 0; n1 += cat == 1; }
+      }
+      best_warp_reduce<FUT>(b);
+      if (FUT) {
+        n0 = (int)__reduce_add_sync(0xffffffffu, (unsigned)n0);
+        n1 = (int)__reduce_add_sync(0xffffffffu, (unsigned)n1);
+      }
+      if (lane == 0) {
+        S.w_score[0][warp] = b.score; S.w_node[0][warp] = b.node; S.w_cnt[0][warp] = FUT ? n0 : b.cnt;
+        if (FUT) { S.w_cnt[1][warp] = n1; S.w_node[1][warp] = b.cat; }
+      }
+      return;
+    }
+    int ms0 = 0, ms1 = 0;  // SOFT, first phase: largest soft-taint count among this thread's candidates per category
     for (int i = tid; i < nmine; i += blockDim.x) {
       FastNodeView nv{fs, i};
       const uint32_t cs = __ldg(cs_row + i);
@@ -453,7 +485,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       double sc = 0.0;
       if (!(use_cache && ((fs.nerr[i] >> rl) & 1ull))) {
         const bool pod_cap = c.pred_predicates && fs.max_tasks[i] <= fs.pod_count[i];
-        cat = eval_pair_fast(c, R, K, trec, nv, cs, pod_cap, &sc);
+        cat = eval_pair_fast<SOFT>(c, R, K, trec, nv, cs, pod_cap, &sc);
         if (FUT) {
           // alloc.predicate: InitResreq <= FutureIdle (allocate.go:816-824); the idle gradient is the subset that fits
           // Idle as well (:722-733). eval_pair_fast answered 0 exactly when the static part, the pod count AND Idle pass.
@@ -470,8 +502,20 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       fs.c_cat[i] = cat;
       fs.c_score[i] = sc;
       fs.c_cs[i] = cs;
+      if (SOFT) {
+        const int soft = (int)((cs >> CS_SOFT_SHIFT) & 0xffu);
+        if (cat == 0) ms0 = max(ms0, soft);
+        if (FUT && cat == 1) ms1 = max(ms1, soft);
+        continue;
+      }
       if (cat == 0 || (FUT && cat == 1)) best_fold(b, sc, nbase + i, 1, cat);
       if (FUT) { n0 += cat == 0; n1 += cat == 1; }
+    }
+    if (SOFT) {
+      ms0 = (int)__reduce_max_sync(0xffffffffu, (unsigned)ms0);
+      ms1 = (int)__reduce_max_sync(0xffffffffu, (unsigned)ms1);
+      if (lane == 0) { S.w_soft[0][warp] = ms0; S.w_soft[1][warp] = ms1; }
+      return;
     }
     best_warp_reduce<FUT>(b);
     if (FUT) {
@@ -665,9 +709,19 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       order = kk < ord_n ? order + term : order;
     }
     const bool has_order = !(ord_has_tdm && (cs & CS_TDM_ORDER_ERR));
-    *score_out = total_score(c, has_order, has_order ? order : 0.0, 0, 0);
-    if (FUT) return !fit_future ? 2 : (fit ? 0 : 1);
-    return fit ? 0 : 2;
+    const int cat_r = FUT ? (!fit_future ? 2 : (fit ? 0 : 1)) : (fit ? 0 : 2);
+    if (SOFT) *score_out = total_score(c, has_order, has_order ? order : 0.0, (int)((cs >> CS_SOFT_SHIFT) & 0xffu), F.g_soft[cat_r == 1 ? 1 : 0]);
+    else *score_out = total_score(c, has_order, has_order ? order : 0.0, 0, 0);
+    return cat_r;
+  };
+  // SOFT: does the row's move from category `oc` to `nc` possibly change a normalisation constant? (conservative)
+  auto soft_event = [&](int oc, int nc, uint32_t cs) -> bool {
+    if (!SOFT || oc == nc) return false;
+    const int soft = (int)((cs >> CS_SOFT_SHIFT) & 0xffu);
+    if (oc == 0 && soft > 0 && soft == F.g_soft[0]) return true;            // a holder of the maximum leaves category 0
+    if (FUT && oc == 1 && soft > 0 && soft == F.g_soft[1]) return true;     // ... leaves category 1
+    if (FUT && nc == 1 && soft > F.g_soft[1]) return true;                  // a larger count enters category 1
+    return false;
   };
   // per-lane operands of eval_dirty for the group record staged in S.trec
   auto stage_ops = [&]() {
@@ -734,8 +788,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       F.cta_best_score = bs; F.cta_best_node = bn; F.cta_cnt = cnt;
       if (FUT) { F.cta_best_cat = bcat; F.cta_cnt1 = cnt1; }
       Best nb{bs, bn, (FUT && bcat == 1) ? cnt1 : cnt, bcat};
-      store_all(p, p.peer_ring, p.ring, (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, 1));
+      const bool flag = soft_event(old_cat, cat, fs.c_cs[i]);
+      store_all(p, p.peer_ring, p.ring, (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, 1, flag));
       F.ev_score = bs; F.ev_node = bn; F.ev_cnt = min(nb.cnt, 2); F.ev_cat = bcat; F.run_m = 1;
+      if (SOFT) F.ev_flag = flag ? 1 : 0;
     }
     __syncwarp();
     asm volatile("bar.arrive 1, 64;" ::: "memory");  // results ready: warp 0 joins with bar.sync 1, 64
@@ -856,11 +912,12 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       if (FUT) {
         F.cta_cnt = F.rl_cnt0 + (cat_m == 0 ? 1 : 0); F.cta_cnt1 = F.rl_cnt1 + (cat_m == 1 ? 1 : 0); F.cta_best_cat = nb.cat;
       } else F.cta_cnt = nb.cnt;
-      store_all(p, p.peer_ring, p.ring, (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, m));
+      const bool flag = soft_event(old_cat, cat_m, fs.c_cs[i]);
+      store_all(p, p.peer_ring, p.ring, (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, m, flag));
       F.ev_score = nb.score; F.ev_node = nb.node; F.ev_cnt = min(nb.cnt, 2); F.ev_cat = nb.cat; F.run_m = m;
+      if (SOFT) F.ev_flag = flag ? 1 : 0;
       F.spec_i[0] = -1; F.spec_i[1] = -1;  // whatever was computed ahead describes an older state of the row
     }
-    (void)old_cat;
     n_runs += 1; n_run_place += m;
     __syncwarp();
     asm volatile("bar.arrive 1, 64;" ::: "memory");  // results ready: warp 0 joins with bar.sync 1, 64
@@ -883,7 +940,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         if (PROF && warp == 2 && lane == 0) atomicAdd(&p.counters[12], (int)(ev_acc_spec >> 10));
         break;
       }
-      if (cmd == CMD_SWEEP) sweep_part();
+      if (cmd == CMD_SWEEP || cmd == CMD_SWEEP2) sweep_part();
       else if (cmd == CMD_DISCARD) discard_part();
       else if (cmd == CMD_RUN) {  // all worker warps, joined on named barrier 2; warp 1 signals warp 0 on barrier 1
         if (F.cur_group != my_group) { stage_ops(); my_group = F.cur_group; }
@@ -1144,6 +1201,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           asm volatile("bar.sync 1, 64;" ::: "memory");  // join the evaluator warp
           DBG_STAGE(0, (int)(pub_pc << 4) | 5);
           nb.score = F.ev_score; nb.node = F.ev_node; nb.cnt = F.ev_cnt; nb.cat = FUT ? F.ev_cat : 0; pub_m = F.run_m;
+          if (SOFT && F.ev_flag) cache_group = -1;  // a normalisation constant may have moved: full sweep next
           if (PROF) {
             // the barrier blocks lazily: read the clock only after a value that needs it has arrived
             long long tj;
@@ -1166,7 +1224,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
 #undef WD_EXTRA
 #define WD_EXTRA
           nb = unpack_best(v);
-          pub_m = (int)((v.w >> 3) & 0x7fu);
+          pub_m = (int)((v.w >> 3) & 0x3fu);
+          if (SOFT && (v.w & 0x200u)) cache_group = -1;
         }
         const int old_cnt = fs.sl_cnt[o];
         bool refold = false;
@@ -1279,6 +1338,24 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           __syncthreads();  // B1
           sweep_part();
           __syncthreads();  // B2
+          if (SOFT) {
+            // first phase done (verdicts, NodeOrderFn sums, per-warp soft-taint maxima): all-gather the maxima, then the
+            // second phase adds the normalised TaintToleration score and folds the bests
+            int m0 = lane < nwarps ? S.w_soft[0][lane] : 0, m1 = lane < nwarps ? S.w_soft[1][lane] : 0;
+            m0 = (int)__reduce_max_sync(0xffffffffu, (unsigned)m0);
+            m1 = (int)__reduce_max_sync(0xffffffffu, (unsigned)m1);
+            Best sm{0.0, m0 | (m1 << 8), 0, 0};
+            exchange_all_fast(p, sm, ag, fs);
+            ag += 1;
+            int g0 = 0, g1 = 0;
+            for (int sl = lane; sl < G; sl += 32) { g0 = max(g0, fs.sl_node[sl] & 0xff); g1 = max(g1, (fs.sl_node[sl] >> 8) & 0xff); }
+            g0 = (int)__reduce_max_sync(0xffffffffu, (unsigned)g0);
+            g1 = (int)__reduce_max_sync(0xffffffffu, (unsigned)g1);
+            if (lane == 0) { F.g_soft[0] = g0; F.g_soft[1] = g1; S.cmd = CMD_SWEEP2; }
+            __syncthreads();  // B1
+            sweep_part();
+            __syncthreads();  // B2
+          }
           FPROF_MARK(2);
           Best mine{0.0, -1, 0, 0};
           int c0 = 0, c1 = 0;

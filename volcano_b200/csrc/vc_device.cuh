@@ -296,7 +296,9 @@ __device__ __forceinline__ int fit_category_t(int R, const TaskRec &t, const NV 
 // SM sub-partition). Adding the 0.0 of a skipped term is exact, so predication does not change results.
 // Returns the fit category (0 idle-fit / 2 infeasible) and the total score of util.PrioritizeNodes.
 // ---------------------------------------------------------------------------------------
-template <class NV>
+// ORDER_ONLY: *score_out = the NodeOrderFn sum alone (0.0 for a node whose sum was aborted); the caller adds the batch
+// scores once the normalisation constants of the candidate set are known.
+template <bool ORDER_ONLY = false, class NV>
 __device__ __forceinline__ int eval_pair_fast(const DevConf &c, int R, int K, const TaskRec &t, const NV &nv,
                                               uint32_t cs, bool pod_cap_hit, double *score_out) {
   constexpr int RT = 8, KT = VC_MAX_KDIMS;
@@ -400,7 +402,7 @@ __device__ __forceinline__ int eval_pair_fast(const DevConf &c, int R, int K, co
     }
   }
   // a NodeOrderFn error aborts the whole NodeOrderMapFn sum for the node (session_plugins.go:984-987)
-  *score_out = total_score(c, has_order, has_order ? order : 0.0, 0, 0);
+  *score_out = ORDER_ONLY ? (has_order ? order : 0.0) : total_score(c, has_order, has_order ? order : 0.0, 0, 0);
   return fit ? 0 : 2;
 }
 

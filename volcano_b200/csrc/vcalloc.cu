@@ -372,7 +372,8 @@ void choose_geometry(vc_snapshot *s) {
   const int R = s->dims.n_dims, K = s->dims.n_kdims;
   // hypernode-level scores change for every node after every placement: per-step full sweeps (k_commit)
   // (Releasing / Pipelined resources alone keep the incremental kernel: its FUT instance)
-  s->fast = !s->topo_any && !s->dc.soft_active && !s->dc.nta_on && s->dc.to_find == 0 && R <= 8 && K <= VC_MAX_KDIMS && !g_tun.commit_generic;
+  // and PreferNoSchedule taints under the TaintToleration batch scorer its SOFT instance
+  s->fast = !s->topo_any && !s->dc.nta_on && s->dc.to_find == 0 && R <= 8 && K <= VC_MAX_KDIMS && !g_tun.commit_generic;
   if (s->fast) {
     if (g_tun.commit_threads <= 0) s->block = 256;  // 7 worker warps: a run's node states are evaluated two per warp
     size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2 + 1;
@@ -474,7 +475,7 @@ void vc_snapshot_destroy(vc_snapshot *s) {
     if (r != s->rank && s->peer_comm[r]) cudaIpcCloseMemHandle(s->peer_comm[r]);
   if (s->comm) cudaFree(s->comm);
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
-                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_score_log, s->d_prof, s->d_wait, s->d_decisions, s->d_visits, s->d_fit, s->d_counters, s->d_bf, s->w_rel, s->d_ev};
+                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_score_log, s->d_prof, s->d_wait, s->d_dbg, s->d_decisions, s->d_visits, s->d_fit, s->d_counters, s->d_bf, s->w_rel, s->d_ev};
   for (void *p : dptrs) if (p) cudaFree(p);
   void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters, s->h_ev, s->delta_pin};
   if (s->delta_dev) cudaFree(s->delta_dev);
@@ -1476,8 +1477,10 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
     CUDA_TRY(cudaMemsetAsync(d_wait, 0, 1024 * 8, s->stream));
   }
   p.cta_wait = d_wait;
-  const void *kfn = s->fast ? (s->dc.has_future ? (g_tun.prof ? (const void *)k_commit_fast<true, true> : (const void *)k_commit_fast<false, true>)
-                                                : (g_tun.prof ? (const void *)k_commit_fast<true, false> : (const void *)k_commit_fast<false, false>))
+  // (the instrumented instance exists for the plain and the FUT shape)
+  const void *kfn = s->fast ? (s->dc.soft_active ? (s->dc.has_future ? (const void *)k_commit_fast<false, true, true> : (const void *)k_commit_fast<false, false, true>)
+                               : s->dc.has_future ? (g_tun.prof ? (const void *)k_commit_fast<true, true> : (const void *)k_commit_fast<false, true>)
+                                                  : (g_tun.prof ? (const void *)k_commit_fast<true, false> : (const void *)k_commit_fast<false, false>))
                   : s->dc.to_find > 0 ? (s->topo_any ? (const void *)k_commit<true, true, true, true> : (const void *)k_commit<true, true, false, true>)
                   : s->topo_any ? (const void *)k_commit<true, true, true> : s->dc.has_future ? (s->dc.soft_active ? (const void *)k_commit<true, true> : (const void *)k_commit<true, false>)
                                      : (s->dc.soft_active ? (const void *)k_commit<false, true> : (const void *)k_commit<false, false>);

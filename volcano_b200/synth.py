@@ -54,6 +54,12 @@ CONFIGS = {
     "cfg2_fut": SynthConfig("cfg2_fut", 10_000, 100_000, 1, "priority+gang+predicates+nodeorder+binpack", releasing_frac=0.3),
     "cfg2_fut_tight": SynthConfig("cfg2_fut_tight", 10_000, 100_000, 1, "priority+gang+predicates+nodeorder+binpack",
                                   utilisation=0.97, min_util=0.8, releasing_frac=0.5),
+    # cfg2 with PreferNoSchedule taints (the normalising TaintToleration batch scorer), alone and with terminating pods
+    "cfg2_soft": SynthConfig("cfg2_soft", 10_000, 100_000, 1, "priority+gang+predicates+nodeorder+binpack", soft_taint_p=0.05),
+    "cfg2_fut_soft": SynthConfig("cfg2_fut_soft", 10_000, 100_000, 1, "priority+gang+predicates+nodeorder+binpack",
+                                 utilisation=0.9, min_util=0.5, releasing_frac=0.4, soft_taint_p=0.05),
+    "mid_soft": SynthConfig("mid_soft", 2_000, 20_000, 2, "priority+gang+drf+predicates+proportion+nodeorder+binpack", soft_taint_p=0.08,
+                            utilisation=0.95, min_util=0.6, releasing_frac=0.4),
     "mid_fut": SynthConfig("mid_fut", 2_000, 20_000, 1, "priority+gang+predicates+nodeorder+binpack", releasing_frac=0.3),
     "cfg3_fut": SynthConfig("cfg3_fut", 10_000, 100_000, 16, "priority+gang+drf+predicates+proportion+nodeorder+binpack",
                             utilisation=0.9, min_util=0.5, releasing_frac=0.4),
