@@ -16,6 +16,9 @@ def main():
     threads = int(sys.argv[2]) if len(sys.argv) > 2 else 16
     engine.init(0)
     snap = make_snapshot(name)
+    if os.environ.get("SAMP"):  # the reference's default adaptive feasible-node sampling, single-worker reading
+        snap.conf.percentage_nodes_to_find = int(os.environ["SAMP"]) if os.environ["SAMP"].isdigit() else 0
+        threads = 1
     t0 = time.time()
     res = engine.gpu_engine(snap)
     print(f"{name}: gpu {res.stats['commit_ms']:.1f} ms (kernel {res.stats['commit_kernel']}), {len(res.decisions)} ops, "

@@ -8,7 +8,12 @@
 // PreferNoSchedule taints and the TaintToleration batch scorer: that score is normalised by the largest count of
 // intolerable soft taints over the candidate set (DefaultNormalizeScore, reverse), a constant per category that only
 // moves when a node holding the maximum leaves the set; the owner flags that event in its publication and the next
-// task takes a full (two-phase) sweep. It exploits the one structural fact of the greedy loop: a placement changes ONE node, so between
+// task takes a full (two-phase) sweep. The SAMP instance serves feasible-node sampling (percentage-nodes-to-find < 100,
+// util/predicate_helper.go:43-140 in its single-worker reading): a task's candidates are the first numNodesToFind
+// feasible nodes in index order from the rotating start - a window that covers whole CTAs (whose cached bests already
+// sit in every CTA's slot table) plus a part of its first and of its last CTA; only those two scan their cache and
+// publish, every CTA folds two ring records and a few slots. (Sessions whose jobs need the role-keyed error cache, the
+// normalising batch scorer or several GPUs stay on k_commit.) It exploits the one structural fact of the greedy loop: a placement changes ONE node, so between
 // two consecutive tasks with the same (class, request) record every other (task, node) verdict and score
 // is unchanged. Per CTA it keeps, for the group being placed,
 //     c_cat[i], c_score[i], c_cs[i]   verdict, total score, static word of each of its nodes (shared memory)
@@ -108,6 +113,7 @@ struct FastSmem {
   double *c_score;
   double *sl_score;
   int32_t *sl_node, *sl_cnt, *sl_cat;
+  int32_t *sl_feas;  // SAMP: feasible nodes (category 0 or 1) of every CTA for the cached group
   int cap;
 };
 struct FastNodeView {
@@ -236,6 +242,46 @@ __device__ __forceinline__ void exchange_all_fast(const K2Params &p, const Best 
   __syncwarp();
 }
 
+// SAMP: the same all-gather with a second vector per slot: x = feasible nodes of the CTA, y = those at or after the
+// rotating start index (meaningful for the CTA that holds it). Fills sl_feas too; returns y of CTA `a_cta`.
+__device__ __forceinline__ int exchange_all_samp(const K2Params &p, const Best &mine, int feas, int tail, unsigned ag, FastSmem &fs, int a_cta) {
+  const int lane = threadIdx.x & 31;
+  const int G = p.n_cta;
+  const unsigned tag = (ag + 1u) & 0x1fffffffu;
+  const size_t par = (size_t)(ag & 1u) * G * MBOX_STRIDE;
+  uint4 *base = p.mbox + par;
+  if (lane == 0) mbox_store(base + (size_t)blockIdx.x * MBOX_STRIDE, pack_best(mine, tag));
+  if (lane == 1) mbox_store(base + (size_t)blockIdx.x * MBOX_STRIDE + 1, make_uint4((unsigned)feas, (unsigned)tail, 0u, tag << 3));
+  unsigned spins = 0;
+  const long long t0w = clock64();
+  int tail_a = 0;
+  for (int s0 = 0; s0 < G; s0 += 32) {
+    const int sidx = s0 + lane;
+    bool need = sidx < G;
+    uint4 a, x;
+    bool pending;
+    do {
+      pending = false;
+      if (need) {
+        a = mbox_load(base + (size_t)sidx * MBOX_STRIDE);
+        x = mbox_load(base + (size_t)sidx * MBOX_STRIDE + 1);
+        if ((a.w >> 3) != tag || (x.w >> 3) != tag) pending = true;
+        else {
+          Best b = unpack_best(a);
+          fs.sl_score[sidx] = b.score; fs.sl_node[sidx] = b.node; fs.sl_cnt[sidx] = b.cnt; fs.sl_cat[sidx] = b.cat;
+          fs.sl_feas[sidx] = (int)x.x;
+          if (sidx == a_cta) tail_a = (int)x.y;
+          need = false;
+        }
+      }
+      pending = __any_sync(0xffffffffu, pending);
+      if (pending) PEER_WATCHDOG(spins, t0w);
+    } while (pending);
+  }
+  __syncwarp();
+  return (int)__reduce_max_sync(0xffffffffu, (unsigned)tail_a);
+}
+
 // best of this CTA from its verdict/score cache (a whole warp); cnt = exact number of candidates of the best's category;
 // the FUT instance also returns how many nodes sit in each category
 template <bool FUT>
@@ -304,6 +350,8 @@ struct CtlFast {  // shared-memory state of the fast kernel next to Ctl
   double ev_score;
   int ev_i, ev_ring, ev_node, ev_cnt, ev_cat, cur_group;
   int ev_kind;  // FUT: the placement just applied to row ev_i was an allocation (0) or a pipeline (1)
+  uint4 rec[6];  // SAMP: the step's ring records as polled (previous publication, P_B, P_A; two vectors each)
+  int ev_feas;  // SAMP: feasible nodes of this CTA after the re-evaluation
   int ev_flag;  // SOFT: the evaluator saw a change of the candidate set that may move g_soft (-> full sweep next)
   int g_soft[2];  // SOFT: largest intolerable-soft-taint count over the candidates of category 0 / 1
   unsigned ev_tag;
@@ -337,8 +385,9 @@ struct RunNodeView {
 // PROF = true keeps the phase / owner-path cycle counters (tools/prof_commit.py, VC_PROF=1); the production
 // instance carries no clock reads on the control warp's critical path.
 #define FPROF_MARK(k) do { if (PROF) { PROF_MARK(k); } } while (0)
-template <bool PROF, bool FUT = false, bool SOFT = false>
+template <bool PROF, bool FUT = false, bool SOFT = false, bool SAMP = false>
 __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams fp) {
+  static_assert(!(SAMP && SOFT), "the sampled candidate set changes per task: its normalisation constants are not cacheable");
   const DevConf &c = p.c;
   const int R = p.d.R, K = p.d.K, N = p.d.N, J = p.d.J, Q = p.d.Q, NR = p.d.NR, T = p.d.T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -373,6 +422,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
   fs.sl_node = reinterpret_cast<int32_t *>(sp); sp += (size_t)G * 4;
   fs.sl_cnt = reinterpret_cast<int32_t *>(sp); sp += (size_t)G * 4;
   fs.sl_cat = reinterpret_cast<int32_t *>(sp); sp += (size_t)G * 4;
+  fs.sl_feas = reinterpret_cast<int32_t *>(sp); sp += (size_t)G * 4;
   sp = reinterpret_cast<unsigned char *>(((uintptr_t)sp + 15) & ~(uintptr_t)15);
   HeapKey *heap = fp.heap_in_smem ? reinterpret_cast<HeapKey *>(sp)
                                   : reinterpret_cast<HeapKey *>(p.rep_heap) + (size_t)lcta * p.rep_heap_stride;
@@ -398,7 +448,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     fs.c_score[i] = 0.0;
     fs.c_cs[i] = 0u;
   }
-  for (int s = tid; s < G; s += blockDim.x) { fs.sl_score[s] = 0.0; fs.sl_node[s] = -1; fs.sl_cnt[s] = 0; fs.sl_cat[s] = 0; }
+  for (int s = tid; s < G; s += blockDim.x) { fs.sl_score[s] = 0.0; fs.sl_node[s] = -1; fs.sl_cnt[s] = 0; fs.sl_cat[s] = 0; fs.sl_feas[s] = 0; }
 
   // ---- per-CTA replica of the mutable control state, packed records ----
   unsigned char *rb = reinterpret_cast<unsigned char *>(p.rep_f64 + (size_t)lcta * p.rep_f64_stride);
@@ -789,6 +839,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
       if (FUT) { F.cta_best_cat = bcat; F.cta_cnt1 = cnt1; }
       Best nb{bs, bn, (FUT && bcat == 1) ? cnt1 : cnt, bcat};
       const bool flag = soft_event(old_cat, cat, fs.c_cs[i]);
+      if (SAMP) {  // second vector of the ring entry: the CTA's feasible-node count
+        mbox_store(p.ring + (size_t)F.ev_ring * RING_STRIDE + 1, make_uint4((unsigned)(cnt + cnt1), 0u, 0u, F.ev_tag << 10));
+        F.ev_feas = cnt + cnt1;
+      }
       store_all(p, p.peer_ring, p.ring, (size_t)F.ev_ring * RING_STRIDE, pack_run(nb, F.ev_tag, 1, flag));
       F.ev_score = bs; F.ev_node = bn; F.ev_cnt = min(nb.cnt, 2); F.ev_cat = bcat; F.run_m = 1;
       if (SOFT) F.ev_flag = flag ? 1 : 0;
@@ -979,6 +1033,10 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     int n_dec = 0, n_vis = 0, n_fit = 0, n_steps = 0, n_full = 0, n_incr = 0, visit_id = 0, n_owner_change = 0, last_owner = -1;
     double g_best_score = 0.0;
     int g_best_node = -1, g_cnt = 0, g_best_owner = -1;
+    // SAMP: util.lastProcessedNodeIndex, feasible nodes of its CTA at or after it (for the cached group), and whether
+    // that count is current
+    int s_start = SAMP ? c.last_idx0 : 0, s_tail = 0, s_total = 0;  // s_total: feasible nodes over all CTAs
+    bool s_tail_valid = false;
     int g_best_cat = 0, g_cnt1 = 0;  // FUT: g_cnt / g_cnt1 = candidates of category 0 / 1 over all CTAs (each clamped to 2 per CTA)
     bool pub_pending = false;
     long long t_a = 0, t_b = 0, t_c = 0, acc_ab = 0, acc_bc = 0, acc_cp = 0, acc_ja = 0;
@@ -1226,6 +1284,25 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           nb = unpack_best(v);
           pub_m = (int)((v.w >> 3) & 0x3fu);
           if (SOFT && (v.w & 0x200u)) cache_group = -1;
+          if (SAMP) {
+            uint4 x;
+            do { x = mbox_load(ent + 1); PEER_WATCHDOG(spins, t0w); } while ((x.w >> 10) != tag);
+            s_total += (int)x.x - fs.sl_feas[o];
+            __syncwarp();
+            if (lane == 0) fs.sl_feas[o] = (int)x.x;
+          }
+        }
+        if (SAMP) {  // the window logic reads the slot table only
+          if (o == cta) {
+            s_total += F.ev_feas - fs.sl_feas[o];
+            __syncwarp();
+            if (lane == 0) fs.sl_feas[o] = F.ev_feas;
+          }
+          __syncwarp();
+          if (lane == 0) { fs.sl_score[o] = nb.score; fs.sl_node[o] = nb.node; fs.sl_cnt[o] = nb.cnt; fs.sl_cat[o] = nb.cat; }
+          __syncwarp();
+          since_sync += 1;
+          return;
         }
         const int old_cnt = fs.sl_cnt[o];
         bool refold = false;
@@ -1267,6 +1344,48 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         }
       };
 
+      // full sweep of this CTA's nodes for the staged group (every warp), reduced to the CTA's best and, for the FUT
+      // instance, its node counts per category
+      auto sweep_local = [&](int rl, bool use_cache, Best &mine, int &c0, int &c1) {
+          if (lane == 0) { S.cmd = CMD_SWEEP; S.sweep_rl = rl; S.sweep_use_cache = use_cache ? 1 : 0; S.visit_id = visit_id; }
+          __syncthreads();  // B1
+          sweep_part();
+          __syncthreads();  // B2
+          if (SOFT) {
+            // first phase done (verdicts, NodeOrderFn sums, per-warp soft-taint maxima): all-gather the maxima, then the
+            // second phase adds the normalised TaintToleration score and folds the bests
+            int m0 = lane < nwarps ? S.w_soft[0][lane] : 0, m1 = lane < nwarps ? S.w_soft[1][lane] : 0;
+            m0 = (int)__reduce_max_sync(0xffffffffu, (unsigned)m0);
+            m1 = (int)__reduce_max_sync(0xffffffffu, (unsigned)m1);
+            Best sm{0.0, m0 | (m1 << 8), 0, 0};
+            exchange_all_fast(p, sm, ag, fs);
+            ag += 1;
+            int g0 = 0, g1 = 0;
+            for (int sl = lane; sl < G; sl += 32) { g0 = max(g0, fs.sl_node[sl] & 0xff); g1 = max(g1, (fs.sl_node[sl] >> 8) & 0xff); }
+            g0 = (int)__reduce_max_sync(0xffffffffu, (unsigned)g0);
+            g1 = (int)__reduce_max_sync(0xffffffffu, (unsigned)g1);
+            if (lane == 0) { F.g_soft[0] = g0; F.g_soft[1] = g1; S.cmd = CMD_SWEEP2; }
+            __syncthreads();  // B1
+            sweep_part();
+            __syncthreads();  // B2
+          }
+          FPROF_MARK(2);
+          mine = Best{0.0, -1, 0, 0};
+          c0 = 0; c1 = 0;
+          if (!FUT) {
+            if (lane < nwarps) best_fold(mine, S.w_score[0][lane], S.w_node[0][lane], S.w_cnt[0][lane]);
+            best_warp_reduce(mine);
+          } else {  // per warp: best (score, node, category) + how many of its nodes sit in category 0 / 1
+            if (lane < nwarps) {
+              best_fold(mine, S.w_score[0][lane], S.w_node[0][lane], 0, S.w_node[1][lane]);
+              c0 = S.w_cnt[0][lane]; c1 = S.w_cnt[1][lane];
+            }
+            best_warp_reduce<true>(mine);
+            c0 = (int)__reduce_add_sync(0xffffffffu, (unsigned)c0);
+            c1 = (int)__reduce_add_sync(0xffffffffu, (unsigned)c1);
+            mine.cnt = mine.node < 0 ? 0 : (mine.cat == 0 ? c0 : c1);
+          }
+      };
       // ---- allocateResourcesForTasks, allocate.go:558-694 ----
       for (;;) {
         if (cursor >= task_end || N == 0) break;  // no nodes: return nil before touching the tasks (allocate.go:563-567)
@@ -1319,9 +1438,225 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         const bool use_cache = c.enable_ecache && named_role && !pure;
         FPROF_MARK(1);
         // the gates above do not need the last publication; everything below (global best, sweeps) does
-        resolve();
+        if (!SAMP) resolve();
         if (PROF) t_b = clock64();
 
+        if (SAMP) {
+          // ======== feasible-node sampling: the candidates are the first to_find feasible nodes from s_start ========
+          const int Kf = c.to_find, npc_ = p.npc;
+          const unsigned lt = (1u << lane) - 1u;
+          // feasible nodes of this CTA with local index >= lo, from the verdict cache
+          auto count_from = [&](int lo) -> int {
+            int n = 0;
+            for (int i = lane; i < nmine; i += 32) n += (i >= lo && fs.c_cat[i] != 2) ? 1 : 0;
+            return (int)__reduce_add_sync(0xffffffffu, (unsigned)n);
+          };
+          // all-gather of (best, feasible count, count at or after s_start); fills the slot table and s_tail
+          auto sync_exchange = [&](const Best &mine, int feas) {
+            const int a_cta = s_start / npc_;
+            const int tl = cta == a_cta ? count_from(s_start - nbase) : 0;
+            s_tail = exchange_all_samp(p, mine, feas, tl, ag, fs, a_cta);
+            int tot = 0;
+            for (int sl = lane; sl < G; sl += 32) tot += fs.sl_feas[sl];
+            s_total = (int)__reduce_add_sync(0xffffffffu, (unsigned)tot);
+            ag += 1; since_sync = 0; s_tail_valid = true;
+          };
+          if (!(pure && grp == cache_group)) {
+            resolve();
+            Best mine{0.0, -1, 0, 0};
+            int c0 = 0, c1 = 0;
+            sweep_local(rl, use_cache, mine, c0, c1);
+            const int feas = FUT ? c0 + c1 : mine.cnt;
+            if (lane == 0) {
+              F.cta_best_score = mine.score; F.cta_best_node = mine.node;
+              if (FUT) { F.cta_cnt = c0; F.cta_cnt1 = c1; F.cta_best_cat = mine.cat; } else F.cta_cnt = mine.cnt;
+            }
+            __syncwarp();
+            sync_exchange(mine, feas);
+            n_full += 1;
+            cache_group = pure ? grp : -1;
+          } else {
+            if (!s_tail_valid || since_sync >= RING_DEPTH / 2 - 4) {
+              resolve();
+              Best mine{F.cta_best_score, F.cta_best_node, (FUT && F.cta_best_cat == 1) ? F.cta_cnt1 : F.cta_cnt, FUT ? F.cta_best_cat : 0};
+              const int feas = F.cta_cnt + (FUT ? F.cta_cnt1 : 0);
+              __syncwarp();
+              sync_exchange(mine, feas);
+            }
+            n_incr += 1;
+          }
+          // ---- the window: CTA A holds s_start, CTA B the to_find-th feasible node; r = how many of B's feasible nodes
+          //      (in index order, from local index b_lo) belong to it ----
+          const int A = s_start / npc_;
+          int B = A, r = 0, total = 0, b_lo = 0;
+          bool wrap_head = false;  // the window runs once around the ring and ends in A's part before s_start
+          auto window = [&]() {
+            total = s_total;
+            B = A; r = Kf; b_lo = s_start - A * npc_; wrap_head = false;
+            if (total < Kf || s_tail >= Kf) return;
+            int cum = s_tail;
+            bool found = false;
+            for (int o0 = 1; o0 < G && !found; o0 += 32) {
+              const int off = o0 + lane;
+              int sl = A + off;
+              sl = sl >= G ? sl - G : sl;
+              const int f = off < G ? fs.sl_feas[sl] : 0;
+              int inc = f;
+              for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+              const unsigned hit = __ballot_sync(0xffffffffu, off < G && cum + inc >= Kf);
+              if (hit) {
+                const int l = __ffs(hit) - 1;
+                const int before = cum + __shfl_sync(0xffffffffu, inc, l) - __shfl_sync(0xffffffffu, f, l);
+                B = A + o0 + l; B = B >= G ? B - G : B; r = Kf - before; b_lo = 0; found = true;
+              } else {
+                cum += __shfl_sync(0xffffffffu, inc, 31);
+              }
+            }
+            if (!found) { B = A; r = Kf - cum; b_lo = 0; wrap_head = true; }
+          };
+          window();
+          auto in_window = [&](int o) -> bool {  // is CTA o one of the window's CTAs?
+            if (total < Kf || wrap_head) return true;
+            const int d_o = o >= A ? o - A : o - A + G, d_b = B >= A ? B - A : B - A + G;
+            return d_o <= d_b;
+          };
+          if (pub_pending && in_window(pub_owner)) {  // the pending publication changes a count the window was built from
+            // (its node cannot sit at or after s_start in A: the previous window ended right before s_start, and after
+            //  a wrap the step starts with a fresh all-gather)
+            resolve();
+            window();
+          }
+          FPROF_MARK(2);  // (SAMP profile: 2 = sweep / sync + window, 3 = part scans, poll and fold)
+          Best g{0.0, -1, 0, 0};
+          int gc0 = 0, gc1 = 0;
+          auto add_part = [&](const Best &b) {  // lane-uniform fold of one part's record
+            if (b.node < 0) return;
+            if (b.cat == 0) gc0 += b.cnt; else gc1 += b.cnt;
+            if (g.node < 0 || better_c(b.cat, b.score, b.node, g.cat, g.score, g.node)) { g.score = b.score; g.node = b.node; g.cat = b.cat; }
+          };
+          if (total < Kf) {
+            // fewer feasible nodes than wanted: every one of them is a candidate, the scan went once around (processed = N)
+            resolve();
+            int own = -1;
+            g = fold_slots<FUT>(fs, G, &own);
+            int t0 = 0, t1 = 0;
+            for (int sl = lane; sl < G; sl += 32) { if (fs.sl_cat[sl] == 0) t0 += fs.sl_cnt[sl]; else t1 += fs.sl_cnt[sl]; }
+            gc0 = (int)__reduce_add_sync(0xffffffffu, (unsigned)t0);
+            gc1 = (int)__reduce_add_sync(0xffffffffu, (unsigned)t1);
+            s_tail_valid = false;  // the winner may sit at or after s_start in A
+          } else {
+            // ---- the two partial CTAs scan their cache and publish; everybody folds the two records and the whole CTAs between ----
+            const unsigned pa = pc, pb = pc + 1u;
+            pc += 2; since_sync += 2;
+            const bool a_part = !(A == B && !wrap_head);  // A's tail [s_start, end of A) is a part of its own
+            // best of this CTA's feasible nodes with local index >= lo, the first `take` of them in index order
+            auto scan_part = [&](int lo, int take, Best &b, int &end_local, int &after) {
+              b = Best{0.0, -1, 0, 0};
+              int base = 0, endl = -1;
+              for (int i0 = 0; i0 < nmine; i0 += 32) {
+                const int i = i0 + lane;
+                const int cc = i < nmine ? fs.c_cat[i] : 2;
+                const bool f = i >= lo && cc != 2;
+                const unsigned m = __ballot_sync(0xffffffffu, f);
+                const int rank = base + __popc(m & lt);
+                const bool inc = f && rank < take;
+                if (inc) { best_fold(b, fs.c_score[i], nbase + i, 1, cc); endl = i; }
+                base += __popc(m);
+              }
+              best_warp_reduce<FUT>(b);
+              end_local = (int)__reduce_max_sync(0xffffffffu, (unsigned)(endl + 1)) - 1;
+              after = base - min(base, take);
+            };
+            auto publish = [&](unsigned slot_pc, const Best &b, int end_local, int after) {
+              if (lane == 0) {
+                const unsigned tag = (slot_pc + 1u) & RUN_TAG_MASK;
+                uint4 *ent = p.ring + (size_t)(slot_pc % RING_DEPTH) * RING_STRIDE;
+                mbox_store(ent + 1, make_uint4((unsigned)end_local, (unsigned)after, 0u, tag << 10));
+                mbox_store(ent, pack_run(b, tag, 1, false));
+              }
+            };
+            if (cta == A && a_part) {
+              Best b; int el, af;
+              scan_part(s_start - nbase, 0x7fffffff, b, el, af);
+              publish(pa, b, el, af);
+            }
+            if (cta == B) {
+              Best b; int el, af;
+              scan_part(b_lo, r, b, el, af);
+              publish(pb, b, el, af);
+            }
+            // the whole CTAs strictly between A and B (all the others after a wrap): folded from the slot table while the
+            // part records are in flight (a pending publication never concerns one of them, see in_window above)
+            const int span = wrap_head ? G - 1 : (B >= A ? B - A : B - A + G) - 1;
+            if (span > 0) {
+              Best mid{0.0, -1, 0, 0};
+              int t0 = 0, t1 = 0;
+              for (int o = 1 + lane; o <= span; o += 32) {
+                int sl = A + o;
+                sl = sl >= G ? sl - G : sl;
+                best_fold(mid, fs.sl_score[sl], fs.sl_node[sl], 0, FUT ? fs.sl_cat[sl] : 0);
+                if (fs.sl_node[sl] >= 0) { if (!FUT || fs.sl_cat[sl] == 0) t0 += fs.sl_cnt[sl]; else t1 += fs.sl_cnt[sl]; }
+              }
+              best_warp_reduce<FUT>(mid);
+              gc0 += (int)__reduce_add_sync(0xffffffffu, (unsigned)t0);
+              gc1 += (int)__reduce_add_sync(0xffffffffu, (unsigned)t1);
+              mid.cnt = 0;
+              if (mid.node >= 0) { g.score = mid.score; g.node = mid.node; g.cat = mid.cat; }
+            }
+            // One poll for everything this step waits for - the previous placement's publication (unless this CTA made
+            // it: then its evaluator warp is joined) and the one or two part records, two vectors each: six lanes load
+            // one vector each until every tag matches, so the L2 round trips overlap instead of adding up.
+            if (pub_pending && pub_owner == cta) resolve();
+            const bool po = pub_pending;  // (a foreign owner's record)
+            {
+              const int which = lane >> 1, vec = lane & 1;  // 0: previous publication, 1: P_B, 2: P_A
+              const bool want = lane < 6 && (which == 0 ? po : which == 1 ? true : a_part);
+              const unsigned spc = which == 0 ? pub_pc : which == 1 ? pb : pa;
+              const unsigned tag = (spc + 1u) & RUN_TAG_MASK;
+              const uint4 *ent = p.ring + (size_t)(spc % RING_DEPTH) * RING_STRIDE + vec;
+              uint4 v = make_uint4(0u, 0u, 0u, 0u);
+              unsigned spins = 0;
+              const long long t0w = clock64();
+              bool pending;
+              do {
+                pending = false;
+                if (want) { v = mbox_load(ent); pending = (v.w >> 10) != tag; }
+                pending = __any_sync(0xffffffffu, pending);
+                if (pending) PEER_WATCHDOG(spins, t0w);
+              } while (pending);
+              if (lane < 6) F.rec[lane] = v;
+              __syncwarp();
+            }
+            if (po) {  // what resolve() does with a foreign record
+              pub_pending = false;
+              const int o = pub_owner;
+              if (o != last_owner) { n_owner_change += 1; last_owner = o; }
+              const Best nb = unpack_best(F.rec[0]);
+              const int nf = (int)F.rec[1].x;
+              s_total += nf - fs.sl_feas[o];
+              __syncwarp();
+              if (lane == 0) { fs.sl_score[o] = nb.score; fs.sl_node[o] = nb.node; fs.sl_cnt[o] = nb.cnt; fs.sl_cat[o] = nb.cat; fs.sl_feas[o] = nf; }
+              __syncwarp();
+              since_sync += 1;
+            }
+            const int end_local = (int)F.rec[3].x, after = (int)F.rec[3].y;
+            add_part(unpack_best(F.rec[2]));
+            if (a_part) add_part(unpack_best(F.rec[4]));
+            // lastProcessedNodeIndex moves past the to_find-th feasible node (predicate_helper.go:135-136)
+            const int nxt = B * npc_ + end_local + 1;
+            s_start = nxt >= N ? 0 : nxt;
+            const int X = s_start / npc_;  // the CTA the next window starts in, and its feasible nodes from there on
+            if (wrap_head) s_tail_valid = false;
+            else if (nxt < N && X == B) s_tail = after;
+            else if (in_window(X)) s_tail_valid = false;  // this step's winner may sit in that CTA (tiny rings only)
+            else s_tail = fs.sl_feas[X];
+          }
+          g_best_score = g.score; g_best_node = g.node; g_best_cat = g.cat;
+          g_best_owner = g.node >= 0 ? g.node / npc_ : -1;
+          g_cnt = gc0; g_cnt1 = gc1;
+          if (!FUT) g_cnt = gc0 + gc1;
+          FPROF_MARK(3);
+        } else
         if (pure && grp == cache_group) {
           // -------- incremental step: verdict cache, slot table and global best are already current --------
           if (since_sync >= RING_DEPTH / 2) {  // keep the publication ring from being overrun
@@ -1334,44 +1669,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           FPROF_MARK(2);
         } else {
           // -------- full sweep --------
-          if (lane == 0) { S.cmd = CMD_SWEEP; S.sweep_rl = rl; S.sweep_use_cache = use_cache ? 1 : 0; S.visit_id = visit_id; }
-          __syncthreads();  // B1
-          sweep_part();
-          __syncthreads();  // B2
-          if (SOFT) {
-            // first phase done (verdicts, NodeOrderFn sums, per-warp soft-taint maxima): all-gather the maxima, then the
-            // second phase adds the normalised TaintToleration score and folds the bests
-            int m0 = lane < nwarps ? S.w_soft[0][lane] : 0, m1 = lane < nwarps ? S.w_soft[1][lane] : 0;
-            m0 = (int)__reduce_max_sync(0xffffffffu, (unsigned)m0);
-            m1 = (int)__reduce_max_sync(0xffffffffu, (unsigned)m1);
-            Best sm{0.0, m0 | (m1 << 8), 0, 0};
-            exchange_all_fast(p, sm, ag, fs);
-            ag += 1;
-            int g0 = 0, g1 = 0;
-            for (int sl = lane; sl < G; sl += 32) { g0 = max(g0, fs.sl_node[sl] & 0xff); g1 = max(g1, (fs.sl_node[sl] >> 8) & 0xff); }
-            g0 = (int)__reduce_max_sync(0xffffffffu, (unsigned)g0);
-            g1 = (int)__reduce_max_sync(0xffffffffu, (unsigned)g1);
-            if (lane == 0) { F.g_soft[0] = g0; F.g_soft[1] = g1; S.cmd = CMD_SWEEP2; }
-            __syncthreads();  // B1
-            sweep_part();
-            __syncthreads();  // B2
-          }
-          FPROF_MARK(2);
           Best mine{0.0, -1, 0, 0};
           int c0 = 0, c1 = 0;
-          if (!FUT) {
-            if (lane < nwarps) best_fold(mine, S.w_score[0][lane], S.w_node[0][lane], S.w_cnt[0][lane]);
-            best_warp_reduce(mine);
-          } else {  // per warp: best (score, node, category) + how many of its nodes sit in category 0 / 1
-            if (lane < nwarps) {
-              best_fold(mine, S.w_score[0][lane], S.w_node[0][lane], 0, S.w_node[1][lane]);
-              c0 = S.w_cnt[0][lane]; c1 = S.w_cnt[1][lane];
-            }
-            best_warp_reduce<true>(mine);
-            c0 = (int)__reduce_add_sync(0xffffffffu, (unsigned)c0);
-            c1 = (int)__reduce_add_sync(0xffffffffu, (unsigned)c1);
-            mine.cnt = mine.node < 0 ? 0 : (mine.cat == 0 ? c0 : c1);
-          }
+          sweep_local(rl, use_cache, mine, c0, c1);
           exchange_all_fast(p, mine, ag, fs);
           Best g = fold_slots<FUT>(fs, G, &g_best_owner);
           ag += 1; since_sync = 0; n_full += 1;
@@ -1693,6 +1993,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     if (lane == 0) {
       S.cmd = CMD_EXIT;
       S.n_dec = n_dec; S.n_vis = n_vis; S.n_fit = n_fit; S.n_steps = n_steps; S.n_full = n_full; S.n_incr = n_incr;
+      S.last_idx = s_start;
       S.pick2 = n_owner_change;
       if (PROF) {
       atomicAdd((unsigned long long *)&p.prof[8], (unsigned long long)acc_post_to_joinstart);
@@ -1727,6 +2028,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     p.counters[1] = S.n_vis;
     p.counters[2] = S.n_fit;
     p.counters[3] = S.n_steps;
+    if (SAMP) p.counters[4] = S.last_idx;
     p.counters[5] = S.n_full;
     p.counters[6] = S.n_incr;
     p.counters[7] = S.pick2;

@@ -248,6 +248,8 @@ struct vc_snapshot {
   bool alloc_ran = false, bf_ran = false;
   int last_idx_cur = 0;   // util.lastProcessedNodeIndex as the last action of the cycle left it
   int *d_dbg = nullptr;
+  bool fut_rows = false;  // Releasing / Pipelined resources present at open
+  bool all_pure = true;  // every job's named roles map to one (class, request) group each: the role-keyed error cache is a no-op
   bool rows_integral = false;  // every quantity a placement adds to / subtracts from a node row is integer-valued
   void *d_bf = nullptr;   // device slab of the backfill inputs / outputs
   size_t d_bf_bytes = 0;
@@ -339,6 +341,7 @@ int build_devconf(vc_snapshot *s, const vc_nodes *nd) {
   }
   // the topology and sampling variants of the commit kernel are <FUT, SOFT> instances
   d.has_future = fut || s->topo_any || d.to_find > 0;
+  s->fut_rows = fut != 0;
   int soft = 0;
   const size_t WN = (size_t)s->dims.taint_words * s->dims.n_nodes;
   for (size_t i = 0; i < WN && !soft; ++i)
@@ -373,12 +376,14 @@ void choose_geometry(vc_snapshot *s) {
   // hypernode-level scores change for every node after every placement: per-step full sweeps (k_commit)
   // (Releasing / Pipelined resources alone keep the incremental kernel: its FUT instance)
   // and PreferNoSchedule taints under the TaintToleration batch scorer its SOFT instance
-  s->fast = !s->topo_any && !s->dc.nta_on && s->dc.to_find == 0 && R <= 8 && K <= VC_MAX_KDIMS && !g_tun.commit_generic;
+  // and feasible-node sampling its SAMP instance (one GPU, no normalising scorer, no job that needs the error cache)
+  const bool samp_ok = s->dc.to_find == 0 || (s->world <= 1 && !s->dc.soft_active && (s->all_pure || !s->dc.enable_ecache));
+  s->fast = !s->topo_any && !s->dc.nta_on && samp_ok && R <= 8 && K <= VC_MAX_KDIMS && !g_tun.commit_generic;
   if (s->fast) {
     if (g_tun.commit_threads <= 0) s->block = 256;  // 7 worker warps: a run's node states are evaluated two per warp
     size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2 + 1;
     s->smem_bytes = ((sizeof(Ctl) + 15) & ~(size_t)15) + ((sizeof(CtlFast) + 15) & ~(size_t)15) + rows * npc * 8 +
-                    (size_t)npc * (8 + 4 * 5) + (size_t)s->n_cta_total * (8 + 4 + 4 + 4) + 64;
+                    (size_t)npc * (8 + 4 * 5) + (size_t)s->n_cta_total * (8 + 4 + 4 + 4 + 4) + 64;
     const size_t heap_bytes = (size_t)s->heap_total * sizeof(HeapKey);
     s->heap_in_smem = (heap_bytes <= 96 * 1024 && s->smem_bytes + heap_bytes <= 200 * 1024) ? 1 : 0;
     if (s->heap_in_smem) s->smem_bytes += heap_bytes + 16;
@@ -859,8 +864,11 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
       if (role_group[r] < 0) role_group[r] = group_of[t];
       else if (role_group[r] != group_of[t]) impure[tk->job[t]] = 1;
     }
-    for (size_t j = 0; j < J; ++j)
+    s->all_pure = true;
+    for (size_t j = 0; j < J; ++j) {
       if (!impure[j]) j_flags_x[j] |= VC_JOBX_PURE;
+      else s->all_pure = false;
+    }
   }
   // role pending counts incl. the tasks in scope (job_info.go:936-939)
   std::vector<int32_t> r_pending(NR, 0);
@@ -1478,7 +1486,9 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   }
   p.cta_wait = d_wait;
   // (the instrumented instance exists for the plain and the FUT shape)
-  const void *kfn = s->fast ? (s->dc.soft_active ? (s->dc.has_future ? (const void *)k_commit_fast<false, true, true> : (const void *)k_commit_fast<false, false, true>)
+  const void *kfn = s->fast && s->dc.to_find > 0 ? (s->fut_rows ? (const void *)k_commit_fast<false, true, false, true>
+                                                                 : g_tun.prof ? (const void *)k_commit_fast<true, false, false, true> : (const void *)k_commit_fast<false, false, false, true>)
+                  : s->fast ? (s->dc.soft_active ? (s->dc.has_future ? (const void *)k_commit_fast<false, true, true> : (const void *)k_commit_fast<false, false, true>)
                                : s->dc.has_future ? (g_tun.prof ? (const void *)k_commit_fast<true, true> : (const void *)k_commit_fast<false, true>)
                                                   : (g_tun.prof ? (const void *)k_commit_fast<true, false> : (const void *)k_commit_fast<false, false>))
                   : s->dc.to_find > 0 ? (s->topo_any ? (const void *)k_commit<true, true, true, true> : (const void *)k_commit<true, true, false, true>)
@@ -1494,7 +1504,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   fp.q_share0 = s->q_share0.d(s->in);
   fp.heap_off = s->s_heap_off.d(s->in); fp.ready_word = s->fast_ready_word; fp.ready_shift = s->fast_ready_shift;
   fp.share_on = s->fast_share_on; fp.heap_in_smem = s->heap_in_smem; fp.heap_total = s->heap_total;
-  fp.run_max = (s->rows_integral && !g_tun.commit_norun)
+  fp.run_max = (s->rows_integral && !g_tun.commit_norun && s->dc.to_find == 0)
                    ? std::max(1, std::min(g_tun.run_max > 0 ? g_tun.run_max : RUN_MAX, std::min(RUN_MAX, 2 * (s->block / 32 - 1)))) : 1;
   fp.score_log = s->d_score_log;
   if (s->world > 1) {  // mailbox, ring and score log live in the exported slabs; the score log is rank 0's (it writes the decisions)
