@@ -111,6 +111,35 @@ def run_oracle(snap, threads, want_results=False):
     return len(dec), dt
 
 
+KERNEL_NAMES = {0: "k_commit (general)", 1: "k_commit_fast (incremental)"}
+# session shapes other than the headline one, same size (10k nodes x 100k tasks): GPU cycle vs the CPU port in the same mode
+MODE_WORKLOADS = [("Releasing resources (terminating pods: FutureIdle gradient, pipelining)", "cfg2_fut"),
+                  ("PreferNoSchedule taints (normalising TaintToleration batch score)", "cfg2_soft")]
+
+
+def mode_results(device, threads):
+    from volcano_b200 import engine
+    from volcano_b200.synth import CONFIGS, make_snapshot
+    out = []
+    for mode, name in MODE_WORKLOADS:
+        try:
+            msnap = make_snapshot(CONFIGS[name])
+            e = engine.Engine(msnap, device=device)
+            e.upload()
+            e.allocate()
+            r = e.allocate()
+            e.close()
+            n, dt, oracle_results = run_oracle(msnap, threads, want_results=True)
+            gpu_v = len(r.decisions) / (r.stats["commit_ms"] * 1e-3)
+            out.append({"mode": mode, "workload": name, "gpu_ms": r.stats["commit_ms"], "gpu_pods_per_s": gpu_v,
+                        "cpu_pods_per_s": n / dt, "cpu_threads": threads, "speedup": gpu_v / (n / dt),
+                        "placements_identical": compare_placements(r, oracle_results)["placements_identical"],
+                        "kernel": KERNEL_NAMES.get(r.stats["commit_kernel"])})
+        except Exception as ex:  # a mode's failure must not hide the headline line
+            out.append({"mode": mode, "workload": name, "error": str(ex)})
+    return out
+
+
 def compare_placements(res, oracle_results):
     """GPU result vs the cpu_baseline leg's result on the SAME snapshot: identical placements (task, node, kind, visit,
     in order), visit outcomes and fit errors; fp64 scores within 1e-6 (north_star). -> dict for the JSON line."""
@@ -463,7 +492,7 @@ def main():
         # reported so that the parity-mode ratio is not mistaken for the production-default ratio
         try:
             snap.conf.percentage_nodes_to_find = 0
-            n2, dt2 = run_oracle(snap, threads)
+            n2, dt2, samp_results = run_oracle(snap, threads, want_results=True)
             cpu["reference_defaults"] = {"value": n2 / dt2, "unit": "pods/s", "placed": n2, "seconds": dt2,
                                          "note": "adaptive feasible-node sampling (deterministic single-worker reading); "
                                                  "different placements than parity mode"}
@@ -473,9 +502,21 @@ def main():
             r2 = eng.allocate()
             cpu["reference_defaults"]["gpu_same_mode"] = {
                 "value": len(r2.decisions) / (r2.stats["commit_ms"] * 1e-3), "unit": "pods/s", "placed": len(r2.decisions),
-                "ms": r2.stats["commit_ms"]}
+                "ms": r2.stats["commit_ms"], "kernel": KERNEL_NAMES.get(r2.stats["commit_kernel"]),
+                "placements_identical": compare_placements(r2, samp_results)["placements_identical"]}
         finally:
             snap.conf.percentage_nodes_to_find = 100
+    modes = None
+    if rank == 0 and not args.no_cpu_baseline and args.workload == WORKLOAD:
+        modes = mode_results(local, max(1, min(16, cpu_cores())))
+        if cpu and "reference_defaults" in cpu and "gpu_same_mode" in cpu["reference_defaults"]:
+            rd = cpu["reference_defaults"]
+            modes.insert(0, {"mode": "feasible-node sampling (the reference's defaults)", "workload": args.workload,
+                             "gpu_ms": rd["gpu_same_mode"]["ms"], "gpu_pods_per_s": rd["gpu_same_mode"]["value"],
+                             "cpu_pods_per_s": rd["value"], "cpu_threads": cpu["cores"],
+                             "speedup": rd["gpu_same_mode"]["value"] / rd["value"],
+                             "placements_identical": rd["gpu_same_mode"].get("placements_identical"),
+                             "kernel": rd["gpu_same_mode"].get("kernel")})
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "pods/s", "n_gpus": world, "steps": args.steps,
@@ -493,6 +534,7 @@ def main():
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "modes": modes,
             "commit_kernel": {"kernel": "k_commit_fast (persistent cooperative, exact greedy loop)", "bound": "latency",
                               "share_of_step": 0.9999, "ms": 1e3 * t_dev / args.steps,
                               "us_per_placement_attempt": 1e6 * t_dev / max(1, n_steps),
