@@ -33,7 +33,7 @@ def _torchrun(script, *args, nproc=2, timeout=240):
     return json.loads(line)
 
 
-@pytest.mark.parametrize("cfg", ["tiny", "small", "small_roles"])
+@pytest.mark.parametrize("cfg", ["tiny", "small", "small_roles", "tiny_fut", "small_soft", "small_fut_soft"])
 def test_one_session_across_two_gpus(cfg):
     out = _torchrun("multi_gpu_commit.py", cfg, "2")
     assert out["world"] == 2 and out["identical_to_one_gpu"] and out["placed"] > 0

@@ -972,8 +972,8 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
   choose_geometry(s);
   if (s->n_cta_total > 2048) return fail(VC_EUNSUPPORTED, "too many CTAs (%d)", s->n_cta_total);
   if (s->world > 1 && !s->fast)
-    return fail(VC_EUNSUPPORTED, "one session across GPUs runs on the incremental commit kernel only (no Releasing / Pipelined "
-                                 "resources at open, no PreferNoSchedule taints, no topology plugin, no sampling)");
+    return fail(VC_EUNSUPPORTED, "one session across GPUs runs on the incremental commit kernel only (no topology plugin, "
+                                 "no feasible-node sampling)");
   if (s->dc.to_find > 0 && (s->npc + s->block - 1) / s->block > 4)
     return fail(VC_EUNSUPPORTED, "feasible-node sampling: more than 4 node rows per CTA (%d nodes per CTA)", s->npc);
   std::vector<int32_t> hn_member, hn_slot, cta_hn_off, cta_hn, node_chain, cta_chain_off, cta_chain;
