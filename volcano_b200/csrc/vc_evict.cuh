@@ -30,7 +30,8 @@ struct EvictTask {  // the preemptor, staged per launch
   uint32_t qalloc_has, qdes_has;
   double qalloc[VC_MAX_DIMS], qdes[VC_MAX_DIMS];
 };
-#define EV_PICK_K 8  // candidates one k_evict_pick launch hands to the host, in the action's node order
+#define EV_PICK_K 32  // candidates one k_evict_pick launch hands to the host, in the action's node order
+#define EV_CMD_OFF 64  // the apply command starts at this int of the mapped buffer (after the pick slots)
 struct EvictParams {
   DevDims d;
   DevConf c;
@@ -129,104 +130,160 @@ __device__ __forceinline__ bool ev_may_be_victim(const EvictParams &p, const Evi
   return false;
 }
 
+// One warp per node, one lane per entry of node.Tasks (strided when a node runs more than 32 pods): the filters are chains
+// of dependent loads (task -> job -> queue ...), so the walk is latency-bound and lanes overlap it; the requests of the
+// possible victims are then summed per dimension with a shuffle tree. Lane 0 scores the node when it is a candidate.
 __global__ void k_evict_rank(EvictParams p, EvictTask t) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   const int N = p.d.N, R = p.d.R, K = p.d.K;
-  if (n >= N) return;
+  if (n >= N) return;  // whole warps leave together
   const uint32_t cs = p.cstat[(size_t)t.klass * N + n];
   uint8_t cand = 0;
   unsigned long long key = 0ull;
   if (cs & CS_STATIC_OK) {
-    // ValidateVictims can only pass when FutureIdle + every filter-passing task covers the request
-    double pot[VC_MAX_DIMS];
-    for (int d = 0; d < R; ++d)
-      pot[d] = (p.idle[(size_t)d * N + n] + p.rel[(size_t)d * N + n]) - p.pip[(size_t)d * N + n];
     double freed[VC_MAX_DIMS];
     for (int d = 0; d < R; ++d) freed[d] = 0.0;
     int n_pass = 0;
-    for (int k = p.rt_off[n]; k < p.rt_off[n + 1]; ++k) {
+    for (int k = p.rt_off[n] + lane; k < p.rt_off[n + 1]; k += 32) {
       const int r = p.rt_idx[k];
       if (!ev_filter(p, t, r)) continue;
       n_pass += 1;
       if (!ev_may_be_victim(p, t, r)) continue;
       for (int d = 0; d < R; ++d) freed[d] += p.rt_req[(size_t)d * p.RT + r];
     }
-    bool fits = true;
-    for (int d = 0; d < R; ++d) {
-      if (d >= 2 && !(t.rec.has & (1u << d))) continue;
-      if (!le_eps(t.rec.req[d], pot[d] + freed[d])) fits = false;
-    }
-    if (t.quota_on && p.exact_sums && t.mode != EV_MODE_RECLAIM) {
-      // the evict loop ends with ssn.Allocatable(queue, preemptor) (preempt.go:380, :405): even with every possible
-      // victim of this node evicted the queue must stay within deserved on the requested dimensions
-      if (!t.quota_open) fits = false;
-      const uint32_t rq_has = t.rec.has & ~3u;
+    n_pass = (int)__reduce_add_sync(0xffffffffu, (unsigned)n_pass);
+    for (int d = 0; d < R; ++d)
+      for (int o = 16; o; o >>= 1) freed[d] += __shfl_xor_sync(0xffffffffu, freed[d], o);
+    if (lane == 0) {
+      // ValidateVictims can only pass when FutureIdle + every possible victim covers the request. The sums above are
+      // exact for integer-valued requests (exact_sums); otherwise a relative slack keeps the test a necessary condition
+      // whatever the order of the additions.
+      const double slack = p.exact_sums ? 0.0 : 1e-9;
+      bool fits = true;
       for (int d = 0; d < R; ++d) {
-        const double rq = t.rec.req[d];
-        if (!(rq > 0.0)) continue;
-        if (d >= 2 && (!(rq_has & (1u << d)) || d == p.d.pods_dim)) continue;
-        const double al = (d < 2 || (t.qalloc_has & (1u << d))) ? t.qalloc[d] : 0.0;
-        const double de = (d < 2 || (t.qdes_has & (1u << d))) ? t.qdes[d] : 0.0;
-        if ((al - freed[d]) + rq > de) fits = false;
+        if (d >= 2 && !(t.rec.has & (1u << d))) continue;
+        const double pot = (p.idle[(size_t)d * N + n] + p.rel[(size_t)d * N + n]) - p.pip[(size_t)d * N + n];
+        const double have = pot + freed[d];
+        if (!le_eps(t.rec.req[d], have + fabs(have) * slack)) fits = false;
       }
-    }
-    if (fits && (t.mode != EV_MODE_RECLAIM || n_pass > 0)) {
-      cand = 1;
-      if (t.mode != EV_MODE_RECLAIM) {  // reclaim walks NodeList order, no scores (reclaim.go:172-180)
-        const EvNodeView nv{p, n};
-        double order = 0.0;
-        const bool has_order = node_order(p.c, R, K, t.rec, nv, cs, &order);
-        key = ev_score_key(total_score(p.c, has_order, has_order ? order : 0.0, 0, 0));
+      if (t.quota_on && p.exact_sums && t.mode != EV_MODE_RECLAIM) {
+        // the evict loop ends with ssn.Allocatable(queue, preemptor) (preempt.go:380, :405): even with every possible
+        // victim of this node evicted the queue must stay within deserved on the requested dimensions
+        if (!t.quota_open) fits = false;
+        const uint32_t rq_has = t.rec.has & ~3u;
+        for (int d = 0; d < R; ++d) {
+          const double rq = t.rec.req[d];
+          if (!(rq > 0.0)) continue;
+          if (d >= 2 && (!(rq_has & (1u << d)) || d == p.d.pods_dim)) continue;
+          const double al = (d < 2 || (t.qalloc_has & (1u << d))) ? t.qalloc[d] : 0.0;
+          const double de = (d < 2 || (t.qdes_has & (1u << d))) ? t.qdes[d] : 0.0;
+          if ((al - freed[d]) + rq > de) fits = false;
+        }
+      }
+      if (fits && (t.mode != EV_MODE_RECLAIM || n_pass > 0)) {
+        cand = 1;
+        if (t.mode != EV_MODE_RECLAIM) {  // reclaim walks NodeList order, no scores (reclaim.go:172-180)
+          const EvNodeView nv{p, n};
+          double order = 0.0;
+          const bool has_order = node_order(p.c, R, K, t.rec, nv, cs, &order);
+          key = ev_score_key(total_score(p.c, has_order, has_order ? order : 0.0, 0, 0));
+        }
       }
     }
   }
-  p.cand[n] = cand;
-  p.key[n] = key;
+  if (lane == 0) {
+    p.cand[n] = cand;
+    p.key[n] = key;
+  }
 }
 
 // one block: the next EV_PICK_K candidates in the action's node order (preempt: score descending, lowest index first
-// among equals; reclaim: index ascending); the nodes handed out are marked tried
-__global__ void k_evict_pick(EvictParams p, int mode) {
+// among equals; reclaim: index ascending); the nodes handed out are marked tried. Tournament with incremental repair:
+// every thread keeps the best of its own nodes in registers, every warp its best in shared memory; handing out a node
+// makes ONE thread rescan its nodes and ONE warp refold, the other 31 entries stay.
+// `cached` != 0: the launch carries N * 8 bytes of dynamic shared memory and the keys of the live candidates are staged there
+// once (0 = not a candidate), so that repairs read shared memory instead of global memory.
+extern __shared__ unsigned long long ev_pick_cache[];
+// The last store of the launch is `seq` into pick_node[EV_PICK_K] (system scope): the host polls that word of the mapped
+// buffer instead of paying a stream synchronisation per hand-out.
+__global__ void k_evict_pick(EvictParams p, int mode, int cached, int seq) {
   __shared__ unsigned long long s_key[32];
   __shared__ int s_node[32];
   __shared__ int s_best;
   const int N = p.d.N;
-  for (int it = 0; it < EV_PICK_K; ++it) {
-    unsigned long long bk = 0ull;
-    int bn = -1;
+  if (cached) {  // key + 1 (the top bit of a score key is never clear with all others set), 0 = not a candidate
+    for (int n = threadIdx.x; n < N; n += blockDim.x)
+      ev_pick_cache[n] = p.cand[n] == 1 ? (mode == EV_MODE_RECLAIM ? 1ull : p.key[n] + 1ull) : 0ull;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  auto better_kn = [](unsigned long long ka, int na, unsigned long long kb, int nb) {
+    return na >= 0 && (nb < 0 || ka > kb || (ka == kb && na < nb));
+  };
+  unsigned long long bk = 0ull;  // this thread's best remaining candidate
+  int bn = -1;
+  auto rescan = [&](int skip) {
+    bk = 0ull; bn = -1;
+    if (cached) {
+      for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const unsigned long long k = ev_pick_cache[n];
+        if (n == skip || k == 0ull) continue;
+        if (bn < 0 || k > bk) { bk = k; bn = n; }
+      }
+      return;
+    }
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
-      if (p.cand[n] != 1) continue;
+      if (n == skip || p.cand[n] != 1) continue;
       const unsigned long long k = mode == EV_MODE_RECLAIM ? 0ull : p.key[n];
       if (bn < 0 || k > bk) { bk = k; bn = n; }  // ascending n per thread: the first of equal keys stays
     }
+  };
+  auto warp_fold = [&]() {  // this warp's best into its shared slot
+    unsigned long long wk = bk;
+    int wn = bn;
     for (int o = 16; o; o >>= 1) {
-      const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
-      const int on = __shfl_xor_sync(0xffffffffu, bn, o);
-      if (on >= 0 && (bn < 0 || ok > bk || (ok == bk && on < bn))) { bk = ok; bn = on; }
+      const unsigned long long ok = __shfl_xor_sync(0xffffffffu, wk, o);
+      const int on = __shfl_xor_sync(0xffffffffu, wn, o);
+      if (better_kn(ok, on, wk, wn)) { wk = ok; wn = on; }
     }
-    if ((threadIdx.x & 31) == 0) { s_key[threadIdx.x >> 5] = bk; s_node[threadIdx.x >> 5] = bn; }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      const int nw = (blockDim.x + 31) >> 5;
-      bk = threadIdx.x < nw ? s_key[threadIdx.x] : 0ull;
-      bn = threadIdx.x < nw ? s_node[threadIdx.x] : -1;
+    if (lane == 0) { s_key[warp] = wk; s_node[warp] = wn; }
+  };
+  rescan(-1);
+  warp_fold();
+  __syncthreads();
+  for (int it = 0; it < EV_PICK_K; ++it) {
+    if (warp == 0) {
+      unsigned long long gk = lane < nw ? s_key[lane] : 0ull;
+      int gn = lane < nw ? s_node[lane] : -1;
       for (int o = 16; o; o >>= 1) {
-        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
-        const int on = __shfl_xor_sync(0xffffffffu, bn, o);
-        if (on >= 0 && (bn < 0 || ok > bk || (ok == bk && on < bn))) { bk = ok; bn = on; }
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, gk, o);
+        const int on = __shfl_xor_sync(0xffffffffu, gn, o);
+        if (better_kn(ok, on, gk, gn)) { gk = ok; gn = on; }
       }
-      if (threadIdx.x == 0) {
-        p.pick_node[it] = bn;
-        if (bn >= 0) p.cand[bn] = 2;
-        s_best = bn;
+      if (lane == 0) {
+        p.pick_node[it] = gn;
+        if (gn >= 0) { p.cand[gn] = 2; if (cached) ev_pick_cache[gn] = 0ull; }
+        s_best = gn;
       }
     }
     __syncthreads();
-    if (s_best < 0) {  // exhausted: the remaining slots say so
+    const int g = s_best;
+    if (g < 0) {  // exhausted: the remaining slots say so
       if (threadIdx.x == 0)
         for (int r = it + 1; r < EV_PICK_K; ++r) p.pick_node[r] = -1;
       break;
     }
+    if ((g % (int)blockDim.x) >> 5 == warp) {  // the warp of the thread that owned the node
+      if (g % (int)blockDim.x == (int)threadIdx.x) rescan(g);  // (cand[g] = 2 was written by another thread: skip g by name)
+      warp_fold();
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int32_t *>(p.pick_node + EV_PICK_K) = seq;
   }
 }
 

@@ -263,7 +263,7 @@ struct vc_snapshot {
   double *w_rel = nullptr;         // working copy of Releasing (Statement.Evict adds to it)
   void *d_ev = nullptr;            // device slab: running-task table + per-preemptor scratch
   size_t d_ev_bytes = 0;
-  int32_t *h_ev = nullptr;         // mapped pinned: [0..7] picked nodes, [16..] apply command
+  int32_t *h_ev = nullptr;         // mapped pinned: [0..EV_PICK_K) picked nodes, [EV_CMD_OFF..] apply command
   // ---- one session across the GPUs of a node (vc_comm_create / vc_comm_attach) ----
   int world = 1, rank = 0;
   int n_cta_total = 0;             // CTAs of all ranks (the exchange); n_cta stays this rank's grid
@@ -1749,7 +1749,7 @@ int ensure_evict_session(vc_snapshot *s) {
     CUDA_TRY(cudaMalloc(&s->d_ev, off));
     s->d_ev_bytes = off;
   }
-  if (!s->h_ev) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&s->h_ev), (16 + 2 + EV_MAX_VICTIMS) * 4, cudaHostAllocMapped));
+  if (!s->h_ev) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&s->h_ev), (EV_CMD_OFF + 2 + EV_MAX_VICTIMS) * 4, cudaHostAllocMapped));
   unsigned char *base = reinterpret_cast<unsigned char *>(s->d_ev);
   CUDA_TRY(cudaMemsetAsync(base, 0, off, s->stream));
   if (s->rt.n > 0) {
@@ -1819,9 +1819,9 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
   p.key = reinterpret_cast<unsigned long long *>(base + o_key); p.cand = base + o_cand;
   int32_t *dev_h = nullptr;
   CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&dev_h), s->h_ev, 0));
-  p.pick_node = dev_h; p.cmd = dev_h + 16;
+  p.pick_node = dev_h; p.cmd = dev_h + EV_CMD_OFF;
   volatile int32_t *h_pick = s->h_ev;
-  int32_t *h_cmd = s->h_ev + 16;
+  int32_t *h_cmd = s->h_ev + EV_CMD_OFF;
   int launches = 0, cur_mode = 0;
   EvictTask et;
   auto stage = [&](int t, int mode) {
@@ -1842,13 +1842,21 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
     }
   };
   int pick_buf[EV_PICK_K], pick_pos = EV_PICK_K, pick_n = 0;
+  // the pick kernel stages the candidates' keys in shared memory when they fit (N * 8 bytes)
+  size_t pick_smem = N * 8 <= 200 * 1024 ? N * 8 : 0;
+  if (pick_smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_evict_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pick_smem));
+  int pick_seq = 0;
+  s->h_ev[EV_PICK_K] = 0;
+  double t_launch = 0.0, t_sync = 0.0;  // host time inside kernel launches / stream synchronisations (vc_stats.prof_cycles, us)
   vch::Ranker rk;
   rk.begin = [&](int t, int mode) -> int {
     stage(t, mode);
     cur_mode = mode;
     pick_pos = pick_n = 0;
     if (N == 0) return VC_OK;
-    k_evict_rank<<<(unsigned)((N + 127) / 128), 128, 0, s->stream>>>(p, et);
+    const double tl0 = now_ms();
+    k_evict_rank<<<(unsigned)((N * 32 + 255) / 256), 256, 0, s->stream>>>(p, et);
+    t_launch += now_ms() - tl0;
     launches++;
     CUDA_TRY(cudaGetLastError());
     return VC_OK;
@@ -1858,10 +1866,21 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
     if (N == 0) return VC_OK;
     if (pick_pos >= pick_n) {
       if (pick_n > 0 && pick_n < EV_PICK_K) return VC_OK;  // the last batch was short: no candidate is left
-      k_evict_pick<<<1, 1024, 0, s->stream>>>(p, cur_mode);
+      const double tl0 = now_ms();
+      pick_seq += 1;
+      k_evict_pick<<<1, 1024, pick_smem, s->stream>>>(p, cur_mode, pick_smem ? 1 : 0, pick_seq);
+      const double tl1 = now_ms();
       launches++;
       CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaStreamSynchronize(s->stream));
+      // the kernel's last store is pick_seq into the mapped buffer: poll it (a stream query every few thousand spins
+      // turns a failed launch into an error instead of an endless wait)
+      for (unsigned spins = 0; h_pick[EV_PICK_K] != pick_seq; ++spins)
+        if ((spins & 0xfffu) == 0xfffu) {
+          const cudaError_t qe = cudaStreamQuery(s->stream);
+          if (qe != cudaSuccess && qe != cudaErrorNotReady) return fail(VC_ECUDA, "evict pick: %s", cudaGetErrorString(qe));
+          if (qe == cudaSuccess && h_pick[EV_PICK_K] != pick_seq) return fail(VC_ECUDA, "evict pick: completion word missing");
+        }
+      t_launch += tl1 - tl0; t_sync += now_ms() - tl1;
       pick_n = 0;
       for (int i = 0; i < EV_PICK_K && h_pick[i] >= 0; ++i) pick_buf[pick_n++] = h_pick[i];
       pick_pos = 0;
@@ -2003,6 +2022,8 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
   r->stats.commit_ms = r->stats.total_ms;
   r->stats.kernel_launches = launches;
   r->stats.n_steps = launches;
+  r->stats.prof_cycles[0] = (int64_t)(t_launch * 1e3);  // microseconds of host time in launches / in synchronisations
+  r->stats.prof_cycles[1] = (int64_t)(t_sync * 1e3);
   *out = r;
   return VC_OK;
 }
