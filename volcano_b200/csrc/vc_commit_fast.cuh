@@ -328,6 +328,7 @@ __device__ __forceinline__ void load_record(void *dst_smem, const void *src_glob
   }
 }
 
+struct SampWin { int A, B, r, b_lo, total; bool wrap; };  // SAMP: one task's candidate window over the ring of CTAs
 #define FAST_MAXQ 64  // queues mirrored in shared memory for the queue scan
 struct CtlFast {  // shared-memory state of the fast kernel next to Ctl
   JobStatic js;
@@ -1037,6 +1038,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     // that count is current
     int s_start = SAMP ? c.last_idx0 : 0, s_tail = 0, s_total = 0;  // s_total: feasible nodes over all CTAs
     bool s_tail_valid = false;
+    SampWin sp_w{0, 0, 0, 0, 0, false};  // SAMP: the window issued one step ahead, its ring slots
+    unsigned sp_pa = 0, sp_pb = 0;
+    bool sp_valid = false;
     int g_best_cat = 0, g_cnt1 = 0;  // FUT: g_cnt / g_cnt1 = candidates of category 0 / 1 over all CTAs (each clamped to 2 per CTA)
     bool pub_pending = false;
     long long t_a = 0, t_b = 0, t_c = 0, acc_ab = 0, acc_bc = 0, acc_cp = 0, acc_ja = 0;
@@ -1260,7 +1264,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           DBG_STAGE(0, (int)(pub_pc << 4) | 5);
           nb.score = F.ev_score; nb.node = F.ev_node; nb.cnt = F.ev_cnt; nb.cat = FUT ? F.ev_cat : 0; pub_m = F.run_m;
           if (SOFT && F.ev_flag) cache_group = -1;  // a normalisation constant may have moved: full sweep next
-          if (PROF) {
+          if (PROF && !SAMP) {
             // the barrier blocks lazily: read the clock only after a value that needs it has arrived
             long long tj;
             asm volatile("{ .reg .b32 t; mov.b32 t, %1; mov.u64 %0, %%clock64; }" : "=l"(tj) : "r"(nb.node) : "memory");
@@ -1287,6 +1291,8 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           if (SAMP) {
             uint4 x;
             do { x = mbox_load(ent + 1); PEER_WATCHDOG(spins, t0w); } while ((x.w >> 10) != tag);
+            // (the count at or after s_start follows when the re-evaluated node lies there)
+            if (o == s_start / p.npc && pub_node >= s_start) s_tail += (int)x.x - fs.sl_feas[o];
             s_total += (int)x.x - fs.sl_feas[o];
             __syncwarp();
             if (lane == 0) fs.sl_feas[o] = (int)x.x;
@@ -1294,6 +1300,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
         }
         if (SAMP) {  // the window logic reads the slot table only
           if (o == cta) {
+            if (o == s_start / p.npc && pub_node >= s_start) s_tail += F.ev_feas - fs.sl_feas[o];
             s_total += F.ev_feas - fs.sl_feas[o];
             __syncwarp();
             if (lane == 0) fs.sl_feas[o] = F.ev_feas;
@@ -1461,6 +1468,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             s_total = (int)__reduce_add_sync(0xffffffffu, (unsigned)tot);
             ag += 1; since_sync = 0; s_tail_valid = true;
           };
+          bool plain_step = false;  // an incremental step that needed neither a sweep nor a resynchronisation
           if (!(pure && grp == cache_group)) {
             resolve();
             Best mine{0.0, -1, 0, 0};
@@ -1482,23 +1490,24 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
               const int feas = F.cta_cnt + (FUT ? F.cta_cnt1 : 0);
               __syncwarp();
               sync_exchange(mine, feas);
+            } else {
+              plain_step = true;
             }
             n_incr += 1;
           }
           // ---- the window: CTA A holds s_start, CTA B the to_find-th feasible node; r = how many of B's feasible nodes
-          //      (in index order, from local index b_lo) belong to it ----
-          const int A = s_start / npc_;
-          int B = A, r = 0, total = 0, b_lo = 0;
-          bool wrap_head = false;  // the window runs once around the ring and ends in A's part before s_start
-          auto window = [&]() {
-            total = s_total;
-            B = A; r = Kf; b_lo = s_start - A * npc_; wrap_head = false;
-            if (total < Kf || s_tail >= Kf) return;
+          //      (in index order, from local index b_lo) belong to it; wrap = the window runs once around the ring and ends
+          //      in A's part before s_start ----
+          auto window = [&](SampWin &w) {
+            w.A = s_start / npc_;
+            w.total = s_total;
+            w.B = w.A; w.r = Kf; w.b_lo = s_start - w.A * npc_; w.wrap = false;
+            if (w.total < Kf || s_tail >= Kf) return;
             int cum = s_tail;
             bool found = false;
             for (int o0 = 1; o0 < G && !found; o0 += 32) {
               const int off = o0 + lane;
-              int sl = A + off;
+              int sl = w.A + off;
               sl = sl >= G ? sl - G : sl;
               const int f = off < G ? fs.sl_feas[sl] : 0;
               int inc = f;
@@ -1507,26 +1516,80 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
               if (hit) {
                 const int l = __ffs(hit) - 1;
                 const int before = cum + __shfl_sync(0xffffffffu, inc, l) - __shfl_sync(0xffffffffu, f, l);
-                B = A + o0 + l; B = B >= G ? B - G : B; r = Kf - before; b_lo = 0; found = true;
+                w.B = w.A + o0 + l; w.B = w.B >= G ? w.B - G : w.B; w.r = Kf - before; w.b_lo = 0; found = true;
               } else {
                 cum += __shfl_sync(0xffffffffu, inc, 31);
               }
             }
-            if (!found) { B = A; r = Kf - cum; b_lo = 0; wrap_head = true; }
+            if (!found) { w.B = w.A; w.r = Kf - cum; w.b_lo = 0; w.wrap = true; }
           };
-          window();
-          auto in_window = [&](int o) -> bool {  // is CTA o one of the window's CTAs?
-            if (total < Kf || wrap_head) return true;
-            const int d_o = o >= A ? o - A : o - A + G, d_b = B >= A ? B - A : B - A + G;
+          auto in_window = [&](const SampWin &w, int o) -> bool {  // is CTA o one of the window's CTAs?
+            if (w.total < Kf || w.wrap) return true;
+            const int d_o = o >= w.A ? o - w.A : o - w.A + G, d_b = w.B >= w.A ? w.B - w.A : w.B - w.A + G;
             return d_o <= d_b;
           };
-          if (pub_pending && in_window(pub_owner)) {  // the pending publication changes a count the window was built from
-            // (its node cannot sit at or after s_start in A: the previous window ended right before s_start, and after
-            //  a wrap the step starts with a fresh all-gather)
-            resolve();
-            window();
+          // best of this CTA's feasible nodes with local index >= lo, the first `take` of them in index order
+          auto scan_part = [&](int lo, int take, Best &b, int &end_local, int &after) {
+            b = Best{0.0, -1, 0, 0};
+            int base = 0, endl = -1;
+            for (int i0 = 0; i0 < nmine; i0 += 32) {
+              const int i = i0 + lane;
+              const int cc = i < nmine ? fs.c_cat[i] : 2;
+              const bool f = i >= lo && cc != 2;
+              const unsigned m = __ballot_sync(0xffffffffu, f);
+              const int rank = base + __popc(m & lt);
+              const bool inc = f && rank < take;
+              if (inc) { best_fold(b, fs.c_score[i], nbase + i, 1, cc); endl = i; }
+              base += __popc(m);
+            }
+            best_warp_reduce<FUT>(b);
+            end_local = (int)__reduce_max_sync(0xffffffffu, (unsigned)(endl + 1)) - 1;
+            after = base - min(base, take);
+          };
+          auto publish = [&](unsigned slot_pc, const Best &b, int end_local, int after) {
+            if (lane == 0) {
+              const unsigned tag = (slot_pc + 1u) & RUN_TAG_MASK;
+              uint4 *ent = p.ring + (size_t)(slot_pc % RING_DEPTH) * RING_STRIDE;
+              mbox_store(ent + 1, make_uint4((unsigned)end_local, (unsigned)after, 0u, tag << 10));
+              mbox_store(ent, pack_run(b, tag, 1, false));
+            }
+          };
+          // the two partial CTAs of window w scan their cache and publish (A's part after s_start into slot pa unless the
+          // window lies inside A; B's first r feasible nodes into slot pb)
+          auto issue = [&](const SampWin &w, unsigned pa, unsigned pb) {
+            const bool a_part = !(w.A == w.B && !w.wrap);
+            if (cta == w.A && a_part) {
+              Best b; int el, af;
+              scan_part(s_start - nbase, 0x7fffffff, b, el, af);
+              publish(pa, b, el, af);
+            }
+            if (cta == w.B) {
+              Best b; int el, af;
+              scan_part(w.b_lo, w.r, b, el, af);
+              publish(pb, b, el, af);
+            }
+          };
+          long long tq0 = 0;
+#define SAMP_T(acc) do { if (PROF && SAMP) { const long long n_ = clock64(); acc += n_ - tq0; tq0 = n_; } } while (0)
+          if (PROF) tq0 = clock64();
+          SampWin w;
+          unsigned pa = 0, pb = 0;
+          // a window issued one step ahead (below) is taken as it is when nothing moved in between
+          const bool used_spec = sp_valid && plain_step;
+          sp_valid = false;
+          if (used_spec) {
+            w = sp_w; pa = sp_pa; pb = sp_pb;
+          } else {
+            window(w);
+            if (pub_pending && in_window(w, pub_owner)) {  // the pending publication changes a count the window was built from
+              // (its node cannot sit at or after s_start in A: the previous window ended right before s_start, and after
+              //  a wrap the step starts with a fresh all-gather)
+              resolve();
+              window(w);
+            }
           }
           FPROF_MARK(2);  // (SAMP profile: 2 = sweep / sync + window, 3 = part scans, poll and fold)
+          SAMP_T(acc_post_to_joinstart);  // prof[8]: window (or taking the one issued ahead)
           Best g{0.0, -1, 0, 0};
           int gc0 = 0, gc1 = 0;
           auto add_part = [&](const Best &b) {  // lane-uniform fold of one part's record
@@ -1534,7 +1597,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             if (b.cat == 0) gc0 += b.cnt; else gc1 += b.cnt;
             if (g.node < 0 || better_c(b.cat, b.score, b.node, g.cat, g.score, g.node)) { g.score = b.score; g.node = b.node; g.cat = b.cat; }
           };
-          if (total < Kf) {
+          if (w.total < Kf) {
             // fewer feasible nodes than wanted: every one of them is a candidate, the scan went once around (processed = N)
             resolve();
             int own = -1;
@@ -1543,56 +1606,23 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             for (int sl = lane; sl < G; sl += 32) { if (fs.sl_cat[sl] == 0) t0 += fs.sl_cnt[sl]; else t1 += fs.sl_cnt[sl]; }
             gc0 = (int)__reduce_add_sync(0xffffffffu, (unsigned)t0);
             gc1 = (int)__reduce_add_sync(0xffffffffu, (unsigned)t1);
-            s_tail_valid = false;  // the winner may sit at or after s_start in A
+            // (s_start stays; should the winner sit at or after it in A, its publication adjusts s_tail when it is consumed)
           } else {
-            // ---- the two partial CTAs scan their cache and publish; everybody folds the two records and the whole CTAs between ----
-            const unsigned pa = pc, pb = pc + 1u;
-            pc += 2; since_sync += 2;
-            const bool a_part = !(A == B && !wrap_head);  // A's tail [s_start, end of A) is a part of its own
-            // best of this CTA's feasible nodes with local index >= lo, the first `take` of them in index order
-            auto scan_part = [&](int lo, int take, Best &b, int &end_local, int &after) {
-              b = Best{0.0, -1, 0, 0};
-              int base = 0, endl = -1;
-              for (int i0 = 0; i0 < nmine; i0 += 32) {
-                const int i = i0 + lane;
-                const int cc = i < nmine ? fs.c_cat[i] : 2;
-                const bool f = i >= lo && cc != 2;
-                const unsigned m = __ballot_sync(0xffffffffu, f);
-                const int rank = base + __popc(m & lt);
-                const bool inc = f && rank < take;
-                if (inc) { best_fold(b, fs.c_score[i], nbase + i, 1, cc); endl = i; }
-                base += __popc(m);
-              }
-              best_warp_reduce<FUT>(b);
-              end_local = (int)__reduce_max_sync(0xffffffffu, (unsigned)(endl + 1)) - 1;
-              after = base - min(base, take);
-            };
-            auto publish = [&](unsigned slot_pc, const Best &b, int end_local, int after) {
-              if (lane == 0) {
-                const unsigned tag = (slot_pc + 1u) & RUN_TAG_MASK;
-                uint4 *ent = p.ring + (size_t)(slot_pc % RING_DEPTH) * RING_STRIDE;
-                mbox_store(ent + 1, make_uint4((unsigned)end_local, (unsigned)after, 0u, tag << 10));
-                mbox_store(ent, pack_run(b, tag, 1, false));
-              }
-            };
-            if (cta == A && a_part) {
-              Best b; int el, af;
-              scan_part(s_start - nbase, 0x7fffffff, b, el, af);
-              publish(pa, b, el, af);
+            if (!used_spec) {
+              pa = pc; pb = pc + 1u;
+              pc += 2; since_sync += 2;
+              issue(w, pa, pb);
             }
-            if (cta == B) {
-              Best b; int el, af;
-              scan_part(b_lo, r, b, el, af);
-              publish(pb, b, el, af);
-            }
+            SAMP_T(acc_join_wait);  // prof[10]: issue (when not taken from the step before)
+            const bool a_part = !(w.A == w.B && !w.wrap);
             // the whole CTAs strictly between A and B (all the others after a wrap): folded from the slot table while the
             // part records are in flight (a pending publication never concerns one of them, see in_window above)
-            const int span = wrap_head ? G - 1 : (B >= A ? B - A : B - A + G) - 1;
+            const int span = w.wrap ? G - 1 : (w.B >= w.A ? w.B - w.A : w.B - w.A + G) - 1;
             if (span > 0) {
               Best mid{0.0, -1, 0, 0};
               int t0 = 0, t1 = 0;
               for (int o = 1 + lane; o <= span; o += 32) {
-                int sl = A + o;
+                int sl = w.A + o;
                 sl = sl >= G ? sl - G : sl;
                 best_fold(mid, fs.sl_score[sl], fs.sl_node[sl], 0, FUT ? fs.sl_cat[sl] : 0);
                 if (fs.sl_node[sl] >= 0) { if (!FUT || fs.sl_cat[sl] == 0) t0 += fs.sl_cnt[sl]; else t1 += fs.sl_cnt[sl]; }
@@ -1606,6 +1636,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             // One poll for everything this step waits for - the previous placement's publication (unless this CTA made
             // it: then its evaluator warp is joined) and the one or two part records, two vectors each: six lanes load
             // one vector each until every tag matches, so the L2 round trips overlap instead of adding up.
+            SAMP_T(acc_join_to_post);  // prof[11]: fold of the whole CTAs
             if (pub_pending && pub_owner == cta) resolve();
             const bool po = pub_pending;  // (a foreign owner's record)
             {
@@ -1627,12 +1658,14 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
               if (lane < 6) F.rec[lane] = v;
               __syncwarp();
             }
+            SAMP_T(acc_ja);  // prof[12]: poll
             if (po) {  // what resolve() does with a foreign record
               pub_pending = false;
               const int o = pub_owner;
               if (o != last_owner) { n_owner_change += 1; last_owner = o; }
               const Best nb = unpack_best(F.rec[0]);
               const int nf = (int)F.rec[1].x;
+              if (o == s_start / npc_ && pub_node >= s_start) s_tail += nf - fs.sl_feas[o];
               s_total += nf - fs.sl_feas[o];
               __syncwarp();
               if (lane == 0) { fs.sl_score[o] = nb.score; fs.sl_node[o] = nb.node; fs.sl_cnt[o] = nb.cnt; fs.sl_cat[o] = nb.cat; fs.sl_feas[o] = nf; }
@@ -1643,13 +1676,30 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             add_part(unpack_best(F.rec[2]));
             if (a_part) add_part(unpack_best(F.rec[4]));
             // lastProcessedNodeIndex moves past the to_find-th feasible node (predicate_helper.go:135-136)
-            const int nxt = B * npc_ + end_local + 1;
+            const int nxt = w.B * npc_ + end_local + 1;
             s_start = nxt >= N ? 0 : nxt;
             const int X = s_start / npc_;  // the CTA the next window starts in, and its feasible nodes from there on
-            if (wrap_head) s_tail_valid = false;
-            else if (nxt < N && X == B) s_tail = after;
-            else if (in_window(X)) s_tail_valid = false;  // this step's winner may sit in that CTA (tiny rings only)
+            // (a winner that sits in CTA X at or after the new start adjusts s_tail when its publication is consumed)
+            if (nxt < N && X == w.B) s_tail = after;
             else s_tail = fs.sl_feas[X];
+            // ---- one step ahead: the next window only depends on where this one ended, not on which of its nodes wins -
+            //      unless the winner's CTA lies inside it (its feasible count is about to change). The parts are scanned
+            //      and published now, so that they are in flight during this step's bookkeeping; the next step takes them
+            //      if it is a plain incremental step of the same group, and ignores them otherwise.
+            SAMP_T(acc_ab);  // prof[13]: records folded, next start
+            if (s_tail_valid && since_sync < RING_DEPTH / 2 - 8) {
+              SampWin w2;
+              window(w2);
+              const int own = g.node >= 0 ? g.node / npc_ : -1;
+              if (w2.total >= Kf && !w2.wrap && !(own >= 0 && in_window(w2, own))) {
+                sp_w = w2; sp_pa = pc; sp_pb = pc + 1u;
+                pc += 2; since_sync += 2;
+                issue(w2, sp_pa, sp_pb);
+                sp_valid = true;
+                acc_n += 1;  // prof[9]: windows issued ahead
+              }
+            }
+            SAMP_T(acc_bc);  // prof[14]: issuing the next window
           }
           g_best_score = g.score; g_best_node = g.node; g_best_cat = g.cat;
           g_best_owner = g.node >= 0 ? g.node / npc_ : -1;
@@ -1819,7 +1869,7 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
             __syncthreads();  // B1 of CMD_EVAL
             DBG_STAGE(0, (int)(pub_pc << 4) | 3);
             if (PROF) t_post = clock64();
-            if (PROF && t_join != 0) { acc_join_to_post += t_post - t_join; acc_ja += t_a - t_join; acc_ab += t_b - t_a; acc_bc += t_c - t_b; acc_cp += t_post - t_c; }
+            if (PROF && !SAMP && t_join != 0) { acc_join_to_post += t_post - t_join; acc_ja += t_a - t_join; acc_ab += t_b - t_a; acc_bc += t_c - t_b; acc_cp += t_post - t_c; }
           }
         }
         // job.UpdateTaskStatus + event handlers: drf (drf.go:391-418), proportion (proportion.go:475-497)
