@@ -105,4 +105,12 @@ int vh_backfill_pick(const vc_dims *d, const vc_conf *conf, const vc_nodes *nd, 
   return (int)p.order.size();
 }
 
+// preconditions of the run-length batches (vch::runs_exact, vch::future_rows_exact): 1 = m placements leave exactly row -/+ m * request
+int vh_runs_exact(int D, int N, int T, const double *row_a, const double *row_b, const double *req) {
+  return vch::runs_exact((size_t)D, (size_t)N, (size_t)T, {row_a, row_b}, {req}) ? 1 : 0;
+}
+int vh_future_rows_exact(int D, int N, int T, const double *idle, const double *rel, const double *pip, const double *req) {
+  return vch::future_rows_exact((size_t)D, (size_t)N, (size_t)T, idle, rel, pip, req) ? 1 : 0;
+}
+
 }  // extern "C"

@@ -276,3 +276,32 @@ def test_proportion_deserved_properties(shim, seed):
         if snap.q_capability_has[qi] & abi.VC_RES_HAS_ANY:    # capped queues stay under their capability
             assert np.all(des[:2, qi] <= snap.q_capability[:2, qi] + 1e-6)
     assert np.all(share >= 0)
+
+
+def test_run_length_exactness_preconditions(shim):
+    """vch::runs_exact / future_rows_exact (vc_host.hpp): run-length batches need integer-valued rows and requests with
+    |row| (+ |Releasing| + |Pipelined| per node for the FutureIdle expression) + 32 max|request| below 2^53."""
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    shim.vh_runs_exact.argtypes = [C.c_int] * 3 + [dp] * 3
+    shim.vh_future_rows_exact.argtypes = [C.c_int] * 3 + [dp] * 4
+
+    def arr(a):
+        a = np.ascontiguousarray(a, np.float64)
+        return a, a.ctypes.data_as(dp)
+
+    D, N, T = 2, 5, 3
+    idle, pi = arr(np.array([[4000, 8000, 0, 16000, 32000], [8e15, 7.9e15, 0, 1, 2]]))  # an ephemeral-storage-sized dimension
+    used, pu = arr(np.zeros((D, N)))
+    req, pr = arr(np.array([[100, 250, 4000], [0, 0, 0]]))
+    assert shim.vh_runs_exact(D, N, T, pi, pu, pr) == 1
+    frac, pf = arr(np.array([[100.5, 250, 4000], [0, 0, 0]]))
+    assert shim.vh_runs_exact(D, N, T, pi, pu, pf) == 0           # a fractional request
+    big, pb = arr(np.array([[100, 250, 4000], [0, 0, 5e13]]))
+    assert shim.vh_runs_exact(D, N, T, pi, pu, pb) == 0           # 8e15 + 32 * 5e13 leaves the exact range
+    rel, prl = arr(np.array([[0, 1000, 0, 0, 0], [0, 0, 0, 0, 0]]))
+    pip, pp = arr(np.zeros((D, N)))
+    assert shim.vh_future_rows_exact(D, N, T, pi, prl, pp, pr) == 1
+    rel2, prl2 = arr(np.array([[0, 1000, 0, 0, 0], [2e15, 0, 0, 0, 0]]))
+    assert shim.vh_future_rows_exact(D, N, T, pi, prl2, pp, pr) == 0   # Idle + Releasing of node 0 passes 2^53
+    assert shim.vh_future_rows_exact(D, N, T, pi, None, None, pr) == 1  # no Releasing / Pipelined rows at all
