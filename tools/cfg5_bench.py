@@ -42,8 +42,10 @@ for c in range(cycles):
                  "upload_ms": 1e3 * (t1 - t0), "allocate_ms": 1e3 * (t2 - t1), "preempt_ms": 1e3 * (t3 - t2),
                  "reclaim_ms": 1e3 * (t4 - t3), "cycle_ms": 1e3 * (t4 - t0), "placed": placed,
                  "preempt_launches": rp.stats["kernel_launches"], "reclaim_launches": rr.stats["kernel_launches"],
-                 "preempt_host_ms": {"in_launch_calls": rp.stats["prof_cycles"][0] / 1e3, "in_stream_sync": rp.stats["prof_cycles"][1] / 1e3},
-                 "reclaim_host_ms": {"in_launch_calls": rr.stats["prof_cycles"][0] / 1e3, "in_stream_sync": rr.stats["prof_cycles"][1] / 1e3},
+                 "preempt_host_ms": {"in_launch_calls": rp.stats["prof_cycles"][0] / 1e3, "waiting_for_handout": rp.stats["prof_cycles"][1] / 1e3,
+                                     "ranked_ahead": rp.stats["prof_cycles"][2], "ranked_ahead_used": rp.stats["prof_cycles"][3]},
+                 "reclaim_host_ms": {"in_launch_calls": rr.stats["prof_cycles"][0] / 1e3, "waiting_for_handout": rr.stats["prof_cycles"][1] / 1e3,
+                                     "ranked_ahead": rr.stats["prof_cycles"][2], "ranked_ahead_used": rr.stats["prof_cycles"][3]},
                  "generate_s": t_gen})
     if c == 0:
         from oracle.pyoracle import OracleSession

@@ -31,7 +31,7 @@ struct EvictTask {  // the preemptor, staged per launch
   double qalloc[VC_MAX_DIMS], qdes[VC_MAX_DIMS];
 };
 #define EV_PICK_K 32  // candidates one k_evict_pick launch hands to the host, in the action's node order
-#define EV_CMD_OFF 64  // the apply command starts at this int of the mapped buffer (after the pick slots)
+#define EV_CMD_OFF 80  // the apply command starts at this int of the mapped buffer (after the two sets of pick slots)
 struct EvictParams {
   DevDims d;
   DevConf c;
@@ -130,72 +130,87 @@ __device__ __forceinline__ bool ev_may_be_victim(const EvictParams &p, const Evi
   return false;
 }
 
-// One warp per node, one lane per entry of node.Tasks (strided when a node runs more than 32 pods): the filters are chains
-// of dependent loads (task -> job -> queue ...), so the walk is latency-bound and lanes overlap it; the requests of the
-// possible victims are then summed per dimension with a shuffle tree. Lane 0 scores the node when it is a candidate.
-__global__ void k_evict_rank(EvictParams p, EvictTask t) {
-  const int n = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
+// LPN lanes per node (16: two nodes per warp), one lane per entry of node.Tasks (strided when a node runs more pods than
+// that): the filters are chains of dependent loads (task -> job -> queue ...), so the walk is latency-bound and the lanes
+// overlap it; the requests of the possible victims are then summed per dimension with a shuffle tree inside the group.
+// The group's first lane scores the node when it is a candidate. RMAX bounds the resource dimensions (register budget).
+template <int LPN, int RMAX>
+__global__ void __launch_bounds__(256) k_evict_rank(EvictParams p, EvictTask t) {
+  const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int n = (int)(gid / LPN);
+  const int gl = (int)(threadIdx.x % LPN);  // lane inside the group
   const int N = p.d.N, R = p.d.R, K = p.d.K;
-  if (n >= N) return;  // whole warps leave together
-  const uint32_t cs = p.cstat[(size_t)t.klass * N + n];
-  uint8_t cand = 0;
-  unsigned long long key = 0ull;
-  if (cs & CS_STATIC_OK) {
-    double freed[VC_MAX_DIMS];
-    for (int d = 0; d < R; ++d) freed[d] = 0.0;
-    int n_pass = 0;
-    for (int k = p.rt_off[n] + lane; k < p.rt_off[n + 1]; k += 32) {
+  const bool live = n < N;
+  const uint32_t cs = live ? p.cstat[(size_t)t.klass * N + n] : 0u;
+  const bool stat_ok = live && (cs & CS_STATIC_OK);
+  double freed[RMAX];
+#pragma unroll
+  for (int d = 0; d < RMAX; ++d) freed[d] = 0.0;
+  int n_pass = 0;
+  if (stat_ok) {
+    for (int k = p.rt_off[n] + gl; k < p.rt_off[n + 1]; k += LPN) {
       const int r = p.rt_idx[k];
       if (!ev_filter(p, t, r)) continue;
       n_pass += 1;
       if (!ev_may_be_victim(p, t, r)) continue;
-      for (int d = 0; d < R; ++d) freed[d] += p.rt_req[(size_t)d * p.RT + r];
+#pragma unroll
+      for (int d = 0; d < RMAX; ++d)
+        if (d < R) freed[d] += p.rt_req[(size_t)d * p.RT + r];
     }
-    n_pass = (int)__reduce_add_sync(0xffffffffu, (unsigned)n_pass);
-    for (int d = 0; d < R; ++d)
-      for (int o = 16; o; o >>= 1) freed[d] += __shfl_xor_sync(0xffffffffu, freed[d], o);
-    if (lane == 0) {
-      // ValidateVictims can only pass when FutureIdle + every possible victim covers the request. The sums above are
-      // exact for integer-valued requests (exact_sums); otherwise a relative slack keeps the test a necessary condition
-      // whatever the order of the additions.
-      const double slack = p.exact_sums ? 0.0 : 1e-9;
-      bool fits = true;
-      for (int d = 0; d < R; ++d) {
-        if (d >= 2 && !(t.rec.has & (1u << d))) continue;
-        const double pot = (p.idle[(size_t)d * N + n] + p.rel[(size_t)d * N + n]) - p.pip[(size_t)d * N + n];
-        const double have = pot + freed[d];
-        if (!le_eps(t.rec.req[d], have + fabs(have) * slack)) fits = false;
+  }
+  // sums over the group (every lane of the warp takes part in the shuffles; groups are aligned, xor < LPN stays inside)
+#pragma unroll
+  for (int o = LPN / 2; o; o >>= 1) {
+    n_pass += __shfl_xor_sync(0xffffffffu, n_pass, o);
+#pragma unroll
+    for (int d = 0; d < RMAX; ++d)
+      if (d < R) freed[d] += __shfl_xor_sync(0xffffffffu, freed[d], o);
+  }
+  if (!live || gl != 0) return;
+  uint8_t cand = 0;
+  unsigned long long key = 0ull;
+  if (stat_ok) {
+    // ValidateVictims can only pass when FutureIdle + every possible victim covers the request. The sums above are
+    // exact for integer-valued requests (exact_sums); otherwise a relative slack keeps the test a necessary condition
+    // whatever the order of the additions.
+    const double slack = p.exact_sums ? 0.0 : 1e-9;
+    bool fits = true;
+#pragma unroll
+    for (int d = 0; d < RMAX; ++d) {
+      if (d >= R) continue;
+      if (d >= 2 && !(t.rec.has & (1u << d))) continue;
+      const double pot = (p.idle[(size_t)d * N + n] + p.rel[(size_t)d * N + n]) - p.pip[(size_t)d * N + n];
+      const double have = pot + freed[d];
+      if (!le_eps(t.rec.req[d], have + fabs(have) * slack)) fits = false;
+    }
+    if (t.quota_on && p.exact_sums && t.mode != EV_MODE_RECLAIM) {
+      // the evict loop ends with ssn.Allocatable(queue, preemptor) (preempt.go:380, :405): even with every possible
+      // victim of this node evicted the queue must stay within deserved on the requested dimensions
+      if (!t.quota_open) fits = false;
+      const uint32_t rq_has = t.rec.has & ~3u;
+#pragma unroll
+      for (int d = 0; d < RMAX; ++d) {
+        if (d >= R) continue;
+        const double rq = t.rec.req[d];
+        if (!(rq > 0.0)) continue;
+        if (d >= 2 && (!(rq_has & (1u << d)) || d == p.d.pods_dim)) continue;
+        const double al = (d < 2 || (t.qalloc_has & (1u << d))) ? t.qalloc[d] : 0.0;
+        const double de = (d < 2 || (t.qdes_has & (1u << d))) ? t.qdes[d] : 0.0;
+        if ((al - freed[d]) + rq > de) fits = false;
       }
-      if (t.quota_on && p.exact_sums && t.mode != EV_MODE_RECLAIM) {
-        // the evict loop ends with ssn.Allocatable(queue, preemptor) (preempt.go:380, :405): even with every possible
-        // victim of this node evicted the queue must stay within deserved on the requested dimensions
-        if (!t.quota_open) fits = false;
-        const uint32_t rq_has = t.rec.has & ~3u;
-        for (int d = 0; d < R; ++d) {
-          const double rq = t.rec.req[d];
-          if (!(rq > 0.0)) continue;
-          if (d >= 2 && (!(rq_has & (1u << d)) || d == p.d.pods_dim)) continue;
-          const double al = (d < 2 || (t.qalloc_has & (1u << d))) ? t.qalloc[d] : 0.0;
-          const double de = (d < 2 || (t.qdes_has & (1u << d))) ? t.qdes[d] : 0.0;
-          if ((al - freed[d]) + rq > de) fits = false;
-        }
-      }
-      if (fits && (t.mode != EV_MODE_RECLAIM || n_pass > 0)) {
-        cand = 1;
-        if (t.mode != EV_MODE_RECLAIM) {  // reclaim walks NodeList order, no scores (reclaim.go:172-180)
-          const EvNodeView nv{p, n};
-          double order = 0.0;
-          const bool has_order = node_order(p.c, R, K, t.rec, nv, cs, &order);
-          key = ev_score_key(total_score(p.c, has_order, has_order ? order : 0.0, 0, 0));
-        }
+    }
+    if (fits && (t.mode != EV_MODE_RECLAIM || n_pass > 0)) {
+      cand = 1;
+      if (t.mode != EV_MODE_RECLAIM) {  // reclaim walks NodeList order, no scores (reclaim.go:172-180)
+        const EvNodeView nv{p, n};
+        double order = 0.0;
+        const bool has_order = node_order(p.c, R, K, t.rec, nv, cs, &order);
+        key = ev_score_key(total_score(p.c, has_order, has_order ? order : 0.0, 0, 0));
       }
     }
   }
-  if (lane == 0) {
-    p.cand[n] = cand;
-    p.key[n] = key;
-  }
+  p.cand[n] = cand;
+  p.key[n] = key;
 }
 
 // one block: the next EV_PICK_K candidates in the action's node order (preempt: score descending, lowest index first
@@ -207,11 +222,14 @@ __global__ void k_evict_rank(EvictParams p, EvictTask t) {
 extern __shared__ unsigned long long ev_pick_cache[];
 // The last store of the launch is `seq` into pick_node[EV_PICK_K] (system scope): the host polls that word of the mapped
 // buffer instead of paying a stream synchronisation per hand-out.
-__global__ void k_evict_pick(EvictParams p, int mode, int cached, int seq) {
+__global__ void k_evict_pick_big(EvictParams p, int mode, int cached, int seq) {
   __shared__ unsigned long long s_key[32];
   __shared__ int s_node[32];
   __shared__ int s_best;
+  __shared__ int s_pick[EV_PICK_K];  // hand-outs, written to the mapped host buffer once at the end (a store to system memory
+                                     // per iteration sits on the critical path of the block-wide barriers)
   const int N = p.d.N;
+  if (threadIdx.x < EV_PICK_K) s_pick[threadIdx.x] = -1;
   if (cached) {  // key + 1 (the top bit of a score key is never clear with all others set), 0 = not a candidate
     for (int n = threadIdx.x; n < N; n += blockDim.x)
       ev_pick_cache[n] = p.cand[n] == 1 ? (mode == EV_MODE_RECLAIM ? 1ull : p.key[n] + 1ull) : 0ull;
@@ -262,23 +280,102 @@ __global__ void k_evict_pick(EvictParams p, int mode, int cached, int seq) {
         if (better_kn(ok, on, gk, gn)) { gk = ok; gn = on; }
       }
       if (lane == 0) {
-        p.pick_node[it] = gn;
+        s_pick[it] = gn;
         if (gn >= 0) { p.cand[gn] = 2; if (cached) ev_pick_cache[gn] = 0ull; }
         s_best = gn;
       }
     }
     __syncthreads();
     const int g = s_best;
-    if (g < 0) {  // exhausted: the remaining slots say so
-      if (threadIdx.x == 0)
-        for (int r = it + 1; r < EV_PICK_K; ++r) p.pick_node[r] = -1;
-      break;
-    }
+    if (g < 0) break;  // exhausted: the remaining slots keep their -1
     if ((g % (int)blockDim.x) >> 5 == warp) {  // the warp of the thread that owned the node
       if (g % (int)blockDim.x == (int)threadIdx.x) rescan(g);  // (cand[g] = 2 was written by another thread: skip g by name)
       warp_fold();
     }
     __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x < EV_PICK_K) {
+    *reinterpret_cast<volatile int32_t *>(p.pick_node + threadIdx.x) = s_pick[threadIdx.x];
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int32_t *>(p.pick_node + EV_PICK_K) = seq;
+  }
+}
+
+// k_evict_pick, the common case (the candidates' keys fit in shared memory, N * 8 bytes): two-level selection with two
+// block barriers in all. Phase 1, every warp on its own 1/32 of the nodes: EV_PICK_K rounds of a warp arg-max (each lane
+// keeps the best of its ~N/1024 nodes in registers, the winner rescans its shared-memory entries) give the warp's first
+// EV_PICK_K candidates in order. Phase 2, one warp: a 32-way merge of those sorted lists. Same order as the sequential
+// tournament: key descending, node ascending.
+__global__ void __launch_bounds__(1024) k_evict_pick(EvictParams p, int mode, int seq) {
+  __shared__ unsigned long long l_key[32][EV_PICK_K];
+  __shared__ int l_node[32][EV_PICK_K];
+  __shared__ int s_pick[EV_PICK_K];
+  const int N = p.d.N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int n = threadIdx.x; n < N; n += blockDim.x)  // key + 1 (never wraps: see ev_score_key), 0 = not a candidate
+    ev_pick_cache[n] = p.cand[n] == 1 ? (mode == EV_MODE_RECLAIM ? 1ull : p.key[n] + 1ull) : 0ull;
+  if (threadIdx.x < EV_PICK_K) s_pick[threadIdx.x] = -1;
+  __syncwarp();  // a lane only ever reads the entries it wrote
+  auto better_kn = [](unsigned long long ka, int na, unsigned long long kb, int nb) {
+    return na >= 0 && (nb < 0 || ka > kb || (ka == kb && na < nb));
+  };
+  unsigned long long bk = 0ull;
+  int bn = -1;
+  auto rescan = [&]() {
+    bk = 0ull; bn = -1;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const unsigned long long k = ev_pick_cache[n];
+      if (k == 0ull) continue;
+      if (bn < 0 || k > bk) { bk = k; bn = n; }  // ascending n per thread: the first of equal keys stays
+    }
+  };
+  rescan();
+  for (int it = 0; it < EV_PICK_K; ++it) {
+    unsigned long long wk = bk;
+    int wn = bn;
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long ok = __shfl_xor_sync(0xffffffffu, wk, o);
+      const int on = __shfl_xor_sync(0xffffffffu, wn, o);
+      if (better_kn(ok, on, wk, wn)) { wk = ok; wn = on; }
+    }
+    if (lane == it) { l_key[warp][it] = wk; l_node[warp][it] = wn; }
+    if (wn < 0) {  // this warp is out of candidates: the rest of its list says so
+      if (lane > it && lane < EV_PICK_K) { l_key[warp][lane] = 0ull; l_node[warp][lane] = -1; }
+      break;
+    }
+    if (bn == wn) { ev_pick_cache[wn] = 0ull; rescan(); }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int hp = 0;  // lane l walks warp l's list
+    unsigned long long ck = l_key[lane][0];
+    int cn = l_node[lane][0];
+    for (int it = 0; it < EV_PICK_K; ++it) {
+      unsigned long long gk = ck;
+      int gn = cn;
+      for (int o = 16; o; o >>= 1) {
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, gk, o);
+        const int on = __shfl_xor_sync(0xffffffffu, gn, o);
+        if (better_kn(ok, on, gk, gn)) { gk = ok; gn = on; }
+      }
+      if (gn < 0) break;
+      if (lane == 0) { s_pick[it] = gn; p.cand[gn] = 2; }
+      if (cn == gn) {
+        hp += 1;
+        ck = hp < EV_PICK_K ? l_key[lane][hp] : 0ull;
+        cn = hp < EV_PICK_K ? l_node[lane][hp] : -1;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < EV_PICK_K) {
+    *reinterpret_cast<volatile int32_t *>(p.pick_node + threadIdx.x) = s_pick[threadIdx.x];
+    __threadfence_system();
   }
   __syncthreads();
   if (threadIdx.x == 0) {

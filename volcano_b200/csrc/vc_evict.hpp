@@ -75,6 +75,9 @@ struct EvictOp { int kind, task, node; };  // VC_OP_EVICT (task = running-task i
 // The device side as the control loop sees it
 struct Ranker {
   // rank every node for preemptor `t` under `mode`; then next() yields the candidate nodes in the action's order, -1 at the end
+  // optional: the preemptor the control loop will try next if the one passed to the coming begin() fails (the device may
+  // rank it ahead; a success in between voids that ranking)
+  std::function<void(int t, int mode)> hint = [](int, int) {};
   std::function<int(int t, int mode)> begin;     // returns 0 or a VC_E* code
   std::function<int(int *node)> next;
   std::function<int(int t, int node, const std::vector<int> &victims)> apply;

@@ -1742,7 +1742,8 @@ int ensure_evict_session(vc_snapshot *s) {
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
   const size_t o_off = take((N + 1) * 4), o_idx = take(B * 4), o_req = take(R * B * 8), o_kreq = take(K * B * 8),
                o_knz = take(K * B * 8), o_flags = take(B * 4), o_job = take(B * 4), o_ev = take(B), o_key = take(N * 8),
-               o_cand = take(N), o_prio = take(B * 4), o_jready = take(std::max<size_t>(J, 1) * 4), o_qover = take(std::max<size_t>(Q, 1));
+               o_cand = take(N), o_prio = take(B * 4), o_jready = take(std::max<size_t>(J, 1) * 4), o_qover = take(std::max<size_t>(Q, 1)),
+               o_key2 = take(N * 8), o_cand2 = take(N);  // second ranking scratch: the preemptor ranked one ahead
   if (off > s->d_ev_bytes) {
     if (s->d_ev) cudaFree(s->d_ev);
     s->d_ev = nullptr;
@@ -1750,6 +1751,7 @@ int ensure_evict_session(vc_snapshot *s) {
     s->d_ev_bytes = off;
   }
   if (!s->h_ev) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&s->h_ev), (EV_CMD_OFF + 2 + EV_MAX_VICTIMS) * 4, cudaHostAllocMapped));
+  (void)o_key2; (void)o_cand2;
   unsigned char *base = reinterpret_cast<unsigned char *>(s->d_ev);
   CUDA_TRY(cudaMemsetAsync(base, 0, off, s->stream));
   if (s->rt.n > 0) {
@@ -1786,7 +1788,8 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
   const size_t o_off = take((N + 1) * 4), o_idx = take(B * 4), o_req = take(R * B * 8), o_kreq = take(K * B * 8),
                o_knz = take(K * B * 8), o_flags = take(B * 4), o_job = take(B * 4), o_ev = take(B), o_key = take(N * 8),
-               o_cand = take(N), o_prio = take(B * 4), o_jready = take(std::max<size_t>(J, 1) * 4), o_qover = take(std::max<size_t>(Q, 1));
+               o_cand = take(N), o_prio = take(B * 4), o_jready = take(std::max<size_t>(J, 1) * 4), o_qover = take(std::max<size_t>(Q, 1)),
+               o_key2 = take(N * 8), o_cand2 = take(N);  // second ranking scratch: the preemptor ranked one ahead
   unsigned char *base = reinterpret_cast<unsigned char *>(s->d_ev);
   EvictParams p;
   std::memset(&p, 0, sizeof p);
@@ -1820,7 +1823,6 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
   int32_t *dev_h = nullptr;
   CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&dev_h), s->h_ev, 0));
   p.pick_node = dev_h; p.cmd = dev_h + EV_CMD_OFF;
-  volatile int32_t *h_pick = s->h_ev;
   int32_t *h_cmd = s->h_ev + EV_CMD_OFF;
   int launches = 0, cur_mode = 0;
   EvictTask et;
@@ -1845,20 +1847,61 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
   // the pick kernel stages the candidates' keys in shared memory when they fit (N * 8 bytes)
   size_t pick_smem = N * 8 <= 200 * 1024 ? N * 8 : 0;
   if (pick_smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_evict_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pick_smem));
-  int pick_seq = 0;
-  s->h_ev[EV_PICK_K] = 0;
-  double t_launch = 0.0, t_sync = 0.0;  // host time inside kernel launches / stream synchronisations (vc_stats.prof_cycles, us)
-  vch::Ranker rk;
-  rk.begin = [&](int t, int mode) -> int {
+  double t_launch = 0.0, t_sync = 0.0;  // host time inside kernel launches / waiting for a hand-out (vc_stats.prof_cycles, us)
+  // Two ranking scratch sets (candidate flags, keys, hand-out slots): while the host walks the candidates of one
+  // preemptor the device already ranks the one the control loop will most likely try next (rk.hint). Most preemptors fail,
+  // and a failed one leaves the session untouched, so the ranking made ahead is still exact; any eviction / pipeline /
+  // discard in between (`epoch`) voids it.
+  struct RankSet { unsigned long long *key; uint8_t *cand; int32_t *d_pick; volatile int32_t *h_pick; int seq; };
+  RankSet sets[2] = {{reinterpret_cast<unsigned long long *>(base + o_key), base + o_cand, dev_h, s->h_ev, 0},
+                     {reinterpret_cast<unsigned long long *>(base + o_key2), base + o_cand2, dev_h + (EV_PICK_K + 1),
+                      s->h_ev + (EV_PICK_K + 1), 0}};
+  s->h_ev[EV_PICK_K] = 0; s->h_ev[2 * EV_PICK_K + 1] = 0;
+  int cur = 0, hint_t = -1, hint_mode = 0, pref_t = -1, pref_mode = 0, n_ahead = 0, n_ahead_used = 0;
+  unsigned epoch = 0, pref_epoch = 0;
+  bool first_pending = false;  // the first hand-out of the preemptor under trial is launched but not consumed yet
+  auto with_set = [&](int k) { EvictParams q = p; q.key = sets[k].key; q.cand = sets[k].cand; q.pick_node = sets[k].d_pick; return q; };
+  auto launch_pick = [&](int k, int mode) -> int {
+    sets[k].seq += 1;
+    if (pick_smem) k_evict_pick<<<1, 1024, pick_smem, s->stream>>>(with_set(k), mode, sets[k].seq);
+    else k_evict_pick_big<<<1, 1024, 0, s->stream>>>(with_set(k), mode, 0, sets[k].seq);
+    launches++;
+    CUDA_TRY(cudaGetLastError());
+    return VC_OK;
+  };
+  auto launch_rank_pick = [&](int k, int t, int mode) -> int {
     stage(t, mode);
+    const double tl0 = now_ms();
+    if (R <= 8) k_evict_rank<16, 8><<<(unsigned)((N * 16 + 255) / 256), 256, 0, s->stream>>>(with_set(k), et);
+    else k_evict_rank<16, VC_MAX_DIMS><<<(unsigned)((N * 16 + 255) / 256), 256, 0, s->stream>>>(with_set(k), et);
+    launches++;
+    CUDA_TRY(cudaGetLastError());
+    const int rc2 = launch_pick(k, mode);
+    t_launch += now_ms() - tl0;
+    return rc2;
+  };
+  vch::Ranker rk;
+  rk.hint = [&](int t, int mode) { hint_t = t; hint_mode = mode; };
+  rk.begin = [&](int t, int mode) -> int {
     cur_mode = mode;
     pick_pos = pick_n = 0;
     if (N == 0) return VC_OK;
-    const double tl0 = now_ms();
-    k_evict_rank<<<(unsigned)((N * 32 + 255) / 256), 256, 0, s->stream>>>(p, et);
-    t_launch += now_ms() - tl0;
-    launches++;
-    CUDA_TRY(cudaGetLastError());
+    int rc2 = VC_OK;
+    if (pref_t == t && pref_mode == mode && pref_epoch == epoch) {
+      cur = 1 - cur;  // ranked ahead on a session state that still stands
+      n_ahead_used += 1;
+    } else if ((rc2 = launch_rank_pick(cur, t, mode))) {
+      return rc2;
+    }
+    pref_t = -1;
+    first_pending = true;
+    if (hint_t >= 0 && hint_t != t) {
+      if ((rc2 = launch_rank_pick(1 - cur, hint_t, hint_mode))) return rc2;
+      pref_t = hint_t; pref_mode = hint_mode; pref_epoch = epoch;
+      n_ahead += 1;
+    }
+    hint_t = -1;
+    stage(t, mode);  // `et` describes the preemptor under trial again
     return VC_OK;
   };
   rk.next = [&](int *node) -> int {
@@ -1866,21 +1909,24 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
     if (N == 0) return VC_OK;
     if (pick_pos >= pick_n) {
       if (pick_n > 0 && pick_n < EV_PICK_K) return VC_OK;  // the last batch was short: no candidate is left
-      const double tl0 = now_ms();
-      pick_seq += 1;
-      k_evict_pick<<<1, 1024, pick_smem, s->stream>>>(p, cur_mode, pick_smem ? 1 : 0, pick_seq);
+      if (!first_pending) {
+        const double tl0 = now_ms();
+        const int rc2 = launch_pick(cur, cur_mode);
+        t_launch += now_ms() - tl0;
+        if (rc2) return rc2;
+      }
+      first_pending = false;
       const double tl1 = now_ms();
-      launches++;
-      CUDA_TRY(cudaGetLastError());
-      // the kernel's last store is pick_seq into the mapped buffer: poll it (a stream query every few thousand spins
-      // turns a failed launch into an error instead of an endless wait)
-      for (unsigned spins = 0; h_pick[EV_PICK_K] != pick_seq; ++spins)
+      // the kernel's last store is its sequence number into the mapped buffer: poll it (a stream query every few thousand
+      // spins turns a failed launch into an error instead of an endless wait)
+      volatile int32_t *h_pick = sets[cur].h_pick;
+      for (unsigned spins = 0; h_pick[EV_PICK_K] != sets[cur].seq; ++spins)
         if ((spins & 0xfffu) == 0xfffu) {
           const cudaError_t qe = cudaStreamQuery(s->stream);
           if (qe != cudaSuccess && qe != cudaErrorNotReady) return fail(VC_ECUDA, "evict pick: %s", cudaGetErrorString(qe));
-          if (qe == cudaSuccess && h_pick[EV_PICK_K] != pick_seq) return fail(VC_ECUDA, "evict pick: completion word missing");
+          if (qe == cudaSuccess && h_pick[EV_PICK_K] != sets[cur].seq) return fail(VC_ECUDA, "evict pick: completion word missing");
         }
-      t_launch += tl1 - tl0; t_sync += now_ms() - tl1;
+      t_sync += now_ms() - tl1;
       pick_n = 0;
       for (int i = 0; i < EV_PICK_K && h_pick[i] >= 0; ++i) pick_buf[pick_n++] = h_pick[i];
       pick_pos = 0;
@@ -1891,6 +1937,7 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
   };
   auto apply_cmd = [&](int t, int node, const std::vector<int> &victims, int undo) -> int {
     if (victims.size() > EV_MAX_VICTIMS) return fail(VC_EUNSUPPORTED, "more than %d victims on one node", EV_MAX_VICTIMS);
+    epoch += 1;  // node rows, ReadyTaskNum, queue shares move: a ranking made ahead is void
     stage(t, cur_mode);
     CUDA_TRY(cudaStreamSynchronize(s->stream));  // the previous command has been consumed
     h_cmd[0] = node; h_cmd[1] = (int32_t)victims.size();
@@ -1952,6 +1999,7 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
         for (;;) {
           if (!e.job_starving(pj) || ptasks[pj].empty()) break;
           const int t = ptasks[pj].pop();
+          if (!ptasks[pj].empty()) rk.hint(ptasks[pj].h[0], EV_MODE_PREEMPT_INTER);  // tried next unless this one succeeds
           if ((rc = e.try_task(rk, stmt, t, EV_MODE_PREEMPT_INTER, &assigned))) return bail(rc);
         }
         if (e.job_pipelined(pj)) {
@@ -2005,6 +2053,7 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
           const int t = ptasks[job].pop();
           if (s->t_flags[t] & VC_TASK_PREEMPT_NEVER) continue;     // reclaim.go:140-143
           if (!e.gate(VC_EN_PREEMPTIVE, q, t)) continue;           // ssn.Preemptive, reclaim.go:145-148
+          if (!ptasks[job].empty()) rk.hint(ptasks[job].h[0], EV_MODE_RECLAIM);
           bool assigned = false;
           if ((rc = e.try_task(rk, stmt, t, EV_MODE_RECLAIM, &assigned))) return bail(rc);
         }
@@ -2024,6 +2073,8 @@ int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
   r->stats.n_steps = launches;
   r->stats.prof_cycles[0] = (int64_t)(t_launch * 1e3);  // microseconds of host time in launches / in synchronisations
   r->stats.prof_cycles[1] = (int64_t)(t_sync * 1e3);
+  r->stats.prof_cycles[2] = n_ahead;       // preemptors ranked one ahead / of those, how many rankings were used
+  r->stats.prof_cycles[3] = n_ahead_used;
   *out = r;
   return VC_OK;
 }
