@@ -309,6 +309,19 @@ def multi_gpu_arm(args, rank, world, local):
                     "note": "N independent clusters, one per GPU (weak scaling, no data-path exchange) - not the headline"}
     except Exception as ex:
         replicas = {"error": str(ex)}
+    # ---- parity of the multi-GPU session: rank 0 runs the SAME cluster on its GPU alone (the arm bench.py checks against the
+    #      CPU port at N=1) and compares every decision, visit and fit error ---------------------------------------------------
+    same = None
+    if rank == 0:
+        try:
+            e1 = engine.Engine(snap, device=local)
+            e1.upload()
+            r1 = e1.allocate()
+            e1.close()
+            same = bool(np.array_equal(r1.decisions, last.decisions) and np.array_equal(r1.visits, last.visits) and
+                        np.array_equal(r1.fit_errors, last.fit_errors))
+        except Exception as ex:
+            same = "error: %s" % ex
     if rank == 0:
         line = {
             "metric": METRIC, "value": placed / t_dev, "unit": "pods/s", "n_gpus": world, "steps": args.steps,
@@ -316,6 +329,9 @@ def multi_gpu_arm(args, rank, world, local):
             "cycle_ms_p50": statistics.median(dev_ms), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.workload, world),
             "sweeps_per_step": n_steps / args.steps,
+            "placements_identical": same,
+            "parity": {"placements_identical": same, "against": "the same session on one GPU (decisions, scores, visits, fit errors "
+                       "bit-equal); that arm is compared with the CPU port by the N=1 run"},
             "e2e": {"value": e2e_placed / t_e2e, "unit": "pods/s", "h2d_bytes_per_step": int(h2d) * world,
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps,
                     "note": "the snapshot is uploaded to every rank (h2d counts all of them); decisions come back from rank 0"},
