@@ -107,6 +107,7 @@ func signature(e *session) string {
 	}
 	for _, t := range e.tasks {
 		mix(string(t.UID))
+		mix(t.Pod.Status.NominatedNodeName) // a new nomination is a new session for the device
 	}
 	for _, j := range e.jobs {
 		mix(string(j.UID))
@@ -259,6 +260,10 @@ func openCycle(ssn *framework.Session) bool {
 	rt := e.cRunning()
 	if rc := C.vc_snapshot_set_running(cur.snap, &rt, ptrU(e.tFlags)); rc != 0 {
 		fail("running tasks")
+		return false
+	}
+	if rc := C.vc_snapshot_set_nominated(cur.snap, ptrI(e.nominated)); rc != 0 { // nil clears the list
+		fail("nominated nodes")
 		return false
 	}
 	nd, tk, cl, jb, qu := e.cNodes(), e.t.c(), e.cClasses(), e.cJobs(), e.cQueues()

@@ -52,6 +52,7 @@ type session struct {
 	conf C.vc_conf
 
 	outOfScope string // non-empty: a feature the device path does not model; the shim runs the stock action instead
+	nominated  []int32 // per pending task: index of Pod.Status.NominatedNodeName in ssn.NodeList, -1 none (allocate.go:624-634)
 
 	// vc_nodes
 	nAlloc, nIdle, nUsed, nRel, nPip, nKAlloc, nKReq, nKNz []float64
@@ -491,6 +492,20 @@ func encodeSession(ssn *framework.Session, enqueueConfigured bool) *session {
 	nodeIndex := map[string]int{}
 	for i, n := range e.nodes {
 		nodeIndex[n.Name] = i
+	}
+	// Pod.Status.NominatedNodeName -> index in ssn.NodeList (allocate.go:626-627: a name outside ssn.Nodes counts as none)
+	for i, t := range e.tasks {
+		if name := t.Pod.Status.NominatedNodeName; len(name) > 0 {
+			if e.nominated == nil {
+				e.nominated = make([]int32, len(e.tasks))
+				for k := range e.nominated {
+					e.nominated[k] = -1
+				}
+			}
+			if ni, ok := nodeIndex[name]; ok {
+				e.nominated[i] = int32(ni)
+			}
+		}
 	}
 	e.rt.node, e.rt.flags = make([]int32, len(e.runTasks)), make([]uint32, len(e.runTasks))
 	for i, t := range e.runTasks {

@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define VC_ABI_VERSION 4
+#define VC_ABI_VERSION 5
 #define VC_MAX_DIMS 16   /* R  */
 #define VC_MAX_KDIMS 4   /* dims seen by the upstream kube-scheduler scorers (cpu, memory, nvidia.com/gpu, ...) */
 #define VC_MAX_WORDS 4   /* 64-bit words per label / taint bitset */
@@ -390,6 +390,14 @@ int vc_snapshot_set_topology(vc_snapshot *s, const vc_hypernodes *topo);
    vc_dims.n_tasks (allocate skips them, allocate.go:255-271) but stay counted in vc_jobs.pending_besteffort. The list is
    copied; it stays in effect for later uploads of this snapshot until replaced (n_tasks = 0 clears it). */
 int vc_snapshot_set_backfill(vc_snapshot *s, int32_t n_tasks, const vc_tasks *tasks);
+
+/* Optional, before vc_snapshot_upload: Pod.Status.NominatedNodeName of the pending tasks (set by a preemption of an earlier
+   cycle) as node indices, [vc_dims.n_tasks], -1 = none or a node that is not in the session. allocate tries such a node first
+   (actions/allocate/allocate.go:624-634): if InitResreq <= its FutureIdle, ph.PredicateNodes runs on that one node, and a pass
+   makes it the task's only candidate. NULL clears the list. Sessions that carry a nominated task run on the general commit
+   kernel; vc_preempt_run / vc_reclaim_run refuse them (taskEligibleToPreempt's nominated-node rules, preempt.go:436-470, are
+   not modelled). The list is copied and stays in effect for later uploads until replaced. */
+int vc_snapshot_set_nominated(vc_snapshot *s, const int32_t *nominated_node);
 
 /* Optional, before vc_snapshot_upload: the tasks that occupy nodes (victim candidates of preempt / reclaim) and,
    per pending task of vc_tasks, VC_TASK_* flags (task_flags may be NULL = all zero). Copied; stays in effect for

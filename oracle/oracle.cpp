@@ -337,6 +337,7 @@ struct Session {
   std::vector<int32_t> fit_errors;
   int64_t sweeps = 0;
   int64_t last_processed_node_index = 0;  // util/scheduler_helper.go:50
+  std::vector<int32_t> t_nominated;       // [T_alloc] node of Pod.Status.NominatedNodeName or -1; empty: none
   Pool *pool = nullptr;
   ~Session() { delete pool; }
 };
@@ -1359,7 +1360,22 @@ bool allocate_resources_for_tasks(Session &s, int j, GoHeap &tasks, std::vector<
       continue;
     }
     // ssn.PrePredicateFn: nil for pods in scope (predicates PreFilter skip/ok; proportion state clone)
-    predicate_nodes(s, ph, t, feasible);
+    // Pod.Status.NominatedNodeName, allocate.go:624-634: the nominated node first, alone, when InitResreq <= its FutureIdle
+    feasible.clear();
+    const int nom = (!s.t_nominated.empty() && t < (int)s.t_nominated.size()) ? s.t_nominated[t] : -1;
+    if (nom >= 0 && fits_future_idle(s, t, nom)) {
+      // ph.PredicateNodes(task, []*api.NodeInfo{nominatedNodeInfo}, ...), util/predicate_helper.go:43-140 on a one-node list
+      const int lr = r - ph.role_base;
+      const bool enable_cache = s.conf.enable_predicate_error_cache != 0 && !(s.r_flags[r] & VC_ROLE_EMPTY_NAME);
+      if (ph.node_err[lr].empty()) ph.node_err[lr].assign(s.N, 0);
+      s.sweeps++;
+      if (!(enable_cache && ph.exists[lr] && ph.node_err[lr][nom])) {
+        if (predicate(s, t, nom)) feasible.push_back(nom);
+        else { ph.node_err[lr][nom] = 1; ph.exists[lr] = 1; }
+      }
+      s.last_processed_node_index = 0;  // (startIndex + processedNodes) % allNodes with allNodes = 1 (:135-136)
+    }
+    if (feasible.empty()) predicate_nodes(s, ph, t, feasible);
     if (feasible.empty()) {
       s.fit_errors.push_back(t);
       s.r_failed[r] = 1;
@@ -2221,6 +2237,14 @@ int vco_session_set_backfill(void *h, int32_t n, const vc_tasks *bt) {
 }
 int vco_backfill(void *h) { return backfill_execute(*(Session *)h); }
 // vc_snapshot_set_running for the oracle: node.Tasks entries are appended to the session's task arrays
+// Pod.Status.NominatedNodeName of the pending tasks as node indices (-1 none); mirrors vc_snapshot_set_nominated
+int vco_session_set_nominated(void *h, const int32_t *nominated_node) {
+  Session &s = *(Session *)h;
+  s.t_nominated.clear();
+  if (nominated_node) s.t_nominated.assign(nominated_node, nominated_node + s.T_alloc);
+  return VC_OK;
+}
+
 int vco_session_set_running(void *h, const vc_running_tasks *rt, const uint32_t *task_flags) {
   Session &s = *(Session *)h;
   if (s.T_run0 >= 0) return VC_EINVAL;

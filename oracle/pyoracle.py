@@ -131,6 +131,10 @@ class OracleSession:
         bt = snap.backfill_tasks()
         if bt is not None and L.vco_session_set_backfill(self.h, snap.B, C.byref(bt)) != 0:
             raise RuntimeError("oracle set_backfill failed")
+        nom = getattr(snap, "t_nominated", None)
+        if nom is not None and snap.T and (nom >= 0).any():
+            L.vco_session_set_nominated.argtypes = [_vp, C.POINTER(C.c_int32)]
+            L.vco_session_set_nominated(self.h, np.ascontiguousarray(nom, np.int32).ctypes.data_as(C.POINTER(C.c_int32)))
         rt = snap.running_tasks()
         if rt is not None or snap.t_flags.any():
             tf = snap.t_flags.ctypes.data_as(C.POINTER(C.c_uint32)) if snap.T else None

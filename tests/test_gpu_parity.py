@@ -505,3 +505,23 @@ def test_cfg5_cycle_vs_oracle(gpu, oracle_engine):
     _assert_same_evict(res.preempt, ref.preempt)
     _assert_same_evict(res.reclaim, ref.reclaim)
     assert (ref.preempt.decisions["kind"] == 2).sum() + (ref.reclaim.decisions["kind"] == 2).sum() > 10
+
+
+def test_nominated_node_vs_oracle(gpu, oracle_engine):
+    """Pod.Status.NominatedNodeName (actions/allocate/allocate.go:624-634): the nominated node is tried first, alone; parity
+    with the oracle in the full-evaluation mode and with feasible-node sampling (where the one-node PredicateNodes call
+    resets util.lastProcessedNodeIndex), on the general commit kernel such sessions take."""
+    from tests.test_oracle_golden import _nominated_cluster
+    for args in (("n2",), ("n0", "8"), ("gone",), ("n2", "4", 34), ("n1", "4", 67)):
+        tc = _nominated_cluster(*args)
+        res = gpu.gpu_engine(tc.snap)
+        ref = oracle_engine(tc.snap)
+        _assert_same(res, ref)
+        if (tc.snap.t_nominated >= 0).any():
+            assert res.stats["commit_kernel"] == 0  # VC_KERNEL_GENERAL
+        from oracle.pyoracle import OracleSession
+        from oracle import pyoracle
+        o = OracleSession(tc.snap, threads=1)
+        o.allocate()
+        assert res.stats["last_processed_node_index"] == pyoracle.lib().vco_last_processed_node_index(o.h), args
+        o.close()

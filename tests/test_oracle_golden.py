@@ -412,3 +412,60 @@ def test_predicate_nodes_error_cache_goldens():
     nodes, cache, exists = o.predicate_nodes(0)
     o.close()
     assert list(nodes) == [0] and not exists and list(cache) == [0]
+
+
+def _nominated_cluster(nominated, node0_free="4", mode_pct=None):
+    """Two nodes: n0 nearly full (binpack prefers it), n1 empty. One pending pod of 1 cpu with a NominatedNodeName."""
+    from volcano_b200.api import BuildNode, BuildPod, BuildPodGroup, BuildQueue, BuildResourceList
+    from volcano_b200.snapshot import PluginOption
+    from volcano_b200.uthelper import TestCommonStruct
+    nodes = [BuildNode("n0", BuildResourceList("8", "16Gi", ("pods", "10"))), BuildNode("n1", BuildResourceList("8", "16Gi", ("pods", "10"))),
+             BuildNode("n2", BuildResourceList("8", "16Gi", ("pods", "10")))]
+    pods = [BuildPod("c1", "r0", "n0", "Running", BuildResourceList(node0_free, "1Gi"), "pgr"),
+            BuildPod("c1", "p0", "", "Pending", BuildResourceList("1", "1Gi"), "pg1"),
+            BuildPod("c1", "p1", "", "Pending", BuildResourceList("1", "1Gi"), "pg1")]
+    pods[1].nominated_node_name = nominated
+    tc = TestCommonStruct(Name="nominated", Nodes=nodes, Pods=pods, Queues=[BuildQueue("q1", 1, None)],
+                          PodGroups=[BuildPodGroup("pgr", "c1", "q1", 1), BuildPodGroup("pg1", "c1", "q1", 1)])
+    tiers = [[PluginOption.make("priority", EnabledJobOrder=True, EnabledTaskOrder=True), PluginOption.make("gang", EnabledJobReady=True)],
+             [PluginOption.make("predicates", EnabledPredicate=True), PluginOption.make("binpack", EnabledNodeOrder=True)]]
+    kw = {} if mode_pct is None else dict(percentage_nodes_to_find=mode_pct, min_nodes_to_find=1, last_processed_node_index=2)
+    tc.RegisterSession(tiers, **kw)
+    return tc
+
+
+def test_nominated_node_is_tried_first(oracle_engine):
+    """actions/allocate/allocate.go:624-634: a pending pod with Status.NominatedNodeName goes to that node when its request fits
+    the node's FutureIdle and the predicates pass there - whatever the other nodes would score; otherwise the search over all
+    nodes decides. (The reference has no unit test of this branch; the expectations restate the code.)"""
+    # binpack alone would send both pods to n0 (4 of 8 cpu used); p0 is nominated to the empty n2
+    tc = _nominated_cluster("n2")
+    tc.Run(oracle_engine)
+    assert tc.binds["c1/p0"] == "n2" and tc.binds["c1/p1"] == "n0"
+    d = tc.result.decisions
+    assert d["score"][list(d["task"]).index(tc.snap.task_keys.index("c1/p0"))] == 0.0  # a single candidate is not scored
+    # nominated node without room (7 of 8 cpu used, the pod asks 1 cpu + ... fits; make it 8): falls back to the search
+    tc = _nominated_cluster("n0", node0_free="8")
+    tc.Run(oracle_engine)
+    assert tc.binds["c1/p0"] in ("n1", "n2")
+    # a nominated node that is not in the session counts as none
+    tc = _nominated_cluster("gone")
+    tc.Run(oracle_engine)
+    assert tc.binds["c1/p0"] == "n0"
+    assert (tc.snap.t_nominated == -1).all()
+
+
+def test_nominated_node_resets_the_rotating_index(oracle_engine):
+    """ph.PredicateNodes on the one-node list stores (start + processed) % 1 = 0 into util.lastProcessedNodeIndex
+    (util/predicate_helper.go:135-136): with feasible-node sampling the next task's scan starts at node 0."""
+    from oracle.pyoracle import OracleSession
+    tc = _nominated_cluster("n2", mode_pct=34)  # 34 % of 3 nodes -> one feasible node per task, scan starts at index 2
+    o = OracleSession(tc.snap, threads=1)
+    dec, vis, fe = o.allocate()
+    from oracle import pyoracle
+    last = pyoracle.lib().vco_last_processed_node_index(o.h)
+    o.close()
+    names = {tc.snap.task_keys[t]: tc.snap.node_names[n] for t, n in zip(dec["task"], dec["node"])}
+    assert names["c1/p0"] == "n2"       # the nominated node
+    assert names["c1/p1"] == "n0"       # scanned from index 0 after the reset, first feasible node
+    assert last == 1

@@ -25,6 +25,8 @@ def make_case(seed, big=False):
     rnd = random.Random(seed)
     rnd2 = random.Random(seed * 7919 + 13)  # later additions draw from their own stream: earlier seeds keep their clusters
     mix_names = rnd2.random() < 0.3  # jobs mixing pods with and without a numeric name index (CompareTask is intransitive there)
+    rnd3 = random.Random(seed * 104729 + 7)  # a third stream: nominated nodes (one case in eight)
+    nominate = rnd3.random() < 0.125
     be_p = rnd.choice([0.05, 0.05, 0.3])  # share of BestEffort pods (the backfill action's tasks)
     n_nodes = rnd.randint(3, 40) if not big else rnd.randint(40, 400)
     nodes = []
@@ -127,6 +129,8 @@ def make_case(seed, big=False):
                 p.priority = rnd.randint(0, 3)
             if rnd.random() < be_p:
                 p.requests = {}  # BestEffort: stays out of the allocate action, counts as pending best-effort
+            if nominate and not running and rnd3.random() < 0.3:  # Status.NominatedNodeName, allocate.go:624-634
+                p.nominated_node_name = rnd3.choice(nodes).name if rnd3.random() < 0.9 else "no-such-node"
             pods.append(p)
     # plugin set
     names = ["priority", "gang", "drf", "predicates", "proportion", "nodeorder", "binpack", "tdm", "network-topology-aware"]

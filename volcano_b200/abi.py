@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-VC_ABI_VERSION = 4
+VC_ABI_VERSION = 5
 VC_MAX_DIMS = 16
 VC_MAX_KDIMS = 4
 VC_MAX_WORDS = 4
@@ -239,6 +239,7 @@ SYMBOLS = {
     "vc_snapshot_set_topology": (C.c_int, [_vp, C.POINTER(vc_hypernodes)]),
     "vc_snapshot_set_backfill": (C.c_int, [_vp, C.c_int32, C.POINTER(vc_tasks)]),
     "vc_snapshot_set_running": (C.c_int, [_vp, C.POINTER(vc_running_tasks), C.POINTER(C.c_uint32)]),
+    "vc_snapshot_set_nominated": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "vc_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_void_p]),
     "vc_comm_attach": (C.c_int, [_vp, C.c_void_p]),
     "vc_comm_prepare": (C.c_int, [_vp]),

@@ -187,6 +187,7 @@ class Pod:
     revocable_zone: str = ""  # annotation volcano.sh/revocable-zone
     preemption_policy: str = ""    # pod.Spec.PreemptionPolicy ("Never": the pod never preempts / reclaims)
     priority_class_name: str = ""  # pod.Spec.PriorityClassName (conformance: system-*-critical pods are never evicted)
+    nominated_node_name: str = ""  # pod.Status.NominatedNodeName (left by a preemption of an earlier cycle, allocate.go:624-634)
 
     def __post_init__(self):
         if not self.uid:

@@ -42,6 +42,7 @@ struct K2Params {
   const uint32_t *req_has;
   const int32_t *t_class, *t_role;
   const int32_t *task_order, *job_task_off;
+  const int32_t *nominated;  // [T] node index of Pod.Status.NominatedNodeName, -1 none; nullptr: no task has one
   // jobs
   const int32_t *j_queue, *j_min, *j_ntasks, *j_pbe, *j_taskmintotal, *j_roleoff, *j_prio, *j_ready0, *j_waiting0;
   const uint32_t *j_flags, *j_rank;
@@ -1016,7 +1017,46 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
       // ---- feasible-node sampling, util/predicate_helper.go:43-140 in its single-worker reading: scan the nodes in
       // index order starting at lastProcessedNodeIndex, stop after `to_find` feasible ones; nodes skipped through the
       // error cache count as processed, predicate failures of processed nodes enter the cache ----
+      // ---- Pod.Status.NominatedNodeName (set by a preemption of an earlier cycle), allocate.go:624-634: when the node is in
+      //      the session and InitResreq <= its FutureIdle, ph.PredicateNodes runs on that ONE node first; a pass makes it the
+      //      only candidate (taken without scoring), anything else falls back to the search over all nodes. With
+      //      feasible-node sampling that call also leaves util.lastProcessedNodeIndex at (start + processed) % 1 = 0. ----
+      bool nom_hit = false;
+      const int nom = p.nominated ? p.nominated[t] : -1;
+      if (nom >= 0) {
+        if (tid < 32) {  // warp 0: the owner lane evaluates, everybody exchanges
+          Local l;
+          local_init(l);
+          const int i = nom - nbase;
+          if (lane == 0 && i >= 0 && i < nmine) {
+            SmemNodeView nv{sn, i};
+            if (fit_category_t<FUT>(R, trec, nv) != 2) {  // task.InitResreq.LessEqual(nominatedNodeInfo.FutureIdle(), Zero)
+              l.proc = 1;                                   // PredicateNodes is called
+              if (!(use_cache && ((sn.nerr[i] >> rl) & 1ull))) {
+                int cat; bool ho; double od;
+                verdict(i, cs_row[i], &cat, &ho, &od);
+                if (cat == 2) { if (use_cache) sn.nerr[i] |= (1ull << rl); }
+                else { l.cnt[cat] = 1; l.node[cat] = nom; l.score[cat] = 0.0; }
+              }
+            }
+          }
+          local_warp_reduce<FUT>(l);
+          l.proc = (int)__reduce_max_sync(0xffffffffu, (unsigned)l.proc);
+          const unsigned seq = S.seq + 1;
+          __syncwarp();
+          Local g = exchange<true>(p, l, seq);  // the full record: it carries `proc` (the tags of the two record formats cannot be mistaken for each other)
+          if (lane == 0) {
+            S.seq = seq;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) { S.cnt[k] = g.cnt[k]; S.best_node[k] = g.node[k]; S.best_score[k] = g.score[k]; S.max_soft[k] = 0; }
+            if (g.proc > 0) S.last_idx = 0;  // (start + processedNodes) % len([nominated]) whatever the sampling mode
+          }
+        }
+        __syncthreads();
+        nom_hit = S.cnt[0] + S.cnt[1] > 0;
+      }
       const bool sampling = SAMP && c.to_find > 0;
+      if (!nom_hit) {
       if (SAMP && sampling) {
         const int start = S.last_idx, Kf = c.to_find;
         const int rows = (cap + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -1177,6 +1217,7 @@ __global__ void __launch_bounds__(256, 1) k_commit(K2Params p) {
         g_soft1 = S.max_soft[1];
         if (S.cnt[0] + S.cnt[1] == 0) break;
       }
+      }  // !nom_hit
       if (tid == 0) S.n_steps += 1;
 
       if (S.cnt[0] + S.cnt[1] == 0) {  // no feasible node, allocate.go:639-659

@@ -248,6 +248,10 @@ struct vc_snapshot {
   bool alloc_ran = false, bf_ran = false;
   int last_idx_cur = 0;   // util.lastProcessedNodeIndex as the last action of the cycle left it
   int *d_dbg = nullptr;
+  std::vector<int32_t> h_nominated;  // [T] node index per task or -1 (vc_snapshot_set_nominated); empty: none
+  bool any_nominated = false;
+  int32_t *d_nominated = nullptr;
+  size_t d_nominated_cap = 0;
   bool fut_rows = false;  // Releasing / Pipelined resources present at open
   bool all_pure = true;  // every job's named roles map to one (class, request) group each: the role-keyed error cache is a no-op
   bool rows_integral = false;  // every quantity a placement adds to / subtracts from a node row is integer-valued
@@ -378,7 +382,8 @@ void choose_geometry(vc_snapshot *s) {
   // and PreferNoSchedule taints under the TaintToleration batch scorer its SOFT instance
   // and feasible-node sampling its SAMP instance (one GPU, no normalising scorer, no job that needs the error cache)
   const bool samp_ok = s->dc.to_find == 0 || (s->world <= 1 && !s->dc.soft_active && (s->all_pure || !s->dc.enable_ecache));
-  s->fast = !s->topo_any && !s->dc.nta_on && samp_ok && R <= 8 && K <= VC_MAX_KDIMS && !g_tun.commit_generic;
+  // (a session with nominated tasks takes the general kernel: allocate.go:624-634 is implemented there)
+  s->fast = !s->topo_any && !s->dc.nta_on && samp_ok && !s->any_nominated && R <= 8 && K <= VC_MAX_KDIMS && !g_tun.commit_generic;
   if (s->fast) {
     if (g_tun.commit_threads <= 0) s->block = 256;  // 7 worker warps: a run's node states are evaluated two per warp
     size_t rows = 3 * (size_t)R + (s->dc.has_future ? 2 * (size_t)R : 0) + 2 * (size_t)K + 2 + 1;
@@ -480,7 +485,7 @@ void vc_snapshot_destroy(vc_snapshot *s) {
     if (r != s->rank && s->peer_comm[r]) cudaIpcCloseMemHandle(s->peer_comm[r]);
   if (s->comm) cudaFree(s->comm);
   void *dptrs[] = {s->in.dev, s->cstat, s->w_idle, s->w_used, s->w_pip, s->w_kreq, s->w_knz, s->w_pod_count,
-                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_score_log, s->d_prof, s->d_wait, s->d_dbg, s->d_decisions, s->d_visits, s->d_fit, s->d_counters, s->d_bf, s->w_rel, s->d_ev};
+                   s->rep_i32, s->rep_f64, s->rep_heap, s->rep_hn_used, s->rep_placed, s->d_job_alloc, s->hn_score, s->mbox, s->ring, s->d_score_log, s->d_prof, s->d_wait, s->d_dbg, s->d_nominated, s->d_decisions, s->d_visits, s->d_fit, s->d_counters, s->d_bf, s->w_rel, s->d_ev};
   for (void *p : dptrs) if (p) cudaFree(p);
   void *hptrs[] = {s->in.pin, s->h_decisions, s->h_visits, s->h_fit, s->h_counters, s->h_ev, s->delta_pin};
   if (s->delta_dev) cudaFree(s->delta_dev);
@@ -967,6 +972,24 @@ int vc_snapshot_upload(vc_snapshot *s, const vc_nodes *nd, const vc_tasks *tk, c
     for (size_t d = 0; d < R && d < FAST_R; ++d) r.des[d] = q_des[d * Q + q];
   }
 
+  // nominated nodes of the pending tasks (vc_snapshot_set_nominated): range check, device copy
+  s->any_nominated = false;
+  if (!s->h_nominated.empty()) {
+    if (s->h_nominated.size() != T) return fail(VC_EINVAL, "nominated-node list: %zu entries for %zu tasks", s->h_nominated.size(), T);
+    for (size_t t = 0; t < T; ++t) {
+      if (s->h_nominated[t] >= (int32_t)N) return fail(VC_EINVAL, "task %zu: nominated node %d out of range", t, s->h_nominated[t]);
+      if (s->h_nominated[t] >= 0) s->any_nominated = true;
+    }
+    if (s->any_nominated) {
+      if (T > s->d_nominated_cap) {
+        if (s->d_nominated) cudaFree(s->d_nominated);
+        s->d_nominated = nullptr;
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&s->d_nominated), T * 4));
+        s->d_nominated_cap = T;
+      }
+      CUDA_TRY(cudaMemcpyAsync(s->d_nominated, s->h_nominated.data(), T * 4, cudaMemcpyHostToDevice, s->stream));
+    }
+  }
   // network-topology-aware: hyperNodeResourceCache at open (network_topology_aware.go:106-125) and, for the
   // commit kernel, the hypernodes each CTA's node slice belongs to
   choose_geometry(s);
@@ -1441,6 +1464,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   p.req = s->t_req.d(s->in); p.tkreq = s->t_kreq.d(s->in); p.tknz = s->t_knz.d(s->in); p.req_has = s->t_has.d(s->in);
   p.t_class = s->t_class.d(s->in); p.t_role = s->t_role.d(s->in);
   p.task_order = s->task_order.d(s->in); p.job_task_off = s->job_task_off.d(s->in);
+  p.nominated = s->any_nominated ? s->d_nominated : nullptr;
   p.j_queue = s->j_queue.d(s->in); p.j_min = s->j_min.d(s->in); p.j_ntasks = s->j_ntasks.d(s->in);
   p.j_pbe = s->j_pbe.d(s->in); p.j_taskmintotal = s->j_taskmintotal.d(s->in); p.j_roleoff = s->j_roleoff.d(s->in);
   p.j_prio = s->j_prio.d(s->in); p.j_ready0 = s->j_ready0.d(s->in); p.j_waiting0 = s->j_waiting0.d(s->in);
@@ -1603,7 +1627,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   r->stats.d2h_bytes = 32 + (int64_t)n_dec * sizeof(vc_decision) + (int64_t)n_vis * sizeof(vc_visit) + (int64_t)n_fit * 4;
   r->stats.kernel_launches = 2;  // k_class_static + k_commit
   r->stats.n_steps = s->h_counters[3];
-  r->stats.last_processed_node_index = s->dc.to_find > 0 ? s->h_counters[4] : s->dc.last_idx0;
+  r->stats.last_processed_node_index = (s->dc.to_find > 0 || s->any_nominated) ? s->h_counters[4] : s->dc.last_idx0;
   r->stats.commit_kernel = s->fast ? VC_KERNEL_INCREMENTAL : VC_KERNEL_GENERAL;
   s->last_idx_cur = r->stats.last_processed_node_index;
   for (int k = 0; k < 8; ++k) r->stats.prof_cycles[k] = s->h_prof[k];
@@ -1775,6 +1799,8 @@ int ensure_evict_session(vc_snapshot *s) {
 int run_evict_action(vc_snapshot *s, bool reclaim, vc_result **out) {
   if (!s || !out) return fail(VC_EINVAL, "null argument");
   if (!s->uploaded) return fail(VC_EINVAL, "vc_snapshot_upload must precede the action");
+  if (s->any_nominated)
+    return fail(VC_EUNSUPPORTED, "preempt / reclaim: a pending task carries a NominatedNodeName (taskEligibleToPreempt's rules are not modelled)");
   const double t0 = now_ms();
   int rc = ensure_evict_session(s);
   if (rc) return rc;
@@ -2087,6 +2113,14 @@ int vc_reclaim_run(vc_snapshot *s, vc_result **out) { return run_evict_action(s,
 // ---------------------------------------------------------------------------------------
 // backfill (actions/backfill/backfill.go)
 // ---------------------------------------------------------------------------------------
+int vc_snapshot_set_nominated(vc_snapshot *s, const int32_t *nominated_node) {
+  if (!s) return fail(VC_EINVAL, "null snapshot");
+  s->uploaded = false;  // validated against the node table and shipped by the next upload
+  if (!nominated_node) { s->h_nominated.clear(); return VC_OK; }
+  s->h_nominated.assign(nominated_node, nominated_node + s->dims.n_tasks);
+  return VC_OK;
+}
+
 int vc_snapshot_set_backfill(vc_snapshot *s, int32_t n_tasks, const vc_tasks *bt) {
   if (!s) return fail(VC_EINVAL, "null snapshot");
   if (n_tasks < 0 || (n_tasks > 0 && !bt)) return fail(VC_EINVAL, "backfill task list: negative size / null pointer");

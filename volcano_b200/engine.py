@@ -94,6 +94,9 @@ class Engine:
         rt = s.running_tasks()  # node.Tasks (victim candidates of preempt / reclaim) + per-task flags; restated on every upload
         tf = s.t_flags.ctypes.data_as(C.POINTER(C.c_uint32)) if s.T else None
         _check(self.L.vc_snapshot_set_running(self.h, C.byref(rt) if rt is not None else None, tf))
+        nom = getattr(s, "t_nominated", None)  # Pod.Status.NominatedNodeName per pending task; restated on every upload
+        has_nom = nom is not None and s.T and bool((nom >= 0).any())
+        _check(self.L.vc_snapshot_set_nominated(self.h, nom.ctypes.data_as(C.POINTER(C.c_int32)) if has_nom else None))
         _check(self.L.vc_snapshot_upload(self.h, C.byref(n), C.byref(t), C.byref(c), C.byref(j), C.byref(q),
                                          C.byref(s.conf)))
         self._uploaded = True

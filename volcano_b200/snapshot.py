@@ -205,6 +205,7 @@ class Snapshot:
         self.B = B  # BestEffort pending tasks (the backfill action's tasks; not part of T)
         self.RT = 0  # tasks that occupy nodes (victim candidates of preempt / reclaim), see set_running
         self.t_flags = np.zeros(T, np.uint32)  # VC_TASK_* per pending task
+        self.t_nominated = np.full(T, -1, np.int32)  # node index of Pod.Status.NominatedNodeName per pending task, -1 none
         self.Wl, self.Wt, self.Z, self.pods_dim = Wl, Wt, Z, pods_dim
         f8, i4, i8, u4, u8 = np.float64, np.int32, np.int64, np.uint32, np.uint64
         # nodes
@@ -845,6 +846,8 @@ def encode_cluster(nodes: Sequence[Node], pods: Sequence[Pod], podgroups: Sequen
     for t, p in enumerate(task_pods):
         if p.preemption_policy == "Never":
             s.t_flags[t] |= abi.VC_TASK_PREEMPT_NEVER
+        if p.nominated_node_name:  # a node that is not in the session counts as none (allocate.go:627 `ok`)
+            s.t_nominated[t] = nidx.get(p.nominated_node_name, -1)
     # node.Tasks: the pods that can become victims (api.PreemptableStatus: Bound | Running, api/helpers.go:70-77)
     run_pods = [p for p in pods if p.node_name in nidx and get_task_status(p) in ("Running", "Bound")]
     s.set_running(len(run_pods))
