@@ -101,7 +101,8 @@ struct FastParams {  // extra kernel arguments of the fast kernel
   const QueueStatic *qstat;
   const double *q_share0;  // [Q]
   int run_max;             // 1: one placement per publication; RUN_MAX: run-length batches (rows integer-valued)
-  double *score_log;       // [T] score of the chosen node per placement attempt (written by the owner CTA of a run)
+  uint4 *score_log;        // [T] per placement attempt inside a run: (score bits lo, hi, attempt index + 1, 0), written by the
+                           // owner CTA as one 16-byte store and polled by CTA 0 - the tag makes a fence before the record unnecessary
 };
 
 struct FastSmem {
@@ -941,9 +942,9 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
     const double sc_m = __shfl_sync(0xffffffffu, sc, m - 1);
     const int cat_m = __shfl_sync(0xffffffffu, cat, m - 1);
     // scores of placements 1..m-1 of the run (placement j is chosen in state j-1 ... of the row BEFORE it: lane j-1)
-    if (lane < m - 1) {  // visible before the record below (system scope: the reader may sit on another GPU)
-      fp.score_log[F.run_att0 + 1 + lane] = sc;
-      if (p.n_ranks > 1) __threadfence_system(); else __threadfence();
+    if (lane < m - 1) {  // self-validating entries (the reader, CTA 0 of rank 0, polls the tag): no fence on the owner's path
+      const unsigned long long sb = (unsigned long long)__double_as_longlong(sc);
+      mbox_store(fp.score_log + F.run_att0 + 1 + lane, make_uint4((unsigned)sb, (unsigned)(sb >> 32), (unsigned)(F.run_att0 + 2 + lane), 0u));
     }
     // the remaining m-1 placements on the row (Statement.Allocate: node_info.go:467-471, predicates.go:254-255)
     const double km = (double)(m - 1);
@@ -1888,12 +1889,21 @@ __global__ void __launch_bounds__(256, 1) k_commit_fast(K2Params p, FastParams f
           resolve();
           extra = pub_m - 1;
           if (extra > 0) {
-            if (out_cta && cnt_run != 1) __threadfence();  // the score log entries precede the record that was just read
             if (lane < extra) {
               const int tj = mk.x;  // lane l: task l+1 of the run
               const int k = n_ops + lane;
               ops[k * 3 + 0] = tj; ops[k * 3 + 1] = best; ops[k * 3 + 2] = VC_OP_ALLOCATE;
-              if (out_cta) ops_score[k] = cnt_run == 1 ? 0.0 : __ldcg(&fp.score_log[att0 + 1 + lane]);
+              if (out_cta) {
+                double sv = 0.0;
+                if (cnt_run != 1) {  // the owner's entry for this attempt (usually there already: it was stored before the record)
+                  uint4 v;
+                  unsigned spins = 0;
+                  const long long t0w = clock64();
+                  do { v = mbox_load(fp.score_log + att0 + 1 + lane); PEER_WATCHDOG(spins, t0w); } while (v.z != (unsigned)(att0 + 2 + lane));
+                  sv = __longlong_as_double((long long)((unsigned long long)v.x | ((unsigned long long)v.y << 32)));
+                }
+                ops_score[k] = sv;
+              }
             }
             if (lane == 0) { S.r_pending[rl] -= extra; S.r_occ[rl] += extra; }
             ready += extra; n_ops += extra; n_att += extra; cursor += extra; n_steps += extra; n_incr += extra;

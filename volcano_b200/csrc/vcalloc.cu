@@ -173,7 +173,7 @@ struct vc_snapshot {
   int fast_ready_word = 0, fast_ready_shift = 0, fast_share_on = 0, heap_total = 0, heap_in_smem = 0;
   bool fast = false;
   uint4 *ring = nullptr;
-  double *d_score_log = nullptr;  // [T] chosen-node score per placement attempt of the run-length batches
+  uint4 *d_score_log = nullptr;   // [T] tagged chosen-node score per placement attempt of the run-length batches
   int last_full = 0, last_incr = 0;
   // ---- HyperNode tree (vc_snapshot_set_topology) ----
   bool has_topo = false;
@@ -272,7 +272,7 @@ struct vc_snapshot {
   int world = 1, rank = 0;
   int n_cta_total = 0;             // CTAs of all ranks (the exchange); n_cta stays this rank's grid
   unsigned char *comm = nullptr;   // this rank's slab: mailbox | ring | score log (cudaMalloc, exported over CUDA IPC)
-  size_t comm_bytes = 0, comm_mbox_bytes = 0, comm_ring_off = 0, comm_log_off = 0;
+  size_t comm_bytes = 0, comm_mbox_bytes = 0, comm_ring_off = 0, comm_log_off = 0, comm_bytes_all = 0;
   unsigned char *peer_comm[8] = {nullptr};  // every rank's slab as mapped into this process (own one included)
   bool comm_attached = false;
   // ---- incremental upload (vc_snapshot_update_nodes) ----
@@ -553,7 +553,8 @@ int vc_comm_create(vc_snapshot *s, int world, int rank, void *handle_out) {
   s->comm_mbox_bytes = mbox;
   s->comm_ring_off = (mbox + 255) & ~(size_t)255;
   s->comm_log_off = (s->comm_ring_off + ring + 255) & ~(size_t)255;
-  const size_t bytes = s->comm_log_off + (T + 64) * sizeof(double);
+  const size_t bytes = s->comm_log_off + (T + 64) * sizeof(uint4);
+  s->comm_bytes_all = bytes;
   if (!s->comm || s->comm_bytes < bytes) {
     if (s->comm) cudaFree(s->comm);
     s->comm = nullptr;
@@ -585,7 +586,7 @@ int vc_comm_attach(vc_snapshot *s, const void *handles) {
 
 int vc_comm_prepare(vc_snapshot *s) {
   if (!s || !s->comm) return fail(VC_EINVAL, "no communication slab (vc_comm_create)");
-  CUDA_TRY(cudaMemsetAsync(s->comm, 0, s->comm_log_off, s->stream));  // mailbox + ring; the score log needs no reset
+  CUDA_TRY(cudaMemsetAsync(s->comm, 0, s->comm_bytes_all, s->stream));  // mailbox + ring + score log (its entries are tagged by attempt index)
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   return VC_OK;
 }
@@ -1436,7 +1437,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   if (!s->d_prof) CUDA_TRY(cudaMalloc(&s->d_prof, 16 * sizeof(long long)));
   const size_t ring_bytes = sizeof(uint4) * RING_STRIDE * RING_DEPTH;
   if (!s->ring) CUDA_TRY(cudaMalloc(&s->ring, ring_bytes));
-  if (!s->d_score_log) CUDA_TRY(cudaMalloc(&s->d_score_log, (T + 64) * sizeof(double)));
+  if (!s->d_score_log) CUDA_TRY(cudaMalloc(&s->d_score_log, (T + 64) * sizeof(uint4)));
   if (!s->d_decisions) {
     CUDA_TRY(cudaMalloc(&s->d_decisions, std::max<size_t>(1, T) * sizeof(vc_decision)));
     CUDA_TRY(cudaMalloc(&s->d_visits, (T + J + 1) * sizeof(vc_visit)));
@@ -1538,7 +1539,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
       p.peer_mbox[r] = reinterpret_cast<uint4 *>(s->peer_comm[r]);
       p.peer_ring[r] = reinterpret_cast<uint4 *>(s->peer_comm[r] + s->comm_ring_off);
     }
-    fp.score_log = reinterpret_cast<double *>(s->peer_comm[0] + s->comm_log_off);
+    fp.score_log = reinterpret_cast<uint4 *>(s->peer_comm[0] + s->comm_log_off);
   }
   // ---- the timed region (vc_stats.commit_ms) starts here: the per-cycle resets and working copies are work
   //      every cycle does, so they are inside it ----
@@ -1547,6 +1548,7 @@ int vc_allocate_run(vc_snapshot *s, vc_result **out) {
   if (s->world <= 1) {  // with several ranks vc_comm_prepare cleared the exported slab before the ranks' barrier
     CUDA_TRY(cudaMemsetAsync(s->ring, 0, ring_bytes, s->stream));
     CUDA_TRY(cudaMemsetAsync(s->mbox, 0, mbox_bytes, s->stream));
+    if (s->fast) CUDA_TRY(cudaMemsetAsync(s->d_score_log, 0, (T + 64) * sizeof(uint4), s->stream));
   }
   CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 16 * 4, s->stream));
   // working copies of the mutable node state (the uploaded snapshot stays intact for re-runs / K1)
