@@ -63,3 +63,61 @@ def test_graft_entry_build_is_consistent():
     """build() is what the driver runs on CPU every round: it must agree with the header's ABI version."""
     import __graft_entry__ as g
     g.build()
+
+
+def _header_structs():
+    """typedef struct vc_x { ... } vc_x; -> {name: [field, ...]} parsed from include/vcalloc.h (comments stripped)."""
+    hdr = open(os.path.join(ROOT, "include", "vcalloc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    out = {}
+    for m in re.finditer(r"typedef\s+struct\s+(\w+)\s*\{(.*?)\}\s*(\w+)\s*;", hdr, flags=re.S):
+        name, body = m.group(3), m.group(2)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            # "const double *a, *b" / "int32_t x[16]" / "vc_plugin_option plugins[VC_MAX_PLUGINS]"
+            decl = re.sub(r"^(const\s+)?(struct\s+)?\w+\s+", "", decl, count=1)
+            for d in decl.split(","):
+                d = d.strip().lstrip("*").strip()
+                d = re.sub(r"^const\s+", "", d)
+                d = re.sub(r"\[.*\]$", "", d).strip().lstrip("*").strip()
+                if d:
+                    fields.append(d)
+        out[name] = fields
+    return out
+
+
+def test_ctypes_mirror_matches_the_header_field_by_field(tmp_path):
+    """Every struct of include/vcalloc.h: size and the offset of every field as gcc lays them out vs the ctypes mirror in
+    volcano_b200/abi.py (the layouts are written twice by hand; this is the check that they agree)."""
+    import shutil
+    import subprocess
+    from volcano_b200 import abi
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    structs = _header_structs()
+    assert {"vc_dims", "vc_nodes", "vc_tasks", "vc_jobs", "vc_queues", "vc_classes", "vc_conf", "vc_decision", "vc_visit",
+            "vc_stats", "vc_hypernodes", "vc_running_tasks"} <= set(structs), sorted(structs)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vcalloc.h"', "int main(void) {"]
+    for name, fields in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for f in fields:
+            lines.append(f'  printf("{name}.{f} %zu\\n", offsetof({name}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    checked = 0
+    for name, fields in structs.items():
+        mirror = getattr(abi, name, None)
+        assert mirror is not None, f"abi.py lacks {name}"
+        assert C.sizeof(mirror) == int(got[name]), (name, C.sizeof(mirror), got[name])
+        assert [f for f, _ in mirror._fields_] == fields, (name, [f for f, _ in mirror._fields_], fields)
+        for f in fields:
+            assert getattr(mirror, f).offset == int(got[f"{name}.{f}"]), (name, f)
+            checked += 1
+    assert checked >= 140
