@@ -337,7 +337,10 @@ def multi_gpu_arm(args, rank, world, local):
                     "note": "the snapshot is uploaded to every rank (h2d counts all of them); decisions come back from rank 0"},
             "gpu_launches": 2 * args.steps * world,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "sharded": dense},
+            "roofline": {"bound": "hbm", "kernel": "K1 node-sharded over the ranks (wall clock incl. its two NCCL collectives)",
+                         "achieved": (dense or {}).get("achieved_gbs_all_gpus"),
+                         "peak": ((dense or {}).get("peak_per_gpu") or 0) * world or None, "unit": "GB/s",
+                         "frac": (dense or {}).get("frac_of_n_times_peak"), "traffic": None, "sharded": dense},
             "cpu_baseline": None,
             "commit_kernel": {"kernel": "k_commit_fast, one persistent kernel per GPU, node axis cut over all their CTAs",
                               "bound": "latency (one NVLink round trip whenever the winning node moves to another GPU)",
