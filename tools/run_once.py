@@ -9,6 +9,8 @@ from volcano_b200.synth import make_snapshot  # noqa: E402
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 mode = sys.argv[2] if len(sys.argv) > 2 else "allocate"
 snap = make_snapshot(cfg)
+if os.environ.get("SAMP"):  # feasible-node sampling (0 = the reference's adaptive default)
+    snap.conf.percentage_nodes_to_find = int(os.environ["SAMP"]) if os.environ["SAMP"].isdigit() else 0
 e = engine.Engine(snap)
 e.upload()
 if mode == "dense":
