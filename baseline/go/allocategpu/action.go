@@ -286,6 +286,9 @@ type Action struct{}
 func New() *Action             { return &Action{} }
 func (a *Action) Name() string { return "allocate" }
 func (a *Action) Initialize() {
+	if C.vc_abi_version() != C.VC_ABI_VERSION {
+		panic("libvcalloc.so does not match the vcalloc.h this shim was compiled against")
+	}
 	if rc := C.vc_init(0); rc != 0 {
 		panic(C.GoString(C.vc_last_error())) // no CUDA device: the library has no CPU path
 	}
