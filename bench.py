@@ -189,7 +189,7 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     from volcano_b200.synth import make_snapshot
-    snap = make_snapshot(WORKLOAD)
+    snap = make_snapshot(args.workload)
     threads = max(1, min(16, cpu_cores()))
     for _ in range(args.warmup if args.warmup < 2 else 1):  # warm-up is a CPU cache matter only; one pass
         run_oracle(snap, threads)
@@ -205,7 +205,7 @@ def reference_arm(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong" if max(world, args.gpus) > 1 else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": config_dict(WORKLOAD, max(world, args.gpus)),
+        "config": config_dict(args.workload, max(world, args.gpus)),
         "cpu_baseline": {"value": val, "unit": "pods/s", "cores": threads, "kind": "port",
                          "sample": "full workload, one allocate cycle per step"},
         "e2e": {"value": val, "unit": "pods/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
