@@ -469,3 +469,12 @@ def test_nominated_node_resets_the_rotating_index(oracle_engine):
     assert names["c1/p0"] == "n2"       # the nominated node
     assert names["c1/p1"] == "n0"       # scanned from index 0 after the reset, first feasible node
     assert last == 1
+
+
+@pytest.mark.parametrize("enable,case", G.priority_preempt_cases(), ids=lambda c: getattr(c, "Name", str(c))[:50])
+def test_priority_plugin_preempt_goldens(enable, case, oracle_engine):
+    """plugins/priority/priority_test.go:62-165 TestPreempt: allocate then preempt with the priority plugin alone - the
+    victim on the shared node is the pod of lower task priority; with EnabledPreemptable false nothing is evicted."""
+    case.RegisterSession(G.priority_preempt_tiers(enable), actions=("allocate", "preempt"))
+    case.Run(oracle_engine)
+    assert case.CheckAll() is None, case.CheckAll()
