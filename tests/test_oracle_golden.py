@@ -478,3 +478,25 @@ def test_priority_plugin_preempt_goldens(enable, case, oracle_engine):
     case.RegisterSession(G.priority_preempt_tiers(enable), actions=("allocate", "preempt"))
     case.Run(oracle_engine)
     assert case.CheckAll() is None, case.CheckAll()
+
+
+def test_conformance_plugin_golden():
+    """plugins/conformance/conformance_test.go:32-92 TestConformancePlugin: of the preemptees kube-system/test-pod and
+    test-namespace/test-pod only the second is a possible victim (conformance.go:48-63: critical priority classes and the
+    kube-system namespace are never evicted). The session encoder carries that as VC_RT_CRITICAL per running task, which is
+    all the conformance vote reads (device: ev_may_be_victim, host: EvictSession, oracle: tier_victims)."""
+    from volcano_b200 import abi
+    from volcano_b200.api import BuildNode, BuildPod, BuildPodGroup, BuildQueue, BuildResourceList
+    from volcano_b200.snapshot import PluginOption
+    from volcano_b200.uthelper import TestCommonStruct
+    R1 = BuildResourceList("1", "1Gi")
+    pods = [BuildPod("kube-system", "test-pod", "test-node", "Running", R1, "pg1"),
+            BuildPod("test-namespace", "test-pod", "test-node", "Running", R1, "pg2"),
+            BuildPod("test-namespace", "crit", "test-node", "Running", R1, "pg2")]
+    pods[2].priority_class_name = "system-node-critical"
+    tc = TestCommonStruct(Name="conformance plugin", Nodes=[BuildNode("test-node", BuildResourceList("8", "8Gi", ("pods", "10")))],
+                          Pods=pods, Queues=[BuildQueue("q1", 1, None)],
+                          PodGroups=[BuildPodGroup("pg1", "kube-system", "q1", 1), BuildPodGroup("pg2", "test-namespace", "q1", 1)])
+    snap = tc.RegisterSession([[PluginOption.make("conformance", EnabledPreemptable=True)]], actions=("preempt",))
+    crit = {snap.running_task_keys[r]: bool(snap.rt_flags[r] & abi.VC_RT_CRITICAL) for r in range(snap.RT)}
+    assert crit == {"kube-system/test-pod": True, "test-namespace/test-pod": False, "test-namespace/crit": True}
